@@ -1,0 +1,170 @@
+/* subzero_b200.h -- C ABI of the B200 contact-force step.
+ *
+ * One call per timestep replaces the range floe_interactions_all.m:9-265 of the reference
+ * (ghost floes, broad phase, pair loop over collisions/floe_interactions.m, mirror, torque,
+ * per-floe sums, periodic wrap) plus the stress rows of calc_trajectory.m:9-13 and
+ * calc_collisionNum.m:3-6.  It takes the place of the >= 3 calls per contacting pair that the
+ * reference makes through its mex gateway  private/mexclipper.cpp:83 (mexFunction; boolean branch
+ * :204-305), reached from polyclip.m:73.
+ *
+ * Conventions (modelled on the reference gateway, private/mexclipper.cpp):
+ *   - plain pointers and sizes only; the caller owns every buffer it passes in or receives into
+ *     (cf. :54-61 inputs copied, :65-81 outputs caller-visible arrays);
+ *   - no exceptions cross the ABI; every entry point returns 0 or a negative SzStatus, and
+ *     sz_last_error() returns the message (the gateway's mexErrMsgTxt strings, e.g. :304);
+ *   - a context owns device buffers and streams; one host thread per context (the gateway is
+ *     stateless per call, :294; here state is only a cache of allocations);
+ *   - floe indices in outputs are 1-BASED positions in the extended floe list (originals, then
+ *     x-ghosts, then y-ghosts), exactly the numbers the reference stores in
+ *     Floe(i).interactions(:,1); the wall partner is +Inf (floe_interactions_all.m:167).
+ *
+ * There is no CPU fallback: every compute entry point fails with SZ_ERR_CUDA when no sm_100a
+ * device is usable.
+ */
+#ifndef SUBZERO_B200_H
+#define SUBZERO_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum SzStatus {
+    SZ_OK = 0,
+    SZ_ERR_ARG = -1,        /* bad argument (gateway: type/shape checks, mexclipper.cpp:22-41) */
+    SZ_ERR_CUDA = -2,       /* CUDA runtime error / no device */
+    SZ_ERR_CLIPPER = -3,    /* "Clipper Error." (mexclipper.cpp:303-304): the sweep failed for some pair */
+    SZ_ERR_CAPACITY = -4,   /* a pair exceeded the largest narrow-phase size class */
+    SZ_ERR_STATE = -5       /* results requested before a step was run */
+} SzStatus;
+
+/* Physics/configuration.  Defaults (sz_default_params) are the constants hard-coded in the
+ * reference; they are parameters here because the validation cases change them by editing the
+ * source (README.md:113,218,242). */
+typedef struct SzParams {
+    double Lx, Ly;            /* max(c2_boundary(1,:)), max(c2_boundary(2,:))   floe_interactions_all.m:9-10 */
+    double modulus;           /* global Modulus                                  floe_interactions_all.m:7   */
+    double dt;                /*                                                 floe_interactions.m:178     */
+    double nu;                /* 0.3   Poisson ratio                             floe_interactions.m:20      */
+    double mu;                /* 0.2   Coulomb friction                          floe_interactions.m:21      */
+    double merge_frac;        /* 0.55  overlap/area => +-Inf                     floe_interactions.m:55-58   */
+    double wall_frac;         /* 0.75  boundary overlap => Inf                   floe_interactions.m:37      */
+    double amin_per_vertex;   /* 100/1.75  Amin = min(N1,N2)*this                floe_interactions.m:79      */
+    double vertex_match_tol;  /* 1     dist<1                                    floe_interactions.m:99      */
+    double on_edge_tol;       /* 1e-8  abs(d)<1e-8                               floe_interactions.m:127     */
+    double dl_min;            /* 0.1   dl<0.1 => no force                        floe_interactions.m:141     */
+    double close_gap;         /* 1     norm(c(:,1)-c(:,end))>1 => close outline  floe_interactions.m:62-67   */
+    double big_floe_r;        /* 1e5   r>1e5 => min(h)/min(r)                    floe_interactions.m:15      */
+    double domain_area_frac;  /* 0.95                                            floe_interactions.m:54      */
+    int32_t Nb;               /* number of leading topography floes (never "i" of a pair, :76) */
+    int32_t periodic;         /* PERIODIC  */
+    int32_t collision;        /* COLLISION */
+    int32_t want_clip_polys;  /* 1: keep clip #1's int64 polygons per pair for bit-exact parity checks */
+} SzParams;
+
+/* The hot-path fields of the reference's Floe struct array (Initialize_Model/initialize_floe_values.m:12-52),
+ * flattened to structure-of-arrays.  Dead floes are dropped by the caller first
+ * (floe_interactions_all.m:12-13); `alive` is still honoured as in :101-103. */
+typedef struct SzFloesSoA {
+    int32_t n;                /* N0 */
+    int64_t nverts;           /* voff[n] */
+    const double* x;          /* Xi  */
+    const double* y;          /* Yi  */
+    const double* rmax;
+    const double* h;
+    const double* area;
+    const double* u;          /* Ui  */
+    const double* v;          /* Vi  */
+    const double* ksi;        /* ksi_ice */
+    const uint8_t* alive;
+    const int32_t* voff;      /* [n+1] offsets into vx/vy */
+    const double* vx;         /* c_alpha(1,:) -- outline about the centroid, CLOSED (first vertex repeated, :17) */
+    const double* vy;         /* c_alpha(2,:) */
+} SzFloesSoA;
+
+/* The boundary "floe" of the non-periodic wall call (floe_interactions_all.m:151, Subzero.m:68-70).
+ * x,y = holes(floebound.poly).Vertices as the MATLAB wrapper reads them (floe_interactions.m:31-32);
+ * box_x,box_y = c2_boundary (closed, 2x5) used for the bbox guard (:54) and the centroid test (:152). */
+typedef struct SzBoundary {
+    const double* x; const double* y; int32_t n;
+    const double* box_x; const double* box_y; int32_t box_n;
+    double area, h, xi, yi, u, v, ksi;
+} SzBoundary;
+
+typedef struct SzSummary {
+    int32_t n0;               /* input floes */
+    int32_t n;                /* extended list: originals + x-ghosts + y-ghosts */
+    int64_t n_pairs;          /* candidate pairs taken through the narrow phase */
+    int64_t n_pairs_force;    /* pairs that produced contact rows */
+    int64_t n_rows;           /* contact rows over all floes of the extended list (own + wall + mirrored) */
+    int64_t n_clip_paths;     /* debug polygons kept (want_clip_polys) */
+    int64_t n_clip_verts;
+    double  collision_count;  /* calc_collisionNum over the first n0 floes */
+    int32_t n_clipper_fail;   /* pairs whose sweep failed (reference would raise "Clipper Error.") */
+    int32_t n_capacity_fail;  /* pairs that exceeded the largest size class */
+    float   ms_device;        /* device time of the step (CUDA events), excluding host<->device copies */
+} SzSummary;
+
+typedef struct SzContext SzContext;
+
+/* ---- lifetime ---- */
+int  sz_create(SzContext** out, int device);            /* device = CUDA ordinal */
+void sz_destroy(SzContext* ctx);
+const char* sz_last_error(void);                        /* thread-local message of the last failure */
+void sz_default_params(SzParams* p);
+int  sz_abi_version(void);
+
+/* ---- one contact step, host buffers in (the mex / ctypes entry point) ---- */
+int sz_contact_step(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes,
+                    const SzBoundary* bnd /* may be NULL when periodic */, SzSummary* out);
+
+/* ---- split form for device-resident state: upload once, step many times ---- */
+int sz_upload(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes, const SzBoundary* bnd);
+int sz_step_resident(SzContext* ctx, SzSummary* out);
+
+/* ---- results of the last step (caller-allocated; sizes from SzSummary) ---- */
+/* per floe of the input list, each [n0] unless noted; any pointer may be NULL to skip */
+int sz_get_floe_outputs(SzContext* ctx,
+                        double* fx, double* fy, double* torque,   /* collision_force / collision_torque, ghosts folded in (:242-245,262-263) */
+                        double* overlap_area,                      /* OverlapArea */
+                        double* stress,                            /* [n0*4], row-major 2x2, calc_trajectory.m:12-13 (un-averaged) */
+                        double* xi, double* yi,                    /* centroid after the periodic wrap (:267-277) */
+                        uint8_t* alive,                            /* 0 where the centroid left a non-periodic domain (:152-155) */
+                        int32_t* kill, int32_t* transfer);         /* 1-based ids as in :138-145,175-179; 0 = none */
+/* ghost bookkeeping [n - n0]: parent = 1-based index in the extended list, floe_num = FloeNums (negative) */
+int sz_get_ghosts(SzContext* ctx, int32_t* parent, int32_t* floe_num, double* gx, double* gy);
+/* candidate pairs [n_pairs], 1-based (i<j), ascending (i,j) = the order of Floe(i).potentialInteractions;
+ * overlap_state: 0, +Inf or -Inf (floe_interactions.m:55-58); status: 0 ok, <0 SzStatus of that pair */
+int sz_get_pairs(SzContext* ctx, int32_t* pi, int32_t* pj, double* overlap_state, int32_t* n_regions, int32_t* status);
+/* contact rows in the reference's canonical order: row_off [n+1], rows [n_rows*7]
+ * = [partner Fx Fy Px Py torque overlap], exactly Floe(i).interactions */
+int sz_get_rows(SzContext* ctx, int64_t* row_off, double* rows);
+/* debug (want_clip_polys): clip #1 result of every pair as Clipper's int64 coordinates.
+ * pair_path_off [n_pairs+1] -> path_vert_off [n_clip_paths+1] -> x,y [n_clip_verts] */
+int sz_get_clip_polys(SzContext* ctx, int64_t* pair_path_off, int64_t* path_vert_off, int64_t* x, int64_t* y);
+
+/* ---- stand-alone polygon clip with the gateway's semantics (private/mexclipper.cpp:204-305):
+ * `count` independent (subject, clip) pairs, one closed path each, int64 coordinates, even-odd fill,
+ * method 0 dif / 1 int / 2 xor / 3 uni.  Runs the same device sweep as the narrow phase.
+ * Two-phase: call with out_x == NULL to obtain sizes. */
+int sz_clip_batch(SzContext* ctx, int32_t count, const int32_t* method,
+                  const int64_t* subj_off, const int64_t* sx, const int64_t* sy,
+                  const int64_t* clip_off, const int64_t* cx, const int64_t* cy,
+                  int32_t* status,            /* [count] 0 ok / SzStatus */
+                  int64_t* pair_path_off,     /* [count+1] */
+                  int64_t* path_vert_off,     /* [n_paths+1], may be NULL in the size query */
+                  int64_t* out_x, int64_t* out_y,
+                  int64_t* n_paths, int64_t* n_verts);
+
+/* ---- synthetic input of BASELINE.json configs[4]: periodic Voronoi floe field (host utility) ---- */
+typedef struct SzField SzField;   /* owns the SoA arrays */
+int  sz_field_voronoi(SzField** out, int32_t n_floes, uint64_t seed, double mean_area, double inflate,
+                      SzParams* prm_out /* Lx, Ly, modulus filled in */);
+int  sz_field_view(const SzField* f, SzFloesSoA* view);
+void sz_field_free(SzField* f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBZERO_B200_H */

@@ -1,0 +1,37 @@
+/* sz_oracle.h -- TEST INFRASTRUCTURE ONLY (see sz_oracle.cpp).  C interface of the CPU checker. */
+#ifndef SZ_ORACLE_H
+#define SZ_ORACLE_H
+#include <stdint.h>
+#include "../include/subzero_b200.h"   /* struct layouts only */
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct SzoResult SzoResult;
+/* broad_mode 0 = literal O(N^2) loop of floe_interactions_all.m:76-120; 1 = same predicate over a cell grid */
+SzoResult* szo_contact_step(const SzParams* prm, const SzFloesSoA* floes, const SzBoundary* bnd, int nthreads, int broad_mode);
+void szo_free(SzoResult* r);
+const char* szo_error(const SzoResult* r);
+void szo_summary(const SzoResult* r, SzSummary* s);
+void szo_get_floe_outputs(const SzoResult* r, double* fx, double* fy, double* torque, double* overlap_area, double* stress,
+                          double* xi, double* yi, uint8_t* alive, int32_t* kill, int32_t* transfer);
+void szo_get_ghosts(const SzoResult* r, int32_t* parent, int32_t* floe_num, double* gx, double* gy);
+void szo_get_pairs(const SzoResult* r, int32_t* pi, int32_t* pj, double* overlap_state, int32_t* n_regions, int32_t* status);
+void szo_get_rows(const SzoResult* r, int64_t* row_off, double* rows);
+void szo_get_clip_polys(const SzoResult* r, int64_t* pair_path_off, int64_t* path_vert_off, int64_t* x, int64_t* y);
+int  szo_polyclip(const double* x1, const double* y1, int n1, const double* x2, const double* y2, int n2, int method,
+                  double* ox, double* oy, int cap, int* off, int off_cap);
+void szo_polyshape_area_centroid(const double* x, const double* y, int n, double* out3);
+double szo_polyarea(const double* x, const double* y, int n);
+int  szo_interx(const double* x1, const double* y1, int n1, const double* x2, const double* y2, int n2, double* out, int cap);
+void szo_inpolygon(const double* px, const double* py, int np, const double* xv, const double* yv, int nv, uint8_t* in);
+int  szo_p_poly_dist(const double* px, const double* py, int np, const double* xv, const double* yv, int nv, double* d);
+int64_t szo_matlab_int64(double v);
+int  szo_floe_interactions(const SzParams* prm, const double* cax, const double* cay, int n1, const double* body1,
+                           const double* c2x, const double* c2y, int n2, const double* body2, int is_boundary,
+                           const double* boxx, const double* boxy, int nbox,
+                           double* rows_out, int rows_cap, double* overlap_state);
+int  szo_hardware_threads(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,421 @@
+// sz_pairforce.cuh -- the pair force law of collisions/floe_interactions.m for ONE (floe, partner)
+// or (floe, wall) pair, written for one CUDA thread per pair on top of the Clipper-exact sweep in
+// sz_clip.cuh.  Everything the reference does through MATLAB temporaries (cell arrays of regions,
+// dense InterX matrices, per-edge vectors of the general branch) is streamed through a
+// fixed-capacity workspace instead; floating-point operations are kept in the reference's order and
+// individually rounded (this translation unit is compiled with -fmad=false / -ffp-contract=off).
+//
+// Reference map (file:line of /root/reference):
+//   spring constants                floe_interactions.m:10-21      -> pair_force() head
+//   clip #1 (+ wall 0.75 test)      :25-41, polyclip.m:63-73       -> run_clip(), Workspace::ra*
+//   region areas, merge test        :43-60                          -> ring_area_centroid()
+//   InterX                          InterX.m:54-77                  -> interx()
+//   per-region contact + direction  :92-150                         -> region loop
+//   sign test (clips #2, #3..)      :151-165
+//   normal + tangential force       :167-187
+//   p_poly_dist / inpolygon         polygon_operations/p_poly_dist.m:111-288, inpolygon.m:150-224
+#pragma once
+#include "sz_clip.cuh"
+
+namespace szpf {
+
+using szclip::i64;
+using szclip::P64;
+
+#define SZ_INF (__builtin_huge_val())
+#define SZ_EPS 2.220446049250313e-16
+#define SZ_SCALE 4294967296.0
+
+struct Params {            // device copy of SzParams (include/subzero_b200.h)
+    double Lx, Ly, modulus, dt, nu, mu, merge_frac, wall_frac, amin_per_vertex, vertex_match_tol,
+           on_edge_tol, dl_min, close_gap, big_floe_r, domain_area_frac;
+    int Nb, periodic, collision;
+    // c2_boundary extent + area for the merge-test guard (floe_interactions.m:54); has_box = 0 when absent
+    double bxmin, bxmax, bymin, bymax, barea; int has_box;
+};
+
+struct Body { double h, area, Xi, Yi, Ui, Vi, ksi; };   // the fields of floe1 / floe2 the law reads
+
+enum PairStatus { PS_OK = 0, PS_CLIPPER_FAIL = -3 /* SZ_ERR_CLIPPER */, PS_CAPACITY = -4 /* SZ_ERR_CAPACITY */, PS_BAD_POLY = -1 /* SZ_ERR_ARG */ };
+
+struct PairResult {
+    int status;            // PairStatus
+    int n_rows;            // contact rows produced (0 when the pair exerts no force)
+    double overlap_state;  // 0, +Inf, -Inf  (floe_interactions.m:38,56,58)
+};
+
+// polyclip.m:66  int64(x*scale): round half away from zero, saturating, NaN -> 0
+SZ_HD i64 matlab_int64(double v)
+{
+    if (v != v) return 0;
+    if (v >= 9223372036854775807.0) return 0x7FFFFFFFFFFFFFFFLL;
+    if (v <= -9223372036854775808.0) return (i64)0x8000000000000000ULL;
+    double t = trunc(v), f = v - t;
+    i64 r = (i64)t;
+    if (f >= 0.5) r += 1; else if (f <= -0.5) r -= 1;
+    return r;
+}
+
+template <class ClipC, int NV_, int RV_, int RP_, int NP_, int ROWS_>
+struct PairCaps { typedef ClipC Clip; enum { NV = NV_, RV = RV_, RP = RP_, NP = NP_, ROWS = ROWS_ }; };
+
+template <class C>
+struct Workspace {
+    szclip::ClipEngine<typename C::Clip> eng;
+    double c1x[C::NV], c1y[C::NV], c2x[C::NV], c2y[C::NV];   // world outlines (closed); caller fills, n1/n2 points
+    int n1, n2;
+    i64 rax[C::RV], ray[C::RV]; int ra_off[C::RP + 1]; int ra_n;   // clip #1 regions, Clipper coordinates
+    double ar[C::RP];
+    i64 rbx[C::RV], rby[C::RV]; int rb_off[C::RP + 1]; int rb_n;   // clip #2 regions
+    double px[C::NP], py[C::NP]; int np;                          // InterX points
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class C>
+struct RegionSink {       // collects emitted paths into (x,y,off) pools; flags overflow
+    i64* x; i64* y; int* off; int n_paths, n_pts; bool overflow;
+    SZ_HD RegionSink(i64* x_, i64* y_, int* off_) : x(x_), y(y_), off(off_), n_paths(0), n_pts(0), overflow(false) { off[0] = 0; }
+    SZ_HD void begin_path(int cnt) { if (n_paths >= C::RP || n_pts + cnt > C::RV) overflow = true; else { ++n_paths; off[n_paths] = off[n_paths - 1]; } }
+    SZ_HD void point(P64 p) { if (overflow) return; x[n_pts] = p.x; y[n_pts] = p.y; ++n_pts; off[n_paths] = n_pts; }
+};
+struct CountSink { int n; SZ_HD void begin_path(int) { ++n; } SZ_HD void point(P64) {} };
+struct ShiftedOutline {   // [X1new' Y1new'] packed by polyclip.m:66
+    const double* x; const double* y; double dx, dy;
+    SZ_HD P64 operator()(int i) const { P64 p; p.x = matlab_int64((x[i] + dx) * SZ_SCALE); p.y = matlab_int64((y[i] + dy) * SZ_SCALE); return p; }
+};
+struct IntRing {          // a Clipper result fed back as input: int64(double(X)/2^32*2^32) == X for |X| < 2^53
+    const i64* x; const i64* y;
+    SZ_HD P64 operator()(int i) const
+    {
+        P64 p;
+        p.x = matlab_int64(((double)x[i] / SZ_SCALE) * SZ_SCALE);
+        p.y = matlab_int64(((double)y[i] / SZ_SCALE) * SZ_SCALE);
+        return p;
+    }
+};
+
+// one polyclip() call: returns PS_OK / error; paths land in (ox,oy,ooff,*on)
+template <class C, class GS, class GC>
+SZ_HD int run_clip(Workspace<C>& w, int method, const GS& subj, int ns, const GC& clip, int nc, i64* ox, i64* oy, int* ooff, int* on)
+{
+    w.eng.begin(method);
+    w.eng.add_path(subj, ns, 0);
+    w.eng.add_path(clip, nc, 1);
+    int st = w.eng.execute();
+    if (st == szclip::ST_OVERFLOW) return PS_CAPACITY;
+    if (st != szclip::ST_OK) return PS_CLIPPER_FAIL;
+    RegionSink<C> sink(ox, oy, ooff);
+    w.eng.emit(sink);
+    if (sink.overflow) return PS_CAPACITY;
+    *on = sink.n_paths;
+    return PS_OK;
+}
+
+// area(polyshape) / centroid(polyshape): shoelace relative to vertex 0 (pinned by FloeShapes.mat)
+SZ_HD void ring_area_centroid(const i64* X, const i64* Y, int n, double& area, double& cx, double& cy)
+{
+    if (n < 3) { area = 0; cx = cy = SZ_INF - SZ_INF; return; }
+    const double x0 = (double)X[0] / SZ_SCALE, y0 = (double)Y[0] / SZ_SCALE;
+    double a2 = 0, sx = 0, sy = 0;
+    double xi = 0, yi = 0;
+    for (int i = 0; i < n; ++i) {
+        int j = (i + 1 == n) ? 0 : i + 1;
+        double xj = (double)X[j] / SZ_SCALE - x0, yj = (double)Y[j] / SZ_SCALE - y0;
+        double c = xi * yj - xj * yi;
+        a2 += c; sx += (xi + xj) * c; sy += (yi + yj) * c;
+        xi = xj; yi = yj;
+    }
+    area = fabs(a2) / 2;
+    cx = x0 + sx / (3 * a2);
+    cy = y0 + sy / (3 * a2);
+}
+// polyarea(): abs(sum((x([2:end 1])-x).*(y([2:end 1])+y))/2), untranslated
+SZ_HD double ring_polyarea(const i64* X, const i64* Y, int n)
+{
+    double s = 0;
+    for (int i = 0; i < n; ++i) {
+        int j = (i + 1 == n) ? 0 : i + 1;
+        double xi = (double)X[i] / SZ_SCALE, yi = (double)Y[i] / SZ_SCALE, xj = (double)X[j] / SZ_SCALE, yj = (double)Y[j] / SZ_SCALE;
+        s += (xj - xi) * (yj + yi);
+    }
+    return fabs(s / 2);
+}
+
+// InterX.m:54-77 (two-curve form).  Points are collected, sorted (x, then y) and de-duplicated.
+template <class C>
+SZ_HD bool interx(Workspace<C>& w)
+{
+    const int n1 = w.n1 - 1, n2 = w.n2 - 1;
+    int np = 0;
+    for (int j = 0; j < n2; ++j) {
+        const double x2a = w.c2x[j], y2a = w.c2y[j], x2b = w.c2x[j + 1], y2b = w.c2y[j + 1];
+        const double dx2 = x2b - x2a, dy2 = y2b - y2a;
+        const double S2 = dx2 * y2a - dy2 * x2a;
+        for (int i = 0; i < n1; ++i) {
+            const double x1a = w.c1x[i], y1a = w.c1y[i], x1b = w.c1x[i + 1], y1b = w.c1y[i + 1];
+            const double dx1 = x1b - x1a, dy1 = y1b - y1a;
+            const double S1 = dx1 * y1a - dy1 * x1a;
+            const double a0 = dx1 * y2a - dy1 * x2a, a1 = dx1 * y2b - dy1 * x2b;
+            if (!(((a0 - S1) * (a1 - S1)) <= 0)) continue;
+            const double b0 = y1a * dx2 - x1a * dy2, b1 = y1b * dx2 - x1b * dy2;
+            if (!(((b0 - S2) * (b1 - S2)) <= 0)) continue;
+            const double L = dy2 * dx1 - dy1 * dx2;
+            if (L == 0) continue;
+            if (np >= C::NP) return false;
+            w.px[np] = (dx2 * S1 - dx1 * S2) / L;
+            w.py[np] = (dy2 * S1 - dy1 * S2) / L;
+            ++np;
+        }
+    }
+    // unique(...,'rows')
+    for (int i = 1; i < np; ++i) {
+        double vx = w.px[i], vy = w.py[i]; int k = i - 1;
+        while (k >= 0 && (w.px[k] > vx || (w.px[k] == vx && w.py[k] > vy))) { w.px[k + 1] = w.px[k]; w.py[k + 1] = w.py[k]; --k; }
+        w.px[k + 1] = vx; w.py[k + 1] = vy;
+    }
+    int m = 0;
+    for (int i = 0; i < np; ++i) if (m == 0 || !(w.px[i] == w.px[m - 1] && w.py[i] == w.py[m - 1])) { w.px[m] = w.px[i]; w.py[m] = w.py[i]; ++m; }
+    w.np = m;
+    return true;
+}
+
+// inpolygon.m:150-224 for a single query point against the closed ring [X;X(1)] of a region
+SZ_HD bool in_region(double x, double y, const i64* X, const i64* Y, int n, double xmin, double xmax, double ymin, double ymax)
+{
+    if (!(x >= xmin && x <= xmax && y >= ymin && y <= ymax)) return false;
+    double sumdq = 0; bool on = false;
+    double ax = (double)X[0] / SZ_SCALE, ay = (double)Y[0] / SZ_SCALE;
+    double vx0 = ax - x, vy0 = ay - y;
+    bool px0 = vx0 > 0, py0 = vy0 > 0;
+    double q0 = (double)((!px0 && py0) + 2 * (!px0 && !py0) + 3 * (px0 && !py0));
+    for (int m = 0; m < n; ++m) {
+        int j = (m + 1 == n) ? 0 : m + 1;
+        double bx = (double)X[j] / SZ_SCALE, by = (double)Y[j] / SZ_SCALE;
+        double avx = fabs(0.5 * (ax + bx)), avy = fabs(0.5 * (ay + by));
+        double sf = avx > avy ? avx : avy; double pr = avx * avy; if (pr > sf) sf = pr;
+        double seps = sf * SZ_EPS * 3;
+        double vx1 = bx - x, vy1 = by - y;
+        bool px1 = vx1 > 0, py1 = vy1 > 0;
+        double q1 = (double)((!px1 && py1) + 2 * (!px1 && !py1) + 3 * (px1 && !py1));
+        double cross = vx0 * vy1 - vx1 * vy0;
+        double sgn = (double)((cross > 0) - (cross < 0));
+        if (fabs(cross) < seps) sgn = 0;
+        double dot = vx0 * vx1 + vy0 * vy1;
+        double dq = q1 - q0;
+        if (fabs(dq) == 3) dq = -dq / 3; else if (fabs(dq) == 2) dq = 2 * sgn;
+        sumdq += dq;
+        if (sgn == 0 && dot <= 0) on = true;
+        ax = bx; ay = by; vx0 = vx1; vy0 = vy1; q0 = q1;
+    }
+    return (sumdq != 0) || on;
+}
+
+// |p_poly_dist(x,y, c1)|: unsigned distance from one point to the closed outline c1 (n1 points,
+// first == last).  Returns <0 when the reference would raise (repeated vertices / flat polygon).
+template <class C>
+SZ_HD double abs_poly_dist(const Workspace<C>& w, double xq, double yq)
+{
+    const int nv = w.n1, ns = nv - 1;
+    double dpv_min = SZ_INF; int i_dpv = 0;
+    for (int k = 0; k < nv; ++k) {
+        double d = hypot(w.c1x[k] - xq, w.c1y[k] - yq);
+        if (fabs(d) < dpv_min) { dpv_min = fabs(d); i_dpv = k; }
+    }
+    double cr_min = 0; int i_cr = 0; bool have = false;
+    for (int k = 0; k < ns; ++k) {
+        double dvx = w.c1x[k + 1] - w.c1x[k], dvy = w.c1y[k + 1] - w.c1y[k];
+        double vds = hypot(dvx, dvy);
+        double ct = dvx / vds, st = dvy / vds;
+        double p1rx = ct * w.c1x[k] + st * w.c1y[k];
+        double p1ry = -st * w.c1x[k] + ct * w.c1y[k];
+        double r = (xq * ct + yq * st) - p1rx;
+        double cr = (xq * (-st) + yq * ct) - p1ry;
+        if (r > 0 && r < vds) { double a = fabs(cr); if (!have || a < cr_min) { cr_min = a; i_cr = k; have = true; } }
+    }
+    bool is_vertex = !have || ((i_cr != i_dpv) && (cr_min - dpv_min) > 0);
+    return is_vertex ? dpv_min : cr_min;
+}
+template <class C>
+SZ_HD bool outline_ok_for_poly_dist(const Workspace<C>& w)   // p_poly_dist.m:166-179
+{
+    const int ns = w.n1 - 1;
+    if (w.n1 < 3) return false;
+    double s = 0, last = 0;
+    for (int k = 0; k < ns; ++k) {
+        double vds = hypot(w.c1x[k + 1] - w.c1x[k], w.c1y[k + 1] - w.c1y[k]);
+        if (vds < 10 * SZ_EPS) return false;
+        if (k + 1 < ns) s += vds; else last = vds;
+    }
+    return !((s - last) < 10 * SZ_EPS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The force law.  On entry w.c1*/w.c2* hold the two world outlines exactly as the reference builds
+// them (floe_interactions.m:25, floe_interactions_all.m:105; for the wall c2 = hole vertices).
+// rows[r*5 + {0..4}] = Fx, Fy, Px, Py, overlap  for r < res.n_rows.
+template <class C>
+SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows)
+{
+    res.status = PS_OK; res.n_rows = 0; res.overlap_state = 0;
+    double h1 = f1.h; const double h2 = f2.h;
+    double r1 = sqrt(f1.area); const double r2 = sqrt(f2.area);
+    double force_factor = P.modulus * (h1 * h2) / (h1 * r2 + h2 * r1);
+    double overlap = 0;
+    if (boundary) force_factor = P.modulus * h1 / r1;
+    else if (r1 > P.big_floe_r || r2 > P.big_floe_r) {
+        r1 = r1 < r2 ? r1 : r2; h1 = h1 < h2 ? h1 : h2;
+        force_factor = P.modulus * h1 / r1;
+    }
+    const double G = P.modulus / (2 * (1 + P.nu)), mu = P.mu;
+    const int method = boundary ? 0 : 1;
+
+    // clip #1
+    {
+        ShiftedOutline s1{w.c1x, w.c1y, 0.0, 0.0}, s2{w.c2x, w.c2y, 0.0, 0.0};
+        int st = run_clip(w, method, s1, w.n1, s2, w.n2, w.rax, w.ray, w.ra_off, &w.ra_n);
+        if (st != PS_OK) { res.status = st; return; }
+    }
+    if (boundary && w.ra_n > 0) {
+        if (ring_polyarea(w.rax, w.ray, w.ra_off[1]) / f1.area > P.wall_frac) overlap = SZ_INF;
+    }
+    double sum_ar = 0;
+    for (int k = 0; k < w.ra_n; ++k) {
+        double a, cx, cy;
+        ring_area_centroid(w.rax + w.ra_off[k], w.ray + w.ra_off[k], w.ra_off[k + 1] - w.ra_off[k], a, cx, cy);
+        w.ar[k] = a; sum_ar += a;
+    }
+    {   // merge test (:54-60)
+        bool guard = P.periodic != 0;
+        if (!guard && P.has_box) {
+            double xmx = w.c1x[0], xmn = w.c1x[0], ymx = w.c1y[0], ymn = w.c1y[0];
+            for (int i = 1; i < w.n1; ++i) {
+                if (w.c1x[i] > xmx) xmx = w.c1x[i]; if (w.c1x[i] < xmn) xmn = w.c1x[i];
+                if (w.c1y[i] > ymx) ymx = w.c1y[i]; if (w.c1y[i] < ymn) ymn = w.c1y[i];
+            }
+            guard = (xmx < P.bxmax && xmn > P.bxmin && ymx < P.bymax && ymn > P.bymin) || f2.area < P.domain_area_frac * P.barea;
+        }
+        if (guard) {
+            if (sum_ar / f1.area > P.merge_frac) overlap = SZ_INF;
+            else if (sum_ar / f2.area > P.merge_frac) overlap = -SZ_INF;
+        }
+    }
+    // close the outlines when their ends are more than close_gap apart (:62-67); capacity reserved by the caller
+    {
+        double gx = w.c1x[0] - w.c1x[w.n1 - 1], gy = w.c1y[0] - w.c1y[w.n1 - 1];
+        if (sqrt(gx * gx + gy * gy) > P.close_gap) { w.c1x[w.n1] = w.c1x[0]; w.c1y[w.n1] = w.c1y[0]; ++w.n1; }
+        gx = w.c2x[0] - w.c2x[w.n2 - 1]; gy = w.c2y[0] - w.c2y[w.n2 - 1];
+        if (sqrt(gx * gx + gy * gy) > P.close_gap) { w.c2x[w.n2] = w.c2x[0]; w.c2y[w.n2] = w.c2y[0]; ++w.n2; }
+    }
+    if (!interx(w)) { res.status = PS_CAPACITY; return; }
+    res.overlap_state = overlap;
+    if (w.np < 2 || overlap == SZ_INF || overlap == -SZ_INF || w.ra_n == 0) return;   // :71-74 zero force
+    res.overlap_state = 0;
+
+    const int N1 = w.n1 - 1, N2 = w.n2 - 1;
+    const double amin = (double)(N1 < N2 ? N1 : N2) * P.amin_per_vertex;
+    int n_rows = 0;
+    bool outline_checked = false, outline_ok = true;
+    for (int k = 0; k < w.ra_n; ++k) {
+        if (w.ar[k] < amin) continue;                                   // :83
+        if (n_rows >= C::ROWS) { res.status = PS_CAPACITY; return; }
+        const i64* RX = w.rax + w.ra_off[k]; const i64* RY = w.ray + w.ra_off[k];
+        const int nr = w.ra_off[k + 1] - w.ra_off[k];
+        const double Ak = w.ar[k];
+        double a_unused, cx, cy;
+        ring_area_centroid(RX, RY, nr, a_unused, cx, cy);
+        // dsearchn + dist<1 (:98-100)
+        int m = 0; double p0x = 0, p0y = 0, p1x = 0, p1y = 0;
+        for (int q = 0; q < w.np; ++q) {
+            double best = SZ_INF; int bi = 0;
+            for (int v = 0; v < nr; ++v) {
+                double dx = (double)RX[v] / SZ_SCALE - w.px[q], dy = (double)RY[v] / SZ_SCALE - w.py[q];
+                double d2 = dx * dx + dy * dy;
+                if (d2 < best) { best = d2; bi = v; }
+            }
+            if (sqrt(best) < P.vertex_match_tol) {
+                if (m == 0) { p0x = (double)RX[bi] / SZ_SCALE; p0y = (double)RY[bi] / SZ_SCALE; }
+                else if (m == 1) { p1x = (double)RX[bi] / SZ_SCALE; p1y = (double)RY[bi] / SZ_SCALE; }
+                ++m;
+            }
+        }
+        double fdx = 0, fdy = 0, dl = 0, pcx = cx, pcy = cy;
+        if (Ak == 0) { pcx = 0; pcy = 0; }
+        else if (m == 2) {
+            double xgh = p1x - p0x, ygh = p1y - p0y;
+            double b = sqrt(xgh * xgh + ygh * ygh);
+            fdx = -ygh / b; fdy = xgh / b; dl = b;
+        } else if (m != 0) {
+            // general branch (:117-137), streamed edge by edge
+            if (!outline_checked) { outline_ok = outline_ok_for_poly_dist(w); outline_checked = true; }
+            if (!outline_ok) { res.status = PS_BAD_POLY; return; }
+            double xmin = SZ_INF, xmax = -SZ_INF, ymin = SZ_INF, ymax = -SZ_INF;
+            for (int v = 0; v < nr; ++v) {
+                double x = (double)RX[v] / SZ_SCALE, y = (double)RY[v] / SZ_SCALE;
+                if (x < xmin) xmin = x; if (x > xmax) xmax = x; if (y < ymin) ymin = y; if (y > ymax) ymax = y;
+            }
+            double sx = 0, sy = 0, sb = 0; int non = 0;
+            for (int e = 0; e < nr; ++e) {
+                int e1 = (e + 1 == nr) ? 0 : e + 1;
+                double xa = (double)RX[e] / SZ_SCALE, ya = (double)RY[e] / SZ_SCALE, xb = (double)RX[e1] / SZ_SCALE, yb = (double)RY[e1] / SZ_SCALE;
+                double xgh = xb - xa, ygh = yb - ya, xm = (xb + xa) / 2, ym = (yb + ya) / 2;
+                double b = sqrt(xgh * xgh + ygh * ygh);
+                double nx = -ygh / b, ny = xgh / b;
+                double xt = xm + nx / 100, yt = ym + ny / 100;
+                if (!in_region(xt, yt, RX, RY, nr, xmin, xmax, ymin, ymax)) { nx = -nx; ny = -ny; }
+                double d = abs_poly_dist(w, xm, ym);
+                if (d < P.on_edge_tol) {
+                    sx += (-force_factor * b) * nx; sy += (-force_factor * b) * ny; sb += b; ++non;
+                }
+            }
+            if (non < nr && non > 0) {
+                double nrm = sqrt(sx * sx + sy * sy);
+                fdx = sx / nrm; fdy = sy / nrm; dl = sb / (double)non;
+            }
+        }
+        if (dl < P.dl_min) { fdx = 0; fdy = 0; }
+        // sign test (:151-165)
+        {
+            ShiftedOutline s1{w.c1x, w.c1y, fdx, fdy}, s2{w.c2x, w.c2y, 0.0, 0.0};
+            int st = run_clip(w, method, s1, w.n1, s2, w.n2, w.rbx, w.rby, w.rb_off, &w.rb_n);
+            if (st != PS_OK) { res.status = st; return; }
+            for (int ii = 0; ii < w.rb_n; ++ii) {
+                IntRing a{w.rbx + w.rb_off[ii], w.rby + w.rb_off[ii]}, b{RX, RY};
+                // clip #3 only needs "empty or not": run the sweep and look for an output path
+                w.eng.begin(1);
+                w.eng.add_path(a, w.rb_off[ii + 1] - w.rb_off[ii], 0);
+                w.eng.add_path(b, nr, 1);
+                int st3 = w.eng.execute();
+                if (st3 == szclip::ST_OVERFLOW) { res.status = PS_CAPACITY; return; }
+                if (st3 != szclip::ST_OK) { res.status = PS_CLIPPER_FAIL; return; }
+                CountSink cs; cs.n = 0;
+                w.eng.emit(cs);
+                if (cs.n > 0) {
+                    double anew = ring_polyarea(w.rbx + w.rb_off[ii], w.rby + w.rb_off[ii], w.rb_off[ii + 1] - w.rb_off[ii]);
+                    if (anew / Ak - 1 > 0) { fdx = -fdx; fdy = -fdy; }
+                }
+            }
+        }
+        const double fx = fdx * Ak * force_factor, fy = fdy * Ak * force_factor;
+        // tangential (:170-183)
+        const double v1x = f1.Ui + f1.ksi * (pcx - f1.Xi), v1y = f1.Vi + f1.ksi * (pcy - f1.Yi);
+        const double v2x = f2.Ui + f2.ksi * (pcx - f2.Xi), v2y = f2.Vi + f2.ksi * (pcy - f2.Yi);
+        const double vtx = v1x - v2x, vty = v1y - v2y;
+        const double vn = sqrt(vtx * vtx + vty * vty);
+        double dtx = 0, dty = 0;
+        if (!((fabs(vtx) > fabs(vty) ? fabs(vtx) : fabs(vty)) == 0)) { dtx = vtx / vn; dty = vty / vn; }
+        const double dotv = dtx * vtx + dty * vty;
+        const double coef = -dotv * dl * G * vn;
+        double ftx = coef * dtx * P.dt, fty = coef * dty * P.dt;
+        const double fnorm = sqrt(fx * fx + fy * fy);
+        if (sqrt(ftx * ftx + fty * fty) > mu * fnorm) { ftx = -mu * fnorm * dtx; fty = -mu * fnorm * dty; }
+        double* r = rows + (size_t)n_rows * 5;
+        r[0] = fx + ftx; r[1] = fy + fty; r[2] = pcx; r[3] = pcy; r[4] = Ak;
+        ++n_rows;
+    }
+    // caller rule (floe_interactions_all.m:135): rows are kept only when some force component is non-zero
+    double sabs = 0;
+    for (int r = 0; r < n_rows; ++r) sabs += fabs(rows[r * 5]) + fabs(rows[r * 5 + 1]);
+    res.n_rows = (sabs != 0) ? n_rows : 0;
+}
+
+}  // namespace szpf

@@ -1,0 +1,59 @@
+// Host build of the product's pair force law (subzero_b200/csrc/sz_pairforce.cuh) for CPU-side
+// parity tests against the oracle (test infrastructure; the product never runs this on the CPU).
+#include "../../subzero_b200/csrc/sz_pairforce.cuh"
+#include "../../include/subzero_b200.h"
+#include <vector>
+#include <memory>
+
+using namespace szpf;
+typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3000> BigClip;
+typedef PairCaps<BigClip, 1300, 5200, 64, 6000, 32> BigPair;
+typedef szclip::ClipCaps<32, 16, 96, 32, 64, 32, 16, 48> SmallClip;
+typedef PairCaps<SmallClip, 20, 64, 6, 40, 4> SmallPair;
+
+static void fill_params(const SzParams* p, const double* boxx, const double* boxy, int nbox, Params& P)
+{
+    P.Lx = p->Lx; P.Ly = p->Ly; P.modulus = p->modulus; P.dt = p->dt; P.nu = p->nu; P.mu = p->mu; P.merge_frac = p->merge_frac;
+    P.wall_frac = p->wall_frac; P.amin_per_vertex = p->amin_per_vertex; P.vertex_match_tol = p->vertex_match_tol;
+    P.on_edge_tol = p->on_edge_tol; P.dl_min = p->dl_min; P.close_gap = p->close_gap; P.big_floe_r = p->big_floe_r;
+    P.domain_area_frac = p->domain_area_frac; P.Nb = p->Nb; P.periodic = p->periodic; P.collision = p->collision;
+    P.has_box = nbox > 0;
+    if (nbox > 0) {
+        P.bxmin = P.bxmax = boxx[0]; P.bymin = P.bymax = boxy[0];
+        for (int i = 1; i < nbox; ++i) { if (boxx[i] < P.bxmin) P.bxmin = boxx[i]; if (boxx[i] > P.bxmax) P.bxmax = boxx[i]; if (boxy[i] < P.bymin) P.bymin = boxy[i]; if (boxy[i] > P.bymax) P.bymax = boxy[i]; }
+        // area(polyshape(c2_boundary')) with the same vertex-0-relative shoelace
+        double a2 = 0; for (int i = 0; i < nbox; ++i) { int j = (i + 1) % nbox; double xi = boxx[i] - boxx[0], yi = boxy[i] - boxy[0], xj = boxx[j] - boxx[0], yj = boxy[j] - boxy[0]; a2 += xi * yj - xj * yi; }
+        P.barea = fabs(a2) / 2;
+    } else { P.bxmin = P.bxmax = P.bymin = P.bymax = P.barea = 0; }
+}
+
+template <class CAPS>
+static int run(const SzParams* prm, const double* cax, const double* cay, int n1, const double* body1,
+               const double* c2x, const double* c2y, int n2, const double* body2, int is_boundary,
+               const double* boxx, const double* boxy, int nbox, double* rows_out, int rows_cap, double* overlap_state)
+{
+    if (n1 + 1 > CAPS::NV || n2 + 1 > CAPS::NV) return PS_CAPACITY;
+    std::unique_ptr<Workspace<CAPS>> w(new Workspace<CAPS>);
+    Params P; fill_params(prm, boxx, boxy, nbox, P);
+    Body b1{body1[0], body1[1], body1[2], body1[3], body1[4], body1[5], body1[6]};
+    Body b2{body2[0], body2[1], body2[2], body2[3], body2[4], body2[5], body2[6]};
+    w->n1 = n1; w->n2 = n2;
+    for (int i = 0; i < n1; ++i) { w->c1x[i] = cax[i] + b1.Xi; w->c1y[i] = cay[i] + b1.Yi; }
+    for (int i = 0; i < n2; ++i) { w->c2x[i] = c2x[i]; w->c2y[i] = c2y[i]; }
+    PairResult res; std::vector<double> rows(CAPS::ROWS * 5);
+    pair_force(*w, b1, b2, is_boundary != 0, P, res, rows.data());
+    if (res.status != PS_OK) return res.status;
+    *overlap_state = res.overlap_state;
+    if (res.n_rows > rows_cap) return -2;
+    for (int i = 0; i < res.n_rows * 5; ++i) rows_out[i] = rows[i];
+    return res.n_rows;
+}
+
+extern "C" int szport_floe_interactions(const SzParams* prm, const double* cax, const double* cay, int n1, const double* body1,
+                                        const double* c2x, const double* c2y, int n2, const double* body2, int is_boundary,
+                                        const double* boxx, const double* boxy, int nbox,
+                                        double* rows_out, int rows_cap, double* overlap_state, int small_class)
+{
+    if (small_class) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);
+    return run<BigPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);
+}
