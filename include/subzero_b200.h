@@ -146,16 +146,18 @@ int sz_get_clip_polys(SzContext* ctx, int64_t* pair_path_off, int64_t* path_vert
 
 /* ---- stand-alone polygon clip with the gateway's semantics (private/mexclipper.cpp:204-305):
  * `count` independent (subject, clip) pairs, one closed path each, int64 coordinates, even-odd fill,
- * method 0 dif / 1 int / 2 xor / 3 uni.  Runs the same device sweep as the narrow phase.
- * Two-phase: call with out_x == NULL to obtain sizes. */
+ * method 0 dif / 1 int / 2 xor / 3 uni (mexclipper.cpp:206-230).  Runs the same device sweep as the
+ * narrow phase.  sz_clip_batch computes and keeps the result on the device; sz_get_clip_batch copies
+ * it out in the gateway's order (item, then Clipper's path order, :299-302). */
 int sz_clip_batch(SzContext* ctx, int32_t count, const int32_t* method,
-                  const int64_t* subj_off, const int64_t* sx, const int64_t* sy,
-                  const int64_t* clip_off, const int64_t* cx, const int64_t* cy,
-                  int32_t* status,            /* [count] 0 ok / SzStatus */
-                  int64_t* pair_path_off,     /* [count+1] */
-                  int64_t* path_vert_off,     /* [n_paths+1], may be NULL in the size query */
-                  int64_t* out_x, int64_t* out_y,
+                  const int64_t* subj_off, const int64_t* sx, const int64_t* sy,   /* subj_off [count+1] */
+                  const int64_t* clip_off, const int64_t* cx, const int64_t* cy,   /* clip_off [count+1] */
                   int64_t* n_paths, int64_t* n_verts);
+int sz_get_clip_batch(SzContext* ctx,
+                      int32_t* status,            /* [count] 0 ok / SzStatus ("Clipper Error." = SZ_ERR_CLIPPER) */
+                      int64_t* item_path_off,     /* [count+1] */
+                      int64_t* path_vert_off,     /* [n_paths+1] */
+                      int64_t* out_x, int64_t* out_y);                              /* [n_verts] */
 
 /* ---- synthetic input of BASELINE.json configs[4]: periodic Voronoi floe field (host utility) ---- */
 typedef struct SzField SzField;   /* owns the SoA arrays */

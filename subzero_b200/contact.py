@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's contact step over the C ABI.
+
+`ContactContext` is a thin object wrapper of the ABI (one context = one GPU = one host thread).
+`floe_interactions_all(...)` keeps the call signature of the reference's floe_interactions_all.m:1 and
+replaces its lines 9-285 (minus calc_trajectory) with one GPU step: it is what a Python host would call
+where Subzero.m:133,301 call the MATLAB function.  The MATLAB-side drop-in (wrapper + mex shim) lives in
+subzero_b200/matlab/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import FloesSoA, Boundary, SzParams, SzSummary, default_params  # noqa: F401  (re-exported)
+
+
+class ContactContext:
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        abi.check(abi.lib().sz_create(C.byref(self._h), int(device)))
+        self.summary = None
+        self._n0 = 0
+
+    def close(self):
+        if self._h:
+            abi.lib().sz_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stepping
+    def _finish(self, code, s, allow_pair_errors):
+        self.summary = s
+        if code in (abi.SZ_ERR_CLIPPER,) and allow_pair_errors:
+            return s
+        abi.check(code)
+        return s
+
+    def step(self, prm, floes, boundary=None, allow_pair_errors=False):
+        """One contact step with host buffers in (sz_contact_step)."""
+        s = SzSummary()
+        fs = floes.struct()
+        bs = boundary.struct() if boundary is not None else None
+        self._n0 = floes.n
+        code = abi.lib().sz_contact_step(self._h, C.byref(prm), C.byref(fs), C.byref(bs) if bs is not None else None, C.byref(s))
+        return self._finish(code, s, allow_pair_errors)
+
+    def upload(self, prm, floes, boundary=None):
+        fs = floes.struct()
+        bs = boundary.struct() if boundary is not None else None
+        self._n0 = floes.n
+        abi.check(abi.lib().sz_upload(self._h, C.byref(prm), C.byref(fs), C.byref(bs) if bs is not None else None))
+
+    def step_resident(self, allow_pair_errors=False):
+        s = SzSummary()
+        code = abi.lib().sz_step_resident(self._h, C.byref(s))
+        return self._finish(code, s, allow_pair_errors)
+
+    # ---- results
+    def floe_outputs(self, into=None):
+        n = self._n0
+        o = into if into is not None else {
+            "fx": np.empty(n), "fy": np.empty(n), "torque": np.empty(n), "overlap_area": np.empty(n), "stress": np.empty((n, 2, 2)),
+            "xi": np.empty(n), "yi": np.empty(n), "alive": np.empty(n, np.uint8), "kill": np.empty(n, np.int32), "transfer": np.empty(n, np.int32)}
+        p = abi._ptr
+        abi.check(abi.lib().sz_get_floe_outputs(
+            self._h, p(o["fx"], abi.c_dp), p(o["fy"], abi.c_dp), p(o["torque"], abi.c_dp), p(o["overlap_area"], abi.c_dp), p(o["stress"], abi.c_dp),
+            p(o["xi"], abi.c_dp), p(o["yi"], abi.c_dp), p(o["alive"], abi.c_bp), p(o["kill"], abi.c_ip), p(o["transfer"], abi.c_ip)))
+        return o
+
+    def ghosts(self):
+        g = self.summary.n - self.summary.n0
+        o = {"parent": np.empty(g, np.int32), "floe_num": np.empty(g, np.int32), "x": np.empty(g), "y": np.empty(g)}
+        p = abi._ptr
+        abi.check(abi.lib().sz_get_ghosts(self._h, p(o["parent"], abi.c_ip), p(o["floe_num"], abi.c_ip), p(o["x"], abi.c_dp), p(o["y"], abi.c_dp)))
+        return o
+
+    def pairs(self):
+        n = self.summary.n_pairs
+        o = {"i": np.empty(n, np.int32), "j": np.empty(n, np.int32), "overlap_state": np.empty(n), "n_regions": np.empty(n, np.int32), "status": np.empty(n, np.int32)}
+        p = abi._ptr
+        abi.check(abi.lib().sz_get_pairs(self._h, p(o["i"], abi.c_ip), p(o["j"], abi.c_ip), p(o["overlap_state"], abi.c_dp), p(o["n_regions"], abi.c_ip), p(o["status"], abi.c_ip)))
+        return o
+
+    def rows(self):
+        """(row_off [n+1], rows [K,7]) -- rows[row_off[m]:row_off[m+1]] is Floe(m+1).interactions"""
+        off = np.empty(self.summary.n + 1, np.int64)
+        rows = np.empty((self.summary.n_rows, 7))
+        abi.check(abi.lib().sz_get_rows(self._h, abi._ptr(off, abi.c_lp), abi._ptr(rows, abi.c_dp)))
+        return off, rows
+
+    def clip_polys(self):
+        s = self.summary
+        ppo = np.empty(s.n_pairs + 1, np.int64)
+        pvo = np.empty(s.n_clip_paths + 1, np.int64)
+        x = np.empty(s.n_clip_verts, np.int64)
+        y = np.empty(s.n_clip_verts, np.int64)
+        p = abi._ptr
+        abi.check(abi.lib().sz_get_clip_polys(self._h, p(ppo, abi.c_lp), p(pvo, abi.c_lp), p(x, abi.c_lp), p(y, abi.c_lp)))
+        return ppo, pvo, x, y
+
+    # ---- stand-alone clip (mex gateway semantics, private/mexclipper.cpp:204-305)
+    def clip_batch(self, subjects, clips, methods):
+        """subjects/clips: lists of (n,2) int64 arrays; methods: 0 dif / 1 int / 2 xor / 3 uni.
+        Returns (status [count], list of lists of (m,2) int64 paths)."""
+        cnt = len(subjects)
+        soff = np.zeros(cnt + 1, np.int64)
+        coff = np.zeros(cnt + 1, np.int64)
+        for k in range(cnt):
+            soff[k + 1] = soff[k] + len(subjects[k])
+            coff[k + 1] = coff[k] + len(clips[k])
+        sxy = np.concatenate([np.asarray(s, np.int64).reshape(-1, 2) for s in subjects]) if cnt else np.zeros((0, 2), np.int64)
+        cxy = np.concatenate([np.asarray(s, np.int64).reshape(-1, 2) for s in clips]) if cnt else np.zeros((0, 2), np.int64)
+        sx, sy = np.ascontiguousarray(sxy[:, 0]), np.ascontiguousarray(sxy[:, 1])
+        cx, cy = np.ascontiguousarray(cxy[:, 0]), np.ascontiguousarray(cxy[:, 1])
+        m = np.ascontiguousarray(methods, np.int32)
+        npth, nvt = C.c_int64(), C.c_int64()
+        p = abi._ptr
+        abi.check(abi.lib().sz_clip_batch(self._h, cnt, p(m, abi.c_ip), p(soff, abi.c_lp), p(sx, abi.c_lp), p(sy, abi.c_lp),
+                                          p(coff, abi.c_lp), p(cx, abi.c_lp), p(cy, abi.c_lp), C.byref(npth), C.byref(nvt)))
+        status = np.empty(cnt, np.int32)
+        ipo = np.empty(cnt + 1, np.int64)
+        pvo = np.empty(npth.value + 1, np.int64)
+        ox = np.empty(nvt.value, np.int64)
+        oy = np.empty(nvt.value, np.int64)
+        abi.check(abi.lib().sz_get_clip_batch(self._h, p(status, abi.c_ip), p(ipo, abi.c_lp), p(pvo, abi.c_lp), p(ox, abi.c_lp), p(oy, abi.c_lp)))
+        out = []
+        for k in range(cnt):
+            out.append([np.stack([ox[pvo[q]:pvo[q + 1]], oy[pvo[q]:pvo[q + 1]]], 1) for q in range(ipo[k], ipo[k + 1])])
+        return status, out
+
+
+# ------------------------------------------------------------------------------------------------
+def floes_to_soa(Floe):
+    """Flatten a list of floe records (dicts with the reference's field names) to the SoA the ABI takes."""
+    n = len(Floe)
+    get = lambda k: np.array([float(f[k]) for f in Floe], np.float64)
+    voff = np.zeros(n + 1, np.int32)
+    xs, ys = [], []
+    for i, f in enumerate(Floe):
+        ca = np.asarray(f["c_alpha"], np.float64)          # 2 x (n+1), closed
+        xs.append(ca[0])
+        ys.append(ca[1])
+        voff[i + 1] = voff[i] + ca.shape[1]
+    vx = np.concatenate(xs) if n else np.zeros(0)
+    vy = np.concatenate(ys) if n else np.zeros(0)
+    return FloesSoA(get("Xi"), get("Yi"), get("rmax"), get("h"), get("area"), get("Ui"), get("Vi"), get("ksi_ice"),
+                    np.array([int(f["alive"]) for f in Floe], np.uint8), voff, vx, vy)
+
+
+_default_ctx = None
+
+
+def floe_interactions_all(Floe, floebound, ocean, winds, c2_boundary, dt, HFo, min_floe_size, Nx, Ny, Nb, dissolvedNEW, doInt,
+                          COLLISION, PERIODIC, RIDGING, RAFTING, Modulus=None, ctx=None, params=None):
+    """The reference's call signature (floe_interactions_all.m:1; `Modulus` is the reference's global, :7).
+
+    Floe: list of dicts with fields c_alpha (2 x n+1, closed), Xi, Yi, rmax, h, area, Ui, Vi, ksi_ice, alive.
+    floebound: dict with c (2 x m hole vertices, floe_interactions.m:31), area, h, Xi, Yi, Ui, Vi, ksi_ice -- or None when PERIODIC.
+    Writes, per floe, the fields the reference writes in :78-88,136-137,196-198,231,259-263,267-277:
+      interactions (K x 7), OverlapArea, collision_force (1x2), collision_torque, Stress-sum input (`StressSum`, 2x2,
+      calc_trajectory.m:12-13), alive, Xi, Yi, potentialInteractions (emptied, the reference rmfield-s it at :507);
+    and returns (Floe, dissolvedNEW, kill, transfer).  calc_trajectory, ridging/rafting and the kill/fuse tail
+    (:281,288-512) stay with the host model.
+    """
+    global _default_ctx
+    if Modulus is None:
+        raise ValueError("Modulus (the reference's `global Modulus`) must be given")
+    c2 = np.asarray(c2_boundary, np.float64)
+    Floe = [f for f in Floe if int(f["alive"]) != 0]                        # :12-13
+    prm = params if params is not None else default_params()
+    prm.Lx, prm.Ly = float(c2[0].max()), float(c2[1].max())                    # :9-10
+    prm.modulus, prm.dt, prm.Nb = float(Modulus), float(dt), int(Nb)
+    prm.periodic, prm.collision = int(bool(PERIODIC)), int(bool(COLLISION))
+    soa = floes_to_soa(Floe)
+    bnd = None
+    if not PERIODIC and floebound is not None:
+        bc = np.asarray(floebound["c"], np.float64)
+        bnd = Boundary(bc[0], bc[1], c2[0], c2[1], float(floebound["area"]), float(floebound.get("h", 0)), float(floebound.get("Xi", 0)),
+                       float(floebound.get("Yi", 0)), float(floebound.get("Ui", 0)), float(floebound.get("Vi", 0)), float(floebound.get("ksi_ice", 0)))
+    if ctx is None:
+        if _default_ctx is None:
+            _default_ctx = ContactContext(0)
+        ctx = _default_ctx
+    ctx.step(prm, soa, bnd)
+    out = ctx.floe_outputs()
+    off, rows = ctx.rows()
+    for i, f in enumerate(Floe):
+        if i < Nb:
+            continue
+        f["interactions"] = rows[off[i]:off[i + 1]].copy()
+        f["OverlapArea"] = float(out["overlap_area"][i])
+        f["collision_force"] = np.array([out["fx"][i], out["fy"][i]])
+        f["collision_torque"] = float(out["torque"][i])
+        f["StressSum"] = out["stress"][i].copy()
+        f["alive"] = int(out["alive"][i])
+        f["Xi"], f["Yi"] = float(out["xi"][i]), float(out["yi"][i])
+        f["potentialInteractions"] = []
+    return Floe, dissolvedNEW, out["kill"].copy(), out["transfer"].copy()

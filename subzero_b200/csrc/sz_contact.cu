@@ -1,0 +1,1053 @@
+// sz_contact.cu -- the contact step on one B200: ghost floes, spatial-hash broad phase, narrow-phase
+// orchestration, contact-row assembly (mirror, torque, per-floe sums, stress, collision count) and
+// the C ABI of include/subzero_b200.h.  Replaces floe_interactions_all.m:9-285 of the reference.
+//
+// Device data layout (all structure-of-arrays, FP64 unless noted):
+//   originals [n0]       x y rmax h area u v ksi, alive u8, voff i32[n0+1]; vertex pool vx vy [V]
+//                        (c_alpha about the centroid, closed) -- uploaded once per step / per topology
+//   extended list [n]    ex ey (centroid, ghost-shifted), esrc (original sharing outline + body),
+//                        efn (FloeNums, negative for ghosts), eparent, ealive  -- built by K0
+//   cell grid            cell_start i32[ncell+1]; floes bucketed by cell: s_idx s_x s_y s_r
+//   pairs [P]            pi pj ascending (i,j) = order of Floe(i).potentialInteractions; pair_off[n+1]
+//   per pair             status nrows row_start ovl_state; contact-row pool 5 doubles per row
+//   transpose            toff[n+1], tlist: for each floe the pairs in which it is the partner (mirror)
+//   rows [K][7]          canonical order of Floe(m).interactions; row_off[n+1]
+//
+// Kernels: K0 ghost_flag/ghost_emit (+ scan), bbox; K1 cell_count/cell_fill, broad<count>/<fill>
+// (warp per floe, ballot compaction, in-warp rank sort); K2+K3 narrow phase (sz_narrow*.cu);
+// K4 tcount/tfill, rowcount, assemble, fold, kill fix-up.  Every FP64 expression keeps the
+// reference's operation order; the file is compiled with -fmad=false.
+#include "../../include/subzero_b200.h"
+#include "sz_narrow.cuh"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+using sznarrow::NarrowArgs;
+using sznarrow::ClipArgs;
+using szpf::Params;
+using szpf::Body;
+typedef long long i64;
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void sz_set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* sz_last_error(void) { return g_err; }
+extern "C" int sz_abi_version(void) { return 1; }
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    sz_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); return SZ_ERR_CUDA; } } while (0)
+
+template <class T>
+struct DBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n, bool keep = false)
+    {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = n + n / 4 + 64;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
+        if (p) cudaFree(p);
+        p = q; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// counters living in device memory, mirrored into pinned host memory with one copy
+struct Counters {
+    int n1, n;                     // extended-list sizes after the x pass / after the y pass
+    int n_pairs;
+    int row_used, path_used, vert_used;
+    int listM, listL, wlistM, wlistL;
+    int total_rows;
+    int n_pairs_force, n_fail, n_cap_fail;
+    u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
+    u64 rmax_bits;
+    u64 n_fin_rows, n_inf_rows;
+    int clip_listM, clip_listL, clip_path_used, clip_vert_used;
+};
+
+struct SzContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
+    // inputs
+    bool have_input = false, have_step = false;
+    SzParams prm; Params dprm; bool have_bnd = false; Body bbody;
+    int n0 = 0; i64 nverts = 0;
+    DBuf<double> x, y, rmax, h, area, u, v, ksi, vx, vy, bx, by, boxx, boxy;
+    DBuf<uint8_t> alive;
+    DBuf<int> voff;
+    int bn = 0, boxn = 0;
+    // extended list
+    int n = 0, n1 = 0;
+    DBuf<double> ex, ey; DBuf<int> esrc, efn, eparent, gx_of, gy_of; DBuf<uint8_t> ealive;
+    DBuf<int> flag, pos, scan_tmp;
+    // grid
+    DBuf<int> cid, cell_cnt, cell_start, s_idx; DBuf<double> s_x, s_y, s_r;
+    // pairs
+    int n_pairs = 0;
+    DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
+    DBuf<int> listM, listL;
+    DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
+    DBuf<double> row_pool;
+    DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
+    DBuf<unsigned char> scratchM, scratchL;
+    // assembly
+    DBuf<int> tcnt, toff, tlist, rcnt, row_off;
+    DBuf<double> rows; i64 n_rows = 0;
+    DBuf<double> osum;             // [n*3] own column sums Fx Fy tau
+    DBuf<uint8_t> has_rows;
+    DBuf<int> kill_i, transfer_i, tmax;
+    // per-original outputs
+    DBuf<double> o_fx, o_fy, o_tq, o_ov, o_stress, o_xi, o_yi; DBuf<uint8_t> o_alive; DBuf<int> o_kill, o_transfer;
+    SzSummary summary;
+    // clip batch
+    int clip_count = 0; i64 clip_paths = 0, clip_verts = 0;
+    DBuf<int> c_method, c_status, c_path_start, c_npaths, c_path_vstart, c_path_len, c_listM, c_listL;
+    DBuf<i64> c_soff, c_coff, c_sx, c_sy, c_cx, c_cy, c_pvx, c_pvy;
+};
+
+// ------------------------------------------------------------------------------------------------ scan
+// Exclusive prefix sum of int32: out[k] = sum in[0..k), k in [0, n_out).  Reads of in[k] for k >= n_in
+// yield 0, so calling with n_out = n_in + 1 leaves the grand total in out[n_in].
+#define SCAN_TPB 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_TPB * SCAN_ITEMS)
+__global__ void __launch_bounds__(SCAN_TPB) scan_tile_kernel(const int* __restrict__ in, int n_in, int* __restrict__ out, int n_out, int* __restrict__ tile_sums)
+{
+    __shared__ int warp_sums[SCAN_TPB / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS]; int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { int idx = base + k; v[k] = (idx < n_in) ? in[idx] : 0; s += v[k]; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int ws = (lane < SCAN_TPB / 32) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < SCAN_TPB / 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, ws, d); if (lane >= d) ws += t; }
+        if (lane < SCAN_TPB / 32) warp_sums[lane] = ws;   // inclusive
+    }
+    __syncthreads();
+    int run = incl - s + (wid > 0 ? warp_sums[wid - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { int idx = base + k; if (idx < n_out) out[idx] = run; run += v[k]; }
+    if (threadIdx.x == SCAN_TPB - 1 && tile_sums) tile_sums[blockIdx.x] = run;
+}
+__global__ void scan_add_kernel(int* __restrict__ out, int n_out, const int* __restrict__ tile_off)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n_out) out[idx] += tile_off[idx / SCAN_TILE];
+}
+// tmp must hold >= n_out/SCAN_TILE + n_out/SCAN_TILE^2 + 8 ints
+static void exclusive_scan(const int* in, int n_in, int* out, int n_out, int* tmp, cudaStream_t st)
+{
+    const int tiles = (n_out + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles <= 1) { scan_tile_kernel<<<1, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, nullptr); return; }
+    int* sums = tmp; int* sums_scanned = tmp + tiles + 1;
+    scan_tile_kernel<<<tiles, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, sums);
+    exclusive_scan(sums, tiles, sums_scanned, tiles, sums_scanned + tiles + 1, st);
+    scan_add_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(out, n_out, sums_scanned);
+}
+static size_t scan_tmp_ints(size_t n) { size_t t = 0; while (n > SCAN_TILE) { n = (n + SCAN_TILE - 1) / SCAN_TILE; t += 2 * n + 4; } return t + 16; }
+
+// ------------------------------------------------------------------------------------------------ K0 ghosts
+__device__ __forceinline__ double sgn_d(double v) { return (double)((v > 0) - (v < 0)); }
+
+// flag[i] = alive(i) && max_v |c_alpha(axis,v) + centroid(axis)| > L      (floe_interactions_all.m:30-31, 51-52)
+__global__ void ghost_flag_kernel(int axis, int n_bound, const int* __restrict__ n_dev, const double* __restrict__ ec,
+                                  const int* __restrict__ esrc, const uint8_t* __restrict__ ealive,
+                                  const int* __restrict__ voff, const double* __restrict__ vc, double L, int* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bound) return;
+    const int n = n_dev ? *n_dev : n_bound;
+    int f = 0;
+    if (i < n && ealive[i]) {
+        const int s = esrc[i]; const double c = ec[i];
+        double m = -SZ_INF;
+        for (int t = voff[s]; t < voff[s + 1]; ++t) { double a = fabs(vc[t] + c); if (a > m) m = a; }
+        f = (m > L);
+    }
+    flag[i] = f;
+}
+// appended copy with the centroid shifted by -2L*sign(centroid)             (:33-36, 54-57)
+__global__ void ghost_emit_kernel(int axis, int n_bound, const int* __restrict__ n_dev, int n0, const int* __restrict__ flag, const int* __restrict__ pos,
+                                  double* __restrict__ ex, double* __restrict__ ey, int* __restrict__ esrc, int* __restrict__ efn,
+                                  int* __restrict__ eparent, uint8_t* __restrict__ ealive, int* __restrict__ gx_of, int* __restrict__ gy_of,
+                                  double L, int* __restrict__ n_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = n_dev ? *n_dev : n_bound;
+    if (i == 0) *n_out = n + pos[n_bound];
+    if (i >= n || !flag[i]) return;
+    const int g = n + pos[i];
+    if (axis == 0) { ex[g] = ex[i] - 2 * L * sgn_d(ex[i]); ey[g] = ey[i]; if (i < n0) gx_of[i] = g; }
+    else { ex[g] = ex[i]; ey[g] = ey[i] - 2 * L * sgn_d(ey[i]); if (i < n0) gy_of[i] = g; }
+    esrc[g] = esrc[i]; efn[g] = -abs(efn[i]); eparent[g] = i + 1; ealive[g] = ealive[i];
+}
+__global__ void init_extended_kernel(int n0, const double* __restrict__ x, const double* __restrict__ y, const uint8_t* __restrict__ alive,
+                                     double* ex, double* ey, int* esrc, int* efn, int* eparent, uint8_t* ealive, int* gx_of, int* gy_of)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    ex[i] = x[i]; ey[i] = y[i]; esrc[i] = i; efn[i] = i + 1; eparent[i] = 0; ealive[i] = alive[i]; gx_of[i] = -1; gy_of[i] = -1;
+}
+
+// order-preserving map double -> u64 so that atomicMin/atomicMax work
+__device__ __host__ __forceinline__ u64 enc_d(double v) { u64 b; memcpy(&b, &v, 8); return (b >> 63) ? ~b : (b | 0x8000000000000000ULL); }
+__device__ __host__ __forceinline__ double dec_d(u64 b) { b = (b >> 63) ? (b & 0x7FFFFFFFFFFFFFFFULL) : ~b; double v; memcpy(&v, &b, 8); return v; }
+
+__global__ void bbox_kernel(int n_bound, const int* __restrict__ n_dev, const double* __restrict__ ex, const double* __restrict__ ey,
+                            const int* __restrict__ esrc, const double* __restrict__ rmax, Counters* c)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *n_dev;
+    double xmn = SZ_INF, xmx = -SZ_INF, ymn = SZ_INF, ymx = -SZ_INF, rm = 0;
+    if (i < n_bound && i < n) {
+        const double x = ex[i], y = ey[i];
+        if (x == x && y == y) { xmn = xmx = x; ymn = ymx = y; }
+        const double r = rmax[esrc[i]]; if (r > rm) rm = r;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        xmn = fmin(xmn, __shfl_xor_sync(0xffffffffu, xmn, d)); xmx = fmax(xmx, __shfl_xor_sync(0xffffffffu, xmx, d));
+        ymn = fmin(ymn, __shfl_xor_sync(0xffffffffu, ymn, d)); ymx = fmax(ymx, __shfl_xor_sync(0xffffffffu, ymx, d));
+        rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (xmn <= xmx) { atomicMin(&c->bbox[0], enc_d(xmn)); atomicMax(&c->bbox[1], enc_d(xmx)); atomicMin(&c->bbox[2], enc_d(ymn)); atomicMax(&c->bbox[3], enc_d(ymx)); }
+        atomicMax(&c->rmax_bits, enc_d(rm));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1 broad phase
+struct GridDesc { double x0, y0, cell; int nx, ny; };
+__device__ __forceinline__ int cell_coord(double v, double v0, double cell, int n) { int c = (int)((v - v0) / cell); return c < 0 ? 0 : (c >= n ? n - 1 : c); }
+
+__global__ void cell_count_kernel(int n, GridDesc g, const double* __restrict__ ex, const double* __restrict__ ey, const uint8_t* __restrict__ ealive,
+                                  int* __restrict__ cid, int* __restrict__ cell_cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = ex[i], y = ey[i];
+    int c = -1;
+    if (ealive[i] && x == x && y == y) { c = cell_coord(y, g.y0, g.cell, g.ny) * g.nx + cell_coord(x, g.x0, g.cell, g.nx); atomicAdd(&cell_cnt[c], 1); }
+    cid[i] = c;
+}
+__global__ void cell_fill_kernel(int n, const int* __restrict__ cid, const int* __restrict__ cell_start, int* __restrict__ cell_pos,
+                                 const double* __restrict__ ex, const double* __restrict__ ey, const int* __restrict__ esrc, const double* __restrict__ rmax,
+                                 int* __restrict__ s_idx, double* __restrict__ s_x, double* __restrict__ s_y, double* __restrict__ s_r)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cid[i];
+    if (c < 0) return;
+    const int t = cell_start[c] + atomicAdd(&cell_pos[c], 1);
+    s_idx[t] = i; s_x[t] = ex[i]; s_y[t] = ey[i]; s_r[t] = rmax[esrc[i]];
+}
+
+struct BroadArgs {
+    int n, n0, Nb, collision; GridDesc g; double minL2;
+    const double* ex; const double* ey; const int* esrc; const int* efn; const uint8_t* ealive; const double* rmax;
+    const int* cell_start; const int* s_idx; const double* s_x; const double* s_y; const double* s_r;
+    int* pcnt; const int* pair_off; int* pi; int* pj;
+};
+// The predicate of floe_interactions_all.m:103 for partner j of floe i (j > i checked by the caller):
+//   alive(j) && sqrt((xi-xj)^2+(yi-yj)^2) < rmax_i+rmax_j && (~ismember(|FloeNums(j)|,mems) || 2(rmax_i+rmax_j) > min(2Lx,2Ly))
+// `mems` (:93-99,113) in closed form: a ghost j is a member iff its original o_j is a forward partner of
+// a = i (i an original) or of a = i's original (i a ghost), i.e. o_j > a and the pair (a, o_j) itself passes
+// the distance test with a eligible for the pair loop.
+__device__ __forceinline__ bool ghost_is_member(const BroadArgs& b, int i, int j)
+{
+    const int oj = b.esrc[j];
+    const int a = (b.efn[i] < 0) ? b.esrc[i] : i;
+    if (!(oj > a) || a < b.Nb) return false;
+    if (!b.ealive[a] || !b.ealive[oj]) return false;
+    const double xa = b.ex[a], ya = b.ey[a];
+    if (xa != xa) return false;
+    const double dx = xa - b.ex[oj], dy = ya - b.ey[oj];
+    return sqrt(dx * dx + dy * dy) < (b.rmax[a] + b.rmax[oj]);
+}
+// one warp per floe i: lanes stride over the three cell rows (each row's three cells are contiguous in
+// the bucketed arrays), ballot + popc compacts accepted partners, then an in-warp rank sort restores
+// ascending j (the order of Floe(i).potentialInteractions)
+template <bool FILL>
+__global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int i = b.Nb + warp;
+    if (i >= b.n) return;
+    const double xi = b.ex[i], yi = b.ey[i];
+    const bool active = b.ealive[i] && (xi == xi) && b.collision && (yi == yi);
+    int count = 0;
+    const int off = FILL ? b.pair_off[i] : 0;
+    if (active) {
+        const double ri = b.rmax[b.esrc[i]];
+        const int cxi = cell_coord(xi, b.g.x0, b.g.cell, b.g.nx), cyi = cell_coord(yi, b.g.y0, b.g.cell, b.g.ny);
+        const int cx0 = cxi > 0 ? cxi - 1 : 0, cx1 = cxi + 1 < b.g.nx ? cxi + 1 : b.g.nx - 1;
+        for (int cy = (cyi > 0 ? cyi - 1 : 0); cy <= cyi + 1 && cy < b.g.ny; ++cy) {
+            const int t0 = b.cell_start[cy * b.g.nx + cx0], t1 = b.cell_start[cy * b.g.nx + cx1 + 1];
+            for (int tb = t0; tb < t1; tb += 32) {
+                const int t = tb + lane;
+                bool ok = false; int j = -1;
+                if (t < t1) {
+                    j = b.s_idx[t];
+                    if (j > i) {
+                        const double dx = xi - b.s_x[t], dy = yi - b.s_y[t], rs = ri + b.s_r[t];
+                        if (sqrt(dx * dx + dy * dy) < rs) {
+                            ok = true;
+                            if (b.efn[j] < 0 && ghost_is_member(b, i, j) && !(2 * rs > b.minL2)) ok = false;
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (FILL && ok) b.pj[off + count + __popc(m & ((1u << lane) - 1))] = j;
+                count += __popc(m);
+            }
+        }
+    }
+    if (!FILL) { if (lane == 0) b.pcnt[i] = count; return; }
+    if (count == 0) return;
+    __syncwarp();
+    if (count <= 32) {
+        const int v = (lane < count) ? b.pj[off + lane] : 0x7fffffff;
+        int rank = 0;
+        for (int m = 0; m < count; ++m) rank += (__shfl_sync(0xffffffffu, v, m) < v);
+        __syncwarp();
+        if (lane < count) { b.pj[off + rank] = v; b.pi[off + lane] = i; }
+    } else {
+        if (lane == 0) {
+            for (int a = 1; a < count; ++a) { int v = b.pj[off + a], k = a - 1; while (k >= 0 && b.pj[off + k] > v) { b.pj[off + k + 1] = b.pj[off + k]; --k; } b.pj[off + k + 1] = v; }
+        }
+        for (int k = lane; k < count; k += 32) b.pi[off + k] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4 assembly
+__global__ void tcount_kernel(int np, const int* __restrict__ pj, const int* __restrict__ nrows, int* __restrict__ tcnt)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < np && nrows[p] > 0) atomicAdd(&tcnt[pj[p]], 1);
+}
+__global__ void tfill_kernel(int np, const int* __restrict__ pj, const int* __restrict__ nrows, const int* __restrict__ toff, int* __restrict__ tpos, int* __restrict__ tlist)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < np && nrows[p] > 0) { const int j = pj[p]; tlist[toff[j] + atomicAdd(&tpos[j], 1)] = p; }
+}
+// rows of floe m = own pairs + wall + mirrored (floe_interactions_all.m:136,167,196)
+__global__ void rowcount_kernel(int n, const int* __restrict__ pair_off, const int* __restrict__ nrows, const int* __restrict__ wnrows,
+                                const int* __restrict__ toff, int* __restrict__ tlist, int* __restrict__ rcnt)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    int c = 0;
+    for (int p = pair_off[m]; p < pair_off[m + 1]; ++p) c += nrows[p];
+    if (wnrows) c += wnrows[m];
+    const int t0 = toff[m], t1 = toff[m + 1];
+    for (int a = t0 + 1; a < t1; ++a) { int v = tlist[a], k = a - 1; while (k >= t0 && tlist[k] > v) { tlist[k + 1] = tlist[k]; --k; } tlist[k + 1] = v; }   // ascending i
+    for (int t = t0; t < t1; ++t) c += nrows[tlist[t]];
+    rcnt[m] = c;
+}
+
+// polygon_operations/inpolygon.m:64-224 for one point against a double polygon (used for the
+// centroid-in-domain test, floe_interactions_all.m:152)
+__device__ bool in_polygon_d(double x, double y, const double* xv, const double* yv, int nv)
+{
+    if (nv < 1) return false;
+    double xmin = xv[0], xmax = xv[0], ymin = yv[0], ymax = yv[0];
+    for (int k = 1; k < nv; ++k) { xmin = fmin(xmin, xv[k]); xmax = fmax(xmax, xv[k]); ymin = fmin(ymin, yv[k]); ymax = fmax(ymax, yv[k]); }
+    if (!(x >= xmin && x <= xmax && y >= ymin && y <= ymax)) return false;
+    const bool closed = !(nv >= 3 && (xv[0] != xv[nv - 1] || yv[0] != yv[nv - 1]));
+    const int ne = closed ? nv - 1 : nv;      // edges
+    if (ne < 1) return false;
+    double sumdq = 0; bool on = false;
+    double ax = xv[0], ay = yv[0];
+    double vx0 = ax - x, vy0 = ay - y;
+    bool px0 = vx0 > 0, py0 = vy0 > 0;
+    double q0 = (double)((!px0 && py0) + 2 * (!px0 && !py0) + 3 * (px0 && !py0));
+    for (int m = 0; m < ne; ++m) {
+        const int j = (m + 1 < nv) ? m + 1 : 0;
+        const double bx = xv[j], by = yv[j];
+        const double avx = fabs(0.5 * (ax + bx)), avy = fabs(0.5 * (ay + by));
+        double sf = avx > avy ? avx : avy; const double pr = avx * avy; if (pr > sf) sf = pr;
+        const double seps = sf * SZ_EPS * 3;
+        const double vx1 = bx - x, vy1 = by - y;
+        const bool px1 = vx1 > 0, py1 = vy1 > 0;
+        const double q1 = (double)((!px1 && py1) + 2 * (!px1 && !py1) + 3 * (px1 && !py1));
+        const double cross = vx0 * vy1 - vx1 * vy0;
+        double sg = (double)((cross > 0) - (cross < 0));
+        if (fabs(cross) < seps) sg = 0;
+        const double dot = vx0 * vx1 + vy0 * vy1;
+        double dq = q1 - q0;
+        if (fabs(dq) == 3) dq = -dq / 3; else if (fabs(dq) == 2) dq = 2 * sg;
+        sumdq += dq;
+        if (sg == 0 && dot <= 0) on = true;
+        ax = bx; ay = by; vx0 = vx1; vy0 = vy1; q0 = q1;
+    }
+    return (sumdq != 0) || on;
+}
+
+struct AssembleArgs {
+    int n, n0, Nb, periodic, wall; double Lx, Ly;
+    const double* ex; const double* ey; const int* esrc; const uint8_t* ealive; const double* area; const double* h;
+    const int* pair_off; const int* pi; const int* pj; const int* nrows; const int* row_start; const double* ovl; const int* pstatus;
+    const int* wnrows; const int* wrow_start; const int* wstatus;
+    const int* toff; const int* tlist; const int* row_off; const double* pool;
+    const double* boxx; const double* boxy; int boxn;
+    double* rows; double* osum; uint8_t* has_rows; int* kill_i; int* transfer_i;
+    double* o_ov; double* o_stress; double* o_xi; double* o_yi; uint8_t* o_alive;
+    Counters* cnt;
+};
+// one thread per floe of the extended list writes its rows in the reference's canonical order and, walking
+// them top to bottom like MATLAB's column sum, accumulates torque, force sums, overlap area and stress
+__global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= a.n) return;
+    const double xm = a.ex[m], ym = a.ey[m];
+    // periodic wrap of the centroid (:267-277); the stress uses the wrapped centroid
+    double xw = xm, yw = ym;
+    if (a.periodic && m >= a.Nb && m < a.n0) {
+        if (fabs(xw) > a.Lx) xw = xw - 2 * a.Lx * sgn_d(xw);
+        if (fabs(yw) > a.Ly) yw = yw - 2 * a.Ly * sgn_d(yw);
+    }
+    double* R = a.rows + (size_t)a.row_off[m] * 7;
+    const int nr_total = a.row_off[m + 1] - a.row_off[m];
+    double sfx = 0, sfy = 0, st = 0, ova = 0;
+    double s11 = 0, s12 = 0, s21 = 0, s22 = 0, t11 = 0, t12 = 0, t21 = 0, t22 = 0;
+    int nfin = 0, ninf = 0, kill = 0, transfer = 0;
+    auto put = [&](double partner, double fx, double fy, double px, double py, double ov) {
+        const double tau = (px - xm) * fy - (py - ym) * fx;                 // cross([P-r 0],[F 0]) (:255-259)
+        R[0] = partner; R[1] = fx; R[2] = fy; R[3] = px; R[4] = py; R[5] = tau; R[6] = ov; R += 7;
+        sfx += fx; sfy += fy; st += tau;
+        s11 += (px - xw) * fx; s12 += (py - yw) * fx; s21 += (px - xw) * fy; s22 += (py - yw) * fy;   // calc_trajectory.m:12
+        t11 += fx * (px - xw); t12 += fy * (px - xw); t21 += fx * (py - yw); t22 += fy * (py - yw);
+    };
+    // own pairs, ascending partner (:125-147)
+    for (int p = a.pair_off[m]; p < a.pair_off[m + 1]; ++p) {
+        const int nr = a.nrows[p];
+        if (nr > 0) {
+            const double* src = a.pool + (size_t)a.row_start[p] * 5;
+            double so = 0;
+            for (int q = 0; q < nr; ++q) { put((double)(a.pj[p] + 1), src[q * 5], src[q * 5 + 1], src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); so += src[q * 5 + 4]; ++nfin; }
+            ova = so + ova;
+        } else if (a.pstatus[p] == 0) {
+            const double ov = a.ovl[p];
+            if ((ov == SZ_INF || ov == -SZ_INF) && m >= a.Nb) {          // :138-145
+                if (m < a.n0 && ov > 0) { kill = m + 1; transfer = a.pj[p] + 1; }
+                else if (a.pj[p] + 1 <= a.n0) kill = a.pj[p] + 1;
+            }
+        }
+    }
+    // wall rows (:150-172)
+    uint8_t alive_out = a.ealive[m];
+    if (a.wall && m >= a.Nb && a.wstatus[m] == 0) {
+        if (!in_polygon_d(xm, ym, a.boxx, a.boxy, a.boxn)) alive_out = 0;  // :152-155
+        const int nr = a.wnrows[m];
+        if (nr > 0) {
+            const double* src = a.pool + (size_t)a.wrow_start[m] * 5;
+            double so = 0;
+            for (int q = 0; q < nr; ++q) {
+                double fx = src[q * 5], fy = src[q * 5 + 1];
+                if (fabs(src[q * 5 + 3]) == a.Ly) fx = 0;                    // :160-162
+                if (fabs(src[q * 5 + 2]) == a.Lx) fy = 0;                    // :163-165
+                put(SZ_INF, fx, fy, src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); so += src[q * 5 + 4]; ++ninf;
+            }
+            ova = so + ova;
+        }
+    }
+    // mirrored rows from lower-numbered floes, ascending i (:187-214)
+    for (int t = a.toff[m]; t < a.toff[m + 1]; ++t) {
+        const int p = a.tlist[t]; const int nr = a.nrows[p];
+        const double* src = a.pool + (size_t)a.row_start[p] * 5;
+        for (int q = 0; q < nr; ++q) { put((double)(a.pi[p] + 1), -src[q * 5], -src[q * 5 + 1], src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); ova = ova + src[q * 5 + 4]; ++nfin; }
+    }
+    a.osum[(size_t)m * 3] = sfx; a.osum[(size_t)m * 3 + 1] = sfy; a.osum[(size_t)m * 3 + 2] = st;
+    a.has_rows[m] = nr_total > 0;
+    a.kill_i[m] = kill; a.transfer_i[m] = transfer;
+    if (m < a.n0) {
+        a.o_ov[m] = ova; a.o_xi[m] = xw; a.o_yi[m] = yw; a.o_alive[m] = alive_out;
+        double* S = a.o_stress + (size_t)m * 4;
+        if (m >= a.Nb && alive_out && nr_total > 0) {
+            const double k = 1 / (2 * a.area[m] * a.h[m]);
+            S[0] = k * (s11 + t11); S[1] = k * (s12 + t12); S[2] = k * (s21 + t21); S[3] = k * (s22 + t22);
+        } else { S[0] = S[1] = S[2] = S[3] = 0; }
+        if (nfin) atomicAdd(&a.cnt->n_fin_rows, (u64)nfin);
+        if (ninf) atomicAdd(&a.cnt->n_inf_rows, (u64)ninf);
+    }
+}
+// ghost sums folded into their parents in creation order (:242-245), then the floe's own column sums (:262-263)
+__global__ void fold_kernel(int n0, int Nb, const int* __restrict__ gx_of, const int* __restrict__ gy_of, const double* __restrict__ osum,
+                            const uint8_t* __restrict__ has_rows, double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ tq)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n0) return;
+    double f0 = 0, f1 = 0, t = 0;
+    const int gx = gx_of[m], gy = gy_of[m];
+    if (gx >= 0) { f0 = f0 + (has_rows[gx] ? osum[(size_t)gx * 3] : 0.0); f1 = f1 + (has_rows[gx] ? osum[(size_t)gx * 3 + 1] : 0.0); t = t + (has_rows[gx] ? osum[(size_t)gx * 3 + 2] : 0.0); }
+    if (gy >= 0) { f0 = f0 + (has_rows[gy] ? osum[(size_t)gy * 3] : 0.0); f1 = f1 + (has_rows[gy] ? osum[(size_t)gy * 3 + 1] : 0.0); t = t + (has_rows[gy] ? osum[(size_t)gy * 3 + 2] : 0.0); }
+    if (m >= Nb && has_rows[m]) { f0 = osum[(size_t)m * 3] + f0; f1 = osum[(size_t)m * 3 + 1] + f1; t = osum[(size_t)m * 3 + 2] + t; }
+    fx[m] = f0; fy[m] = f1; tq[m] = t;
+}
+// :175-179  for i=1:length(kill): if kill(i) ~= i && kill(i) > 0, transfer(kill(i)) = i   (serial: the largest i wins)
+__global__ void kill_mark_kernel(int n, const int* __restrict__ kill_i, int* __restrict__ tmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = kill_i[i];
+    if (k > 0 && k != i + 1) atomicMax(&tmax[k - 1], i + 1);
+}
+__global__ void kill_final_kernel(int n0, const int* __restrict__ kill_i, const int* __restrict__ transfer_i, const int* __restrict__ tmax, int* kill, int* transfer)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    kill[i] = kill_i[i]; transfer[i] = tmax[i] ? tmax[i] : transfer_i[i];
+}
+__global__ void pair_stats_kernel(int np, const int* __restrict__ status, const int* __restrict__ nrows, int count_force, Counters* c)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = 0, e = 0, k = 0;
+    if (p < np) { const int s = status[p]; f = (s == 0 && nrows[p] > 0); e = (s == szpf::PS_CLIPPER_FAIL || s == szpf::PS_BAD_POLY); k = (s == szpf::PS_CAPACITY); }
+    const unsigned mf = __ballot_sync(0xffffffffu, f), me = __ballot_sync(0xffffffffu, e), mk = __ballot_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) {
+        if (mf && count_force) atomicAdd(&c->n_pairs_force, __popc(mf));
+        if (me) atomicAdd(&c->n_fail, __popc(me));
+        if (mk) atomicAdd(&c->n_cap_fail, __popc(mk));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline int nblk(i64 n, int tpb) { return (int)((n + tpb - 1) / tpb); }
+
+extern "C" void sz_default_params(SzParams* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->nu = 0.3; p->mu = 0.2; p->merge_frac = 0.55; p->wall_frac = 0.75; p->amin_per_vertex = 100.0 / 1.75;
+    p->vertex_match_tol = 1; p->on_edge_tol = 1e-8; p->dl_min = 0.1; p->close_gap = 1; p->big_floe_r = 1e5; p->domain_area_frac = 0.95;
+    p->dt = 10; p->collision = 1; p->periodic = 0; p->Nb = 0; p->want_clip_polys = 0;
+}
+
+extern "C" int sz_create(SzContext** out, int device)
+{
+    if (!out) { sz_set_error("sz_create: out is NULL"); return SZ_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { sz_set_error("sz_create: no CUDA device is usable (there is no CPU fallback)"); return SZ_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { sz_set_error("sz_create: device %d out of range (%d devices)", device, ndev); return SZ_ERR_ARG; }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { sz_set_error("sz_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return SZ_ERR_CUDA; }
+    CK(cudaSetDevice(device));
+    SzContext* c = new SzContext;
+    c->device = device;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    CK(cudaMalloc(&c->d_cnt, sizeof(Counters)));
+    CK(cudaMallocHost(&c->h_cnt, sizeof(Counters)));
+    memset(&c->summary, 0, sizeof(c->summary));
+    *out = c;
+    return SZ_OK;
+}
+
+extern "C" void sz_destroy(SzContext* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
+                          &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
+    for (auto* b : db) b->release();
+    DBuf<int>* ib[] = {&c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
+                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
+                       &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
+                       &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
+                       &c->c_path_len, &c->c_listM, &c->c_listL};
+    for (auto* b : ib) b->release();
+    DBuf<uint8_t>* ub[] = {&c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
+    for (auto* b : ub) b->release();
+    DBuf<i64>* lb[] = {&c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
+    for (auto* b : lb) b->release();
+    if (c->d_cnt) cudaFree(c->d_cnt);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static void fill_device_params(const SzParams* p, const SzBoundary* bnd, Params& P)
+{
+    P.Lx = p->Lx; P.Ly = p->Ly; P.modulus = p->modulus; P.dt = p->dt; P.nu = p->nu; P.mu = p->mu; P.merge_frac = p->merge_frac;
+    P.wall_frac = p->wall_frac; P.amin_per_vertex = p->amin_per_vertex; P.vertex_match_tol = p->vertex_match_tol;
+    P.on_edge_tol = p->on_edge_tol; P.dl_min = p->dl_min; P.close_gap = p->close_gap; P.big_floe_r = p->big_floe_r;
+    P.domain_area_frac = p->domain_area_frac; P.Nb = p->Nb; P.periodic = p->periodic; P.collision = p->collision;
+    P.has_box = (bnd && bnd->box_n > 0) ? 1 : 0;
+    P.bxmin = P.bxmax = P.bymin = P.bymax = P.barea = 0;
+    if (P.has_box) {
+        const double* bx = bnd->box_x; const double* by = bnd->box_y; const int nb = bnd->box_n;
+        P.bxmin = P.bxmax = bx[0]; P.bymin = P.bymax = by[0];
+        for (int i = 1; i < nb; ++i) { P.bxmin = std::min(P.bxmin, bx[i]); P.bxmax = std::max(P.bxmax, bx[i]); P.bymin = std::min(P.bymin, by[i]); P.bymax = std::max(P.bymax, by[i]); }
+        // area(polyshape(c2_boundary')) (floe_interactions.m:54): vertex-0-relative shoelace, not contracted
+        volatile double a2 = 0;
+        for (int i = 0; i < nb; ++i) {
+            const int j = (i + 1) % nb;
+            volatile double xi = bx[i] - bx[0], yi = by[i] - by[0], xj = bx[j] - bx[0], yj = by[j] - by[0];
+            volatile double t1 = xi * yj, t2 = xj * yi; volatile double c = t1 - t2;
+            a2 = a2 + c;
+        }
+        P.barea = fabs(a2) / 2;
+    }
+}
+
+extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f, const SzBoundary* bnd)
+{
+    if (!c || !prm || !f) { sz_set_error("sz_upload: NULL argument"); return SZ_ERR_ARG; }
+    if (f->n < 0 || f->nverts < 0 || (f->n > 0 && (!f->x || !f->y || !f->rmax || !f->h || !f->area || !f->u || !f->v || !f->ksi || !f->alive || !f->voff)) ||
+        (f->nverts > 0 && (!f->vx || !f->vy))) { sz_set_error("sz_upload: floe arrays missing"); return SZ_ERR_ARG; }
+    if (f->n > 0 && (f->voff[0] != 0 || (i64)f->voff[f->n] != f->nverts)) { sz_set_error("sz_upload: voff[0] must be 0 and voff[n] == nverts"); return SZ_ERR_ARG; }
+    if (f->n > 500000000 / 4) { sz_set_error("sz_upload: too many floes"); return SZ_ERR_ARG; }
+    if (prm->Nb < 0 || !(prm->Lx > 0) || !(prm->Ly > 0)) { sz_set_error("sz_upload: bad Nb/Lx/Ly"); return SZ_ERR_ARG; }
+    if (!prm->periodic && bnd && (bnd->n < 3 || !bnd->x || !bnd->y)) { sz_set_error("sz_upload: boundary polygon needs >= 3 vertices"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    const int n = f->n; const size_t nv = (size_t)f->nverts;
+    c->have_step = false;
+    CK(c->x.ensure(n)); CK(c->y.ensure(n)); CK(c->rmax.ensure(n)); CK(c->h.ensure(n)); CK(c->area.ensure(n));
+    CK(c->u.ensure(n)); CK(c->v.ensure(n)); CK(c->ksi.ensure(n)); CK(c->alive.ensure(n)); CK(c->voff.ensure(n + 1));
+    CK(c->vx.ensure(nv)); CK(c->vy.ensure(nv));
+    cudaStream_t st = c->stream;
+    if (n > 0) {
+        const size_t b = (size_t)n * 8;
+        CK(cudaMemcpyAsync(c->x.p, f->x, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->y.p, f->y, b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->rmax.p, f->rmax, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->h.p, f->h, b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->area.p, f->area, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->u.p, f->u, b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->v.p, f->v, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->ksi.p, f->ksi, b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->alive.p, f->alive, n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->voff.p, f->voff, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (nv) { CK(cudaMemcpyAsync(c->vx.p, f->vx, nv * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->vy.p, f->vy, nv * 8, cudaMemcpyHostToDevice, st)); }
+    }
+    c->have_bnd = false; c->bn = 0; c->boxn = 0;
+    if (bnd && !prm->periodic) {
+        c->have_bnd = true; c->bn = bnd->n; c->boxn = bnd->box_n;
+        CK(c->bx.ensure(bnd->n)); CK(c->by.ensure(bnd->n)); CK(c->boxx.ensure(std::max(1, bnd->box_n))); CK(c->boxy.ensure(std::max(1, bnd->box_n)));
+        CK(cudaMemcpyAsync(c->bx.p, bnd->x, (size_t)bnd->n * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->by.p, bnd->y, (size_t)bnd->n * 8, cudaMemcpyHostToDevice, st));
+        if (bnd->box_n > 0) { CK(cudaMemcpyAsync(c->boxx.p, bnd->box_x, (size_t)bnd->box_n * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->boxy.p, bnd->box_y, (size_t)bnd->box_n * 8, cudaMemcpyHostToDevice, st)); }
+        c->bbody.h = bnd->h; c->bbody.area = bnd->area; c->bbody.Xi = bnd->xi; c->bbody.Yi = bnd->yi; c->bbody.Ui = bnd->u; c->bbody.Vi = bnd->v; c->bbody.ksi = bnd->ksi;
+    }
+    c->prm = *prm;
+    fill_device_params(prm, (bnd && !prm->periodic) ? bnd : nullptr, c->dprm);
+    c->n0 = n; c->nverts = f->nverts;
+    CK(cudaStreamSynchronize(st));   // the caller may reuse its buffers
+    c->have_input = true;
+    return SZ_OK;
+}
+
+static int read_counters(SzContext* c)
+{
+    CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+#define CKS(call) do { int r_ = (call); if (r_ != SZ_OK) return r_; } while (0)
+#define D_CNT(field) ((int*)((char*)c->d_cnt + offsetof(Counters, field)))
+
+// runs the narrow phase over the pairs (wall = 0) or over floe-vs-wall (wall = 1), escalating S -> M -> L
+static int run_narrow(SzContext* c, int wall, int n_work)
+{
+    cudaStream_t st = c->stream;
+    NarrowArgs a; memset(&a, 0, sizeof(a));
+    a.ex = c->ex.p; a.ey = c->ey.p; a.esrc = c->esrc.p;
+    a.h = c->h.p; a.area = c->area.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
+    a.pi = c->pi.p; a.pj = c->pj.p; a.n_work = n_work;
+    a.row_pool = c->row_pool.p; a.row_cap = (int)std::min<size_t>(c->row_pool.cap / 5, 0x7fffffff); a.row_used = D_CNT(row_used);
+    a.P = c->dprm;
+    int* cntM; int* cntL; int* lstM; int* lstL;
+    if (wall) {
+        a.wall = 1; a.first_floe = 0; a.bx = c->bx.p; a.by = c->by.p; a.bn = c->bn; a.bbody = c->bbody;
+        a.status = c->wstatus.p; a.nrows = c->wnrows.p; a.row_start = c->wrow_start.p; a.ovl_state = c->wovl.p;
+        cntM = D_CNT(wlistM); cntL = D_CNT(wlistL); lstM = c->wlistM.p; lstL = c->wlistL.p;
+    } else {
+        a.status = c->pstatus.p; a.nrows = c->pnrows.p; a.row_start = c->prow_start.p; a.ovl_state = c->povl.p;
+        a.want_polys = c->prm.want_clip_polys;
+        a.poly_path_start = c->poly_path_start.p; a.poly_npaths = c->poly_npaths.p; a.path_vstart = c->path_vstart.p; a.path_len = c->path_len.p;
+        a.path_cap = (int)c->path_vstart.cap; a.path_used = D_CNT(path_used); a.pvx = c->pvx.p; a.pvy = c->pvy.p; a.vert_cap = (int)c->pvx.cap; a.vert_used = D_CNT(vert_used);
+        cntM = D_CNT(listM); cntL = D_CNT(listL); lstM = c->listM.p; lstL = c->listL.p;
+    }
+    a.next_list = lstM; a.next_count = cntM;
+    sz_launch_narrow_S(&a, st);
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    int nM = wall ? c->h_cnt->wlistM : c->h_cnt->listM;
+    if (nM > 0) {
+        const int threads = std::min(nM, 148 * 64);
+        CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
+        a.list = lstM; a.list_count = cntM; a.next_list = lstL; a.next_count = cntL; a.scratch = c->scratchM.p; a.n_threads = threads;
+        sz_launch_narrow_M(&a, st);
+        CK(cudaGetLastError());
+        CKS(read_counters(c));
+        int nL = wall ? c->h_cnt->wlistL : c->h_cnt->listL;
+        if (nL > 0) {
+            const int threadsL = std::min(nL, 148 * 8);
+            CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
+            a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
+            sz_launch_narrow_L(&a, st);
+            CK(cudaGetLastError());
+            CKS(read_counters(c));
+        }
+    }
+    return SZ_OK;
+}
+
+extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
+{
+    if (!c) { sz_set_error("sz_step_resident: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_input) { sz_set_error("sz_step_resident: no floes uploaded"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const SzParams& P = c->prm;
+    const int n0 = c->n0, Nb = P.Nb;
+    const int ncap = P.periodic ? 4 * n0 : n0;         // every floe has at most an x-, a y- and an xy-ghost
+    c->have_step = false;
+    CK(cudaEventRecord(c->ev0, st));
+    CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
+
+    // ---- K0: extended list
+    CK(c->ex.ensure(ncap + 1)); CK(c->ey.ensure(ncap + 1)); CK(c->esrc.ensure(ncap + 1)); CK(c->efn.ensure(ncap + 1)); CK(c->eparent.ensure(ncap + 1));
+    CK(c->ealive.ensure(ncap + 1)); CK(c->gx_of.ensure(n0 + 1)); CK(c->gy_of.ensure(n0 + 1));
+    CK(c->flag.ensure(2 * (size_t)n0 + 2)); CK(c->pos.ensure(2 * (size_t)n0 + 2));
+    if (n0 > 0) init_extended_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p, c->gx_of.p, c->gy_of.p);
+    {
+        Counters init; memset(&init, 0, sizeof(init));
+        init.n1 = n0; init.n = n0;
+        init.bbox[0] = enc_d(SZ_INF); init.bbox[1] = enc_d(-SZ_INF); init.bbox[2] = enc_d(SZ_INF); init.bbox[3] = enc_d(-SZ_INF); init.rmax_bits = enc_d(0.0);
+        *c->h_cnt = init;
+        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyHostToDevice, st));
+    }
+    if (P.periodic && n0 > 0) {
+        CK(c->scan_tmp.ensure(scan_tmp_ints(2 * (size_t)n0 + 2)));
+        // x pass over the originals
+        ghost_flag_kernel<<<nblk(n0, 128), 128, 0, st>>>(0, n0, nullptr, c->ex.p, c->esrc.p, c->ealive.p, c->voff.p, c->vx.p, P.Lx, c->flag.p);
+        exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+        ghost_emit_kernel<<<nblk(n0, 256), 256, 0, st>>>(0, n0, nullptr, n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
+                                                         c->gx_of.p, c->gy_of.p, P.Lx, D_CNT(n1));
+        // y pass over originals + x-ghosts (their number is only known on the device: bound 2*n0)
+        ghost_flag_kernel<<<nblk(2 * (i64)n0, 128), 128, 0, st>>>(1, 2 * n0, D_CNT(n1), c->ey.p, c->esrc.p, c->ealive.p, c->voff.p, c->vy.p, P.Ly, c->flag.p);
+        exclusive_scan(c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1, c->scan_tmp.p, st);
+        ghost_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(n1), n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
+                                                                  c->gx_of.p, c->gy_of.p, P.Ly, D_CNT(n));
+    }
+    if (ncap > 0) bbox_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->d_cnt);
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    const int n = c->h_cnt->n; c->n = n; c->n1 = c->h_cnt->n1;
+
+    // ---- K1: cell grid + candidate pairs
+    GridDesc g; g.x0 = g.y0 = 0; g.cell = 1; g.nx = g.ny = 1;
+    {
+        const double rm = dec_d(c->h_cnt->rmax_bits);
+        const double xmn = dec_d(c->h_cnt->bbox[0]), xmx = dec_d(c->h_cnt->bbox[1]), ymn = dec_d(c->h_cnt->bbox[2]), ymx = dec_d(c->h_cnt->bbox[3]);
+        if (xmn <= xmx && std::isfinite(xmn) && std::isfinite(xmx) && std::isfinite(ymn) && std::isfinite(ymx)) {
+            g.x0 = xmn; g.y0 = ymn;
+            double cell = 2 * rm; if (!(cell > 0) || !std::isfinite(cell)) cell = 1;
+            // keep the grid below ~16M cells
+            while ((xmx - xmn) / cell * ((ymx - ymn) / cell) > 1.6e7) cell *= 2;
+            g.cell = cell;
+            g.nx = (int)((xmx - xmn) / cell) + 1; g.ny = (int)((ymx - ymn) / cell) + 1;
+        }
+    }
+    const int ncell = g.nx * g.ny;
+    CK(c->cid.ensure(n + 1)); CK(c->cell_cnt.ensure(ncell + 2)); CK(c->cell_start.ensure(ncell + 2));
+    CK(c->s_idx.ensure(n + 1)); CK(c->s_x.ensure(n + 1)); CK(c->s_y.ensure(n + 1)); CK(c->s_r.ensure(n + 1));
+    CK(c->pcnt.ensure(n + 2)); CK(c->pair_off.ensure(n + 2));
+    CK(c->scan_tmp.ensure(scan_tmp_ints(std::max<size_t>({(size_t)ncell + 2, (size_t)n + 2, 2 * (size_t)n0 + 2}))));
+    CK(cudaMemsetAsync(c->cell_cnt.p, 0, (size_t)(ncell + 1) * 4, st));
+    CK(cudaMemsetAsync(c->pcnt.p, 0, (size_t)(n + 1) * 4, st));
+    BroadArgs b; memset(&b, 0, sizeof(b));
+    if (n > 0) {
+        cell_count_kernel<<<nblk(n, 256), 256, 0, st>>>(n, g, c->ex.p, c->ey.p, c->ealive.p, c->cid.p, c->cell_cnt.p);
+        exclusive_scan(c->cell_cnt.p, ncell, c->cell_start.p, ncell + 1, c->scan_tmp.p, st);
+        CK(cudaMemsetAsync(c->cell_cnt.p, 0, (size_t)(ncell + 1) * 4, st));
+        cell_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->cid.p, c->cell_start.p, c->cell_cnt.p, c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->s_idx.p, c->s_x.p, c->s_y.p, c->s_r.p);
+        b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly);
+        b.ex = c->ex.p; b.ey = c->ey.p; b.esrc = c->esrc.p; b.efn = c->efn.p; b.ealive = c->ealive.p; b.rmax = c->rmax.p;
+        b.cell_start = c->cell_start.p; b.s_idx = c->s_idx.p; b.s_x = c->s_x.p; b.s_y = c->s_y.p; b.s_r = c->s_r.p;
+        b.pcnt = c->pcnt.p; b.pair_off = c->pair_off.p;
+        if (n > Nb) broad_kernel<false><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b);
+    }
+    exclusive_scan(c->pcnt.p, n, c->pair_off.p, n + 1, c->scan_tmp.p, st);
+    CK(cudaMemcpyAsync(D_CNT(n_pairs), c->pair_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    const int np = c->h_cnt->n_pairs; c->n_pairs = np;
+    CK(c->pi.ensure(np + 1)); CK(c->pj.ensure(np + 1)); CK(c->pstatus.ensure(np + 1)); CK(c->pnrows.ensure(np + 1)); CK(c->prow_start.ensure(np + 1)); CK(c->povl.ensure(np + 1));
+    CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
+    if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; broad_kernel<true><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b); }
+
+    // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
+    const bool wall = c->have_bnd && !P.periodic;
+    if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }
+    CK(c->row_pool.ensure(5 * ((size_t)np + (wall ? n : 0) + 256)));
+    if (P.want_clip_polys) {
+        CK(c->poly_path_start.ensure(np + 1)); CK(c->poly_npaths.ensure(np + 1));
+        CK(c->path_vstart.ensure((size_t)np + 256)); CK(c->path_len.ensure(c->path_vstart.cap)); CK(c->pvx.ensure(8 * (size_t)np + 1024)); CK(c->pvy.ensure(c->pvx.cap));
+    }
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        Counters z = *c->h_cnt;
+        z.row_used = z.path_used = z.vert_used = z.listM = z.listL = z.wlistM = z.wlistL = 0;
+        *c->h_cnt = z;
+        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(c->pstatus.p, 0, (size_t)(np + 1) * 4, st)); CK(cudaMemsetAsync(c->pnrows.p, 0, (size_t)(np + 1) * 4, st));
+        if (np > 0) CKS(run_narrow(c, 0, np));
+        if (wall) {
+            // floes below Nb take no part in the wall call (:125 loops i = 1+Nb:N)
+            CK(cudaMemsetAsync(c->wstatus.p, 0, (size_t)(n + 1) * 4, st)); CK(cudaMemsetAsync(c->wnrows.p, 0, (size_t)(n + 1) * 4, st));
+            if (n > 0) CKS(run_narrow(c, 1, n));
+        }
+        CKS(read_counters(c));
+        bool again = false;
+        if ((size_t)c->h_cnt->row_used * 5 > c->row_pool.cap) { CK(c->row_pool.ensure((size_t)c->h_cnt->row_used * 5 + 1024)); again = true; }
+        if (P.want_clip_polys) {
+            if ((size_t)c->h_cnt->path_used > c->path_vstart.cap) { CK(c->path_vstart.ensure(c->h_cnt->path_used + 64)); CK(c->path_len.ensure(c->path_vstart.cap)); again = true; }
+            if ((size_t)c->h_cnt->vert_used > c->pvx.cap) { CK(c->pvx.ensure(c->h_cnt->vert_used + 64)); CK(c->pvy.ensure(c->pvx.cap)); again = true; }
+        }
+        if (!again) break;
+        if (attempt == 2) { sz_set_error("sz_step_resident: result pools kept overflowing"); return SZ_ERR_CAPACITY; }
+    }
+
+    // ---- K4: mirror, rows, sums
+    CK(c->tcnt.ensure(n + 2)); CK(c->toff.ensure(n + 2)); CK(c->tlist.ensure(np + 1)); CK(c->rcnt.ensure(n + 2)); CK(c->row_off.ensure(n + 2));
+    CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
+    if (np > 0) tcount_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->tcnt.p);
+    exclusive_scan(c->tcnt.p, n, c->toff.p, n + 1, c->scan_tmp.p, st);
+    CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
+    if (np > 0) tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p);
+    if (n > 0) rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p);
+    exclusive_scan(c->rcnt.p, n, c->row_off.p, n + 1, c->scan_tmp.p, st);
+    CK(cudaMemcpyAsync(D_CNT(total_rows), c->row_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    const i64 nrows = c->h_cnt->total_rows; c->n_rows = nrows;
+    CK(c->rows.ensure((size_t)nrows * 7 + 7)); CK(c->osum.ensure((size_t)n * 3 + 3)); CK(c->has_rows.ensure(n + 1));
+    CK(c->kill_i.ensure(n + 1)); CK(c->transfer_i.ensure(n + 1)); CK(c->tmax.ensure(n0 + 1));
+    CK(c->o_fx.ensure(n0 + 1)); CK(c->o_fy.ensure(n0 + 1)); CK(c->o_tq.ensure(n0 + 1)); CK(c->o_ov.ensure(n0 + 1)); CK(c->o_stress.ensure(4 * (size_t)n0 + 4));
+    CK(c->o_xi.ensure(n0 + 1)); CK(c->o_yi.ensure(n0 + 1)); CK(c->o_alive.ensure(n0 + 1)); CK(c->o_kill.ensure(n0 + 1)); CK(c->o_transfer.ensure(n0 + 1));
+    if (n > 0) {
+        AssembleArgs a; memset(&a, 0, sizeof(a));
+        a.n = n; a.n0 = n0; a.Nb = Nb; a.periodic = P.periodic; a.wall = wall; a.Lx = P.Lx; a.Ly = P.Ly;
+        a.ex = c->ex.p; a.ey = c->ey.p; a.esrc = c->esrc.p; a.ealive = c->ealive.p; a.area = c->area.p; a.h = c->h.p;
+        a.pair_off = c->pair_off.p; a.pi = c->pi.p; a.pj = c->pj.p; a.nrows = c->pnrows.p; a.row_start = c->prow_start.p; a.ovl = c->povl.p; a.pstatus = c->pstatus.p;
+        a.wnrows = c->wnrows.p; a.wrow_start = c->wrow_start.p; a.wstatus = c->wstatus.p;
+        a.toff = c->toff.p; a.tlist = c->tlist.p; a.row_off = c->row_off.p; a.pool = c->row_pool.p;
+        a.boxx = c->boxx.p; a.boxy = c->boxy.p; a.boxn = c->boxn;
+        a.rows = c->rows.p; a.osum = c->osum.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
+        a.o_ov = c->o_ov.p; a.o_stress = c->o_stress.p; a.o_xi = c->o_xi.p; a.o_yi = c->o_yi.p; a.o_alive = c->o_alive.p; a.cnt = c->d_cnt;
+        assemble_kernel<<<nblk(n, 128), 128, 0, st>>>(a);
+        CK(cudaMemsetAsync(c->tmax.p, 0, (size_t)(n0 + 1) * 4, st));
+        kill_mark_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->kill_i.p, c->tmax.p);
+        if (n0 > 0) {
+            kill_final_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->kill_i.p, c->transfer_i.p, c->tmax.p, c->o_kill.p, c->o_transfer.p);
+            fold_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, Nb, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p);
+        }
+        if (np > 0) pair_stats_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, 1, c->d_cnt);
+        if (wall) pair_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, 0, c->d_cnt);
+    }
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+
+    SzSummary& s = c->summary; memset(&s, 0, sizeof(s));
+    s.n0 = n0; s.n = n; s.n_pairs = np; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows;
+    s.n_clip_paths = P.want_clip_polys ? c->h_cnt->path_used : 0; s.n_clip_verts = P.want_clip_polys ? c->h_cnt->vert_used : 0;
+    s.collision_count = (double)c->h_cnt->n_fin_rows / 2 + (double)c->h_cnt->n_inf_rows;   // calc_collisionNum.m:6
+    s.n_clipper_fail = c->h_cnt->n_fail; s.n_capacity_fail = c->h_cnt->n_cap_fail; s.ms_device = ms;
+    c->have_step = true;
+    if (out) *out = s;
+    if (s.n_capacity_fail > 0) { sz_set_error("%d pair(s) exceed the largest narrow-phase size class (1299 vertices per outline)", s.n_capacity_fail); return SZ_ERR_CAPACITY; }
+    if (s.n_clipper_fail > 0) { sz_set_error("Clipper Error. (%d pair(s); per-pair status via sz_get_pairs)", s.n_clipper_fail); return SZ_ERR_CLIPPER; }
+    return SZ_OK;
+}
+
+extern "C" int sz_contact_step(SzContext* c, const SzParams* prm, const SzFloesSoA* f, const SzBoundary* bnd, SzSummary* out)
+{
+    int r = sz_upload(c, prm, f, bnd);
+    if (r != SZ_OK) return r;
+    return sz_step_resident(c, out);
+}
+
+// ------------------------------------------------------------------------------------------------ getters
+#define NEED_STEP(name) do { if (!c) { sz_set_error(name ": NULL context"); return SZ_ERR_ARG; } \
+    if (!c->have_step) { sz_set_error(name ": no step has been run"); return SZ_ERR_STATE; } CK(cudaSetDevice(c->device)); } while (0)
+#define D2H(dst, src, bytes) do { if ((dst) && (bytes) > 0) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, c->stream)); } while (0)
+
+extern "C" int sz_get_floe_outputs(SzContext* c, double* fx, double* fy, double* torque, double* overlap_area, double* stress,
+                                   double* xi, double* yi, uint8_t* alive, int32_t* kill, int32_t* transfer)
+{
+    NEED_STEP("sz_get_floe_outputs");
+    const size_t n = (size_t)c->n0;
+    D2H(fx, c->o_fx.p, n * 8); D2H(fy, c->o_fy.p, n * 8); D2H(torque, c->o_tq.p, n * 8); D2H(overlap_area, c->o_ov.p, n * 8);
+    D2H(stress, c->o_stress.p, n * 32); D2H(xi, c->o_xi.p, n * 8); D2H(yi, c->o_yi.p, n * 8); D2H(alive, c->o_alive.p, n);
+    D2H(kill, c->o_kill.p, n * 4); D2H(transfer, c->o_transfer.p, n * 4);
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+extern "C" int sz_get_ghosts(SzContext* c, int32_t* parent, int32_t* floe_num, double* gx, double* gy)
+{
+    NEED_STEP("sz_get_ghosts");
+    const size_t g = (size_t)(c->n - c->n0); const int n0 = c->n0;
+    D2H(parent, c->eparent.p + n0, g * 4); D2H(floe_num, c->efn.p + n0, g * 4); D2H(gx, c->ex.p + n0, g * 8); D2H(gy, c->ey.p + n0, g * 8);
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+extern "C" int sz_get_pairs(SzContext* c, int32_t* pi, int32_t* pj, double* overlap_state, int32_t* n_regions, int32_t* status)
+{
+    NEED_STEP("sz_get_pairs");
+    const size_t np = (size_t)c->n_pairs;
+    D2H(pi, c->pi.p, np * 4); D2H(pj, c->pj.p, np * 4); D2H(overlap_state, c->povl.p, np * 8); D2H(n_regions, c->pnrows.p, np * 4); D2H(status, c->pstatus.p, np * 4);
+    CK(cudaStreamSynchronize(c->stream));
+    if (pi) for (size_t k = 0; k < np; ++k) pi[k] += 1;      // 1-based, like Floe(i).potentialInteractions(k).floeNum
+    if (pj) for (size_t k = 0; k < np; ++k) pj[k] += 1;
+    if (overlap_state && status) for (size_t k = 0; k < np; ++k) if (status[k] != 0) overlap_state[k] = 0;
+    return SZ_OK;
+}
+extern "C" int sz_get_rows(SzContext* c, int64_t* row_off, double* rows)
+{
+    NEED_STEP("sz_get_rows");
+    const int n = c->n;
+    if (row_off) {
+        std::vector<int> tmp(n + 1);
+        CK(cudaMemcpyAsync(tmp.data(), c->row_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k <= n; ++k) row_off[k] = tmp[k];
+    }
+    D2H(rows, c->rows.p, (size_t)c->n_rows * 56);
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+// reorder (start, count) pools into item-major CSR
+static int export_paths(SzContext* c, int n_items, const int* d_item_start, const int* d_item_np, const int* d_status, const int* d_path_vstart, const int* d_path_len,
+                        int n_pool_paths, const i64* d_px, const i64* d_py, int n_pool_verts,
+                        int64_t* item_path_off, int64_t* path_vert_off, int64_t* ox, int64_t* oy)
+{
+    std::vector<int> is(n_items), in(n_items), stt(n_items, 0), pvs(n_pool_paths), pln(n_pool_paths);
+    std::vector<i64> px(n_pool_verts), py(n_pool_verts);
+    cudaStream_t st = c->stream;
+    if (n_items) { CK(cudaMemcpyAsync(is.data(), d_item_start, (size_t)n_items * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(in.data(), d_item_np, (size_t)n_items * 4, cudaMemcpyDeviceToHost, st));
+                   if (d_status) CK(cudaMemcpyAsync(stt.data(), d_status, (size_t)n_items * 4, cudaMemcpyDeviceToHost, st)); }
+    if (n_pool_paths) { CK(cudaMemcpyAsync(pvs.data(), d_path_vstart, (size_t)n_pool_paths * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(pln.data(), d_path_len, (size_t)n_pool_paths * 4, cudaMemcpyDeviceToHost, st)); }
+    if (n_pool_verts) { CK(cudaMemcpyAsync(px.data(), d_px, (size_t)n_pool_verts * 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(py.data(), d_py, (size_t)n_pool_verts * 8, cudaMemcpyDeviceToHost, st)); }
+    CK(cudaStreamSynchronize(st));
+    i64 np = 0, nv = 0;
+    if (item_path_off) item_path_off[0] = 0;
+    if (path_vert_off) path_vert_off[0] = 0;
+    for (int k = 0; k < n_items; ++k) {
+        const int cnt = (stt[k] == 0) ? in[k] : 0;
+        for (int q = 0; q < cnt; ++q) {
+            const int pp = is[k] + q;
+            for (int t = 0; t < pln[pp]; ++t) { if (ox) ox[nv] = px[pvs[pp] + t]; if (oy) oy[nv] = py[pvs[pp] + t]; ++nv; }
+            ++np;
+            if (path_vert_off) path_vert_off[np] = nv;
+        }
+        if (item_path_off) item_path_off[k + 1] = np;
+    }
+    return SZ_OK;
+}
+extern "C" int sz_get_clip_polys(SzContext* c, int64_t* pair_path_off, int64_t* path_vert_off, int64_t* x, int64_t* y)
+{
+    NEED_STEP("sz_get_clip_polys");
+    if (!c->prm.want_clip_polys) { sz_set_error("sz_get_clip_polys: the step was run without want_clip_polys"); return SZ_ERR_STATE; }
+    return export_paths(c, c->n_pairs, c->poly_path_start.p, c->poly_npaths.p, c->pstatus.p, c->path_vstart.p, c->path_len.p, (int)c->summary.n_clip_paths,
+                        c->pvx.p, c->pvy.p, (int)c->summary.n_clip_verts, pair_path_off, path_vert_off, x, y);
+}
+
+// ------------------------------------------------------------------------------------------------ clip batch
+extern "C" int sz_clip_batch(SzContext* c, int32_t count, const int32_t* method, const int64_t* soff, const int64_t* sx, const int64_t* sy,
+                             const int64_t* coff, const int64_t* cx, const int64_t* cy, int64_t* n_paths, int64_t* n_verts)
+{
+    if (!c || count < 0 || (count > 0 && (!method || !soff || !coff || !sx || !sy || !cx || !cy))) { sz_set_error("sz_clip_batch: bad arguments"); return SZ_ERR_ARG; }
+    for (int k = 0; k < count; ++k) {
+        if (method[k] < 0 || method[k] > 3) { sz_set_error("sz_clip_batch: method must be 0..3 (mexclipper.cpp:206-230)"); return SZ_ERR_ARG; }
+        if (soff[k + 1] < soff[k] || coff[k + 1] < coff[k]) { sz_set_error("sz_clip_batch: offsets must be non-decreasing"); return SZ_ERR_ARG; }
+    }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    c->clip_count = -1;
+    const size_t ns = count ? (size_t)soff[count] : 0, nc = count ? (size_t)coff[count] : 0;
+    CK(c->c_method.ensure(count + 1)); CK(c->c_status.ensure(count + 1)); CK(c->c_path_start.ensure(count + 1)); CK(c->c_npaths.ensure(count + 1));
+    CK(c->c_listM.ensure(count + 1)); CK(c->c_listL.ensure(count + 1));
+    CK(c->c_soff.ensure(count + 2)); CK(c->c_coff.ensure(count + 2)); CK(c->c_sx.ensure(ns + 1)); CK(c->c_sy.ensure(ns + 1)); CK(c->c_cx.ensure(nc + 1)); CK(c->c_cy.ensure(nc + 1));
+    if (count > 0) {
+        CK(cudaMemcpyAsync(c->c_method.p, method, (size_t)count * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->c_soff.p, soff, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->c_coff.p, coff, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (ns) { CK(cudaMemcpyAsync(c->c_sx.p, sx, ns * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->c_sy.p, sy, ns * 8, cudaMemcpyHostToDevice, st)); }
+        if (nc) { CK(cudaMemcpyAsync(c->c_cx.p, cx, nc * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->c_cy.p, cy, nc * 8, cudaMemcpyHostToDevice, st)); }
+    }
+    CK(c->c_path_vstart.ensure((size_t)count * 2 + 64)); CK(c->c_path_len.ensure(c->c_path_vstart.cap));
+    CK(c->c_pvx.ensure(ns + nc + 1024)); CK(c->c_pvy.ensure(c->c_pvx.cap));
+    for (int attempt = 0; attempt < 3 && count > 0; ++attempt) {
+        CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
+        CK(cudaMemsetAsync(c->c_status.p, 0, (size_t)count * 4, st)); CK(cudaMemsetAsync(c->c_npaths.p, 0, (size_t)count * 4, st));
+        ClipArgs a; memset(&a, 0, sizeof(a));
+        a.count = count; a.method = c->c_method.p; a.soff = c->c_soff.p; a.sx = c->c_sx.p; a.sy = c->c_sy.p; a.coff = c->c_coff.p; a.cx = c->c_cx.p; a.cy = c->c_cy.p;
+        a.status = c->c_status.p; a.item_path_start = c->c_path_start.p; a.item_npaths = c->c_npaths.p;
+        a.path_vstart = c->c_path_vstart.p; a.path_len = c->c_path_len.p; a.path_cap = (int)c->c_path_vstart.cap; a.path_used = D_CNT(clip_path_used);
+        a.pvx = c->c_pvx.p; a.pvy = c->c_pvy.p; a.vert_cap = (int)c->c_pvx.cap; a.vert_used = D_CNT(clip_vert_used);
+        a.next_list = c->c_listM.p; a.next_count = D_CNT(clip_listM);
+        sz_launch_clip_S(&a, st);
+        CK(cudaGetLastError());
+        CKS(read_counters(c));
+        if (c->h_cnt->clip_listM > 0) {
+            const int threads = std::min(c->h_cnt->clip_listM, 148 * 64);
+            CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
+            a.list = c->c_listM.p; a.list_count = D_CNT(clip_listM); a.next_list = c->c_listL.p; a.next_count = D_CNT(clip_listL); a.scratch = c->scratchM.p; a.n_threads = threads;
+            sz_launch_clip_M(&a, st);
+            CK(cudaGetLastError());
+            CKS(read_counters(c));
+            if (c->h_cnt->clip_listL > 0) {
+                const int threadsL = std::min(c->h_cnt->clip_listL, 148 * 8);
+                CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
+                a.list = c->c_listL.p; a.list_count = D_CNT(clip_listL); a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
+                sz_launch_clip_L(&a, st);
+                CK(cudaGetLastError());
+                CKS(read_counters(c));
+            }
+        }
+        bool again = false;
+        if ((size_t)c->h_cnt->clip_path_used > c->c_path_vstart.cap) { CK(c->c_path_vstart.ensure(c->h_cnt->clip_path_used + 64)); CK(c->c_path_len.ensure(c->c_path_vstart.cap)); again = true; }
+        if ((size_t)c->h_cnt->clip_vert_used > c->c_pvx.cap) { CK(c->c_pvx.ensure(c->h_cnt->clip_vert_used + 64)); CK(c->c_pvy.ensure(c->c_pvx.cap)); again = true; }
+        if (!again) break;
+        if (attempt == 2) { sz_set_error("sz_clip_batch: result pools kept overflowing"); return SZ_ERR_CAPACITY; }
+    }
+    c->clip_count = count;
+    c->clip_paths = count ? c->h_cnt->clip_path_used : 0; c->clip_verts = count ? c->h_cnt->clip_vert_used : 0;
+    if (n_paths) *n_paths = c->clip_paths;
+    if (n_verts) *n_verts = c->clip_verts;
+    return SZ_OK;
+}
+extern "C" int sz_get_clip_batch(SzContext* c, int32_t* status, int64_t* item_path_off, int64_t* path_vert_off, int64_t* ox, int64_t* oy)
+{
+    if (!c) { sz_set_error("sz_get_clip_batch: NULL context"); return SZ_ERR_ARG; }
+    if (c->clip_count < 0) { sz_set_error("sz_get_clip_batch: no clip batch has been run"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    if (status && c->clip_count > 0) { CK(cudaMemcpyAsync(status, c->c_status.p, (size_t)c->clip_count * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    return export_paths(c, c->clip_count, c->c_path_start.p, c->c_npaths.p, c->c_status.p, c->c_path_vstart.p, c->c_path_len.p, (int)c->clip_paths,
+                        c->c_pvx.p, c->c_pvy.p, (int)c->clip_verts, item_path_off, path_vert_off, ox, oy);
+}

@@ -1,0 +1,220 @@
+// sz_narrow.cuh -- narrow-phase kernels: one CUDA thread resolves one candidate pair
+// (collisions/floe_interactions.m, reached from floe_interactions_all.m:125-172) or one stand-alone
+// polygon clip (private/mexclipper.cpp:291-298) with the Clipper-exact sweep of sz_clip.cuh.
+//
+// Size classes.  The sweep needs a per-pair arena whose size depends on the vertex counts, so pairs
+// run in three classes; a pair that does not fit (too many vertices, or an arena overflowed during
+// the sweep) is appended to the next class's work list and re-run there from scratch:
+//   class S  <= 19 vertices per outline     arena in per-thread local memory (interleaved by the
+//            (packed Voronoi: 3..13)        hardware, so lanes running the same sweep step touch
+//                                           the same sectors), one thread per pair, grid = all pairs
+//   class M  <= 191 vertices                arena in an HBM scratch slab, persistent threads that
+//   class L  <= 1299 vertices               stride over the work list
+// Each class is instantiated in its own translation unit (sz_narrow_{S,M,L}.cu) so the three
+// ~40 s template instantiations build in parallel; sz_contact.cu calls the extern "C" launchers.
+#pragma once
+#include "sz_pairforce.cuh"
+#include <cuda_runtime.h>
+
+namespace sznarrow {
+
+using szpf::Params;
+using szpf::Body;
+using szclip::i64;
+using szclip::P64;
+
+typedef szclip::ClipCaps<40, 20, 112, 32, 64, 32, 16, 56> ClipS;
+typedef szpf::PairCaps<ClipS, 20, 64, 6, 40, 4> PairS;
+typedef szclip::ClipCaps<384, 192, 1536, 256, 1536, 256, 128, 448> ClipM;
+typedef szpf::PairCaps<ClipM, 192, 768, 16, 512, 16> PairM;
+typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3000> ClipL;
+typedef szpf::PairCaps<ClipL, 1300, 5200, 64, 6000, 32> PairL;
+
+// Everything a narrow-phase launch reads and writes.  Indices are 0-based positions in the extended
+// floe list (originals, x-ghosts, y-ghosts); `src` maps a position to the original floe whose
+// outline and body fields it shares (a ghost is its parent with a shifted centroid,
+// floe_interactions_all.m:33-34,54-55).
+struct NarrowArgs {
+    // extended list
+    const double* ex; const double* ey; const int* esrc;
+    // per original floe
+    const double* h; const double* area; const double* u; const double* v; const double* ksi;
+    const int* voff; const double* vx; const double* vy;
+    // work: pair k = (pi[k], pj[k]); in wall mode "pair" k is floe first_floe + k against the boundary
+    const int* pi; const int* pj;
+    int n_work;                    // class S: number of pairs; M/L: unused (list_count is read on the device)
+    const int* list; const int* list_count;      // M/L work list (pair indices)
+    int* next_list; int* next_count;              // escalation target (NULL in class L)
+    // per-pair outputs
+    int* status; int* nrows; int* row_start; double* ovl_state;
+    // contact-row pool: 5 doubles per row (Fx Fy Px Py overlap), allocated with one atomicAdd per pair
+    double* row_pool; int row_cap; int* row_used;
+    // optional clip #1 polygons (Clipper coordinates) for bit-exact parity checks
+    int want_polys; int* poly_path_start; int* poly_npaths;
+    int* path_vstart; int* path_len; int path_cap; int* path_used;
+    i64* pvx; i64* pvy; int vert_cap; int* vert_used;
+    // wall mode (floe_interactions_all.m:150-172)
+    int wall; int first_floe; const double* bx; const double* by; int bn; Body bbody;
+    void* scratch; int n_threads;  // M/L arenas: n_threads * sizeof(Workspace<C>)
+    Params P;
+};
+
+// Stand-alone clip batch (mex gateway semantics): item k clips subject [soff[k],soff[k+1]) with clip
+// [coff[k],coff[k+1]) using method[k]; result paths go to the pools.
+struct ClipArgs {
+    int count; const int* method;
+    const i64* soff; const i64* sx; const i64* sy;
+    const i64* coff; const i64* cx; const i64* cy;
+    const int* list; const int* list_count; int* next_list; int* next_count;
+    int* status; int* item_path_start; int* item_npaths;
+    int* path_vstart; int* path_len; int path_cap; int* path_used;
+    i64* pvx; i64* pvy; int vert_cap; int* vert_used;
+    void* scratch; int n_threads;
+};
+
+struct PtrGetter { const i64* x; const i64* y; SZ_HD P64 operator()(int i) const { P64 p; p.x = x[i]; p.y = y[i]; return p; } };
+
+// sink that stores emitted paths straight into the global pools (space reserved beforehand)
+struct PoolSink {
+    i64* x; i64* y; int* vstart; int* len; int path; int vert;
+    SZ_HD void begin_path(int cnt) { vstart[path] = vert; len[path] = cnt; ++path; }
+    SZ_HD void point(P64 p) { x[vert] = p.x; y[vert] = p.y; ++vert; }
+};
+struct SizeSink { int paths, verts; SZ_HD void begin_path(int c) { ++paths; verts += c; } SZ_HD void point(P64) {} };
+
+#if defined(__CUDACC__)
+
+template <class C>
+__device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, szpf::Workspace<C>& w)
+{
+    int i, j = -1;
+    Body b1, b2;
+    if (a.wall && k < a.P.Nb) return;     // floes below Nb take no part in the pair loop (floe_interactions_all.m:125)
+    if (a.wall) { i = a.first_floe + k; b2 = a.bbody; }
+    else { i = a.pi[k]; j = a.pj[k]; }
+    const int si = a.esrc[i];
+    const int o1 = a.voff[si], n1 = a.voff[si + 1] - o1;
+    int o2 = 0, n2 = a.bn, sj = 0;
+    if (!a.wall) { sj = a.esrc[j]; o2 = a.voff[sj]; n2 = a.voff[sj + 1] - o2; }
+    // + 1: room for the closing vertex of floe_interactions.m:62-67
+    if (n1 + 1 > C::NV || n2 + 1 > C::NV || n1 < 1 || n2 < 1) {
+        if (n1 >= 1 && n2 >= 1 && a.next_list) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
+        else { a.status[k] = (n1 < 1 || n2 < 1) ? szpf::PS_BAD_POLY : szpf::PS_CAPACITY; a.nrows[k] = 0; a.ovl_state[k] = 0; }
+        return;
+    }
+    b1.h = a.h[si]; b1.area = a.area[si]; b1.Xi = a.ex[i]; b1.Yi = a.ey[i]; b1.Ui = a.u[si]; b1.Vi = a.v[si]; b1.ksi = a.ksi[si];
+    w.n1 = n1; w.n2 = n2;
+    for (int t = 0; t < n1; ++t) { w.c1x[t] = a.vx[o1 + t] + b1.Xi; w.c1y[t] = a.vy[o1 + t] + b1.Yi; }       // floe_interactions.m:25
+    if (a.wall) { for (int t = 0; t < n2; ++t) { w.c2x[t] = a.bx[t]; w.c2y[t] = a.by[t]; } }                    // :31-32
+    else {
+        b2.h = a.h[sj]; b2.area = a.area[sj]; b2.Xi = a.ex[j]; b2.Yi = a.ey[j]; b2.Ui = a.u[sj]; b2.Vi = a.v[sj]; b2.ksi = a.ksi[sj];
+        for (int t = 0; t < n2; ++t) { w.c2x[t] = a.vx[o2 + t] + b2.Xi; w.c2y[t] = a.vy[o2 + t] + b2.Yi; }    // floe_interactions_all.m:105
+    }
+    szpf::PairResult res;
+    double rows[C::ROWS * 5];
+    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows);
+    if (res.status == szpf::PS_CAPACITY && a.next_list) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; return; }
+    a.status[k] = res.status; a.ovl_state[k] = res.overlap_state;
+    int nr = (res.status == szpf::PS_OK) ? res.n_rows : 0;
+    a.nrows[k] = nr;
+    if (nr > 0) {
+        int s = atomicAdd(a.row_used, nr);
+        a.row_start[k] = s;
+        if (s + nr <= a.row_cap) for (int t = 0; t < nr * 5; ++t) a.row_pool[(size_t)s * 5 + t] = rows[t];
+    }
+    if (a.want_polys) {
+        int np = (res.status == szpf::PS_OK) ? w.ra_n : 0;
+        a.poly_npaths[k] = np;
+        if (np > 0) {
+            const int nv = w.ra_off[np];
+            int ps = atomicAdd(a.path_used, np), vs = atomicAdd(a.vert_used, nv);
+            a.poly_path_start[k] = ps;
+            if (ps + np <= a.path_cap && vs + nv <= a.vert_cap) {
+                for (int q = 0; q < np; ++q) { a.path_vstart[ps + q] = vs + w.ra_off[q]; a.path_len[ps + q] = w.ra_off[q + 1] - w.ra_off[q]; }
+                for (int t = 0; t < nv; ++t) { a.pvx[vs + t] = w.rax[t]; a.pvy[vs + t] = w.ray[t]; }
+            }
+        }
+    }
+}
+
+// class S: arena in local memory, one thread per pair
+template <class C>
+__global__ void __launch_bounds__(128) narrow_local_kernel(const NarrowArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_work) return;
+    szpf::Workspace<C> w;
+    resolve_pair<C>(a, k, w);
+}
+
+// classes M/L: arena in HBM scratch, persistent threads striding over the work list
+template <class C>
+__global__ void __launch_bounds__(64) narrow_scratch_kernel(const NarrowArgs a)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= a.n_threads) return;
+    szpf::Workspace<C>& w = reinterpret_cast<szpf::Workspace<C>*>(a.scratch)[tid];
+    const int n = *a.list_count;
+    for (int t = tid; t < n; t += a.n_threads) resolve_pair<C>(a, a.list[t], w);
+}
+
+template <class CC>
+__device__ __forceinline__ void resolve_clip(const ClipArgs& a, int k, szclip::ClipEngine<CC>& eng)
+{
+    const i64 s0 = a.soff[k], c0 = a.coff[k];
+    const int ns = (int)(a.soff[k + 1] - s0), nc = (int)(a.coff[k + 1] - c0);
+    eng.begin(a.method[k]);
+    PtrGetter gs{a.sx + s0, a.sy + s0}, gc{a.cx + c0, a.cy + c0};
+    eng.add_path(gs, ns, 0);
+    eng.add_path(gc, nc, 1);
+    int st = eng.execute();
+    if (st == szclip::ST_OVERFLOW) {
+        if (a.next_list) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
+        else { a.status[k] = szpf::PS_CAPACITY; a.item_npaths[k] = 0; }
+        return;
+    }
+    if (st != szclip::ST_OK) { a.status[k] = szpf::PS_CLIPPER_FAIL; a.item_npaths[k] = 0; return; }
+    SizeSink sz; sz.paths = 0; sz.verts = 0;
+    eng.emit(sz);
+    a.status[k] = 0; a.item_npaths[k] = sz.paths;
+    if (sz.paths > 0) {
+        int ps = atomicAdd(a.path_used, sz.paths), vs = atomicAdd(a.vert_used, sz.verts);
+        a.item_path_start[k] = ps;
+        if (ps + sz.paths <= a.path_cap && vs + sz.verts <= a.vert_cap) {
+            PoolSink sink{a.pvx, a.pvy, a.path_vstart, a.path_len, ps, vs};
+            eng.emit(sink);
+        }
+    }
+}
+template <class CC>
+__global__ void __launch_bounds__(128) clip_local_kernel(const ClipArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.count) return;
+    szclip::ClipEngine<CC> eng;
+    resolve_clip<CC>(a, k, eng);
+}
+template <class C>
+__global__ void __launch_bounds__(64) clip_scratch_kernel(const ClipArgs a)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= a.n_threads) return;
+    szpf::Workspace<C>& w = reinterpret_cast<szpf::Workspace<C>*>(a.scratch)[tid];
+    const int n = *a.list_count;
+    for (int t = tid; t < n; t += a.n_threads) resolve_clip<typename C::Clip>(a, a.list[t], w.eng);
+}
+#endif  // __CUDACC__
+
+}  // namespace sznarrow
+
+// launchers (one translation unit per class); all asynchronous on `stream`
+extern "C" {
+void sz_launch_narrow_S(const sznarrow::NarrowArgs* a, cudaStream_t stream);
+void sz_launch_narrow_M(const sznarrow::NarrowArgs* a, cudaStream_t stream);
+void sz_launch_narrow_L(const sznarrow::NarrowArgs* a, cudaStream_t stream);
+void sz_launch_clip_S(const sznarrow::ClipArgs* a, cudaStream_t stream);
+void sz_launch_clip_M(const sznarrow::ClipArgs* a, cudaStream_t stream);
+void sz_launch_clip_L(const sznarrow::ClipArgs* a, cudaStream_t stream);
+size_t sz_workspace_bytes_M(void);
+size_t sz_workspace_bytes_L(void);
+}

@@ -1,0 +1,225 @@
+"""ctypes binding of the CPU checker oracle/_ref/libsz_oracle.so (TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from subzero_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "_ref", "libsz_oracle.so")
+CLIPPER_LIB = os.path.join(ORACLE_DIR, "_ref", "libclipper_ref.so")
+REFERENCE = "/root/reference"
+
+_lib = None
+_clip = None
+
+
+def build_if_possible():
+    """(Re)build the checker when the reference sources are present (build container); on the GPU box the
+    prebuilt files travel with the snapshot."""
+    if os.path.isdir(os.path.join(REFERENCE, "private")):
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    if not os.path.exists(LIB):
+        raise RuntimeError("oracle library %s missing and /root/reference not available to build it" % LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_if_possible()
+        l = C.CDLL(LIB)
+        l.szo_contact_step.restype = C.c_void_p
+        l.szo_contact_step.argtypes = [C.POINTER(abi.SzParams), C.POINTER(abi.SzFloesSoA), C.POINTER(abi.SzBoundary), C.c_int, C.c_int]
+        l.szo_free.argtypes = [C.c_void_p]
+        l.szo_error.restype = C.c_char_p
+        l.szo_error.argtypes = [C.c_void_p]
+        l.szo_summary.argtypes = [C.c_void_p, C.POINTER(abi.SzSummary)]
+        l.szo_get_floe_outputs.argtypes = [C.c_void_p] + [abi.c_dp] * 7 + [abi.c_bp, abi.c_ip, abi.c_ip]
+        l.szo_get_ghosts.argtypes = [C.c_void_p, abi.c_ip, abi.c_ip, abi.c_dp, abi.c_dp]
+        l.szo_get_pairs.argtypes = [C.c_void_p, abi.c_ip, abi.c_ip, abi.c_dp, abi.c_ip, abi.c_ip]
+        l.szo_get_rows.argtypes = [C.c_void_p, abi.c_lp, abi.c_dp]
+        l.szo_get_clip_polys.argtypes = [C.c_void_p, abi.c_lp, abi.c_lp, abi.c_lp, abi.c_lp]
+        l.szo_polyclip.restype = C.c_int
+        l.szo_polyclip.argtypes = [abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, C.c_int, C.c_int, abi.c_dp, abi.c_dp, C.c_int, abi.c_ip, C.c_int]
+        l.szo_polyshape_area_centroid.argtypes = [abi.c_dp, abi.c_dp, C.c_int, abi.c_dp]
+        l.szo_polyarea.restype = C.c_double
+        l.szo_polyarea.argtypes = [abi.c_dp, abi.c_dp, C.c_int]
+        l.szo_interx.restype = C.c_int
+        l.szo_interx.argtypes = [abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, C.c_int]
+        l.szo_inpolygon.argtypes = [abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, C.c_int, abi.c_bp]
+        l.szo_p_poly_dist.restype = C.c_int
+        l.szo_p_poly_dist.argtypes = [abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, C.c_int, abi.c_dp]
+        l.szo_matlab_int64.restype = C.c_int64
+        l.szo_matlab_int64.argtypes = [C.c_double]
+        l.szo_floe_interactions.restype = C.c_int
+        l.szo_floe_interactions.argtypes = [C.POINTER(abi.SzParams), abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, C.c_int,
+                                            abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, C.c_int, abi.c_dp]
+        l.szo_hardware_threads.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def clipper():
+    """the UNMODIFIED reference Clipper 6.4.2 behind oracle/clipper_ref_shim.cpp"""
+    global _clip
+    if _clip is None:
+        lib()
+        l = C.CDLL(CLIPPER_LIB)
+        l.szref_clip.restype = C.c_int
+        l.szref_clip.argtypes = [abi.c_lp, abi.c_lp, C.c_int, abi.c_lp, abi.c_lp, C.c_int, C.c_int, abi.c_lp, abi.c_lp, C.c_int, abi.c_ip, C.c_int]
+        _clip = l
+    return _clip
+
+
+def ref_clip(subj, clip, method):
+    """reference Clipper on (n,2) int64 arrays -> list of (m,2) int64 paths, or None on 'Clipper Error.'"""
+    s = np.ascontiguousarray(subj, np.int64).reshape(-1, 2)
+    c = np.ascontiguousarray(clip, np.int64).reshape(-1, 2)
+    sx, sy, cx, cy = (np.ascontiguousarray(a) for a in (s[:, 0], s[:, 1], c[:, 0], c[:, 1]))
+    cap = 4 * (len(s) + len(c)) + 64
+    while True:
+        ox, oy, off = np.empty(cap, np.int64), np.empty(cap, np.int64), np.empty(cap, np.int32)
+        p = abi._ptr
+        n = clipper().szref_clip(p(sx, abi.c_lp), p(sy, abi.c_lp), len(s), p(cx, abi.c_lp), p(cy, abi.c_lp), len(c), int(method),
+                                 p(ox, abi.c_lp), p(oy, abi.c_lp), cap, p(off, abi.c_ip), cap)
+        if n == -2:
+            cap *= 4
+            continue
+        break
+    if n < 0:
+        return None
+    return [np.stack([ox[off[k]:off[k + 1]], oy[off[k]:off[k + 1]]], 1) for k in range(n)]
+
+
+class OracleStep:
+    """One run of the oracle's floe_interactions_all restatement; same getters as ContactContext."""
+
+    def __init__(self, prm, floes, boundary=None, nthreads=None, broad_mode=0):
+        l = lib()
+        fs = floes.struct()
+        bs = boundary.struct() if boundary is not None else None
+        if nthreads is None:
+            nthreads = max(1, l.szo_hardware_threads())
+        self._r = l.szo_contact_step(C.byref(prm), C.byref(fs), C.byref(bs) if bs is not None else None, int(nthreads), int(broad_mode))
+        err = l.szo_error(self._r)
+        if err:
+            raise RuntimeError("oracle: " + err.decode())
+        self.summary = abi.SzSummary()
+        l.szo_summary(self._r, C.byref(self.summary))
+        self._n0 = floes.n
+
+    def __del__(self):
+        if getattr(self, "_r", None):
+            lib().szo_free(self._r)
+            self._r = None
+
+    def floe_outputs(self):
+        n = self._n0
+        o = {"fx": np.empty(n), "fy": np.empty(n), "torque": np.empty(n), "overlap_area": np.empty(n), "stress": np.empty((n, 2, 2)),
+             "xi": np.empty(n), "yi": np.empty(n), "alive": np.empty(n, np.uint8), "kill": np.empty(n, np.int32), "transfer": np.empty(n, np.int32)}
+        p = abi._ptr
+        lib().szo_get_floe_outputs(self._r, p(o["fx"], abi.c_dp), p(o["fy"], abi.c_dp), p(o["torque"], abi.c_dp), p(o["overlap_area"], abi.c_dp),
+                                   p(o["stress"], abi.c_dp), p(o["xi"], abi.c_dp), p(o["yi"], abi.c_dp), p(o["alive"], abi.c_bp), p(o["kill"], abi.c_ip), p(o["transfer"], abi.c_ip))
+        return o
+
+    def ghosts(self):
+        g = self.summary.n - self.summary.n0
+        o = {"parent": np.empty(g, np.int32), "floe_num": np.empty(g, np.int32), "x": np.empty(g), "y": np.empty(g)}
+        p = abi._ptr
+        lib().szo_get_ghosts(self._r, p(o["parent"], abi.c_ip), p(o["floe_num"], abi.c_ip), p(o["x"], abi.c_dp), p(o["y"], abi.c_dp))
+        return o
+
+    def pairs(self):
+        n = self.summary.n_pairs
+        o = {"i": np.empty(n, np.int32), "j": np.empty(n, np.int32), "overlap_state": np.empty(n), "n_regions": np.empty(n, np.int32), "status": np.empty(n, np.int32)}
+        p = abi._ptr
+        lib().szo_get_pairs(self._r, p(o["i"], abi.c_ip), p(o["j"], abi.c_ip), p(o["overlap_state"], abi.c_dp), p(o["n_regions"], abi.c_ip), p(o["status"], abi.c_ip))
+        return o
+
+    def rows(self):
+        off = np.empty(self.summary.n + 1, np.int64)
+        rows = np.empty((self.summary.n_rows, 7))
+        lib().szo_get_rows(self._r, abi._ptr(off, abi.c_lp), abi._ptr(rows, abi.c_dp))
+        return off, rows
+
+    def clip_polys(self):
+        s = self.summary
+        ppo, pvo = np.empty(s.n_pairs + 1, np.int64), np.empty(s.n_clip_paths + 1, np.int64)
+        x, y = np.empty(s.n_clip_verts, np.int64), np.empty(s.n_clip_verts, np.int64)
+        p = abi._ptr
+        lib().szo_get_clip_polys(self._r, p(ppo, abi.c_lp), p(pvo, abi.c_lp), p(x, abi.c_lp), p(y, abi.c_lp))
+        return ppo, pvo, x, y
+
+
+def _rel_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    both_nan = np.isnan(a) & np.isnan(b)
+    d = np.abs(np.where(both_inf | both_nan, 0.0, a - b))
+    scale = np.maximum(np.abs(np.where(np.isfinite(b), b, 0.0)), 1e-300)
+    return d / scale
+
+
+def compare_steps(got, ref, rtol=1e-9, check_polys=True):
+    """Parity of a product step (ContactContext) with an oracle step: integer/index outputs bit-exact,
+    FP64 outputs within rtol relative (BASELINE.json north_star: 1e-9).  Returns a dict of measured
+    maxima; raises AssertionError naming the first mismatch."""
+    gs, rs = got.summary, ref.summary
+    assert (gs.n0, gs.n) == (rs.n0, rs.n), "extended list size: got (%d,%d) ref (%d,%d)" % (gs.n0, gs.n, rs.n0, rs.n)
+    gg, rg = got.ghosts(), ref.ghosts()
+    for k in ("parent", "floe_num"):
+        assert np.array_equal(gg[k], rg[k]), "ghost %s differs" % k
+    for k in ("x", "y"):
+        assert np.array_equal(gg[k], rg[k]), "ghost centroid %s differs" % k
+    assert gs.n_pairs == rs.n_pairs, "candidate pairs: got %d ref %d" % (gs.n_pairs, rs.n_pairs)
+    gp, rp = got.pairs(), ref.pairs()
+    for k in ("i", "j", "status", "n_regions"):
+        if not np.array_equal(gp[k], rp[k]):
+            bad = int(np.flatnonzero(gp[k] != rp[k])[0])
+            raise AssertionError("pair list field %s differs first at pair %d (i=%d j=%d): got %d ref %d" % (k, bad, rp["i"][bad], rp["j"][bad], gp[k][bad], rp[k][bad]))
+    assert np.array_equal(gp["overlap_state"], rp["overlap_state"]), "overlap_state differs"
+    out = {"pairs": int(gs.n_pairs), "rows": int(gs.n_rows)}
+    if check_polys:
+        assert (gs.n_clip_paths, gs.n_clip_verts) == (rs.n_clip_paths, rs.n_clip_verts), "clip polygon counts differ: got (%d,%d) ref (%d,%d)" % (
+            gs.n_clip_paths, gs.n_clip_verts, rs.n_clip_paths, rs.n_clip_verts)
+        for a, b, nm in zip(got.clip_polys(), ref.clip_polys(), ("pair_path_off", "path_vert_off", "x", "y")):
+            assert np.array_equal(a, b), "Clipper int64 polygons differ in %s" % nm
+        out["clip_verts"] = int(gs.n_clip_verts)
+    assert gs.n_rows == rs.n_rows, "row count: got %d ref %d" % (gs.n_rows, rs.n_rows)
+    goff, grow = got.rows()
+    roff, rrow = ref.rows()
+    assert np.array_equal(goff, roff), "row offsets differ"
+    assert np.array_equal(grow[:, 0], rrow[:, 0]), "row partner ids differ"
+    # forces/torques can cancel: scale the tolerance by the largest magnitude in the row set
+    mx = 0.0
+    for col, nm in ((1, "Fx"), (2, "Fy"), (3, "Px"), (4, "Py"), (5, "torque"), (6, "overlap")):
+        if len(rrow):
+            scale = max(np.abs(rrow[:, col][np.isfinite(rrow[:, col])]).max(initial=0.0), 1e-300)
+            same_nonfinite = (~np.isfinite(rrow[:, col])) & ((grow[:, col] == rrow[:, col]) | (np.isnan(grow[:, col]) & np.isnan(rrow[:, col])))
+            e = np.where(same_nonfinite, 0.0, np.abs(grow[:, col] - rrow[:, col])) / scale
+            e = np.nan_to_num(e, nan=np.inf)
+            assert e.max(initial=0.0) <= rtol, "rows column %s: max rel err %.3e" % (nm, e.max())
+            mx = max(mx, float(e.max(initial=0.0)))
+    out["rows_max_rel"] = mx
+    go, ro = got.floe_outputs(), ref.floe_outputs()
+    for k in ("alive", "kill", "transfer"):
+        assert np.array_equal(go[k], ro[k]), "per-floe %s differs" % k
+    for k in ("xi", "yi"):
+        assert np.array_equal(go[k], ro[k]), "wrapped centroid %s differs" % k
+    for k in ("fx", "fy", "torque", "overlap_area", "stress"):
+        r = np.asarray(ro[k])
+        scale = max(np.abs(r[np.isfinite(r)]).max(initial=0.0), 1e-300)
+        g = np.asarray(go[k])
+        same_nonfinite = (~np.isfinite(r)) & ((g == r) | (np.isnan(g) & np.isnan(r)))
+        e = np.nan_to_num(np.where(same_nonfinite, 0.0, np.abs(g - r)) / scale, nan=np.inf)
+        assert e.max(initial=0.0) <= rtol, "per-floe %s: max rel err %.3e" % (k, e.max())
+        out[k + "_max_rel"] = float(e.max(initial=0.0))
+        out[k + "_bit_exact"] = bool(np.array_equal(g, r, equal_nan=True))
+    assert gs.collision_count == rs.collision_count, "collision count: got %r ref %r" % (gs.collision_count, rs.collision_count)
+    assert gs.n_pairs_force == rs.n_pairs_force and gs.n_clipper_fail == rs.n_clipper_fail
+    out["rows_bit_exact"] = bool(np.array_equal(grow, rrow, equal_nan=True))
+    return out
