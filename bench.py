@@ -1,0 +1,241 @@
+"""bench.py -- floe-pair contacts resolved per second on the synthetic packed-Voronoi field
+(BASELINE.json configs[4]), one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus 1 --steps K ...  # the reference's CPU path (oracle port linked to the
+                                                            # reference's own Clipper) on the host cores
+
+A "step" is one pass of the contact loop (floe_interactions_all.m:9-285) over the whole field.
+`value`  : candidate pairs taken through narrow phase + force law + reductions per second, inputs resident in HBM
+           (sz_step_resident), timed with CUDA events on the library's stream, max over ranks.
+`e2e`    : the same metric through the host-buffer entry point sz_contact_step + result read-back (per-floe
+           outputs and all contact rows), host<->device copies inside the timed region (pinned host memory).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "floe-pair contacts resolved/s"
+UNIT = "pairs/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst)"
+        except Exception:
+            pass
+    return 6400.0, "fallback from B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons through nvidia-smi during the timed region"""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.reasons, self.max_mhz, self._stop_ev = gpu, [], set(), None, threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,clocks_throttle_reasons.hw_thermal_slowdown,clocks_throttle_reasons.sw_thermal_slowdown,clocks_throttle_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def algorithmic_bytes(floes, summary):
+    """per candidate pair both outlines (16 B/vertex) + both state records (2 x 72 B) + pair id (8 B)
+    + contact rows written (own + mirrored, 56 B each)."""
+    nv_mean = floes.vx.shape[0] / max(1, floes.n)
+    per_pair = 2 * nv_mean * 16 + 2 * 72 + 8
+    return summary.n_pairs * per_pair + summary.n_rows * 56
+
+
+def cpu_sample(n_floes, seed, threads):
+    """the oracle (reference restatement + the reference's Clipper) on a bounded sample of the same workload"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import subzero_b200 as sz
+    import oracle
+    prm, f = sz.voronoi_field(n_floes, seed=seed)
+    t = time.perf_counter()
+    r = oracle.OracleStep(prm, f, nthreads=threads, broad_mode=1)
+    dt = time.perf_counter() - t
+    return r.summary.n_pairs, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    threads = max(1, oracle.lib().szo_hardware_threads())
+    n_sample = args.cpu_floes
+    for _ in range(args.warmup):
+        cpu_sample(min(n_sample, 20000), args.seed, threads)
+    tot_pairs, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        p, dt = cpu_sample(n_sample, args.seed, threads)
+        tot_pairs += p
+        tot_t += dt
+    v = tot_pairs / tot_t
+    sample = "%d-floe periodic Voronoi field (same generator, density and physics as the %d-floe workload), whole contact step, cell-grid broad phase" % (n_sample, args.floes)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+int64",
+            "data": "synthetic", "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes, "sample_floes": n_sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": sample + "; oracle = C++ restatement of the MATLAB path calling the reference's unmodified Clipper 6.4.2 (MATLAB itself is not installed)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--floes", type=int, default=1000000)
+    ap.add_argument("--cpu-floes", type=int, default=200000)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import subzero_b200 as sz
+    from subzero_b200 import abi
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from subzero_b200 import slabs
+    job = slabs.SlabJob(args.floes, args.seed, rank, world, local_rank, dist)
+    prm, floes = job.prm, job.floes
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    launches0 = abi.lib().sz_launch_count()
+    for _ in range(max(3, args.warmup)):
+        job.step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches1 = abi.lib().sz_launch_count()
+    dev_ms, narrow_ms, wall0 = 0.0, 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        ms, ph = job.step_resident()
+        dev_ms += ms
+        narrow_ms += ph["narrow"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    launches = abi.lib().sz_launch_count() - launches1
+    clocks = sampler.stop() if rank == 0 else None
+    pairs_local = job.pairs_owned
+    t = torch.tensor([dev_ms, wall_ms, narrow_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([pairs_local, job.rows_owned, launches], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms, narrow_ms = [float(v) for v in t.tolist()]
+    total_pairs, total_rows, launches = [int(v) for v in cnt.tolist()]
+    ms_per_step = dev_ms / args.steps
+    value = total_pairs / (ms_per_step * 1e-3)
+
+    # ---- end to end: host buffers in (pinned), per-floe outputs + contact rows out, every step
+    e2e_steps = max(1, min(args.steps, 3))
+    job.e2e_step()   # warm
+    barrier()
+    w0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(e2e_steps):
+        h2d, d2h = job.e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - w0) / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    tb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+    e2e_ms = float(te.item())
+    e2e_value = total_pairs / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        alg_bytes = algorithmic_bytes(floes, job.summary) * (1 if world == 1 else 1)
+        narrow_ms_per = narrow_ms / args.steps
+        achieved = alg_bytes / (narrow_ms_per * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "narrow_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+int64",
+                "data": "synthetic",
+                "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes,
+                           "floes_incl_ghosts": int(job.summary.n), "pairs_per_step": total_pairs, "pairs_with_force": int(job.pairs_force_total),
+                           "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "parallelism": job.describe(),
+                           "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed,
+                           "wall_ms_per_step": wall_ms / args.steps},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "narrow_local_kernel<PairS> (narrow phase + force law)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": narrow_ms_per,
+                             "note": "latency/issue-bound sequential sweep per pair; the HBM roofline is reported as the contract asks, see DESIGN.md"}}
+        if world == 1 and not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle
+            threads = max(1, oracle.lib().szo_hardware_threads())
+            p, dt = cpu_sample(args.cpu_floes, args.seed, threads)
+            line["cpu_baseline"] = {"value": p / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d-floe field from the same generator, one whole contact step (%.1f s)" % (args.cpu_floes, dt)}
+        print(json.dumps(line), flush=True)
+    job.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

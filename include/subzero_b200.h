@@ -114,6 +114,7 @@ void sz_destroy(SzContext* ctx);
 const char* sz_last_error(void);                        /* thread-local message of the last failure */
 void sz_default_params(SzParams* p);
 int  sz_abi_version(void);
+long long sz_launch_count(void);                       /* CUDA kernels this library has launched so far (process-wide) */
 
 /* ---- one contact step, host buffers in (the mex / ctypes entry point) ---- */
 int sz_contact_step(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes,
@@ -143,6 +144,11 @@ int sz_get_rows(SzContext* ctx, int64_t* row_off, double* rows);
 /* debug (want_clip_polys): clip #1 result of every pair as Clipper's int64 coordinates.
  * pair_path_off [n_pairs+1] -> path_vert_off [n_clip_paths+1] -> x,y [n_clip_verts] */
 int sz_get_clip_polys(SzContext* ctx, int64_t* pair_path_off, int64_t* path_vert_off, int64_t* x, int64_t* y);
+
+/* diagnostic: device time (CUDA events, ms) of the last step by phase:
+ * [0] ghost floes (floe_interactions_all.m:16-66)   [1] broad phase (:68-120)
+ * [2] narrow phase + force law (:125-174)           [3] mirror/torque/sums (:186-265)   [4] whole step */
+int sz_get_phase_ms(SzContext* ctx, float* ms5);
 
 /* ---- stand-alone polygon clip with the gateway's semantics (private/mexclipper.cpp:204-305):
  * `count` independent (subject, clip) pairs, one closed path each, int64 coordinates, even-odd fill,

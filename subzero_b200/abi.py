@@ -53,6 +53,7 @@ PROTOTYPES = {
     "sz_last_error": (C.c_char_p, []),
     "sz_default_params": (None, [C.POINTER(SzParams)]),
     "sz_abi_version": (C.c_int, []),
+    "sz_launch_count": (C.c_longlong, []),
     "sz_contact_step": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzSummary)]),
     "sz_upload": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary)]),
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
@@ -60,6 +61,7 @@ PROTOTYPES = {
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),
     "sz_get_pairs": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_ip, c_ip]),
     "sz_get_rows": (C.c_int, [C.c_void_p, c_lp, c_dp]),
+    "sz_get_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "sz_get_clip_polys": (C.c_int, [C.c_void_p, c_lp, c_lp, c_lp, c_lp]),
     "sz_clip_batch": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp]),
     "sz_get_clip_batch": (C.c_int, [C.c_void_p, c_ip, c_lp, c_lp, c_lp, c_lp]),

@@ -99,6 +99,12 @@ class ContactContext:
         abi.check(abi.lib().sz_get_rows(self._h, abi._ptr(off, abi.c_lp), abi._ptr(rows, abi.c_dp)))
         return off, rows
 
+    def phase_ms(self):
+        """device ms of the last step: ghosts, broad phase, narrow phase, assembly, total"""
+        a = (C.c_float * 5)()
+        abi.check(abi.lib().sz_get_phase_ms(self._h, a))
+        return dict(zip(("ghosts", "broad", "narrow", "assembly", "total"), [float(v) for v in a]))
+
     def clip_polys(self):
         s = self.summary
         ppo = np.empty(s.n_pairs + 1, np.int64)

@@ -36,12 +36,14 @@ typedef unsigned long long u64;
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
+static long long g_launches = 0;   // kernels launched by this library (sz_launch_count)
 void sz_set_error(const char* fmt, ...)
 {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 extern "C" const char* sz_last_error(void) { return g_err; }
 extern "C" int sz_abi_version(void) { return 1; }
+extern "C" long long sz_launch_count(void) { return g_launches; }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     sz_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); return SZ_ERR_CUDA; } } while (0)
@@ -81,7 +83,8 @@ struct Counters {
 struct SzContext {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
+    float phase_ms[5] = {0, 0, 0, 0, 0};
     Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
     // inputs
     bool have_input = false, have_step = false;
@@ -160,11 +163,11 @@ __global__ void scan_add_kernel(int* __restrict__ out, int n_out, const int* __r
 static void exclusive_scan(const int* in, int n_in, int* out, int n_out, int* tmp, cudaStream_t st)
 {
     const int tiles = (n_out + SCAN_TILE - 1) / SCAN_TILE;
-    if (tiles <= 1) { scan_tile_kernel<<<1, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, nullptr); return; }
+    if (tiles <= 1) { ++g_launches; scan_tile_kernel<<<1, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, nullptr); return; }
     int* sums = tmp; int* sums_scanned = tmp + tiles + 1;
-    scan_tile_kernel<<<tiles, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, sums);
+    ++g_launches; scan_tile_kernel<<<tiles, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, sums);
     exclusive_scan(sums, tiles, sums_scanned, tiles, sums_scanned + tiles + 1, st);
-    scan_add_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(out, n_out, sums_scanned);
+    ++g_launches; scan_add_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(out, n_out, sums_scanned);
 }
 static size_t scan_tmp_ints(size_t n) { size_t t = 0; while (n > SCAN_TILE) { n = (n + SCAN_TILE - 1) / SCAN_TILE; t += 2 * n + 4; } return t + 16; }
 
@@ -561,6 +564,7 @@ extern "C" int sz_create(SzContext** out, int device)
     c->device = device;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    for (auto& e : c->evp) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&c->d_cnt, sizeof(Counters)));
     CK(cudaMallocHost(&c->h_cnt, sizeof(Counters)));
     memset(&c->summary, 0, sizeof(c->summary));
@@ -590,6 +594,7 @@ extern "C" void sz_destroy(SzContext* c)
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto& e : c->evp) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -692,7 +697,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         cntM = D_CNT(listM); cntL = D_CNT(listL); lstM = c->listM.p; lstL = c->listL.p;
     }
     a.next_list = lstM; a.next_count = cntM;
-    sz_launch_narrow_S(&a, st);
+    ++g_launches; sz_launch_narrow_S(&a, st);
     CK(cudaGetLastError());
     CKS(read_counters(c));
     int nM = wall ? c->h_cnt->wlistM : c->h_cnt->listM;
@@ -700,7 +705,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         const int threads = std::min(nM, 148 * 64);
         CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
         a.list = lstM; a.list_count = cntM; a.next_list = lstL; a.next_count = cntL; a.scratch = c->scratchM.p; a.n_threads = threads;
-        sz_launch_narrow_M(&a, st);
+        ++g_launches; sz_launch_narrow_M(&a, st);
         CK(cudaGetLastError());
         CKS(read_counters(c));
         int nL = wall ? c->h_cnt->wlistL : c->h_cnt->listL;
@@ -708,7 +713,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
             const int threadsL = std::min(nL, 148 * 8);
             CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
             a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
-            sz_launch_narrow_L(&a, st);
+            ++g_launches; sz_launch_narrow_L(&a, st);
             CK(cudaGetLastError());
             CKS(read_counters(c));
         }
@@ -733,7 +738,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     CK(c->ex.ensure(ncap + 1)); CK(c->ey.ensure(ncap + 1)); CK(c->esrc.ensure(ncap + 1)); CK(c->efn.ensure(ncap + 1)); CK(c->eparent.ensure(ncap + 1));
     CK(c->ealive.ensure(ncap + 1)); CK(c->gx_of.ensure(n0 + 1)); CK(c->gy_of.ensure(n0 + 1));
     CK(c->flag.ensure(2 * (size_t)n0 + 2)); CK(c->pos.ensure(2 * (size_t)n0 + 2));
-    if (n0 > 0) init_extended_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p, c->gx_of.p, c->gy_of.p);
+    if (n0 > 0) { ++g_launches; init_extended_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p, c->gx_of.p, c->gy_of.p); }
     {
         Counters init; memset(&init, 0, sizeof(init));
         init.n1 = n0; init.n = n0;
@@ -744,21 +749,22 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (P.periodic && n0 > 0) {
         CK(c->scan_tmp.ensure(scan_tmp_ints(2 * (size_t)n0 + 2)));
         // x pass over the originals
-        ghost_flag_kernel<<<nblk(n0, 128), 128, 0, st>>>(0, n0, nullptr, c->ex.p, c->esrc.p, c->ealive.p, c->voff.p, c->vx.p, P.Lx, c->flag.p);
+        ++g_launches; ghost_flag_kernel<<<nblk(n0, 128), 128, 0, st>>>(0, n0, nullptr, c->ex.p, c->esrc.p, c->ealive.p, c->voff.p, c->vx.p, P.Lx, c->flag.p);
         exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
-        ghost_emit_kernel<<<nblk(n0, 256), 256, 0, st>>>(0, n0, nullptr, n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
+        ++g_launches; ghost_emit_kernel<<<nblk(n0, 256), 256, 0, st>>>(0, n0, nullptr, n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
                                                          c->gx_of.p, c->gy_of.p, P.Lx, D_CNT(n1));
         // y pass over originals + x-ghosts (their number is only known on the device: bound 2*n0)
-        ghost_flag_kernel<<<nblk(2 * (i64)n0, 128), 128, 0, st>>>(1, 2 * n0, D_CNT(n1), c->ey.p, c->esrc.p, c->ealive.p, c->voff.p, c->vy.p, P.Ly, c->flag.p);
+        ++g_launches; ghost_flag_kernel<<<nblk(2 * (i64)n0, 128), 128, 0, st>>>(1, 2 * n0, D_CNT(n1), c->ey.p, c->esrc.p, c->ealive.p, c->voff.p, c->vy.p, P.Ly, c->flag.p);
         exclusive_scan(c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1, c->scan_tmp.p, st);
-        ghost_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(n1), n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
+        ++g_launches; ghost_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(n1), n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
                                                                   c->gx_of.p, c->gy_of.p, P.Ly, D_CNT(n));
     }
-    if (ncap > 0) bbox_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->d_cnt);
+    if (ncap > 0) { ++g_launches; bbox_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->d_cnt); }
     CK(cudaGetLastError());
     CKS(read_counters(c));
     const int n = c->h_cnt->n; c->n = n; c->n1 = c->h_cnt->n1;
 
+    CK(cudaEventRecord(c->evp[0], st));
     // ---- K1: cell grid + candidate pairs
     GridDesc g; g.x0 = g.y0 = 0; g.cell = 1; g.nx = g.ny = 1;
     {
@@ -782,15 +788,15 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     CK(cudaMemsetAsync(c->pcnt.p, 0, (size_t)(n + 1) * 4, st));
     BroadArgs b; memset(&b, 0, sizeof(b));
     if (n > 0) {
-        cell_count_kernel<<<nblk(n, 256), 256, 0, st>>>(n, g, c->ex.p, c->ey.p, c->ealive.p, c->cid.p, c->cell_cnt.p);
+        ++g_launches; cell_count_kernel<<<nblk(n, 256), 256, 0, st>>>(n, g, c->ex.p, c->ey.p, c->ealive.p, c->cid.p, c->cell_cnt.p);
         exclusive_scan(c->cell_cnt.p, ncell, c->cell_start.p, ncell + 1, c->scan_tmp.p, st);
         CK(cudaMemsetAsync(c->cell_cnt.p, 0, (size_t)(ncell + 1) * 4, st));
-        cell_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->cid.p, c->cell_start.p, c->cell_cnt.p, c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->s_idx.p, c->s_x.p, c->s_y.p, c->s_r.p);
+        ++g_launches; cell_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->cid.p, c->cell_start.p, c->cell_cnt.p, c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->s_idx.p, c->s_x.p, c->s_y.p, c->s_r.p);
         b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly);
         b.ex = c->ex.p; b.ey = c->ey.p; b.esrc = c->esrc.p; b.efn = c->efn.p; b.ealive = c->ealive.p; b.rmax = c->rmax.p;
         b.cell_start = c->cell_start.p; b.s_idx = c->s_idx.p; b.s_x = c->s_x.p; b.s_y = c->s_y.p; b.s_r = c->s_r.p;
         b.pcnt = c->pcnt.p; b.pair_off = c->pair_off.p;
-        if (n > Nb) broad_kernel<false><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b);
+        if (n > Nb) { ++g_launches; broad_kernel<false><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b); }
     }
     exclusive_scan(c->pcnt.p, n, c->pair_off.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemcpyAsync(D_CNT(n_pairs), c->pair_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
@@ -799,8 +805,9 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     const int np = c->h_cnt->n_pairs; c->n_pairs = np;
     CK(c->pi.ensure(np + 1)); CK(c->pj.ensure(np + 1)); CK(c->pstatus.ensure(np + 1)); CK(c->pnrows.ensure(np + 1)); CK(c->prow_start.ensure(np + 1)); CK(c->povl.ensure(np + 1));
     CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
-    if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; broad_kernel<true><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b); }
+    if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b); }
 
+    CK(cudaEventRecord(c->evp[1], st));
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
     if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }
@@ -832,14 +839,15 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         if (attempt == 2) { sz_set_error("sz_step_resident: result pools kept overflowing"); return SZ_ERR_CAPACITY; }
     }
 
+    CK(cudaEventRecord(c->evp[2], st));
     // ---- K4: mirror, rows, sums
     CK(c->tcnt.ensure(n + 2)); CK(c->toff.ensure(n + 2)); CK(c->tlist.ensure(np + 1)); CK(c->rcnt.ensure(n + 2)); CK(c->row_off.ensure(n + 2));
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
-    if (np > 0) tcount_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->tcnt.p);
+    if (np > 0) { ++g_launches; tcount_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->tcnt.p); }
     exclusive_scan(c->tcnt.p, n, c->toff.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
-    if (np > 0) tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p);
-    if (n > 0) rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p);
+    if (np > 0) { ++g_launches; tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p); }
+    if (n > 0) { ++g_launches; rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p); }
     exclusive_scan(c->rcnt.p, n, c->row_off.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemcpyAsync(D_CNT(total_rows), c->row_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
@@ -859,20 +867,22 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         a.boxx = c->boxx.p; a.boxy = c->boxy.p; a.boxn = c->boxn;
         a.rows = c->rows.p; a.osum = c->osum.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
         a.o_ov = c->o_ov.p; a.o_stress = c->o_stress.p; a.o_xi = c->o_xi.p; a.o_yi = c->o_yi.p; a.o_alive = c->o_alive.p; a.cnt = c->d_cnt;
-        assemble_kernel<<<nblk(n, 128), 128, 0, st>>>(a);
+        ++g_launches; assemble_kernel<<<nblk(n, 128), 128, 0, st>>>(a);
         CK(cudaMemsetAsync(c->tmax.p, 0, (size_t)(n0 + 1) * 4, st));
-        kill_mark_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->kill_i.p, c->tmax.p);
+        ++g_launches; kill_mark_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->kill_i.p, c->tmax.p);
         if (n0 > 0) {
-            kill_final_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->kill_i.p, c->transfer_i.p, c->tmax.p, c->o_kill.p, c->o_transfer.p);
-            fold_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, Nb, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p);
+            ++g_launches; kill_final_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->kill_i.p, c->transfer_i.p, c->tmax.p, c->o_kill.p, c->o_transfer.p);
+            ++g_launches; fold_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, Nb, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p);
         }
-        if (np > 0) pair_stats_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, 1, c->d_cnt);
-        if (wall) pair_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, 0, c->d_cnt);
+        if (np > 0) { ++g_launches; pair_stats_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, 1, c->d_cnt); }
+        if (wall) { ++g_launches; pair_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, 0, c->d_cnt); }
     }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
     CKS(read_counters(c));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    CK(cudaEventElapsedTime(&c->phase_ms[0], c->ev0, c->evp[0])); CK(cudaEventElapsedTime(&c->phase_ms[1], c->evp[0], c->evp[1]));
+    CK(cudaEventElapsedTime(&c->phase_ms[2], c->evp[1], c->evp[2])); CK(cudaEventElapsedTime(&c->phase_ms[3], c->evp[2], c->ev1)); c->phase_ms[4] = ms;
 
     SzSummary& s = c->summary; memset(&s, 0, sizeof(s));
     s.n0 = n0; s.n = n; s.n_pairs = np; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows;
@@ -940,6 +950,12 @@ extern "C" int sz_get_rows(SzContext* c, int64_t* row_off, double* rows)
     }
     D2H(rows, c->rows.p, (size_t)c->n_rows * 56);
     CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+extern "C" int sz_get_phase_ms(SzContext* c, float* ms5)
+{
+    NEED_STEP("sz_get_phase_ms");
+    if (ms5) for (int k = 0; k < 5; ++k) ms5[k] = c->phase_ms[k];
     return SZ_OK;
 }
 // reorder (start, count) pools into item-major CSR
@@ -1011,21 +1027,21 @@ extern "C" int sz_clip_batch(SzContext* c, int32_t count, const int32_t* method,
         a.path_vstart = c->c_path_vstart.p; a.path_len = c->c_path_len.p; a.path_cap = (int)c->c_path_vstart.cap; a.path_used = D_CNT(clip_path_used);
         a.pvx = c->c_pvx.p; a.pvy = c->c_pvy.p; a.vert_cap = (int)c->c_pvx.cap; a.vert_used = D_CNT(clip_vert_used);
         a.next_list = c->c_listM.p; a.next_count = D_CNT(clip_listM);
-        sz_launch_clip_S(&a, st);
+        ++g_launches; sz_launch_clip_S(&a, st);
         CK(cudaGetLastError());
         CKS(read_counters(c));
         if (c->h_cnt->clip_listM > 0) {
             const int threads = std::min(c->h_cnt->clip_listM, 148 * 64);
             CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
             a.list = c->c_listM.p; a.list_count = D_CNT(clip_listM); a.next_list = c->c_listL.p; a.next_count = D_CNT(clip_listL); a.scratch = c->scratchM.p; a.n_threads = threads;
-            sz_launch_clip_M(&a, st);
+            ++g_launches; sz_launch_clip_M(&a, st);
             CK(cudaGetLastError());
             CKS(read_counters(c));
             if (c->h_cnt->clip_listL > 0) {
                 const int threadsL = std::min(c->h_cnt->clip_listL, 148 * 8);
                 CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
                 a.list = c->c_listL.p; a.list_count = D_CNT(clip_listL); a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
-                sz_launch_clip_L(&a, st);
+                ++g_launches; sz_launch_clip_L(&a, st);
                 CK(cudaGetLastError());
                 CKS(read_counters(c));
             }

@@ -1,0 +1,99 @@
+"""The C-ABI library loads and exports every symbol include/subzero_b200.h declares; the product path fails
+loudly without a GPU / without the extension (no CPU fallback).  CPU only -- no compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+import subzero_b200 as sz
+from subzero_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "subzero_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sz_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(abi.PROTOTYPES)
+
+
+def test_library_exports_every_declared_symbol():
+    l = C.CDLL(abi.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(l, name), name
+    assert abi.lib().sz_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    """sizes implied by the header's field lists (8-byte alignment)"""
+    assert C.sizeof(abi.SzParams) == 15 * 8 + 4 * 4
+    assert C.sizeof(abi.SzFloesSoA) == 8 + 8 + 12 * 8
+    assert C.sizeof(abi.SzBoundary) == 8 + 8 + 8 + 8 + 8 + 8 + 7 * 8
+    assert C.sizeof(abi.SzSummary) == 8 + 5 * 8 + 8 + 4 + 4 + 8
+
+
+def test_default_params_are_the_reference_constants():
+    p = sz.default_params()
+    # floe_interactions.m:20-21 nu, mu; :55-58 0.55; :37 0.75; :79 100/1.75; :99 1; :127 1e-8; :141 0.1; :15 1e5; :54 0.95
+    assert (p.nu, p.mu, p.merge_frac, p.wall_frac, p.amin_per_vertex) == (0.3, 0.2, 0.55, 0.75, 100 / 1.75)
+    assert (p.vertex_match_tol, p.on_edge_tol, p.dl_min, p.close_gap, p.big_floe_r, p.domain_area_frac) == (1, 1e-8, 0.1, 1, 1e5, 0.95)
+
+
+def test_bad_arguments_are_rejected_without_a_device():
+    assert abi.lib().sz_create(None, 0) == abi.SZ_ERR_ARG
+    assert b"NULL" in abi.lib().sz_last_error()
+    assert abi.lib().sz_step_resident(None, None) == abi.SZ_ERR_ARG
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sz.SzError) as e:
+        sz.ContactContext(0)
+    assert e.value.code == abi.SZ_ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_missing_extension_fails_loudly(tmp_path):
+    code = ("import sys; sys.path.insert(0, %r); from subzero_b200 import abi; abi.LIB_PATH = %r\n"
+            "try:\n    abi.lib()\nexcept RuntimeError as e:\n    print('RAISED', e)\n") % (ROOT, str(tmp_path / "nope.so"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "RAISED" in r.stdout and "no CPU fallback" in r.stdout
+
+
+def test_product_does_not_reference_the_oracle():
+    """nothing under subzero_b200/ or include/ may import, link or name the checker"""
+    bad = []
+    for base in ("subzero_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            if "_lib" in dp or "__pycache__" in dp:
+                continue
+            for f in files:
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"sz_oracle|libsz_oracle|libclipper_ref|szo_|szref_|import oracle|from oracle", txt):
+                    bad.append(os.path.join(dp, f))
+    assert bad == []
+    out = subprocess.run(["ldd", abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "clipper_ref" not in out
+
+
+def test_field_generator_shapes():
+    prm, f = sz.voronoi_field(4000, seed=0)
+    nv = f.voff[1:] - f.voff[:-1]
+    assert f.n == 4000 and nv.min() >= 4 and nv.max() <= 20          # closed outlines: 3..~13 vertices + the repeat
+    assert abs(nv.mean() - 7.0) < 0.1                                 # mean 6 vertices per cell
+    assert prm.Lx == prm.Ly == 0.5 * (4000 * 4e6) ** 0.5
+    for i in (0, 17, 3999):
+        x, y = f.outline(i)
+        assert x[0] == x[-1] and y[0] == y[-1]                         # closed (initialize_floe_values.m:17)
+        area2 = (x[:-1] * y[1:] - x[1:] * y[:-1]).sum()
+        assert area2 < 0                                               # clockwise, like FloeShapes.mat
+    import numpy as np
+    assert abs(f.area.sum() / (4 * prm.Lx * prm.Ly) - 1.02 ** 2) < 1e-9   # cells tile the domain, inflated by 1.02

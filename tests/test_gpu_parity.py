@@ -1,0 +1,200 @@
+"""Parity of the CUDA path (called through the C ABI) with the oracle on identical inputs.
+Bars (BASELINE.json north_star): ghosts, candidate-pair lists and Clipper int64 polygons bit-exact;
+forces, torques, overlap areas, stress within 1e-9 relative (FP64).  Needs a B200."""
+import numpy as np
+import pytest
+
+import oracle
+import scenarios
+import subzero_b200 as sz
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    with sz.ContactContext(0) as c:
+        yield c
+
+
+def run_both(ctx, prm, soa, bnd=None, broad_mode=0):
+    prm.want_clip_polys = 1
+    before = sz.abi.lib().sz_launch_count()
+    ctx.step(prm, soa, bnd, allow_pair_errors=True)
+    assert sz.abi.lib().sz_launch_count() > before            # our kernels ran
+    ref = oracle.OracleStep(prm, soa, bnd, broad_mode=broad_mode)
+    return oracle.compare_steps(ctx, ref, rtol=RTOL), ref
+
+
+@pytest.mark.parametrize("n,seed", [(64, 0), (500, 1), (5000, 2), (20000, 3)])
+def test_periodic_voronoi_field(ctx, n, seed):
+    prm, soa = sz.voronoi_field(n, seed=seed)
+    rep, ref = run_both(ctx, prm, soa, broad_mode=0 if n <= 5000 else 1)
+    assert ref.summary.n > ref.summary.n0                       # ghosts exist
+    assert rep["pairs"] > 4 * n and rep["rows"] > 0
+
+
+def test_uninflated_voronoi_shared_edges_give_no_polygons(ctx):
+    """exactly shared edges: every Clipper intersection must come back empty, as in the reference"""
+    prm, soa = sz.voronoi_field(3000, seed=4, inflate=0.0)
+    rep, ref = run_both(ctx, prm, soa)
+    assert rep["pairs"] > 10000
+    assert ref.summary.n_clip_paths <= 0.05 * rep["pairs"]        # only rounding slivers survive
+
+
+def test_dead_and_nan_floes_and_collision_off(ctx):
+    prm, soa = sz.voronoi_field(2000, seed=5)
+    soa.alive[::7] = 0
+    soa.x[5] = np.nan
+    soa.y[11] = np.nan
+    run_both(ctx, prm, soa)
+    prm.collision = 0
+    rep, ref = run_both(ctx, prm, soa)
+    assert rep["pairs"] == 0 and ref.summary.n > ref.summary.n0
+
+
+def test_boundary_floes_nb(ctx):
+    """floes 1..Nb (topography) never start a pair (floe_interactions_all.m:76)"""
+    prm, soa = sz.voronoi_field(1500, seed=6)
+    prm.Nb = 40
+    rep, ref = run_both(ctx, prm, soa)
+    assert ref.pairs()["i"].min() > 40
+
+
+def test_small_periodic_domain_big_floes(ctx):
+    """2(rmax_i+rmax_j) > min(2Lx,2Ly): the ghost de-dup exemption of floe_interactions_all.m:103"""
+    prm, soa = sz.voronoi_field(12, seed=8)
+    rep, ref = run_both(ctx, prm, soa)
+    assert ref.summary.n > ref.summary.n0 and rep["pairs"] > 12
+
+
+def test_non_periodic_with_walls(ctx):
+    """same field, PERIODIC = 0: floes poking through the domain wall get wall rows (partner Inf), floes whose
+    centroid left the domain die (floe_interactions_all.m:150-172)"""
+    prm, soa = sz.voronoi_field(1500, seed=9)
+    prm.periodic = 0
+    soa.x[:20] += np.sign(soa.x[:20]) * 1500.0                   # push a few across / onto the wall
+    soa, bnd = soa, scenarios.soa_and_boundary([], prm, periodic=False)[1]
+    rep, ref = run_both(ctx, prm, soa, bnd)
+    off, rows = ref.rows()
+    assert np.isinf(rows[:, 0]).sum() > 10
+    assert ref.floe_outputs()["alive"].sum() < soa.n
+
+
+def test_real_concave_shapes_periodic(ctx):
+    """tiled FloeShapes.mat polygons (7..591 vertices): size classes M and L, multi-region contacts, merges"""
+    prm, Floe = scenarios.real_shape_field(12, seed=1)
+    soa = sz.floes_to_soa(Floe)
+    rep, ref = run_both(ctx, prm, soa)
+    pr = ref.pairs()
+    assert rep["pairs"] > 200 and (pr["n_regions"] > 1).sum() > 5
+    assert np.isinf(pr["overlap_state"]).sum() > 0               # kill / transfer path exercised
+    o = ref.floe_outputs()
+    assert (o["kill"] > 0).sum() > 0
+
+
+def test_real_concave_shapes_with_walls(ctx):
+    prm, Floe = scenarios.real_shape_field(8, seed=2, periodic=False)
+    soa, bnd = scenarios.soa_and_boundary(Floe, prm, periodic=False)
+    rep, ref = run_both(ctx, prm, soa, bnd)
+    off, rows = ref.rows()
+    assert np.isinf(rows[:, 0]).sum() > 3
+
+
+def test_conservation_test_scenarios(ctx):
+    """the five set-ups of the reference's test/conservation_test.m, advanced to contact"""
+    cases, modulus = scenarios.conservation_cases()
+    for name, t in (("head_on", 42000.0), ("offset", 50000.0), ("triangle_between", 30000.0), ("complex_pair", 30000.0), ("complex_wall", 60000.0)):
+        Floe = scenarios.advance(cases[name], t)
+        prm = sz.default_params(Lx=1e5, Ly=1e5, modulus=modulus, dt=10.0, periodic=0, collision=1)
+        soa, bnd = scenarios.soa_and_boundary(Floe, prm, periodic=False)
+        rep, ref = run_both(ctx, prm, soa, bnd)
+        assert rep["rows"] > 0, name
+
+
+def test_empty_and_single_floe(ctx):
+    prm, soa = sz.voronoi_field(8, seed=0)
+    one = sz.FloesSoA(soa.x[:1], soa.y[:1], soa.rmax[:1], soa.h[:1], soa.area[:1], soa.u[:1], soa.v[:1], soa.ksi[:1], soa.alive[:1],
+                      soa.voff[:2], soa.vx[:soa.voff[1]], soa.vy[:soa.voff[1]])
+    run_both(ctx, prm, one)
+    z = np.zeros(0)
+    none = sz.FloesSoA(z, z, z, z, z, z, z, z, np.zeros(0, np.uint8), np.zeros(1, np.int32), z, z)
+    s = ctx.step(prm, none)
+    assert (s.n0, s.n, s.n_pairs, s.n_rows) == (0, 0, 0, 0)
+
+
+def test_resident_step_equals_host_step(ctx):
+    prm, soa = sz.voronoi_field(4000, seed=12)
+    ctx.step(prm, soa)
+    a = ctx.floe_outputs()
+    ra = ctx.rows()
+    ctx.upload(prm, soa)
+    for _ in range(2):
+        ctx.step_resident()
+    b = ctx.floe_outputs()
+    rb = ctx.rows()
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    np.testing.assert_array_equal(ra[1], rb[1])                   # idempotent and deterministic, row for row
+
+
+def test_clip_batch_fuzz_vs_reference_clipper(ctx):
+    """the stand-alone clip entry point (mex gateway semantics) against the unmodified reference Clipper:
+    random stars, shared edges, grid-degenerate and rectilinear polygons, 3..400 vertices, all four clip types"""
+    rng = np.random.default_rng(3)
+    S = 2.0 ** 32
+
+    def star(cx, cy, r, n, jit):
+        a = rng.uniform(0, 2 * np.pi) - 2 * np.pi * np.arange(n) / n
+        rr = r * (1 - jit + jit * rng.uniform(size=n))
+        return np.stack([np.rint((cx + rr * np.cos(a)) * S), np.rint((cy + rr * np.sin(a)) * S)], 1).astype(np.int64)
+
+    subj, clip, meth = [], [], []
+    for t in range(3000):
+        kind = t % 6
+        if kind == 0:
+            d, a = 1000 + 1500 * rng.uniform(), rng.uniform(0, 6.28)
+            ox, oy = rng.uniform(-1e6, 1e6, 2)
+            s, c = star(ox, oy, 1000, rng.integers(3, 10), 0.3), star(ox + d * np.cos(a), oy + d * np.sin(a), 1000, rng.integers(3, 10), 0.3)
+        elif kind == 1:
+            d = 3000 * rng.uniform()
+            s, c = star(0, 0, 2000, rng.integers(8, 60), 0.7), star(d, 0.2 * d, 2000, rng.integers(8, 60), 0.7)
+        elif kind == 2:
+            s, c = rng.integers(0, 7, (rng.integers(3, 9), 2)), rng.integers(0, 7, (rng.integers(3, 9), 2))
+        elif kind == 3:
+            s = star(0, 0, 1500, rng.integers(4, 12), 0.4)
+            c = s[::-1].copy() + rng.integers(-3, 4, 2) * (1 << 31)
+        elif kind == 4:
+            s, c = star(0, 0, 3000, rng.integers(100, 400), 0.8), star(2000 * rng.uniform(), 500, 3000, rng.integers(100, 400), 0.8)
+        else:
+            s, c = rng.integers(0, 9, (rng.integers(3, 12), 2)) << 32, rng.integers(0, 9, (rng.integers(3, 12), 2)) << 32
+        subj.append(np.asarray(s, np.int64)); clip.append(np.asarray(c, np.int64)); meth.append(1 if t % 5 else (t // 5) % 4)
+    status, out = ctx.clip_batch(subj, clip, meth)
+    nonempty = 0
+    for k in range(len(subj)):
+        ref = oracle.ref_clip(subj[k], clip[k], meth[k])
+        if ref is None:
+            assert status[k] == sz.abi.SZ_ERR_CLIPPER, k
+            continue
+        assert status[k] == 0, (k, status[k])
+        assert len(ref) == len(out[k]), k
+        for a, b in zip(ref, out[k]):
+            assert np.array_equal(a, b), k
+        nonempty += len(ref) > 0
+    assert nonempty > 1500
+
+
+def test_full_size_properties_100k(ctx):
+    """at a size the oracle's literal loop cannot do: Newton's third law over the periodic field (every mirrored
+    row cancels its source exactly, so the column sums over the extended list vanish to rounding), row bookkeeping
+    invariants, and agreement with the oracle's grid mode on the same input"""
+    prm, soa = sz.voronoi_field(100000, seed=0)
+    rep, ref = run_both(ctx, prm, soa, broad_mode=1)
+    off, rows = ctx.rows()
+    s = ctx.summary
+    assert rows.shape[0] == s.n_rows == 2 * (ref.pairs()["n_regions"].sum())
+    scale = np.abs(rows[:, 1:3]).sum()
+    assert abs(rows[:, 1].sum()) < 1e-9 * scale and abs(rows[:, 2].sum()) < 1e-9 * scale
+    assert np.all(np.diff(off) >= 0) and off[-1] == s.n_rows
+    assert s.collision_count <= s.n_rows / 2

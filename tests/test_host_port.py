@@ -1,0 +1,151 @@
+"""The product's device code compiled for the host (tests/host/) against the checker, on the CPU:
+the Clipper-exact sweep vs the unmodified reference Clipper, and the pair force law vs the oracle's
+restatement of collisions/floe_interactions.m.  (The product never runs these on the CPU; this keeps the
+algorithmic parity checkable in the GPU-less container.  The same headers are what nvcc compiles.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import scenarios
+import subzero_b200 as sz
+from subzero_b200 import abi
+
+HOST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host")
+P = abi._ptr
+
+
+def test_clip_sweep_fuzz_vs_reference_clipper():
+    """30k random/degenerate polygon pairs (shared edges, grid points, rectilinear, 100-400 vertex stars), all four
+    clip types: path count, order, vertex order and int64 values identical to Clipper 6.4.2; includes the
+    std::sort replica self-test"""
+    r = subprocess.run([os.path.join(HOST, "clip_fuzz"), "30000", "5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches=0" in r.stdout
+
+
+@pytest.fixture(scope="module")
+def port():
+    l = C.CDLL(os.path.join(HOST, "libpair_host.so"))
+    l.szport_floe_interactions.restype = C.c_int
+    l.szport_floe_interactions.argtypes = [C.POINTER(abi.SzParams), abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, C.c_int,
+                                           abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, C.c_int, abi.c_dp, C.c_int]
+    return l
+
+
+def both(port, prm, f1, f2, is_boundary, box, small):
+    """returns (oracle, port) results as (n_rows, rows, overlap_state)"""
+    body = lambda f: np.array([f["h"], f["area"], f["Xi"], f["Yi"], f["Ui"], f["Vi"], f["ksi_ice"]], float)
+    cax, cay = np.ascontiguousarray(f1["c_alpha"][0]), np.ascontiguousarray(f1["c_alpha"][1])
+    if is_boundary:
+        c2x, c2y = np.ascontiguousarray(f2["c"][0]), np.ascontiguousarray(f2["c"][1])
+    else:
+        c2x, c2y = np.ascontiguousarray(f2["c_alpha"][0] + f2["Xi"]), np.ascontiguousarray(f2["c_alpha"][1] + f2["Yi"])
+    b1, b2 = body(f1), body(f2)
+    bx = np.ascontiguousarray(box[0]) if box is not None else np.zeros(0)
+    by = np.ascontiguousarray(box[1]) if box is not None else np.zeros(0)
+    res = []
+    for which in ("oracle", "port"):
+        rows, ov = np.zeros((64, 5)), C.c_double(0)
+        args = [C.byref(prm), P(cax, abi.c_dp), P(cay, abi.c_dp), len(cax), P(b1, abi.c_dp), P(c2x, abi.c_dp), P(c2y, abi.c_dp), len(c2x), P(b2, abi.c_dp),
+                int(is_boundary), P(bx, abi.c_dp), P(by, abi.c_dp), len(bx), P(rows, abi.c_dp), 64, C.byref(ov)]
+        n = oracle.lib().szo_floe_interactions(*args) if which == "oracle" else port.szport_floe_interactions(*args, int(small))
+        res.append((n, rows[:max(n, 0)].copy(), ov.value))
+    return res
+
+
+def assert_same(o, p, what):
+    assert o[0] == p[0], "%s: rows oracle %d port %d" % (what, o[0], p[0])
+    assert (o[2] == p[2]) or (np.isnan(o[2]) and np.isnan(p[2])), what
+    np.testing.assert_array_equal(o[1], p[1], err_msg=what)      # bit-exact: same operations in the same order
+
+
+def floe_dict(soa, i):
+    x, y = soa.outline(i)
+    return {"c_alpha": np.stack([x, y]), "Xi": soa.x[i], "Yi": soa.y[i], "h": soa.h[i], "area": soa.area[i], "Ui": soa.u[i], "Vi": soa.v[i], "ksi_ice": soa.ksi[i]}
+
+
+def test_pair_force_voronoi_pairs_small_and_big_class(port):
+    prm, soa = sz.voronoi_field(1500, seed=11)
+    ref = oracle.OracleStep(prm, soa, broad_mode=1)
+    pr = ref.pairs()
+    g = ref.ghosts()
+    n_force = 0
+    for k in range(0, len(pr["i"]), 3):
+        i, j = pr["i"][k] - 1, pr["j"][k] - 1
+        if i >= soa.n or j >= soa.n:
+            continue
+        f1, f2 = floe_dict(soa, i), floe_dict(soa, j)
+        for small in (1, 0):
+            o, p = both(port, prm, f1, f2, False, None, small)
+            assert_same(o, p, "voronoi pair %d-%d class %d" % (i, j, small))
+        n_force += o[0] > 0
+    assert n_force > 300
+
+
+def test_pair_force_real_concave_shapes(port):
+    """FloeShapes.mat polygons (7..591 vertices) placed to overlap: multi-region contacts, the general (m != 2) branch,
+    merge (+-Inf) outcomes"""
+    polys, _, modulus = scenarios.floe_shapes()
+    prm = sz.default_params(Lx=2e5, Ly=2e5, modulus=modulus, dt=10.0, periodic=1, collision=1)
+    rng = np.random.default_rng(5)
+    kinds = {"rows": 0, "multi": 0, "inf": 0, "none": 0}
+    for t in range(160):
+        a, b = polys[int(rng.integers(0, len(polys)))], polys[int(rng.integers(0, len(polys)))]
+        fa = scenarios.floe_from_polygon(a, u=rng.uniform(-.1, .1), v=rng.uniform(-.1, .1), ksi=rng.uniform(-1e-5, 1e-5))
+        fb = scenarios.floe_from_polygon(b, u=rng.uniform(-.1, .1), v=rng.uniform(-.1, .1), ksi=rng.uniform(-1e-5, 1e-5))
+        d = rng.uniform(0.05, 1.0) * (np.sqrt(fa["area"]) + np.sqrt(fb["area"])) * 0.6
+        th = rng.uniform(0, 2 * np.pi)
+        fb["Xi"], fb["Yi"] = fa["Xi"] + d * np.cos(th), fa["Yi"] + d * np.sin(th)
+        o, p = both(port, prm, fa, fb, False, None, 0)
+        assert_same(o, p, "real pair %d" % t)
+        kinds["rows"] += o[0] > 0
+        kinds["multi"] += o[0] > 1
+        kinds["inf"] += np.isinf(o[2])
+        kinds["none"] += (o[0] == 0 and not np.isinf(o[2]))
+    assert kinds["rows"] > 60 and kinds["multi"] > 5 and kinds["inf"] > 5, kinds
+
+
+def test_pair_force_wall_contacts(port):
+    """floe vs domain wall ('dif' clip, floe_interactions.m:31-40), non-periodic"""
+    polys, _, modulus = scenarios.floe_shapes()
+    L = 1e5
+    prm = sz.default_params(Lx=L, Ly=L, modulus=modulus, dt=10.0, periodic=0, collision=1)
+    c2, fb = scenarios.domain(L, L)
+    rng = np.random.default_rng(9)
+    hits = 0
+    for t in range(80):
+        v = polys[int(rng.integers(0, len(polys)))]
+        f = scenarios.floe_from_polygon(v, u=rng.uniform(-.1, .1), v=rng.uniform(-.1, .1))
+        side = t % 4
+        off = rng.uniform(-0.9, 0.6) * f["rmax"]
+        if side == 0: f["Xi"], f["Yi"] = L + off, rng.uniform(-0.5, 0.5) * L
+        if side == 1: f["Xi"], f["Yi"] = -L - off, rng.uniform(-0.5, 0.5) * L
+        if side == 2: f["Xi"], f["Yi"] = rng.uniform(-0.5, 0.5) * L, L + off
+        if side == 3: f["Xi"], f["Yi"] = L + off, L + off          # corner
+        o, p = both(port, prm, f, fb, True, c2, 0)
+        assert_same(o, p, "wall %d" % t)
+        hits += o[0] > 0
+    assert hits > 20
+
+
+def test_conservation_scenarios(port):
+    """the reference's own test set-ups (test/conservation_test.m), advanced to first contact"""
+    cases, modulus = scenarios.conservation_cases()
+    prm = sz.default_params(Lx=1e5, Ly=1e5, modulus=modulus, dt=10.0, periodic=0, collision=1)
+    c2, fb = scenarios.domain(1e5, 1e5)
+    n = 0
+    for name, t in (("head_on", 42000.0), ("offset", 50000.0), ("triangle_between", 30000.0), ("complex_pair", 30000.0)):
+        Floe = scenarios.advance(cases[name], t)
+        for a in range(len(Floe)):
+            for b in range(a + 1, len(Floe)):
+                o, p = both(port, prm, Floe[a], Floe[b], False, c2, 0)
+                assert_same(o, p, name)
+                n += o[0] > 0
+    f = scenarios.advance(cases["complex_wall"], 60000.0)[0]
+    o, p = both(port, prm, f, fb, True, c2, 0)
+    assert_same(o, p, "complex_wall")
+    assert n >= 3 and o[0] > 0

@@ -1,0 +1,149 @@
+"""The oracle against every known answer the reference holds for this path, plus hand-derived
+known answers for the MATLAB helpers.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+import scenarios
+from subzero_b200 import abi
+
+S = 2.0 ** 32
+P = abi._ptr
+
+
+def polyclip(p1, p2, method):
+    p1, p2 = np.asarray(p1, float), np.asarray(p2, float)
+    x1, y1, x2, y2 = (np.ascontiguousarray(a) for a in (p1[:, 0], p1[:, 1], p2[:, 0], p2[:, 1]))
+    ox, oy, off = np.empty(4096), np.empty(4096), np.empty(256, np.int32)
+    n = oracle.lib().szo_polyclip(P(x1, abi.c_dp), P(y1, abi.c_dp), len(x1), P(x2, abi.c_dp), P(y2, abi.c_dp), len(x2), method,
+                                  P(ox, abi.c_dp), P(oy, abi.c_dp), 4096, P(off, abi.c_ip), 256)
+    assert n >= 0
+    return [np.stack([ox[off[k]:off[k + 1]], oy[off[k]:off[k + 1]]], 1) for k in range(n)]
+
+
+def test_clipper_version_is_the_reference():
+    oracle.clipper().szref_version.restype = C.c_char_p
+    assert oracle.clipper().szref_version() == b"6.4.2"          # private/clipper.hpp:37
+
+
+def test_clipper_test_m_square_case():
+    """private/clipper_test.m:2-11: unit square ∩ unit square shifted by 0.5 -> [0.5,1]^2"""
+    p1 = [[0, 0], [1, 0], [1, 1], [0, 1]]
+    p2 = [[0.5, 0.5], [1.5, 0.5], [1.5, 1.5], [0.5, 1.5]]
+    r = polyclip(p1, p2, 1)
+    assert len(r) == 1
+    assert r[0].tolist() == [[1, 1], [0.5, 1], [0.5, 0.5], [1, 0.5]]   # SURVEY.md E.1 (the reference run here)
+    x, y = np.ascontiguousarray(r[0][:, 0]), np.ascontiguousarray(r[0][:, 1])
+    assert oracle.lib().szo_polyarea(P(x, abi.c_dp), P(y, abi.c_dp), 4) == 0.25
+
+
+def test_clipper_kats():
+    """behaviour known answers of the reference Clipper, scale 2^32, even-odd"""
+    sq = lambda x0, y0, x1, y1: [[x0, y0], [x1, y0], [x1, y1], [x0, y1]]
+    assert polyclip(sq(0, 0, 1, 1), sq(1, 0, 2, 1), 1) == []                       # shared edge
+    assert polyclip(sq(0, 0, 1, 1), sq(1, 1, 2, 2), 1) == []                       # vertex touch
+    r = polyclip(sq(0, 0, 5, 5), sq(2, 2, 3, 3), 1)
+    assert [p.tolist() for p in r] == [[[3, 3], [2, 3], [2, 2], [3, 2]]]           # contained square
+    r_cw = polyclip(sq(0, 0, 5, 5)[::-1], sq(2, 2, 3, 3)[::-1], 1)
+    assert [p.tolist() for p in r_cw] == [p.tolist() for p in r]                   # orientation-independent
+    u = [[0, 0], [3, 0], [3, 3], [2, 3], [2, 1], [1, 1], [1, 3], [0, 3]]
+    r = polyclip(u, sq(-1, 2, 4, 2.5), 1)
+    assert [p.tolist() for p in r] == [[[1, 2.5], [0, 2.5], [0, 2], [1, 2]], [[3, 2.5], [2, 2.5], [2, 2], [3, 2]]]
+    r = polyclip(sq(0, 0, 3, 3), sq(1, 1, 2, 2), 0)                                # difference -> outer + hole
+    assert len(r) == 2 and r[1].tolist() == [[1, 1], [1, 2], [2, 2], [2, 1]]
+    r = polyclip(sq(90000, 0, 100500, 1000), sq(-1e5, -1e5, 1e5, 1e5), 0)          # floe poking through the wall
+    assert [p.tolist() for p in r] == [[[100500, 1000], [100000, 1000], [100000, 0], [100500, 0]]]
+    r = polyclip([[0, 0], [1, 0], [2, 0], [2, 2], [0, 2]], sq(-1, -1, 3, 3), 1)    # collinear vertex dropped
+    assert len(r) == 1 and len(r[0]) == 4
+
+
+def test_polyshape_area_centroid_pinned_by_floeshapes_mat():
+    """462 known answers cached by MATLAB inside test/test_conservation/FloeShapes.mat (BoundaryInfo)"""
+    polys, binfo, modulus = scenarios.floe_shapes()
+    assert len(polys) == 462 and modulus == 90000000.0
+    out = np.empty(3)
+    worst_a = worst_c = 0.0
+    for v, b in zip(polys, binfo):
+        x, y = np.ascontiguousarray(v[:, 0]), np.ascontiguousarray(v[:, 1])
+        oracle.lib().szo_polyshape_area_centroid(P(x, abi.c_dp), P(y, abi.c_dp), len(x), P(out, abi.c_dp))
+        area, cx, cy = b[3], b[5], b[6]
+        worst_a = max(worst_a, abs(out[0] - area) / area)
+        worst_c = max(worst_c, np.hypot(out[1] - cx, out[2] - cy) / np.sqrt(area))
+    assert worst_a < 5e-15 and worst_c < 1e-14, (worst_a, worst_c)
+
+
+def test_matlab_int64_rounding():
+    f = oracle.lib().szo_matlab_int64
+    assert [f(v) for v in (0.5, 1.5, 2.5, -0.5, -1.5, 0.49999999999999994, -2.4, 2.6)] == [1, 2, 3, -1, -2, 0, -2, 3]
+    assert f(float("nan")) == 0 and f(1e30) == 2 ** 63 - 1 and f(-1e30) == -2 ** 63
+
+
+def interx(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    out = np.empty(512)
+    x1, y1, x2, y2 = (np.ascontiguousarray(v) for v in (a[:, 0], a[:, 1], b[:, 0], b[:, 1]))
+    n = oracle.lib().szo_interx(P(x1, abi.c_dp), P(y1, abi.c_dp), len(x1), P(x2, abi.c_dp), P(y2, abi.c_dp), len(x2), P(out, abi.c_dp), 256)
+    return out[:2 * n].reshape(n, 2)
+
+
+def test_interx_known_answers():
+    sq = np.array([[0, 0], [2, 0], [2, 2], [0, 2], [0, 0]], float)
+    p = interx(sq, sq + 1)                       # two crossings, sorted by x then y (unique(...,'rows'))
+    assert p.tolist() == [[1, 2], [2, 1]]
+    assert len(interx(sq, sq + 5)) == 0
+    p = interx(sq, sq + [2, 0])                  # shared (parallel) edge: L == 0 pairs dropped; endpoint touches kept once each
+    assert p.tolist() == [[2, 0], [2, 2]]
+    diag = np.array([[-1, -1], [3, 3]], float)
+    assert interx(sq, diag).tolist() == [[0, 0], [2, 2]]
+
+
+def test_inpolygon_known_answers():
+    xv, yv = np.array([0, 4, 4, 0.0]), np.array([0, 0, 4, 4.0])
+    px, py = np.array([2, 0, 4, 5, 2, -1e-13, 4.0]), np.array([2, 2, 4, 2, 0, 2, 4.0000001])
+    r = np.empty(len(px), np.uint8)
+    oracle.lib().szo_inpolygon(P(px, abi.c_dp), P(py, abi.c_dp), len(px), P(xv, abi.c_dp), P(yv, abi.c_dp), 4, P(r, abi.c_bp))
+    assert r.tolist() == [1, 1, 1, 0, 1, 0, 0]   # interior, edge, vertex, outside, edge, outside the bbox mask, outside
+
+
+def test_p_poly_dist_known_answers():
+    xv, yv = np.array([0, 4, 4, 0, 0.0]), np.array([0, 0, 4, 4, 0.0])
+    px, py = np.array([2, 2, 6, 5, 2.0]), np.array([2, -1, 2, 5, 0.0])
+    d = np.empty(5)
+    assert oracle.lib().szo_p_poly_dist(P(px, abi.c_dp), P(py, abi.c_dp), 5, P(xv, abi.c_dp), P(yv, abi.c_dp), 5, P(d, abi.c_dp)) == 0
+    np.testing.assert_allclose(d, [-2, 1, 2, np.sqrt(2), 0], atol=1e-15)          # negative inside; on the edge: -0 or 0
+    bad = np.array([0, 0, 4, 4, 0.0])
+    assert oracle.lib().szo_p_poly_dist(P(px, abi.c_dp), P(py, abi.c_dp), 5, P(bad, abi.c_dp), P(yv, abi.c_dp), 5, P(d, abi.c_dp)) == -1   # repeated vertex raises
+
+
+def test_broad_phase_grid_equals_literal_double_loop():
+    """the oracle's cell-grid broad phase (used beyond ~3e4 floes) is the literal O(N^2) loop, output for output"""
+    import subzero_b200 as sz
+    prm, f = sz.voronoi_field(3000, seed=3)
+    prm.want_clip_polys = 1
+    a = oracle.OracleStep(prm, f, broad_mode=0)
+    b = oracle.OracleStep(prm, f, broad_mode=1)
+    rep = oracle.compare_steps(b, a, rtol=0.0)
+    assert rep["rows_bit_exact"] and a.summary.n > a.summary.n0 and a.summary.n_pairs > 12000
+
+
+def test_two_block_head_on_force_is_equal_and_opposite():
+    """conservation_test.m:22-26 set-up, advanced until the blocks overlap by 500 m: one rectangular overlap region,
+    normal along x, rows mirrored (floe_interactions_all.m:196)"""
+    import subzero_b200 as sz
+    cases, modulus = scenarios.conservation_cases()
+    Floe = scenarios.advance(cases["head_on"], 42000.0)          # closing speed 0.25 m/s -> gap 1e4 m closes by 10500 m
+    prm = sz.default_params(Lx=1e5, Ly=1e5, modulus=modulus, dt=10.0, periodic=0, collision=1)
+    soa, bnd = scenarios.soa_and_boundary(Floe, prm, periodic=False)
+    r = oracle.OracleStep(prm, soa, bnd)
+    off, rows = r.rows()
+    assert r.summary.n_pairs == 1 and off.tolist() == [0, 1, 2]
+    a, b = rows
+    assert a[0] == 2 and b[0] == 1
+    assert a[6] == b[6] == pytest.approx(500.0 * 3e4, rel=1e-12)  # overlap area
+    np.testing.assert_array_equal(a[1:3], -b[1:3])
+    assert a[1] < 0 and abs(a[2]) < abs(a[1])                    # floe 1 (left) is pushed to -x
+    ff = modulus * 0.25 * 0.25 / (0.25 * 3e4 + 0.25 * 3e4)      # floe_interactions.m:12, sqrt(area) = 3e4
+    assert abs(a[1]) <= ff * a[6] * (1 + 0.2) * (1 + 1e-12)     # normal + Coulomb-capped tangential
+    assert r.summary.collision_count == 1.0
