@@ -1367,40 +1367,54 @@ struct ClipEngine {
     }
 
     // ---------------------------------------------------------------- Execute (:1508-1525, :1560-1621)
-    // Returns ST_OK with the solution left in orec/op (read it with emit()), or an error status.
-    SZ_HDN int execute()
+    // The sweep is exposed step by step so that a warp running 32 independent clips can re-converge
+    // between the phases of every scanbeam (sz_pairforce.cuh: run_sweep); execute() is the same sequence
+    // for a single caller.  After the sweep the solution is left in orec/op (read it with emit()).
+    i64 sw_top_y;
+    // Reset() :1247-1276 + the first PopScanbeam / InsertLocalMinimaIntoAEL of ExecuteInternal :1569-1571.
+    // Returns true while the sweep has scanbeams to process.
+    SZ_HDN bool sweep_begin()
     {
-        if (status != ST_OK) return status;
-        if (n_lm == 0) return (status = ST_CLIPPER_FAIL);      // Reset(): nothing to process -> PopScanbeam fails
-        stl_sort(lm, n_lm, LocMinLess());                      // Reset() :1247-1276
+        if (status != ST_OK) return false;
+        if (n_lm == 0) { status = ST_CLIPPER_FAIL; return false; }    // nothing to process -> PopScanbeam fails
+        stl_sort(lm, n_lm, LocMinLess());
         for (int i = 0; i < n_lm; ++i) {
             insert_scanbeam(lm[i].y);
             Edge& l = ed[lm[i].left];  l.cur = l.bot; l.side = 1; l.out = -1;
             Edge& r = ed[lm[i].right]; r.cur = r.bot; r.side = 2; r.out = -1;
         }
-        ael = NIL; sel = NIL; cur_lm = 0;
-        i64 bot_y, top_y = 0;
-        if (!pop_scanbeam(bot_y)) return (status = ST_CLIPPER_FAIL);
+        ael = NIL; sel = NIL; cur_lm = 0; sw_top_y = 0;
+        i64 bot_y;
+        if (!pop_scanbeam(bot_y)) { status = ST_CLIPPER_FAIL; return false; }
         insert_local_minima(bot_y);
-        while (pop_scanbeam(top_y) || cur_lm < n_lm) {
-            process_horizontals();
-            n_gj = 0;
-            if (!process_intersections(top_y)) { fail(ST_CLIPPER_FAIL); break; }
-            process_edges_at_top(top_y);
-            if (status != ST_OK) break;
-            bot_y = top_y;
-            insert_local_minima(bot_y);
-            if (status != ST_OK) break;
-        }
-        if (status != ST_OK) return status;
-        // orientation fix (:1594-1600)
+        return status == ST_OK;
+    }
+    SZ_HD bool sweep_next() { return pop_scanbeam(sw_top_y) || cur_lm < n_lm; }     // :1572
+    SZ_HDN bool sweep_intersections()                                               // :1574-1576
+    {
+        process_horizontals();
+        n_gj = 0;
+        if (!process_intersections(sw_top_y)) { fail(ST_CLIPPER_FAIL); return false; }
+        return status == ST_OK;
+    }
+    SZ_HD bool sweep_top() { process_edges_at_top(sw_top_y); return status == ST_OK; }   // :1577
+    SZ_HDN bool sweep_minima() { insert_local_minima(sw_top_y); return status == ST_OK; }   // :1578-1579
+    SZ_HDN void sweep_finish()                                                      // :1594-1613
+    {
+        if (status != ST_OK) return;
         for (int i = 0; i < n_or; ++i) {
             if (orec[i].pts == NIL) continue;
             if (orec[i].hole == (ring_area(orec[i].pts) > 0)) reverse_links(orec[i].pts);
         }
         if (n_jn > 0) join_common_edges();
-        if (status != ST_OK) return status;
+        if (status != ST_OK) return;
         for (int i = 0; i < n_or; ++i) if (orec[i].pts != NIL) fixup_out_polygon((idx_t)i);
+    }
+    SZ_HD int execute()
+    {
+        bool run = sweep_begin();
+        while (run && sweep_next()) run = sweep_intersections() && sweep_top() && sweep_minima();
+        sweep_finish();
         return status;
     }
     struct LocMinLess { SZ_HD bool operator()(const LocMin& a, const LocMin& b) const { return b.y < a.y; } };   // :125-131

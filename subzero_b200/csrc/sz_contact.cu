@@ -702,7 +702,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     CKS(read_counters(c));
     int nM = wall ? c->h_cnt->wlistM : c->h_cnt->listM;
     if (nM > 0) {
-        const int threads = std::min(nM, 148 * 64);
+        const int threads = std::min((nM + 63) / 64 * 64, 148 * 64);
         CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
         a.list = lstM; a.list_count = cntM; a.next_list = lstL; a.next_count = cntL; a.scratch = c->scratchM.p; a.n_threads = threads;
         ++g_launches; sz_launch_narrow_M(&a, st);
@@ -710,7 +710,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         CKS(read_counters(c));
         int nL = wall ? c->h_cnt->wlistL : c->h_cnt->listL;
         if (nL > 0) {
-            const int threadsL = std::min(nL, 148 * 8);
+            const int threadsL = std::min((nL + 63) / 64 * 64, 148 * 8);
             CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
             a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
             ++g_launches; sz_launch_narrow_L(&a, st);
@@ -1031,14 +1031,14 @@ extern "C" int sz_clip_batch(SzContext* c, int32_t count, const int32_t* method,
         CK(cudaGetLastError());
         CKS(read_counters(c));
         if (c->h_cnt->clip_listM > 0) {
-            const int threads = std::min(c->h_cnt->clip_listM, 148 * 64);
+            const int threads = std::min((c->h_cnt->clip_listM + 63) / 64 * 64, 148 * 64);
             CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
             a.list = c->c_listM.p; a.list_count = D_CNT(clip_listM); a.next_list = c->c_listL.p; a.next_count = D_CNT(clip_listL); a.scratch = c->scratchM.p; a.n_threads = threads;
             ++g_launches; sz_launch_clip_M(&a, st);
             CK(cudaGetLastError());
             CKS(read_counters(c));
             if (c->h_cnt->clip_listL > 0) {
-                const int threadsL = std::min(c->h_cnt->clip_listL, 148 * 8);
+                const int threadsL = std::min((c->h_cnt->clip_listL + 63) / 64 * 64, 148 * 8);
                 CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
                 a.list = c->c_listL.p; a.list_count = D_CNT(clip_listL); a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
                 ++g_launches; sz_launch_clip_L(&a, st);

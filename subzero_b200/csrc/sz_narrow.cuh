@@ -84,36 +84,45 @@ struct SizeSink { int paths, verts; SZ_HD void begin_path(int c) { ++paths; vert
 
 #if defined(__CUDACC__)
 
+// All 32 lanes of a warp call this together (szpf::pair_force is warp-synchronous); `valid` says whether
+// the lane has a pair.
 template <class C>
-__device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, szpf::Workspace<C>& w)
+__device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool valid, szpf::Workspace<C>& w)
 {
-    int i, j = -1;
+    int i = 0, j = -1;
     Body b1, b2;
-    if (a.wall && k < a.P.Nb) return;     // floes below Nb take no part in the pair loop (floe_interactions_all.m:125)
-    if (a.wall) { i = a.first_floe + k; b2 = a.bbody; }
-    else { i = a.pi[k]; j = a.pj[k]; }
-    const int si = a.esrc[i];
-    const int o1 = a.voff[si], n1 = a.voff[si + 1] - o1;
-    int o2 = 0, n2 = a.bn, sj = 0;
-    if (!a.wall) { sj = a.esrc[j]; o2 = a.voff[sj]; n2 = a.voff[sj + 1] - o2; }
-    // + 1: room for the closing vertex of floe_interactions.m:62-67
-    if (n1 + 1 > C::NV || n2 + 1 > C::NV || n1 < 1 || n2 < 1) {
-        if (n1 >= 1 && n2 >= 1 && a.next_list) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
-        else { a.status[k] = (n1 < 1 || n2 < 1) ? szpf::PS_BAD_POLY : szpf::PS_CAPACITY; a.nrows[k] = 0; a.ovl_state[k] = 0; }
-        return;
-    }
-    b1.h = a.h[si]; b1.area = a.area[si]; b1.Xi = a.ex[i]; b1.Yi = a.ey[i]; b1.Ui = a.u[si]; b1.Vi = a.v[si]; b1.ksi = a.ksi[si];
-    w.n1 = n1; w.n2 = n2;
-    for (int t = 0; t < n1; ++t) { w.c1x[t] = a.vx[o1 + t] + b1.Xi; w.c1y[t] = a.vy[o1 + t] + b1.Yi; }       // floe_interactions.m:25
-    if (a.wall) { for (int t = 0; t < n2; ++t) { w.c2x[t] = a.bx[t]; w.c2y[t] = a.by[t]; } }                    // :31-32
-    else {
-        b2.h = a.h[sj]; b2.area = a.area[sj]; b2.Xi = a.ex[j]; b2.Yi = a.ey[j]; b2.Ui = a.u[sj]; b2.Vi = a.v[sj]; b2.ksi = a.ksi[sj];
-        for (int t = 0; t < n2; ++t) { w.c2x[t] = a.vx[o2 + t] + b2.Xi; w.c2y[t] = a.vy[o2 + t] + b2.Yi; }    // floe_interactions_all.m:105
+    b1.h = b1.area = b1.Xi = b1.Yi = b1.Ui = b1.Vi = b1.ksi = 0; b2 = b1;
+    if (valid && a.wall && k < a.P.Nb) valid = false;     // floes below Nb take no part in the pair loop (floe_interactions_all.m:125)
+    bool escalate = false;
+    if (valid) {
+        if (a.wall) { i = a.first_floe + k; b2 = a.bbody; }
+        else { i = a.pi[k]; j = a.pj[k]; }
+        const int si = a.esrc[i];
+        const int o1 = a.voff[si], n1 = a.voff[si + 1] - o1;
+        int o2 = 0, n2 = a.bn, sj = 0;
+        if (!a.wall) { sj = a.esrc[j]; o2 = a.voff[sj]; n2 = a.voff[sj + 1] - o2; }
+        // + 1: room for the closing vertex of floe_interactions.m:62-67
+        if (n1 + 1 > C::NV || n2 + 1 > C::NV || n1 < 1 || n2 < 1) {
+            if (n1 >= 1 && n2 >= 1 && a.next_list) escalate = true;
+            else { a.status[k] = (n1 < 1 || n2 < 1) ? szpf::PS_BAD_POLY : szpf::PS_CAPACITY; a.nrows[k] = 0; a.ovl_state[k] = 0; if (a.want_polys) a.poly_npaths[k] = 0; }
+            valid = false;
+        } else {
+            b1.h = a.h[si]; b1.area = a.area[si]; b1.Xi = a.ex[i]; b1.Yi = a.ey[i]; b1.Ui = a.u[si]; b1.Vi = a.v[si]; b1.ksi = a.ksi[si];
+            w.n1 = n1; w.n2 = n2;
+            for (int t = 0; t < n1; ++t) { w.c1x[t] = a.vx[o1 + t] + b1.Xi; w.c1y[t] = a.vy[o1 + t] + b1.Yi; }       // floe_interactions.m:25
+            if (a.wall) { for (int t = 0; t < n2; ++t) { w.c2x[t] = a.bx[t]; w.c2y[t] = a.by[t]; } }                    // :31-32
+            else {
+                b2.h = a.h[sj]; b2.area = a.area[sj]; b2.Xi = a.ex[j]; b2.Yi = a.ey[j]; b2.Ui = a.u[sj]; b2.Vi = a.v[sj]; b2.ksi = a.ksi[sj];
+                for (int t = 0; t < n2; ++t) { w.c2x[t] = a.vx[o2 + t] + b2.Xi; w.c2y[t] = a.vy[o2 + t] + b2.Yi; }    // floe_interactions_all.m:105
+            }
+        }
     }
     szpf::PairResult res;
     double rows[C::ROWS * 5];
-    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows);
-    if (res.status == szpf::PS_CAPACITY && a.next_list) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; return; }
+    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid);
+    if (valid && res.status == szpf::PS_CAPACITY && a.next_list) { escalate = true; valid = false; }
+    if (escalate) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
+    if (!valid) return;
     a.status[k] = res.status; a.ovl_state[k] = res.overlap_state;
     int nr = (res.status == szpf::PS_OK) ? res.n_rows : 0;
     a.nrows[k] = nr;
@@ -142,20 +151,22 @@ template <class C>
 __global__ void __launch_bounds__(128) narrow_local_kernel(const NarrowArgs a)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n_work) return;
     szpf::Workspace<C> w;
-    resolve_pair<C>(a, k, w);
+    resolve_pair<C>(a, k, k < a.n_work, w);
 }
 
-// classes M/L: arena in HBM scratch, persistent threads striding over the work list
+// classes M/L: arena in HBM scratch, persistent threads striding over the work list (n_threads is a
+// multiple of the block size, so whole warps stay together)
 template <class C>
 __global__ void __launch_bounds__(64) narrow_scratch_kernel(const NarrowArgs a)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= a.n_threads) return;
     szpf::Workspace<C>& w = reinterpret_cast<szpf::Workspace<C>*>(a.scratch)[tid];
     const int n = *a.list_count;
-    for (int t = tid; t < n; t += a.n_threads) resolve_pair<C>(a, a.list[t], w);
+    for (int base = 0; base < n; base += a.n_threads) {
+        const int t = base + tid;
+        resolve_pair<C>(a, t < n ? a.list[t] : 0, t < n, w);
+    }
 }
 
 template <class CC>

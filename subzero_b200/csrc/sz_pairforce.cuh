@@ -79,35 +79,62 @@ struct RegionSink {       // collects emitted paths into (x,y,off) pools; flags 
     SZ_HD void point(P64 p) { if (overflow) return; x[n_pts] = p.x; y[n_pts] = p.y; ++n_pts; off[n_paths] = n_pts; }
 };
 struct CountSink { int n; SZ_HD void begin_path(int) { ++n; } SZ_HD void point(P64) {} };
-struct ShiftedOutline {   // [X1new' Y1new'] packed by polyclip.m:66
+// ------------------------------------------------------------------------------------------------
+// Warp-synchronous execution.  On the GPU the 32 lanes of a warp resolve 32 independent pairs.  Left to
+// itself the hardware lets the lanes drift apart in the branchy sweep (the first profile showed 4 of 32
+// lanes active on average), so the force law below is written as a per-lane phase machine around ONE
+// clip site, and the lanes re-converge explicitly before every clip and between the phases of every
+// scanbeam.  All 32 lanes of a warp must call pair_force() together (lanes without a pair pass
+// valid = false).  On the host the macros collapse and the same code handles one pair.
+#if defined(__CUDA_ARCH__)
+#define SZ_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#define SZ_WARP_SYNC() __syncwarp()
+#else
+#define SZ_WARP_ANY(p) (p)
+#define SZ_WARP_SYNC() ((void)0)
+#endif
+
+// the subject / clip path of the next clip: either a world outline shifted by (dx,dy) and packed like
+// polyclip.m:66, or a Clipper result ring fed back in (int64(double(X)/2^32*2^32))
+struct ClipInput {
     const double* x; const double* y; double dx, dy;
-    SZ_HD P64 operator()(int i) const { P64 p; p.x = matlab_int64((x[i] + dx) * SZ_SCALE); p.y = matlab_int64((y[i] + dy) * SZ_SCALE); return p; }
-};
-struct IntRing {          // a Clipper result fed back as input: int64(double(X)/2^32*2^32) == X for |X| < 2^53
-    const i64* x; const i64* y;
+    const i64* ix; const i64* iy;
+    int n; int ring;
     SZ_HD P64 operator()(int i) const
     {
         P64 p;
-        p.x = matlab_int64(((double)x[i] / SZ_SCALE) * SZ_SCALE);
-        p.y = matlab_int64(((double)y[i] / SZ_SCALE) * SZ_SCALE);
+        if (ring) { p.x = matlab_int64(((double)ix[i] / SZ_SCALE) * SZ_SCALE); p.y = matlab_int64(((double)iy[i] / SZ_SCALE) * SZ_SCALE); }
+        else { p.x = matlab_int64((x[i] + dx) * SZ_SCALE); p.y = matlab_int64((y[i] + dy) * SZ_SCALE); }
         return p;
     }
 };
 
-// one polyclip() call: returns PS_OK / error; paths land in (ox,oy,ooff,*on)
-template <class C, class GS, class GC>
-SZ_HD int run_clip(Workspace<C>& w, int method, const GS& subj, int ns, const GC& clip, int nc, i64* ox, i64* oy, int* ooff, int* on)
+// One polyclip() call per participating lane (want = false: the lane only keeps the warp company).
+// Returns PS_OK / PS_CAPACITY / PS_CLIPPER_FAIL; the solution stays in eng (read it with emit()).
+template <class E>
+SZ_HDN int run_sweep(E& eng, bool want, int method, const ClipInput& subj, const ClipInput& clip)
 {
-    w.eng.begin(method);
-    w.eng.add_path(subj, ns, 0);
-    w.eng.add_path(clip, nc, 1);
-    int st = w.eng.execute();
-    if (st == szclip::ST_OVERFLOW) return PS_CAPACITY;
-    if (st != szclip::ST_OK) return PS_CLIPPER_FAIL;
-    RegionSink<C> sink(ox, oy, ooff);
-    w.eng.emit(sink);
-    if (sink.overflow) return PS_CAPACITY;
-    *on = sink.n_paths;
+    bool run = false;
+    if (want) {
+        eng.begin(method);
+        eng.add_path(subj, subj.n, 0);
+        eng.add_path(clip, clip.n, 1);
+        run = eng.sweep_begin();
+    }
+    for (;;) {
+        SZ_WARP_SYNC();
+        if (run) run = eng.sweep_next();
+        if (!SZ_WARP_ANY(run)) break;
+        if (run) run = eng.sweep_intersections();
+        SZ_WARP_SYNC();
+        if (run) run = eng.sweep_top();
+        SZ_WARP_SYNC();
+        if (run) run = eng.sweep_minima();
+    }
+    if (!want) return PS_OK;
+    eng.sweep_finish();
+    if (eng.status == szclip::ST_OVERFLOW) return PS_CAPACITY;
+    if (eng.status != szclip::ST_OK) return PS_CLIPPER_FAIL;
     return PS_OK;
 }
 
@@ -253,165 +280,207 @@ SZ_HD bool outline_ok_for_poly_dist(const Workspace<C>& w)   // p_poly_dist.m:16
 // The force law.  On entry w.c1*/w.c2* hold the two world outlines exactly as the reference builds
 // them (floe_interactions.m:25, floe_interactions_all.m:105; for the wall c2 = hole vertices).
 // rows[r*5 + {0..4}] = Fx, Fy, Px, Py, overlap  for r < res.n_rows.
+//
+// Phase machine (one loop iteration = at most one Clipper execution per lane):
+//   PH_CLIP1  clip #1 (:29/:34)        -> regions, areas, merge test, InterX (:43-84); first region
+//   PH_CLIP2  clip #2 (:152-155)       -> the re-clip after the 1 m nudge along force_dir
+//   PH_CLIP3  clip #3.. (:158)         -> one per new region: does it meet region k?  (toggles the sign)
+// After the last clip of a region its force row is written (:167-187) and the next region's contact
+// direction (:96-150) is prepared.
 template <class C>
-SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows)
+SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true)
 {
+    enum { PH_CLIP1 = 0, PH_CLIP2 = 1, PH_CLIP3 = 2, PH_DONE = 3 };
     res.status = PS_OK; res.n_rows = 0; res.overlap_state = 0;
-    double h1 = f1.h; const double h2 = f2.h;
-    double r1 = sqrt(f1.area); const double r2 = sqrt(f2.area);
-    double force_factor = P.modulus * (h1 * h2) / (h1 * r2 + h2 * r1);
-    double overlap = 0;
-    if (boundary) force_factor = P.modulus * h1 / r1;
-    else if (r1 > P.big_floe_r || r2 > P.big_floe_r) {
-        r1 = r1 < r2 ? r1 : r2; h1 = h1 < h2 ? h1 : h2;
-        force_factor = P.modulus * h1 / r1;
-    }
+    int phase = valid ? PH_CLIP1 : PH_DONE;
+    double force_factor = 0, overlap = 0, amin = 0;
     const double G = P.modulus / (2 * (1 + P.nu)), mu = P.mu;
     const int method = boundary ? 0 : 1;
-
-    // clip #1
-    {
-        ShiftedOutline s1{w.c1x, w.c1y, 0.0, 0.0}, s2{w.c2x, w.c2y, 0.0, 0.0};
-        int st = run_clip(w, method, s1, w.n1, s2, w.n2, w.rax, w.ray, w.ra_off, &w.ra_n);
-        if (st != PS_OK) { res.status = st; return; }
-    }
-    if (boundary && w.ra_n > 0) {
-        if (ring_polyarea(w.rax, w.ray, w.ra_off[1]) / f1.area > P.wall_frac) overlap = SZ_INF;
-    }
-    double sum_ar = 0;
-    for (int k = 0; k < w.ra_n; ++k) {
-        double a, cx, cy;
-        ring_area_centroid(w.rax + w.ra_off[k], w.ray + w.ra_off[k], w.ra_off[k + 1] - w.ra_off[k], a, cx, cy);
-        w.ar[k] = a; sum_ar += a;
-    }
-    {   // merge test (:54-60)
-        bool guard = P.periodic != 0;
-        if (!guard && P.has_box) {
-            double xmx = w.c1x[0], xmn = w.c1x[0], ymx = w.c1y[0], ymn = w.c1y[0];
-            for (int i = 1; i < w.n1; ++i) {
-                if (w.c1x[i] > xmx) xmx = w.c1x[i]; if (w.c1x[i] < xmn) xmn = w.c1x[i];
-                if (w.c1y[i] > ymx) ymx = w.c1y[i]; if (w.c1y[i] < ymn) ymn = w.c1y[i];
-            }
-            guard = (xmx < P.bxmax && xmn > P.bxmin && ymx < P.bymax && ymn > P.bymin) || f2.area < P.domain_area_frac * P.barea;
-        }
-        if (guard) {
-            if (sum_ar / f1.area > P.merge_frac) overlap = SZ_INF;
-            else if (sum_ar / f2.area > P.merge_frac) overlap = -SZ_INF;
+    if (valid) {
+        double h1 = f1.h; const double h2 = f2.h;
+        double r1 = sqrt(f1.area); const double r2 = sqrt(f2.area);
+        force_factor = P.modulus * (h1 * h2) / (h1 * r2 + h2 * r1);                  // :12
+        if (boundary) force_factor = P.modulus * h1 / r1;                             // :13-14
+        else if (r1 > P.big_floe_r || r2 > P.big_floe_r) {                            // :15-19
+            r1 = r1 < r2 ? r1 : r2; h1 = h1 < h2 ? h1 : h2;
+            force_factor = P.modulus * h1 / r1;
         }
     }
-    // close the outlines when their ends are more than close_gap apart (:62-67); capacity reserved by the caller
-    {
-        double gx = w.c1x[0] - w.c1x[w.n1 - 1], gy = w.c1y[0] - w.c1y[w.n1 - 1];
-        if (sqrt(gx * gx + gy * gy) > P.close_gap) { w.c1x[w.n1] = w.c1x[0]; w.c1y[w.n1] = w.c1y[0]; ++w.n1; }
-        gx = w.c2x[0] - w.c2x[w.n2 - 1]; gy = w.c2y[0] - w.c2y[w.n2 - 1];
-        if (sqrt(gx * gx + gy * gy) > P.close_gap) { w.c2x[w.n2] = w.c2x[0]; w.c2y[w.n2] = w.c2y[0]; ++w.n2; }
-    }
-    if (!interx(w)) { res.status = PS_CAPACITY; return; }
-    res.overlap_state = overlap;
-    if (w.np < 2 || overlap == SZ_INF || overlap == -SZ_INF || w.ra_n == 0) return;   // :71-74 zero force
-    res.overlap_state = 0;
-
-    const int N1 = w.n1 - 1, N2 = w.n2 - 1;
-    const double amin = (double)(N1 < N2 ? N1 : N2) * P.amin_per_vertex;
-    int n_rows = 0;
+    int k = 0, ii = 0, n_rows = 0, nr = 0;
+    const i64* RX = w.rax; const i64* RY = w.ray;
+    double fdx = 0, fdy = 0, dl = 0, pcx = 0, pcy = 0, Ak = 0;
     bool outline_checked = false, outline_ok = true;
-    for (int k = 0; k < w.ra_n; ++k) {
-        if (w.ar[k] < amin) continue;                                   // :83
-        if (n_rows >= C::ROWS) { res.status = PS_CAPACITY; return; }
-        const i64* RX = w.rax + w.ra_off[k]; const i64* RY = w.ray + w.ra_off[k];
-        const int nr = w.ra_off[k + 1] - w.ra_off[k];
-        const double Ak = w.ar[k];
-        double a_unused, cx, cy;
-        ring_area_centroid(RX, RY, nr, a_unused, cx, cy);
-        // dsearchn + dist<1 (:98-100)
-        int m = 0; double p0x = 0, p0y = 0, p1x = 0, p1y = 0;
-        for (int q = 0; q < w.np; ++q) {
-            double best = SZ_INF; int bi = 0;
-            for (int v = 0; v < nr; ++v) {
-                double dx = (double)RX[v] / SZ_SCALE - w.px[q], dy = (double)RY[v] / SZ_SCALE - w.py[q];
-                double d2 = dx * dx + dy * dy;
-                if (d2 < best) { best = d2; bi = v; }
-            }
-            if (sqrt(best) < P.vertex_match_tol) {
-                if (m == 0) { p0x = (double)RX[bi] / SZ_SCALE; p0y = (double)RY[bi] / SZ_SCALE; }
-                else if (m == 1) { p1x = (double)RX[bi] / SZ_SCALE; p1y = (double)RY[bi] / SZ_SCALE; }
-                ++m;
-            }
+
+    for (;;) {
+        if (!SZ_WARP_ANY(phase != PH_DONE)) break;
+        // ---- the clip this lane needs now
+        ClipInput subj, clip;
+        subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = w.n1; subj.ring = 0;
+        clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = w.n2; clip.ring = 0;
+        int m_now = method;
+        if (phase == PH_CLIP2) { subj.dx = fdx; subj.dy = fdy; }
+        else if (phase == PH_CLIP3) {
+            subj.ring = 1; subj.ix = w.rbx + w.rb_off[ii]; subj.iy = w.rby + w.rb_off[ii]; subj.n = w.rb_off[ii + 1] - w.rb_off[ii];
+            clip.ring = 1; clip.ix = RX; clip.iy = RY; clip.n = nr;
+            m_now = 1;
         }
-        double fdx = 0, fdy = 0, dl = 0, pcx = cx, pcy = cy;
-        if (Ak == 0) { pcx = 0; pcy = 0; }
-        else if (m == 2) {
-            double xgh = p1x - p0x, ygh = p1y - p0y;
-            double b = sqrt(xgh * xgh + ygh * ygh);
-            fdx = -ygh / b; fdy = xgh / b; dl = b;
-        } else if (m != 0) {
-            // general branch (:117-137), streamed edge by edge
-            if (!outline_checked) { outline_ok = outline_ok_for_poly_dist(w); outline_checked = true; }
-            if (!outline_ok) { res.status = PS_BAD_POLY; return; }
-            double xmin = SZ_INF, xmax = -SZ_INF, ymin = SZ_INF, ymax = -SZ_INF;
-            for (int v = 0; v < nr; ++v) {
-                double x = (double)RX[v] / SZ_SCALE, y = (double)RY[v] / SZ_SCALE;
-                if (x < xmin) xmin = x; if (x > xmax) xmax = x; if (y < ymin) ymin = y; if (y > ymax) ymax = y;
+        const int st = run_sweep(w.eng, phase != PH_DONE, m_now, subj, clip);
+        if (phase == PH_DONE) continue;
+        if (st != PS_OK) { res.status = st; phase = PH_DONE; continue; }
+
+        bool next_region = false;       // prepare the contact direction of region k
+        bool finish_region = false;     // clips of region k are done: write its row
+        if (phase == PH_CLIP1) {
+            RegionSink<C> sink(w.rax, w.ray, w.ra_off);
+            w.eng.emit(sink);
+            if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
+            w.ra_n = sink.n_paths;
+            if (boundary && w.ra_n > 0) {                                             // :35-40
+                if (ring_polyarea(w.rax, w.ray, w.ra_off[1]) / f1.area > P.wall_frac) overlap = SZ_INF;
             }
-            double sx = 0, sy = 0, sb = 0; int non = 0;
-            for (int e = 0; e < nr; ++e) {
-                int e1 = (e + 1 == nr) ? 0 : e + 1;
-                double xa = (double)RX[e] / SZ_SCALE, ya = (double)RY[e] / SZ_SCALE, xb = (double)RX[e1] / SZ_SCALE, yb = (double)RY[e1] / SZ_SCALE;
-                double xgh = xb - xa, ygh = yb - ya, xm = (xb + xa) / 2, ym = (yb + ya) / 2;
+            double sum_ar = 0;                                                        // :43-51
+            for (int q = 0; q < w.ra_n; ++q) {
+                double a, cx, cy;
+                ring_area_centroid(w.rax + w.ra_off[q], w.ray + w.ra_off[q], w.ra_off[q + 1] - w.ra_off[q], a, cx, cy);
+                w.ar[q] = a; sum_ar += a;
+            }
+            {   // merge test (:54-60)
+                bool guard = P.periodic != 0;
+                if (!guard && P.has_box) {
+                    double xmx = w.c1x[0], xmn = w.c1x[0], ymx = w.c1y[0], ymn = w.c1y[0];
+                    for (int i = 1; i < w.n1; ++i) {
+                        if (w.c1x[i] > xmx) xmx = w.c1x[i];
+                        if (w.c1x[i] < xmn) xmn = w.c1x[i];
+                        if (w.c1y[i] > ymx) ymx = w.c1y[i];
+                        if (w.c1y[i] < ymn) ymn = w.c1y[i];
+                    }
+                    guard = (xmx < P.bxmax && xmn > P.bxmin && ymx < P.bymax && ymn > P.bymin) || f2.area < P.domain_area_frac * P.barea;
+                }
+                if (guard) {
+                    if (sum_ar / f1.area > P.merge_frac) overlap = SZ_INF;
+                    else if (sum_ar / f2.area > P.merge_frac) overlap = -SZ_INF;
+                }
+            }
+            // close the outlines when their ends are more than close_gap apart (:62-67); capacity reserved by the caller
+            {
+                double gx = w.c1x[0] - w.c1x[w.n1 - 1], gy = w.c1y[0] - w.c1y[w.n1 - 1];
+                if (sqrt(gx * gx + gy * gy) > P.close_gap) { w.c1x[w.n1] = w.c1x[0]; w.c1y[w.n1] = w.c1y[0]; ++w.n1; }
+                gx = w.c2x[0] - w.c2x[w.n2 - 1]; gy = w.c2y[0] - w.c2y[w.n2 - 1];
+                if (sqrt(gx * gx + gy * gy) > P.close_gap) { w.c2x[w.n2] = w.c2x[0]; w.c2y[w.n2] = w.c2y[0]; ++w.n2; }
+            }
+            if (!interx(w)) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
+            res.overlap_state = overlap;
+            if (w.np < 2 || overlap == SZ_INF || overlap == -SZ_INF || w.ra_n == 0) { phase = PH_DONE; continue; }   // :71-74 zero force
+            res.overlap_state = 0;
+            const int N1 = w.n1 - 1, N2 = w.n2 - 1;
+            amin = (double)(N1 < N2 ? N1 : N2) * P.amin_per_vertex;                   // :79
+            k = -1; next_region = true;
+        } else if (phase == PH_CLIP2) {
+            RegionSink<C> sink(w.rbx, w.rby, w.rb_off);
+            w.eng.emit(sink);
+            if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
+            w.rb_n = sink.n_paths;
+            ii = 0;
+            if (w.rb_n > 0) phase = PH_CLIP3; else finish_region = true;
+        } else {   // PH_CLIP3: clip #3 only needs "empty or not" (:159)
+            CountSink cs; cs.n = 0;
+            w.eng.emit(cs);
+            if (cs.n > 0) {
+                const double anew = ring_polyarea(w.rbx + w.rb_off[ii], w.rby + w.rb_off[ii], w.rb_off[ii + 1] - w.rb_off[ii]);   // :160
+                if (anew / Ak - 1 > 0) { fdx = -fdx; fdy = -fdy; }                     // :161-163
+            }
+            ++ii;
+            if (ii >= w.rb_n) finish_region = true;
+        }
+
+        if (finish_region) {
+            const double fx = fdx * Ak * force_factor, fy = fdy * Ak * force_factor;  // :167
+            // tangential (:170-183)
+            const double v1x = f1.Ui + f1.ksi * (pcx - f1.Xi), v1y = f1.Vi + f1.ksi * (pcy - f1.Yi);
+            const double v2x = f2.Ui + f2.ksi * (pcx - f2.Xi), v2y = f2.Vi + f2.ksi * (pcy - f2.Yi);
+            const double vtx = v1x - v2x, vty = v1y - v2y;
+            const double vn = sqrt(vtx * vtx + vty * vty);
+            double dtx = 0, dty = 0;
+            if (!((fabs(vtx) > fabs(vty) ? fabs(vtx) : fabs(vty)) == 0)) { dtx = vtx / vn; dty = vty / vn; }
+            const double dotv = dtx * vtx + dty * vty;
+            const double coef = -dotv * dl * G * vn;
+            double ftx = coef * dtx * P.dt, fty = coef * dty * P.dt;
+            const double fnorm = sqrt(fx * fx + fy * fy);
+            if (sqrt(ftx * ftx + fty * fty) > mu * fnorm) { ftx = -mu * fnorm * dtx; fty = -mu * fnorm * dty; }
+            double* r = rows + (size_t)n_rows * 5;
+            r[0] = fx + ftx; r[1] = fy + fty; r[2] = pcx; r[3] = pcy; r[4] = Ak;
+            ++n_rows;
+            next_region = true;
+        }
+
+        if (next_region) {
+            // advance to the next region with Ar >= Amin (:83)
+            ++k;
+            while (k < w.ra_n && w.ar[k] < amin) ++k;
+            if (k >= w.ra_n) { phase = PH_DONE; continue; }
+            if (n_rows >= C::ROWS) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
+            RX = w.rax + w.ra_off[k]; RY = w.ray + w.ra_off[k];
+            nr = w.ra_off[k + 1] - w.ra_off[k];
+            Ak = w.ar[k];
+            double a_unused, cx, cy;
+            ring_area_centroid(RX, RY, nr, a_unused, cx, cy);                         // :96-97
+            // dsearchn + dist<1 (:98-100)
+            int m = 0; double p0x = 0, p0y = 0, p1x = 0, p1y = 0;
+            for (int q = 0; q < w.np; ++q) {
+                double best = SZ_INF; int bi = 0;
+                for (int v = 0; v < nr; ++v) {
+                    double dx = (double)RX[v] / SZ_SCALE - w.px[q], dy = (double)RY[v] / SZ_SCALE - w.py[q];
+                    double d2 = dx * dx + dy * dy;
+                    if (d2 < best) { best = d2; bi = v; }
+                }
+                if (sqrt(best) < P.vertex_match_tol) {
+                    if (m == 0) { p0x = (double)RX[bi] / SZ_SCALE; p0y = (double)RY[bi] / SZ_SCALE; }
+                    else if (m == 1) { p1x = (double)RX[bi] / SZ_SCALE; p1y = (double)RY[bi] / SZ_SCALE; }
+                    ++m;
+                }
+            }
+            fdx = 0; fdy = 0; dl = 0; pcx = cx; pcy = cy;
+            if (Ak == 0) { pcx = 0; pcy = 0; }                                        // :103-106
+            else if (m == 2) {                                                        // :107-112
+                double xgh = p1x - p0x, ygh = p1y - p0y;
                 double b = sqrt(xgh * xgh + ygh * ygh);
-                double nx = -ygh / b, ny = xgh / b;
-                double xt = xm + nx / 100, yt = ym + ny / 100;
-                if (!in_region(xt, yt, RX, RY, nr, xmin, xmax, ymin, ymax)) { nx = -nx; ny = -ny; }
-                double d = abs_poly_dist(w, xm, ym);
-                if (d < P.on_edge_tol) {
-                    sx += (-force_factor * b) * nx; sy += (-force_factor * b) * ny; sb += b; ++non;
+                fdx = -ygh / b; fdy = xgh / b; dl = b;
+            } else if (m != 0) {
+                // general branch (:117-137), streamed edge by edge
+                if (!outline_checked) { outline_ok = outline_ok_for_poly_dist(w); outline_checked = true; }
+                if (!outline_ok) { res.status = PS_BAD_POLY; phase = PH_DONE; continue; }
+                double xmin = SZ_INF, xmax = -SZ_INF, ymin = SZ_INF, ymax = -SZ_INF;
+                for (int v = 0; v < nr; ++v) {
+                    double x = (double)RX[v] / SZ_SCALE, y = (double)RY[v] / SZ_SCALE;
+                    if (x < xmin) xmin = x;
+                    if (x > xmax) xmax = x;
+                    if (y < ymin) ymin = y;
+                    if (y > ymax) ymax = y;
+                }
+                double sx = 0, sy = 0, sb = 0; int non = 0;
+                for (int e = 0; e < nr; ++e) {
+                    int e1 = (e + 1 == nr) ? 0 : e + 1;
+                    double xa = (double)RX[e] / SZ_SCALE, ya = (double)RY[e] / SZ_SCALE, xb = (double)RX[e1] / SZ_SCALE, yb = (double)RY[e1] / SZ_SCALE;
+                    double xgh = xb - xa, ygh = yb - ya, xm = (xb + xa) / 2, ym = (yb + ya) / 2;
+                    double b = sqrt(xgh * xgh + ygh * ygh);
+                    double nx = -ygh / b, ny = xgh / b;
+                    double xt = xm + nx / 100, yt = ym + ny / 100;
+                    if (!in_region(xt, yt, RX, RY, nr, xmin, xmax, ymin, ymax)) { nx = -nx; ny = -ny; }
+                    double d = abs_poly_dist(w, xm, ym);
+                    if (d < P.on_edge_tol) {
+                        sx += (-force_factor * b) * nx; sy += (-force_factor * b) * ny; sb += b; ++non;
+                    }
+                }
+                if (non < nr && non > 0) {
+                    double nrm = sqrt(sx * sx + sy * sy);
+                    fdx = sx / nrm; fdy = sy / nrm; dl = sb / (double)non;
                 }
             }
-            if (non < nr && non > 0) {
-                double nrm = sqrt(sx * sx + sy * sy);
-                fdx = sx / nrm; fdy = sy / nrm; dl = sb / (double)non;
-            }
+            if (dl < P.dl_min) { fdx = 0; fdy = 0; }                                  // :141-142
+            phase = PH_CLIP2;                                                         // sign test (:151-165)
         }
-        if (dl < P.dl_min) { fdx = 0; fdy = 0; }
-        // sign test (:151-165)
-        {
-            ShiftedOutline s1{w.c1x, w.c1y, fdx, fdy}, s2{w.c2x, w.c2y, 0.0, 0.0};
-            int st = run_clip(w, method, s1, w.n1, s2, w.n2, w.rbx, w.rby, w.rb_off, &w.rb_n);
-            if (st != PS_OK) { res.status = st; return; }
-            for (int ii = 0; ii < w.rb_n; ++ii) {
-                IntRing a{w.rbx + w.rb_off[ii], w.rby + w.rb_off[ii]}, b{RX, RY};
-                // clip #3 only needs "empty or not": run the sweep and look for an output path
-                w.eng.begin(1);
-                w.eng.add_path(a, w.rb_off[ii + 1] - w.rb_off[ii], 0);
-                w.eng.add_path(b, nr, 1);
-                int st3 = w.eng.execute();
-                if (st3 == szclip::ST_OVERFLOW) { res.status = PS_CAPACITY; return; }
-                if (st3 != szclip::ST_OK) { res.status = PS_CLIPPER_FAIL; return; }
-                CountSink cs; cs.n = 0;
-                w.eng.emit(cs);
-                if (cs.n > 0) {
-                    double anew = ring_polyarea(w.rbx + w.rb_off[ii], w.rby + w.rb_off[ii], w.rb_off[ii + 1] - w.rb_off[ii]);
-                    if (anew / Ak - 1 > 0) { fdx = -fdx; fdy = -fdy; }
-                }
-            }
-        }
-        const double fx = fdx * Ak * force_factor, fy = fdy * Ak * force_factor;
-        // tangential (:170-183)
-        const double v1x = f1.Ui + f1.ksi * (pcx - f1.Xi), v1y = f1.Vi + f1.ksi * (pcy - f1.Yi);
-        const double v2x = f2.Ui + f2.ksi * (pcx - f2.Xi), v2y = f2.Vi + f2.ksi * (pcy - f2.Yi);
-        const double vtx = v1x - v2x, vty = v1y - v2y;
-        const double vn = sqrt(vtx * vtx + vty * vty);
-        double dtx = 0, dty = 0;
-        if (!((fabs(vtx) > fabs(vty) ? fabs(vtx) : fabs(vty)) == 0)) { dtx = vtx / vn; dty = vty / vn; }
-        const double dotv = dtx * vtx + dty * vty;
-        const double coef = -dotv * dl * G * vn;
-        double ftx = coef * dtx * P.dt, fty = coef * dty * P.dt;
-        const double fnorm = sqrt(fx * fx + fy * fy);
-        if (sqrt(ftx * ftx + fty * fty) > mu * fnorm) { ftx = -mu * fnorm * dtx; fty = -mu * fnorm * dty; }
-        double* r = rows + (size_t)n_rows * 5;
-        r[0] = fx + ftx; r[1] = fy + fty; r[2] = pcx; r[3] = pcy; r[4] = Ak;
-        ++n_rows;
     }
+    if (res.status != PS_OK) { res.n_rows = 0; return; }
     // caller rule (floe_interactions_all.m:135): rows are kept only when some force component is non-zero
     double sabs = 0;
     for (int r = 0; r < n_rows; ++r) sabs += fabs(rows[r * 5]) + fabs(rows[r * 5 + 1]);
