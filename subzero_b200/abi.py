@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libsubzero_b200.so")
+LIB_PATH = os.environ.get("SZ_LIB", os.path.join(_HERE, "_lib", "libsubzero_b200.so"))   # SZ_LIB: experiment builds only
 
 SZ_OK, SZ_ERR_ARG, SZ_ERR_CUDA, SZ_ERR_CLIPPER, SZ_ERR_CAPACITY, SZ_ERR_STATE = 0, -1, -2, -3, -4, -5
 

@@ -12,11 +12,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "_lib")
+OUT = os.environ.get("SZ_BUILD_DIR", os.path.join(HERE, "_lib"))       # SZ_BUILD_DIR / SZ_EXTRA_NVCC: experiment builds
 LIB = os.path.join(OUT, "libsubzero_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"]
+NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"] + os.environ.get("SZ_EXTRA_NVCC", "").split()
 CU = ["sz_contact.cu", "sz_narrow_S.cu", "sz_narrow_M.cu", "sz_narrow_L.cu"]
 CPP = ["sz_field.cpp"]
 HEADERS = ["sz_clip.cuh", "sz_pairforce.cuh", "sz_narrow.cuh", os.path.join("..", "..", "include", "subzero_b200.h")]

@@ -33,6 +33,13 @@
 #define SZ_HD inline
 #define SZ_HDN inline
 #endif
+// medium-size engine methods: force-inlined by default (measured faster on B200: fewer spills at call
+// boundaries), __noinline__ when SZ_COMPACT_CODE is defined (3.4x smaller SASS)
+#if defined(__CUDACC__) && defined(SZ_COMPACT_CODE)
+#define SZ_HDM __host__ __device__ __noinline__
+#else
+#define SZ_HDM SZ_HD
+#endif
 
 namespace szclip {
 
@@ -174,7 +181,7 @@ struct StlSort {
             ++f;
         }
     }
-    SZ_HD void sort(int n)
+    SZ_HDM void sort(int n)
     {
         if (n <= 0) return;
         if (n > 16) {
@@ -263,7 +270,7 @@ struct ClipEngine {
     SZ_HD void reverse_horizontal(idx_t e) { i64 t = ed[e].top.x; ed[e].top.x = ed[e].bot.x; ed[e].bot.x = t; }   // :756-765
 
     // clipper.cpp:911-925
-    SZ_HD idx_t find_next_loc_min(idx_t e)
+    SZ_HDM idx_t find_next_loc_min(idx_t e)
     {
         for (;;) {
             while (ed[e].bot != ed[ed[e].prev].bot || ed[e].cur == ed[e].top) e = ed[e].next;
@@ -279,7 +286,7 @@ struct ClipEngine {
     }
 
     // clipper.cpp:928-1042 without the Skip-edge (open path) branches
-    SZ_HD idx_t process_bound(idx_t e, bool fwd)
+    SZ_HDM idx_t process_bound(idx_t e, bool fwd)
     {
         idx_t result = e, horz;
         if (is_horz(e)) {
@@ -327,7 +334,7 @@ struct ClipEngine {
     // clipper.cpp:1045-1221 AddPath(pg, polyType, Closed=true).  `get(i)` returns vertex i of the
     // caller's path (n vertices).  Returns false when the reference would (degenerate path).
     template <class Getter>
-    SZ_HD bool add_path(const Getter& get, int n, int poly_type)
+    SZ_HDM bool add_path(const Getter& get, int n, int poly_type)
     {
         int hi = n - 1;
         if (hi < 0) return false;
@@ -418,7 +425,7 @@ struct ClipEngine {
     }
 
     // ---------------------------------------------------------------- scanbeam (:1335-1348)
-    SZ_HD void insert_scanbeam(i64 y)
+    SZ_HDM void insert_scanbeam(i64 y)
     {
         int k = n_sb;
         while (k > 0 && sb[k - 1] > y) --k;
@@ -430,7 +437,7 @@ struct ClipEngine {
     SZ_HD bool pop_scanbeam(i64& y) { if (n_sb == 0) return false; y = sb[--n_sb]; return true; }
 
     // ---------------------------------------------------------------- AEL / SEL plumbing
-    SZ_HD void delete_from_ael(idx_t e)   // :1367-1377
+    SZ_HDM void delete_from_ael(idx_t e)   // :1367-1377
     {
         idx_t p = ed[e].pael, n = ed[e].nael;
         if (p == NIL && n == NIL && e != ael) return;
@@ -438,7 +445,7 @@ struct ClipEngine {
         if (n != NIL) ed[n].pael = p;
         ed[e].nael = NIL; ed[e].pael = NIL;
     }
-    SZ_HD void delete_from_sel(idx_t e)   // :2080-2090
+    SZ_HDM void delete_from_sel(idx_t e)   // :2080-2090
     {
         idx_t p = ed[e].psel, n = ed[e].nsel;
         if (p == NIL && n == NIL && e != sel) return;
@@ -446,7 +453,7 @@ struct ClipEngine {
         if (n != NIL) ed[n].psel = p;
         ed[e].nsel = NIL; ed[e].psel = NIL;
     }
-    SZ_HD void swap_in_ael(idx_t a, idx_t b)   // :1395-1439
+    SZ_HDM void swap_in_ael(idx_t a, idx_t b)   // :1395-1439
     {
         if (ed[a].nael == ed[a].pael || ed[b].nael == ed[b].pael) return;
         if (ed[a].nael == b) {
@@ -466,7 +473,7 @@ struct ClipEngine {
         }
         if (ed[a].pael == NIL) ael = a; else if (ed[b].pael == NIL) ael = b;
     }
-    SZ_HD void swap_in_sel(idx_t a, idx_t b)   // :2558-2601
+    SZ_HDM void swap_in_sel(idx_t a, idx_t b)   // :2558-2601
     {
         if (ed[a].nsel == NIL && ed[a].psel == NIL) return;
         if (ed[b].nsel == NIL && ed[b].psel == NIL) return;
@@ -487,7 +494,7 @@ struct ClipEngine {
         }
         if (ed[a].psel == NIL) sel = a; else if (ed[b].psel == NIL) sel = b;
     }
-    SZ_HD void update_edge_into_ael(idx_t& e)   // :1442-1462
+    SZ_HDM void update_edge_into_ael(idx_t& e)   // :1442-1462
     {
         const idx_t nx = ed[e].nlml;
         if (nx == NIL) { fail(ST_CLIPPER_FAIL); return; }
@@ -510,7 +517,7 @@ struct ClipEngine {
         }
         return ed[e2].cur.x < ed[e1].cur.x;
     }
-    SZ_HD void insert_into_ael(idx_t e, idx_t start)   // :3319-3345
+    SZ_HDM void insert_into_ael(idx_t e, idx_t start)   // :3319-3345
     {
         if (ael == NIL) { ed[e].pael = NIL; ed[e].nael = NIL; ael = e; }
         else if (start == NIL && inserts_before(ael, e)) { ed[e].pael = NIL; ed[e].nael = ael; ed[ael].pael = e; ael = e; }
@@ -553,7 +560,7 @@ struct ClipEngine {
     }
 
     // ---------------------------------------------------------------- output records
-    SZ_HD void set_hole_state(idx_t e, idx_t r)   // :2301-2324
+    SZ_HDM void set_hole_state(idx_t e, idx_t r)   // :2301-2324
     {
         idx_t e2 = ed[e].pael, tmp = NIL;
         while (e2 != NIL) {
@@ -573,7 +580,7 @@ struct ClipEngine {
         return r;
     }
     // :2463-2499.  On arena exhaustion: flag the overflow and change nothing structurally.
-    SZ_HD idx_t add_out_pt(idx_t e, P64 pt)
+    SZ_HDM idx_t add_out_pt(idx_t e, P64 pt)
     {
         if (ed[e].out < 0) {
             if (n_or >= C::OR || n_op >= C::OP) { fail(ST_OVERFLOW); return 0; }
@@ -621,7 +628,7 @@ struct ClipEngine {
     }
 
     // :1841-1881
-    SZ_HD idx_t add_local_min_poly(idx_t e1, idx_t e2, P64 pt)
+    SZ_HDM idx_t add_local_min_poly(idx_t e1, idx_t e2, P64 pt)
     {
         idx_t result, e, prev_e;
         if (is_horz(e2) || ed[e1].dx > ed[e2].dx) {
@@ -664,7 +671,7 @@ struct ClipEngine {
         } while (o != start);
         return fp::mul(a, 0.5);
     }
-    SZ_HD bool first_is_bottom_pt(idx_t b1, idx_t b2) const   // :798-819
+    SZ_HDM bool first_is_bottom_pt(idx_t b1, idx_t b2) const   // :798-819
     {
         idx_t p = op[b1].prev;
         while (op[p].pt == op[b1].pt && p != b1) p = op[p].prev;
@@ -683,7 +690,7 @@ struct ClipEngine {
         if (mx1 == mx2 && mn1 == mn2) return ring_area(b1) > 0;
         return (dx1p >= dx2p && dx1p >= dx2n) || (dx1n >= dx2p && dx1n >= dx2n);
     }
-    SZ_HD idx_t get_bottom_pt(idx_t pp) const   // :822-857
+    SZ_HDM idx_t get_bottom_pt(idx_t pp) const   // :822-857
     {
         idx_t dups = NIL;
         idx_t p = op[pp].next;
@@ -704,7 +711,7 @@ struct ClipEngine {
         }
         return pp;
     }
-    SZ_HD idx_t lowermost_rec(idx_t r1, idx_t r2)   // :2327-2344
+    SZ_HDM idx_t lowermost_rec(idx_t r1, idx_t r2)   // :2327-2344
     {
         if (orec[r1].bottom == NIL) orec[r1].bottom = get_bottom_pt(orec[r1].pts);
         if (orec[r2].bottom == NIL) orec[r2].bottom = get_bottom_pt(orec[r2].pts);
@@ -730,7 +737,7 @@ struct ClipEngine {
         return r;
     }
     // :2367-2460
-    SZ_HD void append_polygon(idx_t e1, idx_t e2)
+    SZ_HDM void append_polygon(idx_t e1, idx_t e2)
     {
         const idx_t r1 = ed[e1].out, r2 = ed[e2].out;
         idx_t hole_rec;
@@ -775,7 +782,7 @@ struct ClipEngine {
         }
         orec[r2].idx = orec[r1].idx;
     }
-    SZ_HD void add_local_max_poly(idx_t e1, idx_t e2, P64 pt)   // :1884-1897
+    SZ_HDM void add_local_max_poly(idx_t e1, idx_t e2, P64 pt)   // :1884-1897
     {
         add_out_pt(e1, pt);
         if (ed[e1].out == ed[e2].out) { ed[e1].out = -1; ed[e2].out = -1; }
@@ -784,7 +791,7 @@ struct ClipEngine {
     }
 
     // :2106-2298 for closed even-odd paths (|WindCnt| == 1 on every edge, see header note)
-    SZ_HD void intersect_edges(idx_t e1, idx_t e2, P64 pt)
+    SZ_HDM void intersect_edges(idx_t e1, idx_t e2, P64 pt)
     {
         const bool c1 = ed[e1].out >= 0, c2 = ed[e2].out >= 0;
         const bool same = ed[e1].poly == ed[e2].poly;
@@ -815,7 +822,7 @@ struct ClipEngine {
     }
 
     // ---------------------------------------------------------------- local minima -> AEL (:1978-2077)
-    SZ_HD void insert_local_minima(i64 bot_y)
+    SZ_HDM void insert_local_minima(i64 bot_y)
     {
         while (cur_lm < n_lm && lm[cur_lm].y == bot_y) {
             const idx_t lb = lm[cur_lm].left, rb = lm[cur_lm].right;
@@ -967,7 +974,7 @@ struct ClipEngine {
     }
 
     // ---------------------------------------------------------------- intersections (:622-689, :2827-2954)
-    SZ_HD P64 intersect_point(idx_t a, idx_t b) const
+    SZ_HDM P64 intersect_point(idx_t a, idx_t b) const
     {
         const Edge& e1 = ed[a]; const Edge& e2 = ed[b];
         P64 ip;
@@ -1037,7 +1044,7 @@ struct ClipEngine {
     }
     struct INodeLess { SZ_HD bool operator()(const INode& a, const INode& b) const { return b.pt.y < a.pt.y; } };   // :2921-2924
     SZ_HD bool edges_adjacent(const INode& n) const { return ed[n.e1].nsel == n.e2 || ed[n.e1].psel == n.e2; }   // :2927-2931
-    SZ_HD bool fixup_intersection_order()   // :2934-2954
+    SZ_HDM bool fixup_intersection_order()   // :2934-2954
     {
         sel = ael;                                        // CopyAELToSEL :1929-1939
         for (idx_t e = ael; e != NIL; e = ed[e].nael) { ed[e].psel = ed[e].pael; ed[e].nsel = ed[e].nael; }
@@ -1053,7 +1060,7 @@ struct ClipEngine {
         }
         return true;
     }
-    SZ_HD bool process_intersections(i64 top_y)   // :2827-2845
+    SZ_HDM bool process_intersections(i64 top_y)   // :2827-2845
     {
         if (ael == NIL) return true;
         n_il = 0;
@@ -1071,7 +1078,7 @@ struct ClipEngine {
     }
 
     // ---------------------------------------------------------------- top of scanbeam (:2957-3113)
-    SZ_HD void do_maxima(idx_t e)
+    SZ_HDM void do_maxima(idx_t e)
     {
         const idx_t mp = maxima_pair_ex(e);
         if (mp == NIL) {
@@ -1162,7 +1169,7 @@ struct ClipEngine {
         }
         return left < right;
     }
-    SZ_HD bool join_horz(idx_t o1, idx_t o1b, idx_t o2, idx_t o2b, P64 pt, bool discard_left)   // :3371-3455
+    SZ_HDM bool join_horz(idx_t o1, idx_t o1b, idx_t o2, idx_t o2b, P64 pt, bool discard_left)   // :3371-3455
     {
         const bool d1_l2r = !(op[o1].pt.x > op[o1b].pt.x);
         const bool d2_l2r = !(op[o2].pt.x > op[o2b].pt.x);
@@ -1270,7 +1277,7 @@ struct ClipEngine {
         }
     }
     // :484-523, returns 0 outside, +1 inside, -1 on the boundary
-    SZ_HD int point_in_ring(P64 pt, idx_t o) const
+    SZ_HDM int point_in_ring(P64 pt, idx_t o) const
     {
         int result = 0;
         const idx_t start = o;
@@ -1347,7 +1354,7 @@ struct ClipEngine {
             }
         }
     }
-    SZ_HD void fixup_out_polygon(idx_t r)   // :3143-3181 (PreserveCollinear off)
+    SZ_HDM void fixup_out_polygon(idx_t r)   // :3143-3181 (PreserveCollinear off)
     {
         idx_t last_ok = NIL;
         orec[r].bottom = NIL;

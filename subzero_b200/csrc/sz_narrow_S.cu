@@ -4,7 +4,7 @@ using namespace sznarrow;
 extern "C" void sz_launch_narrow_S(const NarrowArgs* a, cudaStream_t stream)
 {
     if (a->n_work <= 0) return;
-    const int tpb = 128;
+    const int tpb = SZ_S_TPB;
     narrow_local_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
 }
 extern "C" void sz_launch_clip_S(const ClipArgs* a, cudaStream_t stream)

@@ -86,7 +86,15 @@ struct CountSink { int n; SZ_HD void begin_path(int) { ++n; } SZ_HD void point(P
 // clip site, and the lanes re-converge explicitly before every clip and between the phases of every
 // scanbeam.  All 32 lanes of a warp must call pair_force() together (lanes without a pair pass
 // valid = false).  On the host the macros collapse and the same code handles one pair.
-#if defined(__CUDA_ARCH__)
+#if !defined(SZ_WARP_SYNC_ONLY)
+#define SZ_BLOCK_SYNC 1
+#endif
+#if defined(__CUDA_ARCH__) && defined(SZ_BLOCK_SYNC)
+// block-synchronous variant: every warp of the CTA walks the phases together, so the instruction lines of a
+// phase are fetched once per CTA instead of once per warp (the sweep's SASS is far larger than the I-cache)
+#define SZ_WARP_ANY(p) __syncthreads_or((p))
+#define SZ_WARP_SYNC() __syncthreads()
+#elif defined(__CUDA_ARCH__)
 #define SZ_WARP_ANY(p) __any_sync(0xffffffffu, (p))
 #define SZ_WARP_SYNC() __syncwarp()
 #else
