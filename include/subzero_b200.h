@@ -8,7 +8,8 @@
  * :204-305), reached from polyclip.m:73.
  *
  * Conventions (modelled on the reference gateway, private/mexclipper.cpp):
- *   - plain pointers and sizes only; the caller owns every buffer it passes in or receives into
+ *   - plain pointers and sizes only (host or device memory, the copy direction is inferred); the caller owns every
+ *     buffer it passes in or receives into
  *     (cf. :54-61 inputs copied, :65-81 outputs caller-visible arrays);
  *   - no exceptions cross the ABI; every entry point returns 0 or a negative SzStatus, and
  *     sz_last_error() returns the message (the gateway's mexErrMsgTxt strings, e.g. :304);
@@ -104,6 +105,7 @@ typedef struct SzSummary {
     int32_t n_clipper_fail;   /* pairs whose sweep failed (reference would raise "Clipper Error.") */
     int32_t n_capacity_fail;  /* pairs that exceeded the largest size class */
     float   ms_device;        /* device time of the step (CUDA events), excluding host<->device copies */
+    int64_t n_pairs_owned;    /* pairs whose first floe this context owns (== n_pairs unless an extended list was supplied) */
 } SzSummary;
 
 typedef struct SzContext SzContext;
@@ -123,6 +125,23 @@ int sz_contact_step(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes
 /* ---- split form for device-resident state: upload once, step many times ---- */
 int sz_upload(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes, const SzBoundary* bnd);
 int sz_step_resident(SzContext* ctx, SzSummary* out);
+
+/* ---- multi-GPU slabs: the caller supplies its part of the extended floe list instead of having it built.
+ * One record of `floes` per entry (originals and periodic images this rank owns, plus halo entries received from
+ * the neighbouring slabs), ascending `gid`; x,y are the image centroids (floe_interactions_all.m:34,55).  Pairs are
+ * resolved when either floe is owned; rows, sums and per-floe outputs ([n] in this mode) are produced for owned
+ * entries; row partner ids and kill/transfer are global 1-based positions; kill/transfer come back per entry
+ * before the serial fix-up of :175-179 (which spans ranks and is left to the caller).  Pointers may be host or
+ * device memory (as for every other entry point). */
+typedef struct SzExtendedList {
+    const int32_t* gid;        /* 1-based position in the global extended list */
+    const int32_t* floe_num;   /* FloeNums: original id, negative for images (:35,56) */
+    const double*  root_x;     /* centroid of the original the entry is an image of (its own centroid for originals) */
+    const double*  root_y;
+    const uint8_t* owned;      /* 1: rows and sums of this entry are this context's job */
+    const int32_t* parent;     /* images: 1-based LOCAL index of the parent entry when it is owned here, else 0 */
+} SzExtendedList;
+int sz_upload_extended(SzContext* ctx, const SzParams* prm, const SzFloesSoA* entries, const SzBoundary* bnd, const SzExtendedList* ext);
 
 /* ---- results of the last step (caller-allocated; sizes from SzSummary) ---- */
 /* per floe of the input list, each [n0] unless noted; any pointer may be NULL to skip */

@@ -37,10 +37,14 @@ class SzBoundary(C.Structure):
         (n, C.c_double) for n in ("area", "h", "xi", "yi", "u", "v", "ksi")]
 
 
+class SzExtendedList(C.Structure):
+    _fields_ = [("gid", c_ip), ("floe_num", c_ip), ("root_x", c_dp), ("root_y", c_dp), ("owned", c_bp), ("parent", c_ip)]
+
+
 class SzSummary(C.Structure):
     _fields_ = [("n0", C.c_int32), ("n", C.c_int32), ("n_pairs", C.c_int64), ("n_pairs_force", C.c_int64), ("n_rows", C.c_int64),
                 ("n_clip_paths", C.c_int64), ("n_clip_verts", C.c_int64), ("collision_count", C.c_double),
-                ("n_clipper_fail", C.c_int32), ("n_capacity_fail", C.c_int32), ("ms_device", C.c_float)]
+                ("n_clipper_fail", C.c_int32), ("n_capacity_fail", C.c_int32), ("ms_device", C.c_float), ("n_pairs_owned", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -56,6 +60,7 @@ PROTOTYPES = {
     "sz_launch_count": (C.c_longlong, []),
     "sz_contact_step": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzSummary)]),
     "sz_upload": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary)]),
+    "sz_upload_extended": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzExtendedList)]),
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
     "sz_get_floe_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),

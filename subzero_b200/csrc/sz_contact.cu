@@ -73,7 +73,7 @@ struct Counters {
     int row_used, path_used, vert_used;
     int listM, listL, wlistM, wlistL;
     int total_rows;
-    int n_pairs_force, n_fail, n_cap_fail;
+    int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned;
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
     u64 rmax_bits;
     u64 n_fin_rows, n_inf_rows;
@@ -96,7 +96,9 @@ struct SzContext {
     int bn = 0, boxn = 0;
     // extended list
     int n = 0, n1 = 0;
-    DBuf<double> ex, ey; DBuf<int> esrc, efn, eparent, gx_of, gy_of; DBuf<uint8_t> ealive;
+    DBuf<double> ex, ey, erootx, erooty; DBuf<int> esrc, efn, eparent, gx_of, gy_of, egid; DBuf<uint8_t> ealive, eowned;
+    bool ext_mode = false;          // extended list supplied by the caller (multi-GPU slabs), K0 skipped
+    int nout = 0;                   // entries with per-floe outputs: n0 (single GPU) or n (extended mode)
     DBuf<int> flag, pos, scan_tmp;
     // grid
     DBuf<int> cid, cell_cnt, cell_start, s_idx; DBuf<double> s_x, s_y, s_r;
@@ -214,6 +216,32 @@ __global__ void init_extended_kernel(int n0, const double* __restrict__ x, const
     ex[i] = x[i]; ey[i] = y[i]; esrc[i] = i; efn[i] = i + 1; eparent[i] = 0; ealive[i] = alive[i]; gx_of[i] = -1; gy_of[i] = -1;
 }
 
+// single-GPU mode: global position, ownership and root centroid of every entry of the extended list
+__global__ void finish_extended_kernel(int n_bound, const int* __restrict__ n_dev, const double* __restrict__ x, const double* __restrict__ y,
+                                       const int* __restrict__ esrc, int* __restrict__ egid, uint8_t* __restrict__ eowned,
+                                       double* __restrict__ erootx, double* __restrict__ erooty)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_bound || e >= *n_dev) return;
+    egid[e] = e + 1; eowned[e] = 1; erootx[e] = x[esrc[e]]; erooty[e] = y[esrc[e]];
+}
+// extended mode: the (at most two) ghost children of every entry, ascending = creation order (:242-245)
+__global__ void child_init_kernel(int n, int* c0, int* c1) { const int e = blockIdx.x * blockDim.x + threadIdx.x; if (e < n) { c0[e] = 0x7fffffff; c1[e] = -1; } }
+__global__ void child_mark_kernel(int n, const int* __restrict__ parent, int* c0, int* c1)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int p = parent[e] - 1;          // eparent is 1-based, 0 = none
+    if (p >= 0 && p < n) { atomicMin(&c0[p], e); atomicMax(&c1[p], e); }
+}
+__global__ void child_final_kernel(int n, int* c0, int* c1)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (c0[e] == 0x7fffffff) c0[e] = -1;
+    if (c1[e] == c0[e]) c1[e] = -1;
+}
+
 // order-preserving map double -> u64 so that atomicMin/atomicMax work
 __device__ __host__ __forceinline__ u64 enc_d(double v) { u64 b; memcpy(&b, &v, 8); return (b >> 63) ? ~b : (b | 0x8000000000000000ULL); }
 __device__ __host__ __forceinline__ double dec_d(u64 b) { b = (b >> 63) ? (b & 0x7FFFFFFFFFFFFFFFULL) : ~b; double v; memcpy(&v, &b, 8); return v; }
@@ -270,6 +298,7 @@ __global__ void cell_fill_kernel(int n, const int* __restrict__ cid, const int* 
 struct BroadArgs {
     int n, n0, Nb, collision; GridDesc g; double minL2;
     const double* ex; const double* ey; const int* esrc; const int* efn; const uint8_t* ealive; const double* rmax;
+    const int* egid; const uint8_t* eowned; const double* erootx; const double* erooty;
     const int* cell_start; const int* s_idx; const double* s_x; const double* s_y; const double* s_r;
     int* pcnt; const int* pair_off; int* pi; int* pj;
 };
@@ -280,14 +309,15 @@ struct BroadArgs {
 // the distance test with a eligible for the pair loop.
 __device__ __forceinline__ bool ghost_is_member(const BroadArgs& b, int i, int j)
 {
-    const int oj = b.esrc[j];
-    const int a = (b.efn[i] < 0) ? b.esrc[i] : i;
-    if (!(oj > a) || a < b.Nb) return false;
-    if (!b.ealive[a] || !b.ealive[oj]) return false;
-    const double xa = b.ex[a], ya = b.ey[a];
+    // a and o_j are identified by their FloeNums; their centroids travel with every image (erootx/erooty), their
+    // rmax and alive flag are the image's own, so the test needs no other entry of the list (multi-GPU halos)
+    const int A = abs(b.efn[i]), O = abs(b.efn[j]);
+    if (!(O > A) || A <= b.Nb) return false;
+    if (!b.ealive[i] || !b.ealive[j]) return false;
+    const double xa = b.erootx[i], ya = b.erooty[i];
     if (xa != xa) return false;
-    const double dx = xa - b.ex[oj], dy = ya - b.ey[oj];
-    return sqrt(dx * dx + dy * dy) < (b.rmax[a] + b.rmax[oj]);
+    const double dx = xa - b.erootx[j], dy = ya - b.erooty[j];
+    return sqrt(dx * dx + dy * dy) < (b.rmax[b.esrc[i]] + b.rmax[b.esrc[j]]);
 }
 // one warp per floe i: lanes stride over the three cell rows (each row's three cells are contiguous in
 // the bucketed arrays), ballot + popc compacts accepted partners, then an in-warp rank sort restores
@@ -296,10 +326,11 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int i = b.Nb + warp;
+    const int i = warp;
     if (i >= b.n) return;
     const double xi = b.ex[i], yi = b.ey[i];
-    const bool active = b.ealive[i] && (xi == xi) && b.collision && (yi == yi);
+    const bool active = b.egid[i] > b.Nb && b.ealive[i] && (xi == xi) && b.collision && (yi == yi);
+    const bool own_i = b.eowned[i] != 0;
     int count = 0;
     const int off = FILL ? b.pair_off[i] : 0;
     if (active) {
@@ -313,7 +344,7 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
                 bool ok = false; int j = -1;
                 if (t < t1) {
                     j = b.s_idx[t];
-                    if (j > i) {
+                    if (j > i && (own_i || b.eowned[j])) {     // a pair is resolved where either floe is owned
                         const double dx = xi - b.s_x[t], dy = yi - b.s_y[t], rs = ri + b.s_r[t];
                         if (sqrt(dx * dx + dy * dy) < rs) {
                             ok = true;
@@ -356,11 +387,12 @@ __global__ void tfill_kernel(int np, const int* __restrict__ pj, const int* __re
     if (p < np && nrows[p] > 0) { const int j = pj[p]; tlist[toff[j] + atomicAdd(&tpos[j], 1)] = p; }
 }
 // rows of floe m = own pairs + wall + mirrored (floe_interactions_all.m:136,167,196)
-__global__ void rowcount_kernel(int n, const int* __restrict__ pair_off, const int* __restrict__ nrows, const int* __restrict__ wnrows,
+__global__ void rowcount_kernel(int n, const uint8_t* __restrict__ eowned, const int* __restrict__ pair_off, const int* __restrict__ nrows, const int* __restrict__ wnrows,
                                 const int* __restrict__ toff, int* __restrict__ tlist, int* __restrict__ rcnt)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n) return;
+    if (!eowned[m]) { rcnt[m] = 0; return; }
     int c = 0;
     for (int p = pair_off[m]; p < pair_off[m + 1]; ++p) c += nrows[p];
     if (wnrows) c += wnrows[m];
@@ -409,7 +441,8 @@ __device__ bool in_polygon_d(double x, double y, const double* xv, const double*
 }
 
 struct AssembleArgs {
-    int n, n0, Nb, periodic, wall; double Lx, Ly;
+    int n, nout, Nb, periodic, wall; double Lx, Ly;
+    const int* egid; const int* efn; const uint8_t* eowned;
     const double* ex; const double* ey; const int* esrc; const uint8_t* ealive; const double* area; const double* h;
     const int* pair_off; const int* pi; const int* pj; const int* nrows; const int* row_start; const double* ovl; const int* pstatus;
     const int* wnrows; const int* wrow_start; const int* wstatus;
@@ -425,10 +458,16 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= a.n) return;
+    const bool owned = a.eowned[m] != 0, orig = a.efn[m] > 0, pairing = a.egid[m] > a.Nb;   // pairing: i >= 1+Nb (:125)
+    if (!owned) {
+        a.osum[(size_t)m * 3] = a.osum[(size_t)m * 3 + 1] = a.osum[(size_t)m * 3 + 2] = 0; a.has_rows[m] = 0; a.kill_i[m] = 0; a.transfer_i[m] = 0;
+        if (m < a.nout) { a.o_ov[m] = 0; a.o_xi[m] = a.ex[m]; a.o_yi[m] = a.ey[m]; a.o_alive[m] = a.ealive[m]; double* S = a.o_stress + (size_t)m * 4; S[0] = S[1] = S[2] = S[3] = 0; }
+        return;
+    }
     const double xm = a.ex[m], ym = a.ey[m];
     // periodic wrap of the centroid (:267-277); the stress uses the wrapped centroid
     double xw = xm, yw = ym;
-    if (a.periodic && m >= a.Nb && m < a.n0) {
+    if (a.periodic && pairing && orig) {
         if (fabs(xw) > a.Lx) xw = xw - 2 * a.Lx * sgn_d(xw);
         if (fabs(yw) > a.Ly) yw = yw - 2 * a.Ly * sgn_d(yw);
     }
@@ -450,19 +489,19 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
         if (nr > 0) {
             const double* src = a.pool + (size_t)a.row_start[p] * 5;
             double so = 0;
-            for (int q = 0; q < nr; ++q) { put((double)(a.pj[p] + 1), src[q * 5], src[q * 5 + 1], src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); so += src[q * 5 + 4]; ++nfin; }
+            for (int q = 0; q < nr; ++q) { put((double)a.egid[a.pj[p]], src[q * 5], src[q * 5 + 1], src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); so += src[q * 5 + 4]; ++nfin; }
             ova = so + ova;
         } else if (a.pstatus[p] == 0) {
             const double ov = a.ovl[p];
-            if ((ov == SZ_INF || ov == -SZ_INF) && m >= a.Nb) {          // :138-145
-                if (m < a.n0 && ov > 0) { kill = m + 1; transfer = a.pj[p] + 1; }
-                else if (a.pj[p] + 1 <= a.n0) kill = a.pj[p] + 1;
+            if ((ov == SZ_INF || ov == -SZ_INF) && pairing) {          // :138-145
+                if (orig && ov > 0) { kill = a.egid[m]; transfer = a.egid[a.pj[p]]; }
+                else if (a.efn[a.pj[p]] > 0) kill = a.egid[a.pj[p]];
             }
         }
     }
     // wall rows (:150-172)
     uint8_t alive_out = a.ealive[m];
-    if (a.wall && m >= a.Nb && a.wstatus[m] == 0) {
+    if (a.wall && pairing && a.wstatus[m] == 0) {
         if (!in_polygon_d(xm, ym, a.boxx, a.boxy, a.boxn)) alive_out = 0;  // :152-155
         const int nr = a.wnrows[m];
         if (nr > 0) {
@@ -481,33 +520,33 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
     for (int t = a.toff[m]; t < a.toff[m + 1]; ++t) {
         const int p = a.tlist[t]; const int nr = a.nrows[p];
         const double* src = a.pool + (size_t)a.row_start[p] * 5;
-        for (int q = 0; q < nr; ++q) { put((double)(a.pi[p] + 1), -src[q * 5], -src[q * 5 + 1], src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); ova = ova + src[q * 5 + 4]; ++nfin; }
+        for (int q = 0; q < nr; ++q) { put((double)a.egid[a.pi[p]], -src[q * 5], -src[q * 5 + 1], src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); ova = ova + src[q * 5 + 4]; ++nfin; }
     }
     a.osum[(size_t)m * 3] = sfx; a.osum[(size_t)m * 3 + 1] = sfy; a.osum[(size_t)m * 3 + 2] = st;
     a.has_rows[m] = nr_total > 0;
     a.kill_i[m] = kill; a.transfer_i[m] = transfer;
-    if (m < a.n0) {
+    if (m < a.nout) {
         a.o_ov[m] = ova; a.o_xi[m] = xw; a.o_yi[m] = yw; a.o_alive[m] = alive_out;
         double* S = a.o_stress + (size_t)m * 4;
-        if (m >= a.Nb && alive_out && nr_total > 0) {
+        if (pairing && orig && alive_out && nr_total > 0) {
             const double k = 1 / (2 * a.area[m] * a.h[m]);
             S[0] = k * (s11 + t11); S[1] = k * (s12 + t12); S[2] = k * (s21 + t21); S[3] = k * (s22 + t22);
         } else { S[0] = S[1] = S[2] = S[3] = 0; }
-        if (nfin) atomicAdd(&a.cnt->n_fin_rows, (u64)nfin);
-        if (ninf) atomicAdd(&a.cnt->n_inf_rows, (u64)ninf);
+        if (orig && nfin) atomicAdd(&a.cnt->n_fin_rows, (u64)nfin);      // calc_collisionNum runs over the original floes
+        if (orig && ninf) atomicAdd(&a.cnt->n_inf_rows, (u64)ninf);
     }
 }
 // ghost sums folded into their parents in creation order (:242-245), then the floe's own column sums (:262-263)
-__global__ void fold_kernel(int n0, int Nb, const int* __restrict__ gx_of, const int* __restrict__ gy_of, const double* __restrict__ osum,
+__global__ void fold_kernel(int nout, int Nb, const int* __restrict__ egid, const int* __restrict__ gx_of, const int* __restrict__ gy_of, const double* __restrict__ osum,
                             const uint8_t* __restrict__ has_rows, double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ tq)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n0) return;
+    if (m >= nout) return;
     double f0 = 0, f1 = 0, t = 0;
     const int gx = gx_of[m], gy = gy_of[m];
     if (gx >= 0) { f0 = f0 + (has_rows[gx] ? osum[(size_t)gx * 3] : 0.0); f1 = f1 + (has_rows[gx] ? osum[(size_t)gx * 3 + 1] : 0.0); t = t + (has_rows[gx] ? osum[(size_t)gx * 3 + 2] : 0.0); }
     if (gy >= 0) { f0 = f0 + (has_rows[gy] ? osum[(size_t)gy * 3] : 0.0); f1 = f1 + (has_rows[gy] ? osum[(size_t)gy * 3 + 1] : 0.0); t = t + (has_rows[gy] ? osum[(size_t)gy * 3 + 2] : 0.0); }
-    if (m >= Nb && has_rows[m]) { f0 = osum[(size_t)m * 3] + f0; f1 = osum[(size_t)m * 3 + 1] + f1; t = osum[(size_t)m * 3 + 2] + t; }
+    if (egid[m] > Nb && has_rows[m]) { f0 = osum[(size_t)m * 3] + f0; f1 = osum[(size_t)m * 3 + 1] + f1; t = osum[(size_t)m * 3 + 2] + t; }
     fx[m] = f0; fy[m] = f1; tq[m] = t;
 }
 // :175-179  for i=1:length(kill): if kill(i) ~= i && kill(i) > 0, transfer(kill(i)) = i   (serial: the largest i wins)
@@ -524,13 +563,15 @@ __global__ void kill_final_kernel(int n0, const int* __restrict__ kill_i, const 
     if (i >= n0) return;
     kill[i] = kill_i[i]; transfer[i] = tmax[i] ? tmax[i] : transfer_i[i];
 }
-__global__ void pair_stats_kernel(int np, const int* __restrict__ status, const int* __restrict__ nrows, int count_force, Counters* c)
+__global__ void pair_stats_kernel(int np, const int* __restrict__ status, const int* __restrict__ nrows, const int* __restrict__ pi, const uint8_t* __restrict__ eowned,
+                                  int count_force, Counters* c)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int f = 0, e = 0, k = 0;
-    if (p < np) { const int s = status[p]; f = (s == 0 && nrows[p] > 0); e = (s == szpf::PS_CLIPPER_FAIL || s == szpf::PS_BAD_POLY); k = (s == szpf::PS_CAPACITY); }
-    const unsigned mf = __ballot_sync(0xffffffffu, f), me = __ballot_sync(0xffffffffu, e), mk = __ballot_sync(0xffffffffu, k);
+    int f = 0, e = 0, k = 0, u = 0;
+    if (p < np && eowned[pi ? pi[p] : p]) { u = 1; const int s = status[p]; f = (s == 0 && nrows[p] > 0); e = (s == szpf::PS_CLIPPER_FAIL || s == szpf::PS_BAD_POLY); k = (s == szpf::PS_CAPACITY); }
+    const unsigned mf = __ballot_sync(0xffffffffu, f), me = __ballot_sync(0xffffffffu, e), mk = __ballot_sync(0xffffffffu, k), mu = __ballot_sync(0xffffffffu, u);
     if ((threadIdx.x & 31) == 0) {
+        if (mu && count_force) atomicAdd(&c->n_pairs_owned, __popc(mu));
         if (mf && count_force) atomicAdd(&c->n_pairs_force, __popc(mf));
         if (me) atomicAdd(&c->n_fail, __popc(me));
         if (mk) atomicAdd(&c->n_cap_fail, __popc(mk));
@@ -578,15 +619,15 @@ extern "C" void sz_destroy(SzContext* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
-                          &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
+                          &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
     for (auto* b : db) b->release();
-    DBuf<int>* ib[] = {&c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
+    DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
                        &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
+    DBuf<uint8_t>* ub[] = {&c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
@@ -641,23 +682,23 @@ extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f,
     cudaStream_t st = c->stream;
     if (n > 0) {
         const size_t b = (size_t)n * 8;
-        CK(cudaMemcpyAsync(c->x.p, f->x, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->y.p, f->y, b, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->rmax.p, f->rmax, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->h.p, f->h, b, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->area.p, f->area, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->u.p, f->u, b, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->v.p, f->v, b, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->ksi.p, f->ksi, b, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->alive.p, f->alive, n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->voff.p, f->voff, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
-        if (nv) { CK(cudaMemcpyAsync(c->vx.p, f->vx, nv * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->vy.p, f->vy, nv * 8, cudaMemcpyHostToDevice, st)); }
+        CK(cudaMemcpyAsync(c->x.p, f->x, b, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->y.p, f->y, b, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->rmax.p, f->rmax, b, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->h.p, f->h, b, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->area.p, f->area, b, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->u.p, f->u, b, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->v.p, f->v, b, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->ksi.p, f->ksi, b, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->alive.p, f->alive, n, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->voff.p, f->voff, (size_t)(n + 1) * 4, cudaMemcpyDefault, st));
+        if (nv) { CK(cudaMemcpyAsync(c->vx.p, f->vx, nv * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->vy.p, f->vy, nv * 8, cudaMemcpyDefault, st)); }
     }
     c->have_bnd = false; c->bn = 0; c->boxn = 0;
     if (bnd && !prm->periodic) {
         c->have_bnd = true; c->bn = bnd->n; c->boxn = bnd->box_n;
         CK(c->bx.ensure(bnd->n)); CK(c->by.ensure(bnd->n)); CK(c->boxx.ensure(std::max(1, bnd->box_n))); CK(c->boxy.ensure(std::max(1, bnd->box_n)));
-        CK(cudaMemcpyAsync(c->bx.p, bnd->x, (size_t)bnd->n * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->by.p, bnd->y, (size_t)bnd->n * 8, cudaMemcpyHostToDevice, st));
-        if (bnd->box_n > 0) { CK(cudaMemcpyAsync(c->boxx.p, bnd->box_x, (size_t)bnd->box_n * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->boxy.p, bnd->box_y, (size_t)bnd->box_n * 8, cudaMemcpyHostToDevice, st)); }
+        CK(cudaMemcpyAsync(c->bx.p, bnd->x, (size_t)bnd->n * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->by.p, bnd->y, (size_t)bnd->n * 8, cudaMemcpyDefault, st));
+        if (bnd->box_n > 0) { CK(cudaMemcpyAsync(c->boxx.p, bnd->box_x, (size_t)bnd->box_n * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->boxy.p, bnd->box_y, (size_t)bnd->box_n * 8, cudaMemcpyDefault, st)); }
         c->bbody.h = bnd->h; c->bbody.area = bnd->area; c->bbody.Xi = bnd->xi; c->bbody.Yi = bnd->yi; c->bbody.Ui = bnd->u; c->bbody.Vi = bnd->v; c->bbody.ksi = bnd->ksi;
     }
-    c->prm = *prm;
+    c->prm = *prm; c->ext_mode = false;
     fill_device_params(prm, (bnd && !prm->periodic) ? bnd : nullptr, c->dprm);
     c->n0 = n; c->nverts = f->nverts;
     CK(cudaStreamSynchronize(st));   // the caller may reuse its buffers
@@ -665,9 +706,30 @@ extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f,
     return SZ_OK;
 }
 
+extern "C" int sz_upload_extended(SzContext* c, const SzParams* prm, const SzFloesSoA* f, const SzBoundary* bnd, const SzExtendedList* e)
+{
+    if (!e || (f && f->n > 0 && (!e->gid || !e->floe_num || !e->root_x || !e->root_y || !e->owned || !e->parent))) { sz_set_error("sz_upload_extended: extended-list arrays missing"); return SZ_ERR_ARG; }
+    int r = sz_upload(c, prm, f, bnd);
+    if (r != SZ_OK) return r;
+    const int n = f->n;
+    CK(c->egid.ensure(n + 1)); CK(c->efn.ensure(n + 1)); CK(c->erootx.ensure(n + 1)); CK(c->erooty.ensure(n + 1)); CK(c->eowned.ensure(n + 1)); CK(c->eparent.ensure(n + 1));
+    CK(c->esrc.ensure(n + 1)); CK(c->ex.ensure(n + 1)); CK(c->ey.ensure(n + 1)); CK(c->ealive.ensure(n + 1));
+    if (n > 0) {
+        cudaStream_t st = c->stream;
+        CK(cudaMemcpyAsync(c->egid.p, e->gid, (size_t)n * 4, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->efn.p, e->floe_num, (size_t)n * 4, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->erootx.p, e->root_x, (size_t)n * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->erooty.p, e->root_y, (size_t)n * 8, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->eowned.p, e->owned, (size_t)n, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->eparent.p, e->parent, (size_t)n * 4, cudaMemcpyDefault, st));
+        std::vector<int> ident((size_t)n); for (int k = 0; k < n; ++k) ident[k] = k;
+        CK(cudaMemcpyAsync(c->esrc.p, ident.data(), (size_t)n * 4, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    c->ext_mode = true;
+    return SZ_OK;
+}
+
 static int read_counters(SzContext* c)
 {
-    CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDefault, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SZ_OK;
 }
@@ -686,7 +748,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     a.P = c->dprm;
     int* cntM; int* cntL; int* lstM; int* lstL;
     if (wall) {
-        a.wall = 1; a.first_floe = 0; a.bx = c->bx.p; a.by = c->by.p; a.bn = c->bn; a.bbody = c->bbody;
+        a.wall = 1; a.first_floe = 0; a.egid = c->egid.p; a.eowned = c->eowned.p; a.bx = c->bx.p; a.by = c->by.p; a.bn = c->bn; a.bbody = c->bbody;
         a.status = c->wstatus.p; a.nrows = c->wnrows.p; a.row_start = c->wrow_start.p; a.ovl_state = c->wovl.p;
         cntM = D_CNT(wlistM); cntL = D_CNT(wlistL); lstM = c->wlistM.p; lstL = c->wlistL.p;
     } else {
@@ -729,7 +791,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     cudaStream_t st = c->stream;
     const SzParams& P = c->prm;
     const int n0 = c->n0, Nb = P.Nb;
-    const int ncap = P.periodic ? 4 * n0 : n0;         // every floe has at most an x-, a y- and an xy-ghost
+    const bool ext = c->ext_mode;
+    const int ncap = (P.periodic && !ext) ? 4 * n0 : n0;         // every floe has at most an x-, a y- and an xy-ghost
     c->have_step = false;
     CK(cudaEventRecord(c->ev0, st));
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
@@ -737,16 +800,17 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     // ---- K0: extended list
     CK(c->ex.ensure(ncap + 1)); CK(c->ey.ensure(ncap + 1)); CK(c->esrc.ensure(ncap + 1)); CK(c->efn.ensure(ncap + 1)); CK(c->eparent.ensure(ncap + 1));
     CK(c->ealive.ensure(ncap + 1)); CK(c->gx_of.ensure(n0 + 1)); CK(c->gy_of.ensure(n0 + 1));
+    CK(c->egid.ensure(ncap + 1)); CK(c->eowned.ensure(ncap + 1)); CK(c->erootx.ensure(ncap + 1)); CK(c->erooty.ensure(ncap + 1));
     CK(c->flag.ensure(2 * (size_t)n0 + 2)); CK(c->pos.ensure(2 * (size_t)n0 + 2));
-    if (n0 > 0) { ++g_launches; init_extended_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p, c->gx_of.p, c->gy_of.p); }
+    if (n0 > 0 && !ext) { ++g_launches; init_extended_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p, c->gx_of.p, c->gy_of.p); }
     {
         Counters init; memset(&init, 0, sizeof(init));
         init.n1 = n0; init.n = n0;
         init.bbox[0] = enc_d(SZ_INF); init.bbox[1] = enc_d(-SZ_INF); init.bbox[2] = enc_d(SZ_INF); init.bbox[3] = enc_d(-SZ_INF); init.rmax_bits = enc_d(0.0);
         *c->h_cnt = init;
-        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
     }
-    if (P.periodic && n0 > 0) {
+    if (P.periodic && n0 > 0 && !ext) {
         CK(c->scan_tmp.ensure(scan_tmp_ints(2 * (size_t)n0 + 2)));
         // x pass over the originals
         ++g_launches; ghost_flag_kernel<<<nblk(n0, 128), 128, 0, st>>>(0, n0, nullptr, c->ex.p, c->esrc.p, c->ealive.p, c->voff.p, c->vx.p, P.Lx, c->flag.p);
@@ -758,6 +822,16 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         exclusive_scan(c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1, c->scan_tmp.p, st);
         ++g_launches; ghost_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(n1), n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
                                                                   c->gx_of.p, c->gy_of.p, P.Ly, D_CNT(n));
+    }
+    if (ext && n0 > 0) {
+        // the caller supplied the extended list (sz_upload_extended): every entry has its own outline and body record
+        CK(cudaMemcpyAsync(c->ex.p, c->x.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->ey.p, c->y.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(c->ealive.p, c->alive.p, (size_t)n0, cudaMemcpyDeviceToDevice, st));
+        ++g_launches; child_init_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->gx_of.p, c->gy_of.p);
+        ++g_launches; child_mark_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->eparent.p, c->gx_of.p, c->gy_of.p);
+        ++g_launches; child_final_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->gx_of.p, c->gy_of.p);
+    } else if (ncap > 0) {
+        ++g_launches; finish_extended_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->x.p, c->y.p, c->esrc.p, c->egid.p, c->eowned.p, c->erootx.p, c->erooty.p);
     }
     if (ncap > 0) { ++g_launches; bbox_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->d_cnt); }
     CK(cudaGetLastError());
@@ -794,9 +868,10 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         ++g_launches; cell_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->cid.p, c->cell_start.p, c->cell_cnt.p, c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->s_idx.p, c->s_x.p, c->s_y.p, c->s_r.p);
         b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly);
         b.ex = c->ex.p; b.ey = c->ey.p; b.esrc = c->esrc.p; b.efn = c->efn.p; b.ealive = c->ealive.p; b.rmax = c->rmax.p;
+        b.egid = c->egid.p; b.eowned = c->eowned.p; b.erootx = c->erootx.p; b.erooty = c->erooty.p;
         b.cell_start = c->cell_start.p; b.s_idx = c->s_idx.p; b.s_x = c->s_x.p; b.s_y = c->s_y.p; b.s_r = c->s_r.p;
         b.pcnt = c->pcnt.p; b.pair_off = c->pair_off.p;
-        if (n > Nb) { ++g_launches; broad_kernel<false><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b); }
+        { ++g_launches; broad_kernel<false><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
     }
     exclusive_scan(c->pcnt.p, n, c->pair_off.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemcpyAsync(D_CNT(n_pairs), c->pair_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
@@ -805,7 +880,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     const int np = c->h_cnt->n_pairs; c->n_pairs = np;
     CK(c->pi.ensure(np + 1)); CK(c->pj.ensure(np + 1)); CK(c->pstatus.ensure(np + 1)); CK(c->pnrows.ensure(np + 1)); CK(c->prow_start.ensure(np + 1)); CK(c->povl.ensure(np + 1));
     CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
-    if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)(n - Nb), 256), 256, 0, st>>>(b); }
+    if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
@@ -820,7 +895,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         Counters z = *c->h_cnt;
         z.row_used = z.path_used = z.vert_used = z.listM = z.listL = z.wlistM = z.wlistL = 0;
         *c->h_cnt = z;
-        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
         CK(cudaMemsetAsync(c->pstatus.p, 0, (size_t)(np + 1) * 4, st)); CK(cudaMemsetAsync(c->pnrows.p, 0, (size_t)(np + 1) * 4, st));
         if (np > 0) CKS(run_narrow(c, 0, np));
         if (wall) {
@@ -847,19 +922,21 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     exclusive_scan(c->tcnt.p, n, c->toff.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
     if (np > 0) { ++g_launches; tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p); }
-    if (n > 0) { ++g_launches; rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p); }
+    if (n > 0) { ++g_launches; rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->eowned.p, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p); }
     exclusive_scan(c->rcnt.p, n, c->row_off.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemcpyAsync(D_CNT(total_rows), c->row_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
     CKS(read_counters(c));
     const i64 nrows = c->h_cnt->total_rows; c->n_rows = nrows;
     CK(c->rows.ensure((size_t)nrows * 7 + 7)); CK(c->osum.ensure((size_t)n * 3 + 3)); CK(c->has_rows.ensure(n + 1));
-    CK(c->kill_i.ensure(n + 1)); CK(c->transfer_i.ensure(n + 1)); CK(c->tmax.ensure(n0 + 1));
-    CK(c->o_fx.ensure(n0 + 1)); CK(c->o_fy.ensure(n0 + 1)); CK(c->o_tq.ensure(n0 + 1)); CK(c->o_ov.ensure(n0 + 1)); CK(c->o_stress.ensure(4 * (size_t)n0 + 4));
-    CK(c->o_xi.ensure(n0 + 1)); CK(c->o_yi.ensure(n0 + 1)); CK(c->o_alive.ensure(n0 + 1)); CK(c->o_kill.ensure(n0 + 1)); CK(c->o_transfer.ensure(n0 + 1));
+    const int nout = ext ? n : n0; c->nout = nout;
+    CK(c->kill_i.ensure(n + 1)); CK(c->transfer_i.ensure(n + 1)); CK(c->tmax.ensure(nout + 1));
+    CK(c->o_fx.ensure(nout + 1)); CK(c->o_fy.ensure(nout + 1)); CK(c->o_tq.ensure(nout + 1)); CK(c->o_ov.ensure(nout + 1)); CK(c->o_stress.ensure(4 * (size_t)nout + 4));
+    CK(c->o_xi.ensure(nout + 1)); CK(c->o_yi.ensure(nout + 1)); CK(c->o_alive.ensure(nout + 1)); CK(c->o_kill.ensure(nout + 1)); CK(c->o_transfer.ensure(nout + 1));
     if (n > 0) {
         AssembleArgs a; memset(&a, 0, sizeof(a));
-        a.n = n; a.n0 = n0; a.Nb = Nb; a.periodic = P.periodic; a.wall = wall; a.Lx = P.Lx; a.Ly = P.Ly;
+        a.n = n; a.nout = nout; a.Nb = Nb; a.periodic = P.periodic; a.wall = wall; a.Lx = P.Lx; a.Ly = P.Ly;
+        a.egid = c->egid.p; a.efn = c->efn.p; a.eowned = c->eowned.p;
         a.ex = c->ex.p; a.ey = c->ey.p; a.esrc = c->esrc.p; a.ealive = c->ealive.p; a.area = c->area.p; a.h = c->h.p;
         a.pair_off = c->pair_off.p; a.pi = c->pi.p; a.pj = c->pj.p; a.nrows = c->pnrows.p; a.row_start = c->prow_start.p; a.ovl = c->povl.p; a.pstatus = c->pstatus.p;
         a.wnrows = c->wnrows.p; a.wrow_start = c->wrow_start.p; a.wstatus = c->wstatus.p;
@@ -868,14 +945,17 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         a.rows = c->rows.p; a.osum = c->osum.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
         a.o_ov = c->o_ov.p; a.o_stress = c->o_stress.p; a.o_xi = c->o_xi.p; a.o_yi = c->o_yi.p; a.o_alive = c->o_alive.p; a.cnt = c->d_cnt;
         ++g_launches; assemble_kernel<<<nblk(n, 128), 128, 0, st>>>(a);
-        CK(cudaMemsetAsync(c->tmax.p, 0, (size_t)(n0 + 1) * 4, st));
-        ++g_launches; kill_mark_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->kill_i.p, c->tmax.p);
-        if (n0 > 0) {
-            ++g_launches; kill_final_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->kill_i.p, c->transfer_i.p, c->tmax.p, c->o_kill.p, c->o_transfer.p);
-            ++g_launches; fold_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, Nb, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p);
+        if (!ext) {
+            CK(cudaMemsetAsync(c->tmax.p, 0, (size_t)(nout + 1) * 4, st));
+            ++g_launches; kill_mark_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->kill_i.p, c->tmax.p);
+            if (nout > 0) { ++g_launches; kill_final_kernel<<<nblk(nout, 256), 256, 0, st>>>(nout, c->kill_i.p, c->transfer_i.p, c->tmax.p, c->o_kill.p, c->o_transfer.p); }
+        } else {
+            // extended mode: raw per-entry kill/transfer (global ids); the cross-rank fix-up of :175-179 is the caller's
+            CK(cudaMemcpyAsync(c->o_kill.p, c->kill_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->o_transfer.p, c->transfer_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st));
         }
-        if (np > 0) { ++g_launches; pair_stats_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, 1, c->d_cnt); }
-        if (wall) { ++g_launches; pair_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, 0, c->d_cnt); }
+        if (nout > 0) { ++g_launches; fold_kernel<<<nblk(nout, 256), 256, 0, st>>>(nout, Nb, c->egid.p, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p); }
+        if (np > 0) { ++g_launches; pair_stats_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, c->pi.p, c->eowned.p, 1, c->d_cnt); }
+        if (wall) { ++g_launches; pair_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, nullptr, c->eowned.p, 0, c->d_cnt); }
     }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
@@ -885,7 +965,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     CK(cudaEventElapsedTime(&c->phase_ms[2], c->evp[1], c->evp[2])); CK(cudaEventElapsedTime(&c->phase_ms[3], c->evp[2], c->ev1)); c->phase_ms[4] = ms;
 
     SzSummary& s = c->summary; memset(&s, 0, sizeof(s));
-    s.n0 = n0; s.n = n; s.n_pairs = np; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows;
+    s.n0 = n0; s.n = n; s.n_pairs = np; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows; s.n_pairs_owned = c->h_cnt->n_pairs_owned;
     s.n_clip_paths = P.want_clip_polys ? c->h_cnt->path_used : 0; s.n_clip_verts = P.want_clip_polys ? c->h_cnt->vert_used : 0;
     s.collision_count = (double)c->h_cnt->n_fin_rows / 2 + (double)c->h_cnt->n_inf_rows;   // calc_collisionNum.m:6
     s.n_clipper_fail = c->h_cnt->n_fail; s.n_capacity_fail = c->h_cnt->n_cap_fail; s.ms_device = ms;
@@ -906,13 +986,13 @@ extern "C" int sz_contact_step(SzContext* c, const SzParams* prm, const SzFloesS
 // ------------------------------------------------------------------------------------------------ getters
 #define NEED_STEP(name) do { if (!c) { sz_set_error(name ": NULL context"); return SZ_ERR_ARG; } \
     if (!c->have_step) { sz_set_error(name ": no step has been run"); return SZ_ERR_STATE; } CK(cudaSetDevice(c->device)); } while (0)
-#define D2H(dst, src, bytes) do { if ((dst) && (bytes) > 0) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, c->stream)); } while (0)
+#define D2H(dst, src, bytes) do { if ((dst) && (bytes) > 0) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDefault, c->stream)); } while (0)
 
 extern "C" int sz_get_floe_outputs(SzContext* c, double* fx, double* fy, double* torque, double* overlap_area, double* stress,
                                    double* xi, double* yi, uint8_t* alive, int32_t* kill, int32_t* transfer)
 {
     NEED_STEP("sz_get_floe_outputs");
-    const size_t n = (size_t)c->n0;
+    const size_t n = (size_t)c->nout;
     D2H(fx, c->o_fx.p, n * 8); D2H(fy, c->o_fy.p, n * 8); D2H(torque, c->o_tq.p, n * 8); D2H(overlap_area, c->o_ov.p, n * 8);
     D2H(stress, c->o_stress.p, n * 32); D2H(xi, c->o_xi.p, n * 8); D2H(yi, c->o_yi.p, n * 8); D2H(alive, c->o_alive.p, n);
     D2H(kill, c->o_kill.p, n * 4); D2H(transfer, c->o_transfer.p, n * 4);
@@ -922,6 +1002,7 @@ extern "C" int sz_get_floe_outputs(SzContext* c, double* fx, double* fy, double*
 extern "C" int sz_get_ghosts(SzContext* c, int32_t* parent, int32_t* floe_num, double* gx, double* gy)
 {
     NEED_STEP("sz_get_ghosts");
+    if (c->ext_mode) { sz_set_error("sz_get_ghosts: not available for a caller-supplied extended list"); return SZ_ERR_STATE; }
     const size_t g = (size_t)(c->n - c->n0); const int n0 = c->n0;
     D2H(parent, c->eparent.p + n0, g * 4); D2H(floe_num, c->efn.p + n0, g * 4); D2H(gx, c->ex.p + n0, g * 8); D2H(gy, c->ey.p + n0, g * 8);
     CK(cudaStreamSynchronize(c->stream));
@@ -933,8 +1014,12 @@ extern "C" int sz_get_pairs(SzContext* c, int32_t* pi, int32_t* pj, double* over
     const size_t np = (size_t)c->n_pairs;
     D2H(pi, c->pi.p, np * 4); D2H(pj, c->pj.p, np * 4); D2H(overlap_state, c->povl.p, np * 8); D2H(n_regions, c->pnrows.p, np * 4); D2H(status, c->pstatus.p, np * 4);
     CK(cudaStreamSynchronize(c->stream));
-    if (pi) for (size_t k = 0; k < np; ++k) pi[k] += 1;      // 1-based, like Floe(i).potentialInteractions(k).floeNum
-    if (pj) for (size_t k = 0; k < np; ++k) pj[k] += 1;
+    if (pi || pj) {                                             // 1-based positions in the (global) extended list
+        std::vector<int> gid((size_t)c->n);
+        CK(cudaMemcpy(gid.data(), c->egid.p, (size_t)c->n * 4, cudaMemcpyDefault));
+        if (pi) for (size_t k = 0; k < np; ++k) pi[k] = gid[pi[k]];
+        if (pj) for (size_t k = 0; k < np; ++k) pj[k] = gid[pj[k]];
+    }
     if (overlap_state && status) for (size_t k = 0; k < np; ++k) if (status[k] != 0) overlap_state[k] = 0;
     return SZ_OK;
 }
@@ -944,7 +1029,7 @@ extern "C" int sz_get_rows(SzContext* c, int64_t* row_off, double* rows)
     const int n = c->n;
     if (row_off) {
         std::vector<int> tmp(n + 1);
-        CK(cudaMemcpyAsync(tmp.data(), c->row_off.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(tmp.data(), c->row_off.p, (size_t)(n + 1) * 4, cudaMemcpyDefault, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         for (int k = 0; k <= n; ++k) row_off[k] = tmp[k];
     }
@@ -966,10 +1051,10 @@ static int export_paths(SzContext* c, int n_items, const int* d_item_start, cons
     std::vector<int> is(n_items), in(n_items), stt(n_items, 0), pvs(n_pool_paths), pln(n_pool_paths);
     std::vector<i64> px(n_pool_verts), py(n_pool_verts);
     cudaStream_t st = c->stream;
-    if (n_items) { CK(cudaMemcpyAsync(is.data(), d_item_start, (size_t)n_items * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(in.data(), d_item_np, (size_t)n_items * 4, cudaMemcpyDeviceToHost, st));
-                   if (d_status) CK(cudaMemcpyAsync(stt.data(), d_status, (size_t)n_items * 4, cudaMemcpyDeviceToHost, st)); }
-    if (n_pool_paths) { CK(cudaMemcpyAsync(pvs.data(), d_path_vstart, (size_t)n_pool_paths * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(pln.data(), d_path_len, (size_t)n_pool_paths * 4, cudaMemcpyDeviceToHost, st)); }
-    if (n_pool_verts) { CK(cudaMemcpyAsync(px.data(), d_px, (size_t)n_pool_verts * 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(py.data(), d_py, (size_t)n_pool_verts * 8, cudaMemcpyDeviceToHost, st)); }
+    if (n_items) { CK(cudaMemcpyAsync(is.data(), d_item_start, (size_t)n_items * 4, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(in.data(), d_item_np, (size_t)n_items * 4, cudaMemcpyDefault, st));
+                   if (d_status) CK(cudaMemcpyAsync(stt.data(), d_status, (size_t)n_items * 4, cudaMemcpyDefault, st)); }
+    if (n_pool_paths) { CK(cudaMemcpyAsync(pvs.data(), d_path_vstart, (size_t)n_pool_paths * 4, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(pln.data(), d_path_len, (size_t)n_pool_paths * 4, cudaMemcpyDefault, st)); }
+    if (n_pool_verts) { CK(cudaMemcpyAsync(px.data(), d_px, (size_t)n_pool_verts * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(py.data(), d_py, (size_t)n_pool_verts * 8, cudaMemcpyDefault, st)); }
     CK(cudaStreamSynchronize(st));
     i64 np = 0, nv = 0;
     if (item_path_off) item_path_off[0] = 0;
@@ -1011,10 +1096,10 @@ extern "C" int sz_clip_batch(SzContext* c, int32_t count, const int32_t* method,
     CK(c->c_listM.ensure(count + 1)); CK(c->c_listL.ensure(count + 1));
     CK(c->c_soff.ensure(count + 2)); CK(c->c_coff.ensure(count + 2)); CK(c->c_sx.ensure(ns + 1)); CK(c->c_sy.ensure(ns + 1)); CK(c->c_cx.ensure(nc + 1)); CK(c->c_cy.ensure(nc + 1));
     if (count > 0) {
-        CK(cudaMemcpyAsync(c->c_method.p, method, (size_t)count * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->c_soff.p, soff, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->c_coff.p, coff, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (ns) { CK(cudaMemcpyAsync(c->c_sx.p, sx, ns * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->c_sy.p, sy, ns * 8, cudaMemcpyHostToDevice, st)); }
-        if (nc) { CK(cudaMemcpyAsync(c->c_cx.p, cx, nc * 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(c->c_cy.p, cy, nc * 8, cudaMemcpyHostToDevice, st)); }
+        CK(cudaMemcpyAsync(c->c_method.p, method, (size_t)count * 4, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(c->c_soff.p, soff, (size_t)(count + 1) * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->c_coff.p, coff, (size_t)(count + 1) * 8, cudaMemcpyDefault, st));
+        if (ns) { CK(cudaMemcpyAsync(c->c_sx.p, sx, ns * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->c_sy.p, sy, ns * 8, cudaMemcpyDefault, st)); }
+        if (nc) { CK(cudaMemcpyAsync(c->c_cx.p, cx, nc * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->c_cy.p, cy, nc * 8, cudaMemcpyDefault, st)); }
     }
     CK(c->c_path_vstart.ensure((size_t)count * 2 + 64)); CK(c->c_path_len.ensure(c->c_path_vstart.cap));
     CK(c->c_pvx.ensure(ns + nc + 1024)); CK(c->c_pvy.ensure(c->c_pvx.cap));
@@ -1063,7 +1148,7 @@ extern "C" int sz_get_clip_batch(SzContext* c, int32_t* status, int64_t* item_pa
     if (!c) { sz_set_error("sz_get_clip_batch: NULL context"); return SZ_ERR_ARG; }
     if (c->clip_count < 0) { sz_set_error("sz_get_clip_batch: no clip batch has been run"); return SZ_ERR_STATE; }
     CK(cudaSetDevice(c->device));
-    if (status && c->clip_count > 0) { CK(cudaMemcpyAsync(status, c->c_status.p, (size_t)c->clip_count * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    if (status && c->clip_count > 0) { CK(cudaMemcpyAsync(status, c->c_status.p, (size_t)c->clip_count * 4, cudaMemcpyDefault, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
     return export_paths(c, c->clip_count, c->c_path_start.p, c->c_npaths.p, c->c_status.p, c->c_path_vstart.p, c->c_path_len.p, (int)c->clip_paths,
                         c->c_pvx.p, c->c_pvy.p, (int)c->clip_verts, item_path_off, path_vert_off, ox, oy);
 }

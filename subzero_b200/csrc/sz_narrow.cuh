@@ -36,7 +36,7 @@ typedef szpf::PairCaps<ClipL, 1300, 5200, 64, 6000, 32> PairL;
 // floe_interactions_all.m:33-34,54-55).
 struct NarrowArgs {
     // extended list
-    const double* ex; const double* ey; const int* esrc;
+    const double* ex; const double* ey; const int* esrc; const int* egid; const unsigned char* eowned;
     // per original floe
     const double* h; const double* area; const double* u; const double* v; const double* ksi;
     const int* voff; const double* vx; const double* vy;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     int i = 0, j = -1;
     Body b1, b2;
     b1.h = b1.area = b1.Xi = b1.Yi = b1.Ui = b1.Vi = b1.ksi = 0; b2 = b1;
-    if (valid && a.wall && k < a.P.Nb) valid = false;     // floes below Nb take no part in the pair loop (floe_interactions_all.m:125)
+    if (valid && a.wall && (a.egid[k] <= a.P.Nb || !a.eowned[k])) valid = false;     // floes below Nb take no part in the pair loop (floe_interactions_all.m:125)
     bool escalate = false;
     if (valid) {
         if (a.wall) { i = a.first_floe + k; b2 = a.bbody; }
