@@ -669,7 +669,12 @@ extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f,
     if (!c || !prm || !f) { sz_set_error("sz_upload: NULL argument"); return SZ_ERR_ARG; }
     if (f->n < 0 || f->nverts < 0 || (f->n > 0 && (!f->x || !f->y || !f->rmax || !f->h || !f->area || !f->u || !f->v || !f->ksi || !f->alive || !f->voff)) ||
         (f->nverts > 0 && (!f->vx || !f->vy))) { sz_set_error("sz_upload: floe arrays missing"); return SZ_ERR_ARG; }
-    if (f->n > 0 && (f->voff[0] != 0 || (i64)f->voff[f->n] != f->nverts)) { sz_set_error("sz_upload: voff[0] must be 0 and voff[n] == nverts"); return SZ_ERR_ARG; }
+    {   // voff sanity (only when the offsets are host memory; device pointers are taken on trust)
+        cudaPointerAttributes pa; bool host = true;
+        if (f->n > 0 && cudaPointerGetAttributes(&pa, f->voff) == cudaSuccess) host = (pa.type == cudaMemoryTypeUnregistered || pa.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+        if (f->n > 0 && host && (f->voff[0] != 0 || (i64)f->voff[f->n] != f->nverts)) { sz_set_error("sz_upload: voff[0] must be 0 and voff[n] == nverts"); return SZ_ERR_ARG; }
+    }
     if (f->n > 500000000 / 4) { sz_set_error("sz_upload: too many floes"); return SZ_ERR_ARG; }
     if (prm->Nb < 0 || !(prm->Lx > 0) || !(prm->Ly > 0)) { sz_set_error("sz_upload: bad Nb/Lx/Ly"); return SZ_ERR_ARG; }
     if (!prm->periodic && bnd && (bnd->n < 3 || !bnd->x || !bnd->y)) { sz_set_error("sz_upload: boundary polygon needs >= 3 vertices"); return SZ_ERR_ARG; }

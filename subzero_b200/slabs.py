@@ -1,61 +1,439 @@
-"""Work partition of one contact step over the GPUs of one box (one process per GPU).
+"""Work partition of one contact step over the GPUs of one box: spatial slabs with a halo exchange.
 
-world == 1: the whole field on one device.
+One process per GPU.  The domain [-Lx, Lx) is cut into `world` equal-width slabs along x; a floe belongs to
+the slab that holds its centroid (floes are numbered slab by slab, so every rank owns a contiguous range of
+global floe ids).  Every step each rank
+
+  1. builds the periodic images of ITS floes (floe_interactions_all.m:16-66) and numbers them in the global
+     extended list with one tiny all-gather of counts -- the global list [originals | x-ghosts | y-ghosts] is the
+     reference's, so every `j > i` comparison, partner id and row order is the single-GPU one;
+  2. sends to every other rank the entries (state + outline) that lie within reach (2 max(rmax)) of the x-extent
+     of that rank's entries: the halo exchange, variable-size peer-to-peer messages over NCCL (NVLink);
+  3. resolves, on its own GPU, every pair with at least one owned floe through the extended-list entry point of
+     the C ABI (sz_upload_extended) -- pairs straddling two slabs are evaluated on both sides (about
+     2 * reach / slab_width of all pairs), which keeps each floe's rows bit-identical to the single-GPU
+     result and removes the return exchange of partial forces: the forces on an owned periodic image are
+     folded into its parent by the owner (:242-245), exactly as on one GPU;
+  4. applies the serial kill/transfer fix-up of :175-179 across ranks (all-gather of the rare merge events).
+
+All list surgery is torch tensor code, so the same functions run on CPU tensors under gloo (tests) and on CUDA
+tensors under NCCL.  There is no data-path collective besides the halo exchange and two small all-gathers.
 """
+import ctypes as C
+from dataclasses import dataclass
+
 import numpy as np
+import torch
 
 from . import abi
 from .contact import ContactContext
 from .field import voronoi_field
 
+F64, I64 = torch.float64, torch.int64
+N_STATE = 14          # gid, floe_num, x, y, root_x, root_y, rmax, h, area, u, v, ksi, alive, nverts
+
+
+# ------------------------------------------------------------------------------------------------ host-side layout
+def slab_of(x, Lx, world):
+    w = 2.0 * Lx / world
+    s = np.floor((np.asarray(x) + Lx) / w)
+    s = np.where(np.isnan(s), 0, s)
+    return np.clip(s, 0, world - 1).astype(np.int64)
+
+
+def sort_by_slab(soa, Lx, world):
+    """Renumber the floes slab by slab (stable).  Returns (permuted FloesSoA, id_start [world+1])."""
+    slab = slab_of(soa.x, Lx, world)
+    order = np.argsort(slab, kind="stable")
+    nv = (soa.voff[1:] - soa.voff[:-1]).astype(np.int64)
+    new_nv = nv[order]
+    new_off = np.zeros(soa.n + 1, np.int64)
+    np.cumsum(new_nv, out=new_off[1:])
+    idx = np.repeat(soa.voff[:-1].astype(np.int64)[order] - new_off[:-1], new_nv) + np.arange(int(new_off[-1]))
+    out = abi.FloesSoA(*(getattr(soa, k)[order] for k in abi.FloesSoA.FIELDS), soa.alive[order], new_off.astype(np.int32), soa.vx[idx], soa.vy[idx])
+    starts = np.searchsorted(slab[order], np.arange(world + 1), side="left").astype(np.int64)
+    return out, starts
+
+
+def take_range(soa, a, b):
+    v0, v1 = int(soa.voff[a]), int(soa.voff[b])
+    return abi.FloesSoA(*(getattr(soa, k)[a:b] for k in abi.FloesSoA.FIELDS), soa.alive[a:b], (soa.voff[a:b + 1] - v0).astype(np.int32), soa.vx[v0:v1], soa.vy[v0:v1])
+
+
+# ------------------------------------------------------------------------------------------------ communication
+class Comm:
+    """the three exchanges the slab step needs, over torch.distributed (nccl or gloo) or nothing (world 1)"""
+
+    def __init__(self, dist, rank, world, device):
+        self.dist, self.rank, self.world, self.device = dist, rank, world, device
+        # gloo moves CPU tensors only: CUDA tensors are staged through the host (tests that emulate two ranks on one GPU)
+        self.stage = world > 1 and dist.get_backend() == "gloo" and torch.device(device).type == "cuda"
+
+    def all_gather(self, t):
+        """t [k] -> [world, k]"""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        src = t.cpu() if self.stage else t
+        out = [torch.empty_like(src) for _ in range(self.world)]
+        self.dist.all_gather(out, src.contiguous())
+        return torch.stack(out).to(t.device)
+
+    def exchange(self, send, send_counts, recv_counts):
+        """variable all-to-all of rows: send [sum(send_counts), k] grouped by destination -> [sum(recv_counts), k]"""
+        k = send.shape[1:]
+        dev = send.device
+        if self.stage:
+            send = send.cpu()
+        recv = torch.empty((int(sum(recv_counts)),) + tuple(k), dtype=send.dtype, device=send.device)
+        if self.world == 1:
+            return recv
+        ops, so, ro = [], 0, 0
+        for p in range(self.world):
+            sc, rc = int(send_counts[p]), int(recv_counts[p])
+            if p != self.rank:
+                if sc:
+                    ops.append(self.dist.P2POp(self.dist.isend, send[so:so + sc].contiguous(), p))
+                if rc:
+                    ops.append(self.dist.P2POp(self.dist.irecv, recv[ro:ro + rc], p))
+            so += sc
+            ro += rc
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+        return recv.to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ per-rank state
+@dataclass
+class SlabState:
+    """this rank's floes (a contiguous range of global ids) as torch tensors on the compute device"""
+    id0: int
+    n_global: int
+    x: torch.Tensor
+    y: torch.Tensor
+    rmax: torch.Tensor
+    h: torch.Tensor
+    area: torch.Tensor
+    u: torch.Tensor
+    v: torch.Tensor
+    ksi: torch.Tensor
+    alive: torch.Tensor      # uint8
+    voff: torch.Tensor       # int64 [n+1]
+    vx: torch.Tensor
+    vy: torch.Tensor
+    ext: tuple = None        # (minvx, maxvx, minvy, maxvy) per floe: static while the outlines do not change
+
+    @staticmethod
+    def from_soa(soa, id0, n_global, device):
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(device)
+        s = SlabState(id0, n_global, *(t(getattr(soa, k), F64) for k in abi.FloesSoA.FIELDS), t(soa.alive, torch.uint8), t(soa.voff, I64), t(soa.vx, F64), t(soa.vy, F64))
+        s.update_outline_extents()
+        return s
+
+    @property
+    def n(self):
+        return self.x.shape[0]
+
+    def update_outline_extents(self):
+        n = self.n
+        nv = self.voff[1:] - self.voff[:-1]
+        seg = torch.repeat_interleave(torch.arange(n, device=self.x.device), nv)
+        big = torch.full((n,), float("inf"), dtype=F64, device=self.x.device)
+        mn = lambda v: big.clone().scatter_reduce(0, seg, v, "amin", include_self=True)
+        mx = lambda v: (-big).scatter_reduce(0, seg, v, "amax", include_self=True)
+        self.ext = (mn(self.vx), mx(self.vx), mn(self.vy), mx(self.vy))
+
+
+@dataclass
+class LocalList:
+    """this rank's part of the global extended floe list, ascending gid (what sz_upload_extended takes)"""
+    gid: torch.Tensor        # int64, 0-based global position
+    floe_num: torch.Tensor   # int64, FloeNums
+    x: torch.Tensor
+    y: torch.Tensor
+    root_x: torch.Tensor
+    root_y: torch.Tensor
+    body: torch.Tensor       # [n, 6] rmax h area u v ksi
+    alive: torch.Tensor      # uint8
+    owned: torch.Tensor      # uint8
+    parent: torch.Tensor     # int64, 1-based local index of an owned image's parent, 0 otherwise
+    voff: torch.Tensor       # int64 [n+1]
+    vx: torch.Tensor
+    vy: torch.Tensor
+    n_ext_global: int
+    halo_sent: int
+    halo_bytes: int
+
+
+def _sgn(t):
+    return (t > 0).to(F64) - (t < 0).to(F64)
+
+
+def build_local_list(st, Lx, Ly, periodic, reach, comm):
+    """Steps 1 and 2 of the module docstring.  `reach` = 2 * max(rmax) over all ranks."""
+    dev = st.x.device
+    n = st.n
+    ar = torch.arange(n, device=dev)
+    alive = st.alive != 0
+    minvx, maxvx, minvy, maxvy = st.ext
+    if periodic:
+        # x pass over the originals (:28-39): max_v |c_alpha(1,v) + Xi| > Lx; fl(v + X) is monotone in v, so the maximum
+        # over the vertices is attained at an extreme of the outline
+        fx = alive & (torch.maximum((maxvx + st.x).abs(), (minvx + st.x).abs()) > Lx)
+        xg_par = fx.nonzero().squeeze(1)
+        xg_x, xg_y = st.x[xg_par] - 2 * Lx * _sgn(st.x[xg_par]), st.y[xg_par]
+        # y pass over originals + x-ghosts (:49-60)
+        src_all = torch.cat([ar, xg_par])
+        x_all, y_all = torch.cat([st.x, xg_x]), torch.cat([st.y, xg_y])
+        fy = alive[src_all] & (torch.maximum((maxvy[src_all] + y_all).abs(), (minvy[src_all] + y_all).abs()) > Ly)
+        yg_par = fy.nonzero().squeeze(1)
+        yg_x, yg_y = x_all[yg_par], y_all[yg_par] - 2 * Ly * _sgn(y_all[yg_par])
+    else:
+        xg_par = yg_par = torch.zeros(0, dtype=I64, device=dev)
+        xg_x = xg_y = yg_x = yg_y = torch.zeros(0, dtype=F64, device=dev)
+        src_all = ar
+    cx, cy = xg_par.shape[0], yg_par.shape[0]
+    cyo = int((yg_par < n).sum()) if cy else 0
+    # x-extents of this rank's entries: A = originals (and their y-images), B = x-images (and theirs)
+    inf = float("inf")
+    fin = st.x[~torch.isnan(st.x)]
+    a_lo, a_hi = (float(fin.min()), float(fin.max())) if fin.numel() else (inf, -inf)
+    b_lo, b_hi = (float(xg_x.min()), float(xg_x.max())) if cx else (inf, -inf)
+    meta = comm.all_gather(torch.tensor([cx, cyo, cy - cyo, a_lo, a_hi, b_lo, b_hi], dtype=F64, device=dev)).cpu()
+    cnt = meta[:, :3].to(I64)
+    r = comm.rank
+    n0 = st.n_global
+    n1 = n0 + int(cnt[:, 0].sum())
+    base_yo, base_yx = n1, n1 + int(cnt[:, 1].sum())
+    n_ext = base_yx + int(cnt[:, 2].sum())
+    gid = torch.cat([st.id0 + ar,
+                     n0 + int(cnt[:r, 0].sum()) + torch.arange(cx, device=dev),
+                     base_yo + int(cnt[:r, 1].sum()) + torch.arange(cyo, device=dev),
+                     base_yx + int(cnt[:r, 2].sum()) + torch.arange(cy - cyo, device=dev)])
+    src = torch.cat([ar, xg_par, src_all[yg_par]])                       # local original each own entry images
+    ox, oy = torch.cat([st.x, xg_x, yg_x]), torch.cat([st.y, xg_y, yg_y])
+    n_own = n + cx + cy
+    fnum = torch.cat([st.id0 + ar + 1, -(st.id0 + src[n:] + 1)])
+    par_own = torch.cat([torch.full((n,), -1, dtype=I64, device=dev), xg_par, yg_par])   # index into the own list
+
+    # ---- halo selection and exchange
+    send_idx, send_counts = [], [0] * comm.world
+    for p in range(comm.world):
+        if p == r:
+            continue
+        alo, ahi, blo, bhi = (float(v) for v in meta[p, 3:7])
+        m = ((ox >= alo - reach) & (ox <= ahi + reach)) | ((ox >= blo - reach) & (ox <= bhi + reach))
+        idx = m.nonzero().squeeze(1)
+        send_idx.append(idx)
+        send_counts[p] = idx.shape[0]
+    sidx = torch.cat(send_idx) if send_idx else torch.zeros(0, dtype=I64, device=dev)
+    ssrc = src[sidx]
+    nv_own = st.voff[1:] - st.voff[:-1]
+    s_nv = nv_own[ssrc]
+    state = torch.stack([gid[sidx].to(F64), fnum[sidx].to(F64), ox[sidx], oy[sidx], st.x[ssrc], st.y[ssrc], st.rmax[ssrc], st.h[ssrc], st.area[ssrc],
+                         st.u[ssrc], st.v[ssrc], st.ksi[ssrc], st.alive[ssrc].to(F64), s_nv.to(F64)], 1) if sidx.numel() else torch.zeros((0, N_STATE), dtype=F64, device=dev)
+    s_voff = torch.zeros(sidx.shape[0] + 1, dtype=I64, device=dev)
+    torch.cumsum(s_nv, 0, out=s_voff[1:])
+    vidx = torch.repeat_interleave(st.voff[:-1][ssrc] - s_voff[:-1], s_nv) + torch.arange(int(s_voff[-1]), device=dev)
+    sverts = torch.stack([st.vx[vidx], st.vy[vidx]], 1)
+    vert_counts, o = [0] * comm.world, 0
+    for p in range(comm.world):
+        vert_counts[p] = int(s_voff[o + send_counts[p]] - s_voff[o])
+        o += send_counts[p]
+    theirs = comm.all_gather(torch.tensor(send_counts + vert_counts, dtype=I64, device=dev)).cpu()
+    recv_counts = [int(theirs[p, r]) for p in range(comm.world)]
+    recv_vcounts = [int(theirs[p, comm.world + r]) for p in range(comm.world)]
+    rstate = comm.exchange(state, send_counts, recv_counts)
+    rverts = comm.exchange(sverts, vert_counts, recv_vcounts)
+
+    # ---- merge own + halo, ascending gid
+    nh = rstate.shape[0]
+    all_gid = torch.cat([gid, rstate[:, 0].to(I64)])
+    order = torch.argsort(all_gid)
+    pos = torch.empty_like(order)
+    pos[order] = torch.arange(order.shape[0], device=dev)                # position of every entry in the sorted list
+    parent = torch.zeros(n_own + nh, dtype=I64, device=dev)
+    has_par = par_own >= 0
+    parent[:n_own][has_par] = pos[par_own[has_par]] + 1
+    own_body = torch.stack([st.rmax[src], st.h[src], st.area[src], st.u[src], st.v[src], st.ksi[src]], 1)
+    body = torch.cat([own_body, rstate[:, 6:12]])[order]
+    nv_all = torch.cat([nv_own[src], rstate[:, 13].to(I64)])
+    start_all = torch.cat([st.voff[:-1][src], st.vx.shape[0] + (torch.cumsum(rstate[:, 13].to(I64), 0) - rstate[:, 13].to(I64))])
+    nv_s, start_s = nv_all[order], start_all[order]
+    voff = torch.zeros(order.shape[0] + 1, dtype=I64, device=dev)
+    torch.cumsum(nv_s, 0, out=voff[1:])
+    gidx = torch.repeat_interleave(start_s - voff[:-1], nv_s) + torch.arange(int(voff[-1]), device=dev)
+    pool_x, pool_y = torch.cat([st.vx, rverts[:, 0]]), torch.cat([st.vy, rverts[:, 1]])
+    return LocalList(
+        gid=all_gid[order], floe_num=torch.cat([fnum, rstate[:, 1].to(I64)])[order],
+        x=torch.cat([ox, rstate[:, 2]])[order], y=torch.cat([oy, rstate[:, 3]])[order],
+        root_x=torch.cat([st.x[src], rstate[:, 4]])[order], root_y=torch.cat([st.y[src], rstate[:, 5]])[order],
+        body=body, alive=torch.cat([st.alive[src], rstate[:, 12].to(torch.uint8)])[order],
+        owned=torch.cat([torch.ones(n_own, dtype=torch.uint8, device=dev), torch.zeros(nh, dtype=torch.uint8, device=dev)])[order],
+        parent=parent[order], voff=voff, vx=pool_x[gidx], vy=pool_y[gidx], n_ext_global=n_ext,
+        halo_sent=int(sidx.shape[0]), halo_bytes=int(state.numel() * 8 + sverts.numel() * 8))
+
+
+def fix_kill_transfer(gid, floe_num, owned, kill_i, transfer_i, id0, n_own, comm):
+    """floe_interactions_all.m:175-179 across ranks:  for i = 1:length(kill): if kill(i) ~= i && kill(i) > 0,
+    transfer(kill(i)) = i  (serial, so the largest i wins).  Inputs are per local entry; returns (kill, transfer)
+    for this rank's original floes."""
+    dev = gid.device
+    mine = (owned != 0) & (floe_num > 0)
+    kill = kill_i[mine].clone()
+    transfer = transfer_i[mine].clone()
+    ev = (owned != 0) & (kill_i > 0) & (kill_i != gid + 1)
+    rec = torch.stack([gid[ev] + 1, kill_i[ev]], 1).to(I64)
+    cnts = comm.all_gather(torch.tensor([rec.shape[0]], dtype=I64, device=dev)).cpu().flatten()
+    mx = int(cnts.max())
+    if mx == 0:
+        return kill, transfer
+    pad = torch.zeros((mx, 2), dtype=I64, device=dev)
+    pad[:rec.shape[0]] = rec
+    allrec = comm.all_gather(pad.flatten()).reshape(comm.world, mx, 2)
+    recs = torch.cat([allrec[p, :int(cnts[p])] for p in range(comm.world)])
+    tgt = recs[:, 1] - 1 - id0
+    ok = (tgt >= 0) & (tgt < n_own)
+    if ok.any():
+        win = torch.zeros(n_own, dtype=I64, device=dev).scatter_reduce(0, tgt[ok], recs[ok, 0], "amax", include_self=True)
+        transfer = torch.where(win > 0, win.to(transfer.dtype), transfer)
+    return kill, transfer
+
+
+# ------------------------------------------------------------------------------------------------ the job
+class SlabStep:
+    """one rank's contact step over its slab: halo exchange + local GPU step + extraction of its floes' results"""
+
+    def __init__(self, prm, st, comm, ctx):
+        self.prm, self.st, self.comm, self.ctx = prm, st, comm, ctx
+        rm = st.rmax.max() if st.n else torch.zeros((), dtype=F64, device=st.x.device)
+        self.reach = 2.0 * float(comm.all_gather(rm.reshape(1).to(F64)).max())
+        self.local = None
+        self.summary = None
+
+    def run(self):
+        st, prm = self.st, self.prm
+        L = build_local_list(st, prm.Lx, prm.Ly, bool(prm.periodic), self.reach, self.comm)
+        self.local = L
+        n = L.gid.shape[0]
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        keep = [L.x.contiguous(), L.y.contiguous()] + [L.body[:, k].contiguous() for k in range(6)] + [L.alive.contiguous(), i32(L.voff), L.vx.contiguous(), L.vy.contiguous(),
+                i32(L.gid + 1), i32(L.floe_num), L.root_x.contiguous(), L.root_y.contiguous(), L.owned.contiguous(), i32(L.parent)]
+        x, y, rmax, h, area, u, v, ksi, alive, voff, vx, vy, gid1, fnum, rx, ry, owned, parent = keep
+        fs = abi.SzFloesSoA()
+        fs.n, fs.nverts = n, vx.shape[0]
+        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
+        for nm, t in (("x", x), ("y", y), ("rmax", rmax), ("h", h), ("area", area), ("u", u), ("v", v), ("ksi", ksi), ("vx", vx), ("vy", vy)):
+            setattr(fs, nm, P(t, abi.c_dp))
+        fs.alive, fs.voff = P(alive, abi.c_bp), P(voff, abi.c_ip)
+        ext = abi.SzExtendedList(P(gid1, abi.c_ip), P(fnum, abi.c_ip), P(rx, abi.c_dp), P(ry, abi.c_dp), P(owned, abi.c_bp), P(parent, abi.c_ip))
+        if x.is_cuda:
+            torch.cuda.current_stream().synchronize()        # the library copies from these tensors on its own stream
+        abi.check(abi.lib().sz_upload_extended(self.ctx._h, C.byref(prm), C.byref(fs), None, C.byref(ext)))
+        self.ctx._n0 = n
+        self.summary = self.ctx.step_resident()
+        return self.summary
+
+    def results(self):
+        """per-floe outputs and contact rows of this rank's original floes, in global id order"""
+        L, ctx = self.local, self.ctx
+        o = ctx.floe_outputs()
+        off, rows = ctx.rows()
+        mine = ((L.owned != 0) & (L.floe_num > 0)).cpu().numpy()
+        out = {k: v[mine] for k, v in o.items()}
+        dev = L.gid.device
+        kill, transfer = fix_kill_transfer(L.gid, L.floe_num, L.owned, torch.as_tensor(o["kill"], dtype=I64).to(dev), torch.as_tensor(o["transfer"], dtype=I64).to(dev),
+                                           self.st.id0, self.st.n, self.comm)
+        out["kill"], out["transfer"] = kill.cpu().numpy().astype(np.int32), transfer.cpu().numpy().astype(np.int32)
+        idx = np.flatnonzero(mine)
+        cnt = off[idx + 1] - off[idx]
+        row_off = np.zeros(idx.shape[0] + 1, np.int64)
+        np.cumsum(cnt, out=row_off[1:])
+        sel = np.repeat(off[idx] - row_off[:-1], cnt) + np.arange(int(row_off[-1]))
+        return out, row_off, rows[sel]
+
 
 class SlabJob:
+    """bench.py's workload: the synthetic periodic Voronoi field (BASELINE.json configs[4]) on `world` GPUs"""
+
     def __init__(self, n_floes, seed, rank, world, local_rank, dist):
         self.rank, self.world, self.dist = rank, world, dist
-        if world != 1:
-            raise NotImplementedError("multi-GPU slabs: see DESIGN.md (e)")
-        self.prm, self.floes = voronoi_field(n_floes, seed=seed)
+        self.prm, field = voronoi_field(n_floes, seed=seed)
         self.ctx = ContactContext(local_rank)
-        self.ctx.upload(self.prm, self.floes)
         self.summary = None
+        if world == 1:
+            self.floes = field
+            self.ctx.upload(self.prm, self.floes)
+            self.step = None
+        else:
+            field, starts = sort_by_slab(field, self.prm.Lx, world)
+            self.floes = take_range(field, int(starts[rank]), int(starts[rank + 1]))
+            dev = torch.device("cuda", local_rank)
+            self.comm = Comm(dist, rank, world, dev)
+            self.state = SlabState.from_soa(self.floes, int(starts[rank]), n_floes, dev)
+            self.step = SlabStep(self.prm, self.state, self.comm, self.ctx)
         self._pin()
 
     def _pin(self):
-        """pinned host copies of the step's inputs and result buffers (e2e leg)"""
-        import torch
+        """pinned host copies of the step's inputs (e2e leg)"""
         f = self.floes
-        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
         self.pinned = abi.FloesSoA(*(pin(getattr(f, k)) for k in abi.FloesSoA.FIELDS), pin(f.alive), pin(f.voff), pin(f.vx), pin(f.vy))
         self._out = None
         self._rows = None
 
     def step_resident(self):
-        s = self.ctx.step_resident()
+        """one step with this rank's floes resident in HBM; returns (device ms, phase ms)"""
+        if self.step is None:
+            s = self.ctx.step_resident()
+            ms = s.ms_device
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s = self.step.run()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)          # halo exchange + list surgery + local step, on the device timeline
         self.summary = s
-        self.pairs_owned, self.rows_owned, self.pairs_force_total = int(s.n_pairs), int(s.n_rows), int(s.n_pairs_force)
-        return s.ms_device, self.ctx.phase_ms()
+        self.pairs_owned, self.pairs_force_total = int(s.n_pairs_owned), int(s.n_pairs_force)
+        ph = self.ctx.phase_ms()
+        self.rows_owned = int(s.n_rows)
+        return ms, ph
 
     def e2e_step(self):
-        """host buffers in, per-floe outputs and all contact rows out; returns (h2d, d2h) bytes"""
-        import torch
+        """host buffers in (pinned), per-floe outputs and all contact rows out; returns (h2d, d2h) bytes"""
         f = self.pinned
-        s = self.ctx.step(self.prm, f)
-        n = f.n
-        if self._out is None:
-            z = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-            self._out = {"fx": z(n, torch.float64), "fy": z(n, torch.float64), "torque": z(n, torch.float64), "overlap_area": z(n, torch.float64),
-                         "stress": z((n, 2, 2), torch.float64), "xi": z(n, torch.float64), "yi": z(n, torch.float64), "alive": z(n, torch.uint8),
-                         "kill": z(n, torch.int32), "transfer": z(n, torch.int32)}
-        if self._rows is None or self._rows[1].shape[0] < s.n_rows or self._rows[0].shape[0] != s.n + 1:
-            self._rows = (torch.empty(s.n + 1, dtype=torch.int64).pin_memory().numpy(), torch.empty((int(s.n_rows * 1.1) + 16, 7), dtype=torch.float64).pin_memory().numpy())
-        self.ctx.floe_outputs(into=self._out)
-        abi.check(abi.lib().sz_get_rows(self.ctx._h, abi._ptr(self._rows[0], abi.c_lp), abi._ptr(self._rows[1], abi.c_dp)))
         h2d = sum(getattr(f, k).nbytes for k in abi.FloesSoA.FIELDS) + f.alive.nbytes + f.voff.nbytes + f.vx.nbytes + f.vy.nbytes
-        d2h = sum(v.nbytes for v in self._out.values()) + (s.n + 1) * 8 + int(s.n_rows) * 56
+        if self.step is None:
+            s = self.ctx.step(self.prm, f)
+            n = f.n
+            if self._out is None:
+                z = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+                self._out = {"fx": z(n, F64), "fy": z(n, F64), "torque": z(n, F64), "overlap_area": z(n, F64), "stress": z((n, 2, 2), F64),
+                             "xi": z(n, F64), "yi": z(n, F64), "alive": z(n, torch.uint8), "kill": z(n, torch.int32), "transfer": z(n, torch.int32)}
+            if self._rows is None or self._rows[1].shape[0] < s.n_rows or self._rows[0].shape[0] != s.n + 1:
+                self._rows = (torch.empty(s.n + 1, dtype=I64).pin_memory().numpy(), torch.empty((int(s.n_rows * 1.1) + 16, 7), dtype=F64).pin_memory().numpy())
+            self.ctx.floe_outputs(into=self._out)
+            abi.check(abi.lib().sz_get_rows(self.ctx._h, abi._ptr(self._rows[0], abi.c_lp), abi._ptr(self._rows[1], abi.c_dp)))
+            d2h = sum(v.nbytes for v in self._out.values()) + (s.n + 1) * 8 + int(s.n_rows) * 56
+        else:
+            # this rank's floes travel host -> device, the slab step runs, its floes' results travel back
+            dev = self.state.x.device
+            up = lambda a, dt: torch.from_numpy(a).to(dev, non_blocking=True).to(dt)
+            st = self.state
+            st.x, st.y, st.rmax, st.h, st.area, st.u, st.v, st.ksi = (up(getattr(f, k), F64) for k in abi.FloesSoA.FIELDS)
+            st.alive, st.voff, st.vx, st.vy = up(f.alive, torch.uint8), up(f.voff, I64), up(f.vx, F64), up(f.vy, F64)
+            st.update_outline_extents()
+            s = self.step.run()
+            out, row_off, rows = self.step.results()
+            d2h = sum(v.nbytes for v in out.values()) + row_off.nbytes + rows.nbytes
+        self.summary = s
         return h2d, d2h
 
     def describe(self):
-        return "1 GPU, whole field"
+        if self.world == 1:
+            return "1 GPU, whole field"
+        return "%d x-slabs, floe ownership by centroid, halo exchange of straddling floes (state + outlines) over NCCL p2p each step" % self.world
 
     def close(self):
         self.ctx.close()
