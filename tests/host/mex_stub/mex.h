@@ -1,0 +1,14 @@
+/* Minimal declarations of the MATLAB mex API, ONLY so that the gateway source can be syntax-checked in a container
+ * without MATLAB (tests/test_abi.py).  Not a MATLAB header and never shipped. */
+#pragma once
+#include <stddef.h>
+typedef struct mxArray_tag mxArray;
+typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
+extern "C" {
+bool mxIsStruct(const mxArray*); bool mxIsDouble(const mxArray*); bool mxIsComplex(const mxArray*); bool mxIsEmpty(const mxArray*);
+mxArray* mxGetField(const mxArray*, size_t, const char*); size_t mxGetNumberOfElements(const mxArray*);
+double* mxGetPr(const mxArray*); double mxGetScalar(const mxArray*);
+mxArray* mxCreateDoubleMatrix(size_t, size_t, mxComplexity); mxArray* mxCreateDoubleScalar(double);
+mxArray* mxCreateStructMatrix(size_t, size_t, int, const char**); void mxSetFieldByNumber(mxArray*, size_t, int, mxArray*);
+void mexErrMsgIdAndTxt(const char*, const char*, ...); int mexAtExit(void (*)(void));
+}

@@ -98,3 +98,22 @@ def test_field_generator_shapes():
         assert area2 < 0                                               # clockwise, like FloeShapes.mat
     import numpy as np
     assert abs(f.area.sum() / (4 * prm.Lx * prm.Ly) - 1.02 ** 2) < 1e-9   # cells tile the domain, inflated by 1.02
+
+
+def test_mex_gateway_source_compiles_against_the_stub_header():
+    """MATLAB is not installed: the gateway (subzero_b200/matlab/sz_contact_mex.cpp, modelled on private/mexclipper.cpp)
+    is syntax-checked against a stub mex.h so that it cannot rot"""
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "tests", "host", "mex_stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "subzero_b200", "matlab", "sz_contact_mex.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_standalone_driver_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    import torch
+    exe = str(tmp_path / "sz_driver")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "sz_driver.cpp"),
+                        "-L" + os.path.dirname(abi.LIB_PATH), "-lsubzero_b200", "-Wl,-rpath," + os.path.dirname(abi.LIB_PATH), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "1000", "1", "1"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
