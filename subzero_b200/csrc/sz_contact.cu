@@ -71,9 +71,10 @@ struct Counters {
     int n1, n;                     // extended-list sizes after the x pass / after the y pass
     int n_pairs;
     int row_used, path_used, vert_used;
-    int listM, listL, wlistM, wlistL;
+    int listS, listM, listL, wlistM, wlistL;
+    int bins[64], bin_fill[64];    // class-S work list: pairs bucketed by vertex count
     int total_rows;
-    int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned;
+    int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject;
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
     u64 rmax_bits;
     u64 n_fin_rows, n_inf_rows;
@@ -105,7 +106,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listM, listL;
+    DBuf<int> listS, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -375,6 +376,75 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ narrow-phase work list
+// Per entry of the extended list: the bounding box of its outline in Clipper's coordinates (polyclip.m:66) and
+// whether the outline survives Clipper's AddPath (>= 3 vertices, not all collinear: clipper.cpp:1058,1119-1123).
+__global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const double* __restrict__ ey, const int* __restrict__ esrc, const int* __restrict__ voff,
+                                const double* __restrict__ vx, const double* __restrict__ vy, i64* __restrict__ ebb, uint8_t* __restrict__ evalid, int* __restrict__ env)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int s = esrc[e], o = voff[s], nv = voff[s + 1] - o;
+    const double X = ex[e], Y = ey[e];
+    i64 xmn = 0x7fffffffffffffffLL, xmx = -0x7fffffffffffffffLL - 1, ymn = xmn, ymx = xmx;
+    szclip::P64 p0{0, 0}, p1{0, 0}; int have = 0; bool valid = false;
+    for (int t = 0; t < nv; ++t) {
+        szclip::P64 p; p.x = szpf::matlab_int64((vx[o + t] + X) * SZ_SCALE); p.y = szpf::matlab_int64((vy[o + t] + Y) * SZ_SCALE);
+        xmn = p.x < xmn ? p.x : xmn; xmx = p.x > xmx ? p.x : xmx; ymn = p.y < ymn ? p.y : ymn; ymx = p.y > ymx ? p.y : ymx;
+        if (have == 0) { p0 = p; have = 1; }
+        else if (have == 1) { if (p != p0) { p1 = p; have = 2; } }
+        else if (!valid && !szclip::slopes_eq3(p0, p1, p)) valid = true;
+    }
+    // coordinates must also stay far from Clipper's hiRange for the shortcut to be trusted
+    if (xmx > (1LL << 61) || ymx > (1LL << 61) || xmn < -(1LL << 61) || ymn < -(1LL << 61)) valid = false;
+    ebb[(size_t)e * 4] = xmn; ebb[(size_t)e * 4 + 1] = xmx; ebb[(size_t)e * 4 + 2] = ymn; ebb[(size_t)e * 4 + 3] = ymx;
+    evalid[e] = valid; env[e] = nv;
+}
+// Pass 0 counts, pass 1 scatters.  A pair whose outlines both survive AddPath and whose integer bounding boxes are
+// strictly disjoint has an empty Clipper intersection (and cannot fail), so floe_interactions returns zero force and
+// overlap 0 (:43-51,71-74): it is answered here.  Every other pair is bucketed by n1 + n2 so that the pairs a CTA
+// sweeps together have the same number of scanbeams.
+__global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
+                                     const uint8_t* __restrict__ evalid, const int* __restrict__ env, int want_polys,
+                                     int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
+                                     int* __restrict__ listS, Counters* c)
+{
+    __shared__ int sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int key = -1, slot = 0;
+    if (p < np) {
+        const int i = pi[p], j = pj[p];
+        const i64* a = ebb + (size_t)i * 4; const i64* b = ebb + (size_t)j * 4;
+        const bool disjoint = evalid[i] && evalid[j] && (a[1] < b[0] || b[1] < a[0] || a[3] < b[2] || b[3] < a[2]);
+        if (disjoint) {
+            if (pass == 0) { status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0; }
+        } else {
+            key = env[i] + env[j]; key = key > 63 ? 63 : key;
+            slot = atomicAdd(&sh[key], 1);
+        }
+    }
+    __syncthreads();
+    if (pass == 0) {
+        if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&c->bins[threadIdx.x], sh[threadIdx.x]);
+        return;
+    }
+    // pass 1: bins[] holds exclusive offsets; reserve this CTA's share of every bucket, then place
+    __shared__ int base[64];
+    if (threadIdx.x < 64) base[threadIdx.x] = sh[threadIdx.x] ? atomicAdd(&c->bin_fill[threadIdx.x], sh[threadIdx.x]) : 0;
+    __syncthreads();
+    if (key >= 0) listS[c->bins[key] + base[key] + slot] = p;
+}
+__global__ void bins_scan_kernel(Counters* c, int np)
+{
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < 64; ++k) { const int v = c->bins[k]; c->bins[k] = run; run += v; c->bin_fill[k] = 0; }
+        c->listS = run; c->n_bbox_reject = np - run;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K4 assembly
 __global__ void tcount_kernel(int np, const int* __restrict__ pj, const int* __restrict__ nrows, int* __restrict__ tcnt)
 {
@@ -622,14 +692,14 @@ extern "C" void sz_destroy(SzContext* c)
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
-                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
+                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->listS, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
+    DBuf<uint8_t>* ub[] = {&c->evalid, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
     for (auto* b : ub) b->release();
-    DBuf<i64>* lb[] = {&c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
+    DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
@@ -764,7 +834,18 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         cntM = D_CNT(listM); cntL = D_CNT(listL); lstM = c->listM.p; lstL = c->listL.p;
     }
     a.next_list = lstM; a.next_count = cntM;
+    if (!wall) {
+        // work list of class S: bounding-box-disjoint pairs answered, the rest bucketed by vertex count
+        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->prm.want_clip_polys,
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->d_cnt);
+        bins_scan_kernel<<<1, 32, 0, st>>>(c->d_cnt, n_work);
+        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->prm.want_clip_polys,
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->d_cnt);
+        g_launches += 3;
+        a.list = c->listS.p; a.list_count = D_CNT(listS);
+    }
     ++g_launches; sz_launch_narrow_S(&a, st);
+    a.list = nullptr; a.list_count = nullptr;
     CK(cudaGetLastError());
     CKS(read_counters(c));
     int nM = wall ? c->h_cnt->wlistM : c->h_cnt->listM;
@@ -888,6 +969,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
+    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1));
+    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p); }
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
     if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }
@@ -898,7 +981,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     }
     for (int attempt = 0; attempt < 3; ++attempt) {
         Counters z = *c->h_cnt;
-        z.row_used = z.path_used = z.vert_used = z.listM = z.listL = z.wlistM = z.wlistL = 0;
+        z.row_used = z.path_used = z.vert_used = z.listS = z.listM = z.listL = z.wlistM = z.wlistL = 0;
+        memset(z.bins, 0, sizeof(z.bins)); memset(z.bin_fill, 0, sizeof(z.bin_fill));
         *c->h_cnt = z;
         CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
         CK(cudaMemsetAsync(c->pstatus.p, 0, (size_t)(np + 1) * 4, st)); CK(cudaMemsetAsync(c->pnrows.p, 0, (size_t)(np + 1) * 4, st));

@@ -146,7 +146,6 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     }
 }
 
-// class S: arena in local memory, one thread per pair
 // class S launch shape: one 1024-thread CTA per SM (64 registers per thread).  With SZ_BLOCK_SYNC (default) all 32
 // warps of the CTA walk the sweep phases together and share the instruction lines of each phase; measured on B200
 // at 1M floes: warp-synchronous 128-thread CTAs 181 ms, block-synchronous 512 threads 154 ms, 1024 threads 147 ms.
@@ -156,12 +155,15 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
 #ifndef SZ_S_TPB
 #define SZ_S_TPB 1024
 #endif
+// class S: arena in local memory, one thread per work item (pairs come through the bucketed work list)
 template <class C>
 __global__ void __launch_bounds__(SZ_S_TPB, SZ_S_MINB) narrow_local_kernel(const NarrowArgs a)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.list ? *a.list_count : a.n_work;
+    if (blockIdx.x * blockDim.x >= n) return;           // whole CTA beyond the list: uniform exit
     szpf::Workspace<C> w;
-    resolve_pair<C>(a, k, k < a.n_work, w);
+    resolve_pair<C>(a, t < n ? (a.list ? a.list[t] : t) : 0, t < n, w);
 }
 
 // classes M/L: arena in HBM scratch, persistent threads striding over the work list (n_threads is a
