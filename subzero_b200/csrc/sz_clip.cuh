@@ -245,8 +245,9 @@ struct ClipEngine {
     INode  il[C::IN];
     Join   jn[C::J];
     Join   gj[C::GJ];
-    i64    sb[C::SB];          // scanbeam Ys, ascending, unique (priority_queue + duplicate popping, :1335-1348)
-    int n_ed, n_op, n_or, n_lm, n_il, n_jn, n_gj, n_sb;
+    i64    sb[C::SB];          // scanbeam Ys (see insert_scanbeam)
+    int n_ed, n_op, n_or, n_lm, n_il, n_jn, n_gj, n_sb;   // n_sb: scanbeam insertions of this sweep
+    int sb_lo, sb_hi;
     int cur_lm;
     idx_t ael, sel;            // m_ActiveEdges, m_SortedEdges
     int clip_op;
@@ -256,7 +257,7 @@ struct ClipEngine {
     SZ_HD void begin(int op_)
     {
         n_ed = n_op = n_or = n_lm = n_il = n_jn = n_gj = n_sb = 0;
-        cur_lm = 0; ael = sel = NIL; clip_op = op_; status = ST_OK;
+        cur_lm = 0; ael = sel = NIL; clip_op = op_; status = ST_OK; sb_lo = sb_hi = C::SB;
     }
     SZ_HD bool is_horz(idx_t e) const { return ed[e].dx == SZ_HORIZONTAL; }
     SZ_HD void fail(int st) { if (status == ST_OK) status = st; }
@@ -425,16 +426,20 @@ struct ClipEngine {
     }
 
     // ---------------------------------------------------------------- scanbeam (:1335-1348)
+    // The reference keeps the pending scanbeam Ys in a priority_queue and pops duplicates; here they are the sorted,
+    // duplicate-free run sb[sb_lo, sb_hi), anchored at the TOP of the buffer: the sweep pops the largest Y from sb_hi and
+    // almost every insertion is a new smallest Y, which lands at sb_lo - 1 without moving anything.  The run only moves
+    // down, so the capacity bounds the number of insertions of one sweep (<= edges + local minima).
     SZ_HDM void insert_scanbeam(i64 y)
     {
-        int k = n_sb;
-        while (k > 0 && sb[k - 1] > y) --k;
-        if (k > 0 && sb[k - 1] == y) return;
-        if (n_sb >= C::SB) { fail(ST_OVERFLOW); return; }
-        for (int t = n_sb; t > k; --t) sb[t] = sb[t - 1];
-        sb[k] = y; ++n_sb;
+        int k = sb_lo;
+        while (k < sb_hi && sb[k] < y) ++k;
+        if (k < sb_hi && sb[k] == y) return;
+        if (sb_lo == 0) { fail(ST_OVERFLOW); return; }
+        for (int t = sb_lo; t < k; ++t) sb[t - 1] = sb[t];
+        sb[k - 1] = y; --sb_lo; ++n_sb;
     }
-    SZ_HD bool pop_scanbeam(i64& y) { if (n_sb == 0) return false; y = sb[--n_sb]; return true; }
+    SZ_HD bool pop_scanbeam(i64& y) { if (sb_lo == sb_hi) return false; y = sb[--sb_hi]; return true; }
 
     // ---------------------------------------------------------------- AEL / SEL plumbing
     SZ_HDM void delete_from_ael(idx_t e)   // :1367-1377

@@ -23,11 +23,11 @@ using szpf::Body;
 using szclip::i64;
 using szclip::P64;
 
-typedef szclip::ClipCaps<40, 20, 112, 32, 64, 32, 16, 56> ClipS;
+typedef szclip::ClipCaps<40, 20, 112, 32, 64, 32, 16, 64> ClipS;
 typedef szpf::PairCaps<ClipS, 20, 64, 6, 40, 4> PairS;
-typedef szclip::ClipCaps<384, 192, 1536, 256, 1536, 256, 128, 448> ClipM;
+typedef szclip::ClipCaps<384, 192, 1536, 256, 1536, 256, 128, 576> ClipM;
 typedef szpf::PairCaps<ClipM, 192, 768, 16, 512, 16> PairM;
-typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3000> ClipL;
+typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3900> ClipL;
 typedef szpf::PairCaps<ClipL, 1300, 5200, 64, 6000, 32> PairL;
 
 // Everything a narrow-phase launch reads and writes.  Indices are 0-based positions in the extended

@@ -94,12 +94,15 @@ struct CountSink { int n; SZ_HD void begin_path(int) { ++n; } SZ_HD void point(P
 // phase are fetched once per CTA instead of once per warp (the sweep's SASS is far larger than the I-cache)
 #define SZ_WARP_ANY(p) __syncthreads_or((p))
 #define SZ_WARP_SYNC() __syncthreads()
+#define SZ_LANE_SYNC() __syncwarp()
 #elif defined(__CUDA_ARCH__)
 #define SZ_WARP_ANY(p) __any_sync(0xffffffffu, (p))
 #define SZ_WARP_SYNC() __syncwarp()
+#define SZ_LANE_SYNC() __syncwarp()
 #else
 #define SZ_WARP_ANY(p) (p)
 #define SZ_WARP_SYNC() ((void)0)
+#define SZ_LANE_SYNC() ((void)0)
 #endif
 
 // the subject / clip path of the next clip: either a world outline shifted by (dx,dy) and packed like
@@ -319,6 +322,9 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
     double fdx = 0, fdy = 0, dl = 0, pcx = 0, pcy = 0, Ak = 0;
     bool outline_checked = false, outline_ok = true;
 
+    // The loop body is a SEQUENCE of predicated blocks with a lane re-convergence point after each one (no early
+    // `continue`): the lanes of a warp resolve different pairs, and a block that one lane leaves early must not make
+    // the others run the rest of the body one lane at a time (first profile: InterX ran with 1.2 of 32 lanes active).
     for (;;) {
         if (!SZ_WARP_ANY(phase != PH_DONE)) break;
         // ---- the clip this lane needs now
@@ -333,16 +339,22 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             m_now = 1;
         }
         const int st = run_sweep(w.eng, phase != PH_DONE, m_now, subj, clip);
-        if (phase == PH_DONE) continue;
-        if (st != PS_OK) { res.status = st; phase = PH_DONE; continue; }
-
+        if (phase != PH_DONE && st != PS_OK) { res.status = st; phase = PH_DONE; }
+        const int ph = phase;           // the phase whose clip just ran
         bool next_region = false;       // prepare the contact direction of region k
         bool finish_region = false;     // clips of region k are done: write its row
-        if (phase == PH_CLIP1) {
+        SZ_LANE_SYNC();
+
+        // ---- after clip #1 (:29-84)
+        bool a1 = (ph == PH_CLIP1);
+        if (a1) {
             RegionSink<C> sink(w.rax, w.ray, w.ra_off);
             w.eng.emit(sink);
-            if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
-            w.ra_n = sink.n_paths;
+            if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; a1 = false; }
+            else w.ra_n = sink.n_paths;
+        }
+        SZ_LANE_SYNC();
+        if (a1) {
             if (boundary && w.ra_n > 0) {                                             // :35-40
                 if (ring_polyarea(w.rax, w.ray, w.ra_off[1]) / f1.area > P.wall_frac) overlap = SZ_INF;
             }
@@ -376,21 +388,35 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
                 gx = w.c2x[0] - w.c2x[w.n2 - 1]; gy = w.c2y[0] - w.c2y[w.n2 - 1];
                 if (sqrt(gx * gx + gy * gy) > P.close_gap) { w.c2x[w.n2] = w.c2x[0]; w.c2y[w.n2] = w.c2y[0]; ++w.n2; }
             }
-            if (!interx(w)) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
+        }
+        SZ_LANE_SYNC();
+        if (a1) {
+            if (!interx(w)) { res.status = PS_CAPACITY; phase = PH_DONE; a1 = false; }      // :70
+        }
+        SZ_LANE_SYNC();
+        if (a1) {
             res.overlap_state = overlap;
-            if (w.np < 2 || overlap == SZ_INF || overlap == -SZ_INF || w.ra_n == 0) { phase = PH_DONE; continue; }   // :71-74 zero force
-            res.overlap_state = 0;
-            const int N1 = w.n1 - 1, N2 = w.n2 - 1;
-            amin = (double)(N1 < N2 ? N1 : N2) * P.amin_per_vertex;                   // :79
-            k = -1; next_region = true;
-        } else if (phase == PH_CLIP2) {
+            if (w.np < 2 || overlap == SZ_INF || overlap == -SZ_INF || w.ra_n == 0) phase = PH_DONE;      // :71-74 zero force
+            else {
+                res.overlap_state = 0;
+                const int N1 = w.n1 - 1, N2 = w.n2 - 1;
+                amin = (double)(N1 < N2 ? N1 : N2) * P.amin_per_vertex;               // :79
+                k = -1; next_region = true;
+            }
+        }
+        // ---- after clip #2 (:152-155)
+        if (ph == PH_CLIP2) {
             RegionSink<C> sink(w.rbx, w.rby, w.rb_off);
             w.eng.emit(sink);
-            if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
-            w.rb_n = sink.n_paths;
-            ii = 0;
-            if (w.rb_n > 0) phase = PH_CLIP3; else finish_region = true;
-        } else {   // PH_CLIP3: clip #3 only needs "empty or not" (:159)
+            if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; }
+            else {
+                w.rb_n = sink.n_paths;
+                ii = 0;
+                if (w.rb_n > 0) phase = PH_CLIP3; else finish_region = true;
+            }
+        }
+        // ---- after clip #3 (:158-164): only "empty or not" matters
+        if (ph == PH_CLIP3) {
             CountSink cs; cs.n = 0;
             w.eng.emit(cs);
             if (cs.n > 0) {
@@ -400,7 +426,9 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             ++ii;
             if (ii >= w.rb_n) finish_region = true;
         }
+        SZ_LANE_SYNC();
 
+        // ---- the row of region k (:167-187)
         if (finish_region) {
             const double fx = fdx * Ak * force_factor, fy = fdy * Ak * force_factor;  // :167
             // tangential (:170-183)
@@ -420,20 +448,26 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             ++n_rows;
             next_region = true;
         }
+        SZ_LANE_SYNC();
 
+        // ---- contact direction of the next region with Ar >= Amin (:83,92-150)
         if (next_region) {
-            // advance to the next region with Ar >= Amin (:83)
             ++k;
             while (k < w.ra_n && w.ar[k] < amin) ++k;
-            if (k >= w.ra_n) { phase = PH_DONE; continue; }
-            if (n_rows >= C::ROWS) { res.status = PS_CAPACITY; phase = PH_DONE; continue; }
+            if (k >= w.ra_n) { phase = PH_DONE; next_region = false; }
+            else if (n_rows >= C::ROWS) { res.status = PS_CAPACITY; phase = PH_DONE; next_region = false; }
+        }
+        int m = 0; double cx = 0, cy = 0, p0x = 0, p0y = 0, p1x = 0, p1y = 0;
+        if (next_region) {
             RX = w.rax + w.ra_off[k]; RY = w.ray + w.ra_off[k];
             nr = w.ra_off[k + 1] - w.ra_off[k];
             Ak = w.ar[k];
-            double a_unused, cx, cy;
+            double a_unused;
             ring_area_centroid(RX, RY, nr, a_unused, cx, cy);                         // :96-97
+        }
+        SZ_LANE_SYNC();
+        if (next_region) {
             // dsearchn + dist<1 (:98-100)
-            int m = 0; double p0x = 0, p0y = 0, p1x = 0, p1y = 0;
             for (int q = 0; q < w.np; ++q) {
                 double best = SZ_INF; int bi = 0;
                 for (int v = 0; v < nr; ++v) {
@@ -447,6 +481,9 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
                     ++m;
                 }
             }
+        }
+        SZ_LANE_SYNC();
+        if (next_region) {
             fdx = 0; fdy = 0; dl = 0; pcx = cx; pcy = cy;
             if (Ak == 0) { pcx = 0; pcy = 0; }                                        // :103-106
             else if (m == 2) {                                                        // :107-112
@@ -456,36 +493,40 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             } else if (m != 0) {
                 // general branch (:117-137), streamed edge by edge
                 if (!outline_checked) { outline_ok = outline_ok_for_poly_dist(w); outline_checked = true; }
-                if (!outline_ok) { res.status = PS_BAD_POLY; phase = PH_DONE; continue; }
-                double xmin = SZ_INF, xmax = -SZ_INF, ymin = SZ_INF, ymax = -SZ_INF;
-                for (int v = 0; v < nr; ++v) {
-                    double x = (double)RX[v] / SZ_SCALE, y = (double)RY[v] / SZ_SCALE;
-                    if (x < xmin) xmin = x;
-                    if (x > xmax) xmax = x;
-                    if (y < ymin) ymin = y;
-                    if (y > ymax) ymax = y;
-                }
-                double sx = 0, sy = 0, sb = 0; int non = 0;
-                for (int e = 0; e < nr; ++e) {
-                    int e1 = (e + 1 == nr) ? 0 : e + 1;
-                    double xa = (double)RX[e] / SZ_SCALE, ya = (double)RY[e] / SZ_SCALE, xb = (double)RX[e1] / SZ_SCALE, yb = (double)RY[e1] / SZ_SCALE;
-                    double xgh = xb - xa, ygh = yb - ya, xm = (xb + xa) / 2, ym = (yb + ya) / 2;
-                    double b = sqrt(xgh * xgh + ygh * ygh);
-                    double nx = -ygh / b, ny = xgh / b;
-                    double xt = xm + nx / 100, yt = ym + ny / 100;
-                    if (!in_region(xt, yt, RX, RY, nr, xmin, xmax, ymin, ymax)) { nx = -nx; ny = -ny; }
-                    double d = abs_poly_dist(w, xm, ym);
-                    if (d < P.on_edge_tol) {
-                        sx += (-force_factor * b) * nx; sy += (-force_factor * b) * ny; sb += b; ++non;
+                if (!outline_ok) { res.status = PS_BAD_POLY; phase = PH_DONE; next_region = false; }
+                else {
+                    double xmin = SZ_INF, xmax = -SZ_INF, ymin = SZ_INF, ymax = -SZ_INF;
+                    for (int v = 0; v < nr; ++v) {
+                        double x = (double)RX[v] / SZ_SCALE, y = (double)RY[v] / SZ_SCALE;
+                        if (x < xmin) xmin = x;
+                        if (x > xmax) xmax = x;
+                        if (y < ymin) ymin = y;
+                        if (y > ymax) ymax = y;
+                    }
+                    double sx = 0, sy = 0, sb = 0; int non = 0;
+                    for (int e = 0; e < nr; ++e) {
+                        int e1 = (e + 1 == nr) ? 0 : e + 1;
+                        double xa = (double)RX[e] / SZ_SCALE, ya = (double)RY[e] / SZ_SCALE, xb = (double)RX[e1] / SZ_SCALE, yb = (double)RY[e1] / SZ_SCALE;
+                        double xgh = xb - xa, ygh = yb - ya, xm = (xb + xa) / 2, ym = (yb + ya) / 2;
+                        double b = sqrt(xgh * xgh + ygh * ygh);
+                        double nx = -ygh / b, ny = xgh / b;
+                        double xt = xm + nx / 100, yt = ym + ny / 100;
+                        if (!in_region(xt, yt, RX, RY, nr, xmin, xmax, ymin, ymax)) { nx = -nx; ny = -ny; }
+                        double d = abs_poly_dist(w, xm, ym);
+                        if (d < P.on_edge_tol) {
+                            sx += (-force_factor * b) * nx; sy += (-force_factor * b) * ny; sb += b; ++non;
+                        }
+                    }
+                    if (non < nr && non > 0) {
+                        double nrm = sqrt(sx * sx + sy * sy);
+                        fdx = sx / nrm; fdy = sy / nrm; dl = sb / (double)non;
                     }
                 }
-                if (non < nr && non > 0) {
-                    double nrm = sqrt(sx * sx + sy * sy);
-                    fdx = sx / nrm; fdy = sy / nrm; dl = sb / (double)non;
-                }
             }
-            if (dl < P.dl_min) { fdx = 0; fdy = 0; }                                  // :141-142
-            phase = PH_CLIP2;                                                         // sign test (:151-165)
+            if (next_region) {
+                if (dl < P.dl_min) { fdx = 0; fdy = 0; }                              // :141-142
+                phase = PH_CLIP2;                                                     // sign test (:151-165)
+            }
         }
     }
     if (res.status != PS_OK) { res.n_rows = 0; return; }

@@ -16,7 +16,7 @@ extern "C" int szref_clip(const int64_t* sx, const int64_t* sy, int ns, const in
                           int method, int64_t* out_x, int64_t* out_y, int out_cap, int* out_off, int off_cap);
 
 using namespace szclip;
-typedef ClipCaps<2048, 1024, 8192, 2048, 8192, 2048, 512, 2048> BigCaps;
+typedef ClipCaps<2048, 1024, 8192, 2048, 8192, 2048, 512, 3072> BigCaps;
 typedef ClipEngine<BigCaps> BigEngine;
 
 struct VecGetter { const std::vector<P64>* v; P64 operator()(int i) const { return (*v)[i]; } };

@@ -6,7 +6,7 @@
 #include <memory>
 
 using namespace szpf;
-typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3000> BigClip;
+typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3900> BigClip;
 typedef PairCaps<BigClip, 1300, 5200, 64, 6000, 32> BigPair;
 typedef szclip::ClipCaps<32, 16, 96, 32, 64, 32, 16, 48> SmallClip;
 typedef PairCaps<SmallClip, 20, 64, 6, 40, 4> SmallPair;
