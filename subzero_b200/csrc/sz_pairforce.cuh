@@ -179,6 +179,31 @@ SZ_HD double ring_polyarea(const i64* X, const i64* Y, int n)
     return fabs(s / 2);
 }
 
+// Certificate used to answer clip #3 ("does the new region meet region k?", floe_interactions.m:158-159) without a
+// sweep: the point (cX, cY) (Clipper units) lies on the inner side of EVERY edge line of the ring by at least
+// SZ_CERT_MARGIN units.  A point in the kernel of a simple polygon with that margin is the centre of a disc of that
+// radius inside the polygon; if one point certifies for both rings their intersection contains a disc of radius 2^20
+// units (0.24 mm), which Clipper -- whose vertices are rounded by at most a few units -- cannot return as empty.
+// FP64 suffices: |cross| = len * distance, its rounding error is below len * 2^-7 units for rings smaller than 2^43.
+#define SZ_CERT_MARGIN 1048576.0
+SZ_HD bool certify_inside(const i64* X, const i64* Y, int n, double cX, double cY)
+{
+    if (n < 3) return false;
+    double sign = 0;
+    double ax = (double)X[n - 1], ay = (double)Y[n - 1];
+    for (int i = 0; i < n; ++i) {
+        const double bx = (double)X[i], by = (double)Y[i];
+        const double ex = bx - ax, ey = by - ay;
+        const double cr = ex * (cY - ay) - ey * (cX - ax);
+        const double len2 = ex * ex + ey * ey;
+        if (!(cr * cr >= (SZ_CERT_MARGIN * SZ_CERT_MARGIN) * len2) || len2 == 0) return false;
+        const double sg = cr > 0 ? 1.0 : -1.0;
+        if (sign == 0) sign = sg; else if (sg != sign) return false;
+        ax = bx; ay = by;
+    }
+    return true;
+}
+
 // InterX.m:54-77 (two-curve form).  Points are collected, sorted (x, then y) and de-duplicated.
 template <class C>
 SZ_HD bool interx(Workspace<C>& w)
@@ -343,6 +368,7 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
         const int ph = phase;           // the phase whose clip just ran
         bool next_region = false;       // prepare the contact direction of region k
         bool finish_region = false;     // clips of region k are done: write its row
+        bool advance = false;           // look at the next new region of the sign test
         SZ_LANE_SYNC();
 
         // ---- after clip #1 (:29-84)
@@ -412,7 +438,7 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             else {
                 w.rb_n = sink.n_paths;
                 ii = 0;
-                if (w.rb_n > 0) phase = PH_CLIP3; else finish_region = true;
+                advance = true;
             }
         }
         // ---- after clip #3 (:158-164): only "empty or not" matters
@@ -424,6 +450,21 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
                 if (anew / Ak - 1 > 0) { fdx = -fdx; fdy = -fdy; }                     // :161-163
             }
             ++ii;
+            advance = true;
+        }
+        SZ_LANE_SYNC();
+        // ---- next new region: answered by the certificate when one point is well inside both rings, else clip #3
+        if (advance) {
+            phase = PH_CLIP3;
+            const double cX = pcx * SZ_SCALE, cY = pcy * SZ_SCALE;      // centroid of region k
+            while (ii < w.rb_n) {
+                const i64* NX = w.rbx + w.rb_off[ii]; const i64* NY = w.rby + w.rb_off[ii];
+                const int nn = w.rb_off[ii + 1] - w.rb_off[ii];
+                if (!(Ak != 0 && certify_inside(RX, RY, nr, cX, cY) && certify_inside(NX, NY, nn, cX, cY))) break;
+                const double anew = ring_polyarea(NX, NY, nn);                         // :160
+                if (anew / Ak - 1 > 0) { fdx = -fdx; fdy = -fdy; }                     // :161-163
+                ++ii;
+            }
             if (ii >= w.rb_n) finish_region = true;
         }
         SZ_LANE_SYNC();
