@@ -106,7 +106,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listS, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid;
+    DBuf<int> listS, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -380,7 +380,8 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
 // Per entry of the extended list: the bounding box of its outline in Clipper's coordinates (polyclip.m:66) and
 // whether the outline survives Clipper's AddPath (>= 3 vertices, not all collinear: clipper.cpp:1058,1119-1123).
 __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const double* __restrict__ ey, const int* __restrict__ esrc, const int* __restrict__ voff,
-                                const double* __restrict__ vx, const double* __restrict__ vy, i64* __restrict__ ebb, uint8_t* __restrict__ evalid, int* __restrict__ env)
+                                const double* __restrict__ vx, const double* __restrict__ vy, i64* __restrict__ ebb, uint8_t* __restrict__ evalid, int* __restrict__ env,
+                                uint8_t* __restrict__ econvex)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -399,6 +400,13 @@ __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const doub
     if (xmx > (1LL << 61) || ymx > (1LL << 61) || xmn < -(1LL << 61) || ymn < -(1LL << 61)) valid = false;
     ebb[(size_t)e * 4] = xmn; ebb[(size_t)e * 4 + 1] = xmx; ebb[(size_t)e * 4 + 2] = ymn; ebb[(size_t)e * 4 + 3] = ymx;
     evalid[e] = valid; env[e] = nv;
+    // strict convexity of the outline in Clipper's coordinates (closing vertex dropped): enables the margin-certified
+    // sign test of szpf::convex_sign_test
+    struct Get { const double* x; const double* y; double X, Y; int o;
+                 __device__ szclip::P64 operator()(int i) const { szclip::P64 p; p.x = szpf::matlab_int64((x[o + i] + X) * SZ_SCALE); p.y = szpf::matlab_int64((y[o + i] + Y) * SZ_SCALE); return p; } };
+    int no = nv;
+    while (no > 1 && vx[o + no - 1] == vx[o] && vy[o + no - 1] == vy[o]) --no;
+    econvex[e] = valid && szpf::ring_is_strictly_convex(Get{vx, vy, X, Y, o}, no);
 }
 // Pass 0 counts, pass 1 scatters.  A pair whose outlines both survive AddPath and whose integer bounding boxes are
 // strictly disjoint has an empty Clipper intersection (and cannot fail), so floe_interactions returns zero force and
@@ -697,7 +705,7 @@ extern "C" void sz_destroy(SzContext* c)
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->evalid, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
+    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
@@ -816,7 +824,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
 {
     cudaStream_t st = c->stream;
     NarrowArgs a; memset(&a, 0, sizeof(a));
-    a.ex = c->ex.p; a.ey = c->ey.p; a.esrc = c->esrc.p;
+    a.ex = c->ex.p; a.ey = c->ey.p; a.esrc = c->esrc.p; a.econvex = c->econvex.p;
     a.h = c->h.p; a.area = c->area.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
     a.pi = c->pi.p; a.pj = c->pj.p; a.n_work = n_work;
     a.row_pool = c->row_pool.p; a.row_cap = (int)std::min<size_t>(c->row_pool.cap / 5, 0x7fffffff); a.row_used = D_CNT(row_used);
@@ -969,8 +977,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
-    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1));
-    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p); }
+    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1));
+    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p); }
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
     if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }

@@ -36,7 +36,7 @@ typedef szpf::PairCaps<ClipL, 1300, 5200, 64, 6000, 32> PairL;
 // floe_interactions_all.m:33-34,54-55).
 struct NarrowArgs {
     // extended list
-    const double* ex; const double* ey; const int* esrc; const int* egid; const unsigned char* eowned;
+    const double* ex; const double* ey; const int* esrc; const int* egid; const unsigned char* eowned; const unsigned char* econvex;
     // per original floe
     const double* h; const double* area; const double* u; const double* v; const double* ksi;
     const int* voff; const double* vx; const double* vy;
@@ -93,10 +93,10 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     Body b1, b2;
     b1.h = b1.area = b1.Xi = b1.Yi = b1.Ui = b1.Vi = b1.ksi = 0; b2 = b1;
     if (valid && a.wall && (a.egid[k] <= a.P.Nb || !a.eowned[k])) valid = false;     // floes below Nb take no part in the pair loop (floe_interactions_all.m:125)
-    bool escalate = false;
+    bool escalate = false, convex = false;
     if (valid) {
         if (a.wall) { i = a.first_floe + k; b2 = a.bbody; }
-        else { i = a.pi[k]; j = a.pj[k]; }
+        else { i = a.pi[k]; j = a.pj[k]; convex = a.econvex[i] && a.econvex[j]; }
         const int si = a.esrc[i];
         const int o1 = a.voff[si], n1 = a.voff[si + 1] - o1;
         int o2 = 0, n2 = a.bn, sj = 0;
@@ -119,7 +119,7 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     }
     szpf::PairResult res;
     double rows[C::ROWS * 5];
-    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid);
+    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid, convex);
     if (valid && res.status == szpf::PS_CAPACITY && a.next_list) { escalate = true; valid = false; }
     if (escalate) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
     if (!valid) return;
@@ -146,14 +146,15 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     }
 }
 
-// class S launch shape: one 1024-thread CTA per SM (64 registers per thread).  With SZ_BLOCK_SYNC (default) all 32
-// warps of the CTA walk the sweep phases together and share the instruction lines of each phase; measured on B200
-// at 1M floes: warp-synchronous 128-thread CTAs 181 ms, block-synchronous 512 threads 154 ms, 1024 threads 147 ms.
+// class S launch shape: two 512-thread CTAs per SM (64 registers per thread).  With SZ_BLOCK_SYNC (default) all
+// warps of a CTA walk the sweep phases together and share the instruction lines of each phase; measured on B200 at 1M
+// floes (first version of the sweep): warp-synchronous 128-thread CTAs 181 ms, block-synchronous 512 threads 154 ms,
+// 1024 threads 147 ms; after the work list was bucketed, 2 x 512 with one CTA vote per scanbeam is 5 % ahead of 1 x 1024.
 #ifndef SZ_S_MINB
-#define SZ_S_MINB 1
+#define SZ_S_MINB 2
 #endif
 #ifndef SZ_S_TPB
-#define SZ_S_TPB 1024
+#define SZ_S_TPB 512
 #endif
 // class S: arena in local memory, one thread per work item (pairs come through the bucketed work list)
 template <class C>

@@ -132,14 +132,18 @@ SZ_HDN int run_sweep(E& eng, bool want, int method, const ClipInput& subj, const
         eng.add_path(clip, clip.n, 1);
         run = eng.sweep_begin();
     }
+    // SZ_SWEEP_SYNCS: CTA barriers per scanbeam besides the loop vote (0..3)
+#ifndef SZ_SWEEP_SYNCS
+#define SZ_SWEEP_SYNCS 0
+#endif
     for (;;) {
-        SZ_WARP_SYNC();
+        if (SZ_SWEEP_SYNCS >= 3) SZ_WARP_SYNC(); else SZ_LANE_SYNC();
         if (run) run = eng.sweep_next();
         if (!SZ_WARP_ANY(run)) break;
         if (run) run = eng.sweep_intersections();
-        SZ_WARP_SYNC();
+        if (SZ_SWEEP_SYNCS >= 1) SZ_WARP_SYNC(); else SZ_LANE_SYNC();
         if (run) run = eng.sweep_top();
-        SZ_WARP_SYNC();
+        if (SZ_SWEEP_SYNCS >= 2) SZ_WARP_SYNC(); else SZ_LANE_SYNC();
         if (run) run = eng.sweep_minima();
     }
     if (!want) return PS_OK;
@@ -202,6 +206,110 @@ SZ_HD bool certify_inside(const i64* X, const i64* Y, int n, double cX, double c
         ax = bx; ay = by;
     }
     return true;
+}
+
+// Exact convexity of an outline in Clipper's coordinates (polyclip.m:66): every turn has the same strict sign.
+// `get(i)` returns vertex i of a closed ring given with n distinct-position slots (first vertex NOT repeated).
+template <class Getter>
+SZ_HD bool ring_is_strictly_convex(const Getter& get, int n)
+{
+    if (n < 3) return false;
+    int sign = 0;
+    P64 a = get(n - 2), b = get(n - 1);
+    for (int i = 0; i < n; ++i) {
+        const P64 c = get(i);
+        const i64 ux = b.x - a.x, uy = b.y - a.y, vx = c.x - b.x, vy = c.y - b.y;
+        // sign of ux*vy - uy*vx, exactly
+#if defined(__CUDA_ARCH__)
+        const i64 h1 = __mul64hi(ux, vy), h2 = __mul64hi(uy, vx);
+        const unsigned long long l1 = (unsigned long long)ux * (unsigned long long)vy, l2 = (unsigned long long)uy * (unsigned long long)vx;
+        const int sg = (h1 != h2) ? (h1 > h2 ? 1 : -1) : (l1 != l2 ? (l1 > l2 ? 1 : -1) : 0);
+#else
+        const __int128 cr = (__int128)ux * vy - (__int128)uy * vx;
+        const int sg = cr > 0 ? 1 : (cr < 0 ? -1 : 0);
+#endif
+        if (sg == 0) return false;
+        if (sign == 0) sign = sg; else if (sg != sign) return false;
+        a = b; b = c;
+    }
+    return true;
+}
+
+// FP64 Sutherland-Hodgman clip of the convex polygon S by the convex polygon K (open rings).  Used ONLY to decide
+// the sign test of floe_interactions.m:151-165 when the decision has a wide margin (see convex_sign_test); never to
+// produce a polygon that is output.  Returns the vertex count in (ox, oy), or -1 when a buffer would overflow.
+SZ_HD int sh_clip_convex(const double* sx, const double* sy, int ns, double shx, double shy, const double* kx, const double* ky, int nk,
+                         double* ax, double* ay, double* bx, double* by, int cap)
+{
+    if (ns > cap) return -1;
+    for (int i = 0; i < ns; ++i) { ax[i] = sx[i] + shx; ay[i] = sy[i] + shy; }
+    int n = ns;
+    double area2 = 0;
+    for (int i = 0; i < nk; ++i) { const int j = (i + 1 == nk) ? 0 : i + 1; area2 += (kx[i] - kx[0]) * (ky[j] - ky[0]) - (kx[j] - kx[0]) * (ky[i] - ky[0]); }
+    const double sK = area2 >= 0 ? 1.0 : -1.0;
+    for (int e = 0; e < nk && n > 0; ++e) {
+        const int e1 = (e + 1 == nk) ? 0 : e + 1;
+        const double px = kx[e], py = ky[e], dx = kx[e1] - px, dy = ky[e1] - py;
+        int m = 0;
+        double qx = ax[n - 1], qy = ay[n - 1];
+        double dq = sK * (dx * (qy - py) - dy * (qx - px));
+        for (int i = 0; i < n; ++i) {
+            const double rx = ax[i], ry = ay[i];
+            const double dr = sK * (dx * (ry - py) - dy * (rx - px));
+            if ((dq >= 0) != (dr >= 0)) {
+                if (m >= cap) return -1;
+                const double t = dq / (dq - dr);
+                bx[m] = qx + t * (rx - qx); by[m] = qy + t * (ry - qy); ++m;
+            }
+            if (dr >= 0) { if (m >= cap) return -1; bx[m] = rx; by[m] = ry; ++m; }
+            qx = rx; qy = ry; dq = dr;
+        }
+        double* t1 = ax; ax = bx; bx = t1; t1 = ay; ay = by; by = t1;
+        n = m;
+    }
+    // the result sits in (ax, ay) after the swaps: copy to the caller's first buffer if needed is left to the caller
+    return (nk & 1) ? -2 - n : n;      // odd number of swaps: result is in the (bx, by) the caller passed
+}
+
+// Decides the sign test of floe_interactions.m:151-165 for a convex pair without clips #2/#3 when it can be decided
+// with margin.  The reference re-clips floe 1 nudged by force_dir (1 m) and flips force_dir once for every new
+// region that meets region k and is larger than it (:158-163).  For convex outlines the new intersection is one convex
+// region Q; this computes Q in FP64 (error ~1e-9 m per vertex, like Clipper's own 2^-32 m grid) and answers
+//   -1  no flip:  area(Q) < Ak - tol  (no region of the new clip can exceed Ak, whatever its exact shape)
+//   +1  flip:     area(Q) > Ak + tol, and one disc of radius >= 1 mm lies inside both Q and region k
+//    0  undecided -> the caller runs the reference's clips.
+// tol = 1e-6 Ak + 1 m^2 is six orders of magnitude above either computation's rounding.
+template <class C, class W>
+SZ_HD int convex_sign_test(W& w, double fdx, double fdy, const i64* RX, const i64* RY, int nr, double Ak, double pcx, double pcy)
+{
+    // open rings: drop the closing vertex (and a second closing vertex added by :62-67)
+    int n1 = w.n1, n2 = w.n2;
+    while (n1 > 1 && w.c1x[n1 - 1] == w.c1x[0] && w.c1y[n1 - 1] == w.c1y[0]) --n1;
+    while (n2 > 1 && w.c2x[n2 - 1] == w.c2x[0] && w.c2y[n2 - 1] == w.c2y[0]) --n2;
+    const int cap = C::RV / 2;
+    double* ax = reinterpret_cast<double*>(w.rbx); double* ay = ax + cap;
+    double* bx = reinterpret_cast<double*>(w.rby); double* by = bx + cap;
+    int n = sh_clip_convex(w.c1x, w.c1y, n1, fdx, fdy, w.c2x, w.c2y, n2, ax, ay, bx, by, cap);
+    if (n == -1) return 0;
+    const double* qx = ax; const double* qy = ay;
+    if (n <= -2) { n = -2 - n; qx = bx; qy = by; }
+    const double tol = 1e-6 * Ak + 1.0;
+    if (n < 3) return (0.0 < Ak - tol) ? -1 : 0;
+    double a2 = 0;
+    for (int i = 0; i < n; ++i) { const int j = (i + 1 == n) ? 0 : i + 1; a2 += (qx[i] - qx[0]) * (qy[j] - qy[0]) - (qx[j] - qx[0]) * (qy[i] - qy[0]); }
+    const double aQ = fabs(a2) / 2;
+    if (aQ < Ak - tol) return -1;
+    if (!(aQ > Ak + tol)) return 0;
+    // flip needs "the new region meets region k": a disc around region k's centroid inside both
+    if (!certify_inside(RX, RY, nr, pcx * SZ_SCALE, pcy * SZ_SCALE)) return 0;
+    const double sg = a2 > 0 ? 1.0 : -1.0;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        const double ex = qx[j] - qx[i], ey = qy[j] - qy[i];
+        const double cr = sg * (ex * (pcy - qy[i]) - ey * (pcx - qx[i]));
+        if (!(cr >= 1e-3 * sqrt(ex * ex + ey * ey))) return 0;
+    }
+    return 1;
 }
 
 // InterX.m:54-77 (two-curve form).  Points are collected, sorted (x, then y) and de-duplicated.
@@ -312,6 +420,26 @@ SZ_HD bool outline_ok_for_poly_dist(const Workspace<C>& w)   // p_poly_dist.m:16
     return !((s - last) < 10 * SZ_EPS);
 }
 
+// normal + tangential force of one overlap region (floe_interactions.m:167-187): r = Fx Fy Px Py overlap
+SZ_HD void force_row(const Body& f1, const Body& f2, const Params& P, double G, double mu, double force_factor,
+                     double fdx, double fdy, double dl, double Ak, double pcx, double pcy, double* r)
+{
+    const double fx = fdx * Ak * force_factor, fy = fdy * Ak * force_factor;  // :167
+    // tangential (:170-183)
+    const double v1x = f1.Ui + f1.ksi * (pcx - f1.Xi), v1y = f1.Vi + f1.ksi * (pcy - f1.Yi);
+    const double v2x = f2.Ui + f2.ksi * (pcx - f2.Xi), v2y = f2.Vi + f2.ksi * (pcy - f2.Yi);
+    const double vtx = v1x - v2x, vty = v1y - v2y;
+    const double vn = sqrt(vtx * vtx + vty * vty);
+    double dtx = 0, dty = 0;
+    if (!((fabs(vtx) > fabs(vty) ? fabs(vtx) : fabs(vty)) == 0)) { dtx = vtx / vn; dty = vty / vn; }
+    const double dotv = dtx * vtx + dty * vty;
+    const double coef = -dotv * dl * G * vn;
+    double ftx = coef * dtx * P.dt, fty = coef * dty * P.dt;
+    const double fnorm = sqrt(fx * fx + fy * fy);
+    if (sqrt(ftx * ftx + fty * fty) > mu * fnorm) { ftx = -mu * fnorm * dtx; fty = -mu * fnorm * dty; }
+    r[0] = fx + ftx; r[1] = fy + fty; r[2] = pcx; r[3] = pcy; r[4] = Ak;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The force law.  On entry w.c1*/w.c2* hold the two world outlines exactly as the reference builds
 // them (floe_interactions.m:25, floe_interactions_all.m:105; for the wall c2 = hole vertices).
@@ -324,9 +452,9 @@ SZ_HD bool outline_ok_for_poly_dist(const Workspace<C>& w)   // p_poly_dist.m:16
 // After the last clip of a region its force row is written (:167-187) and the next region's contact
 // direction (:96-150) is prepared.
 template <class C>
-SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true)
+SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true, bool convex_pair = false)
 {
-    enum { PH_CLIP1 = 0, PH_CLIP2 = 1, PH_CLIP3 = 2, PH_DONE = 3 };
+    enum { PH_CLIP1 = 0, PH_CLIP2 = 1, PH_CLIP3 = 2, PH_DONE = 3, PH_NEXT = 4 };
     res.status = PS_OK; res.n_rows = 0; res.overlap_state = 0;
     int phase = valid ? PH_CLIP1 : PH_DONE;
     double force_factor = 0, overlap = 0, amin = 0;
@@ -363,10 +491,10 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             clip.ring = 1; clip.ix = RX; clip.iy = RY; clip.n = nr;
             m_now = 1;
         }
-        const int st = run_sweep(w.eng, phase != PH_DONE, m_now, subj, clip);
-        if (phase != PH_DONE && st != PS_OK) { res.status = st; phase = PH_DONE; }
+        const int st = run_sweep(w.eng, phase != PH_DONE && phase != PH_NEXT, m_now, subj, clip);
+        if (phase != PH_DONE && phase != PH_NEXT && st != PS_OK) { res.status = st; phase = PH_DONE; }
         const int ph = phase;           // the phase whose clip just ran
-        bool next_region = false;       // prepare the contact direction of region k
+        bool next_region = (phase == PH_NEXT);       // prepare the contact direction of region k
         bool finish_region = false;     // clips of region k are done: write its row
         bool advance = false;           // look at the next new region of the sign test
         SZ_LANE_SYNC();
@@ -471,21 +599,7 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
 
         // ---- the row of region k (:167-187)
         if (finish_region) {
-            const double fx = fdx * Ak * force_factor, fy = fdy * Ak * force_factor;  // :167
-            // tangential (:170-183)
-            const double v1x = f1.Ui + f1.ksi * (pcx - f1.Xi), v1y = f1.Vi + f1.ksi * (pcy - f1.Yi);
-            const double v2x = f2.Ui + f2.ksi * (pcx - f2.Xi), v2y = f2.Vi + f2.ksi * (pcy - f2.Yi);
-            const double vtx = v1x - v2x, vty = v1y - v2y;
-            const double vn = sqrt(vtx * vtx + vty * vty);
-            double dtx = 0, dty = 0;
-            if (!((fabs(vtx) > fabs(vty) ? fabs(vtx) : fabs(vty)) == 0)) { dtx = vtx / vn; dty = vty / vn; }
-            const double dotv = dtx * vtx + dty * vty;
-            const double coef = -dotv * dl * G * vn;
-            double ftx = coef * dtx * P.dt, fty = coef * dty * P.dt;
-            const double fnorm = sqrt(fx * fx + fy * fy);
-            if (sqrt(ftx * ftx + fty * fty) > mu * fnorm) { ftx = -mu * fnorm * dtx; fty = -mu * fnorm * dty; }
-            double* r = rows + (size_t)n_rows * 5;
-            r[0] = fx + ftx; r[1] = fy + fty; r[2] = pcx; r[3] = pcy; r[4] = Ak;
+            force_row(f1, f2, P, G, mu, force_factor, fdx, fdy, dl, Ak, pcx, pcy, rows + (size_t)n_rows * 5);
             ++n_rows;
             next_region = true;
         }
@@ -568,6 +682,20 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
                 if (dl < P.dl_min) { fdx = 0; fdy = 0; }                              // :141-142
                 phase = PH_CLIP2;                                                     // sign test (:151-165)
             }
+        }
+        SZ_LANE_SYNC();
+        // ---- convex pairs: the sign test decided with margin, without clips #2/#3 (else the reference's clips run)
+        bool fast_done = false;
+        if (next_region && convex_pair && !boundary && Ak != 0 && (fdx != 0 || fdy != 0)) {
+            const int dec = convex_sign_test<C>(w, fdx, fdy, RX, RY, nr, Ak, pcx, pcy);
+            if (dec != 0) { if (dec > 0) { fdx = -fdx; fdy = -fdy; } fast_done = true; }
+        }
+        SZ_LANE_SYNC();
+        if (fast_done) {
+            // the row of region k, then straight on to the next region in the next iteration
+            force_row(f1, f2, P, G, mu, force_factor, fdx, fdy, dl, Ak, pcx, pcy, rows + (size_t)n_rows * 5);
+            ++n_rows;
+            phase = PH_NEXT;
         }
     }
     if (res.status != PS_OK) { res.n_rows = 0; return; }

@@ -41,7 +41,11 @@ static int run(const SzParams* prm, const double* cax, const double* cay, int n1
     for (int i = 0; i < n1; ++i) { w->c1x[i] = cax[i] + b1.Xi; w->c1y[i] = cay[i] + b1.Yi; }
     for (int i = 0; i < n2; ++i) { w->c2x[i] = c2x[i]; w->c2y[i] = c2y[i]; }
     PairResult res; std::vector<double> rows(CAPS::ROWS * 5);
-    pair_force(*w, b1, b2, is_boundary != 0, P, res, rows.data());
+    // convexity of both outlines in Clipper's coordinates, as the device computes it per floe (ext_prep_kernel)
+    struct G { const double* x; const double* y; P64 operator()(int i) const { P64 p; p.x = matlab_int64(x[i] * SZ_SCALE); p.y = matlab_int64(y[i] * SZ_SCALE); return p; } };
+    auto open_n = [](const double* x, const double* y, int n) { while (n > 1 && x[n - 1] == x[0] && y[n - 1] == y[0]) --n; return n; };
+    const bool convex = !is_boundary && ring_is_strictly_convex(G{w->c1x, w->c1y}, open_n(w->c1x, w->c1y, n1)) && ring_is_strictly_convex(G{w->c2x, w->c2y}, open_n(w->c2x, w->c2y, n2));
+    pair_force(*w, b1, b2, is_boundary != 0, P, res, rows.data(), true, convex);
     if (res.status != PS_OK) return res.status;
     *overlap_state = res.overlap_state;
     if (res.n_rows > rows_cap) return -2;
