@@ -35,6 +35,17 @@ def test_periodic_voronoi_field(ctx, n, seed):
     assert rep["pairs"] > 4 * n and rep["rows"] > 0
 
 
+@pytest.mark.parametrize("inflate,seed", [(0.0003, 41), (0.002, 42), (0.1, 43), (0.35, 44)])
+def test_shortcuts_thin_and_deep_overlaps(ctx, inflate, seed):
+    """margin-certified shortcuts vs the oracle's full evaluation: 0.5 m strips (the 1 m nudge can empty the re-clip)
+    up to deep overlaps with merges (kill/transfer)"""
+    prm, soa = sz.voronoi_field(6000, seed=seed, inflate=inflate)
+    rep, ref = run_both(ctx, prm, soa, broad_mode=1)
+    assert rep["pairs"] > 20000
+    if inflate >= 0.35:
+        assert (ref.floe_outputs()["kill"] > 0).sum() > 0
+
+
 def test_uninflated_voronoi_shared_edges_give_no_polygons(ctx):
     """exactly shared edges: every Clipper intersection must come back empty, as in the reference"""
     prm, soa = sz.voronoi_field(3000, seed=4, inflate=0.0)

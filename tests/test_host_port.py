@@ -86,6 +86,26 @@ def test_pair_force_voronoi_pairs_small_and_big_class(port):
     assert n_force > 300
 
 
+@pytest.mark.parametrize("inflate,seed", [(0.0003, 31), (0.002, 32), (0.1, 33), (0.35, 34)])
+def test_pair_force_convex_shortcuts_thin_and_deep_overlaps(port, inflate, seed):
+    """the margin-certified shortcuts (bounding-box early-out, clip #3 certificate, convex sign test) against the
+    oracle's full three-clip evaluation: overlap strips from 0.5 m (thinner than the 1 m nudge, so the re-clip can
+    vanish) to deep overlaps with merges; rows must stay bit-identical"""
+    prm, soa = sz.voronoi_field(900, seed=seed, inflate=inflate)
+    ref = oracle.OracleStep(prm, soa, broad_mode=1)
+    pr = ref.pairs()
+    n_force = n_inf = 0
+    for k in range(0, len(pr["i"]), 2):
+        i, j = pr["i"][k] - 1, pr["j"][k] - 1
+        if i >= soa.n or j >= soa.n:
+            continue
+        o, p = both(port, prm, floe_dict(soa, i), floe_dict(soa, j), False, None, 1)
+        assert_same(o, p, "inflate %g pair %d-%d" % (inflate, i, j))
+        n_force += o[0] > 0
+        n_inf += np.isinf(o[2])
+    assert n_force + n_inf > 100
+
+
 def test_pair_force_real_concave_shapes(port):
     """FloeShapes.mat polygons (7..591 vertices) placed to overlap: multi-region contacts, the general (m != 2) branch,
     merge (+-Inf) outcomes"""
