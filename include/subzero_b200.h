@@ -142,6 +142,9 @@ typedef struct SzExtendedList {
     const int32_t* parent;     /* images: 1-based LOCAL index of the parent entry when it is owned here, else 0 */
 } SzExtendedList;
 int sz_upload_extended(SzContext* ctx, const SzParams* prm, const SzFloesSoA* entries, const SzBoundary* bnd, const SzExtendedList* ext);
+/* between topology changes only the motion state of the entries changes: refresh it in place ([n] each, NULL = keep) */
+int sz_update_extended_state(SzContext* ctx, const double* x, const double* y, const double* u, const double* v, const double* ksi,
+                             const double* root_x, const double* root_y);
 
 /* ---- results of the last step (caller-allocated; sizes from SzSummary) ---- */
 /* per floe of the input list, each [n0] unless noted; any pointer may be NULL to skip */

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "sz_contact_step": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzSummary)]),
     "sz_upload": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary)]),
     "sz_upload_extended": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzExtendedList)]),
+    "sz_update_extended_state": (C.c_int, [C.c_void_p] + [c_dp] * 7),
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
     "sz_get_floe_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),

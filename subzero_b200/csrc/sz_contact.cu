@@ -810,6 +810,26 @@ extern "C" int sz_upload_extended(SzContext* c, const SzParams* prm, const SzFlo
     return SZ_OK;
 }
 
+extern "C" int sz_update_extended_state(SzContext* c, const double* x, const double* y, const double* u, const double* v, const double* ksi,
+                                        const double* root_x, const double* root_y)
+{
+    if (!c) { sz_set_error("sz_update_extended_state: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_input || !c->ext_mode) { sz_set_error("sz_update_extended_state: no extended list uploaded"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->n0 * 8; cudaStream_t st = c->stream;
+    if (b) {
+        if (x) CK(cudaMemcpyAsync(c->x.p, x, b, cudaMemcpyDefault, st));
+        if (y) CK(cudaMemcpyAsync(c->y.p, y, b, cudaMemcpyDefault, st));
+        if (u) CK(cudaMemcpyAsync(c->u.p, u, b, cudaMemcpyDefault, st));
+        if (v) CK(cudaMemcpyAsync(c->v.p, v, b, cudaMemcpyDefault, st));
+        if (ksi) CK(cudaMemcpyAsync(c->ksi.p, ksi, b, cudaMemcpyDefault, st));
+        if (root_x) CK(cudaMemcpyAsync(c->erootx.p, root_x, b, cudaMemcpyDefault, st));
+        if (root_y) CK(cudaMemcpyAsync(c->erooty.p, root_y, b, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return SZ_OK;
+}
+
 static int read_counters(SzContext* c)
 {
     CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDefault, c->stream));

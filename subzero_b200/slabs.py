@@ -163,14 +163,17 @@ class LocalList:
     n_ext_global: int
     halo_sent: int
     halo_bytes: int
+    plan: dict = None        # what refresh_local_state needs to move only the motion state on later steps
 
 
 def _sgn(t):
     return (t > 0).to(F64) - (t < 0).to(F64)
 
 
-def build_local_list(st, Lx, Ly, periodic, reach, comm):
-    """Steps 1 and 2 of the module docstring.  `reach` = 2 * max(rmax) over all ranks."""
+def build_local_list(st, Lx, Ly, periodic, reach, comm, skin=0.0):
+    """Steps 1 and 2 of the module docstring.  `reach` = 2 * max(rmax) over all ranks; `skin` widens the halo so that the
+    list stays valid while no floe has moved more than skin / 2 (refresh_local_state)."""
+    reach = reach + skin
     dev = st.x.device
     n = st.n
     ar = torch.arange(n, device=dev)
@@ -180,6 +183,7 @@ def build_local_list(st, Lx, Ly, periodic, reach, comm):
         # x pass over the originals (:28-39): max_v |c_alpha(1,v) + Xi| > Lx; fl(v + X) is monotone in v, so the maximum
         # over the vertices is attained at an extreme of the outline
         fx = alive & (torch.maximum((maxvx + st.x).abs(), (minvx + st.x).abs()) > Lx)
+        fy = None
         xg_par = fx.nonzero().squeeze(1)
         xg_x, xg_y = st.x[xg_par] - 2 * Lx * _sgn(st.x[xg_par]), st.y[xg_par]
         # y pass over originals + x-ghosts (:49-60)
@@ -190,6 +194,7 @@ def build_local_list(st, Lx, Ly, periodic, reach, comm):
         yg_x, yg_y = x_all[yg_par], y_all[yg_par] - 2 * Ly * _sgn(y_all[yg_par])
     else:
         xg_par = yg_par = torch.zeros(0, dtype=I64, device=dev)
+        fx = fy = None
         xg_x = xg_y = yg_x = yg_y = torch.zeros(0, dtype=F64, device=dev)
         src_all = ar
     cx, cy = xg_par.shape[0], yg_par.shape[0]
@@ -271,7 +276,45 @@ def build_local_list(st, Lx, Ly, periodic, reach, comm):
         body=body, alive=torch.cat([st.alive[src], rstate[:, 12].to(torch.uint8)])[order],
         owned=torch.cat([torch.ones(n_own, dtype=torch.uint8, device=dev), torch.zeros(nh, dtype=torch.uint8, device=dev)])[order],
         parent=parent[order], voff=voff, vx=pool_x[gidx], vy=pool_y[gidx], n_ext_global=n_ext,
-        halo_sent=int(sidx.shape[0]), halo_bytes=int(state.numel() * 8 + sverts.numel() * 8))
+        halo_sent=int(sidx.shape[0]), halo_bytes=int(state.numel() * 8 + sverts.numel() * 8),
+        plan=dict(xg_par=xg_par, yg_par=yg_par, src=src, src_all=src_all, fx=fx, fy=fy, sidx=sidx, ssrc=ssrc, send_counts=send_counts, recv_counts=recv_counts,
+                  order=order, n_own=n_own, x0=st.x.clone(), y0=st.y.clone(), skin=skin))
+
+
+def refresh_local_state(st, Lx, Ly, periodic, plan, comm):
+    """Later steps of an unchanged topology: only the motion state (centroids, velocities) moves.  Recomputes the image
+    centroids of the planned images, checks that the plan still holds -- same floes poke through the periodic boundary
+    (the image set is exact every step) and no floe has moved more than skin / 2 (the planned halo still covers every
+    candidate pair) -- and exchanges 7 doubles per halo entry.  Returns (valid, state [7, n_local]) with rows
+    x y u v ksi root_x root_y in local (ascending gid) order; valid is agreed by all ranks."""
+    dev = st.x.device
+    n = st.n
+    bad = torch.zeros((), dtype=F64, device=dev)
+    if periodic:
+        minvx, maxvx, minvy, maxvy = st.ext
+        alive = st.alive != 0
+        fx = alive & (torch.maximum((maxvx + st.x).abs(), (minvx + st.x).abs()) > Lx)
+        xg_par = plan["xg_par"]
+        xg_x, xg_y = st.x[xg_par] - 2 * Lx * _sgn(st.x[xg_par]), st.y[xg_par]
+        src_all = plan["src_all"]
+        x_all, y_all = torch.cat([st.x, xg_x]), torch.cat([st.y, xg_y])
+        fy = alive[src_all] & (torch.maximum((maxvy[src_all] + y_all).abs(), (minvy[src_all] + y_all).abs()) > Ly)
+        yg_par = plan["yg_par"]
+        yg_x, yg_y = x_all[yg_par], y_all[yg_par] - 2 * Ly * _sgn(y_all[yg_par])
+        bad = bad + (fx != plan["fx"]).any().to(F64) + (fy != plan["fy"]).any().to(F64)
+        ox, oy = torch.cat([x_all, yg_x]), torch.cat([y_all, yg_y])
+    else:
+        ox, oy = st.x, st.y
+    moved = torch.maximum((st.x - plan["x0"]).abs().max(), (st.y - plan["y0"]).abs().max()) if n else bad
+    bad = bad + (~(moved <= 0.5 * plan["skin"])).to(F64)          # NaN counts as moved
+    src = plan["src"]
+    own = torch.stack([ox, oy, st.u[src], st.v[src], st.ksi[src], st.x[src], st.y[src]], 1)       # [n_own, 7]
+    if comm.world > 1:
+        bad = comm.all_gather(bad.reshape(1)).sum()
+    if float(bad) != 0.0:
+        return False, None
+    recv = comm.exchange(own[plan["sidx"]], plan["send_counts"], plan["recv_counts"])
+    return True, torch.cat([own, recv])[plan["order"]].t().contiguous()
 
 
 def fix_kill_transfer(gid, floe_num, owned, kill_i, transfer_i, id0, n_own, comm):
@@ -304,17 +347,36 @@ def fix_kill_transfer(gid, floe_num, owned, kill_i, transfer_i, id0, n_own, comm
 class SlabStep:
     """one rank's contact step over its slab: halo exchange + local GPU step + extraction of its floes' results"""
 
-    def __init__(self, prm, st, comm, ctx):
+    def __init__(self, prm, st, comm, ctx, skin=None):
         self.prm, self.st, self.comm, self.ctx = prm, st, comm, ctx
+        self.plans = self.fast_steps = 0
         rm = st.rmax.max() if st.n else torch.zeros((), dtype=F64, device=st.x.device)
         self.reach = 2.0 * float(comm.all_gather(rm.reshape(1).to(F64)).max())
+        self.skin = 0.05 * self.reach if skin is None else float(skin)      # halo skin: the plan survives moves < skin / 2
         self.local = None
         self.summary = None
 
+    def invalidate(self):
+        """call when floes were created, destroyed or reshaped (the outlines and the alive flags are part of the plan)"""
+        self.local = None
+
     def run(self):
+        """one contact step.  The first call (and every call after the plan went stale) builds the local list and
+        uploads it; the others move only the motion state: 7 doubles per entry, one small all-gather, one exchange."""
         st, prm = self.st, self.prm
-        L = build_local_list(st, prm.Lx, prm.Ly, bool(prm.periodic), self.reach, self.comm)
+        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
+        if self.local is not None and self.skin > 0:
+            ok, dyn = refresh_local_state(st, prm.Lx, prm.Ly, bool(prm.periodic), self.local.plan, self.comm)
+            if ok:
+                if dyn.is_cuda:
+                    torch.cuda.current_stream().synchronize()
+                abi.check(abi.lib().sz_update_extended_state(self.ctx._h, *(P(dyn[k], abi.c_dp) for k in range(7))))
+                self.fast_steps += 1
+                self.summary = self.ctx.step_resident()
+                return self.summary
+        L = build_local_list(st, prm.Lx, prm.Ly, bool(prm.periodic), self.reach, self.comm, self.skin)
         self.local = L
+        self.plans += 1
         n = L.gid.shape[0]
         i32 = lambda t: t.to(torch.int32).contiguous()
         keep = [L.x.contiguous(), L.y.contiguous()] + [L.body[:, k].contiguous() for k in range(6)] + [L.alive.contiguous(), i32(L.voff), L.vx.contiguous(), L.vy.contiguous(),
@@ -322,7 +384,6 @@ class SlabStep:
         x, y, rmax, h, area, u, v, ksi, alive, voff, vx, vy, gid1, fnum, rx, ry, owned, parent = keep
         fs = abi.SzFloesSoA()
         fs.n, fs.nverts = n, vx.shape[0]
-        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
         for nm, t in (("x", x), ("y", y), ("rmax", rmax), ("h", h), ("area", area), ("u", u), ("v", v), ("ksi", ksi), ("vx", vx), ("vy", vy)):
             setattr(fs, nm, P(t, abi.c_dp))
         fs.alive, fs.voff = P(alive, abi.c_bp), P(voff, abi.c_ip)
