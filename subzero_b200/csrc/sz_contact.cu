@@ -448,7 +448,8 @@ __global__ void bins_scan_kernel(Counters* c, int np)
 {
     if (threadIdx.x == 0) {
         int run = 0;
-        for (int k = 0; k < 64; ++k) { const int v = c->bins[k]; c->bins[k] = run; run += v; c->bin_fill[k] = 0; }
+        // largest outlines first: the CTAs with the longest sweeps start first, which shortens the tail of the launch
+        for (int k = 63; k >= 0; --k) { const int v = c->bins[k]; c->bins[k] = run; run += v; c->bin_fill[k] = 0; }
         c->listS = run; c->n_bbox_reject = np - run;
     }
 }

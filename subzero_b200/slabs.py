@@ -396,22 +396,20 @@ class SlabStep:
         return self.summary
 
     def results(self):
-        """per-floe outputs and contact rows of this rank's original floes, in global id order"""
+        """per-floe outputs and contact rows of this rank's original floes, in global id order (they are one contiguous
+        run of the local list: lower ranks' originals sort before it, higher ranks' and every image after it)"""
         L, ctx = self.local, self.ctx
         o = ctx.floe_outputs()
         off, rows = ctx.rows()
-        mine = ((L.owned != 0) & (L.floe_num > 0)).cpu().numpy()
-        out = {k: v[mine] for k, v in o.items()}
+        first = int(torch.searchsorted(L.gid, self.st.id0))
+        last = first + self.st.n
+        out = {k: v[first:last] for k, v in o.items()}
         dev = L.gid.device
         kill, transfer = fix_kill_transfer(L.gid, L.floe_num, L.owned, torch.as_tensor(o["kill"], dtype=I64).to(dev), torch.as_tensor(o["transfer"], dtype=I64).to(dev),
                                            self.st.id0, self.st.n, self.comm)
         out["kill"], out["transfer"] = kill.cpu().numpy().astype(np.int32), transfer.cpu().numpy().astype(np.int32)
-        idx = np.flatnonzero(mine)
-        cnt = off[idx + 1] - off[idx]
-        row_off = np.zeros(idx.shape[0] + 1, np.int64)
-        np.cumsum(cnt, out=row_off[1:])
-        sel = np.repeat(off[idx] - row_off[:-1], cnt) + np.arange(int(row_off[-1]))
-        return out, row_off, rows[sel]
+        row_off = off[first:last + 1] - off[first]
+        return out, row_off, rows[off[first]:off[last]]
 
 
 class SlabJob:
