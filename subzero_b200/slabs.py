@@ -78,6 +78,14 @@ class Comm:
         self.dist.all_gather(out, src.contiguous())
         return torch.stack(out).to(t.device)
 
+    def all_max(self, t):
+        """elementwise maximum over the ranks (one all-reduce)"""
+        if self.world == 1:
+            return t
+        src = t.cpu() if self.stage else t.clone()
+        self.dist.all_reduce(src, op=self.dist.ReduceOp.MAX)
+        return src.to(t.device)
+
     def exchange(self, send, send_counts, recv_counts):
         """variable all-to-all of rows: send [sum(send_counts), k] grouped by destination -> [sum(recv_counts), k]"""
         k = send.shape[1:]
@@ -309,9 +317,7 @@ def refresh_local_state(st, Lx, Ly, periodic, plan, comm):
     bad = bad + (~(moved <= 0.5 * plan["skin"])).to(F64)          # NaN counts as moved
     src = plan["src"]
     own = torch.stack([ox, oy, st.u[src], st.v[src], st.ksi[src], st.x[src], st.y[src]], 1)       # [n_own, 7]
-    if comm.world > 1:
-        bad = comm.all_gather(bad.reshape(1)).sum()
-    if float(bad) != 0.0:
+    if float(comm.all_max(bad.reshape(1))) != 0.0:
         return False, None
     recv = comm.exchange(own[plan["sidx"]], plan["send_counts"], plan["recv_counts"])
     return True, torch.cat([own, recv])[plan["order"]].t().contiguous()

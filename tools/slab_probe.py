@@ -12,14 +12,15 @@ job = slabs.SlabJob(n, 0, rank, world, local, dist)
 step = job.step
 def sync():
     torch.cuda.synchronize()
-for it in range(5):
+step.run()
+for it in range(6):
     dist.barrier(); sync(); t0 = time.perf_counter()
-    L = slabs.build_local_list(step.st, step.prm.Lx, step.prm.Ly, True, step.reach, step.comm)
+    ok, dyn = slabs.refresh_local_state(step.st, step.prm.Lx, step.prm.Ly, True, step.local.plan, step.comm)
     sync(); t1 = time.perf_counter()
     s = step.run()
     sync(); t2 = time.perf_counter()
     ph = job.ctx.phase_ms()
-    if it >= 2:
-        print("rank %d it %d list %.2f ms | run(total incl. list) %.2f ms | lib step %.2f (narrow %.2f broad %.2f asm %.2f) | local n %d owned pairs %d all pairs %d halo sent %d (%.1f MB)" % (
-            rank, it, 1e3 * (t1 - t0), 1e3 * (t2 - t1), s.ms_device, ph["narrow"], ph["broad"], ph["assembly"], s.n, s.n_pairs_owned, s.n_pairs, L.halo_sent, L.halo_bytes / 1e6), flush=True)
+    if it >= 3:
+        print("rank %d it %d refresh %.3f ms | run %.3f ms | lib step %.3f (narrow %.3f broad %.3f asm %.3f ghosts %.3f) | local n %d owned pairs %d all pairs %d" % (
+            rank, it, 1e3 * (t1 - t0), 1e3 * (t2 - t1), s.ms_device, ph["narrow"], ph["broad"], ph["assembly"], ph["ghosts"], s.n, s.n_pairs_owned, s.n_pairs), flush=True)
 dist.barrier(); dist.destroy_process_group()
