@@ -360,6 +360,7 @@ class SlabStep:
         self.reach = 2.0 * float(comm.all_gather(rm.reshape(1).to(F64)).max())
         self.skin = 0.05 * self.reach if skin is None else float(skin)      # halo skin: the plan survives moves < skin / 2
         self.local = None
+        self._first = None
         self.summary = None
 
     def invalidate(self):
@@ -382,6 +383,7 @@ class SlabStep:
                 return self.summary
         L = build_local_list(st, prm.Lx, prm.Ly, bool(prm.periodic), self.reach, self.comm, self.skin)
         self.local = L
+        self._first = None
         self.plans += 1
         n = L.gid.shape[0]
         i32 = lambda t: t.to(torch.int32).contiguous()
@@ -401,17 +403,33 @@ class SlabStep:
         self.summary = self.ctx.step_resident()
         return self.summary
 
-    def results(self):
+    def results(self, pinned=None):
         """per-floe outputs and contact rows of this rank's original floes, in global id order (they are one contiguous
-        run of the local list: lower ranks' originals sort before it, higher ranks' and every image after it)"""
+        run of the local list: lower ranks' originals sort before it, higher ranks' and every image after it).
+        `pinned`: optional dict that caches page-locked receive buffers between calls."""
         L, ctx = self.local, self.ctx
-        o = ctx.floe_outputs()
-        off, rows = ctx.rows()
-        first = int(torch.searchsorted(L.gid, self.st.id0))
+        n_loc, n_rows = int(L.gid.shape[0]), int(self.summary.n_rows)
+        if pinned is not None:
+            if pinned.get("n") != n_loc:
+                z = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+                pinned.update(n=n_loc, out={"fx": z(n_loc, F64), "fy": z(n_loc, F64), "torque": z(n_loc, F64), "overlap_area": z(n_loc, F64), "stress": z((n_loc, 2, 2), F64),
+                                            "xi": z(n_loc, F64), "yi": z(n_loc, F64), "alive": z(n_loc, torch.uint8), "kill": z(n_loc, torch.int32), "transfer": z(n_loc, torch.int32)},
+                              off=z(n_loc + 1, I64), rows=None)
+            if pinned["rows"] is None or pinned["rows"].shape[0] < n_rows:
+                pinned["rows"] = torch.empty((int(n_rows * 1.1) + 16, 7), dtype=F64).pin_memory().numpy()
+            o = ctx.floe_outputs(into=pinned["out"])
+            off, rows = pinned["off"], pinned["rows"]
+            abi.check(abi.lib().sz_get_rows(ctx._h, abi._ptr(off, abi.c_lp), abi._ptr(rows, abi.c_dp)))
+        else:
+            o = ctx.floe_outputs()
+            off, rows = ctx.rows()
+        if self._first is None:
+            self._first = int(torch.searchsorted(L.gid, self.st.id0))
+        first = self._first
         last = first + self.st.n
         out = {k: v[first:last] for k, v in o.items()}
         dev = L.gid.device
-        kill, transfer = fix_kill_transfer(L.gid, L.floe_num, L.owned, torch.as_tensor(o["kill"], dtype=I64).to(dev), torch.as_tensor(o["transfer"], dtype=I64).to(dev),
+        kill, transfer = fix_kill_transfer(L.gid, L.floe_num, L.owned, torch.from_numpy(o["kill"]).to(dev).to(I64), torch.from_numpy(o["transfer"]).to(dev).to(I64),
                                            self.st.id0, self.st.n, self.comm)
         out["kill"], out["transfer"] = kill.cpu().numpy().astype(np.int32), transfer.cpu().numpy().astype(np.int32)
         row_off = off[first:last + 1] - off[first]
@@ -491,7 +509,9 @@ class SlabJob:
             st.alive, st.voff, st.vx, st.vy = up(f.alive, torch.uint8), up(f.voff, I64), up(f.vx, F64), up(f.vy, F64)
             st.update_outline_extents()
             s = self.step.run()
-            out, row_off, rows = self.step.results()
+            if self._out is None:
+                self._out = {}
+            out, row_off, rows = self.step.results(pinned=self._out)
             d2h = sum(v.nbytes for v in out.values()) + row_off.nbytes + rows.nbytes
         self.summary = s
         return h2d, d2h
