@@ -21,6 +21,7 @@
 #include "sz_narrow.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
@@ -877,22 +878,34 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     a.list = nullptr; a.list_count = nullptr;
     CK(cudaGetLastError());
     CKS(read_counters(c));
+    static const bool dbg = getenv("SZ_DEBUG_TIMING") != nullptr;
+    cudaEvent_t d0, d1; float dms = 0;
+    if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); }
     int nM = wall ? c->h_cnt->wlistM : c->h_cnt->listM;
+    if (dbg) fprintf(stderr, "[sz] class S done: %d -> M\n", nM);
     if (nM > 0) {
-        const int threads = std::min((nM + 63) / 64 * 64, 148 * 64);
+        static const int m_tpsm = getenv("SZ_M_TPSM") ? atoi(getenv("SZ_M_TPSM")) : 512;   // persistent threads per SM of class M (160 KB of HBM scratch each)
+        const int threads = std::min((nM + 63) / 64 * 64, 148 * m_tpsm);
         CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
         a.list = lstM; a.list_count = cntM; a.next_list = lstL; a.next_count = cntL; a.scratch = c->scratchM.p; a.n_threads = threads;
+        if (dbg) cudaEventRecord(d0, st);
         ++g_launches; sz_launch_narrow_M(&a, st);
         CK(cudaGetLastError());
+        if (dbg) cudaEventRecord(d1, st);
         CKS(read_counters(c));
+        if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class M: %d pairs on %d threads, %.2f ms\n", nM, threads, dms); }
         int nL = wall ? c->h_cnt->wlistL : c->h_cnt->listL;
         if (nL > 0) {
-            const int threadsL = std::min((nL + 63) / 64 * 64, 148 * 8);
+            static const int l_tpsm = getenv("SZ_L_TPSM") ? atoi(getenv("SZ_L_TPSM")) : 32;    // class L (1.1 MB each)
+            const int threadsL = std::min((nL + 63) / 64 * 64, 148 * l_tpsm);
             CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
             a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
+            if (dbg) cudaEventRecord(d0, st);
             ++g_launches; sz_launch_narrow_L(&a, st);
             CK(cudaGetLastError());
+            if (dbg) cudaEventRecord(d1, st);
             CKS(read_counters(c));
+            if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class L: %d pairs on %d threads, %.2f ms\n", nL, threadsL, dms); }
         }
     }
     return SZ_OK;
@@ -1234,14 +1247,14 @@ extern "C" int sz_clip_batch(SzContext* c, int32_t count, const int32_t* method,
         CK(cudaGetLastError());
         CKS(read_counters(c));
         if (c->h_cnt->clip_listM > 0) {
-            const int threads = std::min((c->h_cnt->clip_listM + 63) / 64 * 64, 148 * 64);
+            const int threads = std::min((c->h_cnt->clip_listM + 63) / 64 * 64, 148 * 512);
             CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
             a.list = c->c_listM.p; a.list_count = D_CNT(clip_listM); a.next_list = c->c_listL.p; a.next_count = D_CNT(clip_listL); a.scratch = c->scratchM.p; a.n_threads = threads;
             ++g_launches; sz_launch_clip_M(&a, st);
             CK(cudaGetLastError());
             CKS(read_counters(c));
             if (c->h_cnt->clip_listL > 0) {
-                const int threadsL = std::min((c->h_cnt->clip_listL + 63) / 64 * 64, 148 * 8);
+                const int threadsL = std::min((c->h_cnt->clip_listL + 63) / 64 * 64, 148 * 32);
                 CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
                 a.list = c->c_listL.p; a.list_count = D_CNT(clip_listL); a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
                 ++g_launches; sz_launch_clip_L(&a, st);
