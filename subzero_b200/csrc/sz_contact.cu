@@ -72,7 +72,7 @@ struct Counters {
     int n1, n;                     // extended-list sizes after the x pass / after the y pass
     int n_pairs;
     int row_used, path_used, vert_used;
-    int listS, listM, listL, wlistM, wlistL;
+    int listS, listT, listM, listL, wlistT, wlistM, wlistL;
     int bins[64], bin_fill[64];    // class-S work list: pairs bucketed by vertex count
     int total_rows;
     int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject;
@@ -107,7 +107,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listS, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex;
+    DBuf<int> listS, listT, wlistT, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -702,7 +702,7 @@ extern "C" void sz_destroy(SzContext* c)
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
-                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->listS, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
+                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
@@ -851,19 +851,19 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     a.pi = c->pi.p; a.pj = c->pj.p; a.n_work = n_work;
     a.row_pool = c->row_pool.p; a.row_cap = (int)std::min<size_t>(c->row_pool.cap / 5, 0x7fffffff); a.row_used = D_CNT(row_used);
     a.P = c->dprm;
-    int* cntM; int* cntL; int* lstM; int* lstL;
+    int* cntT; int* lstT; int* cntM; int* cntL; int* lstM; int* lstL;
     if (wall) {
         a.wall = 1; a.first_floe = 0; a.egid = c->egid.p; a.eowned = c->eowned.p; a.bx = c->bx.p; a.by = c->by.p; a.bn = c->bn; a.bbody = c->bbody;
         a.status = c->wstatus.p; a.nrows = c->wnrows.p; a.row_start = c->wrow_start.p; a.ovl_state = c->wovl.p;
-        cntM = D_CNT(wlistM); cntL = D_CNT(wlistL); lstM = c->wlistM.p; lstL = c->wlistL.p;
+        cntT = D_CNT(wlistT); lstT = c->wlistT.p; cntM = D_CNT(wlistM); cntL = D_CNT(wlistL); lstM = c->wlistM.p; lstL = c->wlistL.p;
     } else {
         a.status = c->pstatus.p; a.nrows = c->pnrows.p; a.row_start = c->prow_start.p; a.ovl_state = c->povl.p;
         a.want_polys = c->prm.want_clip_polys;
         a.poly_path_start = c->poly_path_start.p; a.poly_npaths = c->poly_npaths.p; a.path_vstart = c->path_vstart.p; a.path_len = c->path_len.p;
         a.path_cap = (int)c->path_vstart.cap; a.path_used = D_CNT(path_used); a.pvx = c->pvx.p; a.pvy = c->pvy.p; a.vert_cap = (int)c->pvx.cap; a.vert_used = D_CNT(vert_used);
-        cntM = D_CNT(listM); cntL = D_CNT(listL); lstM = c->listM.p; lstL = c->listL.p;
+        cntT = D_CNT(listT); lstT = c->listT.p; cntM = D_CNT(listM); cntL = D_CNT(listL); lstM = c->listM.p; lstL = c->listL.p;
     }
-    a.next_list = lstM; a.next_count = cntM;
+    a.next_list = lstT; a.next_count = cntT;
     if (!wall) {
         // work list of class S: bounding-box-disjoint pairs answered, the rest bucketed by vertex count
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->prm.want_clip_polys,
@@ -878,11 +878,20 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     a.list = nullptr; a.list_count = nullptr;
     CK(cudaGetLastError());
     CKS(read_counters(c));
+    const int nT = wall ? c->h_cnt->wlistT : c->h_cnt->listT;
+    if (nT > 0) {
+        // class T: pairs that did not fit class S, arena still in local memory
+        a.list = lstT; a.list_count = cntT; a.n_work = nT; a.next_list = lstM; a.next_count = cntM;
+        ++g_launches; sz_launch_narrow_T(&a, st);
+        a.list = nullptr; a.list_count = nullptr;
+        CK(cudaGetLastError());
+        CKS(read_counters(c));
+    }
     static const bool dbg = getenv("SZ_DEBUG_TIMING") != nullptr;
     cudaEvent_t d0, d1; float dms = 0;
     if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); }
     int nM = wall ? c->h_cnt->wlistM : c->h_cnt->listM;
-    if (dbg) fprintf(stderr, "[sz] class S done: %d -> M\n", nM);
+    if (dbg) fprintf(stderr, "[sz] class S -> T %d, T -> M %d\n", nT, nM);
     if (nM > 0) {
         static const int m_tpsm = getenv("SZ_M_TPSM") ? atoi(getenv("SZ_M_TPSM")) : 512;   // persistent threads per SM of class M (160 KB of HBM scratch each)
         const int threads = std::min((nM + 63) / 64 * 64, 148 * m_tpsm);
@@ -1007,7 +1016,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     CKS(read_counters(c));
     const int np = c->h_cnt->n_pairs; c->n_pairs = np;
     CK(c->pi.ensure(np + 1)); CK(c->pj.ensure(np + 1)); CK(c->pstatus.ensure(np + 1)); CK(c->pnrows.ensure(np + 1)); CK(c->prow_start.ensure(np + 1)); CK(c->povl.ensure(np + 1));
-    CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
+    CK(c->listT.ensure(np + 1)); CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
@@ -1015,7 +1024,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p); }
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
-    if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }
+    if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistT.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }
     CK(c->row_pool.ensure(5 * ((size_t)np + (wall ? n : 0) + 256)));
     if (P.want_clip_polys) {
         CK(c->poly_path_start.ensure(np + 1)); CK(c->poly_npaths.ensure(np + 1));
@@ -1023,7 +1032,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     }
     for (int attempt = 0; attempt < 3; ++attempt) {
         Counters z = *c->h_cnt;
-        z.row_used = z.path_used = z.vert_used = z.listS = z.listM = z.listL = z.wlistM = z.wlistL = 0;
+        z.row_used = z.path_used = z.vert_used = z.listS = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
         memset(z.bins, 0, sizeof(z.bins)); memset(z.bin_fill, 0, sizeof(z.bin_fill));
         *c->h_cnt = z;
         CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));

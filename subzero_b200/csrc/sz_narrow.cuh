@@ -8,6 +8,7 @@
 //   class S  <= 19 vertices per outline     arena in per-thread local memory (interleaved by the
 //            (packed Voronoi: 3..13)        hardware, so lanes running the same sweep step touch
 //                                           the same sectors), one thread per pair, grid = all pairs
+//   class T  <= 47 vertices                 the same with a 35 KB arena (simplified real floes, concave)
 //   class M  <= 191 vertices                arena in an HBM scratch slab, persistent threads that
 //   class L  <= 1299 vertices               stride over the work list
 // Each class is instantiated in its own translation unit (sz_narrow_{S,M,L}.cu) so the three
@@ -25,6 +26,8 @@ using szclip::P64;
 
 typedef szclip::ClipCaps<40, 20, 112, 32, 64, 32, 16, 64> ClipS;
 typedef szpf::PairCaps<ClipS, 20, 64, 6, 40, 4> PairS;
+typedef szclip::ClipCaps<96, 48, 320, 64, 192, 64, 32, 144> ClipT;      // class T ("thirty"): simplified real floes
+typedef szpf::PairCaps<ClipT, 48, 192, 8, 128, 8> PairT;
 typedef szclip::ClipCaps<384, 192, 1536, 256, 1536, 256, 128, 576> ClipM;
 typedef szpf::PairCaps<ClipM, 192, 768, 16, 512, 16> PairM;
 typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3900> ClipL;
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(64) clip_scratch_kernel(const ClipArgs a)
 // launchers (one translation unit per class); all asynchronous on `stream`
 extern "C" {
 void sz_launch_narrow_S(const sznarrow::NarrowArgs* a, cudaStream_t stream);
+void sz_launch_narrow_T(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_M(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_L(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_clip_S(const sznarrow::ClipArgs* a, cudaStream_t stream);

@@ -69,7 +69,7 @@ def advance(Floe, t):
     return out
 
 
-def real_shape_field(n_side, seed=0, spacing=0.8, periodic=True):
+def real_shape_field(n_side, seed=0, spacing=0.8, periodic=True, max_vertices=None):
     """tile FloeShapes.mat polygons (7..591 vertices, concave) on a jittered grid so neighbours overlap"""
     polys, _, modulus = floe_shapes()
     rng = np.random.default_rng(seed)
@@ -79,6 +79,8 @@ def real_shape_field(n_side, seed=0, spacing=0.8, periodic=True):
     for a in range(n_side):
         for b in range(n_side):
             v = polys[int(rng.integers(0, len(polys)))]
+            if max_vertices is not None and len(v) > max_vertices:       # crude FloeSimplify: keep every k-th vertex
+                v = v[np.linspace(0, len(v), max_vertices, endpoint=False).astype(int)]
             area, cx, cy = polyshape_area_centroid(v)
             s = np.sqrt(5.5e7 / area)                                    # similar footprint, keeps the vertex count
             th = rng.uniform(0, 2 * np.pi)

@@ -105,6 +105,15 @@ def test_real_concave_shapes_periodic(ctx):
     assert (o["kill"] > 0).sum() > 0
 
 
+def test_simplified_concave_shapes_class_t(ctx):
+    """real shapes thinned to <= 30 vertices (what FloeSimplify leaves, Subzero.m:169-217): the local-memory class T"""
+    prm, Floe = scenarios.real_shape_field(20, seed=5, max_vertices=30)
+    soa = sz.floes_to_soa(Floe)
+    assert (soa.voff[1:] - soa.voff[:-1]).max() <= 31
+    rep, ref = run_both(ctx, prm, soa)
+    assert rep["pairs"] > 1000 and (ref.pairs()["n_regions"] > 1).sum() > 10
+
+
 def test_real_concave_shapes_with_walls(ctx):
     prm, Floe = scenarios.real_shape_field(8, seed=2, periodic=False)
     soa, bnd = scenarios.soa_and_boundary(Floe, prm, periodic=False)

@@ -4,7 +4,8 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert
 import numpy as np
 import subzero_b200 as sz, scenarios
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-t = time.time(); prm, Floe = scenarios.real_shape_field(side, seed=3); soa = sz.floes_to_soa(Floe); print("field", soa.n, "floes", soa.vx.shape[0], "vertices", round(time.time() - t, 1), "s", flush=True)
+t = time.time(); mv = int(os.environ.get('MAXV', '0')) or None
+prm, Floe = scenarios.real_shape_field(side, seed=3, max_vertices=mv); soa = sz.floes_to_soa(Floe); print("field", soa.n, "floes", soa.vx.shape[0], "vertices", round(time.time() - t, 1), "s", flush=True)
 ctx = sz.ContactContext(0); ctx.upload(prm, soa)
 for it in range(3):
     s = ctx.step_resident(allow_pair_errors=True)
