@@ -67,13 +67,15 @@ struct DBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+#define SZ_BIN_N 24                       // vertex counts 0..23 per outline get their own bucket
+#define SZ_NBINS (SZ_BIN_N * SZ_BIN_N)
 // counters living in device memory, mirrored into pinned host memory with one copy
 struct Counters {
     int n1, n;                     // extended-list sizes after the x pass / after the y pass
     int n_pairs;
     int row_used, path_used, vert_used;
     int listS, listT, listM, listL, wlistT, wlistM, wlistL;
-    int bins[64], bin_fill[64];    // class-S work list: pairs bucketed by vertex count
+    int bins[SZ_NBINS], bin_fill[SZ_NBINS];    // class-S work list: pairs bucketed by the two vertex counts
     int total_rows;
     int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject;
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
@@ -107,7 +109,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listS, listT, wlistT, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex;
+    DBuf<int> listS, listT, wlistT, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex, erot, eno;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
 // whether the outline survives Clipper's AddPath (>= 3 vertices, not all collinear: clipper.cpp:1058,1119-1123).
 __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const double* __restrict__ ey, const int* __restrict__ esrc, const int* __restrict__ voff,
                                 const double* __restrict__ vx, const double* __restrict__ vy, i64* __restrict__ ebb, uint8_t* __restrict__ evalid, int* __restrict__ env,
-                                uint8_t* __restrict__ econvex)
+                                uint8_t* __restrict__ econvex, uint8_t* __restrict__ erot, uint8_t* __restrict__ eno)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -407,7 +409,10 @@ __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const doub
                  __device__ szclip::P64 operator()(int i) const { szclip::P64 p; p.x = szpf::matlab_int64((x[o + i] + X) * SZ_SCALE); p.y = szpf::matlab_int64((y[o + i] + Y) * SZ_SCALE); return p; } };
     int no = nv;
     while (no > 1 && vx[o + no - 1] == vx[o] && vy[o + no - 1] == vy[o]) --no;
-    econvex[e] = valid && szpf::ring_is_strictly_convex(Get{vx, vy, X, Y, o}, no);
+    const bool cvx = valid && no <= 255 && szpf::ring_is_strictly_convex(Get{vx, vy, X, Y, o}, no);
+    econvex[e] = cvx;
+    eno[e] = cvx ? (uint8_t)no : 0;
+    erot[e] = cvx ? (uint8_t)szpf::ring_bottom_vertex(Get{vx, vy, X, Y, o}, no) : 0;     // start of the sweep input (PairHints)
 }
 // Pass 0 counts, pass 1 scatters.  A pair whose outlines both survive AddPath and whose integer bounding boxes are
 // strictly disjoint has an empty Clipper intersection (and cannot fail), so floe_interactions returns zero force and
@@ -418,8 +423,8 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
                                      int* __restrict__ listS, Counters* c)
 {
-    __shared__ int sh[64];
-    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __shared__ int sh[SZ_NBINS];
+    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) sh[t] = 0;
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     int key = -1, slot = 0;
@@ -430,18 +435,19 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
         if (disjoint) {
             if (pass == 0) { status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0; }
         } else {
-            key = env[i] + env[j]; key = key > 63 ? 63 : key;
+            const int ni = env[i] < SZ_BIN_N ? env[i] : SZ_BIN_N - 1, nj = env[j] < SZ_BIN_N ? env[j] : SZ_BIN_N - 1;
+            key = ni * SZ_BIN_N + nj;
             slot = atomicAdd(&sh[key], 1);
         }
     }
     __syncthreads();
     if (pass == 0) {
-        if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&c->bins[threadIdx.x], sh[threadIdx.x]);
+        for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) if (sh[t]) atomicAdd(&c->bins[t], sh[t]);
         return;
     }
     // pass 1: bins[] holds exclusive offsets; reserve this CTA's share of every bucket, then place
-    __shared__ int base[64];
-    if (threadIdx.x < 64) base[threadIdx.x] = sh[threadIdx.x] ? atomicAdd(&c->bin_fill[threadIdx.x], sh[threadIdx.x]) : 0;
+    __shared__ int base[SZ_NBINS];
+    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) base[t] = sh[t] ? atomicAdd(&c->bin_fill[t], sh[t]) : 0;
     __syncthreads();
     if (key >= 0) listS[c->bins[key] + base[key] + slot] = p;
 }
@@ -450,7 +456,11 @@ __global__ void bins_scan_kernel(Counters* c, int np)
     if (threadIdx.x == 0) {
         int run = 0;
         // largest outlines first: the CTAs with the longest sweeps start first, which shortens the tail of the launch
-        for (int k = 63; k >= 0; --k) { const int v = c->bins[k]; c->bins[k] = run; run += v; c->bin_fill[k] = 0; }
+        for (int sum = 2 * (SZ_BIN_N - 1); sum >= 0; --sum)
+            for (int ni = SZ_BIN_N - 1; ni >= 0; --ni) {
+                const int nj = sum - ni; if (nj < 0 || nj >= SZ_BIN_N) continue;
+                const int k = ni * SZ_BIN_N + nj; const int v = c->bins[k]; c->bins[k] = run; run += v; c->bin_fill[k] = 0;
+            }
         c->listS = run; c->n_bbox_reject = np - run;
     }
 }
@@ -707,7 +717,7 @@ extern "C" void sz_destroy(SzContext* c)
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
+    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
@@ -846,7 +856,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
 {
     cudaStream_t st = c->stream;
     NarrowArgs a; memset(&a, 0, sizeof(a));
-    a.ex = c->ex.p; a.ey = c->ey.p; a.esrc = c->esrc.p; a.econvex = c->econvex.p;
+    a.ex = c->ex.p; a.ey = c->ey.p; a.esrc = c->esrc.p; a.econvex = c->econvex.p; a.erot = c->erot.p; a.eno = c->eno.p;
     a.h = c->h.p; a.area = c->area.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
     a.pi = c->pi.p; a.pj = c->pj.p; a.n_work = n_work;
     a.row_pool = c->row_pool.p; a.row_cap = (int)std::min<size_t>(c->row_pool.cap / 5, 0x7fffffff); a.row_used = D_CNT(row_used);
@@ -1020,8 +1030,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
-    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1));
-    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p); }
+    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1));
+    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p); }
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
     if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistT.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }

@@ -39,7 +39,7 @@ typedef szpf::PairCaps<ClipL, 1300, 5200, 64, 6000, 32> PairL;
 // floe_interactions_all.m:33-34,54-55).
 struct NarrowArgs {
     // extended list
-    const double* ex; const double* ey; const int* esrc; const int* egid; const unsigned char* eowned; const unsigned char* econvex;
+    const double* ex; const double* ey; const int* esrc; const int* egid; const unsigned char* eowned; const unsigned char* econvex; const unsigned char* erot; const unsigned char* eno;
     // per original floe
     const double* h; const double* area; const double* u; const double* v; const double* ksi;
     const int* voff; const double* vx; const double* vy;
@@ -96,10 +96,11 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     Body b1, b2;
     b1.h = b1.area = b1.Xi = b1.Yi = b1.Ui = b1.Vi = b1.ksi = 0; b2 = b1;
     if (valid && a.wall && (a.egid[k] <= a.P.Nb || !a.eowned[k])) valid = false;     // floes below Nb take no part in the pair loop (floe_interactions_all.m:125)
-    bool escalate = false, convex = false;
+    bool escalate = false;
+    szpf::PairHints hints{false, 0, 0, 0, 0};
     if (valid) {
         if (a.wall) { i = a.first_floe + k; b2 = a.bbody; }
-        else { i = a.pi[k]; j = a.pj[k]; convex = a.econvex[i] && a.econvex[j]; }
+        else { i = a.pi[k]; j = a.pj[k]; hints.convex = a.econvex[i] && a.econvex[j]; hints.rot1 = a.erot[i]; hints.no1 = a.eno[i]; hints.rot2 = a.erot[j]; hints.no2 = a.eno[j]; }
         const int si = a.esrc[i];
         const int o1 = a.voff[si], n1 = a.voff[si + 1] - o1;
         int o2 = 0, n2 = a.bn, sj = 0;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     }
     szpf::PairResult res;
     double rows[C::ROWS * 5];
-    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid, convex);
+    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid, hints);
     if (valid && res.status == szpf::PS_CAPACITY && a.next_list) { escalate = true; valid = false; }
     if (escalate) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
     if (!valid) return;

@@ -38,6 +38,14 @@ struct Body { double h, area, Xi, Yi, Ui, Vi, ksi; };   // the fields of floe1 /
 
 enum PairStatus { PS_OK = 0, PS_CLIPPER_FAIL = -3 /* SZ_ERR_CLIPPER */, PS_CAPACITY = -4 /* SZ_ERR_CAPACITY */, PS_BAD_POLY = -1 /* SZ_ERR_ARG */ };
 
+// Per-pair hints computed once per floe (ext_prep_kernel / the host test shim).  convex: both outlines are strictly
+// convex in Clipper's coordinates.  For convex outlines the sweep is fed the OPEN ring (no1/no2 vertices, closing
+// duplicate dropped -- AddPath strips it anyway, clipper.cpp:1056) rotated to start at its bottom vertex (rot1/rot2):
+// Clipper's result does not depend on where a closed path starts (one local minimum per convex path; checked on 110k
+// convex pairs incl. shared edges and rectangles against the reference itself), and lanes that sweep pairs with the
+// same vertex counts then touch the same arena words at the same time.
+struct PairHints { bool convex; int rot1, no1, rot2, no2; };
+
 struct PairResult {
     int status;            // PairStatus
     int n_rows;            // contact rows produced (0 when the pair exerts no force)
@@ -111,9 +119,11 @@ struct ClipInput {
     const double* x; const double* y; double dx, dy;
     const i64* ix; const i64* iy;
     int n; int ring;
+    int rot;     // convex outlines are fed to the sweep starting at their bottom vertex (see PairHints); 0 = as stored
     SZ_HD P64 operator()(int i) const
     {
         P64 p;
+        if (rot) { i += rot; if (i >= n) i -= n; }
         if (ring) { p.x = matlab_int64(((double)ix[i] / SZ_SCALE) * SZ_SCALE); p.y = matlab_int64(((double)iy[i] / SZ_SCALE) * SZ_SCALE); }
         else { p.x = matlab_int64((x[i] + dx) * SZ_SCALE); p.y = matlab_int64((y[i] + dy) * SZ_SCALE); }
         return p;
@@ -233,6 +243,15 @@ SZ_HD bool ring_is_strictly_convex(const Getter& get, int n)
         a = b; b = c;
     }
     return true;
+}
+
+// index of the bottom vertex of an open ring in Clipper's sense (largest Y, then smallest X)
+template <class Getter>
+SZ_HD int ring_bottom_vertex(const Getter& get, int n)
+{
+    int best = 0; P64 b = get(0);
+    for (int i = 1; i < n; ++i) { const P64 p = get(i); if (p.y > b.y || (p.y == b.y && p.x < b.x)) { b = p; best = i; } }
+    return best;
 }
 
 // FP64 Sutherland-Hodgman clip of the convex polygon S by the convex polygon K (open rings).  Used ONLY to decide
@@ -452,11 +471,12 @@ SZ_HD void force_row(const Body& f1, const Body& f2, const Params& P, double G, 
 // After the last clip of a region its force row is written (:167-187) and the next region's contact
 // direction (:96-150) is prepared.
 template <class C>
-SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true, bool convex_pair = false)
+SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true, PairHints hints = PairHints{false, 0, 0, 0, 0})
 {
     enum { PH_CLIP1 = 0, PH_CLIP2 = 1, PH_CLIP3 = 2, PH_DONE = 3, PH_NEXT = 4 };
     res.status = PS_OK; res.n_rows = 0; res.overlap_state = 0;
     int phase = valid ? PH_CLIP1 : PH_DONE;
+    const bool convex_pair = hints.convex;
     double force_factor = 0, overlap = 0, amin = 0;
     const double G = P.modulus / (2 * (1 + P.nu)), mu = P.mu;
     const int method = boundary ? 0 : 1;
@@ -482,13 +502,14 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
         if (!SZ_WARP_ANY(phase != PH_DONE)) break;
         // ---- the clip this lane needs now
         ClipInput subj, clip;
-        subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = w.n1; subj.ring = 0;
-        clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = w.n2; clip.ring = 0;
+        subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = w.n1; subj.ring = 0; subj.rot = 0;
+        clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = w.n2; clip.ring = 0; clip.rot = 0;
+        if (convex_pair && !boundary && hints.no1 >= 3 && hints.no2 >= 3) { subj.n = hints.no1; subj.rot = hints.rot1; clip.n = hints.no2; clip.rot = hints.rot2; }
         int m_now = method;
         if (phase == PH_CLIP2) { subj.dx = fdx; subj.dy = fdy; }
         else if (phase == PH_CLIP3) {
-            subj.ring = 1; subj.ix = w.rbx + w.rb_off[ii]; subj.iy = w.rby + w.rb_off[ii]; subj.n = w.rb_off[ii + 1] - w.rb_off[ii];
-            clip.ring = 1; clip.ix = RX; clip.iy = RY; clip.n = nr;
+            subj.ring = 1; subj.ix = w.rbx + w.rb_off[ii]; subj.iy = w.rby + w.rb_off[ii]; subj.n = w.rb_off[ii + 1] - w.rb_off[ii]; subj.rot = 0;
+            clip.ring = 1; clip.ix = RX; clip.iy = RY; clip.n = nr; clip.rot = 0;
             m_now = 1;
         }
         const int st = run_sweep(w.eng, phase != PH_DONE && phase != PH_NEXT, m_now, subj, clip);

@@ -45,7 +45,12 @@ static int run(const SzParams* prm, const double* cax, const double* cay, int n1
     struct G { const double* x; const double* y; P64 operator()(int i) const { P64 p; p.x = matlab_int64(x[i] * SZ_SCALE); p.y = matlab_int64(y[i] * SZ_SCALE); return p; } };
     auto open_n = [](const double* x, const double* y, int n) { while (n > 1 && x[n - 1] == x[0] && y[n - 1] == y[0]) --n; return n; };
     const bool convex = !is_boundary && ring_is_strictly_convex(G{w->c1x, w->c1y}, open_n(w->c1x, w->c1y, n1)) && ring_is_strictly_convex(G{w->c2x, w->c2y}, open_n(w->c2x, w->c2y, n2));
-    pair_force(*w, b1, b2, is_boundary != 0, P, res, rows.data(), true, convex);
+    PairHints hints{convex, 0, 0, 0, 0};
+    if (convex) {
+        hints.no1 = open_n(w->c1x, w->c1y, n1); hints.no2 = open_n(w->c2x, w->c2y, n2);
+        hints.rot1 = ring_bottom_vertex(G{w->c1x, w->c1y}, hints.no1); hints.rot2 = ring_bottom_vertex(G{w->c2x, w->c2y}, hints.no2);
+    }
+    pair_force(*w, b1, b2, is_boundary != 0, P, res, rows.data(), true, hints);
     if (res.status != PS_OK) return res.status;
     *overlap_state = res.overlap_state;
     if (res.n_rows > rows_cap) return -2;
