@@ -67,15 +67,14 @@ struct DBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-#define SZ_BIN_N 24                       // vertex counts 0..23 per outline get their own bucket
-#define SZ_NBINS (SZ_BIN_N * SZ_BIN_N)
+#define SZ_BIN_N 16                       // vertex counts 0..15 per outline get their own bucket (larger ones share the last)
+#define SZ_NBINS (SZ_BIN_N * SZ_BIN_N * 8) // x 8 octants of the partner's direction
 // counters living in device memory, mirrored into pinned host memory with one copy
 struct Counters {
     int n1, n;                     // extended-list sizes after the x pass / after the y pass
     int n_pairs;
     int row_used, path_used, vert_used;
     int listS, listT, listM, listL, wlistT, wlistM, wlistL;
-    int bins[SZ_NBINS], bin_fill[SZ_NBINS];    // class-S work list: pairs bucketed by the two vertex counts
     int total_rows;
     int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject;
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
@@ -109,7 +108,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listS, listT, wlistT, listM, listL, env; DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex, erot, eno;
+    DBuf<int> listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex, erot, eno;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -421,7 +420,8 @@ __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const doub
 __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
                                      const uint8_t* __restrict__ evalid, const int* __restrict__ env, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
-                                     int* __restrict__ listS, Counters* c)
+                                     int* __restrict__ listS, const double* __restrict__ ex, const double* __restrict__ ey,
+                                     int* __restrict__ bins, int* __restrict__ bin_fill, Counters* c)
 {
     __shared__ int sh[SZ_NBINS];
     for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) sh[t] = 0;
@@ -436,22 +436,25 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
             if (pass == 0) { status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0; }
         } else {
             const int ni = env[i] < SZ_BIN_N ? env[i] : SZ_BIN_N - 1, nj = env[j] < SZ_BIN_N ? env[j] : SZ_BIN_N - 1;
-            key = ni * SZ_BIN_N + nj;
+            // pairs of one bucket have the same vertex counts and the partner in the same octant: similar event orders
+            const double dx = ex[j] - ex[i], dy = ey[j] - ey[i];
+            const int oct = (dx > 0) | ((dy > 0) << 1) | ((fabs(dx) > fabs(dy)) << 2);
+            key = (ni * SZ_BIN_N + nj) * 8 + oct;
             slot = atomicAdd(&sh[key], 1);
         }
     }
     __syncthreads();
     if (pass == 0) {
-        for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) if (sh[t]) atomicAdd(&c->bins[t], sh[t]);
+        for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) if (sh[t]) atomicAdd(&bins[t], sh[t]);
         return;
     }
     // pass 1: bins[] holds exclusive offsets; reserve this CTA's share of every bucket, then place
     __shared__ int base[SZ_NBINS];
-    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) base[t] = sh[t] ? atomicAdd(&c->bin_fill[t], sh[t]) : 0;
+    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) base[t] = sh[t] ? atomicAdd(&bin_fill[t], sh[t]) : 0;
     __syncthreads();
-    if (key >= 0) listS[c->bins[key] + base[key] + slot] = p;
+    if (key >= 0) listS[bins[key] + base[key] + slot] = p;
 }
-__global__ void bins_scan_kernel(Counters* c, int np)
+__global__ void bins_scan_kernel(Counters* c, int np, int* __restrict__ bins, int* __restrict__ bin_fill)
 {
     if (threadIdx.x == 0) {
         int run = 0;
@@ -459,7 +462,7 @@ __global__ void bins_scan_kernel(Counters* c, int np)
         for (int sum = 2 * (SZ_BIN_N - 1); sum >= 0; --sum)
             for (int ni = SZ_BIN_N - 1; ni >= 0; --ni) {
                 const int nj = sum - ni; if (nj < 0 || nj >= SZ_BIN_N) continue;
-                const int k = ni * SZ_BIN_N + nj; const int v = c->bins[k]; c->bins[k] = run; run += v; c->bin_fill[k] = 0;
+                for (int oct = 0; oct < 8; ++oct) { const int k = (ni * SZ_BIN_N + nj) * 8 + oct; const int v = bins[k]; bins[k] = run; run += v; bin_fill[k] = 0; }
             }
         c->listS = run; c->n_bbox_reject = np - run;
     }
@@ -712,7 +715,7 @@ extern "C" void sz_destroy(SzContext* c)
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
-                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
+                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
@@ -875,12 +878,14 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     }
     a.next_list = lstT; a.next_count = cntT;
     if (!wall) {
-        // work list of class S: bounding-box-disjoint pairs answered, the rest bucketed by vertex count
+        // work list of class S: bounding-box-disjoint pairs answered, the rest bucketed by vertex counts and direction
+        CK(c->bins.ensure(SZ_NBINS)); CK(c->bin_fill.ensure(SZ_NBINS));
+        CK(cudaMemsetAsync(c->bins.p, 0, SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, SZ_NBINS * sizeof(int), st));
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->d_cnt);
-        bins_scan_kernel<<<1, 32, 0, st>>>(c->d_cnt, n_work);
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->d_cnt);
+        bins_scan_kernel<<<1, 32, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->d_cnt);
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->d_cnt);
         g_launches += 3;
         a.list = c->listS.p; a.list_count = D_CNT(listS);
     }
@@ -1043,7 +1048,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     for (int attempt = 0; attempt < 3; ++attempt) {
         Counters z = *c->h_cnt;
         z.row_used = z.path_used = z.vert_used = z.listS = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
-        memset(z.bins, 0, sizeof(z.bins)); memset(z.bin_fill, 0, sizeof(z.bin_fill));
+
         *c->h_cnt = z;
         CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
         CK(cudaMemsetAsync(c->pstatus.p, 0, (size_t)(np + 1) * 4, st)); CK(cudaMemsetAsync(c->pnrows.p, 0, (size_t)(np + 1) * 4, st));
