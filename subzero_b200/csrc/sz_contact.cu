@@ -68,7 +68,8 @@ struct DBuf {
 };
 
 #define SZ_BIN_N 16                       // vertex counts 0..15 per outline get their own bucket (larger ones share the last)
-#define SZ_NBINS (SZ_BIN_N * SZ_BIN_N * 8) // x 8 octants of the partner's direction
+#define SZ_NSECT 16
+#define SZ_NBINS (SZ_BIN_N * SZ_BIN_N * SZ_NSECT) // x 16 sectors of the partner's direction
 // counters living in device memory, mirrored into pinned host memory with one copy
 struct Counters {
     int n1, n;                     // extended-list sizes after the x pass / after the y pass
@@ -438,8 +439,9 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
             const int ni = env[i] < SZ_BIN_N ? env[i] : SZ_BIN_N - 1, nj = env[j] < SZ_BIN_N ? env[j] : SZ_BIN_N - 1;
             // pairs of one bucket have the same vertex counts and the partner in the same octant: similar event orders
             const double dx = ex[j] - ex[i], dy = ey[j] - ey[i];
-            const int oct = (dx > 0) | ((dy > 0) << 1) | ((fabs(dx) > fabs(dy)) << 2);
-            key = (ni * SZ_BIN_N + nj) * 8 + oct;
+            const double adx = fabs(dx), ady = fabs(dy), mn = adx < ady ? adx : ady, mx = adx < ady ? ady : adx;
+            const int oct = (dx > 0) | ((dy > 0) << 1) | ((adx > ady) << 2) | ((mn > 0.41421356237309503 * mx) << 3);
+            key = (ni * SZ_BIN_N + nj) * SZ_NSECT + oct;
             slot = atomicAdd(&sh[key], 1);
         }
     }
@@ -462,7 +464,7 @@ __global__ void bins_scan_kernel(Counters* c, int np, int* __restrict__ bins, in
         for (int sum = 2 * (SZ_BIN_N - 1); sum >= 0; --sum)
             for (int ni = SZ_BIN_N - 1; ni >= 0; --ni) {
                 const int nj = sum - ni; if (nj < 0 || nj >= SZ_BIN_N) continue;
-                for (int oct = 0; oct < 8; ++oct) { const int k = (ni * SZ_BIN_N + nj) * 8 + oct; const int v = bins[k]; bins[k] = run; run += v; bin_fill[k] = 0; }
+                for (int oct = 0; oct < SZ_NSECT; ++oct) { const int k = (ni * SZ_BIN_N + nj) * SZ_NSECT + oct; const int v = bins[k]; bins[k] = run; run += v; bin_fill[k] = 0; }
             }
         c->listS = run; c->n_bbox_reject = np - run;
     }
