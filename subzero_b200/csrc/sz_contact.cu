@@ -109,7 +109,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<uint8_t> evalid, econvex, erot, eno;
+    DBuf<int> listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -414,27 +414,57 @@ __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const doub
     eno[e] = cvx ? (uint8_t)no : 0;
     erot[e] = cvx ? (uint8_t)szpf::ring_bottom_vertex(Get{vx, vy, X, Y, o}, no) : 0;     // start of the sweep input (PairHints)
 }
+// Separating-axis test for two strictly convex outlines: true when an edge line of one outline has every vertex of
+// the other at least 1 mm (4e6 Clipper units) on its outer side.  Then the outlines are disjoint with a margin a
+// million times Clipper's rounding, the intersection is empty and the sweep cannot fail: zero force, overlap 0.
+__device__ bool sat_separated(const double* __restrict__ vx, const double* __restrict__ vy, int o1, int n1, double X1, double Y1,
+                              int o2, int n2, double X2, double Y2)
+{
+    for (int side = 0; side < 2; ++side) {
+        const int oa = side ? o2 : o1, na = side ? n2 : n1, ob = side ? o1 : o2, nb = side ? n1 : n2;
+        const double XA = side ? X2 : X1, YA = side ? Y2 : Y1, XB = side ? X1 : X2, YB = side ? Y1 : Y2;
+        // orientation of A from its first turn (strictly convex: every turn has this sign)
+        const double t = ((vx[oa + 1] - vx[oa]) * (vy[oa + 2] - vy[oa + 1]) - (vy[oa + 1] - vy[oa]) * (vx[oa + 2] - vx[oa + 1]));
+        const double sg = t > 0 ? 1.0 : -1.0;       // inner side of an edge is where sg * cross > 0
+        for (int e = 0; e < na; ++e) {
+            const int e1 = (e + 1 == na) ? 0 : e + 1;
+            const double ax = vx[oa + e] + XA, ay = vy[oa + e] + YA, dx = (vx[oa + e1] + XA) - ax, dy = (vy[oa + e1] + YA) - ay;
+            const double lim = -1e-3 * sqrt(dx * dx + dy * dy);
+            bool all_out = true;
+            for (int q = 0; q < nb && all_out; ++q) {
+                const double cr = sg * (dx * ((vy[ob + q] + YB) - ay) - dy * ((vx[ob + q] + XB) - ax));
+                all_out = cr < lim;
+            }
+            if (all_out) return true;
+        }
+    }
+    return false;
+}
 // Pass 0 counts, pass 1 scatters.  A pair whose outlines both survive AddPath and whose integer bounding boxes are
 // strictly disjoint has an empty Clipper intersection (and cannot fail), so floe_interactions returns zero force and
 // overlap 0 (:43-51,71-74): it is answered here.  Every other pair is bucketed by n1 + n2 so that the pairs a CTA
 // sweeps together have the same number of scanbeams.
 __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
-                                     const uint8_t* __restrict__ evalid, const int* __restrict__ env, int want_polys,
+                                     const uint8_t* __restrict__ evalid, const int* __restrict__ env, const uint8_t* __restrict__ eno, const int* __restrict__ esrc,
+                                     const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
                                      int* __restrict__ listS, const double* __restrict__ ex, const double* __restrict__ ey,
-                                     int* __restrict__ bins, int* __restrict__ bin_fill, Counters* c)
+                                     int* __restrict__ bins, int* __restrict__ bin_fill, short* __restrict__ pkey, Counters* c)
 {
     __shared__ int sh[SZ_NBINS];
     for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) sh[t] = 0;
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     int key = -1, slot = 0;
-    if (p < np) {
+    if (p < np && pass == 1) { key = pkey[p]; if (key >= 0) slot = atomicAdd(&sh[key], 1); }
+    if (p < np && pass == 0) {
         const int i = pi[p], j = pj[p];
         const i64* a = ebb + (size_t)i * 4; const i64* b = ebb + (size_t)j * 4;
-        const bool disjoint = evalid[i] && evalid[j] && (a[1] < b[0] || b[1] < a[0] || a[3] < b[2] || b[3] < a[2]);
+        bool disjoint = evalid[i] && evalid[j] && (a[1] < b[0] || b[1] < a[0] || a[3] < b[2] || b[3] < a[2]);
+        if (!disjoint && eno[i] >= 3 && eno[j] >= 3)         // both strictly convex (eno is 0 otherwise)
+            disjoint = sat_separated(vx, vy, voff[esrc[i]], eno[i], ex[i], ey[i], voff[esrc[j]], eno[j], ex[j], ey[j]);
         if (disjoint) {
-            if (pass == 0) { status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0; }
+            status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0;
         } else {
             const int ni = env[i] < SZ_BIN_N ? env[i] : SZ_BIN_N - 1, nj = env[j] < SZ_BIN_N ? env[j] : SZ_BIN_N - 1;
             // pairs of one bucket have the same vertex counts and the partner in the same octant: similar event orders
@@ -444,6 +474,7 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
             key = (ni * SZ_BIN_N + nj) * SZ_NSECT + oct;
             slot = atomicAdd(&sh[key], 1);
         }
+        pkey[p] = (short)key;
     }
     __syncthreads();
     if (pass == 0) {
@@ -726,6 +757,7 @@ extern "C" void sz_destroy(SzContext* c)
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
+    c->pkey.release();
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -883,11 +915,11 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         // work list of class S: bounding-box-disjoint pairs answered, the rest bucketed by vertex counts and direction
         CK(c->bins.ensure(SZ_NBINS)); CK(c->bin_fill.ensure(SZ_NBINS));
         CK(cudaMemsetAsync(c->bins.p, 0, SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, SZ_NBINS * sizeof(int), st));
-        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->d_cnt);
+        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
         bins_scan_kernel<<<1, 32, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
-        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->d_cnt);
+        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
         g_launches += 3;
         a.list = c->listS.p; a.list_count = D_CNT(listS);
     }
@@ -1037,7 +1069,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
-    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1));
+    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
     if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p); }
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
