@@ -146,6 +146,30 @@ int sz_upload_extended(SzContext* ctx, const SzParams* prm, const SzFloesSoA* en
 int sz_update_extended_state(SzContext* ctx, const double* x, const double* y, const double* u, const double* v, const double* ksi,
                              const double* root_x, const double* root_y);
 
+/* Device helpers of the slab step's fast path (subzero_b200/slabs.py): all pointers are DEVICE memory.
+ * sz_slab_refresh: for the rank's own entries [originals | x-images | y-images] recompute the image centroids
+ * (floe_interactions_all.m:34,55), write x y u v ksi root_x root_y per entry into own_out, and set *bad_out when the
+ * plan is stale (an image flag of :31,52 changed, or a floe moved more than half_skin).  Synchronous.
+ * sz_slab_scatter: merge own and received 7-double records into the resident extended list (order[l] indexes
+ * [own | recv]); runs on the context's stream ahead of the next sz_step_resident. */
+typedef struct SzSlabRefresh {
+    int32_t n_orig, n_xg, n_yg;
+    const double *x, *y, *u, *v, *ksi;            /* [n_orig] */
+    const uint8_t* alive;                          /* [n_orig] */
+    const double *minvx, *maxvx, *minvy, *maxvy;   /* [n_orig] extents of c_alpha */
+    const int64_t* xg_par;                         /* [n_xg] original each x-image copies */
+    const int64_t* yg_par;                         /* [n_yg] entry of [originals | x-images] each y-image copies */
+    const uint8_t* fx_plan;                        /* [n_orig] */
+    const uint8_t* fy_plan;                        /* [n_orig + n_xg] */
+    const double *x0, *y0;                         /* [n_orig] centroids when the plan was built */
+    double Lx, Ly, half_skin;
+    int32_t periodic;
+    double* own_out;                               /* [(n_orig + n_xg + n_yg) * 7] */
+    int32_t* bad_out;
+} SzSlabRefresh;
+int sz_slab_refresh(SzContext* ctx, const SzSlabRefresh* r);
+int sz_slab_scatter(SzContext* ctx, const double* own, int64_t n_own, const double* recv, int64_t n_recv, const int64_t* order, int64_t n_local);
+
 /* ---- results of the last step (caller-allocated; sizes from SzSummary) ---- */
 /* per floe of the input list, each [n0] unless noted; any pointer may be NULL to skip */
 int sz_get_floe_outputs(SzContext* ctx,

@@ -41,6 +41,12 @@ class SzExtendedList(C.Structure):
     _fields_ = [("gid", c_ip), ("floe_num", c_ip), ("root_x", c_dp), ("root_y", c_dp), ("owned", c_bp), ("parent", c_ip)]
 
 
+class SzSlabRefresh(C.Structure):
+    _fields_ = [("n_orig", C.c_int32), ("n_xg", C.c_int32), ("n_yg", C.c_int32)] + [(n, c_dp) for n in ("x", "y", "u", "v", "ksi")] + [("alive", c_bp)] + [
+        (n, c_dp) for n in ("minvx", "maxvx", "minvy", "maxvy")] + [("xg_par", c_lp), ("yg_par", c_lp), ("fx_plan", c_bp), ("fy_plan", c_bp), ("x0", c_dp), ("y0", c_dp),
+        ("Lx", C.c_double), ("Ly", C.c_double), ("half_skin", C.c_double), ("periodic", C.c_int32), ("own_out", c_dp), ("bad_out", c_ip)]
+
+
 class SzSummary(C.Structure):
     _fields_ = [("n0", C.c_int32), ("n", C.c_int32), ("n_pairs", C.c_int64), ("n_pairs_force", C.c_int64), ("n_rows", C.c_int64),
                 ("n_clip_paths", C.c_int64), ("n_clip_verts", C.c_int64), ("collision_count", C.c_double),
@@ -62,6 +68,8 @@ PROTOTYPES = {
     "sz_upload": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary)]),
     "sz_upload_extended": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzExtendedList)]),
     "sz_update_extended_state": (C.c_int, [C.c_void_p] + [c_dp] * 7),
+    "sz_slab_refresh": (C.c_int, [C.c_void_p, C.POINTER(SzSlabRefresh)]),
+    "sz_slab_scatter": (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, C.c_int64, c_lp, C.c_int64]),
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
     "sz_get_floe_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),

@@ -879,6 +879,72 @@ extern "C" int sz_update_extended_state(SzContext* c, const double* x, const dou
     return SZ_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ slab refresh
+// One thread per entry of the rank's own part of the extended list [originals | x-images | y-images]: recomputes the
+// image centroids from the current centroids (floe_interactions_all.m:34,55), checks the plan (same floes poke through
+// the periodic boundary, :31,52; no floe moved more than half the halo skin) and writes the 7-double motion record.
+__global__ void slab_refresh_kernel(const SzSlabRefresh r)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_own = r.n_orig + r.n_xg + r.n_yg;
+    if (e >= n_own) return;
+    int src; double X, Y; bool bad = false;
+    if (e < r.n_orig) {
+        src = e; X = r.x[e]; Y = r.y[e];
+        if (!(fabs(X - r.x0[e]) <= r.half_skin) || !(fabs(Y - r.y0[e]) <= r.half_skin)) bad = true;
+        if (r.periodic) {
+            const bool fx = r.alive[e] && fmax(fabs(r.maxvx[e] + X), fabs(r.minvx[e] + X)) > r.Lx;
+            if (fx != (r.fx_plan[e] != 0)) bad = true;
+        }
+    } else if (e < r.n_orig + r.n_xg) {
+        src = (int)r.xg_par[e - r.n_orig];
+        X = r.x[src] - 2 * r.Lx * sgn_d(r.x[src]); Y = r.y[src];
+    } else {
+        const int q = (int)r.yg_par[e - r.n_orig - r.n_xg];
+        double Yq;
+        if (q < r.n_orig) { src = q; X = r.x[q]; Yq = r.y[q]; }
+        else { src = (int)r.xg_par[q - r.n_orig]; X = r.x[src] - 2 * r.Lx * sgn_d(r.x[src]); Yq = r.y[src]; }
+        Y = Yq - 2 * r.Ly * sgn_d(Yq);
+    }
+    if (r.periodic && e < r.n_orig + r.n_xg) {
+        const bool fy = r.alive[src] && fmax(fabs(r.maxvy[src] + Y), fabs(r.minvy[src] + Y)) > r.Ly;
+        if (fy != (r.fy_plan[e] != 0)) bad = true;
+    }
+    double* o = r.own_out + (size_t)e * 7;
+    o[0] = X; o[1] = Y; o[2] = r.u[src]; o[3] = r.v[src]; o[4] = r.ksi[src]; o[5] = r.x[src]; o[6] = r.y[src];
+    if (bad) atomicExch(r.bad_out, 1);
+}
+__global__ void slab_scatter_kernel(int n_local, const double* __restrict__ own, long long n_own, const double* __restrict__ recv, const long long* __restrict__ order,
+                                    double* x, double* y, double* u, double* v, double* ksi, double* rx, double* ry)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_local) return;
+    const long long k = order[l];
+    const double* row = k < n_own ? own + k * 7 : recv + (k - n_own) * 7;
+    x[l] = row[0]; y[l] = row[1]; u[l] = row[2]; v[l] = row[3]; ksi[l] = row[4]; rx[l] = row[5]; ry[l] = row[6];
+}
+extern "C" int sz_slab_refresh(SzContext* c, const SzSlabRefresh* r)
+{
+    if (!c || !r || !r->own_out || !r->bad_out) { sz_set_error("sz_slab_refresh: NULL argument"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    const int n_own = r->n_orig + r->n_xg + r->n_yg;
+    CK(cudaMemsetAsync(r->bad_out, 0, 4, c->stream));
+    if (n_own > 0) { ++g_launches; slab_refresh_kernel<<<nblk(n_own, 256), 256, 0, c->stream>>>(*r); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+extern "C" int sz_slab_scatter(SzContext* c, const double* own, int64_t n_own, const double* recv, int64_t n_recv, const int64_t* order, int64_t n_local)
+{
+    if (!c || (n_local > 0 && !order)) { sz_set_error("sz_slab_scatter: NULL argument"); return SZ_ERR_ARG; }
+    if (!c->have_input || !c->ext_mode || n_local != c->n0 || n_own + n_recv != n_local) { sz_set_error("sz_slab_scatter: the resident extended list has a different size"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    if (n_local > 0) { ++g_launches; slab_scatter_kernel<<<nblk(n_local, 256), 256, 0, c->stream>>>((int)n_local, own, n_own, recv, (const long long*)order,
+                                                                                                      c->x.p, c->y.p, c->u.p, c->v.p, c->ksi.p, c->erootx.p, c->erooty.p); }
+    CK(cudaGetLastError());
+    return SZ_OK;      // ordered before the step on the library's stream
+}
+
 static int read_counters(SzContext* c)
 {
     CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDefault, c->stream));

@@ -363,6 +363,37 @@ class SlabStep:
         self._first = None
         self.summary = None
 
+    def _refresh_on_device(self):
+        """refresh_local_state with the list surgery done by the library's slab kernels (CUDA tensors)"""
+        st, prm, plan, comm = self.st, self.prm, self.local.plan, self.comm
+        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ) if t is not None and t.numel() else None
+        dev = st.x.device
+        if "own_buf" not in plan:
+            u8 = lambda t: t.to(torch.uint8).contiguous() if t is not None else None
+            plan.update(own_buf=torch.empty((plan["n_own"], 7), dtype=F64, device=dev), bad_buf=torch.zeros(1, dtype=torch.int32, device=dev),
+                        fx8=u8(plan["fx"]), fy8=u8(plan["fy"]), xg_c=plan["xg_par"].contiguous(), yg_c=plan["yg_par"].contiguous(), order_c=plan["order"].contiguous())
+        r = abi.SzSlabRefresh()
+        r.n_orig, r.n_xg, r.n_yg = st.n, int(plan["xg_c"].shape[0]), int(plan["yg_c"].shape[0])
+        for nm, t in (("x", st.x), ("y", st.y), ("u", st.u), ("v", st.v), ("ksi", st.ksi), ("minvx", st.ext[0]), ("maxvx", st.ext[1]), ("minvy", st.ext[2]), ("maxvy", st.ext[3]),
+                      ("x0", plan["x0"]), ("y0", plan["y0"])):
+            setattr(r, nm, P(t.contiguous(), abi.c_dp))
+        r.alive = P(st.alive, abi.c_bp)
+        r.xg_par, r.yg_par = P(plan["xg_c"], abi.c_lp), P(plan["yg_c"], abi.c_lp)
+        r.fx_plan, r.fy_plan = P(plan["fx8"], abi.c_bp), P(plan["fy8"], abi.c_bp)
+        r.Lx, r.Ly, r.half_skin, r.periodic = prm.Lx, prm.Ly, 0.5 * plan["skin"], int(bool(prm.periodic))
+        r.own_out, r.bad_out = P(plan["own_buf"], abi.c_dp), P(plan["bad_buf"], abi.c_ip)
+        torch.cuda.current_stream().synchronize()
+        abi.check(abi.lib().sz_slab_refresh(self.ctx._h, C.byref(r)))
+        if int(comm.all_max(plan["bad_buf"])) != 0:
+            return False
+        send = plan["own_buf"][plan["sidx"]]
+        recv = comm.exchange(send, plan["send_counts"], plan["recv_counts"])
+        torch.cuda.current_stream().synchronize()
+        n_own, n_recv = plan["n_own"], int(recv.shape[0])
+        abi.check(abi.lib().sz_slab_scatter(self.ctx._h, P(plan["own_buf"], abi.c_dp), n_own, P(recv, abi.c_dp), n_recv, P(plan["order_c"], abi.c_lp), n_own + n_recv))
+        plan["_keep"] = recv          # the scatter kernel reads it asynchronously
+        return True
+
     def invalidate(self):
         """call when floes were created, destroyed or reshaped (the outlines and the alive flags are part of the plan)"""
         self.local = None
@@ -373,11 +404,13 @@ class SlabStep:
         st, prm = self.st, self.prm
         P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
         if self.local is not None and self.skin > 0:
-            ok, dyn = refresh_local_state(st, prm.Lx, prm.Ly, bool(prm.periodic), self.local.plan, self.comm)
+            if st.x.is_cuda:
+                ok = self._refresh_on_device()          # two library kernels + one gather around the exchange
+            else:
+                ok, dyn = refresh_local_state(st, prm.Lx, prm.Ly, bool(prm.periodic), self.local.plan, self.comm)
+                if ok:
+                    abi.check(abi.lib().sz_update_extended_state(self.ctx._h, *(P(dyn[k], abi.c_dp) for k in range(7))))
             if ok:
-                if dyn.is_cuda:
-                    torch.cuda.current_stream().synchronize()
-                abi.check(abi.lib().sz_update_extended_state(self.ctx._h, *(P(dyn[k], abi.c_dp) for k in range(7))))
                 self.fast_steps += 1
                 self.summary = self.ctx.step_resident()
                 return self.summary
