@@ -487,18 +487,25 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
     __syncthreads();
     if (key >= 0) listS[bins[key] + base[key] + slot] = p;
 }
-__global__ void bins_scan_kernel(Counters* c, int np, int* __restrict__ bins, int* __restrict__ bin_fill)
+// Exclusive offsets of the buckets in launch order: longest outlines first (the CTAs with the longest sweeps start
+// first, which shortens the tail of the launch).  One thread per (n1, n2) combination; its rank in the order
+// "n1 + n2 descending, n1 descending" is closed-form, a 256-wide shared-memory scan does the rest.
+__global__ void __launch_bounds__(SZ_BIN_N * SZ_BIN_N) bins_scan_kernel(Counters* c, int np, int* __restrict__ bins, int* __restrict__ bin_fill)
 {
-    if (threadIdx.x == 0) {
-        int run = 0;
-        // largest outlines first: the CTAs with the longest sweeps start first, which shortens the tail of the launch
-        for (int sum = 2 * (SZ_BIN_N - 1); sum >= 0; --sum)
-            for (int ni = SZ_BIN_N - 1; ni >= 0; --ni) {
-                const int nj = sum - ni; if (nj < 0 || nj >= SZ_BIN_N) continue;
-                for (int oct = 0; oct < SZ_NSECT; ++oct) { const int k = (ni * SZ_BIN_N + nj) * SZ_NSECT + oct; const int v = bins[k]; bins[k] = run; run += v; bin_fill[k] = 0; }
-            }
-        c->listS = run; c->n_bbox_reject = np - run;
-    }
+    const int B = SZ_BIN_N, t = threadIdx.x, ni = t / B, nj = t % B, sum = ni + nj;
+    __shared__ int tot[SZ_BIN_N * SZ_BIN_N], scan[SZ_BIN_N * SZ_BIN_N];
+    int before = (sum < B - 1 ? sum : B - 1) - ni;                       // same sum, larger n1
+    for (int u = sum + 1; u <= 2 * B - 2; ++u) before += (u < B) ? u + 1 : 2 * B - 1 - u;
+    int mine = 0;
+    for (int oct = 0; oct < SZ_NSECT; ++oct) mine += bins[t * SZ_NSECT + oct];
+    tot[before] = mine;
+    __syncthreads();
+    scan[t] = tot[t];
+    __syncthreads();
+    for (int d = 1; d < B * B; d <<= 1) { const int v = (t >= d) ? scan[t - d] : 0; __syncthreads(); scan[t] += v; __syncthreads(); }
+    int base = scan[before] - mine;                                       // exclusive
+    for (int oct = 0; oct < SZ_NSECT; ++oct) { const int k = t * SZ_NSECT + oct; const int v = bins[k]; bins[k] = base; base += v; bin_fill[k] = 0; }
+    if (t == 0) { c->listS = scan[B * B - 1]; c->n_bbox_reject = np - scan[B * B - 1]; }
 }
 
 // ------------------------------------------------------------------------------------------------ K4 assembly
@@ -983,7 +990,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         CK(cudaMemsetAsync(c->bins.p, 0, SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, SZ_NBINS * sizeof(int), st));
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
                                                             c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
-        bins_scan_kernel<<<1, 32, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
+        bins_scan_kernel<<<1, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
                                                             c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
         g_launches += 3;
