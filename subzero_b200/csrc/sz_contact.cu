@@ -300,7 +300,7 @@ __global__ void cell_fill_kernel(int n, const int* __restrict__ cid, const int* 
 }
 
 struct BroadArgs {
-    int n, n0, Nb, collision; GridDesc g; double minL2;
+    int n, n0, Nb, collision; GridDesc g; double minL2, rmax_max;
     const double* ex; const double* ey; const int* esrc; const int* efn; const uint8_t* ealive; const double* rmax;
     const int* egid; const uint8_t* eowned; const double* erootx; const double* erooty;
     const int* cell_start; const int* s_idx; const double* s_x; const double* s_y; const double* s_r;
@@ -340,8 +340,10 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
     if (active) {
         const double ri = b.rmax[b.esrc[i]];
         const int cxi = cell_coord(xi, b.g.x0, b.g.cell, b.g.nx), cyi = cell_coord(yi, b.g.y0, b.g.cell, b.g.ny);
-        const int cx0 = cxi > 0 ? cxi - 1 : 0, cx1 = cxi + 1 < b.g.nx ? cxi + 1 : b.g.nx - 1;
-        for (int cy = (cyi > 0 ? cyi - 1 : 0); cy <= cyi + 1 && cy < b.g.ny; ++cy) {
+        // a partner has |dx|, |dy| < ri + rmax_j <= ri + max(rmax): that many cells each way (floor differences <= ceil)
+        const int R = (int)((ri + b.rmax_max) / b.g.cell) + 1;
+        const int cx0 = cxi - R > 0 ? cxi - R : 0, cx1 = cxi + R < b.g.nx ? cxi + R : b.g.nx - 1;
+        for (int cy = (cyi - R > 0 ? cyi - R : 0); cy <= cyi + R && cy < b.g.ny; ++cy) {
             const int t0 = b.cell_start[cy * b.g.nx + cx0], t1 = b.cell_start[cy * b.g.nx + cx1 + 1];
             for (int tb = t0; tb < t1; tb += 32) {
                 const int t = tb + lane;
@@ -1105,7 +1107,10 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         const double xmn = dec_d(c->h_cnt->bbox[0]), xmx = dec_d(c->h_cnt->bbox[1]), ymn = dec_d(c->h_cnt->bbox[2]), ymx = dec_d(c->h_cnt->bbox[3]);
         if (xmn <= xmx && std::isfinite(xmn) && std::isfinite(xmx) && std::isfinite(ymn) && std::isfinite(ymx)) {
             g.x0 = xmn; g.y0 = ymn;
+            // about four floes per cell, but never more than 8 cells per reach (2 max(rmax)); the search widens per floe
             double cell = 2 * rm; if (!(cell > 0) || !std::isfinite(cell)) cell = 1;
+            const double dens = std::sqrt(4.0 * (xmx - xmn) * (ymx - ymn) / std::max(1, n));
+            if (dens > 0 && std::isfinite(dens)) cell = std::min(cell, std::max(cell / 8, dens));
             // keep the grid below ~16M cells
             while ((xmx - xmn) / cell * ((ymx - ymn) / cell) > 1.6e7) cell *= 2;
             g.cell = cell;
@@ -1125,7 +1130,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         exclusive_scan(c->cell_cnt.p, ncell, c->cell_start.p, ncell + 1, c->scan_tmp.p, st);
         CK(cudaMemsetAsync(c->cell_cnt.p, 0, (size_t)(ncell + 1) * 4, st));
         ++g_launches; cell_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->cid.p, c->cell_start.p, c->cell_cnt.p, c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->s_idx.p, c->s_x.p, c->s_y.p, c->s_r.p);
-        b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly);
+        b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly); b.rmax_max = dec_d(c->h_cnt->rmax_bits);
         b.ex = c->ex.p; b.ey = c->ey.p; b.esrc = c->esrc.p; b.efn = c->efn.p; b.ealive = c->ealive.p; b.rmax = c->rmax.p;
         b.egid = c->egid.p; b.eowned = c->eowned.p; b.erootx = c->erootx.p; b.erooty = c->erooty.p;
         b.cell_start = c->cell_start.p; b.s_idx = c->s_idx.p; b.s_x = c->s_x.p; b.s_y = c->s_y.p; b.s_r = c->s_r.p;
