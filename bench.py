@@ -39,13 +39,41 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clock + throttle reasons through nvidia-smi during the timed region"""
+    """samples the SM clock and the throttle reasons during the timed region: NVML every 10 ms when pynvml is there
+    (the timed region can be well under a second), else nvidia-smi every 200 ms"""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.samples, self.reasons, self.max_mhz, self._stop_ev = gpu, [], set(), None, threading.Event()
+        self.how = "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu]) if vis and vis.split(",")[0].isdigit() else gpu
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.how = "nvml"
+        except Exception:
+            self._nv = None
 
     def run(self):
+        if self._nv is not None:
+            nv = self._nv
+            while not self._stop_ev.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    for nm, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+                self._stop_ev.wait(0.01)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,clocks_throttle_reasons.hw_thermal_slowdown,clocks_throttle_reasons.sw_thermal_slowdown,clocks_throttle_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop_ev.is_set():
@@ -65,7 +93,7 @@ class ClockSampler(threading.Thread):
         self._stop_ev.set()
         self.join(timeout=6)
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s), "how": self.how}
 
 
 def algorithmic_bytes(floes, summary):
