@@ -191,6 +191,29 @@ int sz_get_rows(SzContext* ctx, int64_t* row_off, double* rows);
  * pair_path_off [n_pairs+1] -> path_vert_off [n_clip_paths+1] -> x,y [n_clip_verts] */
 int sz_get_clip_polys(SzContext* ctx, int64_t* pair_path_off, int64_t* path_vert_off, int64_t* x, int64_t* y);
 
+/* ---- the integrator half of the timestep, calc_trajectory.m, for the branch the contact-loop
+ * benchmark exercises: doInt.flag = false with the ocean/atmosphere tendencies FxOA, FyOA, torqueOA carried over (no
+ * ocean or wind evaluation; a floe thinner than 0.1 m, which the reference re-forces every step (:94), is reported and
+ * the call fails).  The state stays on the device: contact step -> trajectory step -> contact step ... with no host
+ * round trip.  Single-GPU lists only.
+ *   sz_trajectory_init  after sz_upload: the Floe fields the integrator owns (initialize_floe_values.m:16-24,40-47);
+ *                       NULL = zeros; c0 NULL = the uploaded c_alpha (alpha_i = 0); StressH = zeros(2,2,nz), StressCount = 1
+ *   sz_trajectory_step  after a contact step: consumes its collision_force/torque, stress sum, alive and wrapped
+ *                       centroids (floe_interactions_all.m:279-284), advances Xi Yi alpha_i Ui Vi ksi_ice h mass
+ *                       inertia_moment c_alpha in place (:36-46,67-80,170-222); a sacked floe (:89,116-117) keeps its
+ *                       state and is flagged, like the caller's kill(i) = i
+ *   sz_get_trajectory   any pointer may be NULL; stress = mean(StressH,3) (:20), flags bit 0 sacked, bit 1 needs ocean */
+typedef struct SzTrajectoryInit {
+    const double *mass, *inertia, *alpha, *dXi_p, *dYi_p, *dUi_p, *dVi_p, *dalpha_p, *dksi_p, *FxOA, *FyOA, *torqueOA;   /* [n0] */
+    const double *c0x, *c0y;                                                                                            /* [nverts] */
+    int32_t nz;                  /* depth of the stress history (1000 in the reference, initialize_floe_values.m:24) */
+} SzTrajectoryInit;
+typedef struct SzTrajectoryParams { double dt, HFo, xo_min, xo_max, yo_min, yo_max; } SzTrajectoryParams;   /* HFo = mean(HFo(:)); ocean grid extent (:116) */
+int sz_trajectory_init(SzContext* ctx, const SzTrajectoryInit* init);
+int sz_trajectory_step(SzContext* ctx, const SzTrajectoryParams* prm, int32_t* n_sacked, int32_t* n_needs_ocean);
+int sz_get_trajectory(SzContext* ctx, double* x, double* y, double* u, double* v, double* ksi, double* h, uint8_t* alive, double* mass, double* inertia, double* alpha,
+                      double* dXi_p, double* dYi_p, double* dUi_p, double* dVi_p, double* dalpha_p, double* dksi_p, double* stress, int32_t* flags, double* cax, double* cay);
+
 /* diagnostic: device time (CUDA events, ms) of the last step by phase:
  * [0] ghost floes (floe_interactions_all.m:16-66)   [1] broad phase (:68-120)
  * [2] narrow phase + force law (:125-174)           [3] mirror/torque/sums (:186-265)   [4] whole step */

@@ -806,4 +806,94 @@ int szo_floe_interactions(const SzParams* prm, const double* cax, const double* 
 }
 int szo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
+// ---- calc_trajectory.m, the branch the contact-loop benchmark exercises: doInt.flag = false with
+// FxOA/FyOA/torqueOA carried over, no ocean/wind evaluation.  One call = the loop floe_interactions_all.m:279-284 over
+// the floes of the input list.  Arrays are per floe; c0/c_alpha pools share voff.  sacked[i] = 1 when the reference
+// returns floe = [] (:89,117); unsupported[i] = 1 when the reference would evaluate the ocean (h < 0.1, :94,121).
+void szo_calc_trajectory(int n, double dt, double HFo, double xo_min, double xo_max, double yo_min, double yo_max, int nz,
+                         const double* cfx, const double* cfy, const double* ctq, const double* stress_now, const uint8_t* has_rows,
+                         const double* area, double* x, double* y, double* u, double* v, double* ksi, double* h, uint8_t* alive,
+                         double* mass, double* inertia, double* alpha, double* dXi_p, double* dYi_p, double* dUi_p, double* dVi_p,
+                         double* dalpha_p, double* dksi_p, const double* FxOA, const double* FyOA, const double* torqueOA,
+                         const int32_t* voff, const double* c0x, const double* c0y, double* cax, double* cay,
+                         double* stress_h, int32_t* stress_count, double* stress_out, uint8_t* sacked, uint8_t* unsupported)
+{
+    auto sgn = [](double a) { return (double)((a > 0) - (a < 0)); };
+    for (int i = 0; i < n; ++i) {
+        sacked[i] = 0; unsupported[i] = 0;
+        if (!alive[i]) continue;                                                   // floe_interactions_all.m:280
+        double ext_fx = cfx[i], ext_fy = cfy[i], ext_t = ctq[i];                    // :3-4
+        // a sacked floe comes back as [] and the caller keeps the OLD struct (floe_interactions_all.m:282): remember it
+        const double mass0 = mass[i], inertia0 = inertia[i], h0 = h[i]; const uint8_t alive0 = alive[i]; const int32_t sc0 = stress_count[i];
+        // :9-29 stress history ring (StressCount is 1-based)
+        if (stress_count[i] > nz) stress_count[i] = 1;
+        double* slot = stress_h + ((size_t)i * nz + (stress_count[i] - 1)) * 4;
+        double slot0[4]; for (int k = 0; k < 4; ++k) slot0[k] = slot[k];
+        for (int k = 0; k < 4; ++k) slot[k] = has_rows[i] ? stress_now[(size_t)i * 4 + k] : 0.0;
+        stress_count[i] += 1;
+        double st_new[4];
+        for (int k = 0; k < 4; ++k) { double sm = 0; for (int z = 0; z < nz; ++z) sm += stress_h[((size_t)i * nz + z) * 4 + k]; st_new[k] = sm / nz; }   // mean(StressH,3)
+        // :36-41
+        if (h[i] > 10) h[i] = 10; else if (mass[i] < 100) { mass[i] = 1e3; alive[i] = 0; }
+        while (std::max(std::fabs(ext_fx), std::fabs(ext_fy)) > mass[i] / (5 * dt)) { ext_fx = ext_fx / 10; ext_fy = ext_fy / 10; ext_t = ext_t / 10; }   // :42-46
+        // :67-80 thermodynamic growth
+        const double floe_area = area[i];
+        double floe_mass = mass[i], hh = h[i], floe_inertia = inertia[i];
+        const double dh = HFo * dt / hh;
+        floe_mass = (hh - dh) / hh * floe_mass; mass[i] = floe_mass;
+        floe_inertia = (hh - dh) / hh * floe_inertia; inertia[i] = floe_inertia;
+        h[i] = hh - dh;
+        bool sack = std::isnan(x[i]);                                              // :89
+        if (!sack && h[i] < 0.1) { unsupported[i] = 1; continue; }                 // :94 would re-evaluate the ocean forcing
+        if (!sack) {
+            double cmaxx = -INF, cminx = INF, cmaxy = -INF, cminy = INF;
+            for (int t = voff[i]; t < voff[i + 1]; ++t) { cmaxx = std::max(cmaxx, cax[t]); cminx = std::min(cminx, cax[t]); cmaxy = std::max(cmaxy, cay[t]); cminy = std::min(cminy, cay[t]); }
+            sack = (cmaxx + x[i] > xo_max || cminx + x[i] < xo_min || cmaxy + y[i] > yo_max || cminy + y[i] < yo_min);   // :116-117
+        }
+        if (sack) {
+            sacked[i] = 1; mass[i] = mass0; inertia[i] = inertia0; h[i] = h0; alive[i] = alive0; stress_count[i] = sc0;
+            for (int k = 0; k < 4; ++k) slot[k] = slot0[k];
+            continue;
+        }
+        for (int k = 0; k < 4; ++k) stress_out[(size_t)i * 4 + k] = st_new[k];
+        if (alive[i] != 1) continue;                                               // :118
+        // :174-177 positions, AB2
+        const double dx = 1.5 * dt * u[i] - 0.5 * dt * dXi_p[i], dy = 1.5 * dt * v[i] - 0.5 * dt * dYi_p[i];
+        x[i] = x[i] + dx; dXi_p[i] = u[i];
+        y[i] = y[i] + dy; dYi_p[i] = v[i];
+        alpha[i] = alpha[i] + 1.5 * dt * ksi[i] - 0.5 * dt * dalpha_p[i]; dalpha_p[i] = ksi[i];
+        // :181-208 velocities with the 0.5 h / dt limiter
+        const double ax0 = (FxOA[i] * floe_area + ext_fx), ay0 = (FyOA[i] * floe_area + ext_fy);
+        double dU = ax0 / floe_mass, dV = ay0 / floe_mass;
+        bool have_frac = false; double frac = 0;
+        const double lim = 0.5 * h[i];
+        if (std::fabs(dt * dU) > lim && std::fabs(dt * dV) > lim) {
+            dU = sgn(dU) * 0.5 * h[i] / dt; dV = sgn(dV) * 0.5 * h[i] / dt;
+            const double f1 = dU / ax0 * floe_mass, f2 = dV / ay0 * floe_mass;
+            frac = std::min(f1, f2); have_frac = true;
+            dU = ax0 / floe_mass; dV = ay0 / floe_mass; dU = frac * dU; dV = frac * dV;
+        } else if (std::fabs(dt * dU) > lim && std::fabs(dt * dV) < lim) {
+            dU = sgn(dU) * 0.5 * h[i] / dt;
+            frac = dU / ax0 * floe_mass; have_frac = true;
+            dU = ax0 / floe_mass; dV = ay0 / floe_mass; dU = frac * dU; dV = frac * dV;
+        } else if (std::fabs(dt * dU) < lim && std::fabs(dt * dV) > lim) {
+            dV = sgn(dV) * 0.5 * h[i] / dt;
+            frac = dV / ay0 * floe_mass; have_frac = true;
+            dU = ax0 / floe_mass; dV = ay0 / floe_mass; dU = frac * dU; dV = frac * dV;
+        }
+        u[i] = u[i] + 1.5 * dt * dU - 0.5 * dt * dUi_p[i];
+        v[i] = v[i] + 1.5 * dt * dV - 0.5 * dt * dVi_p[i];
+        dUi_p[i] = dU; dVi_p[i] = dV;
+        // :210-219 angular velocity, clamped to 1e-5
+        double dksi = (torqueOA[i] * floe_area + ext_t) / floe_inertia;
+        if (have_frac) dksi = frac * dksi;
+        double k2 = ksi[i] + 1.5 * dt * dksi - 0.5 * dt * dksi_p[i];
+        if (std::fabs(k2) > 1e-5) k2 = sgn(k2) * 1e-5;
+        ksi[i] = k2; dksi_p[i] = dksi;
+        // :221-222 rotate the outline
+        const double ca = std::cos(alpha[i]), sa = std::sin(alpha[i]);
+        for (int t = voff[i]; t < voff[i + 1]; ++t) { cax[t] = ca * c0x[t] + (-sa) * c0y[t]; cay[t] = sa * c0x[t] + ca * c0y[t]; }
+    }
+}
+
 }  // extern "C"

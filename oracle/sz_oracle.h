@@ -31,6 +31,13 @@ int  szo_floe_interactions(const SzParams* prm, const double* cax, const double*
                            const double* boxx, const double* boxy, int nbox,
                            double* rows_out, int rows_cap, double* overlap_state);
 int  szo_hardware_threads(void);
+void szo_calc_trajectory(int n, double dt, double HFo, double xo_min, double xo_max, double yo_min, double yo_max, int nz,
+                         const double* cfx, const double* cfy, const double* ctq, const double* stress_now, const uint8_t* has_rows,
+                         const double* area, double* x, double* y, double* u, double* v, double* ksi, double* h, uint8_t* alive,
+                         double* mass, double* inertia, double* alpha, double* dXi_p, double* dYi_p, double* dUi_p, double* dVi_p,
+                         double* dalpha_p, double* dksi_p, const double* FxOA, const double* FyOA, const double* torqueOA,
+                         const int32_t* voff, const double* c0x, const double* c0y, double* cax, double* cay,
+                         double* stress_h, int32_t* stress_count, double* stress_out, uint8_t* sacked, uint8_t* unsupported);
 #ifdef __cplusplus
 }
 #endif

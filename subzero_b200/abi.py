@@ -41,6 +41,15 @@ class SzExtendedList(C.Structure):
     _fields_ = [("gid", c_ip), ("floe_num", c_ip), ("root_x", c_dp), ("root_y", c_dp), ("owned", c_bp), ("parent", c_ip)]
 
 
+class SzTrajectoryInit(C.Structure):
+    NAMES = ("mass", "inertia", "alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p", "FxOA", "FyOA", "torqueOA", "c0x", "c0y")
+    _fields_ = [(n, c_dp) for n in NAMES] + [("nz", C.c_int32)]
+
+
+class SzTrajectoryParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("dt", "HFo", "xo_min", "xo_max", "yo_min", "yo_max")]
+
+
 class SzSlabRefresh(C.Structure):
     _fields_ = [("n_orig", C.c_int32), ("n_xg", C.c_int32), ("n_yg", C.c_int32)] + [(n, c_dp) for n in ("x", "y", "u", "v", "ksi")] + [("alive", c_bp)] + [
         (n, c_dp) for n in ("minvx", "maxvx", "minvy", "maxvy")] + [("xg_par", c_lp), ("yg_par", c_lp), ("fx_plan", c_bp), ("fy_plan", c_bp), ("x0", c_dp), ("y0", c_dp),
@@ -75,6 +84,9 @@ PROTOTYPES = {
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),
     "sz_get_pairs": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_ip, c_ip]),
     "sz_get_rows": (C.c_int, [C.c_void_p, c_lp, c_dp]),
+    "sz_trajectory_init": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryInit)]),
+    "sz_trajectory_step": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryParams), c_ip, c_ip]),
+    "sz_get_trajectory": (C.c_int, [C.c_void_p] + [c_dp] * 6 + [c_bp] + [c_dp] * 10 + [c_ip, c_dp, c_dp]),
     "sz_get_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "sz_get_clip_polys": (C.c_int, [C.c_void_p, c_lp, c_lp, c_lp, c_lp]),
     "sz_clip_batch": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp]),

@@ -115,6 +115,39 @@ class ContactContext:
         abi.check(abi.lib().sz_get_clip_polys(self._h, p(ppo, abi.c_lp), p(pvo, abi.c_lp), p(x, abi.c_lp), p(y, abi.c_lp)))
         return ppo, pvo, x, y
 
+    # ---- integrator half of the timestep (calc_trajectory.m, no-ocean branch)
+    def trajectory_init(self, mass, inertia, nz=1000, **fields):
+        """fields: alpha dXi_p dYi_p dUi_p dVi_p dalpha_p dksi_p FxOA FyOA torqueOA [n0], c0x c0y [nverts]; missing = zeros
+        (c0 = the uploaded c_alpha)"""
+        init = abi.SzTrajectoryInit()
+        keep = {"mass": abi.f64(mass), "inertia": abi.f64(inertia)}
+        keep.update({k: abi.f64(v) for k, v in fields.items()})
+        for k in abi.SzTrajectoryInit.NAMES:
+            setattr(init, k, abi._ptr(keep.get(k), abi.c_dp))
+        init.nz = int(nz)
+        abi.check(abi.lib().sz_trajectory_init(self._h, C.byref(init)))
+
+    def trajectory_step(self, dt, HFo=0.0, xo_min=-np.inf, xo_max=np.inf, yo_min=-np.inf, yo_max=np.inf):
+        p = abi.SzTrajectoryParams(float(dt), float(HFo), float(xo_min), float(xo_max), float(yo_min), float(yo_max))
+        ns, no = C.c_int32(), C.c_int32()
+        abi.check(abi.lib().sz_trajectory_step(self._h, C.byref(p), C.byref(ns), C.byref(no)))
+        return ns.value
+
+    def trajectory_state(self, nverts=0):
+        n = self._n0
+        o = {k: np.empty(n) for k in ("x", "y", "u", "v", "ksi", "h")}
+        o["alive"] = np.empty(n, np.uint8)
+        o.update({k: np.empty(n) for k in ("mass", "inertia", "alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p")})
+        o["stress"] = np.empty((n, 2, 2))
+        o["flags"] = np.empty(n, np.int32)
+        o["cax"], o["cay"] = np.empty(nverts), np.empty(nverts)
+        p = abi._ptr
+        order = ("x", "y", "u", "v", "ksi", "h")
+        abi.check(abi.lib().sz_get_trajectory(self._h, *(p(o[k], abi.c_dp) for k in order), p(o["alive"], abi.c_bp),
+                                              *(p(o[k], abi.c_dp) for k in ("mass", "inertia", "alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p")),
+                                              p(o["stress"], abi.c_dp), p(o["flags"], abi.c_ip), p(o["cax"], abi.c_dp) if nverts else None, p(o["cay"], abi.c_dp) if nverts else None))
+        return o
+
     # ---- stand-alone clip (mex gateway semantics, private/mexclipper.cpp:204-305)
     def clip_batch(self, subjects, clips, methods):
         """subjects/clips: lists of (n,2) int64 arrays; methods: 0 dif / 1 int / 2 xor / 3 uni.

@@ -123,6 +123,10 @@ struct SzContext {
     // per-original outputs
     DBuf<double> o_fx, o_fy, o_tq, o_ov, o_stress, o_xi, o_yi; DBuf<uint8_t> o_alive; DBuf<int> o_kill, o_transfer;
     SzSummary summary;
+    // integrator state (sz_trajectory_*): calc_trajectory.m fields kept on the device between steps
+    bool have_traj = false; int traj_nz = 0;
+    DBuf<double> t_mass, t_inertia, t_alpha, t_dXi_p, t_dYi_p, t_dUi_p, t_dVi_p, t_dalpha_p, t_dksi_p, t_FxOA, t_FyOA, t_torqueOA, c0x, c0y, t_stressH, t_stress;
+    DBuf<int> t_scount, t_flags;
     // clip batch
     int clip_count = 0; i64 clip_paths = 0, clip_verts = 0;
     DBuf<int> c_method, c_status, c_path_start, c_npaths, c_path_vstart, c_path_len, c_listM, c_listL;
@@ -767,6 +771,9 @@ extern "C" void sz_destroy(SzContext* c)
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
     c->pkey.release();
+    { DBuf<double>* tb[] = {&c->t_mass, &c->t_inertia, &c->t_alpha, &c->t_dXi_p, &c->t_dYi_p, &c->t_dUi_p, &c->t_dVi_p, &c->t_dalpha_p, &c->t_dksi_p, &c->t_FxOA, &c->t_FyOA, &c->t_torqueOA,
+                          &c->c0x, &c->c0y, &c->t_stressH, &c->t_stress};
+      for (auto* b : tb) b->release(); c->t_scount.release(); c->t_flags.release(); }
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -839,7 +846,7 @@ extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f,
         if (bnd->box_n > 0) { CK(cudaMemcpyAsync(c->boxx.p, bnd->box_x, (size_t)bnd->box_n * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->boxy.p, bnd->box_y, (size_t)bnd->box_n * 8, cudaMemcpyDefault, st)); }
         c->bbody.h = bnd->h; c->bbody.area = bnd->area; c->bbody.Xi = bnd->xi; c->bbody.Yi = bnd->yi; c->bbody.Ui = bnd->u; c->bbody.Vi = bnd->v; c->bbody.ksi = bnd->ksi;
     }
-    c->prm = *prm; c->ext_mode = false;
+    c->prm = *prm; c->ext_mode = false; c->have_traj = false;
     fill_device_params(prm, (bnd && !prm->periodic) ? bnd : nullptr, c->dprm);
     c->n0 = n; c->nverts = f->nverts;
     CK(cudaStreamSynchronize(st));   // the caller may reuse its buffers
@@ -1250,10 +1257,167 @@ extern "C" int sz_contact_step(SzContext* c, const SzParams* prm, const SzFloesS
     return sz_step_resident(c, out);
 }
 
-// ------------------------------------------------------------------------------------------------ getters
 #define NEED_STEP(name) do { if (!c) { sz_set_error(name ": NULL context"); return SZ_ERR_ARG; } \
     if (!c->have_step) { sz_set_error(name ": no step has been run"); return SZ_ERR_STATE; } CK(cudaSetDevice(c->device)); } while (0)
 #define D2H(dst, src, bytes) do { if ((dst) && (bytes) > 0) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDefault, c->stream)); } while (0)
+// ------------------------------------------------------------------------------------------------ trajectory
+struct TrajArgs {
+    int n0, nz; double dt, HFo, xo_min, xo_max, yo_min, yo_max;
+    const double* cfx; const double* cfy; const double* ctq; const double* stress_now; const uint8_t* has_rows; const uint8_t* alive_step; const double* xw; const double* yw;
+    const double* area; double* x; double* y; double* u; double* v; double* ksi; double* h; uint8_t* alive;
+    double* mass; double* inertia; double* alpha; double* dXi_p; double* dYi_p; double* dUi_p; double* dVi_p; double* dalpha_p; double* dksi_p;
+    const double* FxOA; const double* FyOA; const double* torqueOA;
+    const int* voff; const double* c0x; const double* c0y; double* cax; double* cay;
+    double* stress_h; int* scount; int* flags; Counters* cnt;
+};
+// calc_trajectory.m for one floe per thread: the branch with doInt.flag = false and the ocean/atmosphere tendencies
+// FxOA, FyOA, torqueOA carried over (:3-46 stress history slot + force clamp, :67-80 thermodynamic thinning, :89,116-117
+// sacking, :170-222 second-order Adams-Bashforth update of position, heading, velocities, outline rotation).
+// flags: bit 0 sacked (the reference returns [] and the caller keeps the old struct), bit 1 would need the ocean (h < 0.1).
+__global__ void trajectory_kernel(const TrajArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n0) return;
+    a.flags[i] = 0;
+    // the contact step's per-floe results replace the inputs of the integrator (floe_interactions_all.m:152-155,267-277)
+    uint8_t alive = a.alive_step[i];
+    double X = a.xw[i], Y = a.yw[i];
+    a.alive[i] = alive; a.x[i] = X; a.y[i] = Y;
+    if (!alive) return;                                                            // :280
+    double ext_fx = a.cfx[i], ext_fy = a.cfy[i], ext_t = a.ctq[i];
+    double mass = a.mass[i], inertia = a.inertia[i], h = a.h[i];
+    int sc = a.scount[i];
+    if (sc > a.nz) sc = 1;                                                        // :15-17
+    if (h > 10) h = 10; else if (mass < 100) { mass = 1e3; alive = 0; }           // :36-41
+    while (fmax(fabs(ext_fx), fabs(ext_fy)) > mass / (5 * a.dt)) { ext_fx = ext_fx / 10; ext_fy = ext_fy / 10; ext_t = ext_t / 10; }   // :42-46
+    const double floe_area = a.area[i];
+    const double dh = a.HFo * a.dt / h;                                           // :75-79
+    const double floe_mass = (h - dh) / h * mass, floe_inertia = (h - dh) / h * inertia;
+    const double h_new = h - dh;
+    bool sack = (X != X);                                                         // :89
+    if (!sack && h_new < 0.1) { a.flags[i] = 2; atomicAdd(&a.cnt->n_fail, 1); return; }
+    if (!sack) {
+        double cmaxx = -SZ_INF, cminx = SZ_INF, cmaxy = -SZ_INF, cminy = SZ_INF;
+        for (int t = a.voff[i]; t < a.voff[i + 1]; ++t) { cmaxx = fmax(cmaxx, a.cax[t]); cminx = fmin(cminx, a.cax[t]); cmaxy = fmax(cmaxy, a.cay[t]); cminy = fmin(cminy, a.cay[t]); }
+        sack = (cmaxx + X > a.xo_max || cminx + X < a.xo_min || cmaxy + Y > a.yo_max || cminy + Y < a.yo_min);   // :116-117
+    }
+    if (sack) { a.flags[i] = 1; atomicAdd(&a.cnt->n_cap_fail, 1); return; }       // state untouched, like the caller's `kill(i) = i`
+    // commit: stress history slot (:18-19), clamps, thinning
+    double* slot = a.stress_h + ((size_t)i * a.nz + (sc - 1)) * 4;
+    for (int k = 0; k < 4; ++k) slot[k] = a.has_rows[i] ? a.stress_now[(size_t)i * 4 + k] : 0.0;
+    a.scount[i] = sc + 1;
+    a.mass[i] = floe_mass; a.inertia[i] = floe_inertia; a.h[i] = h_new; a.alive[i] = alive;
+    if (alive != 1) return;                                                       // :118
+    const double dt = a.dt, U = a.u[i], V = a.v[i], K = a.ksi[i];
+    a.x[i] = X + (1.5 * dt * U - 0.5 * dt * a.dXi_p[i]); a.dXi_p[i] = U;          // :174-176
+    a.y[i] = Y + (1.5 * dt * V - 0.5 * dt * a.dYi_p[i]); a.dYi_p[i] = V;
+    const double alpha = a.alpha[i] + 1.5 * dt * K - 0.5 * dt * a.dalpha_p[i];     // :177
+    a.alpha[i] = alpha; a.dalpha_p[i] = K;
+    const double ax0 = a.FxOA[i] * floe_area + ext_fx, ay0 = a.FyOA[i] * floe_area + ext_fy;   // :181-182
+    double dU = ax0 / floe_mass, dV = ay0 / floe_mass;
+    bool have_frac = false; double frac = 0;
+    const double lim = 0.5 * h_new;
+    if (fabs(dt * dU) > lim && fabs(dt * dV) > lim) {                             // :184-191
+        dU = sgn_d(dU) * 0.5 * h_new / dt; dV = sgn_d(dV) * 0.5 * h_new / dt;
+        const double f1 = dU / ax0 * floe_mass, f2 = dV / ay0 * floe_mass;
+        frac = f1 < f2 ? f1 : f2; have_frac = true;
+        dU = ax0 / floe_mass; dV = ay0 / floe_mass; dU = frac * dU; dV = frac * dV;
+    } else if (fabs(dt * dU) > lim && fabs(dt * dV) < lim) {                      // :192-197
+        dU = sgn_d(dU) * 0.5 * h_new / dt;
+        frac = dU / ax0 * floe_mass; have_frac = true;
+        dU = ax0 / floe_mass; dV = ay0 / floe_mass; dU = frac * dU; dV = frac * dV;
+    } else if (fabs(dt * dU) < lim && fabs(dt * dV) > lim) {                      // :198-203
+        dV = sgn_d(dV) * 0.5 * h_new / dt;
+        frac = dV / ay0 * floe_mass; have_frac = true;
+        dU = ax0 / floe_mass; dV = ay0 / floe_mass; dU = frac * dU; dV = frac * dV;
+    }
+    a.u[i] = U + 1.5 * dt * dU - 0.5 * dt * a.dUi_p[i];                           // :204-207
+    a.v[i] = V + 1.5 * dt * dV - 0.5 * dt * a.dVi_p[i];
+    a.dUi_p[i] = dU; a.dVi_p[i] = dV;
+    double dksi = (a.torqueOA[i] * floe_area + ext_t) / floe_inertia;             // :209-219
+    if (have_frac) dksi = frac * dksi;
+    double k2 = K + 1.5 * dt * dksi - 0.5 * dt * a.dksi_p[i];
+    if (fabs(k2) > 1e-5) k2 = sgn_d(k2) * 1e-5;
+    a.ksi[i] = k2; a.dksi_p[i] = dksi;
+    const double ca = cos(alpha), sa = sin(alpha);                                // :221-222
+    for (int t = a.voff[i]; t < a.voff[i + 1]; ++t) { const double px = a.c0x[t], py = a.c0y[t]; a.cax[t] = ca * px + (-sa) * py; a.cay[t] = sa * px + ca * py; }
+}
+// floe.Stress = mean(StressH, 3) (calc_trajectory.m:20,28), evaluated when asked for
+__global__ void stress_mean_kernel(int n0, int nz, const double* __restrict__ stress_h, double* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n0 * 4) return;
+    const int i = t >> 2, k = t & 3;
+    double sm = 0;
+    for (int z = 0; z < nz; ++z) sm += stress_h[((size_t)i * nz + z) * 4 + k];
+    out[t] = sm / nz;
+}
+
+extern "C" int sz_trajectory_init(SzContext* c, const SzTrajectoryInit* in)
+{
+    if (!c || !in) { sz_set_error("sz_trajectory_init: NULL argument"); return SZ_ERR_ARG; }
+    if (!c->have_input || c->ext_mode) { sz_set_error("sz_trajectory_init: upload the floes first (single-GPU list)"); return SZ_ERR_STATE; }
+    if (in->nz < 1 || !in->mass || !in->inertia) { sz_set_error("sz_trajectory_init: mass, inertia and nz >= 1 are required"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n0, nv = (size_t)c->nverts; cudaStream_t st = c->stream;
+    struct { DBuf<double>* b; const double* src; } arr[] = {{&c->t_mass, in->mass}, {&c->t_inertia, in->inertia}, {&c->t_alpha, in->alpha}, {&c->t_dXi_p, in->dXi_p}, {&c->t_dYi_p, in->dYi_p},
+        {&c->t_dUi_p, in->dUi_p}, {&c->t_dVi_p, in->dVi_p}, {&c->t_dalpha_p, in->dalpha_p}, {&c->t_dksi_p, in->dksi_p}, {&c->t_FxOA, in->FxOA}, {&c->t_FyOA, in->FyOA}, {&c->t_torqueOA, in->torqueOA}};
+    for (auto& a : arr) {
+        CK(a.b->ensure(n + 1));
+        if (a.src) CK(cudaMemcpyAsync(a.b->p, a.src, n * 8, cudaMemcpyDefault, st)); else CK(cudaMemsetAsync(a.b->p, 0, n * 8, st));
+    }
+    CK(c->c0x.ensure(nv + 1)); CK(c->c0y.ensure(nv + 1));
+    // c0 = the unrotated outline (initialize_floe_values.m:18); default: the current c_alpha, i.e. alpha_i = 0
+    CK(cudaMemcpyAsync(c->c0x.p, in->c0x ? in->c0x : c->vx.p, nv * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->c0y.p, in->c0y ? in->c0y : c->vy.p, nv * 8, cudaMemcpyDefault, st));
+    CK(c->t_stressH.ensure(n * (size_t)in->nz * 4 + 4)); CK(c->t_stress.ensure(n * 4 + 4)); CK(c->t_scount.ensure(n + 1)); CK(c->t_flags.ensure(n + 1));
+    CK(cudaMemsetAsync(c->t_stressH.p, 0, n * (size_t)in->nz * 32, st));            // StressH = zeros(2,2,1000), StressCount = 1 (:24-25)
+    { std::vector<int> ones(n, 1); CK(cudaMemcpyAsync(c->t_scount.p, ones.data(), n * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st)); }
+    CK(cudaMemsetAsync(c->t_flags.p, 0, n * 4, st));
+    CK(cudaStreamSynchronize(st));
+    c->traj_nz = in->nz; c->have_traj = true;
+    return SZ_OK;
+}
+extern "C" int sz_trajectory_step(SzContext* c, const SzTrajectoryParams* p, int32_t* n_sacked, int32_t* n_needs_ocean)
+{
+    if (!c || !p) { sz_set_error("sz_trajectory_step: NULL argument"); return SZ_ERR_ARG; }
+    if (!c->have_traj || !c->have_step || c->ext_mode) { sz_set_error("sz_trajectory_step: needs sz_trajectory_init and a contact step"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const int n0 = c->n0;
+    CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
+    TrajArgs a; memset(&a, 0, sizeof(a));
+    a.n0 = n0; a.nz = c->traj_nz; a.dt = p->dt; a.HFo = p->HFo; a.xo_min = p->xo_min; a.xo_max = p->xo_max; a.yo_min = p->yo_min; a.yo_max = p->yo_max;
+    a.cfx = c->o_fx.p; a.cfy = c->o_fy.p; a.ctq = c->o_tq.p; a.stress_now = c->o_stress.p; a.has_rows = c->has_rows.p; a.alive_step = c->o_alive.p; a.xw = c->o_xi.p; a.yw = c->o_yi.p;
+    a.area = c->area.p; a.x = c->x.p; a.y = c->y.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.h = c->h.p; a.alive = c->alive.p;
+    a.mass = c->t_mass.p; a.inertia = c->t_inertia.p; a.alpha = c->t_alpha.p; a.dXi_p = c->t_dXi_p.p; a.dYi_p = c->t_dYi_p.p; a.dUi_p = c->t_dUi_p.p; a.dVi_p = c->t_dVi_p.p;
+    a.dalpha_p = c->t_dalpha_p.p; a.dksi_p = c->t_dksi_p.p; a.FxOA = c->t_FxOA.p; a.FyOA = c->t_FyOA.p; a.torqueOA = c->t_torqueOA.p;
+    a.voff = c->voff.p; a.c0x = c->c0x.p; a.c0y = c->c0y.p; a.cax = c->vx.p; a.cay = c->vy.p;
+    a.stress_h = c->t_stressH.p; a.scount = c->t_scount.p; a.flags = c->t_flags.p; a.cnt = c->d_cnt;
+    if (n0 > 0) { ++g_launches; trajectory_kernel<<<nblk(n0, 128), 128, 0, st>>>(a); }
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    c->have_step = false;            // the contact results belong to the previous positions now
+    if (n_sacked) *n_sacked = c->h_cnt->n_cap_fail;
+    if (n_needs_ocean) *n_needs_ocean = c->h_cnt->n_fail;
+    if (c->h_cnt->n_fail > 0) { sz_set_error("%d floe(s) thinner than 0.1 m need the ocean forcing re-evaluated (calc_trajectory.m:94): not part of this path", c->h_cnt->n_fail); return SZ_ERR_STATE; }
+    return SZ_OK;
+}
+extern "C" int sz_get_trajectory(SzContext* c, double* x, double* y, double* u, double* v, double* ksi, double* h, uint8_t* alive, double* mass, double* inertia, double* alpha,
+                                 double* dXi_p, double* dYi_p, double* dUi_p, double* dVi_p, double* dalpha_p, double* dksi_p, double* stress, int32_t* flags, double* cax, double* cay)
+{
+    if (!c) { sz_set_error("sz_get_trajectory: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_traj) { sz_set_error("sz_get_trajectory: no integrator state"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n0, nv = (size_t)c->nverts;
+    if (stress && n) { ++g_launches; stress_mean_kernel<<<nblk(4 * (i64)n, 256), 256, 0, c->stream>>>((int)n, c->traj_nz, c->t_stressH.p, c->t_stress.p); }
+    D2H(x, c->x.p, n * 8); D2H(y, c->y.p, n * 8); D2H(u, c->u.p, n * 8); D2H(v, c->v.p, n * 8); D2H(ksi, c->ksi.p, n * 8); D2H(h, c->h.p, n * 8); D2H(alive, c->alive.p, n);
+    D2H(mass, c->t_mass.p, n * 8); D2H(inertia, c->t_inertia.p, n * 8); D2H(alpha, c->t_alpha.p, n * 8); D2H(dXi_p, c->t_dXi_p.p, n * 8); D2H(dYi_p, c->t_dYi_p.p, n * 8);
+    D2H(dUi_p, c->t_dUi_p.p, n * 8); D2H(dVi_p, c->t_dVi_p.p, n * 8); D2H(dalpha_p, c->t_dalpha_p.p, n * 8); D2H(dksi_p, c->t_dksi_p.p, n * 8);
+    D2H(stress, c->t_stress.p, n * 32); D2H(flags, c->t_flags.p, n * 4); D2H(cax, c->vx.p, nv * 8); D2H(cay, c->vy.p, nv * 8);
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ getters
 
 extern "C" int sz_get_floe_outputs(SzContext* c, double* fx, double* fy, double* torque, double* overlap_area, double* stress,
                                    double* xi, double* yi, uint8_t* alive, int32_t* kill, int32_t* transfer)

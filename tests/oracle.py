@@ -59,6 +59,9 @@ def lib():
         l.szo_floe_interactions.argtypes = [C.POINTER(abi.SzParams), abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, C.c_int,
                                             abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, C.c_int, abi.c_dp]
         l.szo_hardware_threads.restype = C.c_int
+        l.szo_calc_trajectory.restype = None
+        l.szo_calc_trajectory.argtypes = [C.c_int] + [C.c_double] * 6 + [C.c_int] + [abi.c_dp] * 4 + [abi.c_bp] + [abi.c_dp] * 7 + [abi.c_bp] + [abi.c_dp] * 12 + [
+            abi.c_ip] + [abi.c_dp] * 4 + [abi.c_dp, abi.c_ip, abi.c_dp, abi.c_bp, abi.c_bp]
         _lib = l
     return _lib
 
@@ -153,6 +156,26 @@ class OracleStep:
         p = abi._ptr
         lib().szo_get_clip_polys(self._r, p(ppo, abi.c_lp), p(pvo, abi.c_lp), p(x, abi.c_lp), p(y, abi.c_lp))
         return ppo, pvo, x, y
+
+
+def calc_trajectory(step, floes, state, dt, HFo=0.0, bounds=(-np.inf, np.inf, -np.inf, np.inf), nz=1000):
+    """the oracle's calc_trajectory restatement applied after an oracle contact step.  `state`: dict of per-floe arrays
+    (mass inertia alpha dXi_p dYi_p dUi_p dVi_p dalpha_p dksi_p FxOA FyOA torqueOA, c0x c0y, stress_h [n,nz,4],
+    stress_count, stress); floes: the FloesSoA the step ran on.  Everything is advanced in place; returns (sacked, unsupported)."""
+    o = step.floe_outputs()
+    off, _ = step.rows()
+    n = floes.n
+    has_rows = np.ascontiguousarray((off[1:n + 1] - off[:n]) > 0, np.uint8)
+    floes.x[:], floes.y[:], floes.alive[:] = o["xi"], o["yi"], o["alive"]
+    sacked, unsup = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    cfx, cfy, ctq, st = (np.ascontiguousarray(o[k]) for k in ("fx", "fy", "torque", "stress"))
+    p, D, B, I = abi._ptr, abi.c_dp, abi.c_bp, abi.c_ip
+    lib().szo_calc_trajectory(n, float(dt), float(HFo), *(float(b) for b in bounds), int(nz), p(cfx, D), p(cfy, D), p(ctq, D), p(st, D), p(has_rows, B),
+                              p(floes.area, D), p(floes.x, D), p(floes.y, D), p(floes.u, D), p(floes.v, D), p(floes.ksi, D), p(floes.h, D), p(floes.alive, B),
+                              *(p(state[k], D) for k in ("mass", "inertia", "alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p", "FxOA", "FyOA", "torqueOA")),
+                              p(floes.voff, I), p(state["c0x"], D), p(state["c0y"], D), p(floes.vx, D), p(floes.vy, D),
+                              p(state["stress_h"], D), p(state["stress_count"], I), p(state["stress"], D), p(sacked, B), p(unsup, B))
+    return sacked, unsup
 
 
 def _rel_err(a, b):
