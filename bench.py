@@ -232,6 +232,23 @@ def main():
     e2e_ms = float(te.item())
     e2e_value = total_pairs / (e2e_ms * 1e-3)
 
+    # ---- timesteps/s with the integrator half of the step on the device (contact step + calc_trajectory, N = 1)
+    ts_with_ab2 = None
+    if world == 1:
+        rho_ice = 920.0
+        mass = floes.area * floes.h * rho_ice
+        job.ctx.trajectory_init(mass, mass * floes.rmax ** 2 / 4, nz=1000)
+        for _ in range(2):
+            job.ctx.step_resident()
+            job.ctx.trajectory_step(prm.dt)
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        nts = max(3, min(args.steps, 10))
+        for _ in range(nts):
+            job.ctx.step_resident()
+            job.ctx.trajectory_step(prm.dt)
+        torch.cuda.synchronize()
+        ts_with_ab2 = nts / (time.perf_counter() - w0)
     if rank == 0:
         peak, peak_src = load_peaks()
         alg_bytes = algorithmic_bytes(floes, job.summary)          # rank 0's launch: its pairs and rows
@@ -249,7 +266,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes,
                            "floes_incl_ghosts": total_ext, "pairs_per_step": total_pairs, "pairs_with_force": total_force,
-                           "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "parallelism": job.describe(),
+                           "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "timesteps_per_s_with_trajectory_update": ts_with_ab2, "parallelism": job.describe(),
                            "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed,
                            "wall_ms_per_step": wall_ms / args.steps},
                 "clocks": clocks,
