@@ -218,3 +218,27 @@ def test_full_size_properties_100k(ctx):
     assert abs(rows[:, 1].sum()) < 1e-9 * scale and abs(rows[:, 2].sum()) < 1e-9 * scale
     assert np.all(np.diff(off) >= 0) and off[-1] == s.n_rows
     assert s.collision_count <= s.n_rows / 2
+
+
+def test_full_benchmark_size_1m_floes(ctx):
+    """BASELINE.json's headline size (bench.py's field: 1M floes, seed 0): size-independent properties -- Newton's third
+    law over the periodic field, row bookkeeping, run-to-run determinism -- and, since the oracle finishes it in seconds on
+    the host cores, the complete comparison as well: 4.5M candidate pairs, 6.1M contact rows, every per-floe output"""
+    prm, soa = sz.voronoi_field(1000000, seed=0)
+    prm.want_clip_polys = 0
+    s = ctx.step(prm, soa)
+    assert s.n_pairs > 4.4e6 and s.n_pairs_force > 2.9e6 and s.n_capacity_fail == 0 and s.n_clipper_fail == 0
+    off, rows = ctx.rows()
+    out = ctx.floe_outputs()
+    scale = np.abs(rows[:, 1:3]).sum()
+    assert abs(rows[:, 1].sum()) < 1e-9 * scale and abs(rows[:, 2].sum()) < 1e-9 * scale         # every mirrored row cancels its source
+    assert rows.shape[0] == s.n_rows and off[-1] == s.n_rows and np.all(np.diff(off) >= 0)
+    assert s.collision_count * 2 == np.isfinite(rows[:off[s.n0], 0]).sum()
+    ctx.upload(prm, soa)
+    ctx.step_resident()
+    off2, rows2 = ctx.rows()
+    assert np.array_equal(off, off2) and np.array_equal(rows, rows2)                                 # deterministic, row for row
+    del rows2, off2
+    ref = oracle.OracleStep(prm, soa, broad_mode=1)
+    rep = oracle.compare_steps(ctx, ref, rtol=RTOL, check_polys=False)
+    assert rep["rows_bit_exact"] and rep["fx_bit_exact"] and rep["torque_bit_exact"] and rep["stress_bit_exact"]
