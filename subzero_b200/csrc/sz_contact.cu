@@ -75,7 +75,7 @@ struct Counters {
     int n1, n;                     // extended-list sizes after the x pass / after the y pass
     int n_pairs;
     int row_used, path_used, vert_used;
-    int listS, listT, listM, listL, wlistT, wlistM, wlistL;
+    int listC, listS, listT, listM, listL, wlistT, wlistM, wlistL;
     int total_rows;
     int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject;
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
@@ -109,7 +109,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
+    DBuf<int> listC, listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -454,20 +454,25 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
                                      const uint8_t* __restrict__ evalid, const int* __restrict__ env, const uint8_t* __restrict__ eno, const int* __restrict__ esrc,
                                      const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
-                                     int* __restrict__ listS, const double* __restrict__ ex, const double* __restrict__ ey,
+                                     int* __restrict__ listC, int* __restrict__ listS, const double* __restrict__ ex, const double* __restrict__ ey,
                                      int* __restrict__ bins, int* __restrict__ bin_fill, short* __restrict__ pkey, Counters* c)
 {
+    // per bucket: pairs of strictly convex outlines (class C) in the high half-word, the others (class S) in the low one
     __shared__ int sh[SZ_NBINS];
     for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) sh[t] = 0;
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int key = -1, slot = 0;
-    if (p < np && pass == 1) { key = pkey[p]; if (key >= 0) slot = atomicAdd(&sh[key], 1); }
+    int key = -1, slot = 0; bool cvx = false;
+    if (p < np && pass == 1) {
+        key = pkey[p];
+        if (key >= 0) { cvx = (key & SZ_NBINS) != 0; key &= SZ_NBINS - 1; const int old = atomicAdd(&sh[key], cvx ? 65536 : 1); slot = cvx ? (old >> 16) : (old & 0xffff); }
+    }
     if (p < np && pass == 0) {
         const int i = pi[p], j = pj[p];
         const i64* a = ebb + (size_t)i * 4; const i64* b = ebb + (size_t)j * 4;
         bool disjoint = evalid[i] && evalid[j] && (a[1] < b[0] || b[1] < a[0] || a[3] < b[2] || b[3] < a[2]);
-        if (!disjoint && eno[i] >= 3 && eno[j] >= 3)         // both strictly convex (eno is 0 otherwise)
+        cvx = eno[i] >= 3 && eno[j] >= 3;                    // both strictly convex (eno is 0 otherwise)
+        if (!disjoint && cvx)
             disjoint = sat_separated(vx, vy, voff[esrc[i]], eno[i], ex[i], ey[i], voff[esrc[j]], eno[j], ex[j], ey[j]);
         if (disjoint) {
             status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0;
@@ -478,26 +483,36 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
             const double adx = fabs(dx), ady = fabs(dy), mn = adx < ady ? adx : ady, mx = adx < ady ? ady : adx;
             const int oct = (dx > 0) | ((dy > 0) << 1) | ((adx > ady) << 2) | ((mn > 0.41421356237309503 * mx) << 3);
             key = (ni * SZ_BIN_N + nj) * SZ_NSECT + oct;
-            slot = atomicAdd(&sh[key], 1);
+            atomicAdd(&sh[key], cvx ? 65536 : 1);
         }
-        pkey[p] = (short)key;
+        pkey[p] = (short)(key < 0 ? key : (key | (cvx ? SZ_NBINS : 0)));
     }
     __syncthreads();
     if (pass == 0) {
-        for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) if (sh[t]) atomicAdd(&bins[t], sh[t]);
+        for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) {
+            const int v = sh[t];
+            if (v >> 16) atomicAdd(&bins[t], v >> 16);
+            if (v & 0xffff) atomicAdd(&bins[SZ_NBINS + t], v & 0xffff);
+        }
         return;
     }
-    // pass 1: bins[] holds exclusive offsets; reserve this CTA's share of every bucket, then place
+    // pass 1: bins[] holds exclusive offsets (class C buckets, then class S buckets); reserve this CTA's share of every
+    // bucket, then place -- class C first, then class S through the same shared array
     __shared__ int base[SZ_NBINS];
-    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) base[t] = sh[t] ? atomicAdd(&bin_fill[t], sh[t]) : 0;
+    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) base[t] = (sh[t] >> 16) ? atomicAdd(&bin_fill[t], sh[t] >> 16) : 0;
     __syncthreads();
-    if (key >= 0) listS[bins[key] + base[key] + slot] = p;
+    if (key >= 0 && cvx) listC[bins[key] + base[key] + slot] = p;
+    __syncthreads();
+    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) base[t] = (sh[t] & 0xffff) ? atomicAdd(&bin_fill[SZ_NBINS + t], sh[t] & 0xffff) : 0;
+    __syncthreads();
+    if (key >= 0 && !cvx) listS[bins[SZ_NBINS + key] + base[key] + slot] = p;
 }
 // Exclusive offsets of the buckets in launch order: longest outlines first (the CTAs with the longest sweeps start
 // first, which shortens the tail of the launch).  One thread per (n1, n2) combination; its rank in the order
 // "n1 + n2 descending, n1 descending" is closed-form, a 256-wide shared-memory scan does the rest.
 __global__ void __launch_bounds__(SZ_BIN_N * SZ_BIN_N) bins_scan_kernel(Counters* c, int np, int* __restrict__ bins, int* __restrict__ bin_fill)
 {
+    bins += blockIdx.x * SZ_NBINS; bin_fill += blockIdx.x * SZ_NBINS;      // block 0: class C buckets, block 1: class S buckets
     const int B = SZ_BIN_N, t = threadIdx.x, ni = t / B, nj = t % B, sum = ni + nj;
     __shared__ int tot[SZ_BIN_N * SZ_BIN_N], scan[SZ_BIN_N * SZ_BIN_N];
     int before = (sum < B - 1 ? sum : B - 1) - ni;                       // same sum, larger n1
@@ -511,7 +526,10 @@ __global__ void __launch_bounds__(SZ_BIN_N * SZ_BIN_N) bins_scan_kernel(Counters
     for (int d = 1; d < B * B; d <<= 1) { const int v = (t >= d) ? scan[t - d] : 0; __syncthreads(); scan[t] += v; __syncthreads(); }
     int base = scan[before] - mine;                                       // exclusive
     for (int oct = 0; oct < SZ_NSECT; ++oct) { const int k = t * SZ_NSECT + oct; const int v = bins[k]; bins[k] = base; base += v; bin_fill[k] = 0; }
-    if (t == 0) { c->listS = scan[B * B - 1]; c->n_bbox_reject = np - scan[B * B - 1]; }
+    if (t == 0) {
+        if (blockIdx.x == 0) { c->listC = scan[B * B - 1]; atomicAdd(&c->n_bbox_reject, np - scan[B * B - 1]); }
+        else { c->listS = scan[B * B - 1]; atomicAdd(&c->n_bbox_reject, -scan[B * B - 1]); }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K4 assembly
@@ -761,7 +779,7 @@ extern "C" void sz_destroy(SzContext* c)
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
-                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
+                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
@@ -995,15 +1013,21 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     a.next_list = lstT; a.next_count = cntT;
     if (!wall) {
         // work list of class S: bounding-box-disjoint pairs answered, the rest bucketed by vertex counts and direction
-        CK(c->bins.ensure(SZ_NBINS)); CK(c->bin_fill.ensure(SZ_NBINS));
-        CK(cudaMemsetAsync(c->bins.p, 0, SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, SZ_NBINS * sizeof(int), st));
+        CK(c->bins.ensure(2 * SZ_NBINS)); CK(c->bin_fill.ensure(2 * SZ_NBINS));
+        CK(cudaMemsetAsync(c->bins.p, 0, 2 * SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, 2 * SZ_NBINS * sizeof(int), st));
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
-        bins_scan_kernel<<<1, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
+        bins_scan_kernel<<<2, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
         g_launches += 3;
-        a.list = c->listS.p; a.list_count = D_CNT(listS);
+        // class C: strictly convex pairs through the four-edge sweep; what it declines is appended to class S's list.
+        // Both launches are sized for all pairs (the list lengths are only known on the device; surplus CTAs exit at once).
+        static const bool no_fast = getenv("SZ_CONVEX_FAST") == nullptr;      // class C is opt-in until it beats class S on the benchmark field
+        a.list = c->listC.p; a.list_count = D_CNT(listC); a.next_list = c->listS.p; a.next_count = D_CNT(listS);
+        if (!no_fast) { ++g_launches; sz_launch_narrow_C(&a, st); CK(cudaGetLastError()); }
+        else { a.list = c->listC.p; a.next_list = lstT; a.next_count = cntT; ++g_launches; sz_launch_narrow_S(&a, st); CK(cudaGetLastError()); }
+        a.list = c->listS.p; a.list_count = D_CNT(listS); a.next_list = lstT; a.next_count = cntT;
     }
     ++g_launches; sz_launch_narrow_S(&a, st);
     a.list = nullptr; a.list_count = nullptr;
@@ -1154,7 +1178,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
-    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
+    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
     if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p); }
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
@@ -1166,7 +1190,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     }
     for (int attempt = 0; attempt < 3; ++attempt) {
         Counters z = *c->h_cnt;
-        z.row_used = z.path_used = z.vert_used = z.listS = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
+        z.row_used = z.path_used = z.vert_used = z.n_bbox_reject = z.listC = z.listS = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
 
         *c->h_cnt = z;
         CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));

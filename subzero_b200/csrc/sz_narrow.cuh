@@ -89,8 +89,8 @@ struct SizeSink { int paths, verts; SZ_HD void begin_path(int c) { ++paths; vert
 
 // All 32 lanes of a warp call this together (szpf::pair_force is warp-synchronous); `valid` says whether
 // the lane has a pair.
-template <class C>
-__device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool valid, szpf::Workspace<C>& w)
+template <class C, bool FAST, class W>
+__device__ __forceinline__ void resolve_pair_impl(const NarrowArgs& a, int k, bool valid, W& w)
 {
     int i = 0, j = -1;
     Body b1, b2;
@@ -123,8 +123,9 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
     }
     szpf::PairResult res;
     double rows[C::ROWS * 5];
-    szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid, hints);
-    if (valid && res.status == szpf::PS_CAPACITY && a.next_list) { escalate = true; valid = false; }
+    if constexpr (FAST) szpf::pair_force_convex<C>(w, b1, b2, a.P, res, rows, valid, hints);
+    else szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid, hints);
+    if (valid && (res.status == szpf::PS_CAPACITY || res.status == szpf::PS_BAIL) && a.next_list) { escalate = true; valid = false; }
     if (escalate) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
     if (!valid) return;
     a.status[k] = res.status; a.ovl_state[k] = res.overlap_state;
@@ -148,6 +149,27 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
             }
         }
     }
+}
+
+template <class C>
+__device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool valid, szpf::Workspace<C>& w) { resolve_pair_impl<C, false>(a, k, valid, w); }
+
+// class C (convex fast path): strictly convex floe-floe pairs, clip #1 by the four-edge sweep of sz_convex.cuh, sign
+// test by its margin certificate; no arena.  A pair the fast path declines is appended to class S's list.
+#ifndef SZ_C_TPB
+#define SZ_C_TPB 256
+#endif
+#ifndef SZ_C_MINB
+#define SZ_C_MINB 2
+#endif
+template <class C>
+__global__ void __launch_bounds__(SZ_C_TPB, SZ_C_MINB) narrow_convex_kernel(const NarrowArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *a.list_count;
+    if ((t & ~31) >= n) return;                          // whole warp beyond the list
+    szpf::WorkspaceLite<C> w;
+    resolve_pair_impl<C, true>(a, t < n ? a.list[t] : 0, t < n, w);
 }
 
 // class S launch shape: two 512-thread CTAs per SM (64 registers per thread).  With SZ_BLOCK_SYNC (default) all
@@ -236,6 +258,7 @@ __global__ void __launch_bounds__(64) clip_scratch_kernel(const ClipArgs a)
 
 // launchers (one translation unit per class); all asynchronous on `stream`
 extern "C" {
+void sz_launch_narrow_C(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_S(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_T(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_M(const sznarrow::NarrowArgs* a, cudaStream_t stream);

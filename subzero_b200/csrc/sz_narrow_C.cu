@@ -1,0 +1,9 @@
+// class C instantiation of the narrow phase (see sz_narrow.cuh): strictly convex pairs, no arena
+#include "sz_narrow.cuh"
+using namespace sznarrow;
+extern "C" void sz_launch_narrow_C(const NarrowArgs* a, cudaStream_t stream)
+{
+    if (a->n_work <= 0) return;
+    const int tpb = SZ_C_TPB;
+    narrow_convex_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
+}

@@ -16,6 +16,7 @@
 //   p_poly_dist / inpolygon         polygon_operations/p_poly_dist.m:111-288, inpolygon.m:150-224
 #pragma once
 #include "sz_clip.cuh"
+#include "sz_convex.cuh"
 
 namespace szpf {
 
@@ -36,7 +37,8 @@ struct Params {            // device copy of SzParams (include/subzero_b200.h)
 
 struct Body { double h, area, Xi, Yi, Ui, Vi, ksi; };   // the fields of floe1 / floe2 the law reads
 
-enum PairStatus { PS_OK = 0, PS_CLIPPER_FAIL = -3 /* SZ_ERR_CLIPPER */, PS_CAPACITY = -4 /* SZ_ERR_CAPACITY */, PS_BAD_POLY = -1 /* SZ_ERR_ARG */ };
+enum PairStatus { PS_OK = 0, PS_CLIPPER_FAIL = -3 /* SZ_ERR_CLIPPER */, PS_CAPACITY = -4 /* SZ_ERR_CAPACITY */, PS_BAD_POLY = -1 /* SZ_ERR_ARG */,
+                  PS_BAIL = -7 /* internal: the convex fast path declined the pair, re-run it with the general sweep */ };
 
 // Per-pair hints computed once per floe (ext_prep_kernel / the host test shim).  convex: both outlines are strictly
 // convex in Clipper's coordinates.  For convex outlines the sweep is fed the OPEN ring (no1/no2 vertices, closing
@@ -78,6 +80,18 @@ struct Workspace {
     double px[C::NP], py[C::NP]; int np;                          // InterX points
 };
 
+// The same buffers without the general sweep's arena: workspace of the convex fast path (sz_convex.cuh), whose
+// sweep state is a few hundred bytes of its own.
+template <class C>
+struct WorkspaceLite {
+    double c1x[C::NV], c1y[C::NV], c2x[C::NV], c2y[C::NV];
+    int n1, n2;
+    i64 rax[C::RV], ray[C::RV]; int ra_off[C::RP + 1]; int ra_n;
+    double ar[C::RP];
+    i64 rbx[C::RV], rby[C::RV]; int rb_off[C::RP + 1]; int rb_n;
+    double px[C::NP], py[C::NP]; int np;
+};
+
 // ------------------------------------------------------------------------------------------------
 template <class C>
 struct RegionSink {       // collects emitted paths into (x,y,off) pools; flags overflow
@@ -96,6 +110,12 @@ struct CountSink { int n; SZ_HD void begin_path(int) { ++n; } SZ_HD void point(P
 // valid = false).  On the host the macros collapse and the same code handles one pair.
 #if !defined(SZ_WARP_SYNC_ONLY)
 #define SZ_BLOCK_SYNC 1
+#endif
+// the convex fast path has no per-scanbeam phases to share: its lanes only vote warp-wide on the loop exit
+#if defined(__CUDA_ARCH__)
+#define SZ_FAST_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define SZ_FAST_ANY(p) (p)
 #endif
 #if defined(__CUDA_ARCH__) && defined(SZ_BLOCK_SYNC)
 // block-synchronous variant: every warp of the CTA walks the phases together, so the instruction lines of a
@@ -332,8 +352,8 @@ SZ_HD int convex_sign_test(W& w, double fdx, double fdy, const i64* RX, const i6
 }
 
 // InterX.m:54-77 (two-curve form).  Points are collected, sorted (x, then y) and de-duplicated.
-template <class C>
-SZ_HD bool interx(Workspace<C>& w)
+template <class C, class W>
+SZ_HD bool interx(W& w)
 {
     const int n1 = w.n1 - 1, n2 = w.n2 - 1;
     int np = 0;
@@ -402,8 +422,8 @@ SZ_HD bool in_region(double x, double y, const i64* X, const i64* Y, int n, doub
 
 // |p_poly_dist(x,y, c1)|: unsigned distance from one point to the closed outline c1 (n1 points,
 // first == last).  Returns <0 when the reference would raise (repeated vertices / flat polygon).
-template <class C>
-SZ_HD double abs_poly_dist(const Workspace<C>& w, double xq, double yq)
+template <class W>
+SZ_HD double abs_poly_dist(const W& w, double xq, double yq)
 {
     const int nv = w.n1, ns = nv - 1;
     double dpv_min = SZ_INF; int i_dpv = 0;
@@ -425,8 +445,8 @@ SZ_HD double abs_poly_dist(const Workspace<C>& w, double xq, double yq)
     bool is_vertex = !have || ((i_cr != i_dpv) && (cr_min - dpv_min) > 0);
     return is_vertex ? dpv_min : cr_min;
 }
-template <class C>
-SZ_HD bool outline_ok_for_poly_dist(const Workspace<C>& w)   // p_poly_dist.m:166-179
+template <class W>
+SZ_HD bool outline_ok_for_poly_dist(const W& w)   // p_poly_dist.m:166-179
 {
     const int ns = w.n1 - 1;
     if (w.n1 < 3) return false;
@@ -470,8 +490,12 @@ SZ_HD void force_row(const Body& f1, const Body& f2, const Params& P, double G, 
 //   PH_CLIP3  clip #3.. (:158)         -> one per new region: does it meet region k?  (toggles the sign)
 // After the last clip of a region its force row is written (:167-187) and the next region's contact
 // direction (:96-150) is prepared.
-template <class C>
-SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true, PairHints hints = PairHints{false, 0, 0, 0, 0})
+//
+// FAST = true is the convex fast path (class C): clip #1 of a strictly convex pair runs in the specialised sweep of
+// sz_convex.cuh, and the sign test must be decided by convex_sign_test; whenever either declines, the pair ends with
+// PS_BAIL and the caller re-runs it with FAST = false.  Everything between the clips is the same code.
+template <class C, bool FAST, class W>
+SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid, PairHints hints)
 {
     enum { PH_CLIP1 = 0, PH_CLIP2 = 1, PH_CLIP3 = 2, PH_DONE = 3, PH_NEXT = 4 };
     res.status = PS_OK; res.n_rows = 0; res.overlap_state = 0;
@@ -499,7 +523,7 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
     // `continue`): the lanes of a warp resolve different pairs, and a block that one lane leaves early must not make
     // the others run the rest of the body one lane at a time (first profile: InterX ran with 1.2 of 32 lanes active).
     for (;;) {
-        if (!SZ_WARP_ANY(phase != PH_DONE)) break;
+        if (!(FAST ? SZ_FAST_ANY(phase != PH_DONE) : SZ_WARP_ANY(phase != PH_DONE))) break;
         // ---- the clip this lane needs now
         ClipInput subj, clip;
         subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = w.n1; subj.ring = 0; subj.rot = 0;
@@ -512,7 +536,15 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             clip.ring = 1; clip.ix = RX; clip.iy = RY; clip.n = nr; clip.rot = 0;
             m_now = 1;
         }
-        const int st = run_sweep(w.eng, phase != PH_DONE && phase != PH_NEXT, m_now, subj, clip);
+        int st = PS_OK;
+        if constexpr (FAST) {
+            if (phase == PH_CLIP1) {
+                int n_out = 0;
+                szcvx::ConvexSweep<ClipInput> cs;
+                if (boundary || !convex_pair || cs.run(subj, subj.n, clip, clip.n, w.rbx, w.rby, C::RV, w.rax, w.ray, C::RV, n_out) != szcvx::CV_OK) st = PS_BAIL;
+                else { w.ra_off[0] = 0; w.ra_off[1] = n_out; w.ra_n = n_out > 0 ? 1 : 0; }
+            } else if (phase == PH_CLIP2 || phase == PH_CLIP3) st = PS_BAIL;
+        } else st = run_sweep(w.eng, phase != PH_DONE && phase != PH_NEXT, m_now, subj, clip);
         if (phase != PH_DONE && phase != PH_NEXT && st != PS_OK) { res.status = st; phase = PH_DONE; }
         const int ph = phase;           // the phase whose clip just ran
         bool next_region = (phase == PH_NEXT);       // prepare the contact direction of region k
@@ -521,12 +553,14 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
         SZ_LANE_SYNC();
 
         // ---- after clip #1 (:29-84)
-        bool a1 = (ph == PH_CLIP1);
-        if (a1) {
-            RegionSink<C> sink(w.rax, w.ray, w.ra_off);
-            w.eng.emit(sink);
-            if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; a1 = false; }
-            else w.ra_n = sink.n_paths;
+        bool a1 = (ph == PH_CLIP1) && phase != PH_DONE;
+        if constexpr (!FAST) {
+            if (a1) {
+                RegionSink<C> sink(w.rax, w.ray, w.ra_off);
+                w.eng.emit(sink);
+                if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; a1 = false; }
+                else w.ra_n = sink.n_paths;
+            }
         }
         SZ_LANE_SYNC();
         if (a1) {
@@ -566,7 +600,7 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
         }
         SZ_LANE_SYNC();
         if (a1) {
-            if (!interx(w)) { res.status = PS_CAPACITY; phase = PH_DONE; a1 = false; }      // :70
+            if (!interx<C>(w)) { res.status = PS_CAPACITY; phase = PH_DONE; a1 = false; }      // :70
         }
         SZ_LANE_SYNC();
         if (a1) {
@@ -579,8 +613,9 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
                 k = -1; next_region = true;
             }
         }
+        if constexpr (!FAST) {
         // ---- after clip #2 (:152-155)
-        if (ph == PH_CLIP2) {
+        if (ph == PH_CLIP2 && phase != PH_DONE) {
             RegionSink<C> sink(w.rbx, w.rby, w.rb_off);
             w.eng.emit(sink);
             if (sink.overflow) { res.status = PS_CAPACITY; phase = PH_DONE; }
@@ -591,7 +626,7 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             }
         }
         // ---- after clip #3 (:158-164): only "empty or not" matters
-        if (ph == PH_CLIP3) {
+        if (ph == PH_CLIP3 && phase != PH_DONE) {
             CountSink cs; cs.n = 0;
             w.eng.emit(cs);
             if (cs.n > 0) {
@@ -600,6 +635,7 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
             }
             ++ii;
             advance = true;
+        }
         }
         SZ_LANE_SYNC();
         // ---- next new region: answered by the certificate when one point is well inside both rings, else clip #3
@@ -724,6 +760,17 @@ SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boun
     double sabs = 0;
     for (int r = 0; r < n_rows; ++r) sabs += fabs(rows[r * 5]) + fabs(rows[r * 5 + 1]);
     res.n_rows = (sabs != 0) ? n_rows : 0;
+}
+template <class C>
+SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true, PairHints hints = PairHints{false, 0, 0, 0, 0})
+{
+    pair_force_impl<C, false>(w, f1, f2, boundary, P, res, rows, valid, hints);
+}
+// class C: strictly convex floe-floe pairs; res.status == PS_BAIL sends the pair to pair_force()
+template <class C>
+SZ_HD void pair_force_convex(WorkspaceLite<C>& w, const Body& f1, const Body& f2, const Params& P, PairResult& res, double* rows, bool valid, PairHints hints)
+{
+    pair_force_impl<C, true>(w, f1, f2, false, P, res, rows, valid, hints);
 }
 
 }  // namespace szpf

@@ -30,7 +30,7 @@ static void fill_params(const SzParams* p, const double* boxx, const double* box
 template <class CAPS>
 static int run(const SzParams* prm, const double* cax, const double* cay, int n1, const double* body1,
                const double* c2x, const double* c2y, int n2, const double* body2, int is_boundary,
-               const double* boxx, const double* boxy, int nbox, double* rows_out, int rows_cap, double* overlap_state)
+               const double* boxx, const double* boxy, int nbox, double* rows_out, int rows_cap, double* overlap_state, bool fast = false)
 {
     if (n1 + 1 > CAPS::NV || n2 + 1 > CAPS::NV) return PS_CAPACITY;
     std::unique_ptr<Workspace<CAPS>> w(new Workspace<CAPS>);
@@ -50,7 +50,14 @@ static int run(const SzParams* prm, const double* cax, const double* cay, int n1
         hints.no1 = open_n(w->c1x, w->c1y, n1); hints.no2 = open_n(w->c2x, w->c2y, n2);
         hints.rot1 = ring_bottom_vertex(G{w->c1x, w->c1y}, hints.no1); hints.rot2 = ring_bottom_vertex(G{w->c2x, w->c2y}, hints.no2);
     }
-    pair_force(*w, b1, b2, is_boundary != 0, P, res, rows.data(), true, hints);
+    if (fast) {
+        // class C as the device runs it: the convex fast path on the engine-less workspace; PS_BAIL = declined
+        std::unique_ptr<WorkspaceLite<CAPS>> wl(new WorkspaceLite<CAPS>);
+        wl->n1 = n1; wl->n2 = n2;
+        for (int i = 0; i < n1; ++i) { wl->c1x[i] = w->c1x[i]; wl->c1y[i] = w->c1y[i]; }
+        for (int i = 0; i < n2; ++i) { wl->c2x[i] = w->c2x[i]; wl->c2y[i] = w->c2y[i]; }
+        pair_force_convex<CAPS>(*wl, b1, b2, P, res, rows.data(), true, hints);
+    } else pair_force(*w, b1, b2, is_boundary != 0, P, res, rows.data(), true, hints);
     if (res.status != PS_OK) return res.status;
     *overlap_state = res.overlap_state;
     if (res.n_rows > rows_cap) return -2;
@@ -63,6 +70,7 @@ extern "C" int szport_floe_interactions(const SzParams* prm, const double* cax, 
                                         const double* boxx, const double* boxy, int nbox,
                                         double* rows_out, int rows_cap, double* overlap_state, int small_class)
 {
+    if (small_class == 2) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state, true);
     if (small_class) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);
     return run<BigPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);
 }

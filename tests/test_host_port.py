@@ -106,6 +106,43 @@ def test_pair_force_convex_shortcuts_thin_and_deep_overlaps(port, inflate, seed)
     assert n_force + n_inf > 100
 
 
+def test_convex_sweep_fuzz_vs_reference_clipper():
+    """the four-edge convex sweep of class C (sz_convex.cuh) against the unmodified reference Clipper: inflated and exact
+    Voronoi neighbourhoods, random hulls far from the origin, integer-grid hulls, nudged copies, overlaps of a few grid
+    units -- every accepted case identical vertex for vertex; it must accept (not decline) the benchmark-like family"""
+    r = subprocess.run([os.path.join(HOST, "convex_fuzz"), "400000", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches=0" in r.stdout
+    vor = [l for l in r.stdout.splitlines() if l.strip().startswith("voronoi ")][0].split()
+    assert int(vor[2]) > 100000 and int(vor[6]) == 0, r.stdout          # accepted, bailed
+
+
+@pytest.mark.parametrize("inflate,seed", [(0.02, 41), (0.0003, 42), (0.002, 43), (0.1, 44), (0.35, 45), (0.0, 46)])
+def test_pair_force_convex_fast_path_class_c(port, inflate, seed):
+    """class C as the device runs it (pair_force_convex on the engine-less workspace) against the oracle's three-clip
+    evaluation; a declined pair (PS_BAIL = -7) is what the device re-runs in class S"""
+    prm, soa = sz.voronoi_field(900, seed=seed, inflate=inflate)
+    ref = oracle.OracleStep(prm, soa, broad_mode=1)
+    pr = ref.pairs()
+    n_force = n_inf = n_bail = n_all = 0
+    for k in range(0, len(pr["i"]), 2):
+        i, j = pr["i"][k] - 1, pr["j"][k] - 1
+        if i >= soa.n or j >= soa.n:
+            continue
+        o, p = both(port, prm, floe_dict(soa, i), floe_dict(soa, j), False, None, 2)
+        n_all += 1
+        if p[0] == -7:
+            n_bail += 1
+            continue
+        assert_same(o, p, "class C, inflate %g pair %d-%d" % (inflate, i, j))
+        n_force += o[0] > 0
+        n_inf += np.isinf(o[2])
+    if inflate > 0:
+        assert n_force + n_inf > 100
+    if inflate == 0.02:
+        assert n_bail < 0.02 * n_all, (n_bail, n_all)       # the benchmark field stays on the fast path
+
+
 def test_pair_force_real_concave_shapes(port):
     """FloeShapes.mat polygons (7..591 vertices) placed to overlap: multi-region contacts, the general (m != 2) branch,
     merge (+-Inf) outcomes"""
