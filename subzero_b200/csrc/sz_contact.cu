@@ -1023,7 +1023,7 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         g_launches += 3;
         // class C: strictly convex pairs through the four-edge sweep; what it declines is appended to class S's list.
         // Both launches are sized for all pairs (the list lengths are only known on the device; surplus CTAs exit at once).
-        static const bool no_fast = getenv("SZ_CONVEX_FAST") == nullptr;      // class C is opt-in until it beats class S on the benchmark field
+        static const bool no_fast = getenv("SZ_NO_CONVEX_FAST") != nullptr;      // experiment switch: everything through class S
         a.list = c->listC.p; a.list_count = D_CNT(listC); a.next_list = c->listS.p; a.next_count = D_CNT(listS);
         if (!no_fast) { ++g_launches; sz_launch_narrow_C(&a, st); CK(cudaGetLastError()); }
         else { a.list = c->listC.p; a.next_list = lstT; a.next_count = cntT; ++g_launches; sz_launch_narrow_S(&a, st); CK(cudaGetLastError()); }

@@ -30,75 +30,77 @@ namespace fp = szclip::fp;
 enum { CV_OK = 0, CV_BAIL = 1 };
 enum { NILE = -1 };
 
-struct Act {                 // the current edge of one bound (clipper.cpp:66-84 TEdge, reduced like szclip::Edge)
-    P64 bot, top;
-    i64 curx, cury;
-    double dx;
-    short vi;                // ring index of `top`
-    signed char step;        // +1: the bound walks the ring forwards, -1: backwards
-    signed char side;        // 1 left, 2 right
-    signed char out;         // OutIdx: 0 or -1
-    signed char wc2;         // even-odd parity of the other path to the left of this edge
-    signed char last;        // NextInLML == NULL (top is the path's top vertex)
-    signed char pad;
-};
 struct INode { P64 pt; int e1, e2; };
 
-// G: callable (int i) -> P64, vertex i of the open ring, i in [0, n), vertex 0 = bottom vertex (largest Y, then
-// smallest X).  Edge ids: 2*poly + {0 left bound, 1 right bound}; poly 0 = subject, 1 = clip.
-template <class G>
+// Edge ids: 2*poly + {0 left bound, 1 right bound}; poly 0 = subject, 1 = clip.  The state of the four bounds is
+// kept as small arrays indexed by edge id; everything that is a flag or an order lives in registers (bit id of a
+// mask; the AEL is four packed nibbles), so the per-scanbeam code touches no index-linked memory at all.
+template <int NV>
 struct ConvexSweep {
-    const G* g[2];
-    int n[2];
-    Act a[4];
-    int ord[4], na;          // AEL, left to right
-    int lm_ord[2], cur_lm; i64 lm_y[2];
+    // the two open rings in Clipper coordinates, vertex 0 = bottom vertex (largest Y, then smallest X)
+    i64 vx[2][NV], vy[2][NV]; int n[2];
+    // current edge of every bound (clipper.cpp:66-84 TEdge, reduced like szclip::Edge)
+    i64 botx[4], boty[4], topx[4], topy[4], curx[4]; double dx[4]; int vi[4];      // vi: ring index of `top`
+    i64 cur_y;                                // Curr.Y of every active edge = bottom of the current scanbeam
+    unsigned ordp; int na;                    // AEL left to right: nibble k of ordp is the edge id at position k
+    unsigned act, f_right, f_out, f_wc2, f_last, f_back;    // bit id: in the AEL / Side == right / OutIdx >= 0 /
+                                              // other path's parity / NextInLML == NULL / the bound walks the ring backwards
+    i64 lm_y[2]; int lm_first, cur_lm;        // the two local minima, sorted by Y descending
     INode il[6]; int n_il;
-    // output record: deque d[lo..hi] in (dx_, dy_), front = d[lo] (OutRec.Pts), back = d[hi] (Pts->Prev)
-    i64* dqx; i64* dqy; int dcap, lo, hi, n_or;
+    // output record: deque d[lo..hi], front = d[lo] (OutRec.Pts), back = d[hi] (Pts->Prev); both ends cached
+    i64* dqx; i64* dqy; int dcap, lo, hi, n_or; P64 fr, bk;
     bool bail; int why;
     SZ_HD void set_bail(int r) { if (!bail) { bail = true; why = r; } }
 
-    SZ_HD P64 vert(int p, int i) const { return (*g[p])(i); }
-    SZ_HD int pos_of(int e) const { for (int k = 0; k < na; ++k) if (ord[k] == e) return k; return -1; }
-    SZ_HD int pael(int e) const { const int k = pos_of(e); return k > 0 ? ord[k - 1] : NILE; }
-    SZ_HD int nael(int e) const { const int k = pos_of(e); return (k >= 0 && k + 1 < na) ? ord[k + 1] : NILE; }
+    SZ_HD int ord_at(int k) const { return (int)((ordp >> (4 * k)) & 15u); }
+    SZ_HD int pos_of(int e) const { for (int k = 0; k < na; ++k) if (ord_at(k) == e) return k; return -1; }
+    SZ_HD int pael(int e) const { const int k = pos_of(e); return k > 0 ? ord_at(k - 1) : NILE; }
+    SZ_HD int nael(int e) const { const int k = pos_of(e); return (k >= 0 && k + 1 < na) ? ord_at(k + 1) : NILE; }
+    SZ_HD bool bit(unsigned m, int e) const { return ((m >> e) & 1u) != 0; }
+    SZ_HD int lm_poly(int k) const { return k == 0 ? lm_first : 1 - lm_first; }
+    SZ_HD P64 bot(int e) const { P64 p; p.x = botx[e]; p.y = boty[e]; return p; }
+    SZ_HD P64 top(int e) const { P64 p; p.x = topx[e]; p.y = topy[e]; return p; }
+    SZ_HD P64 cur(int e) const { P64 p; p.x = curx[e]; p.y = cur_y; return p; }
 
-    SZ_HD i64 top_x(const Act& e, i64 y) const     // clipper.cpp:615-619
+    SZ_HD i64 top_x(int e, i64 y) const     // clipper.cpp:615-619
     {
-        return (y == e.top.y) ? e.top.x : e.bot.x + fp::round_half(fp::mul(e.dx, fp::cvt(y - e.bot.y)));
+        return (y == topy[e]) ? topx[e] : botx[e] + fp::round_half(fp::mul(dx[e], fp::cvt(y - boty[e])));
     }
     // the edge of bound `e` that follows vertex `from` (ring index) -- SetDx :591-596, InitEdge2 :729-742
     SZ_HD void load_edge(int e, int from)
     {
-        Act& r = a[e];
-        const int p = e >> 1, nn = n[p];
-        int to = from + r.step; if (to >= nn) to -= nn; else if (to < 0) to += nn;
-        r.bot = vert(p, from); r.top = vert(p, to); r.vi = (short)to;
-        if (r.top.y >= r.bot.y) { set_bail(1); return; }                 // horizontal (or not a bound of a convex path)
-        r.dx = fp::div(fp::cvt(r.top.x - r.bot.x), fp::cvt(r.top.y - r.bot.y));
-        int nx = to + r.step; if (nx >= nn) nx -= nn; else if (nx < 0) nx += nn;
-        const i64 ny = vert(p, nx).y;
-        if (ny == r.top.y) { set_bail(2); return; }                      // horizontal edge at the top of this one
-        r.last = (signed char)(ny > r.top.y);
-        r.curx = r.bot.x; r.cury = r.bot.y;
+        const int p = e >> 1, nn = n[p], st = bit(f_back, e) ? -1 : 1;
+        int to = from + st; if (to >= nn) to -= nn; else if (to < 0) to += nn;
+        const i64 bx = vx[p][from], by = vy[p][from], tx = vx[p][to], ty = vy[p][to];
+        botx[e] = bx; boty[e] = by; topx[e] = tx; topy[e] = ty; vi[e] = to; curx[e] = bx;
+        if (ty >= by) { set_bail(1); return; }                           // horizontal (or not a bound of a convex path)
+        dx[e] = fp::div(fp::cvt(tx - bx), fp::cvt(ty - by));
+        int nx = to + st; if (nx >= nn) nx -= nn; else if (nx < 0) nx += nn;
+        const i64 ny = vy[p][nx];
+        if (ny == ty) { set_bail(2); return; }                           // horizontal edge at the top of this one
+        if (ny > ty) f_last |= 1u << e; else f_last &= ~(1u << e);
     }
-    SZ_HD bool inserts_before(const Act& e1, const Act& e2) const   // E2InsertsBeforeE1 :3278-3287
+    SZ_HD bool inserts_before(int e1, int e2) const   // E2InsertsBeforeE1 :3278-3287
     {
-        if (e2.curx == e1.curx) {
-            if (e2.top.y > e1.top.y) return e2.top.x < top_x(e1, e2.top.y);
-            else return e1.top.x > top_x(e2, e1.top.y);
+        if (curx[e2] == curx[e1]) {
+            if (topy[e2] > topy[e1]) return topx[e2] < top_x(e1, topy[e2]);
+            else return topx[e1] > top_x(e2, topy[e1]);
         }
-        return e2.curx < e1.curx;
+        return curx[e2] < curx[e1];
     }
-    SZ_HD void insert_at(int k, int e) { for (int t = na; t > k; --t) ord[t] = ord[t - 1]; ord[k] = e; ++na; }
+    SZ_HD void insert_at(int k, int e)
+    {
+        const unsigned lowm = (1u << (4 * k)) - 1u;
+        ordp = (ordp & lowm) | ((unsigned)e << (4 * k)) | ((ordp & ~lowm) << 4);
+        ++na; act |= 1u << e;
+    }
     SZ_HD void insert_into_ael(int e, int start)   // :3319-3345
     {
         if (na == 0) insert_at(0, e);
-        else if (start == NILE && inserts_before(a[ord[0]], a[e])) insert_at(0, e);
+        else if (start == NILE && inserts_before(ord_at(0), e)) insert_at(0, e);
         else {
             int k = (start == NILE) ? 0 : pos_of(start);
-            while (k + 1 < na && !inserts_before(a[ord[k + 1]], a[e])) ++k;
+            while (k + 1 < na && !inserts_before(ord_at(k + 1), e)) ++k;
             insert_at(k + 1, e);
         }
     }
@@ -106,56 +108,63 @@ struct ConvexSweep {
     {
         const int k = pos_of(e);
         if (k < 0) return;
-        for (int t = k; t + 1 < na; ++t) ord[t] = ord[t + 1];
-        --na;
+        const unsigned lowm = (1u << (4 * k)) - 1u;
+        ordp = (ordp & lowm) | ((ordp >> 4) & ~lowm);
+        --na; act &= ~(1u << e);
+    }
+    SZ_HD static unsigned swap_nibbles(unsigned v, int k1, int k2)
+    {
+        const unsigned a = (v >> (4 * k1)) & 15u, b = (v >> (4 * k2)) & 15u;
+        v &= ~((15u << (4 * k1)) | (15u << (4 * k2)));
+        return v | (b << (4 * k1)) | (a << (4 * k2));
     }
     SZ_HD void swap_in_ael(int e1, int e2)
     {
         const int k1 = pos_of(e1), k2 = pos_of(e2);
         if (k1 < 0 || k2 < 0) return;
-        ord[k1] = e2; ord[k2] = e1;
+        ordp = swap_nibbles(ordp, k1, k2);
     }
 
     // ---- output record
     SZ_HD void add_out_pt(int e, P64 pt)   // :2463-2499
     {
-        Act& r = a[e];
-        if (r.out < 0) {
+        if (!bit(f_out, e)) {
             if (n_or != 0) { set_bail(3); return; }       // a second OutRec: outside the model
-            n_or = 1; lo = hi = dcap / 2; dqx[lo] = pt.x; dqy[lo] = pt.y;
-            r.out = 0;                                    // SetHoleState :2301-2324: no other output yet -> not a hole
+            n_or = 1; lo = hi = dcap / 2; dqx[lo] = pt.x; dqy[lo] = pt.y; fr = pt; bk = pt;
+            f_out |= 1u << e;                             // SetHoleState :2301-2324: no other output yet -> not a hole
             return;
         }
-        if (r.side == 1) {
-            if (pt.x == dqx[lo] && pt.y == dqy[lo]) return;
+        if (!bit(f_right, e)) {
+            if (pt == fr) return;
             if (lo == 0) { set_bail(4); return; }
-            --lo; dqx[lo] = pt.x; dqy[lo] = pt.y;
+            --lo; dqx[lo] = pt.x; dqy[lo] = pt.y; fr = pt;
         } else {
-            if (pt.x == dqx[hi] && pt.y == dqy[hi]) return;
+            if (pt == bk) return;
             if (hi + 1 >= dcap) { set_bail(5); return; }
-            ++hi; dqx[hi] = pt.x; dqy[hi] = pt.y;
+            ++hi; dqx[hi] = pt.x; dqy[hi] = pt.y; bk = pt;
         }
     }
+    SZ_HD void set_flag(unsigned& m, int e, bool v) { if (v) m |= 1u << e; else m &= ~(1u << e); }
     SZ_HD void add_local_min_poly(int e1, int e2, P64 pt)   // :1841-1881 (the join test needs an existing OutRec: unreachable)
     {
-        if (a[e1].dx > a[e2].dx) { add_out_pt(e1, pt); a[e2].out = a[e1].out; a[e1].side = 1; a[e2].side = 2; }
-        else { add_out_pt(e2, pt); a[e1].out = a[e2].out; a[e1].side = 2; a[e2].side = 1; }
+        if (dx[e1] > dx[e2]) { add_out_pt(e1, pt); set_flag(f_out, e2, bit(f_out, e1)); set_flag(f_right, e1, false); set_flag(f_right, e2, true); }
+        else { add_out_pt(e2, pt); set_flag(f_out, e1, bit(f_out, e2)); set_flag(f_right, e1, true); set_flag(f_right, e2, false); }
     }
     SZ_HD void add_local_max_poly(int e1, int e2, P64 pt)   // :1884-1897 (one OutRec: the indices are equal)
     {
         add_out_pt(e1, pt);
-        a[e1].out = -1; a[e2].out = -1;
+        f_out &= ~((1u << e1) | (1u << e2));
     }
     SZ_HD void swap_sides_idx(int e1, int e2)
     {
-        signed char s = a[e1].side; a[e1].side = a[e2].side; a[e2].side = s;
-        signed char o = a[e1].out; a[e1].out = a[e2].out; a[e2].out = o;
+        const bool s1 = bit(f_right, e1), s2 = bit(f_right, e2), o1 = bit(f_out, e1), o2 = bit(f_out, e2);
+        set_flag(f_right, e1, s2); set_flag(f_right, e2, s1); set_flag(f_out, e1, o2); set_flag(f_out, e2, o1);
     }
     SZ_HD void intersect_edges(int e1, int e2, P64 pt)   // :2106-2298, closed even-odd paths, ctIntersection
     {
-        const bool c1 = a[e1].out >= 0, c2 = a[e2].out >= 0;
+        const bool c1 = bit(f_out, e1), c2 = bit(f_out, e2);
         const bool same = (e1 >> 1) == (e2 >> 1);
-        if (!same) { a[e1].wc2 ^= 1; a[e2].wc2 ^= 1; }
+        if (!same) f_wc2 ^= (1u << e1) | (1u << e2);
         if (c1 && c2) {
             if (!same) add_local_max_poly(e1, e2, pt);
             else { add_out_pt(e1, pt); add_out_pt(e2, pt); swap_sides_idx(e1, e2); }
@@ -163,108 +172,109 @@ struct ConvexSweep {
         else if (c2) { add_out_pt(e2, pt); swap_sides_idx(e1, e2); }
         else {
             if (!same) add_local_min_poly(e1, e2, pt);
-            else if (a[e1].wc2 > 0 && a[e2].wc2 > 0) add_local_min_poly(e1, e2, pt);
+            else if (bit(f_wc2, e1) && bit(f_wc2, e2)) add_local_min_poly(e1, e2, pt);
         }
     }
 
     // ---- InsertLocalMinimaIntoAEL :1978-2077
     SZ_HD void insert_local_minima(i64 bot_y)
     {
-        while (cur_lm < 2 && lm_y[lm_ord[cur_lm]] == bot_y && !bail) {
-            const int p = lm_ord[cur_lm++];
+        while (cur_lm < 2 && lm_y[lm_poly(cur_lm)] == bot_y && !bail) {
+            const int p = lm_poly(cur_lm++);
             const int lb = 2 * p, rb = 2 * p + 1;
             insert_into_ael(lb, NILE);
             insert_into_ael(rb, lb);
             {   // SetWindingCount :1624-1722 reduced to the other path's parity
                 const int k = pos_of(lb);
                 int q = k - 1;
-                while (q >= 0 && (ord[q] >> 1) != p) --q;
-                signed char w = (q < 0) ? 0 : a[ord[q]].wc2;
-                if (((k - 1 - q) & 1) != 0) w ^= 1;
-                a[lb].wc2 = w; a[rb].wc2 = w;
+                while (q >= 0 && (ord_at(q) >> 1) != p) --q;
+                bool w = (q < 0) ? false : bit(f_wc2, ord_at(q));
+                if (((k - 1 - q) & 1) != 0) w = !w;
+                set_flag(f_wc2, lb, w); set_flag(f_wc2, rb, w);
             }
-            if (a[lb].wc2 != 0) add_local_min_poly(lb, rb, a[lb].bot);
+            if (bit(f_wc2, lb)) add_local_min_poly(lb, rb, bot(lb));
             if (bail) return;
             const int pl = pael(lb);
-            if (a[lb].out >= 0 && pl != NILE) {
-                const Act& q = a[pl]; const Act& l = a[lb];
-                P64 lc; lc.x = l.curx; lc.y = l.cury;
-                if (q.curx == l.bot.x && q.out >= 0 && szclip::slopes_eq4(q.bot, q.top, lc, l.top)) { set_bail(6); return; }   // AddJoin :2046-2055
+            if (bit(f_out, lb) && pl != NILE) {
+                if (curx[pl] == botx[lb] && bit(f_out, pl) && szclip::slopes_eq4(bot(pl), top(pl), cur(lb), top(lb))) { set_bail(6); return; }   // AddJoin :2046-2055
             }
             if (nael(lb) != rb) { set_bail(7); return; }                                                                     // :2057-2076
         }
     }
 
-    // ---- IntersectPoint :622-689
-    SZ_HD P64 intersect_point(const Act& e1, const Act& e2) const
+    // ---- IntersectPoint :622-689 (cur_y is still the bottom of the scanbeam being processed)
+    SZ_HD P64 intersect_point(int a, int b) const
     {
         P64 ip;
-        if (e1.dx == e2.dx) { ip.y = e1.cury; ip.x = top_x(e1, ip.y); return ip; }
-        else if (e1.dx == 0) {
-            ip.x = e1.bot.x;
-            double b2 = fp::sub(fp::cvt(e2.bot.y), fp::div(fp::cvt(e2.bot.x), e2.dx));
-            ip.y = fp::round_half(fp::add(fp::div(fp::cvt(ip.x), e2.dx), b2));
-        } else if (e2.dx == 0) {
-            ip.x = e2.bot.x;
-            double b1 = fp::sub(fp::cvt(e1.bot.y), fp::div(fp::cvt(e1.bot.x), e1.dx));
-            ip.y = fp::round_half(fp::add(fp::div(fp::cvt(ip.x), e1.dx), b1));
+        const double d1 = dx[a], d2 = dx[b];
+        if (d1 == d2) { ip.y = cur_y; ip.x = top_x(a, ip.y); return ip; }
+        else if (d1 == 0) {
+            ip.x = botx[a];
+            double b2 = fp::sub(fp::cvt(boty[b]), fp::div(fp::cvt(botx[b]), d2));
+            ip.y = fp::round_half(fp::add(fp::div(fp::cvt(ip.x), d2), b2));
+        } else if (d2 == 0) {
+            ip.x = botx[b];
+            double b1 = fp::sub(fp::cvt(boty[a]), fp::div(fp::cvt(botx[a]), d1));
+            ip.y = fp::round_half(fp::add(fp::div(fp::cvt(ip.x), d1), b1));
         } else {
-            double b1 = fp::sub(fp::cvt(e1.bot.x), fp::mul(fp::cvt(e1.bot.y), e1.dx));
-            double b2 = fp::sub(fp::cvt(e2.bot.x), fp::mul(fp::cvt(e2.bot.y), e2.dx));
-            double q = fp::div(fp::sub(b2, b1), fp::sub(e1.dx, e2.dx));
+            double b1 = fp::sub(fp::cvt(botx[a]), fp::mul(fp::cvt(boty[a]), d1));
+            double b2 = fp::sub(fp::cvt(botx[b]), fp::mul(fp::cvt(boty[b]), d2));
+            double q = fp::div(fp::sub(b2, b1), fp::sub(d1, d2));
             ip.y = fp::round_half(q);
-            if (fabs(e1.dx) < fabs(e2.dx)) ip.x = fp::round_half(fp::add(fp::mul(e1.dx, q), b1));
-            else ip.x = fp::round_half(fp::add(fp::mul(e2.dx, q), b2));
+            if (fabs(d1) < fabs(d2)) ip.x = fp::round_half(fp::add(fp::mul(d1, q), b1));
+            else ip.x = fp::round_half(fp::add(fp::mul(d2, q), b2));
         }
-        if (ip.y < e1.top.y || ip.y < e2.top.y) {
-            ip.y = (e1.top.y > e2.top.y) ? e1.top.y : e2.top.y;
-            ip.x = (fabs(e1.dx) < fabs(e2.dx)) ? top_x(e1, ip.y) : top_x(e2, ip.y);
+        if (ip.y < topy[a] || ip.y < topy[b]) {
+            ip.y = (topy[a] > topy[b]) ? topy[a] : topy[b];
+            ip.x = (fabs(d1) < fabs(d2)) ? top_x(a, ip.y) : top_x(b, ip.y);
         }
-        if (ip.y > e1.cury) {
-            ip.y = e1.cury;
-            ip.x = (fabs(e1.dx) > fabs(e2.dx)) ? top_x(e2, ip.y) : top_x(e1, ip.y);
+        if (ip.y > cur_y) {
+            ip.y = cur_y;
+            ip.x = (fabs(d1) > fabs(d2)) ? top_x(b, ip.y) : top_x(a, ip.y);
         }
         return ip;
     }
-    // ---- ProcessIntersections :2827-2845
-    SZ_HD void process_intersections(i64 top_y)
+    // ---- ProcessIntersections :2827-2845 when some neighbours change places in this scanbeam.
+    // gt: bit (4a + b) set when Curr.X of edge a > Curr.X of edge b at the top of the scanbeam.
+    SZ_HD void intersections(i64 top_y, unsigned gt)
     {
-        if (na == 0) return;
-        int sel[4]; int ns = na;
-        for (int k = 0; k < na; ++k) { sel[k] = ord[k]; a[ord[k]].curx = top_x(a[ord[k]], top_y); }
+        unsigned sel = ordp; int ns = na;
         n_il = 0;
         bool modified;
         do {   // BuildIntersectList :2871-2900: bubble sort; every pass drops its last element
             modified = false;
             for (int k = 0; k + 1 < ns; ++k) {
-                const int e = sel[k], en = sel[k + 1];
-                if (a[e].curx > a[en].curx) {
-                    P64 pt = intersect_point(a[e], a[en]);
-                    if (pt.y < top_y) { pt.x = top_x(a[e], top_y); pt.y = top_y; }
+                const int e = (int)((sel >> (4 * k)) & 15u), en = (int)((sel >> (4 * k + 4)) & 15u);
+                if ((gt >> (4 * e + en)) & 1u) {
+                    P64 pt = intersect_point(e, en);
+                    if (pt.y < top_y) { pt.x = top_x(e, top_y); pt.y = top_y; }
                     if (n_il >= 6) { set_bail(8); return; }
                     il[n_il].e1 = e; il[n_il].e2 = en; il[n_il].pt = pt; ++n_il;
-                    sel[k] = en; sel[k + 1] = e;
+                    sel = swap_nibbles(sel, k, k + 1);
                     modified = true;
                 }
             }
             if (ns > 1) --ns; else break;
         } while (modified);
-        if (n_il == 0) return;
         if (n_il > 1) {
             // FixupIntersectionOrder :2934-2954: std::sort by Y descending (<= 6 elements: libstdc++ runs a stable
             // insertion sort), then make every intersection one of adjacent edges
-            for (int k = 0; k < na; ++k) sel[k] = ord[k];
+            sel = ordp;
             for (int i = 1; i < n_il; ++i) {
                 INode v = il[i]; int k = i - 1;
                 while (k >= 0 && il[k].pt.y < v.pt.y) { il[k + 1] = il[k]; --k; }
                 il[k + 1] = v;
             }
             for (int i = 0; i < n_il; ++i) {
-                int j = i;
-                while (j < n_il && !sel_adjacent(sel, il[j])) ++j;
+                int j = i, k1 = 0, k2 = 0;
+                for (; j < n_il; ++j) {
+                    k1 = k2 = -9;
+                    for (int k = 0; k < na; ++k) { const int id = (int)((sel >> (4 * k)) & 15u); if (id == il[j].e1) k1 = k; if (id == il[j].e2) k2 = k; }
+                    if (k1 - k2 == 1 || k2 - k1 == 1) break;
+                }
                 if (j == n_il) { set_bail(9); return; }
                 if (j != i) { INode t = il[i]; il[i] = il[j]; il[j] = t; }
-                sel_swap(sel, il[i].e1, il[i].e2);
+                sel = swap_nibbles(sel, k1, k2);
             }
         }
         for (int i = 0; i < n_il && !bail; ++i) {          // ProcessIntersectList :2906-2918
@@ -273,105 +283,134 @@ struct ConvexSweep {
         }
         n_il = 0;
     }
-    SZ_HD bool sel_adjacent(const int* sel, const INode& nd) const
-    {
-        int k1 = -1, k2 = -1;
-        for (int k = 0; k < na; ++k) { if (sel[k] == nd.e1) k1 = k; if (sel[k] == nd.e2) k2 = k; }
-        return k1 - k2 == 1 || k2 - k1 == 1;
-    }
-    SZ_HD void sel_swap(int* sel, int e1, int e2) const
-    {
-        int k1 = -1, k2 = -1;
-        for (int k = 0; k < na; ++k) { if (sel[k] == e1) k1 = k; if (sel[k] == e2) k2 = k; }
-        sel[k1] = e2; sel[k2] = e1;
-    }
 
-    // ---- ProcessEdgesAtTopOfScanbeam :3009-3113
     SZ_HD void do_maxima(int e)   // :2957-3006
     {
         const int mp = e ^ 1;
         // GetMaximaPairEx :2548-2555: the other bound of the path ends at the same top vertex and is active
-        if (!(pos_of(mp) >= 0 && a[mp].last && a[mp].top.x == a[e].top.x && a[mp].top.y == a[e].top.y)) { set_bail(10); return; }
+        if (!(bit(act, mp) && bit(f_last, mp) && topx[mp] == topx[e] && topy[mp] == topy[e])) { set_bail(10); return; }
         int en = nael(e);
         while (en != NILE && en != mp && !bail) {
-            intersect_edges(e, en, a[e].top);
+            intersect_edges(e, en, top(e));
             swap_in_ael(e, en);
             en = nael(e);
         }
         if (bail) return;
-        if (a[e].out == -1 && a[mp].out == -1) { delete_from_ael(e); delete_from_ael(mp); }
-        else if (a[e].out >= 0 && a[mp].out >= 0) { add_local_max_poly(e, mp, a[e].top); delete_from_ael(e); delete_from_ael(mp); }
+        if (!bit(f_out, e) && !bit(f_out, mp)) { delete_from_ael(e); delete_from_ael(mp); }
+        else if (bit(f_out, e) && bit(f_out, mp)) { add_local_max_poly(e, mp, top(e)); delete_from_ael(e); delete_from_ael(mp); }
         else set_bail(11);      // "DoMaxima error": let the general sweep report it
     }
-    SZ_HD void process_edges_at_top(i64 top_y)
-    {
-        int i = 0;
-        while (i < na && !bail) {
-            const int e = ord[i];
-            if (a[e].top.y == top_y && a[e].last) do_maxima(e);       // e and its pair leave the AEL; position i now holds the next edge
-            else { a[e].curx = top_x(a[e], top_y); a[e].cury = top_y; ++i; }
-        }
-        // 4. promote intermediate vertices
-        for (i = 0; i < na && !bail; ++i) {
-            const int e = ord[i];
-            Act& r = a[e];
-            if (r.top.y == top_y && !r.last) {
-                const bool o = r.out >= 0;
-                if (o) add_out_pt(e, r.top);
-                load_edge(e, r.vi);                                   // UpdateEdgeIntoAEL :1442-1462 (out, side, wc2 carry over)
-                if (bail) return;
-                if (o) {
-                    const int ep = (i > 0) ? ord[i - 1] : NILE, en = (i + 1 < na) ? ord[i + 1] : NILE;
-                    P64 rc; rc.x = r.curx; rc.y = r.cury;
-                    if (ep != NILE) {
-                        const Act& q = a[ep]; P64 qc; qc.x = q.curx; qc.y = q.cury;
-                        if (q.curx == r.bot.x && q.cury == r.bot.y && q.out >= 0 && q.cury > q.top.y && szclip::slopes_eq4(rc, r.top, qc, q.top)) { set_bail(12); return; }
-                    }
-                    if (en != NILE) {
-                        const Act& q = a[en]; P64 qc; qc.x = q.curx; qc.y = q.cury;
-                        if (q.curx == r.bot.x && q.cury == r.bot.y && q.out >= 0 && q.cury > q.top.y && szclip::slopes_eq4(rc, r.top, qc, q.top)) { set_bail(13); return; }
-                    }
-                }
-            }
-        }
-    }
 
-    // Runs the whole clip.  On CV_OK the solution ring (BuildResult order) is in (ox, oy)[0, n_out), n_out = 0 when
-    // the intersection is empty.  (wx, wy)[0, wcap) is scratch for the output record.
-    SZ_HD int run(const G& subj, int n1, const G& clip, int n2, i64* wx, i64* wy, int wcap, i64* ox, i64* oy, int ocap, int& n_out)
+    // ---- stepwise interface (the caller keeps the lanes of a warp / CTA together between scanbeams)
+    // before begin(): fill vx/vy/n (load_ring).  (wx, wy)[0, wcap) is scratch for the output record.
+    template <class G> SZ_HD void load_ring(int p, const G& get, int cnt)
     {
-        n_out = 0;
-        why = 17; if (n1 < 3 || n2 < 3) return CV_BAIL;
-        g[0] = &subj; g[1] = &clip; n[0] = n1; n[1] = n2;
+        n[p] = cnt;
+        for (int i = 0; i < cnt && i < NV; ++i) { const P64 q = get(i); vx[p][i] = q.x; vy[p][i] = q.y; }
+    }
+    SZ_HD bool begin(i64* wx, i64* wy, int wcap)
+    {
         dqx = wx; dqy = wy; dcap = wcap; lo = hi = 0; n_or = 0; na = 0; n_il = 0; bail = false; why = 0; cur_lm = 0;
+        ordp = 0; act = f_right = f_out = f_wc2 = f_last = f_back = 0; cur_y = 0; fr.x = fr.y = bk.x = bk.y = 0;
+        if (n[0] < 3 || n[1] < 3 || n[0] > NV || n[1] > NV) { set_bail(17); return false; }
         for (int p = 0; p < 2; ++p) {
-            // the two bounds of the path's single local minimum (AddPath :1172-1219)
-            Act& f = a[2 * p]; Act& b = a[2 * p + 1];
-            f.step = 1; b.step = -1;
-            f.side = b.side = 0; f.out = b.out = -1; f.wc2 = b.wc2 = 0; f.pad = b.pad = 0;
-            load_edge(2 * p, 0); load_edge(2 * p + 1, 0);
-            if (bail) return CV_BAIL;
-            // e = forward edge, e.prev = backward edge: left bound = the one with the larger Dx (:1192-1203)
-            if (f.dx < b.dx) { Act t = f; f = b; b = t; }
-            f.side = 1; b.side = 2;
-            lm_y[p] = f.bot.y;
+            // the two bounds of the path's single local minimum (AddPath :1172-1219): e = forward edge, e.prev = backward
+            // edge; the left bound is the one with the larger Dx (:1192-1203)
+            const int l = 2 * p, r = 2 * p + 1;
+            f_back |= 1u << r;
+            load_edge(l, 0); load_edge(r, 0);
+            if (bail) return false;
+            if (dx[l] < dx[r]) {
+                f_back ^= (1u << l) | (1u << r);
+                i64 t; double d; int q;
+                t = topx[l]; topx[l] = topx[r]; topx[r] = t; t = topy[l]; topy[l] = topy[r]; topy[r] = t;
+                d = dx[l]; dx[l] = dx[r]; dx[r] = d; q = vi[l]; vi[l] = vi[r]; vi[r] = q;
+                const bool ll = bit(f_last, l), lr = bit(f_last, r); set_flag(f_last, l, lr); set_flag(f_last, r, ll);
+            }
+            f_right |= 1u << r;
+            lm_y[p] = boty[l];
         }
         // Reset :1247-1276: minima sorted by Y descending (std::sort of two elements is stable)
-        if (lm_y[1] > lm_y[0]) { lm_ord[0] = 1; lm_ord[1] = 0; } else { lm_ord[0] = 0; lm_ord[1] = 1; }
-        i64 bot_y = lm_y[lm_ord[0]];
-        insert_local_minima(bot_y);
-        while (!bail) {
-            // PopScanbeam: the largest pending Y = tops of the active edges and pending local minima
-            if (na == 0 && cur_lm >= 2) break;
-            bool have = false; i64 top_y = 0;
-            for (int k = 0; k < na; ++k) { const i64 y = a[ord[k]].top.y; if (!have || y > top_y) { top_y = y; have = true; } }
-            if (cur_lm < 2) { const i64 y = lm_y[lm_ord[cur_lm]]; if (!have || y > top_y) { top_y = y; have = true; } }
-            process_intersections(top_y);
-            if (bail) break;
-            process_edges_at_top(top_y);
-            if (bail) break;
-            insert_local_minima(top_y);
+        lm_first = (lm_y[1] > lm_y[0]) ? 1 : 0;
+        cur_y = lm_y[lm_first];
+        insert_local_minima(cur_y);
+        return !bail;
+    }
+    // one scanbeam: PopScanbeam, ProcessIntersections, ProcessEdgesAtTopOfScanbeam, InsertLocalMinimaIntoAEL.
+    // Returns false when the sweep is over (or bailed).
+    SZ_HD bool step()
+    {
+        if (bail) return false;
+        // PopScanbeam: the largest pending Y = tops of the active edges and pending local minima
+        bool have = false; i64 top_y = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int id = 0; id < 4; ++id) if (bit(act, id)) { const i64 y = topy[id]; if (!have || y > top_y) { top_y = y; have = true; } }
+        if (cur_lm < 2) { const i64 y = lm_y[lm_poly(cur_lm)]; if (!have || y > top_y) { top_y = y; have = true; } }
+        if (!have) return false;
+        // BuildIntersectList :2863-2868: Curr.X of every active edge at the top of the scanbeam
+        i64 xt[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int id = 0; id < 4; ++id) { xt[id] = bit(act, id) ? top_x(id, top_y) : 0; if (bit(act, id)) curx[id] = xt[id]; }
+        bool inv = false;
+        for (int k = 0; k + 1 < na; ++k) {
+            const int e = ord_at(k), en = ord_at(k + 1);
+            const i64 xe = e == 0 ? xt[0] : e == 1 ? xt[1] : e == 2 ? xt[2] : xt[3];
+            const i64 xn = en == 0 ? xt[0] : en == 1 ? xt[1] : en == 2 ? xt[2] : xt[3];
+            inv = inv || (xe > xn);
         }
+        if (inv) {
+            unsigned gt = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < 16; ++q) { const int a = q >> 2, b = q & 3; if (a != b && bit(act, a) && bit(act, b) && xt[a] > xt[b]) gt |= 1u << q; }
+            intersections(top_y, gt);
+            if (bail) return false;
+        }
+        cur_y = top_y;
+        // ProcessEdgesAtTopOfScanbeam :3009-3113.  Curr of the edges that stay is already (TopX, topY).
+        unsigned at_top = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int id = 0; id < 4; ++id) if (bit(act, id) && topy[id] == top_y) at_top |= 1u << id;
+        if (at_top & f_last) {
+            int i = 0;
+            while (i < na && !bail) {
+                const int e = ord_at(i);
+                if (bit(at_top & f_last, e)) do_maxima(e);      // e and its pair leave the AEL; position i now holds the next edge
+                else ++i;
+            }
+            if (bail) return false;
+        }
+        // 4. promote intermediate vertices, in AEL order
+        unsigned prom = at_top & ~f_last & act;
+        while (prom != 0 && !bail) {
+            int k = 0;
+            while (!bit(prom, ord_at(k))) ++k;
+            const int e = ord_at(k);
+            prom &= ~(1u << e);
+            const bool o = bit(f_out, e);
+            if (o) add_out_pt(e, top(e));
+            load_edge(e, vi[e]);                                  // UpdateEdgeIntoAEL :1442-1462 (out, side, wc2 carry over)
+            if (bail) return false;
+            if (o) {
+                const int ep = (k > 0) ? ord_at(k - 1) : NILE, en = (k + 1 < na) ? ord_at(k + 1) : NILE;
+                if (ep != NILE && curx[ep] == botx[e] && cur_y == boty[e] && bit(f_out, ep) && cur_y > topy[ep] && szclip::slopes_eq4(cur(e), top(e), cur(ep), top(ep))) { set_bail(12); return false; }
+                if (en != NILE && curx[en] == botx[e] && cur_y == boty[e] && bit(f_out, en) && cur_y > topy[en] && szclip::slopes_eq4(cur(e), top(e), cur(en), top(en))) { set_bail(13); return false; }
+            }
+        }
+        insert_local_minima(top_y);
+        return !bail;
+    }
+    // On CV_OK the solution ring (BuildResult order) is in (ox, oy)[0, n_out), n_out = 0 when the intersection is empty.
+    SZ_HD int finish(i64* ox, i64* oy, int ocap, int& n_out)
+    {
+        n_out = 0;
         if (bail) return CV_BAIL;
         if (n_or == 0) return CV_OK;
         const int m = hi - lo + 1;
@@ -396,6 +435,15 @@ struct ConvexSweep {
         else { for (int t = 0; t < m; ++t) { const int c = (t == m - 1) ? lo : lo + 1 + t; ox[t] = dqx[c]; oy[t] = dqy[c]; } }
         n_out = m;
         return CV_OK;
+    }
+    // the whole clip for a single caller
+    template <class G>
+    SZ_HD int run(const G& subj, int n1, const G& clip, int n2, i64* wx, i64* wy, int wcap, i64* ox, i64* oy, int ocap, int& n_out)
+    {
+        load_ring(0, subj, n1); load_ring(1, clip, n2);
+        bool go = begin(wx, wy, wcap);
+        while (go) go = step();
+        return finish(ox, oy, ocap, n_out);
     }
 };
 

@@ -157,7 +157,7 @@ __device__ __forceinline__ void resolve_pair(const NarrowArgs& a, int k, bool va
 // class C (convex fast path): strictly convex floe-floe pairs, clip #1 by the four-edge sweep of sz_convex.cuh, sign
 // test by its margin certificate; no arena.  A pair the fast path declines is appended to class S's list.
 #ifndef SZ_C_TPB
-#define SZ_C_TPB 256
+#define SZ_C_TPB 512
 #endif
 #ifndef SZ_C_MINB
 #define SZ_C_MINB 2
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(SZ_C_TPB, SZ_C_MINB) narrow_convex_kernel(cons
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *a.list_count;
-    if ((t & ~31) >= n) return;                          // whole warp beyond the list
+    if (blockIdx.x * blockDim.x >= n) return;           // whole CTA beyond the list: uniform exit
     szpf::WorkspaceLite<C> w;
     resolve_pair_impl<C, true>(a, t < n ? a.list[t] : 0, t < n, w);
 }

@@ -111,12 +111,6 @@ struct CountSink { int n; SZ_HD void begin_path(int) { ++n; } SZ_HD void point(P
 #if !defined(SZ_WARP_SYNC_ONLY)
 #define SZ_BLOCK_SYNC 1
 #endif
-// the convex fast path has no per-scanbeam phases to share: its lanes only vote warp-wide on the loop exit
-#if defined(__CUDA_ARCH__)
-#define SZ_FAST_ANY(p) __any_sync(0xffffffffu, (p))
-#else
-#define SZ_FAST_ANY(p) (p)
-#endif
 #if defined(__CUDA_ARCH__) && defined(SZ_BLOCK_SYNC)
 // block-synchronous variant: every warp of the CTA walks the phases together, so the instruction lines of a
 // phase are fetched once per CTA instead of once per warp (the sweep's SASS is far larger than the I-cache)
@@ -519,11 +513,36 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
     double fdx = 0, fdy = 0, dl = 0, pcx = 0, pcy = 0, Ak = 0;
     bool outline_checked = false, outline_ok = true;
 
+    // class C: clip #1 in the four-edge sweep of sz_convex.cuh, one scanbeam per iteration with the lanes kept together
+    int fast_clip1 = PS_BAIL;
+    if constexpr (FAST) {
+        szcvx::ConvexSweep<C::NV> cs;
+        bool run = false;
+        const bool go = valid && convex_pair && !boundary && hints.no1 >= 3 && hints.no2 >= 3;
+        if (go) {
+            ClipInput subj, clip;
+            subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = hints.no1; subj.ring = 0; subj.rot = hints.rot1;
+            clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = hints.no2; clip.ring = 0; clip.rot = hints.rot2;
+            cs.load_ring(0, subj, subj.n); cs.load_ring(1, clip, clip.n);
+        }
+        SZ_LANE_SYNC();
+        if (go) run = cs.begin(w.rbx, w.rby, C::RV);
+        for (;;) {
+            if (!SZ_WARP_ANY(run)) break;
+            if (run) run = cs.step();
+            SZ_LANE_SYNC();
+        }
+        if (go) {
+            int n_out = 0;
+            if (cs.finish(w.rax, w.ray, C::RV, n_out) == szcvx::CV_OK) { fast_clip1 = PS_OK; w.ra_off[0] = 0; w.ra_off[1] = n_out; w.ra_n = n_out > 0 ? 1 : 0; }
+        }
+        SZ_LANE_SYNC();
+    }
     // The loop body is a SEQUENCE of predicated blocks with a lane re-convergence point after each one (no early
     // `continue`): the lanes of a warp resolve different pairs, and a block that one lane leaves early must not make
     // the others run the rest of the body one lane at a time (first profile: InterX ran with 1.2 of 32 lanes active).
     for (;;) {
-        if (!(FAST ? SZ_FAST_ANY(phase != PH_DONE) : SZ_WARP_ANY(phase != PH_DONE))) break;
+        if (!SZ_WARP_ANY(phase != PH_DONE)) break;
         // ---- the clip this lane needs now
         ClipInput subj, clip;
         subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = w.n1; subj.ring = 0; subj.rot = 0;
@@ -538,12 +557,8 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
         }
         int st = PS_OK;
         if constexpr (FAST) {
-            if (phase == PH_CLIP1) {
-                int n_out = 0;
-                szcvx::ConvexSweep<ClipInput> cs;
-                if (boundary || !convex_pair || cs.run(subj, subj.n, clip, clip.n, w.rbx, w.rby, C::RV, w.rax, w.ray, C::RV, n_out) != szcvx::CV_OK) st = PS_BAIL;
-                else { w.ra_off[0] = 0; w.ra_off[1] = n_out; w.ra_n = n_out > 0 ? 1 : 0; }
-            } else if (phase == PH_CLIP2 || phase == PH_CLIP3) st = PS_BAIL;
+            if (phase == PH_CLIP1) st = fast_clip1;                                   // swept before the loop
+            else if (phase == PH_CLIP2 || phase == PH_CLIP3) st = PS_BAIL;            // the sign test was not certified
         } else st = run_sweep(w.eng, phase != PH_DONE && phase != PH_NEXT, m_now, subj, clip);
         if (phase != PH_DONE && phase != PH_NEXT && st != PS_OK) { res.status = st; phase = PH_DONE; }
         const int ph = phase;           // the phase whose clip just ran
