@@ -334,7 +334,30 @@ struct ConvexSweep {
         lm_first = (lm_y[1] > lm_y[0]) ? 1 : 0;
         cur_y = lm_y[lm_first];
         insert_local_minima(cur_y);
-        return !bail;
+        if (bail) return false;
+        // Scanbeams above which only the first path is active (its two bounds, not contributing: nothing can be
+        // output and nothing is inserted) are walked here, outside the lane-synchronous loop: per scanbeam the sweep
+        // only promotes the bound(s) whose top is reached (:3086-3111).  The one other thing it could do -- swap the two
+        // bounds because their rounded TopX values invert (within a grid unit of the path's top) -- is outside the model.
+        if (cur_lm == 1) {
+            const int l = 2 * lm_first, r = l + 1;
+            const i64 y2 = lm_y[1 - lm_first];
+            for (;;) {
+                const i64 ty = topy[l] > topy[r] ? topy[l] : topy[r];
+                if (ty <= y2) break;
+                if (top_x(l, ty) > top_x(r, ty)) { set_bail(18); return false; }
+                cur_y = ty;
+                if ((bit(f_last, l) && topy[l] == ty) || (bit(f_last, r) && topy[r] == ty)) {
+                    // the first path ends below the bottom of the second: DoMaxima removes both bounds, the rest of the
+                    // sweep sees the second path alone and outputs nothing
+                    na = 0; act = 0; cur_lm = 2; return false;
+                }
+                if (topy[l] == ty) load_edge(l, vi[l]);
+                if (topy[r] == ty && !bail) load_edge(r, vi[r]);
+                if (bail) return false;
+            }
+        }
+        return true;
     }
     // one scanbeam: PopScanbeam, ProcessIntersections, ProcessEdgesAtTopOfScanbeam, InsertLocalMinimaIntoAEL.
     // Returns false when the sweep is over (or bailed).
@@ -405,7 +428,11 @@ struct ConvexSweep {
             }
         }
         insert_local_minima(top_y);
-        return !bail;
+        if (bail) return false;
+        // with both minima inserted and one path gone, the other path's bounds are outside it for good: no edge can
+        // contribute again, whatever the remaining scanbeams hold
+        if (cur_lm >= 2 && ((act & 3u) == 0 || (act & 12u) == 0)) return false;
+        return true;
     }
     // On CV_OK the solution ring (BuildResult order) is in (ox, oy)[0, n_out), n_out = 0 when the intersection is empty.
     SZ_HD int finish(i64* ox, i64* oy, int ocap, int& n_out)
