@@ -32,20 +32,39 @@ enum { NILE = -1 };
 
 struct INode { P64 pt; int e1, e2; };
 
-// Edge ids: 2*poly + {0 left bound, 1 right bound}; poly 0 = subject, 1 = clip.  The state of the four bounds is
-// kept as small arrays indexed by edge id; everything that is a flag or an order lives in registers (bit id of a
-// mask; the AEL is four packed nibbles), so the per-scanbeam code touches no index-linked memory at all.
+// Four-entry state arrays.  To keep them in registers on the device an entry chosen at run time has to be read through a
+// select chain and written through predicated moves (every subscript is a literal; a single run-time subscript
+// would send the whole array to local memory).  Measured on B200 this is SLOWER than leaving the arrays in L1-cached local
+// memory (12.0 vs 10.4 ms at 1M floes: the select chains cost more issue slots than the loads they save), so plain
+// subscripts are the default and SZ_CVX_REG_ARRAYS is the experiment switch.
+#if defined(__CUDA_ARCH__) && defined(SZ_CVX_REG_ARRAYS)
+template <class T> SZ_HD T rd4(const T (&a)[4], int e) { return e == 0 ? a[0] : (e == 1 ? a[1] : (e == 2 ? a[2] : a[3])); }
+template <class T> SZ_HD void wr4(T (&a)[4], int e, T v) { if (e == 0) a[0] = v; if (e == 1) a[1] = v; if (e == 2) a[2] = v; if (e == 3) a[3] = v; }
+#else
+template <class T> SZ_HD T rd4(const T (&a)[4], int e) { return a[e]; }
+template <class T> SZ_HD void wr4(T (&a)[4], int e, T v) { a[e] = v; }
+#endif
+#if defined(__CUDA_ARCH__)
+#define SZ_UNROLL4 _Pragma("unroll")
+#else
+#define SZ_UNROLL4
+#endif
+
+// Edge ids: 2*slot + {0 left bound, 1 right bound}; slot 0 is the path whose local minimum is popped first (larger
+// bottom Y; the subject on a tie, like the stable sort of Reset :1251), slot 1 the other one.  Flags and orders live
+// in registers (bit id of a mask; the AEL is four packed nibbles).
 template <int NV>
 struct ConvexSweep {
-    // the two open rings in Clipper coordinates, vertex 0 = bottom vertex (largest Y, then smallest X)
+    // the two open rings in Clipper coordinates, vertex 0 = bottom vertex (largest Y, then smallest X); [0] subject, [1] clip
     i64 vx[2][NV], vy[2][NV]; int n[2];
+    int sw;                                   // slot q holds ring q ^ sw
     // current edge of every bound (clipper.cpp:66-84 TEdge, reduced like szclip::Edge)
     i64 botx[4], boty[4], topx[4], topy[4], curx[4]; double dx[4]; int vi[4];      // vi: ring index of `top`
     i64 cur_y;                                // Curr.Y of every active edge = bottom of the current scanbeam
     unsigned ordp; int na;                    // AEL left to right: nibble k of ordp is the edge id at position k
     unsigned act, f_right, f_out, f_wc2, f_last, f_back;    // bit id: in the AEL / Side == right / OutIdx >= 0 /
                                               // other path's parity / NextInLML == NULL / the bound walks the ring backwards
-    i64 lm_y[2]; int lm_first, cur_lm;        // the two local minima, sorted by Y descending
+    i64 lm_y[2]; int cur_lm;                  // the two local minima (slot order = Y descending)
     INode il[6]; int n_il;
     // output record: deque d[lo..hi], front = d[lo] (OutRec.Pts), back = d[hi] (Pts->Prev); both ends cached
     i64* dqx; i64* dqy; int dcap, lo, hi, n_or; P64 fr, bk;
@@ -57,24 +76,24 @@ struct ConvexSweep {
     SZ_HD int pael(int e) const { const int k = pos_of(e); return k > 0 ? ord_at(k - 1) : NILE; }
     SZ_HD int nael(int e) const { const int k = pos_of(e); return (k >= 0 && k + 1 < na) ? ord_at(k + 1) : NILE; }
     SZ_HD bool bit(unsigned m, int e) const { return ((m >> e) & 1u) != 0; }
-    SZ_HD int lm_poly(int k) const { return k == 0 ? lm_first : 1 - lm_first; }
-    SZ_HD P64 bot(int e) const { P64 p; p.x = botx[e]; p.y = boty[e]; return p; }
-    SZ_HD P64 top(int e) const { P64 p; p.x = topx[e]; p.y = topy[e]; return p; }
-    SZ_HD P64 cur(int e) const { P64 p; p.x = curx[e]; p.y = cur_y; return p; }
+    SZ_HD P64 bot(int e) const { P64 p; p.x = rd4(botx, e); p.y = rd4(boty, e); return p; }
+    SZ_HD P64 top(int e) const { P64 p; p.x = rd4(topx, e); p.y = rd4(topy, e); return p; }
+    SZ_HD P64 cur(int e) const { P64 p; p.x = rd4(curx, e); p.y = cur_y; return p; }
 
-    SZ_HD i64 top_x(int e, i64 y) const     // clipper.cpp:615-619
+    SZ_HD static i64 top_x_of(i64 bx, i64 by, i64 tx, i64 ty, double d, i64 y)     // clipper.cpp:615-619
     {
-        return (y == topy[e]) ? topx[e] : botx[e] + fp::round_half(fp::mul(dx[e], fp::cvt(y - boty[e])));
+        return (y == ty) ? tx : bx + fp::round_half(fp::mul(d, fp::cvt(y - by)));
     }
+    SZ_HD i64 top_x(int e, i64 y) const { return top_x_of(rd4(botx, e), rd4(boty, e), rd4(topx, e), rd4(topy, e), rd4(dx, e), y); }
     // the edge of bound `e` that follows vertex `from` (ring index) -- SetDx :591-596, InitEdge2 :729-742
     SZ_HD void load_edge(int e, int from)
     {
-        const int p = e >> 1, nn = n[p], st = bit(f_back, e) ? -1 : 1;
+        const int p = (e >> 1) ^ sw, nn = n[p], st = bit(f_back, e) ? -1 : 1;
         int to = from + st; if (to >= nn) to -= nn; else if (to < 0) to += nn;
         const i64 bx = vx[p][from], by = vy[p][from], tx = vx[p][to], ty = vy[p][to];
-        botx[e] = bx; boty[e] = by; topx[e] = tx; topy[e] = ty; vi[e] = to; curx[e] = bx;
+        wr4(botx, e, bx); wr4(boty, e, by); wr4(topx, e, tx); wr4(topy, e, ty); wr4(vi, e, to); wr4(curx, e, bx);
         if (ty >= by) { set_bail(1); return; }                           // horizontal (or not a bound of a convex path)
-        dx[e] = fp::div(fp::cvt(tx - bx), fp::cvt(ty - by));
+        wr4(dx, e, fp::div(fp::cvt(tx - bx), fp::cvt(ty - by)));
         int nx = to + st; if (nx >= nn) nx -= nn; else if (nx < 0) nx += nn;
         const i64 ny = vy[p][nx];
         if (ny == ty) { set_bail(2); return; }                           // horizontal edge at the top of this one
@@ -82,11 +101,13 @@ struct ConvexSweep {
     }
     SZ_HD bool inserts_before(int e1, int e2) const   // E2InsertsBeforeE1 :3278-3287
     {
-        if (curx[e2] == curx[e1]) {
-            if (topy[e2] > topy[e1]) return topx[e2] < top_x(e1, topy[e2]);
-            else return topx[e1] > top_x(e2, topy[e1]);
+        const i64 c1 = rd4(curx, e1), c2 = rd4(curx, e2);
+        if (c2 == c1) {
+            const i64 t1y = rd4(topy, e1), t2y = rd4(topy, e2);
+            if (t2y > t1y) return rd4(topx, e2) < top_x(e1, t2y);
+            else return rd4(topx, e1) > top_x(e2, t1y);
         }
-        return curx[e2] < curx[e1];
+        return c2 < c1;
     }
     SZ_HD void insert_at(int k, int e)
     {
@@ -144,10 +165,10 @@ struct ConvexSweep {
             ++hi; dqx[hi] = pt.x; dqy[hi] = pt.y; bk = pt;
         }
     }
-    SZ_HD void set_flag(unsigned& m, int e, bool v) { if (v) m |= 1u << e; else m &= ~(1u << e); }
+    SZ_HD void set_flag(unsigned& m, int e, bool v) { m = (m & ~(1u << e)) | ((v ? 1u : 0u) << e); }
     SZ_HD void add_local_min_poly(int e1, int e2, P64 pt)   // :1841-1881 (the join test needs an existing OutRec: unreachable)
     {
-        if (dx[e1] > dx[e2]) { add_out_pt(e1, pt); set_flag(f_out, e2, bit(f_out, e1)); set_flag(f_right, e1, false); set_flag(f_right, e2, true); }
+        if (rd4(dx, e1) > rd4(dx, e2)) { add_out_pt(e1, pt); set_flag(f_out, e2, bit(f_out, e1)); set_flag(f_right, e1, false); set_flag(f_right, e2, true); }
         else { add_out_pt(e2, pt); set_flag(f_out, e1, bit(f_out, e2)); set_flag(f_right, e1, true); set_flag(f_right, e2, false); }
     }
     SZ_HD void add_local_max_poly(int e1, int e2, P64 pt)   // :1884-1897 (one OutRec: the indices are equal)
@@ -179,9 +200,10 @@ struct ConvexSweep {
     // ---- InsertLocalMinimaIntoAEL :1978-2077
     SZ_HD void insert_local_minima(i64 bot_y)
     {
-        while (cur_lm < 2 && lm_y[lm_poly(cur_lm)] == bot_y && !bail) {
-            const int p = lm_poly(cur_lm++);
+        while (cur_lm < 2 && lm_y[cur_lm] == bot_y && !bail) {
+            const int p = cur_lm++;
             const int lb = 2 * p, rb = 2 * p + 1;
+            wr4(curx, lb, rd4(botx, lb)); wr4(curx, rb, rd4(botx, rb));      // Curr = Bot (Reset :1262-1274)
             insert_into_ael(lb, NILE);
             insert_into_ael(rb, lb);
             {   // SetWindingCount :1624-1722 reduced to the other path's parity
@@ -196,7 +218,7 @@ struct ConvexSweep {
             if (bail) return;
             const int pl = pael(lb);
             if (bit(f_out, lb) && pl != NILE) {
-                if (curx[pl] == botx[lb] && bit(f_out, pl) && szclip::slopes_eq4(bot(pl), top(pl), cur(lb), top(lb))) { set_bail(6); return; }   // AddJoin :2046-2055
+                if (rd4(curx, pl) == rd4(botx, lb) && bit(f_out, pl) && szclip::slopes_eq4(bot(pl), top(pl), cur(lb), top(lb))) { set_bail(6); return; }   // AddJoin :2046-2055
             }
             if (nael(lb) != rb) { set_bail(7); return; }                                                                     // :2057-2076
         }
@@ -206,31 +228,33 @@ struct ConvexSweep {
     SZ_HD P64 intersect_point(int a, int b) const
     {
         P64 ip;
-        const double d1 = dx[a], d2 = dx[b];
-        if (d1 == d2) { ip.y = cur_y; ip.x = top_x(a, ip.y); return ip; }
+        const double d1 = rd4(dx, a), d2 = rd4(dx, b);
+        const i64 bxa = rd4(botx, a), bya = rd4(boty, a), txa = rd4(topx, a), tya = rd4(topy, a);
+        const i64 bxb = rd4(botx, b), byb = rd4(boty, b), txb = rd4(topx, b), tyb = rd4(topy, b);
+        if (d1 == d2) { ip.y = cur_y; ip.x = top_x_of(bxa, bya, txa, tya, d1, ip.y); return ip; }
         else if (d1 == 0) {
-            ip.x = botx[a];
-            double b2 = fp::sub(fp::cvt(boty[b]), fp::div(fp::cvt(botx[b]), d2));
+            ip.x = bxa;
+            double b2 = fp::sub(fp::cvt(byb), fp::div(fp::cvt(bxb), d2));
             ip.y = fp::round_half(fp::add(fp::div(fp::cvt(ip.x), d2), b2));
         } else if (d2 == 0) {
-            ip.x = botx[b];
-            double b1 = fp::sub(fp::cvt(boty[a]), fp::div(fp::cvt(botx[a]), d1));
+            ip.x = bxb;
+            double b1 = fp::sub(fp::cvt(bya), fp::div(fp::cvt(bxa), d1));
             ip.y = fp::round_half(fp::add(fp::div(fp::cvt(ip.x), d1), b1));
         } else {
-            double b1 = fp::sub(fp::cvt(botx[a]), fp::mul(fp::cvt(boty[a]), d1));
-            double b2 = fp::sub(fp::cvt(botx[b]), fp::mul(fp::cvt(boty[b]), d2));
+            double b1 = fp::sub(fp::cvt(bxa), fp::mul(fp::cvt(bya), d1));
+            double b2 = fp::sub(fp::cvt(bxb), fp::mul(fp::cvt(byb), d2));
             double q = fp::div(fp::sub(b2, b1), fp::sub(d1, d2));
             ip.y = fp::round_half(q);
             if (fabs(d1) < fabs(d2)) ip.x = fp::round_half(fp::add(fp::mul(d1, q), b1));
             else ip.x = fp::round_half(fp::add(fp::mul(d2, q), b2));
         }
-        if (ip.y < topy[a] || ip.y < topy[b]) {
-            ip.y = (topy[a] > topy[b]) ? topy[a] : topy[b];
-            ip.x = (fabs(d1) < fabs(d2)) ? top_x(a, ip.y) : top_x(b, ip.y);
+        if (ip.y < tya || ip.y < tyb) {
+            ip.y = (tya > tyb) ? tya : tyb;
+            ip.x = (fabs(d1) < fabs(d2)) ? top_x_of(bxa, bya, txa, tya, d1, ip.y) : top_x_of(bxb, byb, txb, tyb, d2, ip.y);
         }
         if (ip.y > cur_y) {
             ip.y = cur_y;
-            ip.x = (fabs(d1) > fabs(d2)) ? top_x(b, ip.y) : top_x(a, ip.y);
+            ip.x = (fabs(d1) > fabs(d2)) ? top_x_of(bxb, byb, txb, tyb, d2, ip.y) : top_x_of(bxa, bya, txa, tya, d1, ip.y);
         }
         return ip;
     }
@@ -288,16 +312,17 @@ struct ConvexSweep {
     {
         const int mp = e ^ 1;
         // GetMaximaPairEx :2548-2555: the other bound of the path ends at the same top vertex and is active
-        if (!(bit(act, mp) && bit(f_last, mp) && topx[mp] == topx[e] && topy[mp] == topy[e])) { set_bail(10); return; }
+        const P64 te = top(e), tm = top(mp);
+        if (!(bit(act, mp) && bit(f_last, mp) && tm == te)) { set_bail(10); return; }
         int en = nael(e);
         while (en != NILE && en != mp && !bail) {
-            intersect_edges(e, en, top(e));
+            intersect_edges(e, en, te);
             swap_in_ael(e, en);
             en = nael(e);
         }
         if (bail) return;
         if (!bit(f_out, e) && !bit(f_out, mp)) { delete_from_ael(e); delete_from_ael(mp); }
-        else if (bit(f_out, e) && bit(f_out, mp)) { add_local_max_poly(e, mp, top(e)); delete_from_ael(e); delete_from_ael(mp); }
+        else if (bit(f_out, e) && bit(f_out, mp)) { add_local_max_poly(e, mp, te); delete_from_ael(e); delete_from_ael(mp); }
         else set_bail(11);      // "DoMaxima error": let the general sweep report it
     }
 
@@ -311,28 +336,31 @@ struct ConvexSweep {
     SZ_HD bool begin(i64* wx, i64* wy, int wcap)
     {
         dqx = wx; dqy = wy; dcap = wcap; lo = hi = 0; n_or = 0; na = 0; n_il = 0; bail = false; why = 0; cur_lm = 0;
-        ordp = 0; act = f_right = f_out = f_wc2 = f_last = f_back = 0; cur_y = 0; fr.x = fr.y = bk.x = bk.y = 0;
+        ordp = 0; act = f_right = f_out = f_wc2 = f_last = f_back = 0; cur_y = 0; fr.x = fr.y = bk.x = bk.y = 0; sw = 0;
+        SZ_UNROLL4
+        for (int id = 0; id < 4; ++id) { botx[id] = boty[id] = topx[id] = topy[id] = curx[id] = 0; dx[id] = 0; vi[id] = 0; }
         if (n[0] < 3 || n[1] < 3 || n[0] > NV || n[1] > NV) { set_bail(17); return false; }
-        for (int p = 0; p < 2; ++p) {
+        // Reset :1247-1276: minima sorted by Y descending (std::sort of two elements is stable: the subject on a tie)
+        sw = (vy[1][0] > vy[0][0]) ? 1 : 0;
+        SZ_UNROLL4
+        for (int q = 0; q < 2; ++q) {
             // the two bounds of the path's single local minimum (AddPath :1172-1219): e = forward edge, e.prev = backward
             // edge; the left bound is the one with the larger Dx (:1192-1203)
-            const int l = 2 * p, r = 2 * p + 1;
+            const int l = 2 * q, r = 2 * q + 1;
             f_back |= 1u << r;
             load_edge(l, 0); load_edge(r, 0);
             if (bail) return false;
             if (dx[l] < dx[r]) {
                 f_back ^= (1u << l) | (1u << r);
-                i64 t; double d; int q;
+                i64 t; double d; int u;
                 t = topx[l]; topx[l] = topx[r]; topx[r] = t; t = topy[l]; topy[l] = topy[r]; topy[r] = t;
-                d = dx[l]; dx[l] = dx[r]; dx[r] = d; q = vi[l]; vi[l] = vi[r]; vi[r] = q;
+                d = dx[l]; dx[l] = dx[r]; dx[r] = d; u = vi[l]; vi[l] = vi[r]; vi[r] = u;
                 const bool ll = bit(f_last, l), lr = bit(f_last, r); set_flag(f_last, l, lr); set_flag(f_last, r, ll);
             }
             f_right |= 1u << r;
-            lm_y[p] = boty[l];
+            lm_y[q] = boty[l];
         }
-        // Reset :1247-1276: minima sorted by Y descending (std::sort of two elements is stable)
-        lm_first = (lm_y[1] > lm_y[0]) ? 1 : 0;
-        cur_y = lm_y[lm_first];
+        cur_y = lm_y[0];
         insert_local_minima(cur_y);
         if (bail) return false;
         // Scanbeams above which only the first path is active (its two bounds, not contributing: nothing can be
@@ -340,20 +368,19 @@ struct ConvexSweep {
         // only promotes the bound(s) whose top is reached (:3086-3111).  The one other thing it could do -- swap the two
         // bounds because their rounded TopX values invert (within a grid unit of the path's top) -- is outside the model.
         if (cur_lm == 1) {
-            const int l = 2 * lm_first, r = l + 1;
-            const i64 y2 = lm_y[1 - lm_first];
+            const i64 y2 = lm_y[1];
             for (;;) {
-                const i64 ty = topy[l] > topy[r] ? topy[l] : topy[r];
+                const i64 ty = topy[0] > topy[1] ? topy[0] : topy[1];
                 if (ty <= y2) break;
-                if (top_x(l, ty) > top_x(r, ty)) { set_bail(18); return false; }
+                if (top_x(0, ty) > top_x(1, ty)) { set_bail(18); return false; }
                 cur_y = ty;
-                if ((bit(f_last, l) && topy[l] == ty) || (bit(f_last, r) && topy[r] == ty)) {
+                if ((bit(f_last, 0) && topy[0] == ty) || (bit(f_last, 1) && topy[1] == ty)) {
                     // the first path ends below the bottom of the second: DoMaxima removes both bounds, the rest of the
                     // sweep sees the second path alone and outputs nothing
                     na = 0; act = 0; cur_lm = 2; return false;
                 }
-                if (topy[l] == ty) load_edge(l, vi[l]);
-                if (topy[r] == ty && !bail) load_edge(r, vi[r]);
+                if (topy[0] == ty) load_edge(0, vi[0]);
+                if (topy[1] == ty && !bail) load_edge(1, vi[1]);
                 if (bail) return false;
             }
         }
@@ -366,40 +393,29 @@ struct ConvexSweep {
         if (bail) return false;
         // PopScanbeam: the largest pending Y = tops of the active edges and pending local minima
         bool have = false; i64 top_y = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+        SZ_UNROLL4
         for (int id = 0; id < 4; ++id) if (bit(act, id)) { const i64 y = topy[id]; if (!have || y > top_y) { top_y = y; have = true; } }
-        if (cur_lm < 2) { const i64 y = lm_y[lm_poly(cur_lm)]; if (!have || y > top_y) { top_y = y; have = true; } }
+        if (cur_lm < 2) { const i64 y = lm_y[1]; if (!have || y > top_y) { top_y = y; have = true; } }
         if (!have) return false;
         // BuildIntersectList :2863-2868: Curr.X of every active edge at the top of the scanbeam
-        i64 xt[4];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int id = 0; id < 4; ++id) { xt[id] = bit(act, id) ? top_x(id, top_y) : 0; if (bit(act, id)) curx[id] = xt[id]; }
+        SZ_UNROLL4
+        for (int id = 0; id < 4; ++id) curx[id] = bit(act, id) ? top_x(id, top_y) : 0;
         bool inv = false;
-        for (int k = 0; k + 1 < na; ++k) {
-            const int e = ord_at(k), en = ord_at(k + 1);
-            const i64 xe = e == 0 ? xt[0] : e == 1 ? xt[1] : e == 2 ? xt[2] : xt[3];
-            const i64 xn = en == 0 ? xt[0] : en == 1 ? xt[1] : en == 2 ? xt[2] : xt[3];
-            inv = inv || (xe > xn);
-        }
+        for (int k = 0; k + 1 < na; ++k) inv = inv || (rd4(curx, ord_at(k)) > rd4(curx, ord_at(k + 1)));
         if (inv) {
             unsigned gt = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int q = 0; q < 16; ++q) { const int a = q >> 2, b = q & 3; if (a != b && bit(act, a) && bit(act, b) && xt[a] > xt[b]) gt |= 1u << q; }
+            SZ_UNROLL4
+            for (int a = 0; a < 4; ++a) {
+                SZ_UNROLL4
+                for (int b = 0; b < 4; ++b) if (a != b && bit(act, a) && bit(act, b) && curx[a] > curx[b]) gt |= 1u << (4 * a + b);
+            }
             intersections(top_y, gt);
             if (bail) return false;
         }
         cur_y = top_y;
         // ProcessEdgesAtTopOfScanbeam :3009-3113.  Curr of the edges that stay is already (TopX, topY).
         unsigned at_top = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+        SZ_UNROLL4
         for (int id = 0; id < 4; ++id) if (bit(act, id) && topy[id] == top_y) at_top |= 1u << id;
         if (at_top & f_last) {
             int i = 0;
@@ -419,12 +435,13 @@ struct ConvexSweep {
             prom &= ~(1u << e);
             const bool o = bit(f_out, e);
             if (o) add_out_pt(e, top(e));
-            load_edge(e, vi[e]);                                  // UpdateEdgeIntoAEL :1442-1462 (out, side, wc2 carry over)
+            load_edge(e, rd4(vi, e));                             // UpdateEdgeIntoAEL :1442-1462 (out, side, wc2 carry over)
             if (bail) return false;
             if (o) {
                 const int ep = (k > 0) ? ord_at(k - 1) : NILE, en = (k + 1 < na) ? ord_at(k + 1) : NILE;
-                if (ep != NILE && curx[ep] == botx[e] && cur_y == boty[e] && bit(f_out, ep) && cur_y > topy[ep] && szclip::slopes_eq4(cur(e), top(e), cur(ep), top(ep))) { set_bail(12); return false; }
-                if (en != NILE && curx[en] == botx[e] && cur_y == boty[e] && bit(f_out, en) && cur_y > topy[en] && szclip::slopes_eq4(cur(e), top(e), cur(en), top(en))) { set_bail(13); return false; }
+                const P64 be = bot(e);
+                if (ep != NILE && rd4(curx, ep) == be.x && cur_y == be.y && bit(f_out, ep) && cur_y > rd4(topy, ep) && szclip::slopes_eq4(cur(e), top(e), cur(ep), top(ep))) { set_bail(12); return false; }
+                if (en != NILE && rd4(curx, en) == be.x && cur_y == be.y && bit(f_out, en) && cur_y > rd4(topy, en) && szclip::slopes_eq4(cur(e), top(e), cur(en), top(en))) { set_bail(13); return false; }
             }
         }
         insert_local_minima(top_y);
