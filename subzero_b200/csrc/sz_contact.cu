@@ -109,7 +109,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> listC, listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
+    DBuf<int> stage, listC, listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -309,6 +309,7 @@ struct BroadArgs {
     const int* egid; const uint8_t* eowned; const double* erootx; const double* erooty;
     const int* cell_start; const int* s_idx; const double* s_x; const double* s_y; const double* s_r;
     int* pcnt; const int* pair_off; int* pi; int* pj;
+    int* stage; int stage_cap;     // count pass: the first stage_cap partners of every floe, so that the fill pass need not search again
 };
 // The predicate of floe_interactions_all.m:103 for partner j of floe i (j > i checked by the caller):
 //   alive(j) && sqrt((xi-xj)^2+(yi-yj)^2) < rmax_i+rmax_j && (~ismember(|FloeNums(j)|,mems) || 2(rmax_i+rmax_j) > min(2Lx,2Ly))
@@ -341,7 +342,14 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
     const bool own_i = b.eowned[i] != 0;
     int count = 0;
     const int off = FILL ? b.pair_off[i] : 0;
-    if (active) {
+    bool staged = false;
+    if (FILL && b.stage) {
+        count = b.pair_off[i + 1] - off;
+        staged = count <= b.stage_cap;
+        if (staged && lane < count) b.pj[off + lane] = b.stage[(size_t)i * b.stage_cap + lane];      // stage_cap <= 32
+        if (!staged) count = 0;
+    }
+    if (active && !staged) {
         const double ri = b.rmax[b.esrc[i]];
         const int cxi = cell_coord(xi, b.g.x0, b.g.cell, b.g.nx), cyi = cell_coord(yi, b.g.y0, b.g.cell, b.g.ny);
         // a partner has |dx|, |dy| < ri + rmax_j <= ri + max(rmax): that many cells each way (floor differences <= ceil)
@@ -364,6 +372,7 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (FILL && ok) b.pj[off + count + __popc(m & ((1u << lane) - 1))] = j;
+                if (!FILL && ok && b.stage) { const int k = count + __popc(m & ((1u << lane) - 1)); if (k < b.stage_cap) b.stage[(size_t)i * b.stage_cap + k] = j; }
                 count += __popc(m);
             }
         }
@@ -455,7 +464,7 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
                                      const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
                                      int* __restrict__ listC, int* __restrict__ listS, const double* __restrict__ ex, const double* __restrict__ ey,
-                                     int* __restrict__ bins, int* __restrict__ bin_fill, short* __restrict__ pkey, Counters* c)
+                                     int* __restrict__ bins, int* __restrict__ bin_fill, short* __restrict__ pkey, Counters* c, int cvx_key_mode)
 {
     // per bucket: pairs of strictly convex outlines (class C) in the high half-word, the others (class S) in the low one
     __shared__ int sh[SZ_NBINS];
@@ -481,7 +490,17 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
             // pairs of one bucket have the same vertex counts and the partner in the same octant: similar event orders
             const double dx = ex[j] - ex[i], dy = ey[j] - ey[i];
             const double adx = fabs(dx), ady = fabs(dy), mn = adx < ady ? adx : ady, mx = adx < ady ? ady : adx;
-            const int oct = (dx > 0) | ((dy > 0) << 1) | ((adx > ady) << 2) | ((mn > 0.41421356237309503 * mx) << 3);
+            int oct = (dx > 0) | ((dy > 0) << 1) | ((adx > ady) << 2) | ((mn > 0.41421356237309503 * mx) << 3);
+            if (cvx && cvx_key_mode == 1) {
+                // class C sweeps one scanbeam per CTA-synchronous iteration, and only over the Y range the two outlines
+                // share: bucket by the number of vertices in that range (= iterations) instead of the direction
+                const double lo = (double)(a[2] > b[2] ? a[2] : b[2]), hi = (double)(a[3] < b[3] ? a[3] : b[3]);
+                int cnt = 0;
+                const int oi = voff[esrc[i]], oj = voff[esrc[j]];
+                for (int t = 0; t < eno[i]; ++t) { const double y = (vy[oi + t] + ey[i]) * SZ_SCALE; cnt += (y >= lo && y <= hi); }
+                for (int t = 0; t < eno[j]; ++t) { const double y = (vy[oj + t] + ey[j]) * SZ_SCALE; cnt += (y >= lo && y <= hi); }
+                oct = cnt < SZ_NSECT ? cnt : SZ_NSECT - 1;
+            }
             key = (ni * SZ_BIN_N + nj) * SZ_NSECT + oct;
             atomicAdd(&sh[key], cvx ? 65536 : 1);
         }
@@ -779,7 +798,7 @@ extern "C" void sz_destroy(SzContext* c)
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
-                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
+                       &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->stage, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
@@ -1013,13 +1032,14 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     a.next_list = lstT; a.next_count = cntT;
     if (!wall) {
         // work list of class S: bounding-box-disjoint pairs answered, the rest bucketed by vertex counts and direction
+        static const int key_mode = getenv("SZ_CVX_KEY") ? atoi(getenv("SZ_CVX_KEY")) : 1;   // 0: direction sectors for class C too (experiments)
         CK(c->bins.ensure(2 * SZ_NBINS)); CK(c->bin_fill.ensure(2 * SZ_NBINS));
         CK(cudaMemsetAsync(c->bins.p, 0, 2 * SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, 2 * SZ_NBINS * sizeof(int), st));
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt, key_mode);
         bins_scan_kernel<<<2, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
         pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt);
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt, key_mode);
         g_launches += 3;
         // class C: strictly convex pairs through the four-edge sweep; what it declines is appended to class S's list.
         // Both launches are sized for all pairs (the list lengths are only known on the device; surplus CTAs exit at once).
@@ -1166,6 +1186,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         b.egid = c->egid.p; b.eowned = c->eowned.p; b.erootx = c->erootx.p; b.erooty = c->erooty.p;
         b.cell_start = c->cell_start.p; b.s_idx = c->s_idx.p; b.s_x = c->s_x.p; b.s_y = c->s_y.p; b.s_r = c->s_r.p;
         b.pcnt = c->pcnt.p; b.pair_off = c->pair_off.p;
+        static const int stage_cap = getenv("SZ_BROAD_STAGE") ? atoi(getenv("SZ_BROAD_STAGE")) : 16;     // 0: the fill pass searches again
+        if (stage_cap > 0) { CK(c->stage.ensure((size_t)n * stage_cap + 1)); b.stage = c->stage.p; b.stage_cap = stage_cap > 32 ? 32 : stage_cap; }
         { ++g_launches; broad_kernel<false><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
     }
     exclusive_scan(c->pcnt.p, n, c->pair_off.p, n + 1, c->scan_tmp.p, st);
