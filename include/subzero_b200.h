@@ -219,6 +219,18 @@ int sz_get_trajectory(SzContext* ctx, double* x, double* y, double* u, double* v
  * [2] narrow phase + force law (:125-174)           [3] mirror/torque/sums (:186-265)   [4] whole step */
 int sz_get_phase_ms(SzContext* ctx, float* ms5);
 
+/* diagnostic: device time (CUDA events on the library's stream, ms) of the narrow-phase kernel launches of the last
+ * step, by size class: [0] class C (strictly convex pairs, four-edge sweep)   [1] class S   [2] class T
+ * [3] class M   [4] class L; and how many pairs each class received in pairs5 (either pointer may be NULL).
+ * Pairs a class declines or cannot hold are counted again in the class that re-runs them. */
+int sz_get_narrow_class_ms(SzContext* ctx, float* ms5, int32_t* pairs5);
+
+/* run-time switches of the context (experiments and tests; the defaults are the product configuration):
+ *   "convex_fast"  1 (default): strictly convex floe-floe pairs go through class C first; 0: everything through the
+ *                  general sweep of class S.  Results are bit-identical either way (tests/test_gpu_parity.py).
+ * Returns SZ_ERR_ARG for an unknown name. */
+int sz_set_option(SzContext* ctx, const char* name, int32_t value);
+
 /* ---- stand-alone polygon clip with the gateway's semantics (private/mexclipper.cpp:204-305):
  * `count` independent (subject, clip) pairs, one closed path each, int64 coordinates, even-odd fill,
  * method 0 dif / 1 int / 2 xor / 3 uni (mexclipper.cpp:206-230).  Runs the same device sweep as the

@@ -105,6 +105,15 @@ class ContactContext:
         abi.check(abi.lib().sz_get_phase_ms(self._h, a))
         return dict(zip(("ghosts", "broad", "narrow", "assembly", "total"), [float(v) for v in a]))
 
+    def narrow_class_ms(self):
+        """device ms of the narrow-phase kernel launch of every size class in the last step, and the pairs each received"""
+        a, n = (C.c_float * 5)(), (C.c_int32 * 5)()
+        abi.check(abi.lib().sz_get_narrow_class_ms(self._h, a, n))
+        return {k: (float(a[i]), int(n[i])) for i, k in enumerate(("C", "S", "T", "M", "L"))}
+
+    def set_option(self, name, value):
+        abi.check(abi.lib().sz_set_option(self._h, name.encode(), int(value)))
+
     def clip_polys(self):
         s = self.summary
         ppo = np.empty(s.n_pairs + 1, np.int64)

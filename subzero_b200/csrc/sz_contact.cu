@@ -76,6 +76,7 @@ struct Counters {
     int n_pairs;
     int row_used, path_used, vert_used;
     int listC, listS, listT, listM, listL, wlistT, wlistM, wlistL;
+    int listC0, listS0;            // list lengths before class C ran (listS grows by the pairs class C declines)
     int total_rows;
     int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject;
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
@@ -89,6 +90,9 @@ struct SzContext {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
     float phase_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t evk[10] = {};                  // start/stop of the narrow-phase launch of each size class (C, S, T, M, L)
+    bool evk_used[5] = {false, false, false, false, false}; int class_pairs[5] = {0, 0, 0, 0, 0};
+    int opt_convex_fast = 1;
     Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
     // inputs
     bool have_input = false, have_step = false;
@@ -782,6 +786,7 @@ extern "C" int sz_create(SzContext** out, int device)
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     for (auto& e : c->evp) CK(cudaEventCreate(&e));
+    for (auto& e : c->evk) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&c->d_cnt, sizeof(Counters)));
     CK(cudaMallocHost(&c->h_cnt, sizeof(Counters)));
     memset(&c->summary, 0, sizeof(c->summary));
@@ -816,6 +821,7 @@ extern "C" void sz_destroy(SzContext* c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto& e : c->evp) if (e) cudaEventDestroy(e);
+    for (auto& e : c->evk) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1043,21 +1049,30 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         g_launches += 3;
         // class C: strictly convex pairs through the four-edge sweep; what it declines is appended to class S's list.
         // Both launches are sized for all pairs (the list lengths are only known on the device; surplus CTAs exit at once).
-        static const bool no_fast = getenv("SZ_NO_CONVEX_FAST") != nullptr;      // experiment switch: everything through class S
+        static const bool env_no_fast = getenv("SZ_NO_CONVEX_FAST") != nullptr;      // experiment switch: everything through class S
+        const bool no_fast = env_no_fast || !c->opt_convex_fast;
         a.list = c->listC.p; a.list_count = D_CNT(listC); a.next_list = c->listS.p; a.next_count = D_CNT(listS);
+        CK(cudaMemcpyAsync(D_CNT(listC0), D_CNT(listC), 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(D_CNT(listS0), D_CNT(listS), 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaEventRecord(c->evk[0], st));
         if (!no_fast) { ++g_launches; sz_launch_narrow_C(&a, st); CK(cudaGetLastError()); }
         else { a.list = c->listC.p; a.next_list = lstT; a.next_count = cntT; ++g_launches; sz_launch_narrow_S(&a, st); CK(cudaGetLastError()); }
+        CK(cudaEventRecord(c->evk[1], st)); c->evk_used[0] = true;
         a.list = c->listS.p; a.list_count = D_CNT(listS); a.next_list = lstT; a.next_count = cntT;
     }
+    if (!wall) CK(cudaEventRecord(c->evk[2], st));
     ++g_launches; sz_launch_narrow_S(&a, st);
+    if (!wall) { CK(cudaEventRecord(c->evk[3], st)); c->evk_used[1] = true; }
     a.list = nullptr; a.list_count = nullptr;
     CK(cudaGetLastError());
     CKS(read_counters(c));
+    if (!wall) { c->class_pairs[0] = c->h_cnt->listC0; c->class_pairs[1] = c->h_cnt->listS; }
     const int nT = wall ? c->h_cnt->wlistT : c->h_cnt->listT;
     if (nT > 0) {
         // class T: pairs that did not fit class S, arena still in local memory
         a.list = lstT; a.list_count = cntT; a.n_work = nT; a.next_list = lstM; a.next_count = cntM;
+        if (!wall) { CK(cudaEventRecord(c->evk[4], st)); c->class_pairs[2] = nT; }
         ++g_launches; sz_launch_narrow_T(&a, st);
+        if (!wall) { CK(cudaEventRecord(c->evk[5], st)); c->evk_used[2] = true; }
         a.list = nullptr; a.list_count = nullptr;
         CK(cudaGetLastError());
         CKS(read_counters(c));
@@ -1073,8 +1088,10 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
         a.list = lstM; a.list_count = cntM; a.next_list = lstL; a.next_count = cntL; a.scratch = c->scratchM.p; a.n_threads = threads;
         if (dbg) cudaEventRecord(d0, st);
+        if (!wall) { CK(cudaEventRecord(c->evk[6], st)); c->class_pairs[3] = nM; }
         ++g_launches; sz_launch_narrow_M(&a, st);
         CK(cudaGetLastError());
+        if (!wall) { CK(cudaEventRecord(c->evk[7], st)); c->evk_used[3] = true; }
         if (dbg) cudaEventRecord(d1, st);
         CKS(read_counters(c));
         if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class M: %d pairs on %d threads, %.2f ms\n", nM, threads, dms); }
@@ -1085,8 +1102,10 @@ static int run_narrow(SzContext* c, int wall, int n_work)
             CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
             a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
             if (dbg) cudaEventRecord(d0, st);
+            if (!wall) { CK(cudaEventRecord(c->evk[8], st)); c->class_pairs[4] = nL; }
             ++g_launches; sz_launch_narrow_L(&a, st);
             CK(cudaGetLastError());
+            if (!wall) { CK(cudaEventRecord(c->evk[9], st)); c->evk_used[4] = true; }
             if (dbg) cudaEventRecord(d1, st);
             CKS(read_counters(c));
             if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class L: %d pairs on %d threads, %.2f ms\n", nL, threadsL, dms); }
@@ -1212,11 +1231,12 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     }
     for (int attempt = 0; attempt < 3; ++attempt) {
         Counters z = *c->h_cnt;
-        z.row_used = z.path_used = z.vert_used = z.n_bbox_reject = z.listC = z.listS = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
+        z.row_used = z.path_used = z.vert_used = z.n_bbox_reject = z.listC = z.listS = z.listC0 = z.listS0 = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
 
         *c->h_cnt = z;
         CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
         CK(cudaMemsetAsync(c->pstatus.p, 0, (size_t)(np + 1) * 4, st)); CK(cudaMemsetAsync(c->pnrows.p, 0, (size_t)(np + 1) * 4, st));
+        for (int k = 0; k < 5; ++k) { c->evk_used[k] = false; c->class_pairs[k] = 0; }
         if (np > 0) CKS(run_narrow(c, 0, np));
         if (wall) {
             // floes below Nb take no part in the wall call (:125 loops i = 1+Nb:N)
@@ -1519,6 +1539,24 @@ extern "C" int sz_get_phase_ms(SzContext* c, float* ms5)
     NEED_STEP("sz_get_phase_ms");
     if (ms5) for (int k = 0; k < 5; ++k) ms5[k] = c->phase_ms[k];
     return SZ_OK;
+}
+extern "C" int sz_get_narrow_class_ms(SzContext* c, float* ms5, int32_t* pairs5)
+{
+    NEED_STEP("sz_get_narrow_class_ms");
+    for (int k = 0; k < 5; ++k) {
+        float ms = 0;
+        if (c->evk_used[k]) CK(cudaEventElapsedTime(&ms, c->evk[2 * k], c->evk[2 * k + 1]));
+        if (ms5) ms5[k] = ms;
+        if (pairs5) pairs5[k] = c->class_pairs[k];
+    }
+    return SZ_OK;
+}
+extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
+{
+    if (!c || !name) { sz_set_error("sz_set_option: NULL argument"); return SZ_ERR_ARG; }
+    if (strcmp(name, "convex_fast") == 0) { c->opt_convex_fast = value != 0; return SZ_OK; }
+    sz_set_error("sz_set_option: unknown option '%s'", name);
+    return SZ_ERR_ARG;
 }
 // reorder (start, count) pools into item-major CSR
 static int export_paths(SzContext* c, int n_items, const int* d_item_start, const int* d_item_np, const int* d_status, const int* d_path_vstart, const int* d_path_len,

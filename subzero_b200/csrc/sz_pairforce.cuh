@@ -527,10 +527,12 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
         }
         SZ_LANE_SYNC();
         if (go) run = cs.begin(w.rbx, w.rby, C::RV);
+#ifndef SZ_C_STEPS_PER_SYNC
+#define SZ_C_STEPS_PER_SYNC 1
+#endif
         for (;;) {
             if (!SZ_WARP_ANY(run)) break;
-            if (run) run = cs.step();
-            SZ_LANE_SYNC();
+            for (int u = 0; u < SZ_C_STEPS_PER_SYNC; ++u) { if (run) run = cs.step(); SZ_LANE_SYNC(); }
         }
         if (go) {
             int n_out = 0;
@@ -542,7 +544,11 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
     // `continue`): the lanes of a warp resolve different pairs, and a block that one lane leaves early must not make
     // the others run the rest of the body one lane at a time (first profile: InterX ran with 1.2 of 32 lanes active).
     for (;;) {
+#if defined(SZ_FAST_MAIN_WARP) && defined(__CUDA_ARCH__)
+        if (!(FAST ? __any_sync(0xffffffffu, phase != PH_DONE) : SZ_WARP_ANY(phase != PH_DONE))) break;
+#else
         if (!SZ_WARP_ANY(phase != PH_DONE)) break;
+#endif
         // ---- the clip this lane needs now
         ClipInput subj, clip;
         subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = w.n1; subj.ring = 0; subj.rot = 0;

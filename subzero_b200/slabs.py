@@ -513,6 +513,7 @@ class SlabJob:
         self.summary = s
         self.pairs_owned, self.pairs_force_total = int(s.n_pairs_owned), int(s.n_pairs_force)
         ph = self.ctx.phase_ms()
+        ph["classes"] = self.ctx.narrow_class_ms()     # per size class: (kernel ms, pairs)
         self.rows_owned = int(s.n_rows)
         self.ext_entries_owned = int(s.n) if self.step is None else int((self.step.local.owned != 0).sum())
         return ms, ph

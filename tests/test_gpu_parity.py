@@ -46,6 +46,40 @@ def test_shortcuts_thin_and_deep_overlaps(ctx, inflate, seed):
         assert (ref.floe_outputs()["kill"] > 0).sum() > 0
 
 
+@pytest.mark.parametrize("inflate,seed", [(0.02, 51), (0.0, 52), (0.0003, 53), (0.35, 54)])
+def test_class_c_equals_class_s(ctx, inflate, seed):
+    """the convex fast path (class C: four-edge sweep + certified sign test) against the general sweep (class S) on the
+    same field: Clipper polygons, pair states and contact rows must be identical bit for bit, and both equal the oracle.
+    inflate 0.02 is the benchmark geometry (class C keeps practically every pair); 0.0 (exactly shared edges) and 0.0003
+    (strips thinner than the 1 m nudge) make class C decline pairs, which class S then re-runs."""
+    prm, soa = sz.voronoi_field(8000, seed=seed, inflate=inflate)
+    prm.want_clip_polys = 1
+    res = {}
+    for fast in (1, 0):
+        ctx.set_option("convex_fast", fast)
+        try:
+            ctx.step(prm, soa, allow_pair_errors=True)
+        finally:
+            ctx.set_option("convex_fast", 1)
+        cls = ctx.narrow_class_ms()
+        res[fast] = (ctx.pairs(), ctx.rows(), ctx.clip_polys(), cls)
+        if fast:
+            ref = oracle.OracleStep(prm, soa, broad_mode=1)
+            oracle.compare_steps(ctx, ref, rtol=RTOL)
+    (p1, r1, c1, k1), (p0, r0, c0, k0) = res[1], res[0]
+    for key in ("i", "j", "status", "n_regions", "overlap_state"):
+        assert np.array_equal(p1[key], p0[key]), key
+    assert np.array_equal(r1[0], r0[0]) and np.array_equal(r1[1], r0[1], equal_nan=True)
+    for a, b in zip(c1, c0):
+        assert np.array_equal(a, b)
+    n_c, n_s = k1["C"][1], k1["S"][1]
+    assert n_c > 10000 and k0["C"][1] == n_c                       # with the switch off the same list runs in class S
+    if inflate == 0.02:
+        assert n_s < 0.01 * n_c, (n_c, n_s)                        # the benchmark geometry stays on the fast path
+    if inflate == 0.0:
+        assert n_s > 0                                             # shared edges: some pairs are declined and re-run
+
+
 def test_uninflated_voronoi_shared_edges_give_no_polygons(ctx):
     """exactly shared edges: every Clipper intersection must come back empty, as in the reference"""
     prm, soa = sz.voronoi_field(3000, seed=4, inflate=0.0)
