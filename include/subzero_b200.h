@@ -225,6 +225,12 @@ int sz_get_phase_ms(SzContext* ctx, float* ms5);
  * Pairs a class declines or cannot hold are counted again in the class that re-runs them. */
 int sz_get_narrow_class_ms(SzContext* ctx, float* ms5, int32_t* pairs5);
 
+/* Makes every launch and copy of the context go to the caller's CUDA stream (a cudaStream_t; 0 or NULL restores the
+ * context's own non-blocking stream -- pass cudaStreamLegacy, i.e. (cudaStream_t)1, to name the default stream).  With a caller-provided stream the library's work is ordered with the caller's own
+ * kernels and collectives by the stream alone, without host synchronisation (used by the multi-GPU slab step, whose halo
+ * exchange runs on the caller's stream).  Synchronises the previous stream once. */
+int sz_set_stream(SzContext* ctx, void* cuda_stream);
+
 /* run-time switches of the context (experiments and tests; the defaults are the product configuration):
  *   "convex_fast"  1 (default): strictly convex floe-floe pairs go through class C first; 0: everything through the
  *                  general sweep of class S.  Results are bit-identical either way (tests/test_gpu_parity.py).

@@ -111,6 +111,15 @@ class ContactContext:
         abi.check(abi.lib().sz_get_narrow_class_ms(self._h, a, n))
         return {k: (float(a[i]), int(n[i])) for i, k in enumerate(("C", "S", "T", "M", "L"))}
 
+    def set_stream(self, cuda_stream):
+        """route the library's launches to the caller's CUDA stream: an integer handle such as torch's `cuda_stream`, where
+        0 means the (legacy) default stream as it does in torch; None restores the context's own stream"""
+        if cuda_stream is None:
+            h = None
+        else:
+            h = int(cuda_stream) or 1                 # cudaStreamLegacy
+        abi.check(abi.lib().sz_set_stream(self._h, C.c_void_p(h)))
+
     def set_option(self, name, value):
         abi.check(abi.lib().sz_set_option(self._h, name.encode(), int(value)))
 

@@ -87,7 +87,8 @@ struct Counters {
 
 struct SzContext {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // the stream every launch and copy of the library goes to
+    cudaStream_t own_stream = nullptr;      // created by sz_create; `stream` points elsewhere after sz_set_stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
     float phase_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t evk[10] = {};                  // start/stop of the narrow-phase launch of each size class (C, S, T, M, L)
@@ -261,12 +262,12 @@ __device__ __host__ __forceinline__ double dec_d(u64 b) { b = (b >> 63) ? (b & 0
 __global__ void bbox_kernel(int n_bound, const int* __restrict__ n_dev, const double* __restrict__ ex, const double* __restrict__ ey,
                             const int* __restrict__ esrc, const double* __restrict__ rmax, Counters* c)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *n_dev;
     double xmn = SZ_INF, xmx = -SZ_INF, ymn = SZ_INF, ymx = -SZ_INF, rm = 0;
-    if (i < n_bound && i < n) {
+    // grid-stride: a few thousand warps, one set of atomics each (one warp per 32 floes serialised on five addresses)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bound && i < n; i += gridDim.x * blockDim.x) {
         const double x = ex[i], y = ey[i];
-        if (x == x && y == y) { xmn = xmx = x; ymn = ymx = y; }
+        if (x == x && y == y) { xmn = fmin(xmn, x); xmx = fmax(xmx, x); ymn = fmin(ymn, y); ymx = fmax(ymx, y); }
         const double r = rmax[esrc[i]]; if (r > rm) rm = r;
     }
 #pragma unroll
@@ -746,15 +747,22 @@ __global__ void kill_final_kernel(int n0, const int* __restrict__ kill_i, const 
 __global__ void pair_stats_kernel(int np, const int* __restrict__ status, const int* __restrict__ nrows, const int* __restrict__ pi, const uint8_t* __restrict__ eowned,
                                   int count_force, Counters* c)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     int f = 0, e = 0, k = 0, u = 0;
-    if (p < np && eowned[pi ? pi[p] : p]) { u = 1; const int s = status[p]; f = (s == 0 && nrows[p] > 0); e = (s == szpf::PS_CLIPPER_FAIL || s == szpf::PS_BAD_POLY); k = (s == szpf::PS_CAPACITY); }
-    const unsigned mf = __ballot_sync(0xffffffffu, f), me = __ballot_sync(0xffffffffu, e), mk = __ballot_sync(0xffffffffu, k), mu = __ballot_sync(0xffffffffu, u);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        if (!eowned[pi ? pi[p] : p]) continue;
+        const int s = status[p];
+        ++u; f += (s == 0 && nrows[p] > 0); e += (s == szpf::PS_CLIPPER_FAIL || s == szpf::PS_BAD_POLY); k += (s == szpf::PS_CAPACITY);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        f += __shfl_xor_sync(0xffffffffu, f, d); e += __shfl_xor_sync(0xffffffffu, e, d);
+        k += __shfl_xor_sync(0xffffffffu, k, d); u += __shfl_xor_sync(0xffffffffu, u, d);
+    }
     if ((threadIdx.x & 31) == 0) {
-        if (mu && count_force) atomicAdd(&c->n_pairs_owned, __popc(mu));
-        if (mf && count_force) atomicAdd(&c->n_pairs_force, __popc(mf));
-        if (me) atomicAdd(&c->n_fail, __popc(me));
-        if (mk) atomicAdd(&c->n_cap_fail, __popc(mk));
+        if (u && count_force) atomicAdd(&c->n_pairs_owned, u);
+        if (f && count_force) atomicAdd(&c->n_pairs_force, f);
+        if (e) atomicAdd(&c->n_fail, e);
+        if (k) atomicAdd(&c->n_cap_fail, k);
     }
 }
 
@@ -783,7 +791,7 @@ extern "C" int sz_create(SzContext** out, int device)
     CK(cudaSetDevice(device));
     SzContext* c = new SzContext;
     c->device = device;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)); c->stream = c->own_stream;
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     for (auto& e : c->evp) CK(cudaEventCreate(&e));
     for (auto& e : c->evk) CK(cudaEventCreate(&e));
@@ -822,7 +830,7 @@ extern "C" void sz_destroy(SzContext* c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto& e : c->evp) if (e) cudaEventDestroy(e);
     for (auto& e : c->evk) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -990,7 +998,7 @@ extern "C" int sz_slab_refresh(SzContext* c, const SzSlabRefresh* r)
     CK(cudaMemsetAsync(r->bad_out, 0, 4, c->stream));
     if (n_own > 0) { ++g_launches; slab_refresh_kernel<<<nblk(n_own, 256), 256, 0, c->stream>>>(*r); }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
+    if (c->stream == c->own_stream) CK(cudaStreamSynchronize(c->stream));      // a caller-provided stream orders the consumers itself
     return SZ_OK;
 }
 extern "C" int sz_slab_scatter(SzContext* c, const double* own, int64_t n_own, const double* recv, int64_t n_recv, const int64_t* order, int64_t n_local)
@@ -1164,7 +1172,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     } else if (ncap > 0) {
         ++g_launches; finish_extended_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->x.p, c->y.p, c->esrc.p, c->egid.p, c->eowned.p, c->erootx.p, c->erooty.p);
     }
-    if (ncap > 0) { ++g_launches; bbox_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->d_cnt); }
+    if (ncap > 0) { ++g_launches; bbox_kernel<<<std::min(nblk(ncap, 256), 148 * 8), 256, 0, st>>>(ncap, D_CNT(n), c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->d_cnt); }
     CK(cudaGetLastError());
     CKS(read_counters(c));
     const int n = c->h_cnt->n; c->n = n; c->n1 = c->h_cnt->n1;
@@ -1211,6 +1219,10 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     }
     exclusive_scan(c->pcnt.p, n, c->pair_off.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemcpyAsync(D_CNT(n_pairs), c->pair_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
+    // per-entry preparation of the narrow phase (bounding boxes, convexity): independent of the pair list, so it is queued
+    // before the host waits for the pair count
+    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1));
+    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p); }
     CK(cudaGetLastError());
     CKS(read_counters(c));
     const int np = c->h_cnt->n_pairs; c->n_pairs = np;
@@ -1219,8 +1231,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CK(cudaEventRecord(c->evp[1], st));
-    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1)); CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
-    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p); }
+    CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
     if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistT.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }
@@ -1243,7 +1254,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
             CK(cudaMemsetAsync(c->wstatus.p, 0, (size_t)(n + 1) * 4, st)); CK(cudaMemsetAsync(c->wnrows.p, 0, (size_t)(n + 1) * 4, st));
             if (n > 0) CKS(run_narrow(c, 1, n));
         }
-        CKS(read_counters(c));
+        // run_narrow ends with a counter read-back and nothing was launched since: the host copy is current
         bool again = false;
         if ((size_t)c->h_cnt->row_used * 5 > c->row_pool.cap) { CK(c->row_pool.ensure((size_t)c->h_cnt->row_used * 5 + 1024)); again = true; }
         if (P.want_clip_polys) {
@@ -1294,8 +1305,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
             CK(cudaMemcpyAsync(c->o_kill.p, c->kill_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->o_transfer.p, c->transfer_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st));
         }
         if (nout > 0) { ++g_launches; fold_kernel<<<nblk(nout, 256), 256, 0, st>>>(nout, Nb, c->egid.p, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p); }
-        if (np > 0) { ++g_launches; pair_stats_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, c->pi.p, c->eowned.p, 1, c->d_cnt); }
-        if (wall) { ++g_launches; pair_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, nullptr, c->eowned.p, 0, c->d_cnt); }
+        if (np > 0) { ++g_launches; pair_stats_kernel<<<std::min(nblk(np, 256), 148 * 8), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, c->pi.p, c->eowned.p, 1, c->d_cnt); }
+        if (wall) { ++g_launches; pair_stats_kernel<<<std::min(nblk(n, 256), 148 * 8), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, nullptr, c->eowned.p, 0, c->d_cnt); }
     }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
@@ -1549,6 +1560,14 @@ extern "C" int sz_get_narrow_class_ms(SzContext* c, float* ms5, int32_t* pairs5)
         if (ms5) ms5[k] = ms;
         if (pairs5) pairs5[k] = c->class_pairs[k];
     }
+    return SZ_OK;
+}
+extern "C" int sz_set_stream(SzContext* c, void* cuda_stream)
+{
+    if (!c) { sz_set_error("sz_set_stream: NULL context"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;      // (cudaStreamLegacy / cudaStreamPerThread are valid handles)
     return SZ_OK;
 }
 extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)

@@ -362,9 +362,17 @@ class SlabStep:
         self.local = None
         self._first = None
         self.summary = None
+        self._shared_stream = False
+        if st.x.is_cuda and comm.dist is not None and not comm.stage:
+            # NCCL's exchange is ordered on torch's current stream: let the library launch there too, so that refresh ->
+            # exchange -> scatter -> step need no host synchronisation between them
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            self._shared_stream = True
 
     def _refresh_on_device(self):
-        """refresh_local_state with the list surgery done by the library's slab kernels (CUDA tensors)"""
+        """refresh_local_state with the list surgery done by the library's slab kernels (CUDA tensors).  Returns the
+        device flag "the plan is stale on some rank" (already all-reduced); the caller reads it after the step, which it
+        repeats with a new plan in that rare case, instead of stalling the pipeline before the exchange."""
         st, prm, plan, comm = self.st, self.prm, self.local.plan, self.comm
         P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ) if t is not None and t.numel() else None
         dev = st.x.device
@@ -372,27 +380,35 @@ class SlabStep:
             u8 = lambda t: t.to(torch.uint8).contiguous() if t is not None else None
             plan.update(own_buf=torch.empty((plan["n_own"], 7), dtype=F64, device=dev), bad_buf=torch.zeros(1, dtype=torch.int32, device=dev),
                         fx8=u8(plan["fx"]), fy8=u8(plan["fy"]), xg_c=plan["xg_par"].contiguous(), yg_c=plan["yg_par"].contiguous(), order_c=plan["order"].contiguous())
-        r = abi.SzSlabRefresh()
-        r.n_orig, r.n_xg, r.n_yg = st.n, int(plan["xg_c"].shape[0]), int(plan["yg_c"].shape[0])
-        for nm, t in (("x", st.x), ("y", st.y), ("u", st.u), ("v", st.v), ("ksi", st.ksi), ("minvx", st.ext[0]), ("maxvx", st.ext[1]), ("minvy", st.ext[2]), ("maxvy", st.ext[3]),
-                      ("x0", plan["x0"]), ("y0", plan["y0"])):
-            setattr(r, nm, P(t.contiguous(), abi.c_dp))
-        r.alive = P(st.alive, abi.c_bp)
-        r.xg_par, r.yg_par = P(plan["xg_c"], abi.c_lp), P(plan["yg_c"], abi.c_lp)
-        r.fx_plan, r.fy_plan = P(plan["fx8"], abi.c_bp), P(plan["fy8"], abi.c_bp)
-        r.Lx, r.Ly, r.half_skin, r.periodic = prm.Lx, prm.Ly, 0.5 * plan["skin"], int(bool(prm.periodic))
-        r.own_out, r.bad_out = P(plan["own_buf"], abi.c_dp), P(plan["bad_buf"], abi.c_ip)
-        torch.cuda.current_stream().synchronize()
+        srcs = (st.x, st.y, st.u, st.v, st.ksi, st.ext[0], st.ext[1], st.ext[2], st.ext[3], plan["x0"], plan["y0"], st.alive)
+        key = tuple(t.data_ptr() for t in srcs) + tuple(t.is_contiguous() for t in srcs)
+        if plan.get("_refresh_key") != key or not all(key[len(srcs):]):
+            # the descriptor only holds pointers: it is rebuilt when a state tensor was replaced (not when it was updated in place)
+            r = abi.SzSlabRefresh()
+            r.n_orig, r.n_xg, r.n_yg = st.n, int(plan["xg_c"].shape[0]), int(plan["yg_c"].shape[0])
+            keep = []
+            for nm, t in zip(("x", "y", "u", "v", "ksi", "minvx", "maxvx", "minvy", "maxvy", "x0", "y0"), srcs[:11]):
+                t = t.contiguous(); keep.append(t)
+                setattr(r, nm, P(t, abi.c_dp))
+            r.alive = P(st.alive, abi.c_bp)
+            r.xg_par, r.yg_par = P(plan["xg_c"], abi.c_lp), P(plan["yg_c"], abi.c_lp)
+            r.fx_plan, r.fy_plan = P(plan["fx8"], abi.c_bp), P(plan["fy8"], abi.c_bp)
+            r.Lx, r.Ly, r.half_skin, r.periodic = prm.Lx, prm.Ly, 0.5 * plan["skin"], int(bool(prm.periodic))
+            r.own_out, r.bad_out = P(plan["own_buf"], abi.c_dp), P(plan["bad_buf"], abi.c_ip)
+            plan["_refresh_desc"], plan["_refresh_keep"], plan["_refresh_key"] = r, keep, key
+        r = plan["_refresh_desc"]
+        if not self._shared_stream:
+            torch.cuda.current_stream().synchronize()
         abi.check(abi.lib().sz_slab_refresh(self.ctx._h, C.byref(r)))
-        if int(comm.all_max(plan["bad_buf"])) != 0:
-            return False
+        bad = comm.all_max(plan["bad_buf"])           # one small all-reduce, left on the stream
         send = plan["own_buf"][plan["sidx"]]
         recv = comm.exchange(send, plan["send_counts"], plan["recv_counts"])
-        torch.cuda.current_stream().synchronize()
+        if not self._shared_stream:
+            torch.cuda.current_stream().synchronize()
         n_own, n_recv = plan["n_own"], int(recv.shape[0])
         abi.check(abi.lib().sz_slab_scatter(self.ctx._h, P(plan["own_buf"], abi.c_dp), n_own, P(recv, abi.c_dp), n_recv, P(plan["order_c"], abi.c_lp), n_own + n_recv))
-        plan["_keep"] = recv          # the scatter kernel reads it asynchronously
-        return True
+        plan["_keep"] = (recv, send)          # the exchange and the scatter kernel read them asynchronously
+        return bad
 
     def invalidate(self):
         """call when floes were created, destroyed or reshaped (the outlines and the alive flags are part of the plan)"""
@@ -405,7 +421,13 @@ class SlabStep:
         P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
         if self.local is not None and self.skin > 0:
             if st.x.is_cuda:
-                ok = self._refresh_on_device()          # two library kernels + one gather around the exchange
+                bad = self._refresh_on_device()         # two library kernels + one gather around the exchange
+                summary = self.ctx.step_resident()
+                if int(bad) == 0:                       # read after the step (its counter read-backs synchronised already)
+                    self.fast_steps += 1
+                    self.summary = summary
+                    return summary
+                ok = False                              # some rank's plan went stale: this step is repeated with a new plan
             else:
                 ok, dyn = refresh_local_state(st, prm.Lx, prm.Ly, bool(prm.periodic), self.local.plan, self.comm)
                 if ok:
