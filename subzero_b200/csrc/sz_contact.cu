@@ -713,8 +713,17 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
             const double k = 1 / (2 * a.area[m] * a.h[m]);
             S[0] = k * (s11 + t11); S[1] = k * (s12 + t12); S[2] = k * (s21 + t21); S[3] = k * (s22 + t22);
         } else { S[0] = S[1] = S[2] = S[3] = 0; }
-        if (orig && nfin) atomicAdd(&a.cnt->n_fin_rows, (u64)nfin);      // calc_collisionNum runs over the original floes
-        if (orig && ninf) atomicAdd(&a.cnt->n_inf_rows, (u64)ninf);
+    }
+    // calc_collisionNum runs over the original floes.  One atomic per group of lanes that arrive here together instead of
+    // one per floe (a million atomics on one address otherwise).
+    {
+        const int fin = (m < a.nout && orig) ? nfin : 0, inf = (m < a.nout && orig) ? ninf : 0;
+        const unsigned mk = __activemask();
+        const int sf = __reduce_add_sync(mk, fin), si = __reduce_add_sync(mk, inf);
+        if ((int)(threadIdx.x & 31) == __ffs(mk) - 1) {
+            if (sf) atomicAdd(&a.cnt->n_fin_rows, (u64)sf);
+            if (si) atomicAdd(&a.cnt->n_inf_rows, (u64)si);
+        }
     }
 }
 // ghost sums folded into their parents in creation order (:242-245), then the floe's own column sums (:262-263)

@@ -55,7 +55,7 @@ struct PairResult {
 };
 
 // polyclip.m:66  int64(x*scale): round half away from zero, saturating, NaN -> 0
-SZ_HD i64 matlab_int64(double v)
+SZ_HD i64 matlab_int64_general(double v)
 {
     if (v != v) return 0;
     if (v >= 9223372036854775807.0) return 0x7FFFFFFFFFFFFFFFLL;
@@ -63,6 +63,20 @@ SZ_HD i64 matlab_int64(double v)
     double t = trunc(v), f = v - t;
     i64 r = (i64)t;
     if (f >= 0.5) r += 1; else if (f <= -0.5) r -= 1;
+    return r;
+}
+// The same value for |v| < 2^51 (every coordinate of a real field: 2^51 units are 5e5 km) from one round-to-nearest-even
+// conversion: only an exact tie can differ from "half away from zero", and there v - r is exactly +-0.5.
+SZ_HD i64 matlab_int64(double v)
+{
+    if (!(fabs(v) < 2251799813685248.0)) return matlab_int64_general(v);
+#if defined(__CUDA_ARCH__)
+    i64 r = __double2ll_rn(v);
+#else
+    i64 r = (i64)nearbyint(v);          // default rounding mode: to nearest even
+#endif
+    const double d = v - (double)r;
+    if (d == 0.5 && v > 0) r += 1; else if (d == -0.5 && v < 0) r -= 1;
     return r;
 }
 

@@ -130,6 +130,24 @@ int main(int argc, char** argv)
     unsigned long long seed = argc > 2 ? strtoull(argv[2], 0, 10) : 1;
     rng.seed(seed);
     const double S = 4294967296.0;
+    {   // polyclip.m:66 int64(): the one-conversion form against the general one, ties and range ends included
+        long bad = 0;
+        for (long k = 0; k < 4000000 && bad < 5; ++k) {
+            double v;
+            switch (k % 6) {
+                case 0: v = (urand() - 0.5) * 9.1e15; break;
+                case 1: v = (double)irand(-2000000, 2000000) + 0.5; break;
+                case 2: v = std::ldexp((double)irand(-(1 << 30), 1 << 30), irand(-40, 22)); break;
+                case 3: v = std::nextafter((double)irand(-1000, 1000) + 0.5, (k & 8) ? 1e300 : -1e300); break;
+                case 4: v = (urand() - 0.5) * 2.0; break;
+                default: v = (k & 16) ? 2251799813685248.0 - (double)irand(0, 4) * 0.5 : -2251799813685248.0 + (double)irand(0, 4) * 0.5; break;
+            }
+            if (szpf::matlab_int64(v) != szpf::matlab_int64_general(v)) { fprintf(stderr, "matlab_int64 mismatch at %.17g\n", v); ++bad; }
+        }
+        const double specials[] = {0.0, -0.0, 0.5, -0.5, 1.5, -1.5, 2.5, -2.5, 0.49999999999999994, -0.49999999999999994, 1e300, -1e300, 9.3e18, -9.3e18, std::nan("")};
+        for (double v : specials) if (szpf::matlab_int64(v) != szpf::matlab_int64_general(v)) { fprintf(stderr, "matlab_int64 mismatch at %.17g\n", v); ++bad; }
+        if (bad) return 3;
+    }
     long t = 0, round = 0;
     while (t < cases && g_bad < 5) {
         const int fam = (int)(round++ % 8);
