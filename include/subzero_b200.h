@@ -192,9 +192,9 @@ int sz_get_rows(SzContext* ctx, int64_t* row_off, double* rows);
 int sz_get_clip_polys(SzContext* ctx, int64_t* pair_path_off, int64_t* path_vert_off, int64_t* x, int64_t* y);
 
 /* ---- the integrator half of the timestep, calc_trajectory.m, for the branch the contact-loop
- * benchmark exercises: doInt.flag = false with the ocean/atmosphere tendencies FxOA, FyOA, torqueOA carried over (no
- * ocean or wind evaluation; a floe thinner than 0.1 m, which the reference re-forces every step (:94), is reported and
- * the call fails).  The state stays on the device: contact step -> trajectory step -> contact step ... with no host
+ * benchmark exercises: doInt.flag = false with the ocean/atmosphere tendencies FxOA, FyOA, torqueOA carried over (a floe
+ * thinner than 0.1 m, which the reference re-forces every step (:94), is reported and the call fails unless
+ * sz_trajectory_ocean_forcing evaluated it first, see below).  The state stays on the device: contact step -> trajectory step -> contact step ... with no host
  * round trip.  Single-GPU lists only.
  *   sz_trajectory_init  after sz_upload: the Floe fields the integrator owns (initialize_floe_values.m:16-24,40-47);
  *                       NULL = zeros; c0 NULL = the uploaded c_alpha (alpha_i = 0); StressH = zeros(2,2,nz), StressCount = 1
@@ -213,6 +213,33 @@ int sz_trajectory_init(SzContext* ctx, const SzTrajectoryInit* init);
 int sz_trajectory_step(SzContext* ctx, const SzTrajectoryParams* prm, int32_t* n_sacked, int32_t* n_needs_ocean);
 int sz_get_trajectory(SzContext* ctx, double* x, double* y, double* u, double* v, double* ksi, double* h, uint8_t* alive, double* mass, double* inertia, double* alpha,
                       double* dXi_p, double* dYi_p, double* dUi_p, double* dVi_p, double* dalpha_p, double* dksi_p, double* stress, int32_t* flags, double* cax, double* cay);
+
+/* ---- row f1, second half: the ocean / atmosphere forcing of calc_trajectory.m:94-166 (Monte-Carlo points of the floe,
+ * interp2 of the ocean currents and winds, quadratic drag with turning angle, SSH-tilt and Coriolis terms, averaged
+ * over the points inside the floe) and the strain rate of :224-234.
+ *   sz_trajectory_set_ocean    ocean.Xo [nx], ocean.Yo [ny] (ascending), ocean.Uocn/.Vocn and winds.u/.v as MATLAB stores
+ *                              them (ny x nx, column-major: element (iy, ix) at iy + ix*ny), ocean.fCoriolis,
+ *                              ocean.turn_angle and the constants of calc_trajectory.m:57-64 (0 = the reference's values)
+ *   sz_trajectory_set_points   Floe.X, Floe.Y, Floe.A (initialize_floe_values.m:31-33): npts points per floe, floe-major
+ *   sz_trajectory_ocean_forcing  call it between the contact step and sz_trajectory_step, with the same parameters:
+ *                              evaluates FxOA, FyOA, torqueOA exactly for the floes the reference would -- all live floes when
+ *                              do_int != 0 (doInt.flag), else only those thinner than 0.1 m after this step's thinning (:94)
+ *                              -- and makes the next sz_trajectory_step compute floe.strain when do_int != 0.  A floe
+ *                              with no point inside its outline would get new random points in the reference (:100-111):
+ *                              it is counted in n_no_points, flagged (bit 2) and keeps its forcing; the call then
+ *                              returns SZ_ERR_STATE after finishing the others.
+ *   sz_get_trajectory_forcing  FxOA FyOA torqueOA [n0], strain [n0][2][2] (row-major); any pointer may be NULL */
+typedef struct SzOcean {
+    int32_t nx, ny;
+    const double *Xo, *Yo;
+    const double *Uocn, *Vocn, *Uwinds, *Vwinds;
+    double fCoriolis, turn_angle;
+    double rho0, Cd, rho_air, Cd_atm;          /* 1027, 3e-3, 1.2, 1e-3 when 0 */
+} SzOcean;
+int sz_trajectory_set_ocean(SzContext* ctx, const SzOcean* ocean);
+int sz_trajectory_set_points(SzContext* ctx, int32_t npts, const double* X, const double* Y, const uint8_t* A);
+int sz_trajectory_ocean_forcing(SzContext* ctx, const SzTrajectoryParams* prm, int32_t do_int, int32_t* n_evaluated, int32_t* n_no_points);
+int sz_get_trajectory_forcing(SzContext* ctx, double* FxOA, double* FyOA, double* torqueOA, double* strain);
 
 /* diagnostic: device time (CUDA events, ms) of the last step by phase:
  * [0] ghost floes (floe_interactions_all.m:16-66)   [1] broad phase (:68-120)

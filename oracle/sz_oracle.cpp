@@ -896,4 +896,108 @@ void szo_calc_trajectory(int n, double dt, double HFo, double xo_min, double xo_
     }
 }
 
+// interp2(X, Y, V, xq, yq) of MATLAB, 'linear' (calc_trajectory.m:135-138): X [nx], Y [ny] ascending grid vectors,
+// V(iy, ix) stored column-major like MATLAB (iy + ix*ny); NaN outside the grid.  MATLAB's own kernel is not in the
+// reference; this is the textbook bilinear form (parity with MATLAB's rounding unpinned, well inside 1e-9).
+static double interp2_linear(const double* X, int nx, const double* Y, int ny, const double* V, double xq, double yq)
+{
+    if (!(xq >= X[0] && xq <= X[nx - 1] && yq >= Y[0] && yq <= Y[ny - 1])) return INF - INF;
+    int ix = (int)(std::upper_bound(X, X + nx, xq) - X) - 1; if (ix > nx - 2) ix = nx - 2; if (ix < 0) ix = 0;
+    int iy = (int)(std::upper_bound(Y, Y + ny, yq) - Y) - 1; if (iy > ny - 2) iy = ny - 2; if (iy < 0) iy = 0;
+    const double t = (xq - X[ix]) / (X[ix + 1] - X[ix]), sy = (yq - Y[iy]) / (Y[iy + 1] - Y[iy]);
+    const double v00 = V[iy + (size_t)ix * ny], v10 = V[iy + (size_t)(ix + 1) * ny], v01 = V[iy + 1 + (size_t)ix * ny], v11 = V[iy + 1 + (size_t)(ix + 1) * ny];
+    return (v00 * (1 - t) + v10 * t) * (1 - sy) + (v01 * (1 - t) + v11 * t) * sy;
+}
+
+// calc_trajectory.m:94-166: the ocean / atmosphere forcing of every floe the reference would evaluate it for in this
+// call -- doInt.flag (do_int), or floe.h < 0.1 after the thermodynamic thinning -- from the state BEFORE the
+// Adams-Bashforth update.  It repeats the bounds and thinning of :36-41,67-80 to obtain floe_mass and the sacking tests
+// of :89,116-117 (a sacked floe keeps its old FxOA).  x, y, alive are the contact step's per-floe outputs (wrapped
+// centroid, alive after the wall test), like in szo_calc_trajectory.  PX, PY, PA [n * npts]: Floe.X, Floe.Y, Floe.A
+// (Monte-Carlo points of initialize_floe_values.m:31-33, body frame).  no_points[i] = 1 when sum(A) == 0: the reference
+// would draw new random points (:100-111), which cannot be reproduced; FxOA is left untouched for that floe.
+void szo_ocean_forcing(int n, double dt, double HFo, double xo_min, double xo_max, double yo_min, double yo_max, int do_int,
+                       const uint8_t* alive, const double* x, const double* y, const double* u, const double* v, const double* ksi,
+                       const double* h, const double* mass, const double* area, const double* alpha,
+                       const int32_t* voff, const double* cax, const double* cay,
+                       int npts, const double* PX, const double* PY, const uint8_t* PA,
+                       int nx, int ny, const double* Xo, const double* Yo, const double* Uocn, const double* Vocn, const double* Uwinds, const double* Vwinds,
+                       double fc, double turn_angle, double rho0, double Cd, double rho_air, double Cd_atm,
+                       double* FxOA, double* FyOA, double* torqueOA, uint8_t* evaluated, uint8_t* no_points)
+{
+    for (int i = 0; i < n; ++i) {
+        evaluated[i] = 0; no_points[i] = 0;
+        if (!alive[i]) continue;                                                   // floe_interactions_all.m:280
+        double hh = h[i], m = mass[i]; uint8_t al = alive[i];
+        if (hh > 10) hh = 10; else if (m < 100) { m = 1e3; al = 0; }               // :36-41
+        const double dh = HFo * dt / hh;                                           // :75-79
+        const double floe_mass = (hh - dh) / hh * m, h_new = hh - dh, floe_area = area[i];
+        if (std::isnan(x[i])) continue;                                            // :89
+        if (!(do_int || h_new < 0.1)) continue;                                    // :94
+        double cmaxx = -INF, cminx = INF, cmaxy = -INF, cminy = INF;
+        for (int t = voff[i]; t < voff[i + 1]; ++t) { cmaxx = std::max(cmaxx, cax[t]); cminx = std::min(cminx, cax[t]); cmaxy = std::max(cmaxy, cay[t]); cminy = std::min(cminy, cay[t]); }
+        if (cmaxx + x[i] > xo_max || cminx + x[i] < xo_min || cmaxy + y[i] > yo_max || cminy + y[i] < yo_min) continue;   // :116-117
+        if (al != 1) continue;                                                     // :118
+        const double* px = PX + (size_t)i * npts; const double* py = PY + (size_t)i * npts; const uint8_t* pa = PA + (size_t)i * npts;
+        int cnt = 0; for (int k = 0; k < npts; ++k) cnt += pa[k] != 0;
+        if (cnt == 0) { no_points[i] = 1; continue; }                              // :100-111 draws new random points
+        const double ca = std::cos(alpha[i]), sa = std::sin(alpha[i]);
+        const double Xi = x[i], Yi = y[i], Ui = u[i], Vi = v[i], K = ksi[i];
+        // winds averaged over the floe (:140)
+        double su = 0, sv = 0;
+        for (int k = 0; k < npts; ++k) if (pa[k]) {
+            const double xr = ca * px[k] + (-sa) * py[k], yr = sa * px[k] + ca * py[k];                                  // :97
+            su += interp2_linear(Xo, nx, Yo, ny, Uwinds, xr + Xi, yr + Yi); sv += interp2_linear(Xo, nx, Yo, ny, Vwinds, xr + Xi, yr + Yi);
+        }
+        const double U10 = su / cnt, V10 = sv / cnt;
+        const double Fx_atm = rho_air * Cd_atm * std::sqrt(U10 * U10 + V10 * V10) * U10, Fy_atm = rho_air * Cd_atm * std::sqrt(U10 * U10 + V10 * V10) * V10;   // :141-142
+        const double mfa = floe_mass / floe_area;
+        double sfx = 0, sfy = 0, stq = 0;
+        for (int k = 0; k < npts; ++k) if (pa[k]) {
+            const double xr = ca * px[k] + (-sa) * py[k], yr = sa * px[k] + ca * py[k];
+            const double theta = std::atan2(yr, xr), rho = std::hypot(xr, yr);                                           // cart2pol :124
+            const double Uice = Ui - rho * K * std::sin(theta), Vice = Vi + rho * K * std::cos(theta);                   // :127-128
+            const double uo = interp2_linear(Xo, nx, Yo, ny, Uocn, xr + Xi, yr + Yi), vo = interp2_linear(Xo, nx, Yo, ny, Vocn, xr + Xi, yr + Yi);
+            const double fxp = -mfa * fc * vo, fyp = +mfa * fc * uo;                                                     // :144-145
+            const double du = uo - Uice, dv = vo - Vice;                                                                 // :147
+            const double sp = std::sqrt(du * du + dv * dv);
+            const double tx = rho0 * Cd * sp * (std::cos(turn_angle) * du - std::sin(turn_angle) * dv);                  // :149-150
+            const double ty = rho0 * Cd * sp * (std::sin(turn_angle) * du + std::cos(turn_angle) * dv);
+            double Fx = tx + Fx_atm + fxp, Fy = ty + Fy_atm + fyp;                                                       // :152-153
+            const double tq = (-Fx * std::sin(theta) + Fy * std::cos(theta)) * rho;                                      // :157
+            Fx = Fx + mfa * fc * Vi; Fy = Fy - mfa * fc * Ui;                                                            // :160-161
+            sfx += Fx; sfy += Fy; stq += tq;
+        }
+        FxOA[i] = sfx / cnt; FyOA[i] = sfy / cnt; torqueOA[i] = stq / cnt;                                               // :164-166
+        evaluated[i] = 1;
+    }
+}
+
+// calc_trajectory.m:224-234 (doInt.flag): strain rate of every floe that went through the update branch (alive == 1, not
+// sacked) from its UPDATED outline and velocities; the others keep their old floe.strain.
+void szo_floe_strain(int n, const uint8_t* alive, const uint8_t* sacked, const double* area, const double* u, const double* v, const double* ksi,
+                     const int32_t* voff, const double* cax, const double* cay, double* strain)
+{
+    for (int i = 0; i < n; ++i) {
+        if (alive[i] != 1 || sacked[i]) continue;
+        const int o = voff[i], m = voff[i + 1] - o;
+        if (m < 1) continue;
+        double sxu = 0, syu = 0, sxv = 0, syv = 0;      // sum(diff([Uice Uice(1)]) .* diff([c_alpha(2,:) c_alpha(2,1)])) ...
+        auto vel = [&](int t, double& U, double& V) {
+            const double theta = std::atan2(cay[o + t], cax[o + t]), rho = std::hypot(cax[o + t], cay[o + t]);
+            U = u[i] - rho * ksi[i] * std::sin(theta); V = v[i] + rho * ksi[i] * std::cos(theta);
+        };
+        for (int t = 0; t < m; ++t) {
+            const int t1 = (t + 1 == m) ? 0 : t + 1;
+            double U0, V0, U1, V1; vel(t, U0, V0); vel(t1, U1, V1);
+            const double dxc = cax[o + t1] - cax[o + t], dyc = cay[o + t1] - cay[o + t];
+            sxu += (U1 - U0) * dyc; syu += (U1 - U0) * dxc; sxv += (V1 - V0) * dyc; syv += (V1 - V0) * dxc;
+        }
+        const double du_dx = 0.5 * sxu / area[i], du_dy = 0.5 * syu / area[i], dv_dx = 0.5 * sxv / area[i], dv_dy = 0.5 * syv / area[i];
+        // 1/2*([du_dx du_dy; dv_dx dv_dy] + [du_dx dv_dx; du_dy dv_dy]), stored row-major like the stress
+        strain[(size_t)i * 4 + 0] = 0.5 * (du_dx + du_dx); strain[(size_t)i * 4 + 1] = 0.5 * (du_dy + dv_dx);
+        strain[(size_t)i * 4 + 2] = 0.5 * (dv_dx + du_dy); strain[(size_t)i * 4 + 3] = 0.5 * (dv_dy + dv_dy);
+    }
+}
+
 }  // extern "C"

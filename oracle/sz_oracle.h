@@ -38,6 +38,16 @@ void szo_calc_trajectory(int n, double dt, double HFo, double xo_min, double xo_
                          double* dalpha_p, double* dksi_p, const double* FxOA, const double* FyOA, const double* torqueOA,
                          const int32_t* voff, const double* c0x, const double* c0y, double* cax, double* cay,
                          double* stress_h, int32_t* stress_count, double* stress_out, uint8_t* sacked, uint8_t* unsupported);
+void szo_ocean_forcing(int n, double dt, double HFo, double xo_min, double xo_max, double yo_min, double yo_max, int do_int,
+                       const uint8_t* alive, const double* x, const double* y, const double* u, const double* v, const double* ksi,
+                       const double* h, const double* mass, const double* area, const double* alpha,
+                       const int32_t* voff, const double* cax, const double* cay,
+                       int npts, const double* PX, const double* PY, const uint8_t* PA,
+                       int nx, int ny, const double* Xo, const double* Yo, const double* Uocn, const double* Vocn, const double* Uwinds, const double* Vwinds,
+                       double fc, double turn_angle, double rho0, double Cd, double rho_air, double Cd_atm,
+                       double* FxOA, double* FyOA, double* torqueOA, uint8_t* evaluated, uint8_t* no_points);
+void szo_floe_strain(int n, const uint8_t* alive, const uint8_t* sacked, const double* area, const double* u, const double* v, const double* ksi,
+                     const int32_t* voff, const double* cax, const double* cay, double* strain);
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,11 @@ class SzTrajectoryParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("dt", "HFo", "xo_min", "xo_max", "yo_min", "yo_max")]
 
 
+class SzOcean(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("Xo", c_dp), ("Yo", c_dp), ("Uocn", c_dp), ("Vocn", c_dp), ("Uwinds", c_dp), ("Vwinds", c_dp),
+                ("fCoriolis", C.c_double), ("turn_angle", C.c_double), ("rho0", C.c_double), ("Cd", C.c_double), ("rho_air", C.c_double), ("Cd_atm", C.c_double)]
+
+
 class SzSlabRefresh(C.Structure):
     _fields_ = [("n_orig", C.c_int32), ("n_xg", C.c_int32), ("n_yg", C.c_int32)] + [(n, c_dp) for n in ("x", "y", "u", "v", "ksi")] + [("alive", c_bp)] + [
         (n, c_dp) for n in ("minvx", "maxvx", "minvy", "maxvy")] + [("xg_par", c_lp), ("yg_par", c_lp), ("fx_plan", c_bp), ("fy_plan", c_bp), ("x0", c_dp), ("y0", c_dp),
@@ -86,6 +91,10 @@ PROTOTYPES = {
     "sz_get_rows": (C.c_int, [C.c_void_p, c_lp, c_dp]),
     "sz_trajectory_init": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryInit)]),
     "sz_trajectory_step": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryParams), c_ip, c_ip]),
+    "sz_trajectory_set_ocean": (C.c_int, [C.c_void_p, C.POINTER(SzOcean)]),
+    "sz_trajectory_set_points": (C.c_int, [C.c_void_p, C.c_int32, c_dp, c_dp, c_bp]),
+    "sz_trajectory_ocean_forcing": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryParams), C.c_int32, c_ip, c_ip]),
+    "sz_get_trajectory_forcing": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp]),
     "sz_get_trajectory": (C.c_int, [C.c_void_p] + [c_dp] * 6 + [c_bp] + [c_dp] * 10 + [c_ip, c_dp, c_dp]),
     "sz_get_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "sz_get_narrow_class_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

@@ -151,6 +151,38 @@ class ContactContext:
         abi.check(abi.lib().sz_trajectory_step(self._h, C.byref(p), C.byref(ns), C.byref(no)))
         return ns.value
 
+    # ---- ocean / atmosphere forcing (calc_trajectory.m:94-166) and strain (:224-234)
+    def trajectory_set_ocean(self, Xo, Yo, Uocn, Vocn, Uwinds, Vwinds, fCoriolis, turn_angle, rho0=0.0, Cd=0.0, rho_air=0.0, Cd_atm=0.0):
+        """Xo [nx], Yo [ny]; the four fields as (ny, nx) arrays like ocean.Uocn / winds.u in MATLAB"""
+        Xo, Yo = abi.f64(Xo), abi.f64(Yo)
+        cm = lambda a: np.ascontiguousarray(np.asarray(a, np.float64).T)          # column-major ny x nx
+        f = [cm(a) for a in (Uocn, Vocn, Uwinds, Vwinds)]
+        for a in f:
+            assert a.shape == (Xo.shape[0], Yo.shape[0]), "ocean fields must be (ny, nx)"
+        o = abi.SzOcean(int(Xo.shape[0]), int(Yo.shape[0]), abi._ptr(Xo, abi.c_dp), abi._ptr(Yo, abi.c_dp), *(abi._ptr(a, abi.c_dp) for a in f),
+                        float(fCoriolis), float(turn_angle), float(rho0), float(Cd), float(rho_air), float(Cd_atm))
+        abi.check(abi.lib().sz_trajectory_set_ocean(self._h, C.byref(o)))
+
+    def trajectory_set_points(self, X, Y, A):
+        """Floe.X, Floe.Y, Floe.A as (n0, npts) arrays"""
+        X, Y = np.ascontiguousarray(X, np.float64), np.ascontiguousarray(Y, np.float64)
+        A = np.ascontiguousarray(A, np.uint8)
+        assert X.shape == Y.shape == A.shape and X.shape[0] == self._n0
+        abi.check(abi.lib().sz_trajectory_set_points(self._h, int(X.shape[1]), abi._ptr(X, abi.c_dp), abi._ptr(Y, abi.c_dp), abi._ptr(A, abi.c_bp)))
+
+    def trajectory_ocean_forcing(self, dt, HFo=0.0, xo_min=-np.inf, xo_max=np.inf, yo_min=-np.inf, yo_max=np.inf, do_int=True):
+        """call between the contact step and trajectory_step (same parameters); returns (floes evaluated, floes without points)"""
+        p = abi.SzTrajectoryParams(float(dt), float(HFo), float(xo_min), float(xo_max), float(yo_min), float(yo_max))
+        ne, nn = C.c_int32(), C.c_int32()
+        abi.check(abi.lib().sz_trajectory_ocean_forcing(self._h, C.byref(p), int(bool(do_int)), C.byref(ne), C.byref(nn)))
+        return ne.value, nn.value
+
+    def trajectory_forcing(self):
+        n = self._n0
+        o = {"FxOA": np.empty(n), "FyOA": np.empty(n), "torqueOA": np.empty(n), "strain": np.empty((n, 2, 2))}
+        abi.check(abi.lib().sz_get_trajectory_forcing(self._h, *(abi._ptr(o[k], abi.c_dp) for k in ("FxOA", "FyOA", "torqueOA", "strain"))))
+        return o
+
     def trajectory_state(self, nverts=0):
         n = self._n0
         o = {k: np.empty(n) for k in ("x", "y", "u", "v", "ksi", "h")}

@@ -83,6 +83,7 @@ struct Counters {
     u64 rmax_bits;
     u64 n_fin_rows, n_inf_rows;
     int clip_listM, clip_listL, clip_path_used, clip_vert_used;
+    int n_forced, n_no_points;     // ocean forcing: floes evaluated / floes without a Monte-Carlo point inside
 };
 
 struct SzContext {
@@ -131,6 +132,10 @@ struct SzContext {
     // integrator state (sz_trajectory_*): calc_trajectory.m fields kept on the device between steps
     bool have_traj = false; int traj_nz = 0;
     DBuf<double> t_mass, t_inertia, t_alpha, t_dXi_p, t_dYi_p, t_dUi_p, t_dVi_p, t_dalpha_p, t_dksi_p, t_FxOA, t_FyOA, t_torqueOA, c0x, c0y, t_stressH, t_stress;
+    // ocean / atmosphere forcing (calc_trajectory.m:94-166)
+    DBuf<double> oc_Xo, oc_Yo, oc_U, oc_V, oc_Wu, oc_Wv, pt_x, pt_y, t_strain; DBuf<uint8_t> pt_a, t_forced;
+    int oc_nx = 0, oc_ny = 0, npts = 0; bool have_ocean = false, have_points = false, traj_do_int = false;
+    double oc_fc = 0, oc_turn = 0, oc_rho0 = 1027, oc_Cd = 3e-3, oc_rho_air = 1.2, oc_Cd_atm = 1e-3;
     DBuf<int> t_scount, t_flags;
     // clip batch
     int clip_count = 0; i64 clip_paths = 0, clip_verts = 0;
@@ -817,7 +822,8 @@ extern "C" void sz_destroy(SzContext* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
-                          &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi};
+                          &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi,
+                          &c->oc_Xo, &c->oc_Yo, &c->oc_U, &c->oc_V, &c->oc_Wu, &c->oc_Wv, &c->pt_x, &c->pt_y, &c->t_strain};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
                        &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->stage, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
@@ -825,7 +831,7 @@ extern "C" void sz_destroy(SzContext* c)
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
                        &c->c_path_len, &c->c_listM, &c->c_listL};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL};
+    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced};
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
@@ -1355,6 +1361,7 @@ struct TrajArgs {
     const double* FxOA; const double* FyOA; const double* torqueOA;
     const int* voff; const double* c0x; const double* c0y; double* cax; double* cay;
     double* stress_h; int* scount; int* flags; Counters* cnt;
+    const uint8_t* forced; int do_int; double* strain;     // forcing evaluated this step (h < 0.1 is then fine); doInt.flag: floe.strain (:224-234)
 };
 // calc_trajectory.m for one floe per thread: the branch with doInt.flag = false and the ocean/atmosphere tendencies
 // FxOA, FyOA, torqueOA carried over (:3-46 stress history slot + force clamp, :67-80 thermodynamic thinning, :89,116-117
@@ -1381,7 +1388,7 @@ __global__ void trajectory_kernel(const TrajArgs a)
     const double floe_mass = (h - dh) / h * mass, floe_inertia = (h - dh) / h * inertia;
     const double h_new = h - dh;
     bool sack = (X != X);                                                         // :89
-    if (!sack && h_new < 0.1) { a.flags[i] = 2; atomicAdd(&a.cnt->n_fail, 1); return; }
+    if (!sack && h_new < 0.1 && !(a.forced && a.forced[i])) { a.flags[i] = 2; atomicAdd(&a.cnt->n_fail, 1); return; }
     if (!sack) {
         double cmaxx = -SZ_INF, cminx = SZ_INF, cmaxy = -SZ_INF, cminy = SZ_INF;
         for (int t = a.voff[i]; t < a.voff[i + 1]; ++t) { cmaxx = fmax(cmaxx, a.cax[t]); cminx = fmin(cminx, a.cax[t]); cmaxy = fmax(cmaxy, a.cay[t]); cminy = fmin(cminy, a.cay[t]); }
@@ -1427,6 +1434,119 @@ __global__ void trajectory_kernel(const TrajArgs a)
     a.ksi[i] = k2; a.dksi_p[i] = dksi;
     const double ca = cos(alpha), sa = sin(alpha);                                // :221-222
     for (int t = a.voff[i]; t < a.voff[i + 1]; ++t) { const double px = a.c0x[t], py = a.c0y[t]; a.cax[t] = ca * px + (-sa) * py; a.cay[t] = sa * px + ca * py; }
+    if (a.do_int && a.strain) {                                                   // :224-234
+        const int o = a.voff[i], m = a.voff[i + 1] - o;
+        const double Un = a.u[i], Vn = a.v[i];
+        double sxu = 0, syu = 0, sxv = 0, syv = 0, U0 = 0, V0 = 0, Uf = 0, Vf = 0;
+        for (int t = 0; t <= m && m > 0; ++t) {
+            const int tt = (t == m) ? 0 : t;
+            double U1, V1;
+            if (t == m) { U1 = Uf; V1 = Vf; }
+            else {
+                const double theta = atan2(a.cay[o + tt], a.cax[o + tt]), rho = hypot(a.cax[o + tt], a.cay[o + tt]);
+                U1 = Un - rho * k2 * sin(theta); V1 = Vn + rho * k2 * cos(theta);
+                if (t == 0) { Uf = U1; Vf = V1; }
+            }
+            if (t > 0) {
+                const int tp = t - 1;
+                const double dxc = a.cax[o + tt] - a.cax[o + tp], dyc = a.cay[o + tt] - a.cay[o + tp];
+                sxu += (U1 - U0) * dyc; syu += (U1 - U0) * dxc; sxv += (V1 - V0) * dyc; syv += (V1 - V0) * dxc;
+            }
+            U0 = U1; V0 = V1;
+        }
+        const double du_dx = 0.5 * sxu / floe_area, du_dy = 0.5 * syu / floe_area, dv_dx = 0.5 * sxv / floe_area, dv_dy = 0.5 * syv / floe_area;
+        double* E = a.strain + (size_t)i * 4;
+        E[0] = 0.5 * (du_dx + du_dx); E[1] = 0.5 * (du_dy + dv_dx); E[2] = 0.5 * (dv_dx + du_dy); E[3] = 0.5 * (dv_dy + dv_dy);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ ocean / atmosphere forcing
+struct OceanArgs {
+    int n0, npts, nx, ny, do_int; double dt, HFo, xo_min, xo_max, yo_min, yo_max, fc, turn, rho0, Cd, rho_air, Cd_atm;
+    const uint8_t* alive_step; const double* xw; const double* yw; const double* u; const double* v; const double* ksi; const double* h;
+    const double* mass; const double* area; const double* alpha; const int* voff; const double* cax; const double* cay;
+    const double* PX; const double* PY; const uint8_t* PA;
+    const double* Xo; const double* Yo; const double* U; const double* V; const double* Wu; const double* Wv;
+    double* FxOA; double* FyOA; double* torqueOA; uint8_t* forced; int* flags; Counters* cnt;
+};
+// interp2(X, Y, V, xq, yq), 'linear', NaN outside the grid; V column-major (iy + ix*ny) like MATLAB (calc_trajectory.m:135-138)
+__device__ __forceinline__ void interp_cell(const double* __restrict__ X, int nx, double xq, int& ix, double& t)
+{
+    int lo = 0, hi = nx - 1;                       // largest ix with X[ix] <= xq, at most nx - 2
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (X[mid] <= xq) lo = mid; else hi = mid; }
+    ix = lo; t = (xq - X[lo]) / (X[lo + 1] - X[lo]);
+}
+__device__ __forceinline__ double interp_val(const double* __restrict__ V, int ny, int ix, int iy, double t, double s)
+{
+    const double v00 = V[iy + (size_t)ix * ny], v10 = V[iy + (size_t)(ix + 1) * ny], v01 = V[iy + 1 + (size_t)ix * ny], v11 = V[iy + 1 + (size_t)(ix + 1) * ny];
+    return (v00 * (1 - t) + v10 * t) * (1 - s) + (v01 * (1 - t) + v11 * t) * s;
+}
+__device__ __forceinline__ double warp_sum(double v) { for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d); return v; }
+// calc_trajectory.m:94-166, one warp per floe: lanes stride over the floe's Monte-Carlo points, butterfly sums.
+// The bounds / thinning of :36-41,67-80 and the sacking tests of :89,116-117 are repeated to select the floes and to get
+// floe_mass exactly as the integrator will (trajectory_kernel runs after this kernel on the same state).
+__global__ void __launch_bounds__(256) ocean_forcing_kernel(const OceanArgs a)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= a.n0) return;
+    if (!a.alive_step[i]) return;                                                  // floe_interactions_all.m:280
+    double hh = a.h[i], m = a.mass[i]; int alive = a.alive_step[i];
+    if (hh > 10) hh = 10; else if (m < 100) { m = 1e3; alive = 0; }                // :36-41
+    const double dh = a.HFo * a.dt / hh;
+    const double floe_mass = (hh - dh) / hh * m, h_new = hh - dh, floe_area = a.area[i];
+    const double Xi = a.xw[i], Yi = a.yw[i];
+    if (Xi != Xi) return;                                                          // :89
+    if (!(a.do_int || h_new < 0.1)) return;                                        // :94
+    double cmaxx = -SZ_INF, cminx = SZ_INF, cmaxy = -SZ_INF, cminy = SZ_INF;
+    for (int t = a.voff[i] + lane; t < a.voff[i + 1]; t += 32) { cmaxx = fmax(cmaxx, a.cax[t]); cminx = fmin(cminx, a.cax[t]); cmaxy = fmax(cmaxy, a.cay[t]); cminy = fmin(cminy, a.cay[t]); }
+    for (int d = 16; d > 0; d >>= 1) {
+        cmaxx = fmax(cmaxx, __shfl_xor_sync(0xffffffffu, cmaxx, d)); cminx = fmin(cminx, __shfl_xor_sync(0xffffffffu, cminx, d));
+        cmaxy = fmax(cmaxy, __shfl_xor_sync(0xffffffffu, cmaxy, d)); cminy = fmin(cminy, __shfl_xor_sync(0xffffffffu, cminy, d));
+    }
+    if (cmaxx + Xi > a.xo_max || cminx + Xi < a.xo_min || cmaxy + Yi > a.yo_max || cminy + Yi < a.yo_min) return;   // :116-117
+    if (alive != 1) return;                                                        // :118
+    const double* px = a.PX + (size_t)i * a.npts; const double* py = a.PY + (size_t)i * a.npts; const uint8_t* pa = a.PA + (size_t)i * a.npts;
+    double cnt = 0;
+    for (int k = lane; k < a.npts; k += 32) cnt += pa[k] != 0;
+    cnt = warp_sum(cnt);
+    if (cnt == 0) { if (lane == 0) { a.flags[i] |= 4; atomicAdd(&a.cnt->n_no_points, 1); } return; }   // :100-111 draws new random points
+    const double ca = cos(a.alpha[i]), sa = sin(a.alpha[i]);
+    const double Ui = a.u[i], Vi = a.v[i], K = a.ksi[i];
+    double su = 0, sv = 0;                                                         // winds over the floe (:140)
+    for (int k = lane; k < a.npts; k += 32) if (pa[k]) {
+        const double xr = ca * px[k] + (-sa) * py[k], yr = sa * px[k] + ca * py[k];
+        const double xq = xr + Xi, yq = yr + Yi;
+        if (!(xq >= a.Xo[0] && xq <= a.Xo[a.nx - 1] && yq >= a.Yo[0] && yq <= a.Yo[a.ny - 1])) { su = sv = SZ_INF - SZ_INF; continue; }
+        int ix, iy; double t, s; interp_cell(a.Xo, a.nx, xq, ix, t); interp_cell(a.Yo, a.ny, yq, iy, s);
+        su += interp_val(a.Wu, a.ny, ix, iy, t, s); sv += interp_val(a.Wv, a.ny, ix, iy, t, s);
+    }
+    const double U10 = warp_sum(su) / cnt, V10 = warp_sum(sv) / cnt;
+    const double Fx_atm = a.rho_air * a.Cd_atm * sqrt(U10 * U10 + V10 * V10) * U10, Fy_atm = a.rho_air * a.Cd_atm * sqrt(U10 * U10 + V10 * V10) * V10;   // :141-142
+    const double mfa = floe_mass / floe_area, cturn = cos(a.turn), sturn = sin(a.turn);
+    double sfx = 0, sfy = 0, stq = 0;
+    for (int k = lane; k < a.npts; k += 32) if (pa[k]) {
+        const double xr = ca * px[k] + (-sa) * py[k], yr = sa * px[k] + ca * py[k];
+        const double theta = atan2(yr, xr), rho = hypot(xr, yr);                   // cart2pol :124
+        const double sth = sin(theta), cth = cos(theta);
+        const double Uice = Ui - rho * K * sth, Vice = Vi + rho * K * cth;         // :127-128
+        const double xq = xr + Xi, yq = yr + Yi;
+        double uo, vo;
+        if (!(xq >= a.Xo[0] && xq <= a.Xo[a.nx - 1] && yq >= a.Yo[0] && yq <= a.Yo[a.ny - 1])) uo = vo = SZ_INF - SZ_INF;
+        else { int ix, iy; double t, s; interp_cell(a.Xo, a.nx, xq, ix, t); interp_cell(a.Yo, a.ny, yq, iy, s); uo = interp_val(a.U, a.ny, ix, iy, t, s); vo = interp_val(a.V, a.ny, ix, iy, t, s); }
+        const double fxp = -mfa * a.fc * vo, fyp = +mfa * a.fc * uo;               // :144-145
+        const double du = uo - Uice, dv = vo - Vice;                               // :147
+        const double sp = sqrt(du * du + dv * dv);
+        const double tx = a.rho0 * a.Cd * sp * (cturn * du - sturn * dv), ty = a.rho0 * a.Cd * sp * (sturn * du + cturn * dv);   // :149-150
+        double Fx = tx + Fx_atm + fxp, Fy = ty + Fy_atm + fyp;                     // :152-153
+        const double tq = (-Fx * sth + Fy * cth) * rho;                            // :157
+        Fx = Fx + mfa * a.fc * Vi; Fy = Fy - mfa * a.fc * Ui;                      // :160-161
+        sfx += Fx; sfy += Fy; stq += tq;
+    }
+    sfx = warp_sum(sfx); sfy = warp_sum(sfy); stq = warp_sum(stq);
+    if (lane == 0) {
+        a.FxOA[i] = sfx / cnt; a.FyOA[i] = sfy / cnt; a.torqueOA[i] = stq / cnt;   // :164-166
+        a.forced[i] = 1; atomicAdd(&a.cnt->n_forced, 1);
+    }
 }
 // floe.Stress = mean(StressH, 3) (calc_trajectory.m:20,28), evaluated when asked for
 __global__ void stress_mean_kernel(int n0, int nz, const double* __restrict__ stress_h, double* __restrict__ out)
@@ -1459,8 +1579,10 @@ extern "C" int sz_trajectory_init(SzContext* c, const SzTrajectoryInit* in)
     CK(cudaMemsetAsync(c->t_stressH.p, 0, n * (size_t)in->nz * 32, st));            // StressH = zeros(2,2,1000), StressCount = 1 (:24-25)
     { std::vector<int> ones(n, 1); CK(cudaMemcpyAsync(c->t_scount.p, ones.data(), n * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st)); }
     CK(cudaMemsetAsync(c->t_flags.p, 0, n * 4, st));
+    CK(c->t_strain.ensure(n * 4 + 4)); CK(c->t_forced.ensure(n + 1));
+    CK(cudaMemsetAsync(c->t_strain.p, 0, n * 32, st)); CK(cudaMemsetAsync(c->t_forced.p, 0, n, st));      // floe.strain starts at zero
     CK(cudaStreamSynchronize(st));
-    c->traj_nz = in->nz; c->have_traj = true;
+    c->traj_nz = in->nz; c->have_traj = true; c->traj_do_int = false;
     return SZ_OK;
 }
 extern "C" int sz_trajectory_step(SzContext* c, const SzTrajectoryParams* p, int32_t* n_sacked, int32_t* n_needs_ocean)
@@ -1478,13 +1600,82 @@ extern "C" int sz_trajectory_step(SzContext* c, const SzTrajectoryParams* p, int
     a.dalpha_p = c->t_dalpha_p.p; a.dksi_p = c->t_dksi_p.p; a.FxOA = c->t_FxOA.p; a.FyOA = c->t_FyOA.p; a.torqueOA = c->t_torqueOA.p;
     a.voff = c->voff.p; a.c0x = c->c0x.p; a.c0y = c->c0y.p; a.cax = c->vx.p; a.cay = c->vy.p;
     a.stress_h = c->t_stressH.p; a.scount = c->t_scount.p; a.flags = c->t_flags.p; a.cnt = c->d_cnt;
+    a.forced = c->t_forced.p; a.do_int = c->traj_do_int ? 1 : 0; a.strain = c->t_strain.p;
     if (n0 > 0) { ++g_launches; trajectory_kernel<<<nblk(n0, 128), 128, 0, st>>>(a); }
+    CK(cudaMemsetAsync(c->t_forced.p, 0, (size_t)n0, st)); c->traj_do_int = false;
     CK(cudaGetLastError());
     CKS(read_counters(c));
     c->have_step = false;            // the contact results belong to the previous positions now
     if (n_sacked) *n_sacked = c->h_cnt->n_cap_fail;
     if (n_needs_ocean) *n_needs_ocean = c->h_cnt->n_fail;
     if (c->h_cnt->n_fail > 0) { sz_set_error("%d floe(s) thinner than 0.1 m need the ocean forcing re-evaluated (calc_trajectory.m:94): not part of this path", c->h_cnt->n_fail); return SZ_ERR_STATE; }
+    return SZ_OK;
+}
+extern "C" int sz_trajectory_set_ocean(SzContext* c, const SzOcean* o)
+{
+    if (!c) { sz_set_error("sz_trajectory_set_ocean: NULL context"); return SZ_ERR_ARG; }
+    if (!o) { c->have_ocean = false; return SZ_OK; }
+    if (o->nx < 2 || o->ny < 2 || !o->Xo || !o->Yo || !o->Uocn || !o->Vocn || !o->Uwinds || !o->Vwinds) { sz_set_error("sz_trajectory_set_ocean: grid vectors (>= 2 points each) and the four fields are required"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const size_t nx = o->nx, ny = o->ny;
+    CK(c->oc_Xo.ensure(nx)); CK(c->oc_Yo.ensure(ny)); CK(c->oc_U.ensure(nx * ny)); CK(c->oc_V.ensure(nx * ny)); CK(c->oc_Wu.ensure(nx * ny)); CK(c->oc_Wv.ensure(nx * ny));
+    CK(cudaMemcpyAsync(c->oc_Xo.p, o->Xo, nx * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->oc_Yo.p, o->Yo, ny * 8, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(c->oc_U.p, o->Uocn, nx * ny * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->oc_V.p, o->Vocn, nx * ny * 8, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(c->oc_Wu.p, o->Uwinds, nx * ny * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->oc_Wv.p, o->Vwinds, nx * ny * 8, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    c->oc_nx = o->nx; c->oc_ny = o->ny; c->oc_fc = o->fCoriolis; c->oc_turn = o->turn_angle;
+    c->oc_rho0 = o->rho0 != 0 ? o->rho0 : 1027.0; c->oc_Cd = o->Cd != 0 ? o->Cd : 3e-3;          // calc_trajectory.m:57-64
+    c->oc_rho_air = o->rho_air != 0 ? o->rho_air : 1.2; c->oc_Cd_atm = o->Cd_atm != 0 ? o->Cd_atm : 1e-3;
+    c->have_ocean = true;
+    return SZ_OK;
+}
+extern "C" int sz_trajectory_set_points(SzContext* c, int32_t npts, const double* X, const double* Y, const uint8_t* A)
+{
+    if (!c || npts < 1 || !X || !Y || !A) { sz_set_error("sz_trajectory_set_points: NULL argument or npts < 1"); return SZ_ERR_ARG; }
+    if (!c->have_input || c->ext_mode) { sz_set_error("sz_trajectory_set_points: upload the floes first (single-GPU list)"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const size_t tot = (size_t)c->n0 * npts;
+    CK(c->pt_x.ensure(tot + 1)); CK(c->pt_y.ensure(tot + 1)); CK(c->pt_a.ensure(tot + 1));
+    CK(cudaMemcpyAsync(c->pt_x.p, X, tot * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->pt_y.p, Y, tot * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->pt_a.p, A, tot, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    c->npts = npts; c->have_points = true;
+    return SZ_OK;
+}
+extern "C" int sz_trajectory_ocean_forcing(SzContext* c, const SzTrajectoryParams* p, int32_t do_int, int32_t* n_evaluated, int32_t* n_no_points)
+{
+    if (!c || !p) { sz_set_error("sz_trajectory_ocean_forcing: NULL argument"); return SZ_ERR_ARG; }
+    if (!c->have_traj || !c->have_step || c->ext_mode) { sz_set_error("sz_trajectory_ocean_forcing: needs sz_trajectory_init and a contact step"); return SZ_ERR_STATE; }
+    if (!c->have_ocean || !c->have_points) { sz_set_error("sz_trajectory_ocean_forcing: needs sz_trajectory_set_ocean and sz_trajectory_set_points"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const int n0 = c->n0;
+    CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
+    CK(cudaMemsetAsync(c->t_forced.p, 0, (size_t)n0, st));
+    OceanArgs a; memset(&a, 0, sizeof(a));
+    a.n0 = n0; a.npts = c->npts; a.nx = c->oc_nx; a.ny = c->oc_ny; a.do_int = do_int != 0;
+    a.dt = p->dt; a.HFo = p->HFo; a.xo_min = p->xo_min; a.xo_max = p->xo_max; a.yo_min = p->yo_min; a.yo_max = p->yo_max;
+    a.fc = c->oc_fc; a.turn = c->oc_turn; a.rho0 = c->oc_rho0; a.Cd = c->oc_Cd; a.rho_air = c->oc_rho_air; a.Cd_atm = c->oc_Cd_atm;
+    a.alive_step = c->o_alive.p; a.xw = c->o_xi.p; a.yw = c->o_yi.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.h = c->h.p;
+    a.mass = c->t_mass.p; a.area = c->area.p; a.alpha = c->t_alpha.p; a.voff = c->voff.p; a.cax = c->vx.p; a.cay = c->vy.p;
+    a.PX = c->pt_x.p; a.PY = c->pt_y.p; a.PA = c->pt_a.p;
+    a.Xo = c->oc_Xo.p; a.Yo = c->oc_Yo.p; a.U = c->oc_U.p; a.V = c->oc_V.p; a.Wu = c->oc_Wu.p; a.Wv = c->oc_Wv.p;
+    a.FxOA = c->t_FxOA.p; a.FyOA = c->t_FyOA.p; a.torqueOA = c->t_torqueOA.p; a.forced = c->t_forced.p; a.flags = c->t_flags.p; a.cnt = c->d_cnt;
+    if (n0 > 0) { ++g_launches; ocean_forcing_kernel<<<nblk(32 * (i64)n0, 256), 256, 0, st>>>(a); }
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    c->traj_do_int = do_int != 0;
+    if (n_evaluated) *n_evaluated = c->h_cnt->n_forced;
+    if (n_no_points) *n_no_points = c->h_cnt->n_no_points;
+    if (c->h_cnt->n_no_points > 0) { sz_set_error("%d floe(s) have no Monte-Carlo point inside their outline: the reference draws new random points (calc_trajectory.m:100-111); supply new points with sz_trajectory_set_points", c->h_cnt->n_no_points); return SZ_ERR_STATE; }
+    return SZ_OK;
+}
+extern "C" int sz_get_trajectory_forcing(SzContext* c, double* FxOA, double* FyOA, double* torqueOA, double* strain)
+{
+    if (!c) { sz_set_error("sz_get_trajectory_forcing: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_traj) { sz_set_error("sz_get_trajectory_forcing: no integrator state"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n0;
+    D2H(FxOA, c->t_FxOA.p, n * 8); D2H(FyOA, c->t_FyOA.p, n * 8); D2H(torqueOA, c->t_torqueOA.p, n * 8); D2H(strain, c->t_strain.p, n * 32);
+    CK(cudaStreamSynchronize(c->stream));
     return SZ_OK;
 }
 extern "C" int sz_get_trajectory(SzContext* c, double* x, double* y, double* u, double* v, double* ksi, double* h, uint8_t* alive, double* mass, double* inertia, double* alpha,

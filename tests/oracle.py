@@ -62,6 +62,11 @@ def lib():
         l.szo_calc_trajectory.restype = None
         l.szo_calc_trajectory.argtypes = [C.c_int] + [C.c_double] * 6 + [C.c_int] + [abi.c_dp] * 4 + [abi.c_bp] + [abi.c_dp] * 7 + [abi.c_bp] + [abi.c_dp] * 12 + [
             abi.c_ip] + [abi.c_dp] * 4 + [abi.c_dp, abi.c_ip, abi.c_dp, abi.c_bp, abi.c_bp]
+        l.szo_ocean_forcing.restype = None
+        l.szo_ocean_forcing.argtypes = [C.c_int] + [C.c_double] * 6 + [C.c_int, abi.c_bp] + [abi.c_dp] * 9 + [abi.c_ip, abi.c_dp, abi.c_dp, C.c_int, abi.c_dp, abi.c_dp, abi.c_bp,
+                                        C.c_int, C.c_int] + [abi.c_dp] * 6 + [C.c_double] * 6 + [abi.c_dp] * 3 + [abi.c_bp, abi.c_bp]
+        l.szo_floe_strain.restype = None
+        l.szo_floe_strain.argtypes = [C.c_int, abi.c_bp, abi.c_bp] + [abi.c_dp] * 4 + [abi.c_ip, abi.c_dp, abi.c_dp, abi.c_dp]
         _lib = l
     return _lib
 
@@ -176,6 +181,36 @@ def calc_trajectory(step, floes, state, dt, HFo=0.0, bounds=(-np.inf, np.inf, -n
                               p(floes.voff, I), p(state["c0x"], D), p(state["c0y"], D), p(floes.vx, D), p(floes.vy, D),
                               p(state["stress_h"], D), p(state["stress_count"], I), p(state["stress"], D), p(sacked, B), p(unsup, B))
     return sacked, unsup
+
+
+def ocean_forcing(step, floes, state, ocean, points, dt, HFo=0.0, bounds=(-np.inf, np.inf, -np.inf, np.inf), do_int=True):
+    """the oracle's restatement of calc_trajectory.m:94-166 on the state BEFORE calc_trajectory() advances it: call it
+    right before calc_trajectory() of the same step.  ocean: dict Xo Yo Uocn Vocn Uwinds Vwinds [(ny, nx)] fCoriolis
+    turn_angle (+ optional rho0 Cd rho_air Cd_atm); points: (X, Y, A) each (n, npts).  Updates state FxOA/FyOA/torqueOA in
+    place; returns (evaluated, no_points)."""
+    o = step.floe_outputs()
+    n = floes.n
+    x, y, alive = np.ascontiguousarray(o["xi"]), np.ascontiguousarray(o["yi"]), np.ascontiguousarray(o["alive"])
+    X, Y, A = (np.ascontiguousarray(points[0], np.float64), np.ascontiguousarray(points[1], np.float64), np.ascontiguousarray(points[2], np.uint8))
+    Xo, Yo = abi.f64(ocean["Xo"]), abi.f64(ocean["Yo"])
+    cm = lambda a: np.ascontiguousarray(np.asarray(a, np.float64).T)
+    U, V, Wu, Wv = (cm(ocean[k]) for k in ("Uocn", "Vocn", "Uwinds", "Vwinds"))
+    ev, nop = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    p, D, B, I = abi._ptr, abi.c_dp, abi.c_bp, abi.c_ip
+    lib().szo_ocean_forcing(n, float(dt), float(HFo), *(float(b) for b in bounds), int(bool(do_int)), p(alive, B), p(x, D), p(y, D), p(floes.u, D), p(floes.v, D), p(floes.ksi, D),
+                            p(floes.h, D), p(state["mass"], D), p(floes.area, D), p(state["alpha"], D), p(floes.voff, I), p(floes.vx, D), p(floes.vy, D),
+                            int(X.shape[1]), p(X, D), p(Y, D), p(A, B), int(Xo.shape[0]), int(Yo.shape[0]), p(Xo, D), p(Yo, D), p(U, D), p(V, D), p(Wu, D), p(Wv, D),
+                            float(ocean["fCoriolis"]), float(ocean["turn_angle"]), float(ocean.get("rho0", 1027.0)), float(ocean.get("Cd", 3e-3)),
+                            float(ocean.get("rho_air", 1.2)), float(ocean.get("Cd_atm", 1e-3)),
+                            p(state["FxOA"], D), p(state["FyOA"], D), p(state["torqueOA"], D), p(ev, B), p(nop, B))
+    return ev, nop
+
+
+def floe_strain(floes, sacked, strain):
+    """calc_trajectory.m:224-234 on the UPDATED state (after calc_trajectory()); strain (n, 2, 2) updated in place"""
+    p, D, B, I = abi._ptr, abi.c_dp, abi.c_bp, abi.c_ip
+    lib().szo_floe_strain(floes.n, p(floes.alive, B), p(np.ascontiguousarray(sacked, np.uint8), B), p(floes.area, D), p(floes.u, D), p(floes.v, D), p(floes.ksi, D),
+                          p(floes.voff, I), p(floes.vx, D), p(floes.vy, D), p(strain, D))
 
 
 def _rel_err(a, b):

@@ -121,3 +121,166 @@ def test_device_trajectory_matches_oracle_over_coupled_steps(n, nz, hfo):
             np.testing.assert_allclose(got["cax"], ref_soa.vx, rtol=0, atol=1e-9 * np.abs(ref_soa.vx).max())
             assert (got["flags"] & 1).sum() == sacked.sum()
     assert np.abs(st["alpha"]).max() > 0 and np.abs(st["dUi_p"]).max() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ocean / atmosphere forcing (calc_trajectory.m:94-166) and strain (:224-234)
+def uniform_ocean(L, n=9, U=0.0, V=0.0, Wu=0.0, Wv=0.0, fc=0.0, turn=0.0, **kw):
+    Xo = np.linspace(-L, L, n)
+    Yo = np.linspace(-L, L, n + 2)
+    full = lambda v: np.full((Yo.shape[0], Xo.shape[0]), float(v))
+    o = {"Xo": Xo, "Yo": Yo, "Uocn": full(U), "Vocn": full(V), "Uwinds": full(Wu), "Vwinds": full(Wv), "fCoriolis": fc, "turn_angle": turn}
+    o.update(kw)
+    return o
+
+
+def one_floe(u=0.0, v=0.0, ksi=0.0):
+    prm, soa = sz.voronoi_field(16, seed=0)
+    one = sz.FloesSoA(soa.x[:1].copy(), soa.y[:1].copy(), soa.rmax[:1], soa.h[:1].copy(), soa.area[:1], np.array([u]), np.array([v]), np.array([ksi]), soa.alive[:1].copy(),
+                      soa.voff[:2], soa.vx[:soa.voff[1]].copy(), soa.vy[:soa.voff[1]].copy())
+    prm.collision = 0
+    return prm, one
+
+
+def test_oracle_ocean_forcing_known_answers():
+    """hand-derived values of the forcing: quadratic ocean drag, wind drag from the floe-averaged wind, turning angle, the
+    torque as the mean of (-Fx sin(theta) + Fy cos(theta)) rho over the points inside the floe, the SSH-tilt and Coriolis
+    terms on a linear current field (which bilinear interpolation reproduces), the rotation of the points by alpha_i, and
+    the selection rules (doInt.flag / h < 0.1 / no point inside)"""
+    rho0, Cd, rho_air, Cd_atm = 1027.0, 3e-3, 1.2, 1e-3
+    prm, one = one_floe()
+    st = make_state(one, 3)
+    a = 100.0
+    X = np.array([[a, a, -a, 5e5]]); Y = np.array([[a, -a, a, 5e5]]); A = np.array([[1, 1, 1, 0]], np.uint8)       # the 4th point is outside the floe
+    step = oracle.OracleStep(prm, one)
+    # 1. uniform current U0 past a floe at rest
+    U0 = 0.3
+    ev, nop = oracle.ocean_forcing(step, one, st, uniform_ocean(2e5, U=U0), (X, Y, A), dt=10.0)
+    assert ev[0] and not nop[0]
+    Fx = rho0 * Cd * abs(U0) * U0
+    assert st["FxOA"][0] == pytest.approx(Fx, rel=1e-14) and st["FyOA"][0] == 0
+    assert st["torqueOA"][0] == pytest.approx(-Fx * (a - a + a) / 3, rel=1e-12)          # mean(-Fx * yr)
+    # 2. wind + moving floe + turning angle, ocean at rest
+    prm, one = one_floe(u=0.1)
+    turn = 15 * np.pi / 180
+    oracle.ocean_forcing(oracle.OracleStep(prm, one), one, st, uniform_ocean(2e5, Wu=10.0, turn=turn), (X, Y, A), dt=10.0)
+    sp = 0.1
+    assert st["FxOA"][0] == pytest.approx(rho0 * Cd * sp * np.cos(turn) * -0.1 + rho_air * Cd_atm * 10.0 * 10.0, rel=1e-13)
+    assert st["FyOA"][0] == pytest.approx(rho0 * Cd * sp * np.sin(turn) * -0.1, rel=1e-13)
+    # 3. SSH tilt + Coriolis on a linear current field, no drag, points rotated by alpha = 90 degrees
+    prm, one = one_floe(u=0.05, v=-0.02)
+    st = make_state(one, 3)
+    st["alpha"][:] = np.pi / 2
+    oc = uniform_ocean(2e5, fc=1.4e-4, Cd=0.0, Cd_atm=0.0)
+    gx, gy = np.meshgrid(oc["Xo"], oc["Yo"])
+    oc["Uocn"] = 0.1 + 2e-7 * gx - 1e-7 * gy
+    oc["Vocn"] = -0.2 + 3e-7 * gy
+    oracle.ocean_forcing(oracle.OracleStep(prm, one), one, st, oc, (X, Y, A), dt=10.0)
+    xr, yr = -Y[0, :3], X[0, :3]                                                         # A_rot * [x; y] with alpha = pi/2
+    mfa = st["mass"][0] / one.area[0]
+    Uo = 0.1 + 2e-7 * (xr + one.x[0]) - 1e-7 * (yr + one.y[0])
+    Vo = -0.2 + 3e-7 * (yr + one.y[0])
+    assert st["FxOA"][0] == pytest.approx(np.mean(-mfa * 1.4e-4 * Vo) + mfa * 1.4e-4 * -0.02, rel=1e-9)
+    assert st["FyOA"][0] == pytest.approx(np.mean(mfa * 1.4e-4 * Uo) - mfa * 1.4e-4 * 0.05, rel=1e-9)
+    # 4. selection: without doInt.flag only a floe thinner than 0.1 m after this step's thinning is evaluated
+    st["FxOA"][:] = 7.0
+    ev, _ = oracle.ocean_forcing(oracle.OracleStep(prm, one), one, st, oc, (X, Y, A), dt=10.0, do_int=False)
+    assert not ev[0] and st["FxOA"][0] == 7.0
+    hfo = (one.h[0] - 0.05) * one.h[0] / 10.0                                            # h - HFo*dt/h = 0.05
+    ev, _ = oracle.ocean_forcing(oracle.OracleStep(prm, one), one, st, oc, (X, Y, A), dt=10.0, HFo=hfo, do_int=False)
+    assert ev[0] and st["FxOA"][0] != 7.0
+    # 5. no point inside the outline: the reference would draw random points; reported, forcing untouched
+    st["FxOA"][:] = 7.0
+    ev, nop = oracle.ocean_forcing(oracle.OracleStep(prm, one), one, st, oc, (X, Y, np.zeros_like(A)), dt=10.0)
+    assert nop[0] and not ev[0] and st["FxOA"][0] == 7.0
+
+
+def test_oracle_strain_of_rigid_motion():
+    """:226-233 as written sums diff(U).*diff(y) over the outline (not a Green's-theorem quadrature): for a rigid motion
+    U = Ui - ksi*y, V = Vi + ksi*x it gives du_dx = -ksi/2 * sum(dy^2)/area, dv_dy = +ksi/2 * sum(dx^2)/area and off-diagonal
+    terms that cancel in the symmetrisation -- hand-derived here, whatever one thinks of the formula"""
+    ksi = 3e-6
+    prm, one = one_floe(u=0.2, v=-0.1, ksi=ksi)
+    strain = np.full((1, 2, 2), 9.0)
+    oracle.floe_strain(one, np.zeros(1, np.uint8), strain)
+    dx, dy = np.diff(one.vx), np.diff(one.vy)                                             # the outline is closed
+    assert strain[0, 0, 0] == pytest.approx(-0.5 * ksi * np.sum(dy * dy) / one.area[0], rel=1e-9)
+    assert strain[0, 1, 1] == pytest.approx(+0.5 * ksi * np.sum(dx * dx) / one.area[0], rel=1e-9)
+    assert abs(strain[0, 0, 1]) < 1e-15 and strain[0, 0, 1] == strain[0, 1, 0]
+    one.alive[0] = 0
+    strain[:] = 9.0
+    oracle.floe_strain(one, np.zeros(1, np.uint8), strain)
+    assert np.all(strain == 9.0)                                                         # not updated: keeps the old floe.strain
+
+
+def gyre_ocean(L, n=41):
+    """initialize_ocean.m:10-27 on a smaller grid: eddies from a streamfunction, winds with a weak shear"""
+    Xo = np.linspace(-1.6 * L, 1.6 * L, n)
+    Yo = np.linspace(-1.6 * L, 1.6 * L, n)
+    dXo = Xo[1] - Xo[0]
+    gx, gy = np.meshgrid(Xo, Yo)
+    psi = 0.5e4 * np.sin(4 * np.pi / (1.6 * L) * gx) * np.sin(4 * np.pi / (1.6 * L) * gy)
+    U, V = np.zeros_like(gx), np.zeros_like(gx)
+    U[1:, :] = -(psi[1:, :] - psi[:-1, :]) / dXo
+    V[:, 1:] = (psi[:, 1:] - psi[:, :-1]) / dXo
+    return {"Xo": Xo, "Yo": Yo, "Uocn": U, "Vocn": V, "Uwinds": 5.0 + 1e-5 * gy, "Vwinds": -3.0 + 2e-5 * gx, "fCoriolis": 1.4e-4, "turn_angle": 15 * np.pi / 180}
+
+
+def monte_carlo_points(soa, npts, rng):
+    """initialize_floe_values.m:31-33 for convex outlines: uniform points in the rmax box, A = inside the outline"""
+    n = soa.n
+    X = soa.rmax[:, None] * (2 * rng.random((n, npts)) - 1)
+    Y = soa.rmax[:, None] * (2 * rng.random((n, npts)) - 1)
+    A = np.zeros((n, npts), np.uint8)
+    for i in range(n):
+        vx, vy = soa.outline(i)
+        ex, ey = np.diff(vx), np.diff(vy)
+        cr = ex[None, :] * (Y[i][:, None] - vy[None, :-1]) - ey[None, :] * (X[i][:, None] - vx[None, :-1])
+        A[i] = np.all(cr <= 0, axis=1) | np.all(cr >= 0, axis=1)
+    return X, Y, A
+
+
+@pytest.mark.gpu
+def test_device_ocean_forcing_and_strain_match_oracle():
+    """contact step -> ocean forcing -> trajectory step on the device against the same sequence on the oracle, three coupled
+    steps: doInt.flag set, clear (forcing carried over), set again; FxOA/FyOA/torqueOA, strain and the advanced state within
+    1e-9 (relative to each field's magnitude)"""
+    rng = np.random.default_rng(7)
+    n, nz, npts = 2500, 4, 300
+    prm, soa = sz.voronoi_field(n, seed=9)
+    prm.dt = 10.0
+    ref_soa = copy_soa(soa)
+    st = make_state(soa, nz, rng)
+    st["alpha"] = rng.uniform(-0.3, 0.3, n)
+    ca, sa = np.repeat(np.cos(st["alpha"]), np.diff(soa.voff)), np.repeat(np.sin(st["alpha"]), np.diff(soa.voff))
+    st["c0x"], st["c0y"] = ca * soa.vx + sa * soa.vy, -sa * soa.vx + ca * soa.vy          # c_alpha = A_rot(alpha) * c0
+    L = prm.Lx
+    bounds = (-1.5 * L, 1.5 * L, -1.5 * L, 1.5 * L)
+    ocean = gyre_ocean(L)
+    pts = monte_carlo_points(soa, npts, rng)
+    strain = np.zeros((n, 2, 2))
+    with sz.ContactContext(0) as ctx:
+        ctx.upload(prm, soa)
+        ctx.trajectory_init(st["mass"], st["inertia"], nz=nz, **{k: st[k] for k in ("alpha", "dXi_p", "dYi_p", "FxOA", "FyOA", "torqueOA", "c0x", "c0y")})
+        ctx.trajectory_set_ocean(**{k: ocean[k] for k in ("Xo", "Yo", "Uocn", "Vocn", "Uwinds", "Vwinds")}, fCoriolis=ocean["fCoriolis"], turn_angle=ocean["turn_angle"])
+        ctx.trajectory_set_points(*pts)
+        for it, do_int in enumerate((True, False, True)):
+            ctx.step_resident()
+            ne, nn = ctx.trajectory_ocean_forcing(prm.dt, 0.0, *bounds, do_int=do_int)
+            ctx.trajectory_step(prm.dt, 0.0, *bounds)
+            ref = oracle.OracleStep(prm, ref_soa, broad_mode=1)
+            ev, nop = oracle.ocean_forcing(ref, ref_soa, st, ocean, pts, prm.dt, 0.0, bounds, do_int)
+            sacked, unsup = oracle.calc_trajectory(ref, ref_soa, st, prm.dt, 0.0, bounds, nz)
+            if do_int:
+                oracle.floe_strain(ref_soa, sacked, strain)
+            assert (ne, nn) == (int(ev.sum()), int(nop.sum())) and not unsup.any()
+            assert ne == (n if do_int else 0)
+            got = ctx.trajectory_state(nverts=soa.vx.shape[0])
+            frc = ctx.trajectory_forcing()
+            for k, want in (("FxOA", st["FxOA"]), ("FyOA", st["FyOA"]), ("torqueOA", st["torqueOA"]), ("strain", strain)):
+                err = np.abs(frc[k] - want).max() / max(np.abs(want).max(), 1e-300)
+                assert err <= 1e-9, (it, k, err)
+            for k, want in (("x", ref_soa.x), ("y", ref_soa.y), ("u", ref_soa.u), ("v", ref_soa.v), ("ksi", ref_soa.ksi), ("alpha", st["alpha"]), ("dUi_p", st["dUi_p"]), ("dksi_p", st["dksi_p"])):
+                err = np.abs(got[k] - want).max() / max(np.abs(want).max(), 1e-300)
+                assert err <= 1e-9, (it, k, err)
+    assert np.abs(st["FxOA"]).min() > 0 and np.abs(strain).max() > 0
