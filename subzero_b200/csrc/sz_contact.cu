@@ -1292,9 +1292,10 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     exclusive_scan(c->rcnt.p, n, c->row_off.p, n + 1, c->scan_tmp.p, st);
     CK(cudaMemcpyAsync(D_CNT(total_rows), c->row_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
-    CKS(read_counters(c));
-    const i64 nrows = c->h_cnt->total_rows; c->n_rows = nrows;
-    CK(c->rows.ensure((size_t)nrows * 7 + 7)); CK(c->osum.ensure((size_t)n * 3 + 3)); CK(c->has_rows.ensure(n + 1));
+    // every row of the pool appears at most twice (its floe's own row and the partner's mirrored row): the row count is
+    // bounded without waiting for it; the exact value comes back with the step's last counter read
+    const i64 rows_bound = 2 * (i64)c->h_cnt->row_used;
+    CK(c->rows.ensure((size_t)rows_bound * 7 + 7)); CK(c->osum.ensure((size_t)n * 3 + 3)); CK(c->has_rows.ensure(n + 1));
     const int nout = ext ? n : n0; c->nout = nout;
     CK(c->kill_i.ensure(n + 1)); CK(c->transfer_i.ensure(n + 1)); CK(c->tmax.ensure(nout + 1));
     CK(c->o_fx.ensure(nout + 1)); CK(c->o_fy.ensure(nout + 1)); CK(c->o_tq.ensure(nout + 1)); CK(c->o_ov.ensure(nout + 1)); CK(c->o_stress.ensure(4 * (size_t)nout + 4));
@@ -1330,6 +1331,8 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     CK(cudaEventElapsedTime(&c->phase_ms[0], c->ev0, c->evp[0])); CK(cudaEventElapsedTime(&c->phase_ms[1], c->evp[0], c->evp[1]));
     CK(cudaEventElapsedTime(&c->phase_ms[2], c->evp[1], c->evp[2])); CK(cudaEventElapsedTime(&c->phase_ms[3], c->evp[2], c->ev1)); c->phase_ms[4] = ms;
 
+    const i64 nrows = c->h_cnt->total_rows; c->n_rows = nrows;
+    if (nrows > rows_bound) { sz_set_error("sz_step_resident: %lld contact rows exceed the bound %lld", (long long)nrows, (long long)rows_bound); return SZ_ERR_CAPACITY; }
     SzSummary& s = c->summary; memset(&s, 0, sizeof(s));
     s.n0 = n0; s.n = n; s.n_pairs = np; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows; s.n_pairs_owned = c->h_cnt->n_pairs_owned;
     s.n_clip_paths = P.want_clip_polys ? c->h_cnt->path_used : 0; s.n_clip_verts = P.want_clip_polys ? c->h_cnt->vert_used : 0;
