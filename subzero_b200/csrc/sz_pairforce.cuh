@@ -545,7 +545,11 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
 #define SZ_C_STEPS_PER_SYNC 1
 #endif
         for (;;) {
+#if defined(SZ_C_SWEEP_WARP) && defined(__CUDA_ARCH__)
+            if (!__any_sync(0xffffffffu, run)) break;        // experiment: warps sweep independently, the CTA meets again below
+#else
             if (!SZ_WARP_ANY(run)) break;
+#endif
             for (int u = 0; u < SZ_C_STEPS_PER_SYNC; ++u) { if (run) run = cs.step(); SZ_LANE_SYNC(); }
         }
         if (go) {
