@@ -241,6 +241,19 @@ int sz_trajectory_set_points(SzContext* ctx, int32_t npts, const double* X, cons
 int sz_trajectory_ocean_forcing(SzContext* ctx, const SzTrajectoryParams* prm, int32_t do_int, int32_t* n_evaluated, int32_t* n_no_points);
 int sz_get_trajectory_forcing(SzContext* ctx, double* FxOA, double* FyOA, double* torqueOA, double* strain);
 
+/* ---- SURVEY.md 8f row f3, first consumer of the contact rows: Physical_Processes/fracture_floe.m:12-52, the deformation a
+ * floe receives from its deepest contact before fracture.m splits it (the Voronoi split itself draws random points and
+ * stays with the host).  floe_idx: `count` floe numbers (1-based positions in the list of the last contact step, host or
+ * device memory).  For each: the floe-floe row with the largest overlap (:17-22); if its partner is an original floe
+ * (:26): clip 'int' (:29), centroid of the first region and its distance to the region's outline (:34-35), the partner
+ * pushed half that distance along the contact force (:36-39), clip 'dif' (:40); when more than 90 % of the area is left
+ * (:44) the first region becomes the floe's outline about its new centroid (:45-48).  Uses the resident positions and
+ * outlines (after sz_trajectory_step when the device integrates).  Results stay on the device until fetched:
+ *   changed [count], Xi Yi area [count] (the old values for unchanged floes), and for changed floes the new c_alpha as
+ *   an OPEN ring in Clipper's output order: vert_off [count + 1] into cx, cy [n_verts].  Any pointer may be NULL. */
+int sz_fracture_deform(SzContext* ctx, int32_t count, const int32_t* floe_idx, int64_t* n_changed, int64_t* n_verts);
+int sz_get_fracture_deform(SzContext* ctx, uint8_t* changed, double* xi, double* yi, double* area, int64_t* vert_off, double* cx, double* cy);
+
 /* diagnostic: device time (CUDA events, ms) of the last step by phase:
  * [0] ghost floes (floe_interactions_all.m:16-66)   [1] broad phase (:68-120)
  * [2] narrow phase + force law (:125-174)           [3] mirror/torque/sums (:186-265)   [4] whole step */

@@ -1000,4 +1000,65 @@ void szo_floe_strain(int n, const uint8_t* alive, const uint8_t* sacked, const d
     }
 }
 
+// Physical_Processes/fracture_floe.m:12-52 -- the "slight permanent deformation" a floe receives before it is fractured,
+// the deterministic consumer of the contact rows (the Voronoi split that follows draws random points).  For every
+// selected floe (idx, 1-based position in the floe list the contact step ran on = Floe0): the row with the largest
+// overlap among its floe-floe rows (:17-22); if the partner is an original floe (:26), clip the two outlines ('int', :29),
+// take the first region, its polyshape centroid and the distance from the centroid to the region's outline
+// (p_poly_dist, :34-35), push the partner by half that distance along the contact force (:36-39), subtract it from the
+// floe ('dif', :40) and, if more than 90 % of the floe's area is left, make that region the floe's new outline about its
+// new centroid (:41-50).  Outputs per selected floe: changed, Xi, Yi, area and, for changed floes, the new c_alpha
+// (open ring in Clipper's order) in the pools (vert_off [count + 1]).  Returns the vertices needed, or -1 on "Clipper Error.",
+// -3 when p_poly_dist would raise.
+int szo_fracture_deform(const SzFloesSoA* f, const int64_t* row_off, const double* rows, int count, const int32_t* idx,
+                        uint8_t* changed, double* xi, double* yi, double* area, int64_t* vert_off, double* cx, double* cy, int64_t vcap)
+{
+    const int N0 = f->n;
+    int64_t pos = 0; vert_off[0] = 0;
+    auto world = [&](int i, Curve& c) {
+        const int o = f->voff[i], n = f->voff[i + 1] - o;
+        c.x.resize(n); c.y.resize(n);
+        for (int t = 0; t < n; ++t) { c.x[t] = f->vx[o + t] + f->x[i]; c.y[t] = f->vy[o + t] + f->y[i]; }
+    };
+    for (int q = 0; q < count; ++q) {
+        const int i = idx[q] - 1;
+        changed[q] = 0; xi[q] = f->x[i]; yi[q] = f->y[i]; area[q] = f->area[i]; vert_off[q + 1] = pos;
+        // a = floe.interactions without the wall rows; [~,k] = max(a(:,7)) (first maximum)
+        int k = -1; double best = 0;
+        for (int64_t r = row_off[i]; r < row_off[i + 1]; ++r) {
+            const double* a = rows + r * 7;
+            if (std::isinf(a[0])) continue;
+            if (k < 0 || a[6] > best) { best = a[6]; k = (int)r; }
+        }
+        if (k < 0) continue;
+        const double* a = rows + (int64_t)k * 7;
+        const double clip = a[0];
+        if (!(clip < N0 + 1)) continue;                                            // :26 ghost partners are skipped
+        const int j = (int)clip - 1;
+        Curve c1, c2; world(i, c1); world(j, c2);
+        std::vector<Curve> out;
+        try { polyclip(c1, c2, 1, out); } catch (ClipperError&) { return -1; }    // :29
+        if (out.empty()) continue;                                                 // :32
+        double ar, xm, ym;
+        polyshape_area_centroid(out[0].x, out[0].y, ar, xm, ym);                   // :34
+        vec d;
+        try { p_poly_dist(vec{xm}, vec{ym}, out[0].x, out[0].y, d); } catch (PolyDistError&) { return -3; }   // :35
+        const double F = std::sqrt(a[1] * a[1] + a[2] * a[2]);                     // vecnorm(a(k,2:3))
+        const double xs = a[1] * std::fabs(d[0]) / 2 / F, ys = a[2] * std::fabs(d[0]) / 2 / F;   // :37-38
+        for (size_t t = 0; t < c2.x.size(); ++t) { c2.x[t] = c2.x[t] + xs; c2.y[t] = c2.y[t] + ys; }   // :39
+        try { polyclip(c1, c2, 0, out); } catch (ClipperError&) { return -1; }    // :40
+        if (out.empty()) continue;
+        const double Anew = polyarea(out[0].x, out[0].y);                          // :43
+        if (!(Anew / f->area[i] > 0.9)) continue;                                  // :44
+        polyshape_area_centroid(out[0].x, out[0].y, ar, xm, ym);                   // :45
+        changed[q] = 1; xi[q] = xm; yi[q] = ym; area[q] = Anew;                    // :46-47
+        for (size_t t = 0; t < out[0].x.size(); ++t) {
+            if (pos < vcap) { cx[pos] = out[0].x[t] - xm; cy[pos] = out[0].y[t] - ym; }   // :48
+            ++pos;
+        }
+        vert_off[q + 1] = pos;
+    }
+    return (int)pos;
+}
+
 }  // extern "C"

@@ -48,6 +48,8 @@ void szo_ocean_forcing(int n, double dt, double HFo, double xo_min, double xo_ma
                        double* FxOA, double* FyOA, double* torqueOA, uint8_t* evaluated, uint8_t* no_points);
 void szo_floe_strain(int n, const uint8_t* alive, const uint8_t* sacked, const double* area, const double* u, const double* v, const double* ksi,
                      const int32_t* voff, const double* cax, const double* cay, double* strain);
+int  szo_fracture_deform(const SzFloesSoA* f, const int64_t* row_off, const double* rows, int count, const int32_t* idx,
+                         uint8_t* changed, double* xi, double* yi, double* area, int64_t* vert_off, double* cx, double* cy, int64_t vcap);
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,21 @@ class ContactContext:
         abi.check(abi.lib().sz_trajectory_step(self._h, C.byref(p), C.byref(ns), C.byref(no)))
         return ns.value
 
+    # ---- fracture_floe.m:12-52: deformation of the floes about to be fractured (consumer of the contact rows)
+    def fracture_deform(self, idx):
+        """idx: floe numbers (1-based) of the last contact step's list; returns dict changed xi yi area vert_off cx cy"""
+        idx = np.ascontiguousarray(idx, np.int32)
+        n = idx.shape[0]
+        nc, nv = C.c_int64(), C.c_int64()
+        abi.check(abi.lib().sz_fracture_deform(self._h, n, abi._ptr(idx, abi.c_ip), C.byref(nc), C.byref(nv)))
+        o = {"changed": np.zeros(n, np.uint8), "xi": np.zeros(n), "yi": np.zeros(n), "area": np.zeros(n), "vert_off": np.zeros(n + 1, np.int64),
+             "cx": np.zeros(nv.value), "cy": np.zeros(nv.value)}
+        p = abi._ptr
+        abi.check(abi.lib().sz_get_fracture_deform(self._h, p(o["changed"], abi.c_bp), p(o["xi"], abi.c_dp), p(o["yi"], abi.c_dp), p(o["area"], abi.c_dp),
+                                                   p(o["vert_off"], abi.c_lp), p(o["cx"], abi.c_dp), p(o["cy"], abi.c_dp)))
+        assert int(o["changed"].sum()) == nc.value
+        return o
+
     # ---- ocean / atmosphere forcing (calc_trajectory.m:94-166) and strain (:224-234)
     def trajectory_set_ocean(self, Xo, Yo, Uocn, Vocn, Uwinds, Vwinds, fCoriolis, turn_angle, rho0=0.0, Cd=0.0, rho_air=0.0, Cd_atm=0.0):
         """Xo [nx], Yo [ny]; the four fields as (ny, nx) arrays like ocean.Uocn / winds.u in MATLAB"""

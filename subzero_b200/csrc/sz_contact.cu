@@ -84,6 +84,7 @@ struct Counters {
     u64 n_fin_rows, n_inf_rows;
     int clip_listM, clip_listL, clip_path_used, clip_vert_used;
     int n_forced, n_no_points;     // ocean forcing: floes evaluated / floes without a Monte-Carlo point inside
+    int fr_vert_used, fr_changed;  // fracture deformation: vertices of the new outlines, floes changed
 };
 
 struct SzContext {
@@ -132,6 +133,8 @@ struct SzContext {
     // integrator state (sz_trajectory_*): calc_trajectory.m fields kept on the device between steps
     bool have_traj = false; int traj_nz = 0;
     DBuf<double> t_mass, t_inertia, t_alpha, t_dXi_p, t_dYi_p, t_dUi_p, t_dVi_p, t_dalpha_p, t_dksi_p, t_FxOA, t_FyOA, t_torqueOA, c0x, c0y, t_stressH, t_stress;
+    // fracture deformation (fracture_floe.m:12-52)
+    DBuf<int> fr_idx, fr_vstart, fr_vcount, fr_status; DBuf<uint8_t> fr_changed; DBuf<double> fr_xi, fr_yi, fr_area, fr_vx, fr_vy; int fr_count = 0; i64 fr_verts = 0; bool have_fr = false;
     // ocean / atmosphere forcing (calc_trajectory.m:94-166)
     DBuf<double> oc_Xo, oc_Yo, oc_U, oc_V, oc_Wu, oc_Wv, pt_x, pt_y, t_strain; DBuf<uint8_t> pt_a, t_forced;
     int oc_nx = 0, oc_ny = 0, npts = 0; bool have_ocean = false, have_points = false, traj_do_int = false;
@@ -823,15 +826,16 @@ extern "C" void sz_destroy(SzContext* c)
     cudaStreamSynchronize(c->stream);
     DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi,
-                          &c->oc_Xo, &c->oc_Yo, &c->oc_U, &c->oc_V, &c->oc_Wu, &c->oc_Wv, &c->pt_x, &c->pt_y, &c->t_strain};
+                          &c->oc_Xo, &c->oc_Yo, &c->oc_U, &c->oc_V, &c->oc_Wu, &c->oc_Wv, &c->pt_x, &c->pt_y, &c->t_strain,
+                          &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
                        &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->stage, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
-                       &c->c_path_len, &c->c_listM, &c->c_listL};
+                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced};
+    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed};
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
@@ -1779,6 +1783,81 @@ extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
     if (strcmp(name, "convex_fast") == 0) { c->opt_convex_fast = value != 0; return SZ_OK; }
     sz_set_error("sz_set_option: unknown option '%s'", name);
     return SZ_ERR_ARG;
+}
+// ------------------------------------------------------------------------------------------------ fracture deformation
+extern "C" int sz_fracture_deform(SzContext* c, int32_t count, const int32_t* floe_idx, int64_t* n_changed, int64_t* n_verts)
+{
+    NEED_STEP("sz_fracture_deform");
+    if (c->ext_mode) { sz_set_error("sz_fracture_deform: single-GPU lists only"); return SZ_ERR_STATE; }
+    if (count < 0 || (count > 0 && !floe_idx)) { sz_set_error("sz_fracture_deform: bad arguments"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    c->have_fr = false; c->fr_count = count; c->fr_verts = 0;
+    if (n_changed) *n_changed = 0;
+    if (n_verts) *n_verts = 0;
+    if (count == 0) { c->have_fr = true; return SZ_OK; }
+    {   // the numbers must name floes of the list
+        std::vector<int32_t> h(count);
+        CK(cudaMemcpy(h.data(), floe_idx, (size_t)count * 4, cudaMemcpyDefault));
+        for (int32_t v : h) if (v < 1 || v > c->n0) { sz_set_error("sz_fracture_deform: floe number %d outside 1..%d", v, c->n0); return SZ_ERR_ARG; }
+        CK(c->fr_idx.ensure(count + 1));
+        CK(cudaMemcpyAsync(c->fr_idx.p, h.data(), (size_t)count * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st));
+    }
+    CK(c->fr_changed.ensure(count + 1)); CK(c->fr_xi.ensure(count + 1)); CK(c->fr_yi.ensure(count + 1)); CK(c->fr_area.ensure(count + 1));
+    CK(c->fr_vstart.ensure(count + 1)); CK(c->fr_vcount.ensure(count + 1)); CK(c->fr_status.ensure(count + 1));
+    CK(c->fr_vx.ensure((size_t)c->nverts + 64 * (size_t)count + 64)); CK(c->fr_vy.ensure(c->fr_vx.cap));
+    const int threads = std::min((count + 63) / 64 * 64, 148 * 16);
+    CK(c->scratchL.ensure((size_t)threads * sz_workspace_bytes_L()));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
+        sznarrow::FractureArgs a; memset(&a, 0, sizeof(a));
+        a.count = count; a.idx = c->fr_idx.p; a.n0 = c->n0;
+        a.x = c->x.p; a.y = c->y.p; a.area = c->area.p; a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
+        a.row_off = c->row_off.p; a.rows = c->rows.p;
+        a.changed = c->fr_changed.p; a.oxi = c->fr_xi.p; a.oyi = c->fr_yi.p; a.oarea = c->fr_area.p; a.vstart = c->fr_vstart.p; a.vcount = c->fr_vcount.p; a.status = c->fr_status.p;
+        a.pvx = c->fr_vx.p; a.pvy = c->fr_vy.p; a.vert_cap = (int)std::min<size_t>(c->fr_vx.cap, 0x7fffffff); a.vert_used = D_CNT(fr_vert_used); a.n_changed = D_CNT(fr_changed);
+        a.scratch = c->scratchL.p; a.n_threads = threads;
+        ++g_launches; sz_launch_fracture_L(&a, st);
+        CK(cudaGetLastError());
+        CKS(read_counters(c));
+        if ((size_t)c->h_cnt->fr_vert_used <= c->fr_vx.cap) break;
+        if (attempt == 1) { sz_set_error("sz_fracture_deform: vertex pool kept overflowing"); return SZ_ERR_CAPACITY; }
+        CK(c->fr_vx.ensure((size_t)c->h_cnt->fr_vert_used + 64)); CK(c->fr_vy.ensure(c->fr_vx.cap));
+    }
+    c->fr_verts = c->h_cnt->fr_vert_used;
+    std::vector<int> stt(count);
+    CK(cudaMemcpy(stt.data(), c->fr_status.p, (size_t)count * 4, cudaMemcpyDefault));
+    for (int k = 0; k < count; ++k) if (stt[k] != 0) {
+        const int code = stt[k] == szpf::PS_CLIPPER_FAIL ? SZ_ERR_CLIPPER : (stt[k] == szpf::PS_CAPACITY ? SZ_ERR_CAPACITY : SZ_ERR_ARG);
+        sz_set_error("sz_fracture_deform: item %d failed (%s)", k, code == SZ_ERR_CLIPPER ? "Clipper Error." : code == SZ_ERR_CAPACITY ? "outline beyond the largest size class" : "p_poly_dist would raise: degenerate region outline");
+        return code;
+    }
+    c->have_fr = true;
+    if (n_changed) *n_changed = c->h_cnt->fr_changed;
+    if (n_verts) *n_verts = c->fr_verts;
+    return SZ_OK;
+}
+extern "C" int sz_get_fracture_deform(SzContext* c, uint8_t* changed, double* xi, double* yi, double* area, int64_t* vert_off, double* cx, double* cy)
+{
+    if (!c) { sz_set_error("sz_get_fracture_deform: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_fr) { sz_set_error("sz_get_fracture_deform: no result"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->fr_count;
+    D2H(changed, c->fr_changed.p, n); D2H(xi, c->fr_xi.p, n * 8); D2H(yi, c->fr_yi.p, n * 8); D2H(area, c->fr_area.p, n * 8);
+    CK(cudaStreamSynchronize(c->stream));
+    if (vert_off || cx || cy) {
+        std::vector<int> vs(n), vc(n); std::vector<double> px((size_t)c->fr_verts), py((size_t)c->fr_verts);
+        if (n) { CK(cudaMemcpy(vs.data(), c->fr_vstart.p, n * 4, cudaMemcpyDefault)); CK(cudaMemcpy(vc.data(), c->fr_vcount.p, n * 4, cudaMemcpyDefault)); }
+        if (c->fr_verts) { CK(cudaMemcpy(px.data(), c->fr_vx.p, (size_t)c->fr_verts * 8, cudaMemcpyDefault)); CK(cudaMemcpy(py.data(), c->fr_vy.p, (size_t)c->fr_verts * 8, cudaMemcpyDefault)); }
+        int64_t pos = 0;
+        if (vert_off) vert_off[0] = 0;
+        for (size_t k = 0; k < n; ++k) {
+            for (int t = 0; t < vc[k]; ++t) { if (cx) cx[pos + t] = px[(size_t)vs[k] + t]; if (cy) cy[pos + t] = py[(size_t)vs[k] + t]; }
+            pos += vc[k];
+            if (vert_off) vert_off[k + 1] = pos;
+        }
+    }
+    return SZ_OK;
 }
 // reorder (start, count) pools into item-major CSR
 static int export_paths(SzContext* c, int n_items, const int* d_item_start, const int* d_item_np, const int* d_status, const int* d_path_vstart, const int* d_path_len,

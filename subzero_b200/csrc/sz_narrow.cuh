@@ -75,6 +75,17 @@ struct ClipArgs {
     void* scratch; int n_threads;
 };
 
+// Physical_Processes/fracture_floe.m:12-52: the deformation of the floes about to be fractured (see fracture_deform_kernel)
+struct FractureArgs {
+    int count; const int* idx;                  // floe numbers, 1-based positions in the floe list of the last contact step
+    int n0;
+    const double* x; const double* y; const double* area; const int* voff; const double* vx; const double* vy;
+    const int* row_off; const double* rows;     // Floe(i).interactions of that step: [K][7]
+    unsigned char* changed; double* oxi; double* oyi; double* oarea; int* vstart; int* vcount; int* status;
+    double* pvx; double* pvy; int vert_cap; int* vert_used; int* n_changed;
+    void* scratch; int n_threads;
+};
+
 struct PtrGetter { const i64* x; const i64* y; SZ_HD P64 operator()(int i) const { P64 p; p.x = x[i]; p.y = y[i]; return p; } };
 
 // sink that stores emitted paths straight into the global pools (space reserved beforehand)
@@ -207,6 +218,97 @@ __global__ void __launch_bounds__(64) narrow_scratch_kernel(const NarrowArgs a)
     }
 }
 
+// One thread per selected floe (persistent threads over the list, class-L arena in HBM scratch; all threads of the CTA
+// walk the two sweeps together like the narrow phase).  fracture_floe.m:17-50.
+template <class C>
+__global__ void __launch_bounds__(64) fracture_deform_kernel(const FractureArgs a)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    szpf::Workspace<C>& w = reinterpret_cast<szpf::Workspace<C>*>(a.scratch)[tid];
+    for (int base = 0; base < a.count; base += a.n_threads) {
+        const int q = base + tid;
+        bool live = q < a.count;
+        int i = 0, j = 0, st = 0;
+        double fx = 0, fy = 0;
+        if (live) {
+            i = a.idx[q] - 1;
+            a.changed[q] = 0; a.oxi[q] = a.x[i]; a.oyi[q] = a.y[i]; a.oarea[q] = a.area[i]; a.vstart[q] = 0; a.vcount[q] = 0; a.status[q] = 0;
+            // a = interactions without the wall rows; [~,k] = max(a(:,7)): first maximum (:17-22)
+            int k = -1; double best = 0;
+            for (int r = a.row_off[i]; r < a.row_off[i + 1]; ++r) {
+                const double* row = a.rows + (size_t)r * 7;
+                if (row[0] == SZ_INF || row[0] == -SZ_INF) continue;
+                if (k < 0 || row[6] > best) { best = row[6]; k = r; }
+            }
+            if (k < 0) live = false;
+            else {
+                const double* row = a.rows + (size_t)k * 7;
+                if (!(row[0] < a.n0 + 1)) live = false;                 // :26: the partner must be an original floe
+                else { j = (int)row[0] - 1; fx = row[1]; fy = row[2]; }
+            }
+        }
+        if (live) {
+            const int o1 = a.voff[i], n1 = a.voff[i + 1] - o1, o2 = a.voff[j], n2 = a.voff[j + 1] - o2;
+            if (n1 + 1 > C::NV || n2 + 1 > C::NV || n1 < 1 || n2 < 1) { st = szpf::PS_CAPACITY; live = false; }
+            else {
+                w.n1 = n1; w.n2 = n2;
+                for (int t = 0; t < n1; ++t) { w.c1x[t] = a.vx[o1 + t] + a.x[i]; w.c1y[t] = a.vy[o1 + t] + a.y[i]; }    // :23-24
+                for (int t = 0; t < n2; ++t) { w.c2x[t] = a.vx[o2 + t] + a.x[j]; w.c2y[t] = a.vy[o2 + t] + a.y[j]; }    // :27-28
+            }
+        }
+        szpf::ClipInput subj, clip;
+        subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = w.n1; subj.ring = 0; subj.rot = 0;
+        clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = w.n2; clip.ring = 0; clip.rot = 0;
+        int cs = szpf::run_sweep(w.eng, live, 1, subj, clip);                                     // :29 polyclip(..., 'int')
+        if (live && cs != szpf::PS_OK) { st = cs; live = false; }
+        int nr = 0;
+        if (live) {
+            szpf::RegionSink<C> sink(w.rax, w.ray, w.ra_off);
+            w.eng.emit(sink);
+            if (sink.overflow) { st = szpf::PS_CAPACITY; live = false; }
+            else if (sink.n_paths == 0) live = false;                                             // :32
+            else nr = w.ra_off[1];
+        }
+        if (live) {
+            double ar, xm, ym;
+            szpf::ring_area_centroid(w.rax, w.ray, nr, ar, xm, ym);                               // :34 centroid(polyshape(Xt,Yt))
+            if (nr + 1 > C::NP) { st = szpf::PS_CAPACITY; live = false; }
+            else {
+                for (int t = 0; t < nr; ++t) { w.px[t] = (double)w.rax[t] / SZ_SCALE; w.py[t] = (double)w.ray[t] / SZ_SCALE; }
+                int nc = nr;
+                if (w.px[0] != w.px[nr - 1] || w.py[0] != w.py[nr - 1]) { w.px[nr] = w.px[0]; w.py[nr] = w.py[0]; nc = nr + 1; }   // p_poly_dist.m:135-141
+                if (!szpf::outline_ok_for_poly_dist_xy(w.px, w.py, nc)) { st = szpf::PS_BAD_POLY; live = false; }
+                else {
+                    const double d = szpf::abs_poly_dist_xy(w.px, w.py, nc, xm, ym);              // :35 |p_poly_dist|
+                    const double F = sqrt(fx * fx + fy * fy);                                     // :36
+                    clip.dx = fx * d / 2 / F; clip.dy = fy * d / 2 / F;                           // :37-39
+                }
+            }
+        }
+        cs = szpf::run_sweep(w.eng, live, 0, subj, clip);                                         // :40 polyclip(..., 'dif')
+        if (live && cs != szpf::PS_OK) { st = cs; live = false; }
+        if (live) {
+            szpf::RegionSink<C> sink(w.rax, w.ray, w.ra_off);
+            w.eng.emit(sink);
+            if (sink.overflow) { st = szpf::PS_CAPACITY; live = false; }
+            else if (sink.n_paths == 0) live = false;
+            else nr = w.ra_off[1];
+        }
+        if (live) {
+            const double anew = szpf::ring_polyarea(w.rax, w.ray, nr);                            // :43
+            if (anew / a.area[i] > 0.9) {                                                         // :44
+                double ar, xm, ym;
+                szpf::ring_area_centroid(w.rax, w.ray, nr, ar, xm, ym);                           // :45
+                const int vs = atomicAdd(a.vert_used, nr);
+                a.changed[q] = 1; a.oxi[q] = xm; a.oyi[q] = ym; a.oarea[q] = anew; a.vstart[q] = vs; a.vcount[q] = nr;    // :46-48
+                atomicAdd(a.n_changed, 1);
+                if (vs + nr <= a.vert_cap) for (int t = 0; t < nr; ++t) { a.pvx[vs + t] = (double)w.rax[t] / SZ_SCALE - xm; a.pvy[vs + t] = (double)w.ray[t] / SZ_SCALE - ym; }
+            }
+        }
+        if (q < a.count && st != 0) a.status[q] = st;
+    }
+}
+
 template <class CC>
 __device__ __forceinline__ void resolve_clip(const ClipArgs& a, int k, szclip::ClipEngine<CC>& eng)
 {
@@ -266,6 +368,7 @@ void sz_launch_narrow_L(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_clip_S(const sznarrow::ClipArgs* a, cudaStream_t stream);
 void sz_launch_clip_M(const sznarrow::ClipArgs* a, cudaStream_t stream);
 void sz_launch_clip_L(const sznarrow::ClipArgs* a, cudaStream_t stream);
+void sz_launch_fracture_L(const sznarrow::FractureArgs* a, cudaStream_t stream);
 size_t sz_workspace_bytes_M(void);
 size_t sz_workspace_bytes_L(void);
 }

@@ -14,3 +14,9 @@ extern "C" void sz_launch_clip_L(const ClipArgs* a, cudaStream_t stream)
     const int tpb = 64;
     clip_scratch_kernel<PairL><<<(a->n_threads + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
 }
+extern "C" void sz_launch_fracture_L(const FractureArgs* a, cudaStream_t stream)
+{
+    if (a->n_threads <= 0 || a->count <= 0) return;
+    const int tpb = 64;
+    fracture_deform_kernel<PairL><<<(a->n_threads + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
+}

@@ -428,24 +428,22 @@ SZ_HD bool in_region(double x, double y, const i64* X, const i64* Y, int n, doub
     return (sumdq != 0) || on;
 }
 
-// |p_poly_dist(x,y, c1)|: unsigned distance from one point to the closed outline c1 (n1 points,
-// first == last).  Returns <0 when the reference would raise (repeated vertices / flat polygon).
-template <class W>
-SZ_HD double abs_poly_dist(const W& w, double xq, double yq)
+// |p_poly_dist(x, y, xv, yv)|: unsigned distance from one point to a closed outline (nv points, first == last).
+SZ_HD double abs_poly_dist_xy(const double* vx, const double* vy, int nv, double xq, double yq)
 {
-    const int nv = w.n1, ns = nv - 1;
+    const int ns = nv - 1;
     double dpv_min = SZ_INF; int i_dpv = 0;
     for (int k = 0; k < nv; ++k) {
-        double d = hypot(w.c1x[k] - xq, w.c1y[k] - yq);
+        double d = hypot(vx[k] - xq, vy[k] - yq);
         if (fabs(d) < dpv_min) { dpv_min = fabs(d); i_dpv = k; }
     }
     double cr_min = 0; int i_cr = 0; bool have = false;
     for (int k = 0; k < ns; ++k) {
-        double dvx = w.c1x[k + 1] - w.c1x[k], dvy = w.c1y[k + 1] - w.c1y[k];
+        double dvx = vx[k + 1] - vx[k], dvy = vy[k + 1] - vy[k];
         double vds = hypot(dvx, dvy);
         double ct = dvx / vds, st = dvy / vds;
-        double p1rx = ct * w.c1x[k] + st * w.c1y[k];
-        double p1ry = -st * w.c1x[k] + ct * w.c1y[k];
+        double p1rx = ct * vx[k] + st * vy[k];
+        double p1ry = -st * vx[k] + ct * vy[k];
         double r = (xq * ct + yq * st) - p1rx;
         double cr = (xq * (-st) + yq * ct) - p1ry;
         if (r > 0 && r < vds) { double a = fabs(cr); if (!have || a < cr_min) { cr_min = a; i_cr = k; have = true; } }
@@ -453,19 +451,24 @@ SZ_HD double abs_poly_dist(const W& w, double xq, double yq)
     bool is_vertex = !have || ((i_cr != i_dpv) && (cr_min - dpv_min) > 0);
     return is_vertex ? dpv_min : cr_min;
 }
-template <class W>
-SZ_HD bool outline_ok_for_poly_dist(const W& w)   // p_poly_dist.m:166-179
+SZ_HD bool outline_ok_for_poly_dist_xy(const double* vx, const double* vy, int nv)   // p_poly_dist.m:166-179
 {
-    const int ns = w.n1 - 1;
-    if (w.n1 < 3) return false;
+    const int ns = nv - 1;
+    if (nv < 3) return false;
     double s = 0, last = 0;
     for (int k = 0; k < ns; ++k) {
-        double vds = hypot(w.c1x[k + 1] - w.c1x[k], w.c1y[k + 1] - w.c1y[k]);
+        double vds = hypot(vx[k + 1] - vx[k], vy[k + 1] - vy[k]);
         if (vds < 10 * SZ_EPS) return false;
         if (k + 1 < ns) s += vds; else last = vds;
     }
     return !((s - last) < 10 * SZ_EPS);
 }
+// the same against the closed outline c1 of the workspace (n1 points, first == last); the reference would raise for
+// repeated vertices / a flat polygon (outline_ok)
+template <class W>
+SZ_HD double abs_poly_dist(const W& w, double xq, double yq) { return abs_poly_dist_xy(w.c1x, w.c1y, w.n1, xq, yq); }
+template <class W>
+SZ_HD bool outline_ok_for_poly_dist(const W& w) { return outline_ok_for_poly_dist_xy(w.c1x, w.c1y, w.n1); }
 
 // normal + tangential force of one overlap region (floe_interactions.m:167-187): r = Fx Fy Px Py overlap
 SZ_HD void force_row(const Body& f1, const Body& f2, const Params& P, double G, double mu, double force_factor,

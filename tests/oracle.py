@@ -67,6 +67,8 @@ def lib():
                                         C.c_int, C.c_int] + [abi.c_dp] * 6 + [C.c_double] * 6 + [abi.c_dp] * 3 + [abi.c_bp, abi.c_bp]
         l.szo_floe_strain.restype = None
         l.szo_floe_strain.argtypes = [C.c_int, abi.c_bp, abi.c_bp] + [abi.c_dp] * 4 + [abi.c_ip, abi.c_dp, abi.c_dp, abi.c_dp]
+        l.szo_fracture_deform.restype = C.c_int
+        l.szo_fracture_deform.argtypes = [C.POINTER(abi.SzFloesSoA), abi.c_lp, abi.c_dp, C.c_int, abi.c_ip, abi.c_bp, abi.c_dp, abi.c_dp, abi.c_dp, abi.c_lp, abi.c_dp, abi.c_dp, C.c_int64]
         _lib = l
     return _lib
 
@@ -211,6 +213,25 @@ def floe_strain(floes, sacked, strain):
     p, D, B, I = abi._ptr, abi.c_dp, abi.c_bp, abi.c_ip
     lib().szo_floe_strain(floes.n, p(floes.alive, B), p(np.ascontiguousarray(sacked, np.uint8), B), p(floes.area, D), p(floes.u, D), p(floes.v, D), p(floes.ksi, D),
                           p(floes.voff, I), p(floes.vx, D), p(floes.vy, D), p(strain, D))
+
+
+def fracture_deform(step, floes, idx):
+    """the oracle's restatement of fracture_floe.m:12-52 for the floes idx (1-based) of the list `floes`, whose contact
+    rows come from `step`.  Returns dict changed xi yi area vert_off cx cy."""
+    off, rows = step.rows()
+    idx = np.ascontiguousarray(idx, np.int32)
+    n = idx.shape[0]
+    o = {"changed": np.zeros(n, np.uint8), "xi": np.zeros(n), "yi": np.zeros(n), "area": np.zeros(n), "vert_off": np.zeros(n + 1, np.int64)}
+    cap = int(floes.vx.shape[0]) * 4 + 64
+    cx, cy = np.zeros(cap), np.zeros(cap)
+    p, D, B, I, Lp = abi._ptr, abi.c_dp, abi.c_bp, abi.c_ip, abi.c_lp
+    off = np.ascontiguousarray(off, np.int64); rows = np.ascontiguousarray(rows)
+    view = floes.struct()
+    r = lib().szo_fracture_deform(C.byref(view), p(off, Lp), p(rows, D), n, p(idx, I), p(o["changed"], B), p(o["xi"], D), p(o["yi"], D), p(o["area"], D),
+                                  p(o["vert_off"], Lp), p(cx, D), p(cy, D), cap)
+    assert r >= 0 and r <= cap, r
+    o["cx"], o["cy"] = cx[:r].copy(), cy[:r].copy()
+    return o
 
 
 def _rel_err(a, b):

@@ -1,0 +1,92 @@
+"""Physical_Processes/fracture_floe.m:12-52 (first consumer of the contact rows): the deformation a
+floe receives from its deepest contact before it is fractured.  The oracle's restatement against a hand-derived case
+(CPU), and the device path (sz_fracture_deform) against the oracle on overlapping Voronoi fields (GPU)."""
+import numpy as np
+import pytest
+
+import oracle
+import scenarios
+import subzero_b200 as sz
+
+
+def two_squares(gap):
+    """two 2 km squares, the second shifted by `gap` in x: an overlap strip of width 2000 - gap"""
+    sq = np.array([[-1000.0, -1000.0], [-1000.0, 1000.0], [1000.0, 1000.0], [1000.0, -1000.0]])       # clockwise
+    fl = [scenarios.floe_from_polygon(sq), scenarios.floe_from_polygon(sq + [gap, 0.0])]
+    soa = sz.floes_to_soa(fl)
+    prm = sz.default_params(Lx=1e5, Ly=1e5, modulus=1e7, dt=10.0, periodic=1, collision=1)
+    return prm, soa
+
+
+def test_oracle_fracture_deform_known_answer():
+    """squares overlapping in a 100 m x 2000 m strip: region centroid (950, 0), 50 m from its outline; the partner is
+    pushed 25 m along the contact force (-x on floe 1) and subtracted: floe 1 keeps [-1000, 875] x [-1000, 1000]
+    = 93.75 % of its area, so it is replaced by that rectangle about its new centroid (-62.5, 0)"""
+    prm, soa = two_squares(1900.0)
+    step = oracle.OracleStep(prm, soa)
+    off, rows = step.rows()
+    assert off[1] - off[0] == 1 and rows[0, 0] == 2 and rows[0, 1] < 0 and rows[0, 2] == 0          # one contact row, force along -x
+    assert rows[0, 6] == pytest.approx(100.0 * 2000.0, rel=1e-9)
+    d = oracle.fracture_deform(step, soa, [1, 2])
+    assert list(d["changed"]) == [1, 1]
+    assert d["xi"][0] == pytest.approx(-62.5, abs=1e-6) and d["yi"][0] == pytest.approx(0.0, abs=1e-6) and d["area"][0] == pytest.approx(1875.0 * 2000.0, rel=1e-9)
+    n0 = int(d["vert_off"][1])
+    assert n0 == 4
+    assert sorted(np.round(d["cx"][:n0] + d["xi"][0], 6)) == [-1000.0, -1000.0, 875.0, 875.0]
+    assert sorted(np.round(d["cy"][:n0] + d["yi"][0], 6)) == [-1000.0, -1000.0, 1000.0, 1000.0]
+    # the partner is deformed symmetrically: it keeps [1025, 2900] in world x
+    n1 = int(d["vert_off"][2]) - n0
+    assert n1 == 4 and sorted(np.round(d["cx"][n0:] + d["xi"][1], 6)) == [1025.0, 1025.0, 2900.0, 2900.0]
+    # a deeper overlap removes more than 10 % of the floe: no deformation (:44)
+    prm, soa = two_squares(1500.0)
+    d = oracle.fracture_deform(oracle.OracleStep(prm, soa), soa, [1])
+    assert list(d["changed"]) == [0] and d["area"][0] == soa.area[0] and d["vert_off"][1] == 0
+    # no contact at all
+    prm, soa = two_squares(2500.0)
+    d = oracle.fracture_deform(oracle.OracleStep(prm, soa), soa, [1, 2])
+    assert list(d["changed"]) == [0, 0]
+
+
+def check_device_against_oracle(ctx, prm, soa, idx):
+    ctx.step(prm, soa, allow_pair_errors=True)
+    got = ctx.fracture_deform(idx)
+    ref_step = oracle.OracleStep(prm, soa, broad_mode=1)
+    want = oracle.fracture_deform(ref_step, soa, idx)
+    assert np.array_equal(got["changed"], want["changed"])
+    assert np.array_equal(got["vert_off"], want["vert_off"])
+    for k in ("xi", "yi", "area", "cx", "cy"):
+        scale = max(np.abs(want[k]).max(initial=0.0), 1e-300)
+        assert np.abs(got[k] - want[k]).max(initial=0.0) <= 1e-9 * scale, k
+    return want
+
+
+@pytest.mark.gpu
+def test_device_fracture_deform_matches_oracle():
+    """the hand-derived square case, then every floe of an overlapping Voronoi field (shallow and deep overlaps, ghost
+    partners across the periodic boundary, floes without contacts) and a field of real concave shapes"""
+    with sz.ContactContext(0) as ctx:
+        prm, soa = two_squares(1900.0)
+        w = check_device_against_oracle(ctx, prm, soa, [1, 2])
+        assert list(w["changed"]) == [1, 1]
+        n_changed = 0
+        for inflate, seed in ((0.02, 61), (0.1, 62)):
+            prm, soa = sz.voronoi_field(3000, seed=seed, inflate=inflate)
+            w = check_device_against_oracle(ctx, prm, soa, np.arange(1, soa.n + 1))
+            n_changed += int(w["changed"].sum())
+            assert 0 < w["changed"].sum() < soa.n
+        assert n_changed > 1000
+        # real floe shapes (7..591 vertices, concave), tiled so that neighbours overlap
+        polys, _, modulus = scenarios.floe_shapes()
+        rng = np.random.default_rng(3)
+        fl, k = [], 0
+        for gx in range(6):
+            for gy in range(6):
+                v = polys[(7 * k) % len(polys)]
+                f = scenarios.floe_from_polygon(v, u=rng.uniform(-.1, .1), v=rng.uniform(-.1, .1))
+                r = f["rmax"]
+                f["Xi"], f["Yi"] = gx * 1.2e4 + rng.uniform(-1, 1) * 1e3, gy * 1.2e4 + rng.uniform(-1, 1) * 1e3
+                fl.append(f); k += 1
+        soa = sz.floes_to_soa(fl)
+        prm = sz.default_params(Lx=2e5, Ly=2e5, modulus=modulus, dt=10.0, periodic=1, collision=1)
+        w = check_device_against_oracle(ctx, prm, soa, np.arange(1, soa.n + 1))
+        assert w["changed"].sum() > 0
