@@ -99,6 +99,7 @@ struct SzContext {
     Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
     // inputs
     bool have_input = false, have_step = false;
+    bool have_rows = false;                 // the contact rows of the last step are still on the device (also after the integrator moved the floes)
     SzParams prm; Params dprm; bool have_bnd = false; Body bbody;
     int n0 = 0; i64 nverts = 0;
     DBuf<double> x, y, rmax, h, area, u, v, ksi, vx, vy, bx, by, boxx, boxy;
@@ -893,7 +894,7 @@ extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f,
     if (!prm->periodic && bnd && (bnd->n < 3 || !bnd->x || !bnd->y)) { sz_set_error("sz_upload: boundary polygon needs >= 3 vertices"); return SZ_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     const int n = f->n; const size_t nv = (size_t)f->nverts;
-    c->have_step = false;
+    c->have_step = false; c->have_rows = false;
     CK(c->x.ensure(n)); CK(c->y.ensure(n)); CK(c->rmax.ensure(n)); CK(c->h.ensure(n)); CK(c->area.ensure(n));
     CK(c->u.ensure(n)); CK(c->v.ensure(n)); CK(c->ksi.ensure(n)); CK(c->alive.ensure(n)); CK(c->voff.ensure(n + 1));
     CK(c->vx.ensure(nv)); CK(c->vy.ensure(nv));
@@ -1151,7 +1152,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     const int n0 = c->n0, Nb = P.Nb;
     const bool ext = c->ext_mode;
     const int ncap = (P.periodic && !ext) ? 4 * n0 : n0;         // every floe has at most an x-, a y- and an xy-ghost
-    c->have_step = false;
+    c->have_step = false; c->have_rows = false;
     CK(cudaEventRecord(c->ev0, st));
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
 
@@ -1342,7 +1343,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     s.n_clip_paths = P.want_clip_polys ? c->h_cnt->path_used : 0; s.n_clip_verts = P.want_clip_polys ? c->h_cnt->vert_used : 0;
     s.collision_count = (double)c->h_cnt->n_fin_rows / 2 + (double)c->h_cnt->n_inf_rows;   // calc_collisionNum.m:6
     s.n_clipper_fail = c->h_cnt->n_fail; s.n_capacity_fail = c->h_cnt->n_cap_fail; s.ms_device = ms;
-    c->have_step = true;
+    c->have_step = true; c->have_rows = true;
     if (out) *out = s;
     if (s.n_capacity_fail > 0) { sz_set_error("%d pair(s) exceed the largest narrow-phase size class (1299 vertices per outline)", s.n_capacity_fail); return SZ_ERR_CAPACITY; }
     if (s.n_clipper_fail > 0) { sz_set_error("Clipper Error. (%d pair(s); per-pair status via sz_get_pairs)", s.n_clipper_fail); return SZ_ERR_CLIPPER; }
@@ -1787,7 +1788,8 @@ extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
 // ------------------------------------------------------------------------------------------------ fracture deformation
 extern "C" int sz_fracture_deform(SzContext* c, int32_t count, const int32_t* floe_idx, int64_t* n_changed, int64_t* n_verts)
 {
-    NEED_STEP("sz_fracture_deform");
+    if (!c) { sz_set_error("sz_fracture_deform: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_rows) { sz_set_error("sz_fracture_deform: no contact rows on the device (run a contact step first)"); return SZ_ERR_STATE; }
     if (c->ext_mode) { sz_set_error("sz_fracture_deform: single-GPU lists only"); return SZ_ERR_STATE; }
     if (count < 0 || (count > 0 && !floe_idx)) { sz_set_error("sz_fracture_deform: bad arguments"); return SZ_ERR_ARG; }
     CK(cudaSetDevice(c->device));

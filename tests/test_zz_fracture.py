@@ -75,6 +75,27 @@ def test_device_fracture_deform_matches_oracle():
             n_changed += int(w["changed"].sum())
             assert 0 < w["changed"].sum() < soa.n
         assert n_changed > 1000
+        # the reference's order: contact step -> calc_trajectory -> fracture: rows of the old positions, outlines of the new ones
+        prm, soa = sz.voronoi_field(2000, seed=63, inflate=0.05)
+        prm.dt = 10.0
+        ref_soa = sz.FloesSoA(soa.x.copy(), soa.y.copy(), soa.rmax.copy(), soa.h.copy(), soa.area.copy(), soa.u.copy(), soa.v.copy(), soa.ksi.copy(), soa.alive.copy(),
+                              soa.voff.copy(), soa.vx.copy(), soa.vy.copy())
+        mass = soa.area * soa.h * 920.0
+        st = {k: np.zeros(soa.n) for k in ("alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p", "FxOA", "FyOA", "torqueOA")}
+        st.update(mass=mass.copy(), inertia=mass * soa.rmax ** 2 / 4, c0x=soa.vx.copy(), c0y=soa.vy.copy(), stress_h=np.zeros((soa.n, 2, 4)),
+                  stress_count=np.ones(soa.n, np.int32), stress=np.zeros((soa.n, 2, 2)))
+        ctx.upload(prm, soa)
+        ctx.trajectory_init(st["mass"], st["inertia"], nz=2)
+        ctx.step_resident()
+        ctx.trajectory_step(prm.dt)
+        idx = np.arange(1, soa.n + 1, 2)
+        got = ctx.fracture_deform(idx)
+        ref_step = oracle.OracleStep(prm, ref_soa, broad_mode=1)
+        oracle.calc_trajectory(ref_step, ref_soa, st, prm.dt, nz=2)
+        want = oracle.fracture_deform(ref_step, ref_soa, idx)
+        assert np.array_equal(got["changed"], want["changed"]) and np.array_equal(got["vert_off"], want["vert_off"]) and want["changed"].sum() > 100
+        for k in ("xi", "yi", "area", "cx", "cy"):
+            assert np.abs(got[k] - want[k]).max() <= 1e-9 * np.abs(want[k]).max(), k
         # real floe shapes (7..591 vertices, concave), tiled so that neighbours overlap
         polys, _, modulus = scenarios.floe_shapes()
         rng = np.random.default_rng(3)
