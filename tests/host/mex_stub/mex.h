@@ -5,6 +5,7 @@
 typedef struct mxArray_tag mxArray;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
 extern "C" {
+bool mxIsChar(const mxArray*); int mxGetString(const mxArray*, char*, size_t);
 bool mxIsStruct(const mxArray*); bool mxIsDouble(const mxArray*); bool mxIsComplex(const mxArray*); bool mxIsEmpty(const mxArray*);
 mxArray* mxGetField(const mxArray*, size_t, const char*); size_t mxGetNumberOfElements(const mxArray*);
 double* mxGetPr(const mxArray*); double mxGetScalar(const mxArray*);

@@ -103,9 +103,10 @@ def test_field_generator_shapes():
 def test_mex_gateway_source_compiles_against_the_stub_header():
     """MATLAB is not installed: the gateway (subzero_b200/matlab/sz_contact_mex.cpp, modelled on private/mexclipper.cpp)
     is syntax-checked against a stub mex.h so that it cannot rot"""
-    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "tests", "host", "mex_stub"), "-I" + os.path.join(ROOT, "include"),
-                        os.path.join(ROOT, "subzero_b200", "matlab", "sz_contact_mex.cpp")], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    for src in ("sz_contact_mex.cpp", "sz_resident_mex.cpp"):          # one-shot contact step; device-resident timestep (integrator, ocean forcing, fracture deformation)
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "host", "mex_stub"), "-I" + os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "subzero_b200", "matlab", src)], capture_output=True, text=True)
+        assert r.returncode == 0, src + "\n" + r.stderr
 
 
 def test_standalone_driver_builds_and_fails_loudly_without_a_gpu(tmp_path):
