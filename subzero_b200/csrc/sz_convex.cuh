@@ -55,8 +55,13 @@ template <class T> SZ_HD void wr4(T (&a)[4], int e, T v) { a[e] = v; }
 // in registers (bit id of a mask; the AEL is four packed nibbles).
 template <int NV>
 struct ConvexSweep {
-    // the two open rings in Clipper coordinates, vertex 0 = bottom vertex (largest Y, then smallest X); [0] subject, [1] clip
-    i64 vx[2][NV], vy[2][NV]; int n[2];
+    // the two open rings in Clipper coordinates, vertex 0 = bottom vertex (largest Y, then smallest X); ring p (0 subject,
+    // 1 clip) occupies [p*NV, p*NV + n[p]) of the caller's storage (set_storage: 2*NV values each; the narrow phase lends
+    // the buffers of the InterX points, which are dead until the sweep is over, to keep the touched local memory small)
+    i64* vxs; i64* vys; int n[2];
+    SZ_HD void set_storage(i64* x, i64* y) { vxs = x; vys = y; }
+    SZ_HD i64 vxat(int p, int i) const { return vxs[p * NV + i]; }
+    SZ_HD i64 vyat(int p, int i) const { return vys[p * NV + i]; }
     int sw;                                   // slot q holds ring q ^ sw
     // current edge of every bound (clipper.cpp:66-84 TEdge, reduced like szclip::Edge)
     i64 botx[4], boty[4], topx[4], topy[4], curx[4]; double dx[4]; int vi[4];      // vi: ring index of `top`
@@ -90,12 +95,12 @@ struct ConvexSweep {
     {
         const int p = (e >> 1) ^ sw, nn = n[p], st = bit(f_back, e) ? -1 : 1;
         int to = from + st; if (to >= nn) to -= nn; else if (to < 0) to += nn;
-        const i64 bx = vx[p][from], by = vy[p][from], tx = vx[p][to], ty = vy[p][to];
+        const i64 bx = vxat(p, from), by = vyat(p, from), tx = vxat(p, to), ty = vyat(p, to);
         wr4(botx, e, bx); wr4(boty, e, by); wr4(topx, e, tx); wr4(topy, e, ty); wr4(vi, e, to); wr4(curx, e, bx);
         if (ty >= by) { set_bail(1); return; }                           // horizontal (or not a bound of a convex path)
         wr4(dx, e, fp::div(fp::cvt(tx - bx), fp::cvt(ty - by)));
         int nx = to + st; if (nx >= nn) nx -= nn; else if (nx < 0) nx += nn;
-        const i64 ny = vy[p][nx];
+        const i64 ny = vyat(p, nx);
         if (ny == ty) { set_bail(2); return; }                           // horizontal edge at the top of this one
         if (ny > ty) f_last |= 1u << e; else f_last &= ~(1u << e);
     }
@@ -331,7 +336,7 @@ struct ConvexSweep {
     template <class G> SZ_HD void load_ring(int p, const G& get, int cnt)
     {
         n[p] = cnt;
-        for (int i = 0; i < cnt && i < NV; ++i) { const P64 q = get(i); vx[p][i] = q.x; vy[p][i] = q.y; }
+        for (int i = 0; i < cnt && i < NV; ++i) { const P64 q = get(i); vxs[p * NV + i] = q.x; vys[p * NV + i] = q.y; }
     }
     SZ_HD bool begin(i64* wx, i64* wy, int wcap)
     {
@@ -341,7 +346,7 @@ struct ConvexSweep {
         for (int id = 0; id < 4; ++id) { botx[id] = boty[id] = topx[id] = topy[id] = curx[id] = 0; dx[id] = 0; vi[id] = 0; }
         if (n[0] < 3 || n[1] < 3 || n[0] > NV || n[1] > NV) { set_bail(17); return false; }
         // Reset :1247-1276: minima sorted by Y descending (std::sort of two elements is stable: the subject on a tie)
-        sw = (vy[1][0] > vy[0][0]) ? 1 : 0;
+        sw = (vyat(1, 0) > vyat(0, 0)) ? 1 : 0;
         SZ_UNROLL4
         for (int q = 0; q < 2; ++q) {
             // the two bounds of the path's single local minimum (AddPath :1172-1219): e = forward edge, e.prev = backward

@@ -103,7 +103,10 @@ struct WorkspaceLite {
     i64 rax[C::RV], ray[C::RV]; int ra_off[C::RP + 1]; int ra_n;
     double ar[C::RP];
     i64 rbx[C::RV], rby[C::RV]; int rb_off[C::RP + 1]; int rb_n;
-    double px[C::NP], py[C::NP]; int np;
+    // InterX points; the same bytes hold the int64 outlines of the convex sweep, which is over before InterX runs
+    union { double px[C::NP]; i64 svx[C::NP]; };
+    union { double py[C::NP]; i64 svy[C::NP]; };
+    int np;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -533,7 +536,9 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
     // class C: clip #1 in the four-edge sweep of sz_convex.cuh, one scanbeam per iteration with the lanes kept together
     int fast_clip1 = PS_BAIL;
     if constexpr (FAST) {
+        static_assert(C::NP >= 2 * C::NV, "the InterX buffers must hold both int64 outlines");
         szcvx::ConvexSweep<C::NV> cs;
+        cs.set_storage(w.svx, w.svy);
         bool run = false;
         const bool go = valid && convex_pair && !boundary && hints.no1 >= 3 && hints.no2 >= 3;
         if (go) {

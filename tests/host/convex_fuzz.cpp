@@ -97,6 +97,8 @@ static bool check(const Poly& s_in, const Poly& c_in, int fam, long caseno)
     if (s_in.size() < 3 || c_in.size() < 3 || !szpf::ring_is_strictly_convex(gs0, (int)s_in.size()) || !szpf::ring_is_strictly_convex(gc0, (int)c_in.size())) { ++g_skipped; return true; }
     VecGet gs{&s_in, szpf::ring_bottom_vertex(gs0, (int)s_in.size())}, gc{&c_in, szpf::ring_bottom_vertex(gc0, (int)c_in.size())};
     static szcvx::ConvexSweep<64> sw;
+    static i64 ringx[128], ringy[128];
+    sw.set_storage(ringx, ringy);
     i64 wx[64], wy[64], ox[64], oy[64]; int nout = 0;
     const int st = sw.run(gs, (int)s_in.size(), gc, (int)c_in.size(), wx, wy, 64, ox, oy, 64, nout);
     if (st != szcvx::CV_OK) { ++g_bail; ++fams[fam].bail; ++g_why[sw.why & 31]; return true; }
