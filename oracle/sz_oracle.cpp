@@ -1061,4 +1061,104 @@ int szo_fracture_deform(const SzFloesSoA* f, const int64_t* row_off, const doubl
     return (int)pos;
 }
 
+// calc_eulerian_data.m:1-192: mass-weighted coarse-grid averages of the floe state.  Restated as
+// written, including its quirks: dead floes are dropped first (:7-8); boundary floes (Nb > 0, :11-25) are not supported
+// here (returns -1); for PERIODIC domains an x-ghost is appended for every floe with a vertex beyond +-Lx (:39-48), and
+// the y pass (:56-65) tests the polygon left over from the LAST iteration of the x loop for every floe, so either every
+// floe of the list (x-ghosts included) gets a y-ghost or none does; grid rows run from ymax down (:72 fliplr); a cell is
+// processed when the masses of its candidate floes (centre distance < rmax + cell half-diagonal, :113-119) sum to > 0;
+// Aover = area(intersect(box, poly)) -- here Clipper's intersection + the polyshape area of every returned region,
+// geometrically the same set (MATLAB's own polygon kernel is not in the reference: parity unpinned, ~1e-12 relative);
+// sums run over ascending floe index.  Per-floe inputs: [n]; stress, strain: [n][4] row-major.  Outputs: 18 arrays of
+// Ny*Nx doubles, element (jj, ii) at jj*Nx + ii (jj = 0 is the TOP row), in the order
+//   u v du dv stress stressxx stressyx stressxy stressyy strainux strainvx strainuy strainvy c Over Mtot area h
+int szo_calc_eulerian_data(const SzFloesSoA* f, const double* mass, const double* overlap_area, const double* dUi_p, const double* dVi_p,
+                           const double* stress, const double* strain, int Nx, int Ny, int Nb,
+                           double xmin, double xmax, double ymin, double ymax, int periodic, double* out)
+{
+    if (Nb != 0) return -1;
+    struct F { Curve c; double Xi, Yi, rmax, mass, area, over, U, V, H, dU, dV, S[4], E[4]; };
+    auto nz = [](double v) { return std::isnan(v) ? 0.0 : v; };
+    std::vector<F> fl;
+    for (int i = 0; i < f->n; ++i) {
+        if (!f->alive[i]) continue;                                                // :7-8
+        F g; const int o = f->voff[i], m = f->voff[i + 1] - o;
+        g.c.x.assign(f->vx + o, f->vx + o + m); g.c.y.assign(f->vy + o, f->vy + o + m);
+        g.Xi = f->x[i]; g.Yi = f->y[i]; g.rmax = f->rmax[i]; g.mass = nz(mass[i]); g.area = nz(f->area[i]); g.over = overlap_area[i];
+        g.U = nz(f->u[i]); g.V = nz(f->v[i]); g.H = nz(f->h[i]); g.dU = nz(dUi_p[i]); g.dV = nz(dVi_p[i]);       // :100-111
+        for (int k = 0; k < 4; ++k) { g.S[k] = stress[(size_t)i * 4 + k]; g.E[k] = strain[(size_t)i * 4 + k]; }
+        fl.push_back(g);
+    }
+    const double Lx = xmax, Ly = ymax;                                             // :28-29 max(c2_boundary)
+    auto sgn = [](double a) { return (double)((a > 0) - (a < 0)); };
+    if (periodic && !fl.empty()) {
+        const size_t n1 = fl.size();
+        double last_max_abs_y = 0;
+        for (size_t i = 0; i < n1; ++i) {                                          // :39-48
+            double mx = 0, my = 0;
+            for (size_t t = 0; t < fl[i].c.x.size(); ++t) { mx = std::max(mx, std::fabs(fl[i].c.x[t] + fl[i].Xi)); my = std::max(my, std::fabs(fl[i].c.y[t] + fl[i].Yi)); }
+            last_max_abs_y = my;                                                   // `poly` keeps the last floe's polygon
+            if (mx > Lx) { F g = fl[i]; g.Xi = fl[i].Xi - 2 * Lx * sgn(fl[i].Xi); fl.push_back(g); }
+        }
+        const size_t n2 = fl.size();
+        if (last_max_abs_y > Ly)                                                   // :56-65 the stale-polygon test
+            for (size_t i = 0; i < n2; ++i) { F g = fl[i]; g.Yi = fl[i].Yi - 2 * Ly * sgn(fl[i].Yi); fl.push_back(g); }
+    }
+    // :70-80 grid (colon: a + k*d), rows from the top
+    std::vector<double> xe(Nx + 1), ye(Ny + 1);
+    for (int k = 0; k <= Nx; ++k) xe[k] = xmin + k * ((xmax - xmin) / Nx);
+    for (int k = 0; k <= Ny; ++k) ye[k] = ymin + k * ((ymax - ymin) / Ny);
+    xe[Nx] = xmax; ye[Ny] = ymax;
+    std::reverse(ye.begin(), ye.end());
+    const double dx = std::fabs(xe[1] - xe[0]), dy = std::fabs(ye[1] - ye[0]);
+    const double r_max = std::sqrt((dx / 2) * (dx / 2) + (dy / 2) * (dy / 2));
+    const size_t cells = (size_t)Nx * Ny;
+    for (size_t k = 0; k < 18 * cells; ++k) out[k] = 0;
+    enum { O_U, O_V, O_DU, O_DV, O_STRESS, O_SXX, O_SYX, O_SXY, O_SYY, O_EUX, O_EVX, O_EUY, O_EVY, O_C, O_OVER, O_MTOT, O_AREA, O_H };
+    for (int ii = 0; ii < Nx; ++ii) for (int jj = 0; jj < Ny; ++jj) {
+        const double xc = 0.5 * (xe[ii] + xe[ii + 1]), yc = 0.5 * (ye[jj] + ye[jj + 1]);
+        std::vector<int> live; double M0 = 0;
+        for (size_t q = 0; q < fl.size(); ++q) {
+            const double pint = std::sqrt((xc - fl[q].Xi) * (xc - fl[q].Xi) + (yc - fl[q].Yi) * (yc - fl[q].Yi)) - (fl[q].rmax + r_max);
+            if (pint < 0) { live.push_back((int)q); M0 += fl[q].mass; }
+        }
+        if (!(M0 > 0)) continue;                                                   // :131
+        Curve box; box.x = {xe[ii], xe[ii], xe[ii + 1], xe[ii + 1], xe[ii]}; box.y = {ye[jj], ye[jj + 1], ye[jj + 1], ye[jj], ye[jj]};   // :134
+        const double abox = dx * dy;
+        std::vector<int> nums; std::vector<double> aover;
+        for (int q : live) {
+            Curve c; c.x.resize(fl[q].c.x.size()); c.y.resize(c.x.size());
+            for (size_t t = 0; t < c.x.size(); ++t) { c.x[t] = fl[q].c.x[t] + fl[q].Xi; c.y[t] = fl[q].c.y[t] + fl[q].Yi; }
+            std::vector<Curve> reg;
+            try { polyclip(box, c, 1, reg); } catch (ClipperError&) { return -2; }
+            double a = 0;
+            for (auto& r : reg) { double ar, cx, cy; polyshape_area_centroid(r.x, r.y, ar, cx, cy); a += ar; }
+            if (a != 0) { nums.push_back(q); aover.push_back(a); }                 // :146-147
+        }
+        double Mtot = 0, Atot = 0;
+        for (size_t k = 0; k < nums.size(); ++k) { Mtot += fl[nums[k]].mass * aover[k] / fl[nums[k]].area; Atot += aover[k]; }   // :149-150
+        const size_t e = (size_t)jj * Nx + ii;
+        out[O_C * cells + e] = Atot / abox;                                        // :151
+        if (!(Mtot > 0)) continue;
+        auto wsum = [&](auto get) { double s2 = 0; for (size_t k = 0; k < nums.size(); ++k) s2 += get(fl[nums[k]]) * fl[nums[k]].mass * aover[k] / fl[nums[k]].area; return s2 / Mtot; };
+        double so = 0; for (int q : nums) so += fl[q].over;
+        out[O_OVER * cells + e] = so / (double)aover.size();                       // :153
+        out[O_MTOT * cells + e] = Mtot; out[O_AREA * cells + e] = Atot;
+        out[O_H * cells + e] = wsum([](const F& g) { return g.H; });
+        out[O_U * cells + e] = wsum([](const F& g) { return g.U; }); out[O_V * cells + e] = wsum([](const F& g) { return g.V; });
+        out[O_DU * cells + e] = wsum([](const F& g) { return g.dU; }); out[O_DV * cells + e] = wsum([](const F& g) { return g.dV; });
+        const double sxx = wsum([](const F& g) { return g.S[0]; }), syx = wsum([](const F& g) { return g.S[1]; });   // Stress(1,1), Stress(1,2)
+        const double sxy = wsum([](const F& g) { return g.S[2]; }), syy = wsum([](const F& g) { return g.S[3]; });   // Stress(2,1), Stress(2,2)
+        out[O_SXX * cells + e] = sxx; out[O_SYX * cells + e] = syx; out[O_SXY * cells + e] = sxy; out[O_SYY * cells + e] = syy;
+        out[O_EUX * cells + e] = wsum([](const F& g) { return g.E[0]; }); out[O_EVX * cells + e] = wsum([](const F& g) { return g.E[1]; });
+        out[O_EUY * cells + e] = wsum([](const F& g) { return g.E[2]; }); out[O_EVY * cells + e] = wsum([](const F& g) { return g.E[3]; });
+        // max(eig([sxx syx; sxy syy])) (:170); the stress tensor is symmetric, its eigenvalues real
+        const double tr = sxx + syy, det = sxx * syy - syx * sxy, disc = tr * tr / 4 - det;
+        double lam = tr / 2 + std::sqrt(disc > 0 ? disc : 0);
+        if (std::fabs(lam) > 1e8) lam = 0;                                         // :171-173
+        out[O_STRESS * cells + e] = lam;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -50,6 +50,9 @@ void szo_floe_strain(int n, const uint8_t* alive, const uint8_t* sacked, const d
                      const int32_t* voff, const double* cax, const double* cay, double* strain);
 int  szo_fracture_deform(const SzFloesSoA* f, const int64_t* row_off, const double* rows, int count, const int32_t* idx,
                          uint8_t* changed, double* xi, double* yi, double* area, int64_t* vert_off, double* cx, double* cy, int64_t vcap);
+int  szo_calc_eulerian_data(const SzFloesSoA* f, const double* mass, const double* overlap_area, const double* dUi_p, const double* dVi_p,
+                            const double* stress, const double* strain, int Nx, int Ny, int Nb,
+                            double xmin, double xmax, double ymin, double ymax, int periodic, double* out);
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ def lib():
         l.szo_floe_strain.argtypes = [C.c_int, abi.c_bp, abi.c_bp] + [abi.c_dp] * 4 + [abi.c_ip, abi.c_dp, abi.c_dp, abi.c_dp]
         l.szo_fracture_deform.restype = C.c_int
         l.szo_fracture_deform.argtypes = [C.POINTER(abi.SzFloesSoA), abi.c_lp, abi.c_dp, C.c_int, abi.c_ip, abi.c_bp, abi.c_dp, abi.c_dp, abi.c_dp, abi.c_lp, abi.c_dp, abi.c_dp, C.c_int64]
+        l.szo_calc_eulerian_data.restype = C.c_int
+        l.szo_calc_eulerian_data.argtypes = [C.POINTER(abi.SzFloesSoA)] + [abi.c_dp] * 6 + [C.c_int] * 3 + [C.c_double] * 4 + [C.c_int, abi.c_dp]
         _lib = l
     return _lib
 
@@ -232,6 +234,26 @@ def fracture_deform(step, floes, idx):
     assert r >= 0 and r <= cap, r
     o["cx"], o["cy"] = cx[:r].copy(), cy[:r].copy()
     return o
+
+
+EULERIAN_FIELDS = ("u", "v", "du", "dv", "stress", "stressxx", "stressyx", "stressxy", "stressyy", "strainux", "strainvx", "strainuy", "strainvy",
+                   "c", "Over", "Mtot", "area", "h")
+
+
+def calc_eulerian_data(floes, mass, Nx, Ny, box, periodic, overlap_area=None, dUi_p=None, dVi_p=None, stress=None, strain=None, Nb=0):
+    """the oracle's restatement of calc_eulerian_data.m; box = (xmin, xmax, ymin, ymax) of c2_boundary.  Returns a dict of
+    (Ny, Nx) arrays, row 0 = the top row (the reference flips y)."""
+    n = floes.n
+    z = lambda a, shape: np.zeros(shape) if a is None else np.ascontiguousarray(a, np.float64)
+    ov, du, dv, st, en = z(overlap_area, n), z(dUi_p, n), z(dVi_p, n), z(stress, (n, 4)), z(strain, (n, 4))
+    mass = np.ascontiguousarray(mass, np.float64)
+    out = np.zeros((18, Ny, Nx))
+    view = floes.struct()
+    p, D = abi._ptr, abi.c_dp
+    r = lib().szo_calc_eulerian_data(C.byref(view), p(mass, D), p(ov, D), p(du, D), p(dv, D), p(st, D), p(en, D), int(Nx), int(Ny), int(Nb),
+                                     *(float(b) for b in box), int(bool(periodic)), p(out, D))
+    assert r == 0, r
+    return {k: out[i] for i, k in enumerate(EULERIAN_FIELDS)}
 
 
 def _rel_err(a, b):
