@@ -226,8 +226,9 @@ int sz_get_trajectory(SzContext* ctx, double* x, double* y, double* u, double* v
  *                              do_int != 0 (doInt.flag), else only those thinner than 0.1 m after this step's thinning (:94)
  *                              -- and makes the next sz_trajectory_step compute floe.strain when do_int != 0.  A floe
  *                              with no point inside its outline would get new random points in the reference (:100-111):
- *                              it is counted in n_no_points, flagged (bit 2) and keeps its forcing; the call then
- *                              returns SZ_ERR_STATE after finishing the others.
+ *                              it is counted in n_no_points, flagged (bit 2 of sz_get_trajectory's flags, readable until
+ *                              the next sz_trajectory_step) and keeps its forcing; the call then returns SZ_ERR_STATE
+ *                              after finishing the others.
  *   sz_get_trajectory_forcing  FxOA FyOA torqueOA [n0], strain [n0][2][2] (row-major); any pointer may be NULL */
 typedef struct SzOcean {
     int32_t nx, ny;
