@@ -43,14 +43,16 @@ int main(int argc, char** argv)
         if (sz_step_resident(ctx, &s) != SZ_OK) return 7;
     }
     float ph[5]; sz_get_phase_ms(ctx, ph);
+    float cls[5]; int32_t cls_pairs[5]; sz_get_narrow_class_ms(ctx, cls, cls_pairs);      // narrow-phase kernel time per size class
     std::vector<double> fx(n), fy(n);
     sz_get_floe_outputs(ctx, fx.data(), fy.data(), 0, 0, 0, 0, 0, 0, 0, 0);
     double sx = 0, sy = 0; for (int i = 0; i < n; ++i) { sx += fx[i]; sy += fy[i]; }
     printf("{\"floes\": %d, \"floes_incl_ghosts\": %d, \"pairs\": %lld, \"pairs_with_force\": %lld, \"rows\": %lld, \"ms_per_step\": %.4f, "
            "\"pairs_per_s\": %.4e, \"timesteps_per_s\": %.3f, \"phase_ms\": {\"ghosts\": %.3f, \"broad\": %.3f, \"narrow\": %.3f, \"assembly\": %.3f}, "
+           "\"narrow_class_C\": {\"ms\": %.3f, \"pairs\": %d}, \"narrow_class_S\": {\"ms\": %.3f, \"pairs\": %d}, "
            "\"timesteps_per_s_moving\": %.3f, \"sum_fx\": %.6e, \"sum_fy\": %.6e, \"kernels_launched\": %lld}\n",
            s.n0, s.n, (long long)s.n_pairs, (long long)s.n_pairs_force, (long long)s.n_rows, ms, s.n_pairs / (ms * 1e-3), 1e3 / ms,
-           ph[0], ph[1], ph[2], ph[3], ts_ab2, sx, sy, sz_launch_count());
+           ph[0], ph[1], ph[2], ph[3], cls[0], cls_pairs[0], cls[1], cls_pairs[1], ts_ab2, sx, sy, sz_launch_count());
     sz_destroy(ctx); sz_field_free(field);
     return 0;
 }
