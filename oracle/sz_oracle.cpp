@@ -1161,4 +1161,77 @@ int szo_calc_eulerian_data(const SzFloesSoA* f, const double* mass, const double
     return 0;
 }
 
+// Physical_Processes/corners.m:10-99, the deterministic half of the corner-grinding rule: which
+// vertices of a floe are "in contact" (da).  The other half, break1 = rand > angle/Anorm (:72), and frac_corner stay with
+// the host.  As written: the floe list Floe0 is extended with periodic images whether or not the run is periodic
+// (:13-48: x images of floes with a vertex beyond +-Lx, then y images over the extended list); N0 = its length (:51);
+// for every selected floe (idx, 1-based positions in the list; the reference skips the first Nb of the SELECTION, :54)
+// with contact rows: the vertex nearest to each contact point whose partner number is <= N0 (dsearchn, :74), every
+// vertex inside the outline of a partner (inpolygon counts the boundary, :78-82; partners are looked up in the extended
+// list rebuilt from the CURRENT positions), and, when the floe touches the wall (an Inf partner), every vertex outside
+// c2_boundary (:83-86).  Vertices are those of polyshape(c_alpha'): taken here as c_alpha without its closing duplicate,
+// in the stored order (polyshape keeps the order of a clockwise simple outline; it would also drop exactly collinear
+// vertices, which these outlines do not have -- parity with polyshape's clean-up unpinned).
+// Output: da for the vertices of selected floe q at da[da_off[q] .. da_off[q+1]); returns the total, or -1 if vcap is too small.
+int szo_corner_eligibility(const SzFloesSoA* f, const int64_t* row_off, const double* rows, int count, const int32_t* idx, int Nb,
+                           double Lx, double Ly, const double* boxx, const double* boxy, int nbox,
+                           int64_t* da_off, uint8_t* da, int64_t vcap)
+{
+    struct G { int src; double Xi, Yi; };
+    auto sgn = [](double a) { return (double)((a > 0) - (a < 0)); };
+    auto max_abs = [&](int src, double X, double Y, bool ycoord) {
+        double m = 0;
+        for (int t = f->voff[src]; t < f->voff[src + 1]; ++t) m = std::max(m, std::fabs(ycoord ? f->vy[t] + Y : f->vx[t] + X));
+        return m;
+    };
+    std::vector<G> ext;
+    for (int i = 0; i < f->n; ++i) ext.push_back({i, f->x[i], f->y[i]});
+    for (int i = 0; i < f->n; ++i)
+        if (f->alive[i] && max_abs(i, f->x[i], f->y[i], false) > Lx) ext.push_back({i, f->x[i] - 2 * Lx * sgn(f->x[i]), f->y[i]});            // :21-30
+    const size_t n1 = ext.size();
+    for (size_t i = 0; i < n1; ++i)
+        if (f->alive[ext[i].src] && max_abs(ext[i].src, ext[i].Xi, ext[i].Yi, true) > Ly) ext.push_back({ext[i].src, ext[i].Xi, ext[i].Yi - 2 * Ly * sgn(ext[i].Yi)});   // :38-46
+    const double N0 = (double)ext.size();
+    int64_t pos = 0; da_off[0] = 0;
+    for (int q = 0; q < count; ++q) {
+        const int i = idx[q] - 1;
+        int nv = f->voff[i + 1] - f->voff[i];
+        const int o = f->voff[i];
+        if (nv > 1 && f->vx[o] == f->vx[o + nv - 1] && f->vy[o] == f->vy[o + nv - 1]) --nv;                                                  // polyshape drops the closing vertex
+        if (pos + nv > vcap) return -1;
+        for (int t = 0; t < nv; ++t) da[pos + t] = 0;
+        da_off[q + 1] = pos + nv;
+        if (q + 1 < 1 + Nb || row_off[i + 1] == row_off[i]) { pos += nv; continue; }                                                          // :54-55
+        vec vxw(nv), vyw(nv);
+        for (int t = 0; t < nv; ++t) { vxw[t] = f->vx[o + t] + f->x[i]; vyw[t] = f->vy[o + t] + f->y[i]; }
+        std::vector<int> in(nv, 0);
+        bool bnd = false;
+        for (int64_t r = row_off[i]; r < row_off[i + 1]; ++r) {
+            const double* a = rows + r * 7;
+            if (std::isinf(a[0])) { bnd = true; continue; }
+            if (!(a[0] <= N0)) continue;
+            // break2 = dsearchn(polytrue.Vertices, [Xi Yi]) (:74): first nearest vertex
+            int best = 0; double bd = INF;
+            for (int t = 0; t < nv; ++t) { const double d = (vxw[t] - a[3]) * (vxw[t] - a[3]) + (vyw[t] - a[4]) * (vyw[t] - a[4]); if (d < bd) { bd = d; best = t; } }
+            da[pos + best] = 1;
+            // inpolygon of the floe's vertices in the partner's outline (:78-82)
+            const G& g = ext[(size_t)a[0] - 1];
+            vec cx, cy;
+            for (int t = f->voff[g.src]; t < f->voff[g.src + 1]; ++t) { cx.push_back(f->vx[t] + g.Xi); cy.push_back(f->vy[t] + g.Yi); }
+            std::vector<char> inn;
+            inpolygon(vxw, vyw, cx, cy, inn);
+            for (int t = 0; t < nv; ++t) in[t] += inn[t] ? 1 : 0;
+        }
+        if (bnd) {                                                                                                                            // :83-86
+            vec bx(boxx, boxx + nbox), by(boxy, boxy + nbox);
+            std::vector<char> inn;
+            inpolygon(vxw, vyw, bx, by, inn);
+            for (int t = 0; t < nv; ++t) in[t] += inn[t] ? 0 : 1;
+        }
+        for (int t = 0; t < nv; ++t) if (in[t] > 0) da[pos + t] = 1;                                                                          // :87
+        pos += nv;
+    }
+    return (int)pos;
+}
+
 }  // extern "C"

@@ -53,6 +53,9 @@ int  szo_fracture_deform(const SzFloesSoA* f, const int64_t* row_off, const doub
 int  szo_calc_eulerian_data(const SzFloesSoA* f, const double* mass, const double* overlap_area, const double* dUi_p, const double* dVi_p,
                             const double* stress, const double* strain, int Nx, int Ny, int Nb,
                             double xmin, double xmax, double ymin, double ymax, int periodic, double* out);
+int  szo_corner_eligibility(const SzFloesSoA* f, const int64_t* row_off, const double* rows, int count, const int32_t* idx, int Nb,
+                            double Lx, double Ly, const double* boxx, const double* boxy, int nbox,
+                            int64_t* da_off, uint8_t* da, int64_t vcap);
 #ifdef __cplusplus
 }
 #endif

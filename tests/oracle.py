@@ -71,6 +71,9 @@ def lib():
         l.szo_fracture_deform.argtypes = [C.POINTER(abi.SzFloesSoA), abi.c_lp, abi.c_dp, C.c_int, abi.c_ip, abi.c_bp, abi.c_dp, abi.c_dp, abi.c_dp, abi.c_lp, abi.c_dp, abi.c_dp, C.c_int64]
         l.szo_calc_eulerian_data.restype = C.c_int
         l.szo_calc_eulerian_data.argtypes = [C.POINTER(abi.SzFloesSoA)] + [abi.c_dp] * 6 + [C.c_int] * 3 + [C.c_double] * 4 + [C.c_int, abi.c_dp]
+        l.szo_corner_eligibility.restype = C.c_int
+        l.szo_corner_eligibility.argtypes = [C.POINTER(abi.SzFloesSoA), abi.c_lp, abi.c_dp, C.c_int, abi.c_ip, C.c_int, C.c_double, C.c_double, abi.c_dp, abi.c_dp, C.c_int,
+                                             abi.c_lp, abi.c_bp, C.c_int64]
         _lib = l
     return _lib
 
@@ -234,6 +237,23 @@ def fracture_deform(step, floes, idx):
     assert r >= 0 and r <= cap, r
     o["cx"], o["cy"] = cx[:r].copy(), cy[:r].copy()
     return o
+
+
+def corner_eligibility(step, floes, idx, Lx, Ly, c2_boundary, Nb=0):
+    """the oracle's restatement of the deterministic half of corners.m (the mask `da`); returns a list of uint8 arrays, one
+    per selected floe (vertices of c_alpha without the closing duplicate)"""
+    off, rows = step.rows()
+    off = np.ascontiguousarray(off, np.int64); rows = np.ascontiguousarray(rows)
+    idx = np.ascontiguousarray(idx, np.int32)
+    bx, by = np.ascontiguousarray(c2_boundary[0], np.float64), np.ascontiguousarray(c2_boundary[1], np.float64)
+    cap = int(floes.vx.shape[0]) + 8
+    da_off, da = np.zeros(idx.shape[0] + 1, np.int64), np.zeros(cap, np.uint8)
+    view = floes.struct()
+    p = abi._ptr
+    r = lib().szo_corner_eligibility(C.byref(view), p(off, abi.c_lp), p(rows, abi.c_dp), idx.shape[0], p(idx, abi.c_ip), int(Nb), float(Lx), float(Ly),
+                                     p(bx, abi.c_dp), p(by, abi.c_dp), bx.shape[0], p(da_off, abi.c_lp), p(da, abi.c_bp), cap)
+    assert r >= 0, r
+    return [da[da_off[k]:da_off[k + 1]].copy() for k in range(idx.shape[0])]
 
 
 EULERIAN_FIELDS = ("u", "v", "du", "dv", "stress", "stressxx", "stressyx", "stressxy", "stressyy", "strainux", "strainvx", "strainuy", "strainvy",

@@ -111,3 +111,34 @@ def test_device_fracture_deform_matches_oracle():
         prm = sz.default_params(Lx=2e5, Ly=2e5, modulus=modulus, dt=10.0, periodic=1, collision=1)
         w = check_device_against_oracle(ctx, prm, soa, np.arange(1, soa.n + 1))
         assert w["changed"].sum() > 0
+
+
+def test_oracle_corner_eligibility_known_answers():
+    """corners.m:54-88, the deterministic mask `da`: the vertex nearest to each contact point (first of equals) and the
+    vertices lying in (or on) a partner's outline; against the wall, the vertices outside c2_boundary"""
+    prm, soa = two_squares(1900.0)                       # overlap strip x in [900, 1000]; contact point (950, 0)
+    c2, _ = scenarios.domain(1e5, 1e5)
+    step = oracle.OracleStep(prm, soa)
+    da = oracle.corner_eligibility(step, soa, [1, 2], prm.Lx, prm.Ly, c2)
+    # floe 1: vertices (-1000,-1000) (-1000,1000) (1000,1000) (1000,-1000): the two on x = 1000 lie on the partner's outline
+    assert list(da[0]) == [0, 0, 1, 1]
+    # floe 2: vertices (900,-1000) (900,1000) (2900,1000) (2900,-1000): the two on x = 900 are inside floe 1
+    assert list(da[1]) == [1, 1, 0, 0]
+    # no contact: nothing is eligible; the first Nb floes of the selection are skipped
+    prm, soa = two_squares(2500.0)
+    assert all(d.sum() == 0 for d in oracle.corner_eligibility(oracle.OracleStep(prm, soa), soa, [1, 2], prm.Lx, prm.Ly, c2))
+    prm, soa = two_squares(1900.0)
+    da = oracle.corner_eligibility(oracle.OracleStep(prm, soa), soa, [1, 2], prm.Lx, prm.Ly, c2, Nb=1)
+    assert da[0].sum() == 0 and list(da[1]) == [1, 1, 0, 0]
+    # a floe across the east wall of a non-periodic domain: wall rows (partner Inf) flag the vertices outside c2_boundary
+    L = 5000.0
+    c2, fb = scenarios.domain(L, L)
+    sq = np.array([[-1000.0, -1000.0], [-1000.0, 1000.0], [1000.0, 1000.0], [1000.0, -1000.0]]) + [L - 200.0, 0.0]
+    soa = sz.floes_to_soa([scenarios.floe_from_polygon(sq)])
+    prm = sz.default_params(Lx=L, Ly=L, modulus=1e7, dt=10.0, periodic=0, collision=1)
+    bnd = sz.Boundary(fb["c"][0], fb["c"][1], c2[0], c2[1], fb["area"], fb["h"])
+    step = oracle.OracleStep(prm, soa, bnd)
+    off, rows = step.rows()
+    assert off[1] > 0 and np.isinf(rows[0, 0])
+    da = oracle.corner_eligibility(step, soa, [1], L, L, c2)
+    assert list(da[0]) == [0, 0, 1, 1]                   # the two vertices at x = L + 800
