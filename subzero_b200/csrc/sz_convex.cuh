@@ -50,18 +50,22 @@ template <class T> SZ_HD void wr4(T (&a)[4], int e, T v) { a[e] = v; }
 #define SZ_UNROLL4
 #endif
 
+// The sweep's two pieces of bulk storage, lent by the caller: the int64 outlines (ring p at [p*NV, p*NV + n[p]) of vxs/vys)
+// and the output record's deque (dqx/dqy, dcap entries).  It is handed down the (inlined) call chain by reference instead of
+// living in the sweep object: pointers read back from a struct in local memory lose their address space and every access
+// through them becomes a generic LD/ST instead of LDL/STL.
+struct SweepMem { i64* vxs; i64* vys; i64* dqx; i64* dqy; int dcap; };
+
 // Edge ids: 2*slot + {0 left bound, 1 right bound}; slot 0 is the path whose local minimum is popped first (larger
 // bottom Y; the subject on a tie, like the stable sort of Reset :1251), slot 1 the other one.  Flags and orders live
 // in registers (bit id of a mask; the AEL is four packed nibbles).
 template <int NV>
 struct ConvexSweep {
-    // the two open rings in Clipper coordinates, vertex 0 = bottom vertex (largest Y, then smallest X); ring p (0 subject,
-    // 1 clip) occupies [p*NV, p*NV + n[p]) of the caller's storage (set_storage: 2*NV values each; the narrow phase lends
-    // the buffers of the InterX points, which are dead until the sweep is over, to keep the touched local memory small)
-    i64* vxs; i64* vys; int n[2];
-    SZ_HD void set_storage(i64* x, i64* y) { vxs = x; vys = y; }
-    SZ_HD i64 vxat(int p, int i) const { return vxs[p * NV + i]; }
-    SZ_HD i64 vyat(int p, int i) const { return vys[p * NV + i]; }
+    // the two open rings in Clipper coordinates (SweepMem), vertex 0 = bottom vertex (largest Y, then smallest X); [0] subject, [1] clip
+    int n[2];
+    typedef const SweepMem& M;
+    SZ_HD static i64 vxat(M m, int p, int i) { return m.vxs[p * NV + i]; }
+    SZ_HD static i64 vyat(M m, int p, int i) { return m.vys[p * NV + i]; }
     int sw;                                   // slot q holds ring q ^ sw
     // current edge of every bound (clipper.cpp:66-84 TEdge, reduced like szclip::Edge)
     i64 botx[4], boty[4], topx[4], topy[4], curx[4]; double dx[4]; int vi[4];      // vi: ring index of `top`
@@ -72,7 +76,7 @@ struct ConvexSweep {
     i64 lm_y[2]; int cur_lm;                  // the two local minima (slot order = Y descending)
     INode il[6]; int n_il;
     // output record: deque d[lo..hi], front = d[lo] (OutRec.Pts), back = d[hi] (Pts->Prev); both ends cached
-    i64* dqx; i64* dqy; int dcap, lo, hi, n_or; P64 fr, bk;
+    int lo, hi, n_or; P64 fr, bk;
     bool bail; int why;
     SZ_HD void set_bail(int r) { if (!bail) { bail = true; why = r; } }
 
@@ -91,16 +95,16 @@ struct ConvexSweep {
     }
     SZ_HD i64 top_x(int e, i64 y) const { return top_x_of(rd4(botx, e), rd4(boty, e), rd4(topx, e), rd4(topy, e), rd4(dx, e), y); }
     // the edge of bound `e` that follows vertex `from` (ring index) -- SetDx :591-596, InitEdge2 :729-742
-    SZ_HD void load_edge(int e, int from)
+    SZ_HD void load_edge(M m, int e, int from)
     {
         const int p = (e >> 1) ^ sw, nn = n[p], st = bit(f_back, e) ? -1 : 1;
         int to = from + st; if (to >= nn) to -= nn; else if (to < 0) to += nn;
-        const i64 bx = vxat(p, from), by = vyat(p, from), tx = vxat(p, to), ty = vyat(p, to);
+        const i64 bx = vxat(m, p, from), by = vyat(m, p, from), tx = vxat(m, p, to), ty = vyat(m, p, to);
         wr4(botx, e, bx); wr4(boty, e, by); wr4(topx, e, tx); wr4(topy, e, ty); wr4(vi, e, to); wr4(curx, e, bx);
         if (ty >= by) { set_bail(1); return; }                           // horizontal (or not a bound of a convex path)
         wr4(dx, e, fp::div(fp::cvt(tx - bx), fp::cvt(ty - by)));
         int nx = to + st; if (nx >= nn) nx -= nn; else if (nx < 0) nx += nn;
-        const i64 ny = vyat(p, nx);
+        const i64 ny = vyat(m, p, nx);
         if (ny == ty) { set_bail(2); return; }                           // horizontal edge at the top of this one
         if (ny > ty) f_last |= 1u << e; else f_last &= ~(1u << e);
     }
@@ -152,33 +156,33 @@ struct ConvexSweep {
     }
 
     // ---- output record
-    SZ_HD void add_out_pt(int e, P64 pt)   // :2463-2499
+    SZ_HD void add_out_pt(M m, int e, P64 pt)   // :2463-2499
     {
         if (!bit(f_out, e)) {
             if (n_or != 0) { set_bail(3); return; }       // a second OutRec: outside the model
-            n_or = 1; lo = hi = dcap / 2; dqx[lo] = pt.x; dqy[lo] = pt.y; fr = pt; bk = pt;
+            n_or = 1; lo = hi = m.dcap / 2; m.dqx[lo] = pt.x; m.dqy[lo] = pt.y; fr = pt; bk = pt;
             f_out |= 1u << e;                             // SetHoleState :2301-2324: no other output yet -> not a hole
             return;
         }
         if (!bit(f_right, e)) {
             if (pt == fr) return;
             if (lo == 0) { set_bail(4); return; }
-            --lo; dqx[lo] = pt.x; dqy[lo] = pt.y; fr = pt;
+            --lo; m.dqx[lo] = pt.x; m.dqy[lo] = pt.y; fr = pt;
         } else {
             if (pt == bk) return;
-            if (hi + 1 >= dcap) { set_bail(5); return; }
-            ++hi; dqx[hi] = pt.x; dqy[hi] = pt.y; bk = pt;
+            if (hi + 1 >= m.dcap) { set_bail(5); return; }
+            ++hi; m.dqx[hi] = pt.x; m.dqy[hi] = pt.y; bk = pt;
         }
     }
     SZ_HD void set_flag(unsigned& m, int e, bool v) { m = (m & ~(1u << e)) | ((v ? 1u : 0u) << e); }
-    SZ_HD void add_local_min_poly(int e1, int e2, P64 pt)   // :1841-1881 (the join test needs an existing OutRec: unreachable)
+    SZ_HD void add_local_min_poly(M m, int e1, int e2, P64 pt)   // :1841-1881 (the join test needs an existing OutRec: unreachable)
     {
-        if (rd4(dx, e1) > rd4(dx, e2)) { add_out_pt(e1, pt); set_flag(f_out, e2, bit(f_out, e1)); set_flag(f_right, e1, false); set_flag(f_right, e2, true); }
-        else { add_out_pt(e2, pt); set_flag(f_out, e1, bit(f_out, e2)); set_flag(f_right, e1, true); set_flag(f_right, e2, false); }
+        if (rd4(dx, e1) > rd4(dx, e2)) { add_out_pt(m, e1, pt); set_flag(f_out, e2, bit(f_out, e1)); set_flag(f_right, e1, false); set_flag(f_right, e2, true); }
+        else { add_out_pt(m, e2, pt); set_flag(f_out, e1, bit(f_out, e2)); set_flag(f_right, e1, true); set_flag(f_right, e2, false); }
     }
-    SZ_HD void add_local_max_poly(int e1, int e2, P64 pt)   // :1884-1897 (one OutRec: the indices are equal)
+    SZ_HD void add_local_max_poly(M m, int e1, int e2, P64 pt)   // :1884-1897 (one OutRec: the indices are equal)
     {
-        add_out_pt(e1, pt);
+        add_out_pt(m, e1, pt);
         f_out &= ~((1u << e1) | (1u << e2));
     }
     SZ_HD void swap_sides_idx(int e1, int e2)
@@ -186,24 +190,24 @@ struct ConvexSweep {
         const bool s1 = bit(f_right, e1), s2 = bit(f_right, e2), o1 = bit(f_out, e1), o2 = bit(f_out, e2);
         set_flag(f_right, e1, s2); set_flag(f_right, e2, s1); set_flag(f_out, e1, o2); set_flag(f_out, e2, o1);
     }
-    SZ_HD void intersect_edges(int e1, int e2, P64 pt)   // :2106-2298, closed even-odd paths, ctIntersection
+    SZ_HD void intersect_edges(M m, int e1, int e2, P64 pt)   // :2106-2298, closed even-odd paths, ctIntersection
     {
         const bool c1 = bit(f_out, e1), c2 = bit(f_out, e2);
         const bool same = (e1 >> 1) == (e2 >> 1);
         if (!same) f_wc2 ^= (1u << e1) | (1u << e2);
         if (c1 && c2) {
-            if (!same) add_local_max_poly(e1, e2, pt);
-            else { add_out_pt(e1, pt); add_out_pt(e2, pt); swap_sides_idx(e1, e2); }
-        } else if (c1) { add_out_pt(e1, pt); swap_sides_idx(e1, e2); }
-        else if (c2) { add_out_pt(e2, pt); swap_sides_idx(e1, e2); }
+            if (!same) add_local_max_poly(m, e1, e2, pt);
+            else { add_out_pt(m, e1, pt); add_out_pt(m, e2, pt); swap_sides_idx(e1, e2); }
+        } else if (c1) { add_out_pt(m, e1, pt); swap_sides_idx(e1, e2); }
+        else if (c2) { add_out_pt(m, e2, pt); swap_sides_idx(e1, e2); }
         else {
-            if (!same) add_local_min_poly(e1, e2, pt);
-            else if (bit(f_wc2, e1) && bit(f_wc2, e2)) add_local_min_poly(e1, e2, pt);
+            if (!same) add_local_min_poly(m, e1, e2, pt);
+            else if (bit(f_wc2, e1) && bit(f_wc2, e2)) add_local_min_poly(m, e1, e2, pt);
         }
     }
 
     // ---- InsertLocalMinimaIntoAEL :1978-2077
-    SZ_HD void insert_local_minima(i64 bot_y)
+    SZ_HD void insert_local_minima(M m, i64 bot_y)
     {
         while (cur_lm < 2 && lm_y[cur_lm] == bot_y && !bail) {
             const int p = cur_lm++;
@@ -219,7 +223,7 @@ struct ConvexSweep {
                 if (((k - 1 - q) & 1) != 0) w = !w;
                 set_flag(f_wc2, lb, w); set_flag(f_wc2, rb, w);
             }
-            if (bit(f_wc2, lb)) add_local_min_poly(lb, rb, bot(lb));
+            if (bit(f_wc2, lb)) add_local_min_poly(m, lb, rb, bot(lb));
             if (bail) return;
             const int pl = pael(lb);
             if (bit(f_out, lb) && pl != NILE) {
@@ -265,7 +269,7 @@ struct ConvexSweep {
     }
     // ---- ProcessIntersections :2827-2845 when some neighbours change places in this scanbeam.
     // gt: bit (4a + b) set when Curr.X of edge a > Curr.X of edge b at the top of the scanbeam.
-    SZ_HD void intersections(i64 top_y, unsigned gt)
+    SZ_HD void intersections(M m, i64 top_y, unsigned gt)
     {
         unsigned sel = ordp; int ns = na;
         n_il = 0;
@@ -307,13 +311,13 @@ struct ConvexSweep {
             }
         }
         for (int i = 0; i < n_il && !bail; ++i) {          // ProcessIntersectList :2906-2918
-            intersect_edges(il[i].e1, il[i].e2, il[i].pt);
+            intersect_edges(m, il[i].e1, il[i].e2, il[i].pt);
             swap_in_ael(il[i].e1, il[i].e2);
         }
         n_il = 0;
     }
 
-    SZ_HD void do_maxima(int e)   // :2957-3006
+    SZ_HD void do_maxima(M m, int e)   // :2957-3006
     {
         const int mp = e ^ 1;
         // GetMaximaPairEx :2548-2555: the other bound of the path ends at the same top vertex and is active
@@ -321,39 +325,39 @@ struct ConvexSweep {
         if (!(bit(act, mp) && bit(f_last, mp) && tm == te)) { set_bail(10); return; }
         int en = nael(e);
         while (en != NILE && en != mp && !bail) {
-            intersect_edges(e, en, te);
+            intersect_edges(m, e, en, te);
             swap_in_ael(e, en);
             en = nael(e);
         }
         if (bail) return;
         if (!bit(f_out, e) && !bit(f_out, mp)) { delete_from_ael(e); delete_from_ael(mp); }
-        else if (bit(f_out, e) && bit(f_out, mp)) { add_local_max_poly(e, mp, te); delete_from_ael(e); delete_from_ael(mp); }
+        else if (bit(f_out, e) && bit(f_out, mp)) { add_local_max_poly(m, e, mp, te); delete_from_ael(e); delete_from_ael(mp); }
         else set_bail(11);      // "DoMaxima error": let the general sweep report it
     }
 
     // ---- stepwise interface (the caller keeps the lanes of a warp / CTA together between scanbeams)
     // before begin(): fill vx/vy/n (load_ring).  (wx, wy)[0, wcap) is scratch for the output record.
-    template <class G> SZ_HD void load_ring(int p, const G& get, int cnt)
+    template <class G> SZ_HD void load_ring(M m, int p, const G& get, int cnt)
     {
         n[p] = cnt;
-        for (int i = 0; i < cnt && i < NV; ++i) { const P64 q = get(i); vxs[p * NV + i] = q.x; vys[p * NV + i] = q.y; }
+        for (int i = 0; i < cnt && i < NV; ++i) { const P64 q = get(i); m.vxs[p * NV + i] = q.x; m.vys[p * NV + i] = q.y; }
     }
-    SZ_HD bool begin(i64* wx, i64* wy, int wcap)
+    SZ_HD bool begin(M m)
     {
-        dqx = wx; dqy = wy; dcap = wcap; lo = hi = 0; n_or = 0; na = 0; n_il = 0; bail = false; why = 0; cur_lm = 0;
+        lo = hi = 0; n_or = 0; na = 0; n_il = 0; bail = false; why = 0; cur_lm = 0;
         ordp = 0; act = f_right = f_out = f_wc2 = f_last = f_back = 0; cur_y = 0; fr.x = fr.y = bk.x = bk.y = 0; sw = 0;
         SZ_UNROLL4
         for (int id = 0; id < 4; ++id) { botx[id] = boty[id] = topx[id] = topy[id] = curx[id] = 0; dx[id] = 0; vi[id] = 0; }
         if (n[0] < 3 || n[1] < 3 || n[0] > NV || n[1] > NV) { set_bail(17); return false; }
         // Reset :1247-1276: minima sorted by Y descending (std::sort of two elements is stable: the subject on a tie)
-        sw = (vyat(1, 0) > vyat(0, 0)) ? 1 : 0;
+        sw = (vyat(m, 1, 0) > vyat(m, 0, 0)) ? 1 : 0;
         SZ_UNROLL4
         for (int q = 0; q < 2; ++q) {
             // the two bounds of the path's single local minimum (AddPath :1172-1219): e = forward edge, e.prev = backward
             // edge; the left bound is the one with the larger Dx (:1192-1203)
             const int l = 2 * q, r = 2 * q + 1;
             f_back |= 1u << r;
-            load_edge(l, 0); load_edge(r, 0);
+            load_edge(m, l, 0); load_edge(m, r, 0);
             if (bail) return false;
             if (dx[l] < dx[r]) {
                 f_back ^= (1u << l) | (1u << r);
@@ -366,7 +370,7 @@ struct ConvexSweep {
             lm_y[q] = boty[l];
         }
         cur_y = lm_y[0];
-        insert_local_minima(cur_y);
+        insert_local_minima(m, cur_y);
         if (bail) return false;
         // Scanbeams above which only the first path is active (its two bounds, not contributing: nothing can be
         // output and nothing is inserted) are walked here, outside the lane-synchronous loop: per scanbeam the sweep
@@ -384,8 +388,8 @@ struct ConvexSweep {
                     // sweep sees the second path alone and outputs nothing
                     na = 0; act = 0; cur_lm = 2; return false;
                 }
-                if (topy[0] == ty) load_edge(0, vi[0]);
-                if (topy[1] == ty && !bail) load_edge(1, vi[1]);
+                if (topy[0] == ty) load_edge(m, 0, vi[0]);
+                if (topy[1] == ty && !bail) load_edge(m, 1, vi[1]);
                 if (bail) return false;
             }
         }
@@ -393,7 +397,7 @@ struct ConvexSweep {
     }
     // one scanbeam: PopScanbeam, ProcessIntersections, ProcessEdgesAtTopOfScanbeam, InsertLocalMinimaIntoAEL.
     // Returns false when the sweep is over (or bailed).
-    SZ_HD bool step()
+    SZ_HD bool step(M m)
     {
         if (bail) return false;
         // PopScanbeam: the largest pending Y = tops of the active edges and pending local minima
@@ -414,7 +418,7 @@ struct ConvexSweep {
                 SZ_UNROLL4
                 for (int b = 0; b < 4; ++b) if (a != b && bit(act, a) && bit(act, b) && curx[a] > curx[b]) gt |= 1u << (4 * a + b);
             }
-            intersections(top_y, gt);
+            intersections(m, top_y, gt);
             if (bail) return false;
         }
         cur_y = top_y;
@@ -426,7 +430,7 @@ struct ConvexSweep {
             int i = 0;
             while (i < na && !bail) {
                 const int e = ord_at(i);
-                if (bit(at_top & f_last, e)) do_maxima(e);      // e and its pair leave the AEL; position i now holds the next edge
+                if (bit(at_top & f_last, e)) do_maxima(m, e);      // e and its pair leave the AEL; position i now holds the next edge
                 else ++i;
             }
             if (bail) return false;
@@ -439,8 +443,8 @@ struct ConvexSweep {
             const int e = ord_at(k);
             prom &= ~(1u << e);
             const bool o = bit(f_out, e);
-            if (o) add_out_pt(e, top(e));
-            load_edge(e, rd4(vi, e));                             // UpdateEdgeIntoAEL :1442-1462 (out, side, wc2 carry over)
+            if (o) add_out_pt(m, e, top(e));
+            load_edge(m, e, rd4(vi, e));                             // UpdateEdgeIntoAEL :1442-1462 (out, side, wc2 carry over)
             if (bail) return false;
             if (o) {
                 const int ep = (k > 0) ? ord_at(k - 1) : NILE, en = (k + 1 < na) ? ord_at(k + 1) : NILE;
@@ -449,7 +453,7 @@ struct ConvexSweep {
                 if (en != NILE && rd4(curx, en) == be.x && cur_y == be.y && bit(f_out, en) && cur_y > rd4(topy, en) && szclip::slopes_eq4(cur(e), top(e), cur(en), top(en))) { set_bail(13); return false; }
             }
         }
-        insert_local_minima(top_y);
+        insert_local_minima(m, top_y);
         if (bail) return false;
         // with both minima inserted and one path gone, the other path's bounds are outside it for good: no edge can
         // contribute again, whatever the remaining scanbeams hold
@@ -457,42 +461,42 @@ struct ConvexSweep {
         return true;
     }
     // On CV_OK the solution ring (BuildResult order) is in (ox, oy)[0, n_out), n_out = 0 when the intersection is empty.
-    SZ_HD int finish(i64* ox, i64* oy, int ocap, int& n_out)
+    SZ_HD int finish(M m, i64* ox, i64* oy, int ocap, int& n_out)
     {
         n_out = 0;
         if (bail) return CV_BAIL;
         if (n_or == 0) return CV_OK;
-        const int m = hi - lo + 1;
+        const int cnt = hi - lo + 1;
         // ring in Next order from Pts: r(t) = d[lo + t].  Area :406-416
         double ar = 0;
-        for (int t = 0; t < m; ++t) {
+        for (int t = 0; t < cnt; ++t) {
             const int c = lo + t, pv = (t == 0) ? hi : c - 1;
-            ar = fp::add(ar, fp::mul(fp::cvt(dqx[pv] + dqx[c]), fp::cvt(dqy[pv] - dqy[c])));
+            ar = fp::add(ar, fp::mul(fp::cvt(m.dqx[pv] + m.dqx[c]), fp::cvt(m.dqy[pv] - m.dqy[c])));
         }
         ar = fp::mul(ar, 0.5);
         const bool rev = !(ar > 0);        // :1594-1600: not a hole, so reversed unless the area is positive
         // FixupOutPolygon :3143-3181 would remove duplicate / collinear points: outside the model
-        if (m < 3) { why = 14; return CV_BAIL; }
-        for (int t = 0; t < m; ++t) {
-            const int c = lo + t, pv = (t == 0) ? hi : c - 1, nx = (t == m - 1) ? lo : c + 1;
-            P64 A, B, C; A.x = dqx[pv]; A.y = dqy[pv]; B.x = dqx[c]; B.y = dqy[c]; C.x = dqx[nx]; C.y = dqy[nx];
+        if (cnt < 3) { why = 14; return CV_BAIL; }
+        for (int t = 0; t < cnt; ++t) {
+            const int c = lo + t, pv = (t == 0) ? hi : c - 1, nx = (t == cnt - 1) ? lo : c + 1;
+            P64 A, B, C; A.x = m.dqx[pv]; A.y = m.dqy[pv]; B.x = m.dqx[c]; B.y = m.dqy[c]; C.x = m.dqx[nx]; C.y = m.dqy[nx];
             if (B == C || B == A || szclip::slopes_eq3(A, B, C)) { why = 15; return CV_BAIL; }
         }
-        if (m > ocap) { why = 16; return CV_BAIL; }
+        if (cnt > ocap) { why = 16; return CV_BAIL; }
         // BuildResult :3199-3217: start at Pts->Prev, walk Prev
-        if (!rev) { for (int t = 0; t < m; ++t) { ox[t] = dqx[hi - t]; oy[t] = dqy[hi - t]; } }
-        else { for (int t = 0; t < m; ++t) { const int c = (t == m - 1) ? lo : lo + 1 + t; ox[t] = dqx[c]; oy[t] = dqy[c]; } }
-        n_out = m;
+        if (!rev) { for (int t = 0; t < cnt; ++t) { ox[t] = m.dqx[hi - t]; oy[t] = m.dqy[hi - t]; } }
+        else { for (int t = 0; t < cnt; ++t) { const int c = (t == cnt - 1) ? lo : lo + 1 + t; ox[t] = m.dqx[c]; oy[t] = m.dqy[c]; } }
+        n_out = cnt;
         return CV_OK;
     }
     // the whole clip for a single caller
     template <class G>
-    SZ_HD int run(const G& subj, int n1, const G& clip, int n2, i64* wx, i64* wy, int wcap, i64* ox, i64* oy, int ocap, int& n_out)
+    SZ_HD int run(M m, const G& subj, int n1, const G& clip, int n2, i64* ox, i64* oy, int ocap, int& n_out)
     {
-        load_ring(0, subj, n1); load_ring(1, clip, n2);
-        bool go = begin(wx, wy, wcap);
-        while (go) go = step();
-        return finish(ox, oy, ocap, n_out);
+        load_ring(m, 0, subj, n1); load_ring(m, 1, clip, n2);
+        bool go = begin(m);
+        while (go) go = step(m);
+        return finish(m, ox, oy, ocap, n_out);
     }
 };
 

@@ -538,17 +538,17 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
     if constexpr (FAST) {
         static_assert(C::NP >= 2 * C::NV, "the InterX buffers must hold both int64 outlines");
         szcvx::ConvexSweep<C::NV> cs;
-        cs.set_storage(w.svx, w.svy);
+        const szcvx::SweepMem mem{w.svx, w.svy, w.rbx, w.rby, C::RV};       // outlines in the InterX buffers, deque in the clip #2 buffers
         bool run = false;
         const bool go = valid && convex_pair && !boundary && hints.no1 >= 3 && hints.no2 >= 3;
         if (go) {
             ClipInput subj, clip;
             subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = hints.no1; subj.ring = 0; subj.rot = hints.rot1;
             clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = hints.no2; clip.ring = 0; clip.rot = hints.rot2;
-            cs.load_ring(0, subj, subj.n); cs.load_ring(1, clip, clip.n);
+            cs.load_ring(mem, 0, subj, subj.n); cs.load_ring(mem, 1, clip, clip.n);
         }
         SZ_LANE_SYNC();
-        if (go) run = cs.begin(w.rbx, w.rby, C::RV);
+        if (go) run = cs.begin(mem);
 #ifndef SZ_C_STEPS_PER_SYNC
 #define SZ_C_STEPS_PER_SYNC 1
 #endif
@@ -558,11 +558,11 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
 #else
             if (!SZ_WARP_ANY(run)) break;
 #endif
-            for (int u = 0; u < SZ_C_STEPS_PER_SYNC; ++u) { if (run) run = cs.step(); SZ_LANE_SYNC(); }
+            for (int u = 0; u < SZ_C_STEPS_PER_SYNC; ++u) { if (run) run = cs.step(mem); SZ_LANE_SYNC(); }
         }
         if (go) {
             int n_out = 0;
-            if (cs.finish(w.rax, w.ray, C::RV, n_out) == szcvx::CV_OK) { fast_clip1 = PS_OK; w.ra_off[0] = 0; w.ra_off[1] = n_out; w.ra_n = n_out > 0 ? 1 : 0; }
+            if (cs.finish(mem, w.rax, w.ray, C::RV, n_out) == szcvx::CV_OK) { fast_clip1 = PS_OK; w.ra_off[0] = 0; w.ra_off[1] = n_out; w.ra_n = n_out > 0 ? 1 : 0; }
         }
         SZ_LANE_SYNC();
     }

@@ -98,9 +98,9 @@ static bool check(const Poly& s_in, const Poly& c_in, int fam, long caseno)
     VecGet gs{&s_in, szpf::ring_bottom_vertex(gs0, (int)s_in.size())}, gc{&c_in, szpf::ring_bottom_vertex(gc0, (int)c_in.size())};
     static szcvx::ConvexSweep<64> sw;
     static i64 ringx[128], ringy[128];
-    sw.set_storage(ringx, ringy);
     i64 wx[64], wy[64], ox[64], oy[64]; int nout = 0;
-    const int st = sw.run(gs, (int)s_in.size(), gc, (int)c_in.size(), wx, wy, 64, ox, oy, 64, nout);
+    const szcvx::SweepMem mem{ringx, ringy, wx, wy, 64};
+    const int st = sw.run(mem, gs, (int)s_in.size(), gc, (int)c_in.size(), ox, oy, 64, nout);
     if (st != szcvx::CV_OK) { ++g_bail; ++fams[fam].bail; ++g_why[sw.why & 31]; return true; }
     ++g_ok; ++fams[fam].ok;
     // the reference sees the path as stored (any start vertex, optionally closed)
