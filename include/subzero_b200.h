@@ -255,6 +255,18 @@ int sz_get_trajectory_forcing(SzContext* ctx, double* FxOA, double* FyOA, double
 int sz_fracture_deform(SzContext* ctx, int32_t count, const int32_t* floe_idx, int64_t* n_changed, int64_t* n_verts);
 int sz_get_fracture_deform(SzContext* ctx, uint8_t* changed, double* xi, double* yi, double* area, int64_t* vert_off, double* cx, double* cy);
 
+/* ---- SURVEY.md 8f row f3, second consumer of the contact rows: Physical_Processes/corners.m:10-88, the deterministic half
+ * of the corner-grinding rule -- the mask `da` of vertices "in contact" (the random half, break1 = rand > angle/Anorm :72
+ * and frac_corner, stays with the host).  floe_idx: `count` floe numbers (1-based positions in the list of the last contact
+ * step, host or device memory) = the selection Floe(~keep) of Subzero.m:348; nb_skip = Nb (corners.m:54 skips the first Nb
+ * entries of the SELECTION).  As written in the reference: the periodic list is rebuilt from the resident positions whether
+ * or not the run is periodic (:13-51, Lx/Ly of the uploaded parameters); for every contact row with a partner in that list:
+ * the vertex nearest to the contact point (dsearchn :74) and every vertex in or on the partner's outline (inpolygon :78-82);
+ * for wall rows (partner Inf) every vertex outside the uploaded c2_boundary (:83-86).  Result on the device until fetched:
+ *   da_off [count + 1] into da [n_verts], one byte per polyshape vertex (c_alpha without its closing duplicate, stored order). */
+int sz_corner_mask(SzContext* ctx, int32_t count, const int32_t* floe_idx, int32_t nb_skip, int64_t* n_verts);
+int sz_get_corner_mask(SzContext* ctx, int64_t* da_off, uint8_t* da);
+
 /* diagnostic: device time (CUDA events, ms) of the last step by phase:
  * [0] ghost floes (floe_interactions_all.m:16-66)   [1] broad phase (:68-120)
  * [2] narrow phase + force law (:125-174)           [3] mirror/torque/sums (:186-265)   [4] whole step */

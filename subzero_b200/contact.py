@@ -166,6 +166,20 @@ class ContactContext:
         assert int(o["changed"].sum()) == nc.value
         return o
 
+    # ---- corners.m:10-88: the contact mask `da` of the floes selected for corner grinding (consumer of the contact rows)
+    def corner_mask(self, idx, Nb=0):
+        """idx: the selection Floe(~keep) as floe numbers (1-based) of the last contact step's list; Nb: corners.m:54 skips
+        the first Nb entries of the selection.  Returns a list of uint8 arrays, one per selected floe (one byte per vertex
+        of c_alpha without its closing duplicate)"""
+        idx = np.ascontiguousarray(idx, np.int32)
+        n = idx.shape[0]
+        nv = C.c_int64()
+        abi.check(abi.lib().sz_corner_mask(self._h, n, abi._ptr(idx, abi.c_ip), int(Nb), C.byref(nv)))
+        off, da = np.zeros(n + 1, np.int64), np.zeros(max(nv.value, 1), np.uint8)
+        abi.check(abi.lib().sz_get_corner_mask(self._h, abi._ptr(off, abi.c_lp), abi._ptr(da, abi.c_bp)))
+        assert off[n] == nv.value
+        return [da[off[k]:off[k + 1]].copy() for k in range(n)]
+
     # ---- ocean / atmosphere forcing (calc_trajectory.m:94-166) and strain (:224-234)
     def trajectory_set_ocean(self, Xo, Yo, Uocn, Vocn, Uwinds, Vwinds, fCoriolis, turn_angle, rho0=0.0, Cd=0.0, rho_air=0.0, Cd_atm=0.0):
         """Xo [nx], Yo [ny]; the four fields as (ny, nx) arrays like ocean.Uocn / winds.u in MATLAB"""

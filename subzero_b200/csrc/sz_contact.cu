@@ -19,6 +19,7 @@
 // reference's operation order; the file is compiled with -fmad=false.
 #include "../../include/subzero_b200.h"
 #include "sz_narrow.cuh"
+#include "sz_corners.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -85,6 +86,7 @@ struct Counters {
     int clip_listM, clip_listL, clip_path_used, clip_vert_used;
     int n_forced, n_no_points;     // ocean forcing: floes evaluated / floes without a Monte-Carlo point inside
     int fr_vert_used, fr_changed;  // fracture deformation: vertices of the new outlines, floes changed
+    int cr_n1, cr_n;               // corners.m's own periodic list: sizes after the x pass / after the y pass
 };
 
 struct SzContext {
@@ -136,6 +138,8 @@ struct SzContext {
     DBuf<double> t_mass, t_inertia, t_alpha, t_dXi_p, t_dYi_p, t_dUi_p, t_dVi_p, t_dalpha_p, t_dksi_p, t_FxOA, t_FyOA, t_torqueOA, c0x, c0y, t_stressH, t_stress;
     // fracture deformation (fracture_floe.m:12-52)
     DBuf<int> fr_idx, fr_vstart, fr_vcount, fr_status; DBuf<uint8_t> fr_changed; DBuf<double> fr_xi, fr_yi, fr_area, fr_vx, fr_vy; int fr_count = 0; i64 fr_verts = 0; bool have_fr = false;
+    // corner mask (corners.m:10-88)
+    DBuf<int> cr_idx, cr_nv, cr_off, cr_esrc; DBuf<uint8_t> cr_da, cr_ealive; DBuf<double> cr_ex, cr_ey; int cr_count = 0; i64 cr_verts = 0; bool have_cr = false;
     // ocean / atmosphere forcing (calc_trajectory.m:94-166)
     DBuf<double> oc_Xo, oc_Yo, oc_U, oc_V, oc_Wu, oc_Wv, pt_x, pt_y, t_strain; DBuf<uint8_t> pt_a, t_forced;
     int oc_nx = 0, oc_ny = 0, npts = 0; bool have_ocean = false, have_points = false, traj_do_int = false;
@@ -828,15 +832,15 @@ extern "C" void sz_destroy(SzContext* c)
     DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi,
                           &c->oc_Xo, &c->oc_Yo, &c->oc_U, &c->oc_V, &c->oc_Wu, &c->oc_Wv, &c->pt_x, &c->pt_y, &c->t_strain,
-                          &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy};
+                          &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy, &c->cr_ex, &c->cr_ey};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
                        &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->stage, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
-                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status};
+                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status, &c->cr_idx, &c->cr_nv, &c->cr_off, &c->cr_esrc};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed};
+    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed, &c->cr_da, &c->cr_ealive};
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
@@ -1859,6 +1863,119 @@ extern "C" int sz_get_fracture_deform(SzContext* c, uint8_t* changed, double* xi
             if (vert_off) vert_off[k + 1] = pos;
         }
     }
+    return SZ_OK;
+}
+// ------------------------------------------------------------------------------------------------ corner mask
+// corners.m:13-51 rebuilds the periodic list from the current positions, whether or not the run is periodic; only the
+// centroid, the source floe and the alive flag of an image are needed here.
+__global__ void corner_ext_init_kernel(int n0, const double* __restrict__ x, const double* __restrict__ y, const uint8_t* __restrict__ alive,
+                                       double* __restrict__ ex, double* __restrict__ ey, int* __restrict__ esrc, uint8_t* __restrict__ ealive)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    ex[i] = x[i]; ey[i] = y[i]; esrc[i] = i; ealive[i] = alive[i];
+}
+__global__ void corner_ext_emit_kernel(int axis, int n_bound, const int* __restrict__ n_dev, const int* __restrict__ flag, const int* __restrict__ pos,
+                                       double* __restrict__ ex, double* __restrict__ ey, int* __restrict__ esrc, uint8_t* __restrict__ ealive, double L, int* __restrict__ n_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = n_dev ? *n_dev : n_bound;
+    if (i == 0) *n_out = n + pos[n_bound];
+    if (i >= n || !flag[i]) return;
+    const int g = n + pos[i];
+    if (axis == 0) { ex[g] = ex[i] - 2 * L * sgn_d(ex[i]); ey[g] = ey[i]; }                      // corners.m:21-30
+    else { ex[g] = ex[i]; ey[g] = ey[i] - 2 * L * sgn_d(ey[i]); }                                // :38-46
+    esrc[g] = esrc[i]; ealive[g] = ealive[i];
+}
+__global__ void corner_count_kernel(const szcorn::CornerArgs a, int* __restrict__ nv)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < a.count) nv[q] = szcorn::open_count(a, a.idx[q] - 1);
+}
+template <int G>
+__global__ void __launch_bounds__(256) corner_mask_kernel(const szcorn::CornerArgs a)
+{
+    const int lane = threadIdx.x % G;
+    const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    const int groups = gridDim.x * (blockDim.x / G);
+    for (int q = blockIdx.x * (blockDim.x / G) + threadIdx.x / G; q < a.count; q += groups) szcorn::corner_mask_floe<G>(a, q, lane, mask);
+}
+
+extern "C" int sz_corner_mask(SzContext* c, int32_t count, const int32_t* floe_idx, int32_t nb_skip, int64_t* n_verts)
+{
+    if (!c) { sz_set_error("sz_corner_mask: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_rows) { sz_set_error("sz_corner_mask: no contact rows on the device (run a contact step first)"); return SZ_ERR_STATE; }
+    if (c->ext_mode) { sz_set_error("sz_corner_mask: single-GPU lists only"); return SZ_ERR_STATE; }
+    if (count < 0 || nb_skip < 0 || (count > 0 && !floe_idx)) { sz_set_error("sz_corner_mask: bad arguments"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    c->have_cr = false; c->cr_count = count; c->cr_verts = 0;
+    if (n_verts) *n_verts = 0;
+    if (count == 0) { c->have_cr = true; return SZ_OK; }
+    const int n0 = c->n0;
+    {   // the numbers must name floes of the list
+        std::vector<int32_t> h(count);
+        CK(cudaMemcpy(h.data(), floe_idx, (size_t)count * 4, cudaMemcpyDefault));
+        for (int32_t v : h) if (v < 1 || v > n0) { sz_set_error("sz_corner_mask: floe number %d outside 1..%d", v, n0); return SZ_ERR_ARG; }
+        CK(c->cr_idx.ensure(count + 1));
+        CK(cudaMemcpyAsync(c->cr_idx.p, h.data(), (size_t)count * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st));
+    }
+    // ---- corners.m:13-51: originals, x images, then y images over the extended list (at most 4 n0 entries)
+    const size_t ncap = 4 * (size_t)n0 + 1;
+    CK(c->cr_ex.ensure(ncap)); CK(c->cr_ey.ensure(ncap)); CK(c->cr_esrc.ensure(ncap)); CK(c->cr_ealive.ensure(ncap));
+    CK(c->flag.ensure(2 * (size_t)n0 + 2)); CK(c->pos.ensure(2 * (size_t)n0 + 2)); CK(c->scan_tmp.ensure(scan_tmp_ints(std::max(2 * (size_t)n0 + 2, (size_t)count + 2))));
+    const double Lx = c->prm.Lx, Ly = c->prm.Ly;
+    ++g_launches; corner_ext_init_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->cr_ex.p, c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p);
+    ++g_launches; ghost_flag_kernel<<<nblk(n0, 128), 128, 0, st>>>(0, n0, nullptr, c->cr_ex.p, c->cr_esrc.p, c->cr_ealive.p, c->voff.p, c->vx.p, Lx, c->flag.p);
+    exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+    ++g_launches; corner_ext_emit_kernel<<<nblk(n0, 256), 256, 0, st>>>(0, n0, nullptr, c->flag.p, c->pos.p, c->cr_ex.p, c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p, Lx, D_CNT(cr_n1));
+    ++g_launches; ghost_flag_kernel<<<nblk(2 * (i64)n0, 128), 128, 0, st>>>(1, 2 * n0, D_CNT(cr_n1), c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p, c->voff.p, c->vy.p, Ly, c->flag.p);
+    exclusive_scan(c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1, c->scan_tmp.p, st);
+    ++g_launches; corner_ext_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(cr_n1), c->flag.p, c->pos.p, c->cr_ex.p, c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p, Ly, D_CNT(cr_n));
+    // ---- one slot of da per polyshape vertex of every selected floe
+    szcorn::CornerArgs a; memset(&a, 0, sizeof(a));
+    a.count = count; a.idx = c->cr_idx.p; a.nb_skip = nb_skip;
+    a.x = c->x.p; a.y = c->y.p; a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
+    a.row_off = c->row_off.p; a.rows = c->rows.p;
+    a.cex = c->cr_ex.p; a.cey = c->cr_ey.p; a.cesrc = c->cr_esrc.p; a.n_ext = D_CNT(cr_n);
+    a.boxx = c->boxx.p; a.boxy = c->boxy.p; a.nbox = c->have_bnd ? c->boxn : 0;
+    CK(c->cr_nv.ensure(count + 1)); CK(c->cr_off.ensure(count + 2));
+    ++g_launches; corner_count_kernel<<<nblk(count, 256), 256, 0, st>>>(a, c->cr_nv.p);
+    exclusive_scan(c->cr_nv.p, count, c->cr_off.p, count + 1, c->scan_tmp.p, st);
+    CK(cudaGetLastError());
+    int total = 0;
+    CK(cudaMemcpyAsync(&total, c->cr_off.p + count, 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st));
+    if (total < 0) { sz_set_error("sz_corner_mask: more than 2^31 vertices selected"); return SZ_ERR_CAPACITY; }
+    CK(c->cr_da.ensure((size_t)total + 1));
+    a.da_off = c->cr_off.p; a.da = c->cr_da.p;
+    // 8 lanes per floe for Voronoi-sized outlines, a warp per floe for real shapes
+    const bool small = c->nverts <= 12 * (i64)n0;
+    const int per_block = small ? 256 / 8 : 256 / 32;
+    const int blocks = std::max(1, std::min(nblk(count, per_block), 148 * 16));
+    ++g_launches;
+    if (small) corner_mask_kernel<8><<<blocks, 256, 0, st>>>(a); else corner_mask_kernel<32><<<blocks, 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    c->cr_verts = total; c->have_cr = true;
+    if (n_verts) *n_verts = total;
+    return SZ_OK;
+}
+extern "C" int sz_get_corner_mask(SzContext* c, int64_t* da_off, uint8_t* da)
+{
+    if (!c) { sz_set_error("sz_get_corner_mask: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_cr) { sz_set_error("sz_get_corner_mask: no result"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->cr_count;
+    if (da_off) {
+        da_off[0] = 0;
+        if (n) {
+            std::vector<int> off(n + 1);
+            CK(cudaMemcpy(off.data(), c->cr_off.p, (n + 1) * 4, cudaMemcpyDefault));
+            for (size_t k = 0; k <= n; ++k) da_off[k] = off[k];
+        }
+    }
+    D2H(da, c->cr_da.p, (size_t)c->cr_verts);
+    CK(cudaStreamSynchronize(c->stream));
     return SZ_OK;
 }
 // reorder (start, count) pools into item-major CSR

@@ -21,6 +21,9 @@
 //                                                      dalpha_p dksi_p stress(4xN) flags FxOA FyOA torqueOA strain(4xN)
 //                                                      cax cay (V x 1, the rotated c_alpha pool)
 //   d   = sz_resident_mex('fracture_deform', idx)      idx: floe numbers; d: changed xi yi area vert_off cx cy
+//   m   = sz_resident_mex('corner_mask', idx, Nb)      idx: the selection Floe(~keep) of Subzero.m:348 as floe numbers;
+//                                                      m: da_off (numel(idx)+1), da (the mask of corners.m:54-88, one
+//                                                      entry per polyshape vertex of every selected floe)
 //
 // Build (MATLAB):  mex -I../../include sz_resident_mex.cpp -L../_lib -lsubzero_b200
 #include "mex.h"
@@ -242,6 +245,30 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         for (size_t k = 0; k <= m; ++k) mxGetPr(vo)[k] = (double)off[k];
         mxArray* vals[] = {ch, xi, yi, ar, vo, cx, cy};
         for (int k = 0; k < 7; ++k) mxSetFieldByNumber(out, 0, k, vals[k]);
+        plhs[0] = out;
+        return;
+    }
+    if (cmd == "corner_mask") {
+        if (nrhs < 2) mexErrMsgIdAndTxt("subzero_b200:arg", "usage: m = sz_resident_mex('corner_mask', idx [, Nb])");
+        const size_t m = mxGetNumberOfElements(prhs[1]);
+        const double* id = need_array(prhs[1], m, "idx");
+        std::vector<int32_t> idx(m);
+        for (size_t k = 0; k < m; ++k) idx[k] = (int32_t)id[k];
+        int32_t nb = 0;
+        if (nrhs > 2) {
+            if (!mxIsDouble(prhs[2]) || mxGetNumberOfElements(prhs[2]) != 1) mexErrMsgIdAndTxt("subzero_b200:arg", "Nb must be a real scalar");
+            nb = (int32_t)mxGetScalar(prhs[2]);
+        }
+        int64_t nv = 0;
+        check(sz_corner_mask(g_ctx, (int32_t)m, idx.data(), nb, &nv));
+        const char* names[] = {"da_off", "da"};
+        mxArray* out = mxCreateStructMatrix(1, 1, 2, names);
+        mxArray *vo = vec(m + 1), *da = vec((size_t)nv);
+        std::vector<uint8_t> d8((size_t)nv + 1); std::vector<int64_t> off(m + 1);
+        check(sz_get_corner_mask(g_ctx, off.data(), d8.data()));
+        for (size_t k = 0; k <= m; ++k) mxGetPr(vo)[k] = (double)off[k];
+        for (size_t k = 0; k < (size_t)nv; ++k) mxGetPr(da)[k] = d8[k];
+        mxSetFieldByNumber(out, 0, 0, vo); mxSetFieldByNumber(out, 0, 1, da);
         plhs[0] = out;
         return;
     }

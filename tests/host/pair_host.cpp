@@ -1,9 +1,11 @@
 // Host build of the product's pair force law (subzero_b200/csrc/sz_pairforce.cuh) for CPU-side
 // parity tests against the oracle (test infrastructure; the product never runs this on the CPU).
 #include "../../subzero_b200/csrc/sz_pairforce.cuh"
+#include "../../subzero_b200/csrc/sz_corners.cuh"
 #include "../../include/subzero_b200.h"
 #include <vector>
 #include <memory>
+#include <cstring>
 
 using namespace szpf;
 typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3900> BigClip;
@@ -73,4 +75,41 @@ extern "C" int szport_floe_interactions(const SzParams* prm, const double* cax, 
     if (small_class == 2) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state, true);
     if (small_class) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);
     return run<BigPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);
+}
+
+// corners.m:10-88, the contact mask: the product's per-floe core (sz_corners.cuh, one lane per group on the host) over the
+// periodic list built here the way the device kernels build it (originals, x images, y images over the extended list).
+extern "C" int szport_corner_mask(const SzFloesSoA* f, const int64_t* row_off64, const double* rows, int count, const int32_t* idx, int nb_skip,
+                                  double Lx, double Ly, const double* boxx, const double* boxy, int nbox, int64_t* da_off, uint8_t* da, int64_t vcap)
+{
+    const int n0 = f->n;
+    std::vector<double> ex(f->x, f->x + n0), ey(f->y, f->y + n0); std::vector<int> esrc(n0); std::vector<uint8_t> ealive(f->alive, f->alive + n0);
+    for (int i = 0; i < n0; ++i) esrc[i] = i;
+    auto sgn = [](double v) { return (double)((v > 0) - (v < 0)); };
+    auto pass = [&](int axis, double L) {
+        const size_t n = ex.size();
+        for (size_t i = 0; i < n; ++i) {
+            if (!ealive[i]) continue;
+            const int s = esrc[i]; double m = -SZ_INF;
+            for (int t = f->voff[s]; t < f->voff[s + 1]; ++t) { const double a = fabs((axis ? f->vy[t] : f->vx[t]) + (axis ? ey[i] : ex[i])); if (a > m) m = a; }
+            if (!(m > L)) continue;
+            if (axis == 0) { ex.push_back(ex[i] - 2 * L * sgn(ex[i])); ey.push_back(ey[i]); }
+            else { ex.push_back(ex[i]); ey.push_back(ey[i] - 2 * L * sgn(ey[i])); }
+            esrc.push_back(esrc[i]); ealive.push_back(ealive[i]);
+        }
+    };
+    pass(0, Lx); pass(1, Ly);
+    const int n_ext = (int)ex.size();
+    std::vector<int> row_off(n0 + 1), off(count + 1, 0);
+    for (int i = 0; i <= n0; ++i) row_off[i] = (int)row_off64[i];
+    szcorn::CornerArgs a; memset(&a, 0, sizeof(a));
+    a.count = count; a.idx = idx; a.nb_skip = nb_skip; a.x = f->x; a.y = f->y; a.voff = f->voff; a.vx = f->vx; a.vy = f->vy;
+    a.row_off = row_off.data(); a.rows = rows; a.cex = ex.data(); a.cey = ey.data(); a.cesrc = esrc.data(); a.n_ext = &n_ext;
+    a.boxx = boxx; a.boxy = boxy; a.nbox = nbox;
+    for (int q = 0; q < count; ++q) off[q + 1] = off[q] + szcorn::open_count(a, idx[q] - 1);
+    if (off[count] > vcap) return -1;
+    a.da_off = off.data(); a.da = da;
+    for (int q = 0; q < count; ++q) szcorn::corner_mask_floe<1>(a, q, 0, 1u);
+    for (int q = 0; q <= count; ++q) da_off[q] = off[q];
+    return off[count];
 }

@@ -142,3 +142,119 @@ def test_oracle_corner_eligibility_known_answers():
     assert off[1] > 0 and np.isinf(rows[0, 0])
     da = oracle.corner_eligibility(step, soa, [1], L, L, c2)
     assert list(da[0]) == [0, 0, 1, 1]                   # the two vertices at x = L + 800
+
+
+# ---- corners.m:10-88, the contact mask: the product's per-floe core on the host (CPU) and the device path (GPU)
+def _port_corner_mask(step, floes, idx, Lx, Ly, c2_boundary, Nb=0):
+    """sz_corners.cuh compiled for the host (tests/host/pair_host.cpp), one lane per floe"""
+    import ctypes as C
+    import os
+    from subzero_b200 import abi
+    l = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "libpair_host.so"))
+    l.szport_corner_mask.restype = C.c_int
+    l.szport_corner_mask.argtypes = [C.POINTER(abi.SzFloesSoA), abi.c_lp, abi.c_dp, C.c_int, abi.c_ip, C.c_int, C.c_double, C.c_double, abi.c_dp, abi.c_dp, C.c_int,
+                                     abi.c_lp, abi.c_bp, C.c_int64]
+    off, rows = step.rows()
+    off = np.ascontiguousarray(off, np.int64); rows = np.ascontiguousarray(rows)
+    idx = np.ascontiguousarray(idx, np.int32)
+    bx, by = np.ascontiguousarray(c2_boundary[0], np.float64), np.ascontiguousarray(c2_boundary[1], np.float64)
+    cap = int(floes.vx.shape[0]) * 2 + 8
+    da_off, da = np.zeros(idx.shape[0] + 1, np.int64), np.full(cap, 7, np.uint8)
+    view = floes.struct()
+    p = abi._ptr
+    r = l.szport_corner_mask(C.byref(view), p(off, abi.c_lp), p(rows, abi.c_dp), idx.shape[0], p(idx, abi.c_ip), int(Nb), float(Lx), float(Ly),
+                             p(bx, abi.c_dp), p(by, abi.c_dp), bx.shape[0], p(da_off, abi.c_lp), p(da, abi.c_bp), cap)
+    assert r >= 0, r
+    return [da[da_off[k]:da_off[k + 1]].copy() for k in range(idx.shape[0])]
+
+
+def _same_masks(got, want):
+    assert len(got) == len(want)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == w.shape and np.array_equal(g, w), (k, g, w)
+    return sum(int(w.sum()) for w in want)
+
+
+def _wall_case():
+    L = 5000.0
+    c2, fb = scenarios.domain(L, L)
+    sq = np.array([[-1000.0, -1000.0], [-1000.0, 1000.0], [1000.0, 1000.0], [1000.0, -1000.0]])
+    soa = sz.floes_to_soa([scenarios.floe_from_polygon(sq + [L - 200.0, 0.0]), scenarios.floe_from_polygon(sq + [L - 2100.0, 100.0])])
+    prm = sz.default_params(Lx=L, Ly=L, modulus=1e7, dt=10.0, periodic=0, collision=1)
+    bnd = sz.Boundary(fb["c"][0], fb["c"][1], c2[0], c2[1], fb["area"], fb["h"])
+    return prm, soa, bnd, c2
+
+
+def test_corner_mask_core_on_host_matches_oracle():
+    """the code the device runs per floe (sz_corners.cuh) against the oracle's restatement: hand-derived squares, the Nb
+    rule, a wall contact, every floe of a periodic Voronoi field (partners that are periodic images), floes moved after the
+    contact step (rows of the old positions, list of the new ones), real concave shapes, repeated selections"""
+    c2, _ = scenarios.domain(1e5, 1e5)
+    prm, soa = two_squares(1900.0)
+    step = oracle.OracleStep(prm, soa)
+    got = _port_corner_mask(step, soa, [1, 2], prm.Lx, prm.Ly, c2)
+    assert list(got[0]) == [0, 0, 1, 1] and list(got[1]) == [1, 1, 0, 0]
+    for Nb in (0, 1, 2):
+        _same_masks(_port_corner_mask(step, soa, [2, 1, 2], prm.Lx, prm.Ly, c2, Nb), oracle.corner_eligibility(step, soa, [2, 1, 2], prm.Lx, prm.Ly, c2, Nb))
+    prm, soa, bnd, c2w = _wall_case()
+    step = oracle.OracleStep(prm, soa, bnd)
+    want = oracle.corner_eligibility(step, soa, [1, 2], prm.Lx, prm.Ly, c2w)
+    # floe 1 = [3800, 5800] x [-1000, 1000], floe 2 = [1900, 3900] x [-900, 1100]; contact point (3850, 50).  Floe 1: (3800, 1000) is
+    # inside floe 2 and nearest to the contact point, the two vertices at x = 5800 are beyond the wall; floe 2: (3900, -900) only
+    assert list(want[0]) == [0, 1, 1, 1] and list(want[1]) == [0, 0, 0, 1]
+    _same_masks(_port_corner_mask(step, soa, [1, 2], prm.Lx, prm.Ly, c2w), want)
+    flagged = 0
+    for inflate, seed in ((0.02, 71), (0.1, 72)):
+        prm, soa = sz.voronoi_field(1500, seed=seed, inflate=inflate)
+        c2v, _ = scenarios.domain(prm.Lx, prm.Ly)
+        step = oracle.OracleStep(prm, soa, broad_mode=1)
+        idx = np.arange(1, soa.n + 1)
+        flagged += _same_masks(_port_corner_mask(step, soa, idx, prm.Lx, prm.Ly, c2v, Nb=3), oracle.corner_eligibility(step, soa, idx, prm.Lx, prm.Ly, c2v, Nb=3))
+        # the floes moved since the contact step (corners runs after calc_trajectory)
+        rng = np.random.default_rng(seed)
+        moved = sz.FloesSoA(soa.x + rng.uniform(-30, 30, soa.n), soa.y + rng.uniform(-30, 30, soa.n), soa.rmax, soa.h, soa.area, soa.u, soa.v, soa.ksi, soa.alive,
+                            soa.voff, soa.vx, soa.vy)
+        flagged += _same_masks(_port_corner_mask(step, moved, idx[::3], prm.Lx, prm.Ly, c2v), oracle.corner_eligibility(step, moved, idx[::3], prm.Lx, prm.Ly, c2v))
+    assert flagged > 5000
+    prm_r, Floe = scenarios.real_shape_field(5, seed=4)
+    soa, _ = scenarios.soa_and_boundary(Floe, prm_r, periodic=True)
+    c2r, _ = scenarios.domain(prm_r.Lx, prm_r.Ly)
+    step = oracle.OracleStep(prm_r, soa, broad_mode=1)
+    idx = np.arange(1, soa.n + 1)
+    assert _same_masks(_port_corner_mask(step, soa, idx, prm_r.Lx, prm_r.Ly, c2r), oracle.corner_eligibility(step, soa, idx, prm_r.Lx, prm_r.Ly, c2r)) > 20
+
+
+@pytest.mark.gpu
+def test_device_corner_mask_matches_oracle():
+    """sz_corner_mask against the oracle: the same cases as the host test, through the C ABI (8 lanes per floe on Voronoi
+    fields, a warp per floe on real shapes)"""
+    with sz.ContactContext(0) as ctx:
+        c2, _ = scenarios.domain(1e5, 1e5)
+        prm, soa = two_squares(1900.0)
+        ctx.step(prm, soa)
+        got = ctx.corner_mask([1, 2])
+        assert list(got[0]) == [0, 0, 1, 1] and list(got[1]) == [1, 1, 0, 0]
+        step = oracle.OracleStep(prm, soa)
+        for Nb in (0, 1, 2):
+            _same_masks(ctx.corner_mask([2, 1, 2], Nb), oracle.corner_eligibility(step, soa, [2, 1, 2], prm.Lx, prm.Ly, c2, Nb))
+        assert ctx.corner_mask([]) == []
+        prm, soa, bnd, c2w = _wall_case()
+        ctx.step(prm, soa, bnd)
+        _same_masks(ctx.corner_mask([1, 2]), oracle.corner_eligibility(oracle.OracleStep(prm, soa, bnd), soa, [1, 2], prm.Lx, prm.Ly, c2w))
+        flagged = 0
+        for inflate, seed in ((0.02, 71), (0.1, 72)):
+            prm, soa = sz.voronoi_field(3000, seed=seed, inflate=inflate)
+            c2v, _ = scenarios.domain(prm.Lx, prm.Ly)
+            ctx.step(prm, soa, allow_pair_errors=True)
+            step = oracle.OracleStep(prm, soa, broad_mode=1)
+            idx = np.arange(1, soa.n + 1)
+            flagged += _same_masks(ctx.corner_mask(idx, Nb=3), oracle.corner_eligibility(step, soa, idx, prm.Lx, prm.Ly, c2v, Nb=3))
+            flagged += _same_masks(ctx.corner_mask(idx[::3]), oracle.corner_eligibility(step, soa, idx[::3], prm.Lx, prm.Ly, c2v))
+        assert flagged > 10000
+        prm_r, Floe = scenarios.real_shape_field(5, seed=4)
+        soa, _ = scenarios.soa_and_boundary(Floe, prm_r, periodic=True)
+        c2r, _ = scenarios.domain(prm_r.Lx, prm_r.Ly)
+        ctx.step(prm_r, soa, allow_pair_errors=True)
+        step = oracle.OracleStep(prm_r, soa, broad_mode=1)
+        idx = np.arange(1, soa.n + 1)
+        assert _same_masks(ctx.corner_mask(idx), oracle.corner_eligibility(step, soa, idx, prm_r.Lx, prm_r.Ly, c2r)) > 20
