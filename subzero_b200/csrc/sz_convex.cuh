@@ -20,6 +20,7 @@
 // Clipper (generic, near-degenerate, shared-edge and grid inputs) and reports the bail rate.
 #pragma once
 #include "sz_clip.cuh"
+#include <type_traits>
 
 namespace szcvx {
 
@@ -50,6 +51,38 @@ template <class T> SZ_HD void wr4(T (&a)[4], int e, T v) { a[e] = v; }
 #define SZ_UNROLL4
 #endif
 
+// Experiment switch SZ_C_SMEM_EDGES=<mask> (device only, off by default, NOT measured yet): the chosen 8-byte fields of the
+// four edge records live in dynamic shared memory instead of local memory -- bit 0 botx, 1 boty, 2 topx, 3 topy, 4 curx,
+// 5 dx.  Entry e of field slot f of thread t sits at ((4 f + e) * blockDim + t) * 8: any mix of run-time subscripts across
+// a warp is bank-conflict free, and the accessor is stateless (it names the extern array itself) so the accesses compile
+// to LDS/STS.  Cost: popcount(mask) * 32 B per thread (all six: 96 KB per 512-thread CTA, 192 KB per SM at two CTAs, which
+// leaves 64 KB of L1 for the rest of the local-memory working set).  The launcher (sz_narrow_C.cu) sizes the allocation
+// with smem_edge_bytes().
+#if defined(SZ_C_SMEM_EDGES)
+#define SZ_C_SMEM_MASK (SZ_C_SMEM_EDGES)
+#else
+#define SZ_C_SMEM_MASK 0
+#endif
+constexpr int smem_edge_slot(int field) { int s = 0; for (int k = 0; k < field; ++k) s += (SZ_C_SMEM_MASK >> k) & 1; return s; }
+constexpr int smem_edge_fields() { return smem_edge_slot(6); }
+constexpr size_t smem_edge_bytes(int threads_per_block) { return (size_t)smem_edge_fields() * 4 * 8 * (size_t)threads_per_block; }
+#if defined(__CUDA_ARCH__) && SZ_C_SMEM_MASK != 0
+template <class T, int FIELD> struct SmemArr4 {
+    static_assert(sizeof(T) == 8, "8-byte fields only");
+    enum { SLOT = smem_edge_slot(FIELD) };
+    __device__ __forceinline__ T& operator[](int e) const
+    {
+        extern __shared__ __align__(16) unsigned char sz_c_edge_smem[];
+        return reinterpret_cast<T*>(sz_c_edge_smem)[(SLOT * 4 + e) * blockDim.x + threadIdx.x];
+    }
+};
+template <class T, int F> SZ_HD T rd4(const SmemArr4<T, F>& a, int e) { return a[e]; }
+template <class T, int F> SZ_HD void wr4(const SmemArr4<T, F>& a, int e, T v) { a[e] = v; }
+#define SZ_EDGE_FIELD(T, name, field) typename std::conditional<((SZ_C_SMEM_MASK >> (field)) & 1) != 0, SmemArr4<T, field>, T[4]>::type name
+#else
+#define SZ_EDGE_FIELD(T, name, field) T name[4]
+#endif
+
 // The sweep's two pieces of bulk storage, lent by the caller: the int64 outlines (ring p at [p*NV, p*NV + n[p]) of vxs/vys)
 // and the output record's deque (dqx/dqy, dcap entries).  It is handed down the (inlined) call chain by reference instead of
 // living in the sweep object: pointers read back from a struct in local memory lose their address space and every access
@@ -68,7 +101,8 @@ struct ConvexSweep {
     SZ_HD static i64 vyat(M m, int p, int i) { return m.vys[p * NV + i]; }
     int sw;                                   // slot q holds ring q ^ sw
     // current edge of every bound (clipper.cpp:66-84 TEdge, reduced like szclip::Edge)
-    i64 botx[4], boty[4], topx[4], topy[4], curx[4]; double dx[4]; int vi[4];      // vi: ring index of `top`
+    SZ_EDGE_FIELD(i64, botx, 0); SZ_EDGE_FIELD(i64, boty, 1); SZ_EDGE_FIELD(i64, topx, 2); SZ_EDGE_FIELD(i64, topy, 3); SZ_EDGE_FIELD(i64, curx, 4);
+    SZ_EDGE_FIELD(double, dx, 5); int vi[4];      // vi: ring index of `top`
     i64 cur_y;                                // Curr.Y of every active edge = bottom of the current scanbeam
     unsigned ordp; int na;                    // AEL left to right: nibble k of ordp is the edge id at position k
     unsigned act, f_right, f_out, f_wc2, f_last, f_back;    // bit id: in the AEL / Side == right / OutIdx >= 0 /
