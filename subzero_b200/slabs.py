@@ -34,23 +34,47 @@ N_STATE = 14          # gid, floe_num, x, y, root_x, root_y, rmax, h, area, u, v
 
 
 # ------------------------------------------------------------------------------------------------ host-side layout
-def slab_of(x, Lx, world):
-    w = 2.0 * Lx / world
-    s = np.floor((np.asarray(x) + Lx) / w)
-    s = np.where(np.isnan(s), 0, s)
-    return np.clip(s, 0, world - 1).astype(np.int64)
+def slab_edges(x, Lx, world, balance=False):
+    """interior slab edges [world - 1] over [-Lx, Lx): equal widths, or (balance) the quantiles of the centroids, so that
+    every rank owns the same number of floes when the density is not uniform (the halo logic only needs each
+    rank's entries to be contiguous in x)"""
+    x = np.asarray(x, np.float64)
+    xs = np.sort(x[~np.isnan(x)])
+    if not balance or xs.shape[0] == 0:
+        return -Lx + (2.0 * Lx / world) * np.arange(1, world)
+    n = xs.shape[0]
+    return np.array([xs[min(n - 1, (k * n) // world)] for k in range(1, world)])
 
 
-def sort_by_slab(soa, Lx, world):
-    """Renumber the floes slab by slab (stable).  Returns (permuted FloesSoA, id_start [world+1])."""
-    slab = slab_of(soa.x, Lx, world)
-    order = np.argsort(slab, kind="stable")
+def slab_of(x, Lx, world, edges=None):
+    """slab index of a centroid: equal-width slabs, or the slabs between `edges` (a floe on an edge belongs to the upper slab)"""
+    if edges is None:
+        w = 2.0 * Lx / world
+        s = np.floor((np.asarray(x) + Lx) / w)
+        s = np.where(np.isnan(s), 0, s)
+        return np.clip(s, 0, world - 1).astype(np.int64)
+    x = np.asarray(x, np.float64)
+    s = np.searchsorted(np.asarray(edges, np.float64), x, side="right")
+    return np.where(np.isnan(x), 0, s).astype(np.int64)
+
+
+def select(soa, order):
+    """the floes `order` (indices) of a FloesSoA, in that order, with their outlines"""
+    order = np.asarray(order, np.int64)
     nv = (soa.voff[1:] - soa.voff[:-1]).astype(np.int64)
     new_nv = nv[order]
-    new_off = np.zeros(soa.n + 1, np.int64)
+    new_off = np.zeros(order.shape[0] + 1, np.int64)
     np.cumsum(new_nv, out=new_off[1:])
     idx = np.repeat(soa.voff[:-1].astype(np.int64)[order] - new_off[:-1], new_nv) + np.arange(int(new_off[-1]))
-    out = abi.FloesSoA(*(getattr(soa, k)[order] for k in abi.FloesSoA.FIELDS), soa.alive[order], new_off.astype(np.int32), soa.vx[idx], soa.vy[idx])
+    return abi.FloesSoA(*(getattr(soa, k)[order] for k in abi.FloesSoA.FIELDS), soa.alive[order], new_off.astype(np.int32), soa.vx[idx], soa.vy[idx])
+
+
+def sort_by_slab(soa, Lx, world, balance=False):
+    """Renumber the floes slab by slab (stable).  Returns (permuted FloesSoA, id_start [world+1]).  balance: slab edges at
+    the quantiles of the centroids instead of equal widths."""
+    slab = slab_of(soa.x, Lx, world, slab_edges(soa.x, Lx, world, True) if balance else None)
+    order = np.argsort(slab, kind="stable")
+    out = select(soa, order)
     starts = np.searchsorted(slab[order], np.arange(world + 1), side="left").astype(np.int64)
     return out, starts
 

@@ -18,12 +18,23 @@ from subzero_b200 import slabs
 N_FLOES, SEED = 1200, 21
 
 
-def _worker(rank, world, port, outdir, periodic):
+def _field(world, balance):
+    """the test field renumbered slab by slab.  balance: a field of non-uniform density (three quarters of the floes east
+    of x = 0 removed) cut at the quantiles of the centroids instead of at equal widths"""
+    prm, field = sz.voronoi_field(N_FLOES, seed=SEED)
+    if balance:
+        keep = np.nonzero((field.x < 0) | (np.arange(field.n) % 4 == 0))[0]
+        field = slabs.select(field, keep)
+    field, starts = slabs.sort_by_slab(field, prm.Lx, world, balance=balance)
+    return prm, field, starts
+
+
+def _worker(rank, world, port, outdir, periodic, balance=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        prm, field = sz.voronoi_field(N_FLOES, seed=SEED)
-        field, starts = slabs.sort_by_slab(field, prm.Lx, world)
+        prm, field, starts = _field(world, balance)
+        N_FLOES = field.n
         mine = slabs.take_range(field, int(starts[rank]), int(starts[rank + 1]))
         st = slabs.SlabState.from_soa(mine, int(starts[rank]), N_FLOES, torch.device("cpu"))
         comm = slabs.Comm(dist, rank, world, torch.device("cpu"))
@@ -49,13 +60,18 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,periodic", [(2, True), (3, True), (2, False)])
-def test_local_lists_reproduce_the_global_extended_list(tmp_path, world, periodic):
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), periodic), nprocs=world, join=True)
+@pytest.mark.parametrize("world,periodic,balance", [(2, True, False), (3, True, False), (2, False, False), (3, True, True)])
+def test_local_lists_reproduce_the_global_extended_list(tmp_path, world, periodic, balance):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), periodic, balance), nprocs=world, join=True)
     R = [np.load(tmp_path / ("r%d.npz" % r)) for r in range(world)]
-    prm, field = sz.voronoi_field(N_FLOES, seed=SEED)
+    prm, field, starts = _field(world, balance)
+    N_FLOES = field.n
     prm.periodic = int(periodic)
-    field, starts = slabs.sort_by_slab(field, prm.Lx, world)
+    if balance:
+        # slabs cut at the quantiles: equal floe counts although the eastern half holds a quarter of the density
+        assert np.diff(starts).max() - np.diff(starts).min() <= 1 and N_FLOES < 0.7 * 1200
+        width = np.array([field.x[starts[k]:starts[k + 1]].max() - field.x[starts[k]:starts[k + 1]].min() for k in range(world)])
+        assert width.max() > 1.5 * width.min()
     ref = oracle.OracleStep(prm, field, broad_mode=0)
     n0, n = ref.summary.n0, ref.summary.n
     g = ref.ghosts()
@@ -98,7 +114,7 @@ def test_local_lists_reproduce_the_global_extended_list(tmp_path, world, periodi
     for k, r in enumerate(R):
         owner[r["gid"][r["owned"] != 0]] = k
     have = [set(r["gid"].tolist()) for r in R]
-    assert len(pr["i"]) > 4 * N_FLOES
+    assert len(pr["i"]) > (1.5 if balance else 4) * N_FLOES
     straddling = 0
     for i, j in zip(pr["i"] - 1, pr["j"] - 1):
         for k in {owner[i], owner[j]}:
@@ -107,7 +123,7 @@ def test_local_lists_reproduce_the_global_extended_list(tmp_path, world, periodi
     assert straddling > 0
     # the halo is a thin layer, not the whole field
     for r in R:
-        assert (r["owned"] == 0).sum() < 0.45 * len(r["gid"])
+        assert (r["owned"] == 0).sum() < (0.6 if balance else 0.45) * len(r["gid"])     # (balanced: 250 floes per rank in narrow slabs)
     # 3. kill/transfer fix-up across ranks == the serial loop of floe_interactions_all.m:175-179
     kill_all = np.zeros(n, np.int64)
     for r in R:
@@ -121,7 +137,7 @@ def test_local_lists_reproduce_the_global_extended_list(tmp_path, world, periodi
     got_t = np.concatenate([r["transfer"] for r in R])
     np.testing.assert_array_equal(got_k, kill_all[:n0])
     np.testing.assert_array_equal(got_t, transfer)
-    assert (transfer > 0).sum() > 3
+    assert (transfer > 0).sum() > (1 if balance else 3)
 
 
 def test_sort_by_slab_is_a_stable_renumbering():
@@ -136,3 +152,10 @@ def test_sort_by_slab_is_a_stable_renumbering():
     assert x[0] == x[-1] and len(x) == out.voff[i + 1] - out.voff[i]
     one = slabs.take_range(out, int(starts[1]), int(starts[2]))
     assert one.n == starts[2] - starts[1] and one.voff[0] == 0 and one.voff[-1] == one.vx.shape[0]
+    # balanced cuts: the same floes, equal counts, a floe on an edge goes to the upper slab, NaN centroids to slab 0
+    bal, bstarts = slabs.sort_by_slab(field, prm.Lx, 4, balance=True)
+    assert list(np.diff(bstarts)) == [125, 125, 125, 125] and np.isclose(bal.area.sum(), field.area.sum())
+    edges = slabs.slab_edges(field.x, prm.Lx, 4, balance=True)
+    assert np.all(np.diff(slabs.slab_of(bal.x, prm.Lx, 4, edges)) >= 0)
+    assert list(slabs.slab_of([edges[0], np.nan, -prm.Lx, prm.Lx], prm.Lx, 4, edges)) == [1, 0, 0, 3]
+    assert np.allclose(slabs.slab_edges(field.x, prm.Lx, 4), [-prm.Lx / 2, 0, prm.Lx / 2])
