@@ -2,10 +2,12 @@
 // parity tests against the oracle (test infrastructure; the product never runs this on the CPU).
 #include "../../subzero_b200/csrc/sz_pairforce.cuh"
 #include "../../subzero_b200/csrc/sz_corners.cuh"
+#include "../../subzero_b200/csrc/sz_euler.cuh"
 #include "../../include/subzero_b200.h"
 #include <vector>
 #include <memory>
 #include <cstring>
+#include <algorithm>
 
 using namespace szpf;
 typedef szclip::ClipCaps<2600, 1300, 10000, 2600, 10000, 2600, 512, 3900> BigClip;
@@ -112,4 +114,66 @@ extern "C" int szport_corner_mask(const SzFloesSoA* f, const int64_t* row_off64,
     for (int q = 0; q < count; ++q) szcorn::corner_mask_floe<1>(a, q, 0, 1u);
     for (int q = 0; q <= count; ++q) da_off[q] = off[q];
     return off[count];
+}
+
+// calc_eulerian_data.m: the product's item / reduction code (sz_euler.cuh) over the list and the items built here the way
+// the device kernels build them (list: alive floes, x images, the stale-polygon y pass; items floe by floe, stable sort
+// by cell).  Same signature as the checker's entry point.  Returns 0, -1 (Nb != 0), -2 (Clipper failure), -3 (cell_range
+// missed a candidate: a bug), -4 (capacity).
+extern "C" int szport_calc_eulerian_data(const SzFloesSoA* f, const double* mass, const double* overlap_area, const double* dUi_p, const double* dVi_p,
+                                         const double* stress, const double* strain, int Nx, int Ny, int Nb,
+                                         double xmin, double xmax, double ymin, double ymax, int periodic, double* out)
+{
+    if (Nb != 0) return -1;
+    std::vector<int> lsrc; std::vector<double> lx, ly;
+    for (int i = 0; i < f->n; ++i) if (f->alive[i]) { lsrc.push_back(i); lx.push_back(f->x[i]); ly.push_back(f->y[i]); }
+    const double Lx = xmax, Ly = ymax;
+    auto sgn = [](double v) { return (double)((v > 0) - (v < 0)); };
+    if (periodic && !lsrc.empty()) {
+        const size_t n1 = lsrc.size();
+        double last_my = 0;
+        for (size_t i = 0; i < n1; ++i) {
+            const int s = lsrc[i]; double mx = 0, my = 0;
+            for (int t = f->voff[s]; t < f->voff[s + 1]; ++t) { mx = std::max(mx, fabs(f->vx[t] + lx[i])); my = std::max(my, fabs(f->vy[t] + ly[i])); }
+            last_my = my;
+            if (mx > Lx) { lsrc.push_back(s); lx.push_back(lx[i] - 2 * Lx * sgn(lx[i])); ly.push_back(ly[i]); }
+        }
+        const size_t n2 = lsrc.size();
+        if (last_my > Ly) for (size_t i = 0; i < n2; ++i) { lsrc.push_back(lsrc[i]); lx.push_back(lx[i]); ly.push_back(ly[i] - 2 * Ly * sgn(ly[i])); }
+    }
+    const size_t cells = (size_t)Nx * Ny;
+    for (size_t k = 0; k < szeul::N_OUT * cells; ++k) out[k] = 0;
+    szeul::EulerArgs a; memset(&a, 0, sizeof(a));
+    a.g.Nx = Nx; a.g.Ny = Ny; a.g.xmin = xmin; a.g.xmax = xmax; a.g.ymin = ymin; a.g.ymax = ymax;
+    a.n_list = (int)lsrc.size(); a.lsrc = lsrc.data(); a.lx = lx.data(); a.ly = ly.data();
+    a.rmax = f->rmax; a.area = f->area; a.h = f->h; a.u = f->u; a.v = f->v;
+    a.mass = mass; a.over = overlap_area; a.dU = dUi_p; a.dV = dVi_p; a.stress = stress; a.strain = strain;
+    a.voff = f->voff; a.vx = f->vx; a.vy = f->vy; a.out = out;
+    std::vector<int> item_cell, item_q;
+    for (int q = 0; q < a.n_list; ++q) {
+        int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+        const bool any = szeul::cell_range(a, q, i0, i1, j0, j1);
+        for (int jj = 0; jj < Ny; ++jj) for (int ii = 0; ii < Nx; ++ii) {
+            if (!szeul::is_candidate(a, q, ii, jj)) continue;
+            if (!any || ii < i0 || ii > i1 || jj < j0 || jj > j1) return -3;
+        }
+        if (!any) continue;
+        for (int jj = j0; jj <= j1; ++jj) for (int ii = i0; ii <= i1; ++ii) if (szeul::is_candidate(a, q, ii, jj)) { item_cell.push_back(jj * Nx + ii); item_q.push_back(q); }
+    }
+    const int n_items = (int)item_cell.size();
+    std::vector<double> item_area(n_items, 0.0); std::vector<int> item_status(n_items, 0), sorted(n_items), cell_off(cells + 1, 0);
+    a.n_items = n_items; a.item_cell = item_cell.data(); a.item_q = item_q.data(); a.item_area = item_area.data(); a.item_status = item_status.data();
+    std::unique_ptr<Workspace<BigPair>> w(new Workspace<BigPair>);
+    for (int k = 0; k < n_items; ++k) {
+        const int st = szeul::item_area(w->eng, a, k, item_area[k]);
+        if (st == PS_CLIPPER_FAIL) return -2;
+        if (st != PS_OK) return -4;
+    }
+    for (int k = 0; k < n_items; ++k) sorted[k] = k;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](int p, int q) { return item_cell[p] < item_cell[q]; });
+    for (int k = 0; k < n_items; ++k) ++cell_off[item_cell[k] + 1];
+    for (size_t c = 0; c < cells; ++c) cell_off[c + 1] += cell_off[c];
+    a.sorted = sorted.data(); a.cell_off = cell_off.data();
+    for (size_t c = 0; c < cells; ++c) szeul::cell_reduce(a, (int)c);
+    return 0;
 }
