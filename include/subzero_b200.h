@@ -267,6 +267,21 @@ int sz_get_fracture_deform(SzContext* ctx, uint8_t* changed, double* xi, double*
 int sz_corner_mask(SzContext* ctx, int32_t count, const int32_t* floe_idx, int32_t nb_skip, int64_t* n_verts);
 int sz_get_corner_mask(SzContext* ctx, int64_t* da_off, uint8_t* da);
 
+/* ---- calc_eulerian_data.m, mass-weighted averages of the floe state on an Nx x Ny grid over
+ * [xmin, xmax] x [ymin, ymax] (= c2_boundary's extent; Lx = xmax, Ly = ymax like :28-29).  Uses the resident floes (positions,
+ * outlines, rmax, area, h, Ui, Vi, alive; after sz_trajectory_step when the device integrates) and the per-floe arrays the
+ * caller passes (host or device memory, [n0]; stress and strain [n0][4] = (1,1) (1,2) (2,1) (2,2); NULL = zeros; mass is
+ * required).  As written in the reference: dead floes dropped (:7-8), x images for floes poking through +-Lx when periodic
+ * (:39-48), the y pass that tests the LAST floe's polygon for everybody (:56-65), rows from ymax down (:72), a cell is
+ * processed when the masses of its candidate floes sum to > 0 (:113-131), Aover = area of the Clipper-exact intersection of
+ * the cell with the floe (:134-147), sums over ascending list position (:149-187), largest eigenvalue of the averaged stress
+ * (:170-173).  Boundary floes (Nb > 0, :11-25) are not supported (SZ_ERR_ARG).
+ * out: 18 planes of Ny*Nx doubles (host or device memory), element (jj, ii) at jj*Nx + ii with jj = 0 the TOP row, in the order
+ *   u v du dv stress stressxx stressyx stressxy stressyy strainux strainvx strainuy strainvy c Over Mtot area h */
+int sz_eulerian_data(SzContext* ctx, int32_t Nx, int32_t Ny, double xmin, double xmax, double ymin, double ymax, int32_t periodic,
+                     const double* mass, const double* overlap_area, const double* dUi_p, const double* dVi_p, const double* stress, const double* strain,
+                     double* out);
+
 /* diagnostic: device time (CUDA events, ms) of the last step by phase:
  * [0] ghost floes (floe_interactions_all.m:16-66)   [1] broad phase (:68-120)
  * [2] narrow phase + force law (:125-174)           [3] mirror/torque/sums (:186-265)   [4] whole step */

@@ -180,6 +180,23 @@ class ContactContext:
         assert off[n] == nv.value
         return [da[off[k]:off[k + 1]].copy() for k in range(n)]
 
+    # ---- calc_eulerian_data.m: coarse-grid averages of the resident floe state
+    EULERIAN_FIELDS = ("u", "v", "du", "dv", "stress", "stressxx", "stressyx", "stressxy", "stressyy", "strainux", "strainvx", "strainuy", "strainvy",
+                       "c", "Over", "Mtot", "area", "h")
+
+    def eulerian_data(self, mass, Nx, Ny, box, periodic, overlap_area=None, dUi_p=None, dVi_p=None, stress=None, strain=None):
+        """box = (xmin, xmax, ymin, ymax) of c2_boundary; mass [n0]; stress / strain [n0][4]; None = zeros.  Returns a dict of
+        (Ny, Nx) arrays, row 0 = the top row (the reference flips y)"""
+        n = self._n0
+        opt = lambda a, shape: None if a is None else np.ascontiguousarray(np.asarray(a, np.float64).reshape(shape))
+        mass = np.ascontiguousarray(np.asarray(mass, np.float64).reshape(n))
+        ov, du, dv, st, en = opt(overlap_area, n), opt(dUi_p, n), opt(dVi_p, n), opt(stress, (n, 4)), opt(strain, (n, 4))
+        out = np.zeros((18, int(Ny), int(Nx)))
+        p, D = abi._ptr, abi.c_dp
+        abi.check(abi.lib().sz_eulerian_data(self._h, int(Nx), int(Ny), *(float(b) for b in box), int(bool(periodic)),
+                                             p(mass, D), p(ov, D), p(du, D), p(dv, D), p(st, D), p(en, D), p(out, D)))
+        return {k: out[i] for i, k in enumerate(self.EULERIAN_FIELDS)}
+
     # ---- ocean / atmosphere forcing (calc_trajectory.m:94-166) and strain (:224-234)
     def trajectory_set_ocean(self, Xo, Yo, Uocn, Vocn, Uwinds, Vwinds, fCoriolis, turn_angle, rho0=0.0, Cd=0.0, rho_air=0.0, Cd_atm=0.0):
         """Xo [nx], Yo [ny]; the four fields as (ny, nx) arrays like ocean.Uocn / winds.u in MATLAB"""

@@ -20,6 +20,7 @@
 #include "../../include/subzero_b200.h"
 #include "sz_narrow.cuh"
 #include "sz_corners.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -87,6 +88,7 @@ struct Counters {
     int n_forced, n_no_points;     // ocean forcing: floes evaluated / floes without a Monte-Carlo point inside
     int fr_vert_used, fr_changed;  // fracture deformation: vertices of the new outlines, floes changed
     int cr_n1, cr_n;               // corners.m's own periodic list: sizes after the x pass / after the y pass
+    int eu_n1, eu_n2, eu_n, eu_yflag, eu_listL, eu_fail, eu_cap;   // calc_eulerian_data: list sizes (alive, + x images, + y images), the stale-polygon flag, class L items, failures
 };
 
 struct SzContext {
@@ -140,6 +142,8 @@ struct SzContext {
     DBuf<int> fr_idx, fr_vstart, fr_vcount, fr_status; DBuf<uint8_t> fr_changed; DBuf<double> fr_xi, fr_yi, fr_area, fr_vx, fr_vy; int fr_count = 0; i64 fr_verts = 0; bool have_fr = false;
     // corner mask (corners.m:10-88)
     DBuf<int> cr_idx, cr_nv, cr_off, cr_esrc; DBuf<uint8_t> cr_da, cr_ealive; DBuf<double> cr_ex, cr_ey; int cr_count = 0; i64 cr_verts = 0; bool have_cr = false;
+    // coarse-grid averages (calc_eulerian_data.m)
+    DBuf<int> eu_lsrc, eu_icnt, eu_ioff, eu_cell, eu_q, eu_status, eu_iota, eu_sorted, eu_keys, eu_ccnt, eu_coff, eu_listL; DBuf<double> eu_lx, eu_ly, eu_in, eu_area, eu_out; DBuf<uint8_t> eu_tmp;
     // ocean / atmosphere forcing (calc_trajectory.m:94-166)
     DBuf<double> oc_Xo, oc_Yo, oc_U, oc_V, oc_Wu, oc_Wv, pt_x, pt_y, t_strain; DBuf<uint8_t> pt_a, t_forced;
     int oc_nx = 0, oc_ny = 0, npts = 0; bool have_ocean = false, have_points = false, traj_do_int = false;
@@ -832,15 +836,15 @@ extern "C" void sz_destroy(SzContext* c)
     DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi,
                           &c->oc_Xo, &c->oc_Yo, &c->oc_U, &c->oc_V, &c->oc_Wu, &c->oc_Wv, &c->pt_x, &c->pt_y, &c->t_strain,
-                          &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy, &c->cr_ex, &c->cr_ey};
+                          &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy, &c->cr_ex, &c->cr_ey, &c->eu_lx, &c->eu_ly, &c->eu_in, &c->eu_area, &c->eu_out};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
                        &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->stage, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
-                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status, &c->cr_idx, &c->cr_nv, &c->cr_off, &c->cr_esrc};
+                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status, &c->cr_idx, &c->cr_nv, &c->cr_off, &c->cr_esrc, &c->eu_lsrc, &c->eu_icnt, &c->eu_ioff, &c->eu_cell, &c->eu_q, &c->eu_status, &c->eu_iota, &c->eu_sorted, &c->eu_keys, &c->eu_ccnt, &c->eu_coff, &c->eu_listL};
     for (auto* b : ib) b->release();
-    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed, &c->cr_da, &c->cr_ealive};
+    DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed, &c->cr_da, &c->cr_ealive, &c->eu_tmp};
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
     for (auto* b : lb) b->release();
@@ -1978,6 +1982,190 @@ extern "C" int sz_get_corner_mask(SzContext* c, int64_t* da_off, uint8_t* da)
     CK(cudaStreamSynchronize(c->stream));
     return SZ_OK;
 }
+// ------------------------------------------------------------------------------------------------ coarse-grid averages
+// calc_eulerian_data.m:7-65, the floe list: dead floes dropped (:7-8), an x image for every floe with a vertex beyond +-Lx
+// (:39-48), and the y pass as written (:56-65): it tests the polygon left over from the LAST iteration of the x loop, so
+// either every entry (x images included) gets a y image or none does.
+__global__ void euler_alive_kernel(int n0, const uint8_t* __restrict__ alive, int* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n0) flag[i] = alive[i] ? 1 : 0;
+}
+__global__ void euler_list_init_kernel(int n0, const int* __restrict__ flag, const int* __restrict__ pos, const double* __restrict__ x, const double* __restrict__ y,
+                                       int* __restrict__ lsrc, double* __restrict__ lx, double* __restrict__ ly, int* __restrict__ n_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_out = pos[n0];
+    if (i >= n0 || !flag[i]) return;
+    const int g = pos[i];
+    lsrc[g] = i; lx[g] = x[i]; ly[g] = y[i];
+}
+__global__ void euler_xflag_kernel(int n_bound, const int* __restrict__ n_dev, const int* __restrict__ lsrc, const double* __restrict__ lx, const double* __restrict__ ly,
+                                   const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, double Lx, double Ly,
+                                   int* __restrict__ flag, int* __restrict__ yflag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bound) return;
+    const int n = *n_dev;
+    int f = 0;
+    if (i < n) {
+        const int s = lsrc[i];
+        double mx = 0, my = 0;
+        for (int t = voff[s]; t < voff[s + 1]; ++t) { const double a = fabs(vx[t] + lx[i]), b = fabs(vy[t] + ly[i]); if (a > mx) mx = a; if (b > my) my = b; }
+        f = (mx > Lx);
+        if (i == n - 1) *yflag = (my > Ly) ? 1 : 0;
+    }
+    flag[i] = f;
+}
+__global__ void euler_xemit_kernel(int n_bound, const int* __restrict__ n_dev, const int* __restrict__ flag, const int* __restrict__ pos,
+                                   int* __restrict__ lsrc, double* __restrict__ lx, double* __restrict__ ly, double Lx, int* __restrict__ n_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *n_dev;
+    if (i == 0) *n_out = n + pos[n_bound];
+    if (i >= n || !flag[i]) return;
+    const int g = n + pos[i];
+    lsrc[g] = lsrc[i]; lx[g] = lx[i] - 2 * Lx * sgn_d(lx[i]); ly[g] = ly[i];
+}
+__global__ void euler_yemit_kernel(int n_bound, const int* __restrict__ n_dev, const int* __restrict__ yflag,
+                                   int* __restrict__ lsrc, double* __restrict__ lx, double* __restrict__ ly, double Ly, int* __restrict__ n_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *n_dev, yf = *yflag;
+    if (i == 0) *n_out = yf ? 2 * n : n;
+    if (i >= n_bound || i >= n || !yf) return;
+    const int g = n + i;
+    lsrc[g] = lsrc[i]; lx[g] = lx[i]; ly[g] = ly[i] - 2 * Ly * sgn_d(ly[i]);
+}
+// items: the candidate cells of every list entry (:113-119), entry by entry
+__global__ void euler_item_count_kernel(const szeul::EulerArgs a, int* __restrict__ icnt)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n_list) return;
+    int i0, i1, j0, j1, c = 0;
+    if (szeul::cell_range(a, q, i0, i1, j0, j1))
+        for (int jj = j0; jj <= j1; ++jj) for (int ii = i0; ii <= i1; ++ii) c += szeul::is_candidate(a, q, ii, jj) ? 1 : 0;
+    icnt[q] = c;
+}
+__global__ void euler_item_fill_kernel(const szeul::EulerArgs a, const int* __restrict__ ioff, int* __restrict__ item_cell, int* __restrict__ item_q, int* __restrict__ cell_cnt)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n_list) return;
+    int i0, i1, j0, j1, k = ioff[q];
+    if (szeul::cell_range(a, q, i0, i1, j0, j1))
+        for (int jj = j0; jj <= j1; ++jj) for (int ii = i0; ii <= i1; ++ii)
+            if (szeul::is_candidate(a, q, ii, jj)) { const int cell = jj * a.g.Nx + ii; item_cell[k] = cell; item_q[k] = q; ++k; atomicAdd(&cell_cnt[cell], 1); }
+}
+__global__ void euler_iota_kernel(int n, int* __restrict__ v) { const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < n) v[k] = k; }
+__global__ void euler_status_kernel(int n, const int* __restrict__ status, int* __restrict__ n_fail, int* __restrict__ n_cap)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || status[k] == 0) return;
+    atomicAdd(status[k] == szpf::PS_CLIPPER_FAIL ? n_fail : n_cap, 1);
+}
+__global__ void euler_cell_kernel(const szeul::EulerArgs a)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell < a.g.Nx * a.g.Ny) szeul::cell_reduce(a, cell);
+}
+
+extern "C" int sz_eulerian_data(SzContext* c, int32_t Nx, int32_t Ny, double xmin, double xmax, double ymin, double ymax, int32_t periodic,
+                                const double* mass, const double* overlap_area, const double* dUi_p, const double* dVi_p, const double* stress, const double* strain,
+                                double* out)
+{
+    if (!c) { sz_set_error("sz_eulerian_data: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_input || c->ext_mode) { sz_set_error("sz_eulerian_data: upload the floes first (single-GPU list)"); return SZ_ERR_STATE; }
+    if (Nx < 1 || Ny < 1 || (i64)Nx * Ny > (1 << 24) || !mass || !out) { sz_set_error("sz_eulerian_data: bad arguments (1 <= Nx*Ny <= 2^24, mass and out required)"); return SZ_ERR_ARG; }
+    if (c->prm.Nb != 0) { sz_set_error("sz_eulerian_data: boundary floes (Nb > 0, calc_eulerian_data.m:11-25) are not supported"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int n0 = c->n0, cells = Nx * Ny;
+    CK(c->eu_out.ensure((size_t)szeul::N_OUT * cells + 1));
+    CK(cudaMemsetAsync(c->eu_out.p, 0, (size_t)szeul::N_OUT * cells * 8, st));
+    auto finish = [&]() -> int { CK(cudaMemcpyAsync(out, c->eu_out.p, (size_t)szeul::N_OUT * cells * 8, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st)); return SZ_OK; };
+    if (n0 == 0) return finish();
+    // ---- per-floe state the caller supplies (host or device memory); NULL = zeros
+    CK(c->eu_in.ensure(12 * (size_t)n0 + 1));
+    CK(cudaMemsetAsync(c->eu_in.p, 0, 12 * (size_t)n0 * 8, st));
+    double* d_mass = c->eu_in.p; double* d_over = d_mass + n0; double* d_dU = d_over + n0; double* d_dV = d_dU + n0; double* d_stress = d_dV + n0; double* d_strain = d_stress + 4 * (size_t)n0;
+    CK(cudaMemcpyAsync(d_mass, mass, (size_t)n0 * 8, cudaMemcpyDefault, st));
+    if (overlap_area) CK(cudaMemcpyAsync(d_over, overlap_area, (size_t)n0 * 8, cudaMemcpyDefault, st));
+    if (dUi_p) CK(cudaMemcpyAsync(d_dU, dUi_p, (size_t)n0 * 8, cudaMemcpyDefault, st));
+    if (dVi_p) CK(cudaMemcpyAsync(d_dV, dVi_p, (size_t)n0 * 8, cudaMemcpyDefault, st));
+    if (stress) CK(cudaMemcpyAsync(d_stress, stress, 4 * (size_t)n0 * 8, cudaMemcpyDefault, st));
+    if (strain) CK(cudaMemcpyAsync(d_strain, strain, 4 * (size_t)n0 * 8, cudaMemcpyDefault, st));
+    // ---- the list
+    const size_t lcap = 4 * (size_t)n0 + 1;
+    CK(c->eu_lsrc.ensure(lcap)); CK(c->eu_lx.ensure(lcap)); CK(c->eu_ly.ensure(lcap));
+    CK(c->flag.ensure(2 * (size_t)n0 + 2)); CK(c->pos.ensure(2 * (size_t)n0 + 2)); CK(c->scan_tmp.ensure(scan_tmp_ints(std::max<size_t>(lcap + 2, (size_t)cells + 2))));
+    CK(cudaMemsetAsync(D_CNT(eu_n1), 0, 7 * sizeof(int), st));             // eu_n1 .. eu_cap
+    ++g_launches; euler_alive_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->alive.p, c->flag.p);
+    exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+    ++g_launches; euler_list_init_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->flag.p, c->pos.p, c->x.p, c->y.p, c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, D_CNT(eu_n1));
+    if (periodic) {
+        ++g_launches; euler_xflag_kernel<<<nblk(n0, 128), 128, 0, st>>>(n0, D_CNT(eu_n1), c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, c->voff.p, c->vx.p, c->vy.p, xmax, ymax, c->flag.p, D_CNT(eu_yflag));
+        exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+        ++g_launches; euler_xemit_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, D_CNT(eu_n1), c->flag.p, c->pos.p, c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, xmax, D_CNT(eu_n2));
+        ++g_launches; euler_yemit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(2 * n0, D_CNT(eu_n2), D_CNT(eu_yflag), c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, ymax, D_CNT(eu_n));
+    } else {
+        CK(cudaMemcpyAsync(D_CNT(eu_n), D_CNT(eu_n1), sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    const int n_list = c->h_cnt->eu_n;
+    if (n_list <= 0) return finish();
+    // ---- items
+    szeul::EulerArgs a; memset(&a, 0, sizeof(a));
+    a.g.Nx = Nx; a.g.Ny = Ny; a.g.xmin = xmin; a.g.xmax = xmax; a.g.ymin = ymin; a.g.ymax = ymax;
+    a.n_list = n_list; a.lsrc = c->eu_lsrc.p; a.lx = c->eu_lx.p; a.ly = c->eu_ly.p;
+    a.rmax = c->rmax.p; a.area = c->area.p; a.h = c->h.p; a.u = c->u.p; a.v = c->v.p;
+    a.mass = d_mass; a.over = d_over; a.dU = d_dU; a.dV = d_dV; a.stress = d_stress; a.strain = d_strain;
+    a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p; a.out = c->eu_out.p;
+    CK(c->eu_icnt.ensure((size_t)n_list + 2)); CK(c->eu_ioff.ensure((size_t)n_list + 2));
+    CK(c->eu_ccnt.ensure((size_t)cells + 2)); CK(c->eu_coff.ensure((size_t)cells + 2));
+    ++g_launches; euler_item_count_kernel<<<nblk(n_list, 128), 128, 0, st>>>(a, c->eu_icnt.p);
+    exclusive_scan(c->eu_icnt.p, n_list, c->eu_ioff.p, n_list + 1, c->scan_tmp.p, st);
+    CK(cudaGetLastError());
+    int n_items = 0;
+    CK(cudaMemcpyAsync(&n_items, c->eu_ioff.p + n_list, 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st));
+    if (n_items < 0) { sz_set_error("sz_eulerian_data: more than 2^31 (cell, floe) items"); return SZ_ERR_CAPACITY; }
+    if (n_items == 0) return finish();
+    CK(c->eu_cell.ensure((size_t)n_items + 1)); CK(c->eu_q.ensure((size_t)n_items + 1)); CK(c->eu_area.ensure((size_t)n_items + 1)); CK(c->eu_status.ensure((size_t)n_items + 1));
+    CK(c->eu_iota.ensure((size_t)n_items + 1)); CK(c->eu_sorted.ensure((size_t)n_items + 1)); CK(c->eu_keys.ensure((size_t)n_items + 1)); CK(c->eu_listL.ensure((size_t)n_items + 1));
+    CK(cudaMemsetAsync(c->eu_ccnt.p, 0, ((size_t)cells + 1) * 4, st));
+    ++g_launches; euler_item_fill_kernel<<<nblk(n_list, 128), 128, 0, st>>>(a, c->eu_ioff.p, c->eu_cell.p, c->eu_q.p, c->eu_ccnt.p);
+    a.n_items = n_items; a.item_cell = c->eu_cell.p; a.item_q = c->eu_q.p; a.item_area = c->eu_area.p; a.item_status = c->eu_status.p;
+    CK(cudaMemsetAsync(c->eu_status.p, 0, (size_t)n_items * 4, st)); CK(cudaMemsetAsync(c->eu_area.p, 0, (size_t)n_items * 8, st));
+    // ---- one clip per item: class S in local memory, whatever overflows its arena in class L
+    ++g_launches; sz_launch_euler_S(&a, c->eu_listL.p, D_CNT(eu_listL), st);
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    const int nL = c->h_cnt->eu_listL;
+    if (nL > 0) {
+        const int threadsL = std::min((nL + 63) / 64 * 64, 148 * 16);
+        CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
+        ++g_launches; sz_launch_euler_L(&a, c->eu_listL.p, D_CNT(eu_listL), c->scratchL.p, threadsL, st);
+        CK(cudaGetLastError());
+    }
+    ++g_launches; euler_status_kernel<<<nblk(n_items, 256), 256, 0, st>>>(n_items, c->eu_status.p, D_CNT(eu_fail), D_CNT(eu_cap));
+    // ---- items ordered by cell (stable: ascending list position inside a cell), cell offsets, reduction
+    ++g_launches; euler_iota_kernel<<<nblk(n_items, 256), 256, 0, st>>>(n_items, c->eu_iota.p);
+    int end_bit = 1; while ((1 << end_bit) < cells && end_bit < 31) ++end_bit;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->eu_cell.p, c->eu_keys.p, c->eu_iota.p, c->eu_sorted.p, n_items, 0, end_bit, st));
+    CK(c->eu_tmp.ensure(tmp_bytes + 16));
+    ++g_launches; CK(cub::DeviceRadixSort::SortPairs(c->eu_tmp.p, tmp_bytes, c->eu_cell.p, c->eu_keys.p, c->eu_iota.p, c->eu_sorted.p, n_items, 0, end_bit, st));
+    exclusive_scan(c->eu_ccnt.p, cells, c->eu_coff.p, cells + 1, c->scan_tmp.p, st);
+    a.sorted = c->eu_sorted.p; a.cell_off = c->eu_coff.p;
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    if (c->h_cnt->eu_fail > 0) { sz_set_error("Clipper Error. (%d cell-floe intersection(s) of sz_eulerian_data)", c->h_cnt->eu_fail); return SZ_ERR_CLIPPER; }
+    if (c->h_cnt->eu_cap > 0) { sz_set_error("sz_eulerian_data: %d outline(s) exceed the largest size class", c->h_cnt->eu_cap); return SZ_ERR_CAPACITY; }
+    ++g_launches; euler_cell_kernel<<<nblk(cells, 128), 128, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return finish();
+}
+
 // reorder (start, count) pools into item-major CSR
 static int export_paths(SzContext* c, int n_items, const int* d_item_start, const int* d_item_np, const int* d_status, const int* d_path_vstart, const int* d_path_len,
                         int n_pool_paths, const i64* d_px, const i64* d_py, int n_pool_verts,

@@ -15,6 +15,7 @@
 // ~40 s template instantiations build in parallel; sz_contact.cu calls the extern "C" launchers.
 #pragma once
 #include "sz_pairforce.cuh"
+#include "sz_euler.cuh"
 #include <cuda_runtime.h>
 
 namespace sznarrow {
@@ -354,6 +355,33 @@ __global__ void __launch_bounds__(64) clip_scratch_kernel(const ClipArgs a)
     const int n = *a.list_count;
     for (int t = tid; t < n; t += a.n_threads) resolve_clip<typename C::Clip>(a, a.list[t], w.eng);
 }
+// calc_eulerian_data.m:140-147, one (cell, floe) item per thread: the shared area by one Clipper sweep (sz_euler.cuh).
+// Class S keeps the arena in local memory; an item whose arena overflows is appended to the class L list.
+template <class CC>
+__global__ void __launch_bounds__(128) euler_item_local_kernel(const szeul::EulerArgs a, int* next_list, int* next_count)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_items) return;
+    szclip::ClipEngine<CC> eng;
+    double ar = 0;
+    const int st = szeul::item_area(eng, a, k, ar);
+    if (st == szpf::PS_CAPACITY && next_list) { const int t = atomicAdd(next_count, 1); next_list[t] = k; return; }
+    a.item_status[k] = st; a.item_area[k] = ar;
+}
+template <class C>
+__global__ void __launch_bounds__(64) euler_item_scratch_kernel(const szeul::EulerArgs a, const int* list, const int* list_count, void* scratch, int n_threads)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_threads) return;
+    szpf::Workspace<C>& w = reinterpret_cast<szpf::Workspace<C>*>(scratch)[tid];
+    const int n = *list_count;
+    for (int t = tid; t < n; t += n_threads) {
+        const int k = list[t];
+        double ar = 0;
+        const int st = szeul::item_area(w.eng, a, k, ar);
+        a.item_status[k] = st; a.item_area[k] = ar;
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace sznarrow
@@ -369,6 +397,8 @@ void sz_launch_clip_S(const sznarrow::ClipArgs* a, cudaStream_t stream);
 void sz_launch_clip_M(const sznarrow::ClipArgs* a, cudaStream_t stream);
 void sz_launch_clip_L(const sznarrow::ClipArgs* a, cudaStream_t stream);
 void sz_launch_fracture_L(const sznarrow::FractureArgs* a, cudaStream_t stream);
+void sz_launch_euler_S(const szeul::EulerArgs* a, int* next_list, int* next_count, cudaStream_t stream);
+void sz_launch_euler_L(const szeul::EulerArgs* a, const int* list, const int* list_count, void* scratch, int n_threads, cudaStream_t stream);
 size_t sz_workspace_bytes_M(void);
 size_t sz_workspace_bytes_L(void);
 }

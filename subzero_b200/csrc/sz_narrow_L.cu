@@ -20,3 +20,9 @@ extern "C" void sz_launch_fracture_L(const FractureArgs* a, cudaStream_t stream)
     const int tpb = 64;
     fracture_deform_kernel<PairL><<<(a->n_threads + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
 }
+extern "C" void sz_launch_euler_L(const szeul::EulerArgs* a, const int* list, const int* list_count, void* scratch, int n_threads, cudaStream_t stream)
+{
+    if (n_threads <= 0) return;
+    const int tpb = 64;
+    euler_item_scratch_kernel<PairL><<<(n_threads + tpb - 1) / tpb, tpb, 0, stream>>>(*a, list, list_count, scratch, n_threads);
+}

@@ -13,3 +13,9 @@ extern "C" void sz_launch_clip_S(const ClipArgs* a, cudaStream_t stream)
     const int tpb = 128;
     clip_local_kernel<ClipS><<<(a->count + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
 }
+extern "C" void sz_launch_euler_S(const szeul::EulerArgs* a, int* next_list, int* next_count, cudaStream_t stream)
+{
+    if (a->n_items <= 0) return;
+    const int tpb = 128;
+    euler_item_local_kernel<ClipS><<<(a->n_items + tpb - 1) / tpb, tpb, 0, stream>>>(*a, next_list, next_count);
+}

@@ -21,6 +21,9 @@
 //                                                      dalpha_p dksi_p stress(4xN) flags FxOA FyOA torqueOA strain(4xN)
 //                                                      cax cay (V x 1, the rotated c_alpha pool)
 //   d   = sz_resident_mex('fracture_deform', idx)      idx: floe numbers; d: changed xi yi area vert_off cx cy
+//   e   = sz_resident_mex('eulerian_data', g, st)      g: Nx Ny xmin xmax ymin ymax periodic; st: mass [overlap_area dUi_p dVi_p
+//                                                      (N x 1) stress strain (4 x N)]; e: the 18 Ny x Nx fields of
+//                                                      calc_eulerian_data.m (u v du dv stress ... c Over Mtot area h)
 //   m   = sz_resident_mex('corner_mask', idx, Nb)      idx: the selection Floe(~keep) of Subzero.m:348 as floe numbers;
 //                                                      m: da_off (numel(idx)+1), da (the mask of corners.m:54-88, one
 //                                                      entry per polyshape vertex of every selected floe)
@@ -245,6 +248,29 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         for (size_t k = 0; k <= m; ++k) mxGetPr(vo)[k] = (double)off[k];
         mxArray* vals[] = {ch, xi, yi, ar, vo, cx, cy};
         for (int k = 0; k < 7; ++k) mxSetFieldByNumber(out, 0, k, vals[k]);
+        plhs[0] = out;
+        return;
+    }
+    if (cmd == "eulerian_data") {
+        if (nrhs < 3) mexErrMsgIdAndTxt("subzero_b200:arg", "usage: e = sz_resident_mex('eulerian_data', g, st)");
+        const int Nx = (int)scalar_field(prhs[1], "Nx", 0, true), Ny = (int)scalar_field(prhs[1], "Ny", 0, true);
+        if (Nx < 1 || Ny < 1) mexErrMsgIdAndTxt("subzero_b200:arg", "Nx and Ny must be positive");
+        const double xmin = scalar_field(prhs[1], "xmin", 0, true), xmax = scalar_field(prhs[1], "xmax", 0, true);
+        const double ymin = scalar_field(prhs[1], "ymin", 0, true), ymax = scalar_field(prhs[1], "ymax", 0, true);
+        const int periodic = scalar_field(prhs[1], "periodic", 0, false) != 0;
+        const double* mass = mxGetPr(need_field(prhs[2], "mass", g_n));
+        std::vector<double> planes((size_t)18 * Nx * Ny);
+        check(sz_eulerian_data(g_ctx, Nx, Ny, xmin, xmax, ymin, ymax, periodic, mass, opt_field(prhs[2], "overlap_area", g_n), opt_field(prhs[2], "dUi_p", g_n),
+                               opt_field(prhs[2], "dVi_p", g_n), opt_field(prhs[2], "stress", 4 * g_n), opt_field(prhs[2], "strain", 4 * g_n), planes.data()));
+        const char* names[] = {"u", "v", "du", "dv", "stress", "stressxx", "stressyx", "stressxy", "stressyy", "strainux", "strainvx", "strainuy", "strainvy",
+                               "c", "Over", "Mtot", "area", "h"};
+        mxArray* out = mxCreateStructMatrix(1, 1, 18, names);
+        for (int k = 0; k < 18; ++k) {
+            mxArray* m = mxCreateDoubleMatrix(Ny, Nx, mxREAL);        // column-major Ny x Nx from the row-major planes
+            double* d = mxGetPr(m);
+            for (int jj = 0; jj < Ny; ++jj) for (int ii = 0; ii < Nx; ++ii) d[(size_t)ii * Ny + jj] = planes[((size_t)k * Ny + jj) * Nx + ii];
+            mxSetFieldByNumber(out, 0, k, m);
+        }
         plhs[0] = out;
         return;
     }

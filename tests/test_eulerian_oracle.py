@@ -1,5 +1,6 @@
-"""calc_eulerian_data.m: the oracle's restatement against hand-derived answers.  CPU only: the device
-path of this row is not built yet; these known answers are what it will be checked against."""
+"""calc_eulerian_data.m: the oracle's restatement against hand-derived answers, and the product's item /
+reduction code (sz_euler.cuh) compiled for the host against the oracle.  CPU only; the device path (sz_eulerian_data) is
+compared with the oracle in tests/test_zzz_eulerian_device.py (-m gpu)."""
 import numpy as np
 import pytest
 
