@@ -9,7 +9,8 @@ for v in "$@"; do
   echo "== variant $v"
   case "$v" in
     *=*) env $v timeout 300 python tools/scale_probe.py 1000000 ;;
-    *) SZ_LIB=$PWD/build_exp/$v/libsubzero_b200.so timeout 300 python tools/scale_probe.py 1000000 ;;
+    *) SZ_LIB=$PWD/build_exp/$v/libsubzero_b200.so timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "class_c_equals or periodic_voronoi or shortcuts" 2>&1 | tail -2
+       SZ_LIB=$PWD/build_exp/$v/libsubzero_b200.so timeout 300 python tools/scale_probe.py 1000000 ;;
   esac
 done
 } > gpurun_out/convex_probe.log 2>&1

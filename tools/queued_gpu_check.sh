@@ -1,0 +1,18 @@
+#!/bin/bash
+# Everything that was written without a GPU at the end of round 1, in ONE gpurun call (about 12 minutes of box time):
+#   bash tools/class_c_variants.sh                      # here, in the build container (builds build_exp/smem*/)
+#   gpurun --timeout 1500 -- 'bash tools/queued_gpu_check.sh r02a'
+# 1. the two device paths that have never run: the corners mask and the coarse-grid averages (their tests sort last);
+# 2. the round check (full GPU suite, smoke, default bench line, ncu launch list + full capture of class C) -- this also
+#    times the SweepMem change of the class C sweep, which is in the default build but was never measured;
+# 3. the class C shared-memory variants against the default build (tools/convex_probe.sh).
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TAG=${1:-r02a}
+{
+echo "== new device paths"; timeout 600 python -m pytest tests/test_zz_fracture.py tests/test_zzz_eulerian_device.py -q -m gpu 2>&1 | tail -15
+} > gpurun_out/queued_$TAG.log 2>&1
+bash tools/round_gpu_check.sh $TAG > /dev/null 2>&1
+V=""; for d in build_exp/smem*/; do [ -f "$d/libsubzero_b200.so" ] && V="$V $(basename $d)"; done
+[ -n "$V" ] && bash tools/convex_probe.sh $V > /dev/null 2>&1
+cat gpurun_out/queued_$TAG.log; tail -c 3000 gpurun_out/round_check_$TAG.log; grep -E "^==|1000000 2|passed|failed|rror" gpurun_out/convex_probe.log | tail -20
