@@ -70,6 +70,10 @@ SZ_HD bool cell_range(const EulerArgs& a, int q, int& i0, int& i1, int& j0, int&
     if (!(fj0 > 0)) fj0 = 0;
     if (!(fi1 < a.g.Nx - 1)) fi1 = a.g.Nx - 1;
     if (!(fj1 < a.g.Ny - 1)) fj1 = a.g.Ny - 1;
+    if (fi0 > a.g.Nx) fi0 = a.g.Nx;               // far outside the grid (or an infinite centre): keep the casts defined, the range empty
+    if (fj0 > a.g.Ny) fj0 = a.g.Ny;
+    if (fi1 < -1) fi1 = -1;
+    if (fj1 < -1) fj1 = -1;
     i0 = (int)fi0; i1 = (int)fi1; j0 = (int)fj0; j1 = (int)fj1;
     return i0 <= i1 && j0 <= j1;
 }

@@ -114,6 +114,13 @@ def test_product_core_on_host_matches_oracle():
         soa = sz.floes_to_soa(fl)
         mass = soa.area * soa.h * 920.0
         _same_fields(port_calc_eulerian_data(soa, mass, 2, 2, box, per), oracle.calc_eulerian_data(soa, mass, 2, 2, box, per))
+    # floes astronomically far from the grid, or with an infinite centre, are nobody's candidates
+    soa = sz.floes_to_soa([square(0.0, 0.0), square(1e15, 0.0), square(-3e14, 2e15), square(500.0, 500.0)])
+    soa.x[3] = np.inf
+    mass = soa.area * soa.h * 920.0
+    got = port_calc_eulerian_data(soa, mass, 4, 4, box, True)
+    _same_fields(got, oracle.calc_eulerian_data(soa, mass, 4, 4, box, True))
+    assert got["area"].sum() == pytest.approx(4e6, rel=1e-12)
     rng = np.random.default_rng(5)
     prm, soa = sz.voronoi_field(1500, seed=81, inflate=0.05)
     n = soa.n
