@@ -51,6 +51,11 @@ def test_bad_arguments_are_rejected_without_a_device():
     assert abi.lib().sz_create(None, 0) == abi.SZ_ERR_ARG
     assert b"NULL" in abi.lib().sz_last_error()
     assert abi.lib().sz_step_resident(None, None) == abi.SZ_ERR_ARG
+    # the consumers of the contact rows / resident state validate their context before touching the device too
+    assert abi.lib().sz_corner_mask(None, 0, None, 0, None) == abi.SZ_ERR_ARG and b"sz_corner_mask" in abi.lib().sz_last_error()
+    assert abi.lib().sz_get_corner_mask(None, None, None) == abi.SZ_ERR_ARG
+    assert abi.lib().sz_eulerian_data(None, 4, 4, -1.0, 1.0, -1.0, 1.0, 1, None, None, None, None, None, None, None) == abi.SZ_ERR_ARG
+    assert b"sz_eulerian_data" in abi.lib().sz_last_error()
 
 
 def test_no_cpu_fallback():

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <vector>
 #include <cstring>
+#include <chrono>
+#include <string>
 
 int main(int argc, char** argv)
 {
@@ -47,12 +49,48 @@ int main(int argc, char** argv)
     std::vector<double> fx(n), fy(n);
     sz_get_floe_outputs(ctx, fx.data(), fy.data(), 0, 0, 0, 0, 0, 0, 0, 0);
     double sx = 0, sy = 0; for (int i = 0; i < n; ++i) { sx += fx[i]; sy += fy[i]; }
+    // consumers of the contact rows and of the resident state, wall clock around the blocking calls
+    // (each includes its own read-backs): the corners.m mask for 70 % of the floes (Subzero.m:341-348) and calc_eulerian_data
+    // on a 10 x 10 and a 100 x 100 grid.  A failure here is reported in the line, it does not hide the contact-step numbers.
+    double corner_ms = -1, euler10_ms = -1, euler100_ms = -1; long long corner_verts = 0, corner_flagged = 0; std::string extras_err;
+    {
+        typedef std::chrono::steady_clock clk;
+        auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+        std::vector<int32_t> sel;
+        for (int i = 0; i < n; ++i) if (i % 10 < 7) sel.push_back(i + 1);
+        int64_t nv = 0;
+        for (int rep = 0; rep < 2 && extras_err.empty(); ++rep) {          // the second call is the timed one (buffers allocated)
+            auto t0 = clk::now();
+            if (sz_corner_mask(ctx, (int32_t)sel.size(), sel.data(), 0, &nv) != SZ_OK) { extras_err = sz_last_error(); break; }
+            corner_ms = ms_since(t0);
+        }
+        if (extras_err.empty()) {
+            std::vector<int64_t> off(sel.size() + 1); std::vector<uint8_t> da((size_t)nv + 1);
+            if (sz_get_corner_mask(ctx, off.data(), da.data()) != SZ_OK) extras_err = sz_last_error();
+            corner_verts = nv; for (int64_t k = 0; k < nv; ++k) corner_flagged += da[k];
+        }
+        std::vector<double> mass(n);
+        for (int i = 0; i < n; ++i) mass[i] = view.area[i] * view.h[i] * 920.0;
+        for (int g = 0; g < 2 && extras_err.empty(); ++g) {
+            const int N = g == 0 ? 10 : 100;
+            std::vector<double> planes((size_t)18 * N * N);
+            for (int rep = 0; rep < 2 && extras_err.empty(); ++rep) {
+                auto t0 = clk::now();
+                if (sz_eulerian_data(ctx, N, N, -prm.Lx, prm.Lx, -prm.Ly, prm.Ly, 1, mass.data(), 0, 0, 0, 0, 0, planes.data()) != SZ_OK) { extras_err = sz_last_error(); break; }
+                (g == 0 ? euler10_ms : euler100_ms) = ms_since(t0);
+            }
+        }
+        for (char& ch : extras_err) if (ch == '"' || ch == '\\') ch = '\'';
+    }
     printf("{\"floes\": %d, \"floes_incl_ghosts\": %d, \"pairs\": %lld, \"pairs_with_force\": %lld, \"rows\": %lld, \"ms_per_step\": %.4f, "
            "\"pairs_per_s\": %.4e, \"timesteps_per_s\": %.3f, \"phase_ms\": {\"ghosts\": %.3f, \"broad\": %.3f, \"narrow\": %.3f, \"assembly\": %.3f}, "
            "\"narrow_class_C\": {\"ms\": %.3f, \"pairs\": %d}, \"narrow_class_S\": {\"ms\": %.3f, \"pairs\": %d}, "
-           "\"timesteps_per_s_moving\": %.3f, \"sum_fx\": %.6e, \"sum_fy\": %.6e, \"kernels_launched\": %lld}\n",
+           "\"timesteps_per_s_moving\": %.3f, \"sum_fx\": %.6e, \"sum_fy\": %.6e, "
+           "\"corner_mask\": {\"ms\": %.3f, \"selected\": %d, \"vertices\": %lld, \"flagged\": %lld}, \"eulerian_data_ms\": {\"10x10\": %.3f, \"100x100\": %.3f}, "
+           "\"extras_error\": \"%s\", \"kernels_launched\": %lld}\n",
            s.n0, s.n, (long long)s.n_pairs, (long long)s.n_pairs_force, (long long)s.n_rows, ms, s.n_pairs / (ms * 1e-3), 1e3 / ms,
-           ph[0], ph[1], ph[2], ph[3], cls[0], cls_pairs[0], cls[1], cls_pairs[1], ts_ab2, sx, sy, sz_launch_count());
+           ph[0], ph[1], ph[2], ph[3], cls[0], cls_pairs[0], cls[1], cls_pairs[1], ts_ab2, sx, sy,
+           corner_ms, (int)(7 * (long long)n / 10), corner_verts, corner_flagged, euler10_ms, euler100_ms, extras_err.c_str(), sz_launch_count());
     sz_destroy(ctx); sz_field_free(field);
     return 0;
 }
