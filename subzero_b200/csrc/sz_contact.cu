@@ -100,6 +100,7 @@ struct SzContext {
     cudaEvent_t evk[10] = {};                  // start/stop of the narrow-phase launch of each size class (C, S, T, M, L)
     bool evk_used[5] = {false, false, false, false, false}; int class_pairs[5] = {0, 0, 0, 0, 0};
     int opt_convex_fast = 1;
+    int opt_euler_cell_warp = 1;     // calc_eulerian_data: a warp per cell (0: one thread per cell)
     Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
     // inputs
     bool have_input = false, have_step = false;
@@ -1790,6 +1791,7 @@ extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
 {
     if (!c || !name) { sz_set_error("sz_set_option: NULL argument"); return SZ_ERR_ARG; }
     if (strcmp(name, "convex_fast") == 0) { c->opt_convex_fast = value != 0; return SZ_OK; }
+    if (strcmp(name, "euler_cell_warp") == 0) { c->opt_euler_cell_warp = value != 0; return SZ_OK; }
     sz_set_error("sz_set_option: unknown option '%s'", name);
     return SZ_ERR_ARG;
 }
@@ -2063,10 +2065,44 @@ __global__ void euler_status_kernel(int n, const int* __restrict__ status, int* 
     if (k >= n || status[k] == 0) return;
     atomicAdd(status[k] == szpf::PS_CLIPPER_FAIL ? n_fail : n_cap, 1);
 }
-__global__ void euler_cell_kernel(const szeul::EulerArgs a)
+__global__ void euler_cell_kernel(const szeul::EulerArgs a)      // fallback (option euler_cell_warp = 0): one thread per cell
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell < a.g.Nx * a.g.Ny) szeul::cell_reduce(a, cell);
+}
+// A warp per cell.  The reference adds a cell's items up in list order; on a coarse grid over a large field a cell has
+// thousands of them and one thread would chase their scattered state one item at a time.  Here the 32 lanes compute the terms of
+// 32 consecutive items at once (item_terms: the gathers and the products run in parallel), then the terms are added in item
+// order: lane j owns sum j and takes term j of item l, l = 0, 1, ..., by shuffle.  Same terms, same order of additions as
+// cell_reduce, so the same bits.
+__global__ void __launch_bounds__(128) euler_cell_warp_kernel(const szeul::EulerArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= a.g.Nx * a.g.Ny) return;                        // the whole warp leaves together
+    const int k0 = a.cell_off[cell], k1 = a.cell_off[cell + 1];
+    double acc = 0;                                             // sum number `lane` (lanes >= N_TERMS idle)
+    for (int base = k0; base < k1; base += 32) {
+        double t[szeul::N_TERMS];
+#pragma unroll
+        for (int j = 0; j < szeul::N_TERMS; ++j) t[j] = 0;
+        bool valid = false;
+        if (base + lane < k1) valid = szeul::item_terms(a, a.sorted[base + lane], t);
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        const int cnt = min(32, k1 - base);
+        for (int l = 0; l < cnt; ++l) {
+            const bool v = (vm >> l) & 1u;
+#pragma unroll
+            for (int j = 0; j < szeul::N_TERMS; ++j) {
+                const double x = __shfl_sync(0xffffffffu, t[j], l);
+                if (lane == j && (v || j == szeul::T_M0)) acc += x;
+            }
+        }
+    }
+    double S[szeul::N_TERMS];
+#pragma unroll
+    for (int j = 0; j < szeul::N_TERMS; ++j) S[j] = __shfl_sync(0xffffffffu, acc, j);
+    if (lane == 0) szeul::cell_finalize(a, cell, S);
 }
 
 extern "C" int sz_eulerian_data(SzContext* c, int32_t Nx, int32_t Ny, double xmin, double xmax, double ymin, double ymax, int32_t periodic,
@@ -2161,7 +2197,9 @@ extern "C" int sz_eulerian_data(SzContext* c, int32_t Nx, int32_t Ny, double xmi
     CKS(read_counters(c));
     if (c->h_cnt->eu_fail > 0) { sz_set_error("Clipper Error. (%d cell-floe intersection(s) of sz_eulerian_data)", c->h_cnt->eu_fail); return SZ_ERR_CLIPPER; }
     if (c->h_cnt->eu_cap > 0) { sz_set_error("sz_eulerian_data: %d outline(s) exceed the largest size class", c->h_cnt->eu_cap); return SZ_ERR_CAPACITY; }
-    ++g_launches; euler_cell_kernel<<<nblk(cells, 128), 128, 0, st>>>(a);
+    ++g_launches;
+    if (c->opt_euler_cell_warp) euler_cell_warp_kernel<<<nblk(32 * (i64)cells, 128), 128, 0, st>>>(a);
+    else euler_cell_kernel<<<nblk(cells, 128), 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return finish();
 }

@@ -128,45 +128,62 @@ SZ_HD int item_area(E& eng, const EulerArgs& a, int item, double& area_out)
     return szpf::PS_OK;
 }
 
-// One cell (:131-187): its items in ascending list order.
-SZ_HD void cell_reduce(const EulerArgs& a, int cell)
+// ---- one cell (:131-187): its items in ascending list order.
+// What one item adds to the sums of its cell: Mtot (:149), Atot (:150), the OverlapArea sum and the item count of :153, the 13
+// weighted sums of :155-169, and the candidate-mass sum M0 of :131.  Returns false for an item without shared area
+// (:146-147), which contributes to M0 only.
+enum { T_MTOT = 0, T_ATOT = 1, T_OVER = 2, T_CNT = 3, T_VAL = 4 /* h u v du dv sxx syx sxy syy eux evx euy evy */, T_M0 = 17, N_TERMS = 18 };
+SZ_HD bool item_terms(const EulerArgs& a, int item, double* t)
+{
+    const int s = a.lsrc[a.item_q[item]];
+    const double m = nz(a.mass[s]);
+    t[T_M0] = m;
+    const double ar = a.item_area[item];
+    if (!(ar != 0)) return false;
+    const double A = nz(a.area[s]);
+    t[T_MTOT] = m * ar / A; t[T_ATOT] = ar; t[T_OVER] = a.over[s]; t[T_CNT] = 1.0;
+    t[T_VAL + 0] = nz(a.h[s]) * m * ar / A;
+    t[T_VAL + 1] = nz(a.u[s]) * m * ar / A; t[T_VAL + 2] = nz(a.v[s]) * m * ar / A;
+    t[T_VAL + 3] = nz(a.dU[s]) * m * ar / A; t[T_VAL + 4] = nz(a.dV[s]) * m * ar / A;
+    for (int j = 0; j < 4; ++j) { t[T_VAL + 5 + j] = a.stress[(size_t)s * 4 + j] * m * ar / A; t[T_VAL + 9 + j] = a.strain[(size_t)s * 4 + j] * m * ar / A; }
+    return true;
+}
+// the cell's outputs from its sums S[N_TERMS]
+SZ_HD void cell_finalize(const EulerArgs& a, int cell, const double* S)
 {
     const size_t cells = (size_t)a.g.Nx * (size_t)a.g.Ny, e = (size_t)cell;
-    const int k0 = a.cell_off[cell], k1 = a.cell_off[cell + 1];
-    double M0 = 0;
-    for (int k = k0; k < k1; ++k) M0 += nz(a.mass[a.lsrc[a.item_q[a.sorted[k]]]]);
-    if (!(M0 > 0)) return;                                                    // :131
-    double Mtot = 0, Atot = 0, so = 0; int cnt = 0;
-    double S[14];
-    for (int j = 0; j < 14; ++j) S[j] = 0;
-    for (int k = k0; k < k1; ++k) {
-        const int it = a.sorted[k];
-        const double ar = a.item_area[it];
-        if (!(ar != 0)) continue;                                             // :146-147
-        const int s = a.lsrc[a.item_q[it]];
-        const double m = nz(a.mass[s]), A = nz(a.area[s]);
-        Mtot += m * ar / A; Atot += ar;                                       // :149-150
-        so += a.over[s]; ++cnt;
-        const double val[14] = {nz(a.h[s]), nz(a.u[s]), nz(a.v[s]), nz(a.dU[s]), nz(a.dV[s]),
-                                a.stress[(size_t)s * 4], a.stress[(size_t)s * 4 + 1], a.stress[(size_t)s * 4 + 2], a.stress[(size_t)s * 4 + 3],
-                                a.strain[(size_t)s * 4], a.strain[(size_t)s * 4 + 1], a.strain[(size_t)s * 4 + 2], a.strain[(size_t)s * 4 + 3], 0.0};
-        for (int j = 0; j < 13; ++j) S[j] += val[j] * m * ar / A;
-    }
+    if (!(S[T_M0] > 0)) return;                                               // :131
+    const double Mtot = S[T_MTOT], Atot = S[T_ATOT];
     a.out[O_C * cells + e] = Atot / (a.g.dx() * a.g.dy());                    // :151
     if (!(Mtot > 0)) return;
-    a.out[O_OVER * cells + e] = so / (double)cnt;                             // :153
+    a.out[O_OVER * cells + e] = S[T_OVER] / S[T_CNT];                         // :153
     a.out[O_MTOT * cells + e] = Mtot; a.out[O_AREA * cells + e] = Atot;
-    a.out[O_H * cells + e] = S[0] / Mtot;
-    a.out[O_U * cells + e] = S[1] / Mtot; a.out[O_V * cells + e] = S[2] / Mtot;
-    a.out[O_DU * cells + e] = S[3] / Mtot; a.out[O_DV * cells + e] = S[4] / Mtot;
-    const double sxx = S[5] / Mtot, syx = S[6] / Mtot, sxy = S[7] / Mtot, syy = S[8] / Mtot;
+    a.out[O_H * cells + e] = S[T_VAL + 0] / Mtot;
+    a.out[O_U * cells + e] = S[T_VAL + 1] / Mtot; a.out[O_V * cells + e] = S[T_VAL + 2] / Mtot;
+    a.out[O_DU * cells + e] = S[T_VAL + 3] / Mtot; a.out[O_DV * cells + e] = S[T_VAL + 4] / Mtot;
+    const double sxx = S[T_VAL + 5] / Mtot, syx = S[T_VAL + 6] / Mtot, sxy = S[T_VAL + 7] / Mtot, syy = S[T_VAL + 8] / Mtot;
     a.out[O_SXX * cells + e] = sxx; a.out[O_SYX * cells + e] = syx; a.out[O_SXY * cells + e] = sxy; a.out[O_SYY * cells + e] = syy;
-    a.out[O_EUX * cells + e] = S[9] / Mtot; a.out[O_EVX * cells + e] = S[10] / Mtot; a.out[O_EUY * cells + e] = S[11] / Mtot; a.out[O_EVY * cells + e] = S[12] / Mtot;
+    a.out[O_EUX * cells + e] = S[T_VAL + 9] / Mtot; a.out[O_EVX * cells + e] = S[T_VAL + 10] / Mtot;
+    a.out[O_EUY * cells + e] = S[T_VAL + 11] / Mtot; a.out[O_EVY * cells + e] = S[T_VAL + 12] / Mtot;
     // max(eig([sxx syx; sxy syy])) (:170), eigenvalues of the symmetric stress tensor
     const double tr = sxx + syy, det = sxx * syy - syx * sxy, disc = tr * tr / 4 - det;
     double lam = tr / 2 + sqrt(disc > 0 ? disc : 0);
     if (fabs(lam) > 1e8) lam = 0;                                             // :171-173
     a.out[O_STRESS * cells + e] = lam;
+}
+// sequential form: one caller adds the cell's items up in order (the host test; the device's fallback kernel).  The device's
+// default is a warp per cell that computes 32 items' terms at a time and adds them in this same order (euler_cell_warp_kernel).
+SZ_HD void cell_reduce(const EulerArgs& a, int cell)
+{
+    double S[N_TERMS], t[N_TERMS];
+    for (int j = 0; j < N_TERMS; ++j) S[j] = 0;
+    for (int k = a.cell_off[cell]; k < a.cell_off[cell + 1]; ++k) {
+        for (int j = 0; j < N_TERMS; ++j) t[j] = 0;
+        const bool valid = item_terms(a, a.sorted[k], t);
+        S[T_M0] += t[T_M0];
+        if (valid) for (int j = 0; j < T_M0; ++j) S[j] += t[j];
+    }
+    cell_finalize(a, cell, S);
 }
 
 }  // namespace szeul

@@ -53,6 +53,14 @@ def test_device_eulerian_data_matches_oracle():
             assert np.count_nonzero(w["Mtot"]) == Nx * Ny
         for b in ((-L / 3, L / 2, -L / 4, L / 5), (-2 * L, 2 * L, -3 * L, 3 * L)):
             _check(ctx, soa, mass, 6, 9, b, False, **kw)
+        # the two forms of the per-cell reduction (a warp per cell = default, a thread per cell) give the same bits
+        warp = ctx.eulerian_data(mass, 2, 3, (-L, L, -L, L), True, **kw)          # ~500 items per cell: many 32-item rounds per warp
+        ctx.set_option("euler_cell_warp", 0)
+        one = ctx.eulerian_data(mass, 2, 3, (-L, L, -L, L), True, **kw)
+        _check(ctx, soa, mass, 7, 5, (-L, L, -L, L), True, **kw)
+        ctx.set_option("euler_cell_warp", 1)
+        for k in oracle.EULERIAN_FIELDS:
+            assert np.array_equal(warp[k], one[k]), k
         # real concave shapes: items that overflow the class S arena run in class L
         prm_r, Floe = scenarios.real_shape_field(5, seed=4)
         soa, _ = scenarios.soa_and_boundary(Floe, prm_r, periodic=True)
