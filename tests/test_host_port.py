@@ -206,3 +206,65 @@ def test_conservation_scenarios(port):
     o, p = both(port, prm, f, fb, True, c2, 0)
     assert_same(o, p, "complex_wall")
     assert n >= 3 and o[0] > 0
+
+
+def test_force_law_hand_derived_known_answer(port):
+    """floe_interactions.m worked by hand for two 2 km squares (h = 0.25 m, Modulus = 1e7) overlapping in the strip
+    [900, 1000] x [-1000, 1000] while floe 2 slides in +y:
+      * :12      Force_factor = M h1 h2 / (h1 r2 + h2 r1) = 1e7 * 0.0625 / 1000 = 625, r = sqrt(area) = 2000
+      * :167     normal force on floe 1 = Force_factor * A = 625 * 2e5 = 1.25e8 N along -x (A = 100 * 2000)
+      * :117-137 the outlines cross in four points, so the general branch applies: three edges of the overlap rectangle lie on
+                 floe 1's outline (100, 2000 and 100 m; the lateral normals cancel), dl = 2200 / 3
+      * :170-183 tangential: |v_t|^2 dl G dt along floe 2's motion, G = M / (2 (1 + 0.3)); capped at mu |F_n| = 0.2 * 1.25e8
+      * contact point = centroid of the strip (950, 0); the oracle's step adds the torque 950 * F_y (floe_interactions_all.m:231)
+    checked for the oracle and for the product's general sweep in both capacity classes (host builds); the convex fast path must
+    decline the pair (horizontal edges).  All four crossings of two EQUAL squares are endpoint touches, so this case is a known
+    answer in its exact axis-aligned form only; the generic geometry below is also checked turned by 30 degrees, where the convex
+    fast path accepts it"""
+    sq = np.array([[-1000.0, -1000.0], [-1000.0, 1000.0], [1000.0, 1000.0], [1000.0, -1000.0]])
+    M, dt = 1e7, 10.0
+    G, Fn, dl = M / 2.6, 625.0 * 2e5, 2200.0 / 3.0
+    for vy, Ft in ((0.0, 0.0), (0.01, 1e-4 * dl * G * dt), (-0.02, -4e-4 * dl * G * dt), (0.05, 0.2 * Fn), (-0.3, -0.2 * Fn)):
+        fl = [scenarios.floe_from_polygon(sq), scenarios.floe_from_polygon(sq + [1900.0, 0.0], v=vy)]
+        soa = sz.floes_to_soa(fl)
+        prm = sz.default_params(Lx=1e5, Ly=1e5, modulus=M, dt=dt, periodic=1, collision=1)
+        f1, f2 = floe_dict(soa, 0), floe_dict(soa, 1)
+        for small in (0, 1, 2):                          # class L caps, class S caps, class C (must decline)
+            o, p = both(port, prm, f1, f2, False, None, small)
+            if small == 2:
+                # horizontal edges are outside class C's model: it declines (PS_BAIL) and the device re-runs the pair in class S
+                assert p[0] == -7
+                p = o
+            for which, (n, rows, ov) in (("oracle", o), ("port", p)):
+                assert n == 1 and ov == 0, (which, small, n, ov)
+                fx, fy, px, py, a = rows[0]
+                assert a == pytest.approx(2e5, rel=1e-12) and px == pytest.approx(950.0, abs=1e-6) and py == pytest.approx(0.0, abs=1e-6), which
+                assert fx == pytest.approx(-Fn, rel=1e-12), (which, small, fx)
+                assert fy == pytest.approx(Ft, rel=1e-12, abs=1e-6), (which, small, vy, fy, Ft)
+        off, rows = oracle.OracleStep(prm, soa).rows()
+        assert rows[0][0] == 2 and rows[1][0] == 1 and rows[0][5] == pytest.approx(950.0 * Ft, rel=1e-12, abs=1e-3)
+        np.testing.assert_array_equal(rows[0][1:3], -rows[1][1:3])                # the mirrored row (:196)
+    # A generic (non-degenerate) geometry: the partner is taller (2000 x 2400), so its left edge x = 900 crosses floe 1's top and
+    # bottom edges properly, in exactly two points (900, +-1000): the two-point branch (:107-112), dl = 2000, normal along x;
+    # r2 = sqrt(2000 * 2400).  Axis-aligned (class C declines: horizontal edges) and turned by 30 degrees (class C accepts).
+    tall = sq * [1.0, 1.2] + [1900.0, 0.0]
+    Fn2 = M * 0.25 * 0.25 / (0.25 * np.sqrt(2000.0 * 2400.0) + 0.25 * 2000.0) * 2e5
+    Ft2 = 1e-4 * 2000.0 * G * dt
+    assert Ft2 < 0.2 * Fn2
+    for th in (0.0, np.pi / 6):
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        fl = [scenarios.floe_from_polygon(sq @ R.T), scenarios.floe_from_polygon(tall @ R.T, u=-0.01 * np.sin(th), v=0.01 * np.cos(th))]
+        soa = sz.floes_to_soa(fl)
+        prm = sz.default_params(Lx=1e5, Ly=1e5, modulus=M, dt=dt, periodic=1, collision=1)
+        f1, f2 = floe_dict(soa, 0), floe_dict(soa, 1)
+        want = R @ np.array([-Fn2, Ft2])
+        for small in (0, 1, 2):
+            o, p = both(port, prm, f1, f2, False, None, small)
+            if small == 2 and th == 0.0:
+                assert p[0] == -7
+                continue
+            assert o[0] == p[0] == 1, (th, small, o[0], p[0])
+            assert_same(o, p, "tall partner, angle %.2f, class %d" % (th, small))
+            assert p[1][0][:2] == pytest.approx(want, rel=1e-9), (th, small)
+            assert p[1][0][4] == pytest.approx(2e5, rel=1e-9)
+            assert p[1][0][2:4] == pytest.approx(R @ np.array([950.0, 0.0]), abs=1e-5)
