@@ -268,3 +268,42 @@ def test_force_law_hand_derived_known_answer(port):
             assert p[1][0][:2] == pytest.approx(want, rel=1e-9), (th, small)
             assert p[1][0][4] == pytest.approx(2e5, rel=1e-9)
             assert p[1][0][2:4] == pytest.approx(R @ np.array([950.0, 0.0]), abs=1e-5)
+
+
+def test_wall_force_hand_derived_known_answer(port):
+    """the wall branch worked by hand: a 2 km square (h = 0.25 m) centred at (L - 200, 300) pokes 800 m through the east wall of
+    a non-periodic domain (L = 5 km), Modulus = 1e7, sliding in +y at 0.02 m/s:
+      * :31-37   'dif' clip = the part outside the domain, [5000, 5800] x [-700, 1300]: A = 1.6e6 < 0.75 floe area
+      * :13-14   Force_factor = M h1 / r1 = 1e7 * 0.25 / 2000 = 1250          (the wall has no thickness or size of its own)
+      * :167     normal force 1250 * 1.6e6 = 2e9 N along -x; contact point = centroid of that rectangle (5400, 300)
+      * :107-112 the outline crosses the wall in two points (5000, -700) and (5000, 1300): dl = 2000
+      * :170-183 friction against the motion: -v^2 dl G dt = -4e-4 * 2000 * (M / 2.6) * 10, well under the cap 0.2 * 2e9
+      * floe_interactions_all.m:231,262 torque (5400 - 4800) F_y; calc_trajectory.m:9-13 stress_xx = 2 * 600 * F_x / (2 area h)"""
+    L, M, dt, vy = 5000.0, 1e7, 10.0, 0.02
+    c2, fb = scenarios.domain(L, L)
+    sq = np.array([[-1000.0, -1000.0], [-1000.0, 1000.0], [1000.0, 1000.0], [1000.0, -1000.0]])
+    f = scenarios.floe_from_polygon(sq + [L - 200.0, 300.0], v=vy)
+    prm = sz.default_params(Lx=L, Ly=L, modulus=M, dt=dt, periodic=0, collision=1)
+    Fn, Ft = 1250.0 * 1.6e6, -vy * vy * 2000.0 * (M / 2.6) * dt
+    for small in (0, 1):
+        o, p = both(port, prm, f, fb, True, c2, small)
+        assert_same(o, p, "wall, class %d" % small)
+        for n, rows, ov in (o, p):
+            assert n == 1 and ov == 0
+            assert rows[0][0] == pytest.approx(-Fn, rel=1e-12) and rows[0][1] == pytest.approx(Ft, rel=1e-12)
+            assert rows[0][2] == pytest.approx(5400.0, abs=1e-6) and rows[0][3] == pytest.approx(300.0, abs=1e-6) and rows[0][4] == pytest.approx(1.6e6, rel=1e-12)
+    soa = sz.floes_to_soa([f])
+    bnd = sz.Boundary(fb["c"][0], fb["c"][1], c2[0], c2[1], fb["area"], fb["h"])
+    st = oracle.OracleStep(prm, soa, bnd)
+    off, rows = st.rows()
+    assert off.tolist() == [0, 1] and np.isinf(rows[0][0]) and rows[0][5] == pytest.approx(600.0 * Ft, rel=1e-12)
+    out = st.floe_outputs()
+    assert out["fx"][0] == pytest.approx(-Fn, rel=1e-12) and out["torque"][0] == pytest.approx(600.0 * Ft, rel=1e-12) and out["overlap_area"][0] == pytest.approx(1.6e6, rel=1e-12)
+    sxx, sxy = 2 * 600.0 * -Fn / (2 * 4e6 * 0.25), 600.0 * Ft / (2 * 4e6 * 0.25)
+    assert out["stress"][0] == pytest.approx(np.array([[sxx, sxy], [sxy, 0.0]]), rel=1e-12, abs=1e-9)
+    assert out["alive"][0] == 1 and st.summary.collision_count == 1.0          # calc_collisionNum.m: one wall row counts once
+    # past 75 % outside (:37) the floe is flagged to be removed: overlap = Inf and no force
+    g = scenarios.floe_from_polygon(sq + [L + 600.0, 300.0])
+    o, p = both(port, prm, g, fb, True, c2, 1)
+    assert_same(o, p, "wall, mostly outside")
+    assert o[0] == 0 and np.isinf(o[2]) and o[2] > 0
