@@ -319,3 +319,9 @@ def test_hand_derived_known_answers_on_the_device(ctx):
     assert rows[0][3] == pytest.approx(5400.0, abs=1e-6) and rows[0][4] == pytest.approx(300.0, abs=1e-6) and rows[0][6] == pytest.approx(1.6e6, rel=1e-12)
     assert out["fx"][0] == pytest.approx(-Fw, rel=1e-12) and out["torque"][0] == pytest.approx(600.0 * Fy, rel=1e-12)
     assert out["stress"][0][0][0] == pytest.approx(2 * 600.0 * -Fw / (2 * 4e6 * 0.25), rel=1e-12) and s.collision_count == 1.0
+    # a contact across the periodic boundary: image, pair list, mirrored row, fold into the parent (see the derivation there)
+    from test_oracle_golden import periodic_image_case, check_periodic_image_answers
+    prm, soa = periodic_image_case()
+    s = ctx.step(prm, soa)
+    off, rows = ctx.rows()
+    check_periodic_image_answers(s, ctx.ghosts(), ctx.pairs(), off, rows, ctx.floe_outputs())

@@ -147,3 +147,39 @@ def test_two_block_head_on_force_is_equal_and_opposite():
     ff = modulus * 0.25 * 0.25 / (0.25 * 3e4 + 0.25 * 3e4)      # floe_interactions.m:12, sqrt(area) = 3e4
     assert abs(a[1]) <= ff * a[6] * (1 + 0.2) * (1 + 1e-12)     # normal + Coulomb-capped tangential
     assert r.summary.collision_count == 1.0
+
+
+def periodic_image_case():
+    """square A pokes 50 m through +Lx (Lx = 10 km); square B sits just inside -Lx (its edge ON the boundary: not beyond it)"""
+    import subzero_b200 as sz
+    L = 1e4
+    sq = np.array([[-1000.0, -1000.0], [-1000.0, 1000.0], [1000.0, 1000.0], [1000.0, -1000.0]])
+    soa = sz.floes_to_soa([scenarios.floe_from_polygon(sq + [L - 950.0, 0.0]), scenarios.floe_from_polygon(sq + [-L + 1000.0, 0.0])])
+    return sz.default_params(Lx=L, Ly=L, modulus=1e7, dt=10.0, periodic=1, collision=1), soa
+
+
+def check_periodic_image_answers(summary, ghosts, pairs, off, rows, out):
+    """floe_interactions_all.m worked by hand for periodic_image_case():
+      * :28-39   A has a vertex beyond +Lx (strict >): one image at Xi - 2 Lx = -10950, FloeNum -1, parent 1; B's edge lies ON -Lx: none
+      * :76-120  the only candidate pair is (2, 3): |x_B - x_A'| = 1950 < rmax_B + rmax_A' = 2 sqrt(2) 1000
+      * the image overlaps B in [-10000, -9950] x [-1000, 1000]: A = 1e5, Force_factor 625 -> 6.25e7 N, +x on B
+      * :196     mirrored row on the image; :242-245 its force folded into floe 1 (-6.25e7) -- but not its OverlapArea
+      * calc_trajectory.m:9-13 stress_xx of B = 2 (P_x - X_B) F_x / (2 area h) with P_x = -9975; calc_collisionNum.m: 1/2"""
+    assert summary.n0 == 2 and summary.n == 3 and summary.n_pairs == 1 and summary.collision_count == 0.5
+    assert ghosts["parent"].tolist() == [1] and ghosts["floe_num"].tolist() == [-1] and ghosts["x"].tolist() == [-10950.0] and ghosts["y"].tolist() == [0.0]
+    assert pairs["i"].tolist() == [2] and pairs["j"].tolist() == [3]
+    assert off.tolist() == [0, 0, 1, 2]
+    F = 625.0 * 1e5
+    assert rows[0][0] == 3 and rows[1][0] == 2
+    assert rows[0][1] == pytest.approx(F, rel=1e-12) and rows[0][2] == 0 and rows[0][3] == pytest.approx(-9975.0, abs=1e-6) and rows[0][6] == pytest.approx(1e5, rel=1e-12)
+    np.testing.assert_array_equal(rows[1][1:3], -rows[0][1:3])
+    assert out["fx"].tolist() == pytest.approx([-F, F], rel=1e-12) and out["fy"].tolist() == [0.0, 0.0] and out["torque"].tolist() == [0.0, 0.0]
+    assert out["overlap_area"].tolist() == pytest.approx([0.0, 1e5], rel=1e-12)
+    assert out["stress"][1][0][0] == pytest.approx(2 * (-9975.0 + 9000.0) * F / (2 * 4e6 * 0.25), rel=1e-12) and np.all(out["stress"][0] == 0)
+
+
+def test_periodic_image_contact_hand_derived():
+    prm, soa = periodic_image_case()
+    st = oracle.OracleStep(prm, soa)
+    off, rows = st.rows()
+    check_periodic_image_answers(st.summary, st.ghosts(), st.pairs(), off, rows, st.floe_outputs())
