@@ -325,3 +325,11 @@ def test_hand_derived_known_answers_on_the_device(ctx):
     s = ctx.step(prm, soa)
     off, rows = ctx.rows()
     check_periodic_image_answers(s, ctx.ghosts(), ctx.pairs(), off, rows, ctx.floe_outputs())
+    # the thresholds of the loop: Amin, the strict 55 % merge rule, +Inf / -Inf with kill and transfer
+    from test_oracle_golden import run_threshold_checks
+
+    def step(prm, soa):
+        ctx.step(prm, soa)
+        off, rows = ctx.rows()
+        return off, rows, ctx.pairs(), ctx.floe_outputs()
+    run_threshold_checks(step)

@@ -183,3 +183,39 @@ def test_periodic_image_contact_hand_derived():
     st = oracle.OracleStep(prm, soa)
     off, rows = st.rows()
     check_periodic_image_answers(st.summary, st.ghosts(), st.pairs(), off, rows, st.floe_outputs())
+
+
+def run_threshold_checks(step):
+    """thresholds of the contact loop worked by hand on pairs of squares (2 km, h = 0.25 m, Modulus 1e7, Force_factor 625);
+    `step(prm, soa)` returns (row_off, rows, pairs, floe_outputs) of one contact step:
+      * floe_interactions.m:79     regions smaller than Amin = min(N1, N2) * 100 / 1.75 = 228.57 m^2 are dropped: a 0.11 m strip
+                                   (220 m^2) gives no row, a 0.12 m strip (240 m^2) gives 625 * 240 N
+      * :54-60                     overlap / floe area > 0.55 (strict): exactly 55 % is an ordinary contact (625 * 2.2e6 N), 60 % is
+                                   overlap = +Inf, no force; floe_interactions_all.m:138-141: kill(1) = 1, transfer(1) = 2
+      * :57-58 and :142-143,175-179  a small floe 75 % inside a big one (big floe first): overlap = -Inf, kill(1) = 2, and the
+                                   fix-up loop sets transfer(2) = 1"""
+    import subzero_b200 as sz
+    sq = np.array([[-1000.0, -1000.0], [-1000.0, 1000.0], [1000.0, 1000.0], [1000.0, -1000.0]])
+    prm = sz.default_params(Lx=1e5, Ly=1e5, modulus=1e7, dt=10.0, periodic=1, collision=1)
+    pair = lambda second: sz.floes_to_soa([scenarios.floe_from_polygon(sq), scenarios.floe_from_polygon(second)])
+    off, rows, pairs, out = step(prm, pair(sq + [2000.0 - 0.11, 0.0]))
+    assert off.tolist() == [0, 0, 0] and pairs["i"].tolist() == [1] and out["fx"].tolist() == [0.0, 0.0]
+    off, rows, pairs, out = step(prm, pair(sq + [2000.0 - 0.12, 0.0]))
+    assert off.tolist() == [0, 1, 2] and rows[0][6] == pytest.approx(240.0, rel=1e-8) and rows[0][1] == pytest.approx(-625.0 * 240.0, rel=1e-8)
+    off, rows, pairs, out = step(prm, pair(sq + [900.0, 0.0]))
+    assert pairs["overlap_state"].tolist() == [0.0] and out["fx"].tolist() == pytest.approx([-625.0 * 2.2e6, 625.0 * 2.2e6], rel=1e-12)
+    assert out["kill"].tolist() == [0, 0] and out["transfer"].tolist() == [0, 0]
+    off, rows, pairs, out = step(prm, pair(sq + [800.0, 0.0]))
+    assert off.tolist() == [0, 0, 0] and pairs["overlap_state"].tolist() == [np.inf] and out["fx"].tolist() == [0.0, 0.0]
+    assert out["kill"].tolist() == [1, 0] and out["transfer"].tolist() == [2, 0]
+    soa = sz.floes_to_soa([scenarios.floe_from_polygon(sq * 3), scenarios.floe_from_polygon(sq + [2500.0, 0.0])])
+    off, rows, pairs, out = step(prm, soa)
+    assert pairs["overlap_state"].tolist() == [-np.inf] and out["kill"].tolist() == [2, 0] and out["transfer"].tolist() == [0, 1]
+
+
+def test_contact_thresholds_hand_derived():
+    def step(prm, soa):
+        st = oracle.OracleStep(prm, soa)
+        off, rows = st.rows()
+        return off, rows, st.pairs(), st.floe_outputs()
+    run_threshold_checks(step)
