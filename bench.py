@@ -107,15 +107,15 @@ def algorithmic_bytes(floes, summary):
 _cpu_fields = {}
 
 
-def cpu_sample(n_floes, seed, threads):
+def cpu_sample(n_floes, seed, threads, order="site"):
     """the oracle (reference restatement + the reference's Clipper) on a bounded sample of the same workload;
     returns (pairs resolved, seconds of the contact step alone)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import subzero_b200 as sz
     import oracle
-    key = (n_floes, seed)
+    key = (n_floes, seed, order)
     if key not in _cpu_fields:
-        _cpu_fields[key] = sz.voronoi_field(n_floes, seed=seed)
+        _cpu_fields[key] = sz.voronoi_field(n_floes, seed=seed, order=order)
     prm, f = _cpu_fields[key]
     t = time.perf_counter()
     r = oracle.OracleStep(prm, f, nthreads=threads, broad_mode=1)
@@ -131,17 +131,17 @@ def run_reference(args, rank, world):
     threads = max(1, oracle.lib().szo_hardware_threads())
     n_sample = args.cpu_floes
     for _ in range(args.warmup):
-        cpu_sample(min(n_sample, 20000), args.seed, threads)
+        cpu_sample(min(n_sample, 20000), args.seed, threads, args.floe_order)
     tot_pairs, tot_t = 0, 0.0
     for _ in range(args.steps):
-        p, dt = cpu_sample(n_sample, args.seed, threads)
+        p, dt = cpu_sample(n_sample, args.seed, threads, args.floe_order)
         tot_pairs += p
         tot_t += dt
     v = tot_pairs / tot_t
     sample = "%d-floe periodic Voronoi field (same generator, density and physics as the %d-floe workload), whole contact step, cell-grid broad phase" % (n_sample, args.floes)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+int64",
-            "data": "synthetic", "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes, "sample_floes": n_sample},
+            "data": "synthetic", "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes, "sample_floes": n_sample, "floe_order": args.floe_order},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": sample + "; oracle = C++ restatement of the MATLAB path calling the reference's unmodified Clipper 6.4.2 (MATLAB itself is not installed)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--cpu-floes", type=int, default=400000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--floe-order", default="site", choices=["site", "morton"],
+                    help="numbering of the synthetic floes: the generator's site order (default, SURVEY.md 8d) or a Z-order curve (experiment; both arms)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,7 +179,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from subzero_b200 import slabs
-    job = slabs.SlabJob(args.floes, args.seed, rank, world, local_rank, dist)
+    job = slabs.SlabJob(args.floes, args.seed, rank, world, local_rank, dist, order=args.floe_order)
     prm, floes = job.prm, job.floes
 
     def barrier():
@@ -271,7 +273,7 @@ def main():
                 "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes,
                            "floes_incl_ghosts": total_ext, "pairs_per_step": total_pairs, "pairs_with_force": total_force,
                            "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "timesteps_per_s_with_trajectory_update": ts_with_ab2, "parallelism": job.describe(),
-                           "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed,
+                           "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed, "floe_order": args.floe_order,
                            "wall_ms_per_step": wall_ms / args.steps},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},
@@ -286,7 +288,7 @@ def main():
             threads = max(1, oracle.lib().szo_hardware_threads())
             p, dt = 0, 0.0
             for _ in range(3):
-                pp, dd = cpu_sample(args.cpu_floes, args.seed, threads)
+                pp, dd = cpu_sample(args.cpu_floes, args.seed, threads, args.floe_order)
                 p, dt = p + pp, dt + dd
             line["cpu_baseline"] = {"value": p / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d-floe field from the same generator, 3 whole contact steps (%.1f s of CPU work on %d threads); oracle = C++ restatement of the MATLAB path "

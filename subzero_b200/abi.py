@@ -183,6 +183,16 @@ class FloesSoA:
     def n(self):
         return self.x.shape[0]
 
+    def take(self, order):
+        """the floes `order` (indices), in that order, with their outlines"""
+        order = np.asarray(order, np.int64)
+        nv = (self.voff[1:] - self.voff[:-1]).astype(np.int64)
+        new_nv = nv[order]
+        new_off = np.zeros(order.shape[0] + 1, np.int64)
+        np.cumsum(new_nv, out=new_off[1:])
+        idx = np.repeat(self.voff[:-1].astype(np.int64)[order] - new_off[:-1], new_nv) + np.arange(int(new_off[-1]))
+        return FloesSoA(*(getattr(self, k)[order] for k in self.FIELDS), self.alive[order], new_off.astype(np.int32), self.vx[idx], self.vy[idx])
+
     def struct(self):
         s = SzFloesSoA()
         s.n = self.n

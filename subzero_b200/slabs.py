@@ -60,13 +60,7 @@ def slab_of(x, Lx, world, edges=None):
 
 def select(soa, order):
     """the floes `order` (indices) of a FloesSoA, in that order, with their outlines"""
-    order = np.asarray(order, np.int64)
-    nv = (soa.voff[1:] - soa.voff[:-1]).astype(np.int64)
-    new_nv = nv[order]
-    new_off = np.zeros(order.shape[0] + 1, np.int64)
-    np.cumsum(new_nv, out=new_off[1:])
-    idx = np.repeat(soa.voff[:-1].astype(np.int64)[order] - new_off[:-1], new_nv) + np.arange(int(new_off[-1]))
-    return abi.FloesSoA(*(getattr(soa, k)[order] for k in abi.FloesSoA.FIELDS), soa.alive[order], new_off.astype(np.int32), soa.vx[idx], soa.vy[idx])
+    return soa.take(order)
 
 
 def sort_by_slab(soa, Lx, world, balance=False):
@@ -518,9 +512,9 @@ class SlabStep:
 class SlabJob:
     """bench.py's workload: the synthetic periodic Voronoi field (BASELINE.json configs[4]) on `world` GPUs"""
 
-    def __init__(self, n_floes, seed, rank, world, local_rank, dist):
+    def __init__(self, n_floes, seed, rank, world, local_rank, dist, order="site"):
         self.rank, self.world, self.dist = rank, world, dist
-        self.prm, field = voronoi_field(n_floes, seed=seed)
+        self.prm, field = voronoi_field(n_floes, seed=seed, order=order)
         self.ctx = ContactContext(local_rank)
         self.summary = None
         if world == 1:

@@ -123,3 +123,20 @@ def test_standalone_driver_builds_and_fails_loudly_without_a_gpu(tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "1000", "1", "1"], capture_output=True, text=True)
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_morton_order_is_a_spatial_renumbering_of_the_same_field():
+    """voronoi_field(order="morton"): the same floes (a permutation, outlines intact), consecutive numbers close in space"""
+    import numpy as np
+    from subzero_b200 import field
+    prm, a = sz.voronoi_field(3000, seed=5)
+    _, b = sz.voronoi_field(3000, seed=5, order="morton")
+    order = field.morton_order(a.x, a.y, prm.Lx, prm.Ly)
+    assert sorted(order.tolist()) == list(range(3000)) and np.array_equal(b.x, a.x[order]) and np.array_equal(b.area, a.area[order])
+    for k in (0, 1234, 2999):
+        xa, ya = a.outline(int(order[k])); xb, yb = b.outline(k)
+        assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    hop = lambda f: np.hypot(np.diff(f.x), np.diff(f.y)).mean()
+    assert hop(b) < 0.1 * hop(a)                     # neighbours in number are neighbours in space
+    with pytest.raises(ValueError):
+        sz.voronoi_field(10, order="hilbert")

@@ -5,7 +5,8 @@
 # 1. the two device paths that have never run: the corners mask and the coarse-grid averages (their tests sort last);
 # 2. the round check (full GPU suite, smoke, default bench line, ncu launch list + full capture of class C) -- this also
 #    times the SweepMem change of the class C sweep, which is in the default build but was never measured;
-# 3. the class C shared-memory variants against the default build (tools/convex_probe.sh).
+# 3. the same bench with the floes numbered along a Z-order curve (experiment: how much the gather-bound kernels gain);
+# 4. the class C shared-memory variants against the default build (tools/convex_probe.sh).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${1:-r02a}
@@ -14,6 +15,7 @@ echo "== new device paths"; timeout 600 python -m pytest tests/test_zz_fracture.
 } > gpurun_out/queued_$TAG.log 2>&1
 bash tools/round_gpu_check.sh $TAG > /dev/null 2>&1
 [ -x tools/sz_driver ] && timeout 600 tools/sz_driver 1000000 5 3 > gpurun_out/sz_driver_$TAG.json 2> gpurun_out/sz_driver_$TAG.err   # incl. corner mask / eulerian timings
+timeout 600 python bench.py --floe-order morton --no-cpu > gpurun_out/bench_${TAG}_morton.json 2> gpurun_out/bench_${TAG}_morton.err   # what a spatial numbering is worth
 V=""; for d in build_exp/smem*/; do [ -f "$d/libsubzero_b200.so" ] && V="$V $(basename $d)"; done
 [ -n "$V" ] && bash tools/convex_probe.sh $V > /dev/null 2>&1
-cat gpurun_out/queued_$TAG.log; cat gpurun_out/sz_driver_$TAG.json 2>/dev/null; tail -c 3000 gpurun_out/round_check_$TAG.log; grep -E "^==|1000000 2|passed|failed|rror" gpurun_out/convex_probe.log | tail -20
+cat gpurun_out/queued_$TAG.log; cat gpurun_out/sz_driver_$TAG.json 2>/dev/null; tail -c 700 gpurun_out/bench_${TAG}_morton.json 2>/dev/null; tail -c 3000 gpurun_out/round_check_$TAG.log; grep -E "^==|1000000 2|passed|failed|rror" gpurun_out/convex_probe.log | tail -20
