@@ -302,6 +302,9 @@ int sz_set_stream(SzContext* ctx, void* cuda_stream);
 /* run-time switches of the context (experiments and tests; the defaults are the product configuration):
  *   "convex_fast"  1 (default): strictly convex floe-floe pairs go through class C first; 0: everything through the
  *                  general sweep of class S.  Results are bit-identical either way (tests/test_gpu_parity.py).
+ *   "convex_split"  0 (default): class C is one kernel; 1 (experiment, not measured yet): a sweep kernel and a force-law kernel
+ *                  with the intersection polygon handed over in global memory, to halve the per-thread working set.
+ *                  Results are bit-identical either way (tests/test_zzzz_experiments.py).
  *   "euler_cell_warp"  1 (default): sz_eulerian_data adds a cell's items up with a warp per cell (32 items' terms at a time,
  *                  added in list order); 0: one thread per cell.  Same order of additions, same results.
  * Returns SZ_ERR_ARG for an unknown name. */

@@ -100,6 +100,7 @@ struct SzContext {
     cudaEvent_t evk[10] = {};                  // start/stop of the narrow-phase launch of each size class (C, S, T, M, L)
     bool evk_used[5] = {false, false, false, false, false}; int class_pairs[5] = {0, 0, 0, 0, 0};
     int opt_convex_fast = 1;
+    int opt_convex_split = 0;        // experiment: class C as two kernels (sweep, then force law)
     int opt_euler_cell_warp = 1;     // calc_eulerian_data: a warp per cell (0: one thread per cell)
     Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
     // inputs
@@ -127,6 +128,7 @@ struct SzContext {
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
     DBuf<unsigned char> scratchM, scratchL;
+    DBuf<int> ho_st; DBuf<i64> ho_x, ho_y;      // experiment convex_split: clip #1 polygons between the two class C kernels
     // assembly
     DBuf<int> tcnt, toff, tlist, rcnt, row_off;
     DBuf<double> rows; i64 n_rows = 0;
@@ -843,11 +845,11 @@ extern "C" void sz_destroy(SzContext* c)
                        &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->stage, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
-                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status, &c->cr_idx, &c->cr_nv, &c->cr_off, &c->cr_esrc, &c->eu_lsrc, &c->eu_icnt, &c->eu_ioff, &c->eu_cell, &c->eu_q, &c->eu_status, &c->eu_iota, &c->eu_sorted, &c->eu_keys, &c->eu_ccnt, &c->eu_coff, &c->eu_listL};
+                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status, &c->cr_idx, &c->cr_nv, &c->cr_off, &c->cr_esrc, &c->eu_lsrc, &c->eu_icnt, &c->eu_ioff, &c->eu_cell, &c->eu_q, &c->eu_status, &c->eu_iota, &c->eu_sorted, &c->eu_keys, &c->eu_ccnt, &c->eu_coff, &c->eu_listL, &c->ho_st};
     for (auto* b : ib) b->release();
     DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed, &c->cr_da, &c->cr_ealive, &c->eu_tmp};
     for (auto* b : ub) b->release();
-    DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy};
+    DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy, &c->ho_x, &c->ho_y};
     for (auto* b : lb) b->release();
     c->pkey.release();
     { DBuf<double>* tb[] = {&c->t_mass, &c->t_inertia, &c->t_alpha, &c->t_dXi_p, &c->t_dYi_p, &c->t_dUi_p, &c->t_dVi_p, &c->t_dalpha_p, &c->t_dksi_p, &c->t_FxOA, &c->t_FyOA, &c->t_torqueOA,
@@ -1091,6 +1093,13 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         a.list = c->listC.p; a.list_count = D_CNT(listC); a.next_list = c->listS.p; a.next_count = D_CNT(listS);
         CK(cudaMemcpyAsync(D_CNT(listC0), D_CNT(listC), 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(D_CNT(listS0), D_CNT(listS), 4, cudaMemcpyDeviceToDevice, st));
         CK(cudaEventRecord(c->evk[0], st));
+        static const bool env_split = getenv("SZ_CONVEX_SPLIT") != nullptr;
+        if (!no_fast && (c->opt_convex_split || env_split)) {
+            enum { HO_CAP = 16 };                       // a larger intersection polygon sends the pair to class S
+            CK(c->ho_st.ensure((size_t)n_work + 1)); CK(c->ho_x.ensure((size_t)HO_CAP * n_work + 1)); CK(c->ho_y.ensure((size_t)HO_CAP * n_work + 1));
+            a.ho_st = c->ho_st.p; a.ho_x = c->ho_x.p; a.ho_y = c->ho_y.p; a.ho_stride = n_work; a.ho_cap = HO_CAP;
+            g_launches += 2; sz_launch_narrow_C_split(&a, st); CK(cudaGetLastError());
+        } else
         if (!no_fast) { ++g_launches; sz_launch_narrow_C(&a, st); CK(cudaGetLastError()); }
         else { a.list = c->listC.p; a.next_list = lstT; a.next_count = cntT; ++g_launches; sz_launch_narrow_S(&a, st); CK(cudaGetLastError()); }
         CK(cudaEventRecord(c->evk[1], st)); c->evk_used[0] = true;
@@ -1791,6 +1800,7 @@ extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
 {
     if (!c || !name) { sz_set_error("sz_set_option: NULL argument"); return SZ_ERR_ARG; }
     if (strcmp(name, "convex_fast") == 0) { c->opt_convex_fast = value != 0; return SZ_OK; }
+    if (strcmp(name, "convex_split") == 0) { c->opt_convex_split = value != 0; return SZ_OK; }
     if (strcmp(name, "euler_cell_warp") == 0) { c->opt_euler_cell_warp = value != 0; return SZ_OK; }
     sz_set_error("sz_set_option: unknown option '%s'", name);
     return SZ_ERR_ARG;

@@ -60,6 +60,7 @@ struct NarrowArgs {
     // wall mode (floe_interactions_all.m:150-172)
     int wall; int first_floe; const double* bx; const double* by; int bn; Body bbody;
     void* scratch; int n_threads;  // M/L arenas: n_threads * sizeof(Workspace<C>)
+    int* ho_st; i64* ho_x; i64* ho_y; int ho_stride; int ho_cap;      // experiment: class C split in two kernels (szpf::ConvexHandoff), indexed by work-list position
     Params P;
 };
 
@@ -101,8 +102,8 @@ struct SizeSink { int paths, verts; SZ_HD void begin_path(int c) { ++paths; vert
 
 // All 32 lanes of a warp call this together (szpf::pair_force is warp-synchronous); `valid` says whether
 // the lane has a pair.
-template <class C, bool FAST, class W>
-__device__ __forceinline__ void resolve_pair_impl(const NarrowArgs& a, int k, bool valid, W& w)
+template <class C, bool FAST, class W, int MODE = 0>
+__device__ __forceinline__ void resolve_pair_impl(const NarrowArgs& a, int k, bool valid, W& w, int item = 0)
 {
     int i = 0, j = -1;
     Body b1, b2;
@@ -135,7 +136,10 @@ __device__ __forceinline__ void resolve_pair_impl(const NarrowArgs& a, int k, bo
     }
     szpf::PairResult res;
     double rows[C::ROWS * 5];
-    if constexpr (FAST) szpf::pair_force_convex<C>(w, b1, b2, a.P, res, rows, valid, hints);
+    if constexpr (FAST && MODE == 2) {
+        const szpf::ConvexHandoff ho{a.ho_st, a.ho_x, a.ho_y, a.ho_stride, a.ho_cap, item};
+        szpf::pair_force_convex_after_sweep<C>(w, b1, b2, a.P, res, rows, valid, hints, ho);
+    } else if constexpr (FAST) szpf::pair_force_convex<C>(w, b1, b2, a.P, res, rows, valid, hints);
     else szpf::pair_force(w, b1, b2, a.wall != 0, a.P, res, rows, valid, hints);
     if (valid && (res.status == szpf::PS_CAPACITY || res.status == szpf::PS_BAIL) && a.next_list) { escalate = true; valid = false; }
     if (escalate) { int t = atomicAdd(a.next_count, 1); a.next_list[t] = k; }
@@ -182,6 +186,48 @@ __global__ void __launch_bounds__(SZ_C_TPB, SZ_C_MINB) narrow_convex_kernel(cons
     if (blockIdx.x * blockDim.x >= n) return;           // whole CTA beyond the list: uniform exit
     szpf::WorkspaceLite<C> w;
     resolve_pair_impl<C, true>(a, t < n ? a.list[t] : 0, t < n, w);
+}
+
+// Experiment (sz_set_option "convex_split", off by default, not measured yet): class C as two kernels over the same work list.
+// The fused kernel keeps ~1.5 KB of local memory in flight per thread -- 227 MB over the 151,552 resident threads, against
+// 126 MB of L2 -- and moves 17x its algorithmic bytes through DRAM.  Split, the sweep needs the int64 outlines, the edge
+// records and the deque, the force law the double outlines, the region and the Sutherland-Hodgman buffers: about half each.
+// The intersection polygon (6 vertices on average) crosses in a strided global buffer.
+template <class C>
+__global__ void __launch_bounds__(SZ_C_TPB, SZ_C_MINB) narrow_convex_sweep_kernel(const NarrowArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *a.list_count;
+    if (blockIdx.x * blockDim.x >= n) return;           // whole CTA beyond the list: uniform exit
+    bool go = false;
+    szpf::ClipInput subj, clip;
+    subj.x = subj.y = nullptr; subj.dx = subj.dy = 0; subj.ix = subj.iy = nullptr; subj.n = 0; subj.ring = 0; subj.rot = 0;
+    clip = subj;
+    if (t < n) {
+        const int k = a.list[t];
+        const int i = a.pi[k], j = a.pj[k];
+        const int si = a.esrc[i], sj = a.esrc[j];
+        const int o1 = a.voff[si], n1 = a.voff[si + 1] - o1, o2 = a.voff[sj], n2 = a.voff[sj + 1] - o2;
+        const int no1 = a.eno[i], no2 = a.eno[j];
+        // the same pairs the fused kernel sweeps: both outlines strictly convex and small enough for the class
+        if (a.econvex[i] && a.econvex[j] && no1 >= 3 && no2 >= 3 && n1 >= 1 && n2 >= 1 && n1 + 1 <= C::NV && n2 + 1 <= C::NV) {
+            go = true;
+            subj.x = a.vx + o1; subj.y = a.vy + o1; subj.dx = a.ex[i]; subj.dy = a.ey[i]; subj.n = no1; subj.rot = a.erot[i];     // floe_interactions.m:25
+            clip.x = a.vx + o2; clip.y = a.vy + o2; clip.dx = a.ex[j]; clip.dy = a.ey[j]; clip.n = no2; clip.rot = a.erot[j];     // floe_interactions_all.m:105
+        } else a.ho_st[t] = -1;
+    }
+    i64 svx[2 * C::NV], svy[2 * C::NV], dqx[C::RV], dqy[C::RV], ox[C::RV], oy[C::RV];
+    const szpf::ConvexHandoff ho{a.ho_st, a.ho_x, a.ho_y, a.ho_stride, a.ho_cap, t};
+    szpf::convex_sweep_only<C::NV>(go, subj, clip, svx, svy, dqx, dqy, ox, oy, C::RV, ho);
+}
+template <class C>
+__global__ void __launch_bounds__(SZ_C_TPB, SZ_C_MINB) narrow_convex_force_kernel(const NarrowArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *a.list_count;
+    if (blockIdx.x * blockDim.x >= n) return;
+    szpf::WorkspaceLite<C> w;
+    resolve_pair_impl<C, true, szpf::WorkspaceLite<C>, 2>(a, t < n ? a.list[t] : 0, t < n, w, t);
 }
 
 // class S launch shape: two 512-thread CTAs per SM (64 registers per thread).  With SZ_BLOCK_SYNC (default) all
@@ -389,6 +435,7 @@ __global__ void __launch_bounds__(64) euler_item_scratch_kernel(const szeul::Eul
 // launchers (one translation unit per class); all asynchronous on `stream`
 extern "C" {
 void sz_launch_narrow_C(const sznarrow::NarrowArgs* a, cudaStream_t stream);
+void sz_launch_narrow_C_split(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_S(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_T(const sznarrow::NarrowArgs* a, cudaStream_t stream);
 void sz_launch_narrow_M(const sznarrow::NarrowArgs* a, cudaStream_t stream);

@@ -16,3 +16,18 @@ extern "C" void sz_launch_narrow_C(const NarrowArgs* a, cudaStream_t stream)
     }
     narrow_convex_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, smem, stream>>>(*a);
 }
+// experiment: class C as a sweep kernel and a force-law kernel (sz_narrow.cuh); the same grid twice, the second launch reads
+// what the first one left in the handoff buffers (stream order)
+extern "C" void sz_launch_narrow_C_split(const NarrowArgs* a, cudaStream_t stream)
+{
+    if (a->n_work <= 0) return;
+    const int tpb = SZ_C_TPB;
+    static bool once = false;
+    if (!once) {
+        cudaFuncSetAttribute(narrow_convex_sweep_kernel<PairS>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(narrow_convex_force_kernel<PairS>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        once = true;
+    }
+    narrow_convex_sweep_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
+    narrow_convex_force_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
+}

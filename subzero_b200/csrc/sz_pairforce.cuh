@@ -508,8 +508,16 @@ SZ_HD void force_row(const Body& f1, const Body& f2, const Params& P, double G, 
 // FAST = true is the convex fast path (class C): clip #1 of a strictly convex pair runs in the specialised sweep of
 // sz_convex.cuh, and the sign test must be decided by convex_sign_test; whenever either declines, the pair ends with
 // PS_BAIL and the caller re-runs it with FAST = false.  Everything between the clips is the same code.
-template <class C, bool FAST, class W>
-SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid, PairHints hints)
+// Experiment (off by default, NOT measured yet): class C split into two kernels so that each one's per-thread working set is
+// about half as large -- `convex_sweep_only` runs clip #1 alone and leaves the intersection polygon in a strided global
+// buffer, `pair_force_impl<.., MODE = 2>` picks it up and runs the rest of the force law.  Item `item` of a buffer with
+// `stride` items: st[item] = vertex count (0 = empty intersection), -1 = the sweep declined the pair or the polygon does not
+// fit `cap` vertices; vertex k at x[k * stride + item] (lanes of a warp write neighbouring words).
+struct ConvexHandoff { int* st; i64* x; i64* y; int stride; int cap; int item; };
+
+template <class C, bool FAST, class W, int MODE = 0>
+SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid, PairHints hints,
+                           const ConvexHandoff* ho = nullptr)
 {
     enum { PH_CLIP1 = 0, PH_CLIP2 = 1, PH_CLIP3 = 2, PH_DONE = 3, PH_NEXT = 4 };
     res.status = PS_OK; res.n_rows = 0; res.overlap_state = 0;
@@ -535,7 +543,18 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
 
     // class C: clip #1 in the four-edge sweep of sz_convex.cuh, one scanbeam per iteration with the lanes kept together
     int fast_clip1 = PS_BAIL;
-    if constexpr (FAST) {
+    if constexpr (FAST && MODE == 2) {
+        // clip #1 was swept by convex_sweep_only: fetch its polygon
+        if (valid && convex_pair && !boundary && hints.no1 >= 3 && hints.no2 >= 3) {
+            const int n = ho->st[ho->item];
+            if (n >= 0 && n <= C::RV) {
+                for (int t = 0; t < n; ++t) { w.rax[t] = ho->x[(size_t)t * ho->stride + ho->item]; w.ray[t] = ho->y[(size_t)t * ho->stride + ho->item]; }
+                fast_clip1 = PS_OK; w.ra_off[0] = 0; w.ra_off[1] = n; w.ra_n = n > 0 ? 1 : 0;
+            }
+        }
+        SZ_LANE_SYNC();
+    }
+    if constexpr (FAST && MODE != 2) {
         static_assert(C::NP >= 2 * C::NV, "the InterX buffers must hold both int64 outlines");
         szcvx::ConvexSweep<C::NV> cs;
         const szcvx::SweepMem mem{w.svx, w.svy, w.rbx, w.rby, C::RV};       // outlines in the InterX buffers, deque in the clip #2 buffers
@@ -808,6 +827,41 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
     for (int r = 0; r < n_rows; ++r) sabs += fabs(rows[r * 5]) + fabs(rows[r * 5 + 1]);
     res.n_rows = (sabs != 0) ? n_rows : 0;
 }
+// First half of the split class C (see ConvexHandoff): clip #1 of a strictly convex floe-floe pair by the four-edge sweep, the
+// same statements as the FAST block of pair_force_impl, with the outlines read where they lie (subj / clip may point at
+// global memory: (x[i] + dx) * 2^32 is the arithmetic of polyclip.m:66 either way) and the result handed over.
+// Storage: 2 * NV int64 for the outlines, dcap entries for the output deque, dcap for the result ring.
+template <int NV>
+SZ_HD void convex_sweep_only(bool go, const ClipInput& subj, const ClipInput& clip, i64* svx, i64* svy, i64* dqx, i64* dqy, i64* ox, i64* oy, int dcap, const ConvexHandoff& ho)
+{
+    szcvx::ConvexSweep<NV> cs;
+    const szcvx::SweepMem mem{svx, svy, dqx, dqy, dcap};
+    bool run = false;
+    if (go) { cs.load_ring(mem, 0, subj, subj.n); cs.load_ring(mem, 1, clip, clip.n); }
+    SZ_LANE_SYNC();
+    if (go) run = cs.begin(mem);
+    for (;;) {
+        if (!SZ_WARP_ANY(run)) break;
+        if (run) run = cs.step(mem);
+        SZ_LANE_SYNC();
+    }
+    if (go) {
+        int n_out = 0, st = -1;
+        if (cs.finish(mem, ox, oy, dcap, n_out) == szcvx::CV_OK && n_out <= ho.cap) {
+            st = n_out;
+            for (int t = 0; t < n_out; ++t) { ho.x[(size_t)t * ho.stride + ho.item] = ox[t]; ho.y[(size_t)t * ho.stride + ho.item] = oy[t]; }
+        }
+        ho.st[ho.item] = st;
+    }
+    SZ_LANE_SYNC();
+}
+// second half: everything after clip #1
+template <class C>
+SZ_HD void pair_force_convex_after_sweep(WorkspaceLite<C>& w, const Body& f1, const Body& f2, const Params& P, PairResult& res, double* rows, bool valid, PairHints hints, const ConvexHandoff& ho)
+{
+    pair_force_impl<C, true, WorkspaceLite<C>, 2>(w, f1, f2, false, P, res, rows, valid, hints, &ho);
+}
+
 template <class C>
 SZ_HD void pair_force(Workspace<C>& w, const Body& f1, const Body& f2, bool boundary, const Params& P, PairResult& res, double* rows, bool valid = true, PairHints hints = PairHints{false, 0, 0, 0, 0})
 {

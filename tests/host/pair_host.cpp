@@ -34,7 +34,7 @@ static void fill_params(const SzParams* p, const double* boxx, const double* box
 template <class CAPS>
 static int run(const SzParams* prm, const double* cax, const double* cay, int n1, const double* body1,
                const double* c2x, const double* c2y, int n2, const double* body2, int is_boundary,
-               const double* boxx, const double* boxy, int nbox, double* rows_out, int rows_cap, double* overlap_state, bool fast = false)
+               const double* boxx, const double* boxy, int nbox, double* rows_out, int rows_cap, double* overlap_state, bool fast = false, bool split = false)
 {
     if (n1 + 1 > CAPS::NV || n2 + 1 > CAPS::NV) return PS_CAPACITY;
     std::unique_ptr<Workspace<CAPS>> w(new Workspace<CAPS>);
@@ -54,7 +54,26 @@ static int run(const SzParams* prm, const double* cax, const double* cay, int n1
         hints.no1 = open_n(w->c1x, w->c1y, n1); hints.no2 = open_n(w->c2x, w->c2y, n2);
         hints.rot1 = ring_bottom_vertex(G{w->c1x, w->c1y}, hints.no1); hints.rot2 = ring_bottom_vertex(G{w->c2x, w->c2y}, hints.no2);
     }
-    if (fast) {
+    if (split) {
+        // class C split in two (experiment): clip #1 alone, reading the outline where it lies (relative outline + centroid, like
+        // the device's sweep kernel reads the vertex pool), its polygon handed over through a strided buffer; then the rest
+        std::unique_ptr<WorkspaceLite<CAPS>> wl(new WorkspaceLite<CAPS>);
+        wl->n1 = n1; wl->n2 = n2;
+        for (int i = 0; i < n1; ++i) { wl->c1x[i] = w->c1x[i]; wl->c1y[i] = w->c1y[i]; }
+        for (int i = 0; i < n2; ++i) { wl->c2x[i] = w->c2x[i]; wl->c2y[i] = w->c2y[i]; }
+        const int stride = 3, item = 1, cap = 16;
+        std::vector<int> hst(stride, -5); std::vector<i64> hx((size_t)cap * stride, 0), hy((size_t)cap * stride, 0);
+        ConvexHandoff ho{hst.data(), hx.data(), hy.data(), stride, cap, item};
+        ClipInput subj, clip;
+        subj.x = cax; subj.y = cay; subj.dx = b1.Xi; subj.dy = b1.Yi; subj.ix = subj.iy = 0; subj.n = hints.no1; subj.ring = 0; subj.rot = hints.rot1;
+        clip.x = c2x; clip.y = c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = hints.no2; clip.ring = 0; clip.rot = hints.rot2;
+        const bool go = convex && hints.no1 >= 3 && hints.no2 >= 3;
+        std::vector<i64> svx(2 * CAPS::NV), svy(2 * CAPS::NV), dqx(CAPS::RV), dqy(CAPS::RV), ox(CAPS::RV), oy(CAPS::RV);
+        convex_sweep_only<CAPS::NV>(go, subj, clip, svx.data(), svy.data(), dqx.data(), dqy.data(), ox.data(), oy.data(), CAPS::RV, ho);
+        if (go && hst[item] == -5) return -9;                 // the sweep must have answered
+        if (hst[0] != -5 || hst[2] != -5) return -9;          // ... in its own slot only
+        pair_force_convex_after_sweep<CAPS>(*wl, b1, b2, P, res, rows.data(), true, hints, ho);
+    } else if (fast) {
         // class C as the device runs it: the convex fast path on the engine-less workspace; PS_BAIL = declined
         std::unique_ptr<WorkspaceLite<CAPS>> wl(new WorkspaceLite<CAPS>);
         wl->n1 = n1; wl->n2 = n2;
@@ -74,6 +93,7 @@ extern "C" int szport_floe_interactions(const SzParams* prm, const double* cax, 
                                         const double* boxx, const double* boxy, int nbox,
                                         double* rows_out, int rows_cap, double* overlap_state, int small_class)
 {
+    if (small_class == 3) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state, true, true);
     if (small_class == 2) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state, true);
     if (small_class) return run<SmallPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);
     return run<BigPair>(prm, cax, cay, n1, body1, c2x, c2y, n2, body2, is_boundary, boxx, boxy, nbox, rows_out, rows_cap, overlap_state);

@@ -130,11 +130,16 @@ def test_pair_force_convex_fast_path_class_c(port, inflate, seed):
         if i >= soa.n or j >= soa.n:
             continue
         o, p = both(port, prm, floe_dict(soa, i), floe_dict(soa, j), False, None, 2)
+        # the split form of class C (sweep kernel -> handoff buffer -> force kernel, an experiment switch on the device)
+        # must decline and answer exactly like the fused one
+        _, q = both(port, prm, floe_dict(soa, i), floe_dict(soa, j), False, None, 3)
+        assert q[0] == p[0], (i, j, q[0], p[0])
         n_all += 1
         if p[0] == -7:
             n_bail += 1
             continue
         assert_same(o, p, "class C, inflate %g pair %d-%d" % (inflate, i, j))
+        assert_same(o, q, "split class C, inflate %g pair %d-%d" % (inflate, i, j))
         n_force += o[0] > 0
         n_inf += np.isinf(o[2])
     if inflate > 0:
