@@ -22,12 +22,14 @@ extern "C" void sz_launch_narrow_C_split(const NarrowArgs* a, cudaStream_t strea
 {
     if (a->n_work <= 0) return;
     const int tpb = SZ_C_TPB;
+    const size_t smem = szcvx::smem_edge_bytes(tpb);      // non-zero only in builds with SZ_C_SMEM_EDGES: the sweep kernel's edge records
     static bool once = false;
     if (!once) {
-        cudaFuncSetAttribute(narrow_convex_sweep_kernel<PairS>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        if (smem == 0) cudaFuncSetAttribute(narrow_convex_sweep_kernel<PairS>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        else cudaFuncSetAttribute(narrow_convex_sweep_kernel<PairS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(narrow_convex_force_kernel<PairS>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
         once = true;
     }
-    narrow_convex_sweep_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
+    narrow_convex_sweep_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, smem, stream>>>(*a);
     narrow_convex_force_kernel<PairS><<<(a->n_work + tpb - 1) / tpb, tpb, 0, stream>>>(*a);
 }
