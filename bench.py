@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--cpu-floes", type=int, default=400000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="run-time switch of the library (sz_set_option), e.g. convex_split=1; experiments only, recorded in config")
     ap.add_argument("--floe-order", default="site", choices=["site", "morton"],
                     help="numbering of the synthetic floes: the generator's site order (default, SURVEY.md 8d) or a Z-order curve (experiment; both arms)")
     args = ap.parse_args()
@@ -180,6 +182,9 @@ def main():
 
     from subzero_b200 import slabs
     job = slabs.SlabJob(args.floes, args.seed, rank, world, local_rank, dist, order=args.floe_order)
+    for o in args.opt:
+        name, _, val = o.partition("=")
+        job.ctx.set_option(name.strip(), int(val or 1))
     prm, floes = job.prm, job.floes
 
     def barrier():
@@ -273,7 +278,7 @@ def main():
                 "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes,
                            "floes_incl_ghosts": total_ext, "pairs_per_step": total_pairs, "pairs_with_force": total_force,
                            "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "timesteps_per_s_with_trajectory_update": ts_with_ab2, "parallelism": job.describe(),
-                           "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed, "floe_order": args.floe_order,
+                           "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed, "floe_order": args.floe_order, "options": args.opt,
                            "wall_ms_per_step": wall_ms / args.steps},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},

@@ -15,7 +15,8 @@ echo "== new device paths and experiment switches"; timeout 900 python -m pytest
 } > gpurun_out/queued_$TAG.log 2>&1
 bash tools/round_gpu_check.sh $TAG > /dev/null 2>&1
 [ -x tools/sz_driver ] && timeout 600 tools/sz_driver 1000000 5 3 > gpurun_out/sz_driver_$TAG.json 2> gpurun_out/sz_driver_$TAG.err   # incl. corner mask / eulerian timings
+timeout 600 python bench.py --opt convex_split=1 --no-cpu > gpurun_out/bench_${TAG}_split.json 2> gpurun_out/bench_${TAG}_split.err   # class C in two kernels, through the official bench
 timeout 600 python bench.py --floe-order morton --no-cpu > gpurun_out/bench_${TAG}_morton.json 2> gpurun_out/bench_${TAG}_morton.err   # what a spatial numbering is worth
 V=""; for d in build_exp/smem*/; do [ -f "$d/libsubzero_b200.so" ] && V="$V $(basename $d)"; done
 bash tools/convex_probe.sh $V SZ_CONVEX_SPLIT=1 "SZ_LIB=$PWD/build_exp/smem63/libsubzero_b200.so SZ_CONVEX_SPLIT=1" > /dev/null 2>&1      # variants + class C split in two kernels (env form of the option)
-cat gpurun_out/queued_$TAG.log; cat gpurun_out/sz_driver_$TAG.json 2>/dev/null; tail -c 700 gpurun_out/bench_${TAG}_morton.json 2>/dev/null; tail -c 3000 gpurun_out/round_check_$TAG.log; grep -E "^==|1000000 2|passed|failed|rror" gpurun_out/convex_probe.log | tail -20
+cat gpurun_out/queued_$TAG.log; cat gpurun_out/sz_driver_$TAG.json 2>/dev/null; tail -c 700 gpurun_out/bench_${TAG}_morton.json 2>/dev/null; tail -c 700 gpurun_out/bench_${TAG}_split.json 2>/dev/null; tail -c 3000 gpurun_out/round_check_$TAG.log; grep -E "^==|1000000 2|passed|failed|rror" gpurun_out/convex_probe.log | tail -20
