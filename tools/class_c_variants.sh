@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds class C experiment variants next to the product library (build container, no GPU needed), for
-#   gpurun --timeout 1800 -- 'bash tools/queued_gpu_check.sh r02a'      (or tools/convex_probe.sh <names> alone)
+#   gpurun --timeout 2100 -- 'bash tools/queued_gpu_check.sh r02a'      (or tools/convex_probe.sh <names> alone)
 # which runs the class C parity tests and then times a 1M-floe step per variant (tools/scale_probe.py, SZ_LIB).
 # Arguments: masks of SZ_C_SMEM_EDGES (a number N builds build_exp/smemN) or name:flags specs, e.g.
 #   tools/class_c_variants.sh 63 48 16 "smem63_1024x1:-DSZ_C_SMEM_EDGES=63 -DSZ_C_TPB=1024 -DSZ_C_MINB=1"

@@ -1,7 +1,7 @@
 #!/bin/bash
-# Everything that was written without a GPU at the end of round 1, in ONE gpurun call (about 18 minutes of box time):
+# Everything that was written without a GPU at the end of round 1, in ONE gpurun call (about 22 minutes of box time):
 #   bash tools/class_c_variants.sh                      # here, in the build container (builds build_exp/smem*/)
-#   gpurun --timeout 1800 -- 'bash tools/queued_gpu_check.sh r02a'
+#   gpurun --timeout 2100 -- 'bash tools/queued_gpu_check.sh r02a'
 # 1. the two device paths that have never run: the corners mask and the coarse-grid averages (their tests sort last);
 # 2. the round check (full GPU suite, smoke, default bench line, ncu launch list + full capture of class C) -- this also
 #    times the SweepMem change of the class C sweep, which is in the default build but was never measured;
