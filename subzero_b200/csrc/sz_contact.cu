@@ -1380,7 +1380,7 @@ extern "C" int sz_contact_step(SzContext* c, const SzParams* prm, const SzFloesS
 #define D2H(dst, src, bytes) do { if ((dst) && (bytes) > 0) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDefault, c->stream)); } while (0)
 // ------------------------------------------------------------------------------------------------ trajectory
 struct TrajArgs {
-    int n0, nz; double dt, HFo, xo_min, xo_max, yo_min, yo_max;
+    int n0, nz, Nb; double dt, HFo, xo_min, xo_max, yo_min, yo_max;
     const double* cfx; const double* cfy; const double* ctq; const double* stress_now; const uint8_t* has_rows; const uint8_t* alive_step; const double* xw; const double* yw;
     const double* area; double* x; double* y; double* u; double* v; double* ksi; double* h; uint8_t* alive;
     double* mass; double* inertia; double* alpha; double* dXi_p; double* dYi_p; double* dUi_p; double* dVi_p; double* dalpha_p; double* dksi_p;
@@ -1398,6 +1398,7 @@ __global__ void trajectory_kernel(const TrajArgs a)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n0) return;
     a.flags[i] = 0;
+    if (i < a.Nb) return;            // the timestepping loop is `parfor i=1+Nb:N0` (floe_interactions_all.m:249): topography floes are never wrapped, thinned or moved
     // the contact step's per-floe results replace the inputs of the integrator (floe_interactions_all.m:152-155,267-277)
     uint8_t alive = a.alive_step[i];
     double X = a.xw[i], Y = a.yw[i];
@@ -1488,7 +1489,7 @@ __global__ void trajectory_kernel(const TrajArgs a)
 
 // ------------------------------------------------------------------------------------------------ ocean / atmosphere forcing
 struct OceanArgs {
-    int n0, npts, nx, ny, do_int; double dt, HFo, xo_min, xo_max, yo_min, yo_max, fc, turn, rho0, Cd, rho_air, Cd_atm;
+    int n0, npts, nx, ny, do_int, Nb; double dt, HFo, xo_min, xo_max, yo_min, yo_max, fc, turn, rho0, Cd, rho_air, Cd_atm;
     const uint8_t* alive_step; const double* xw; const double* yw; const double* u; const double* v; const double* ksi; const double* h;
     const double* mass; const double* area; const double* alpha; const int* voff; const double* cax; const double* cay;
     const double* PX; const double* PY; const uint8_t* PA;
@@ -1514,7 +1515,7 @@ __device__ __forceinline__ double warp_sum(double v) { for (int d = 16; d > 0; d
 __global__ void __launch_bounds__(256) ocean_forcing_kernel(const OceanArgs a)
 {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= a.n0) return;
+    if (i >= a.n0 || i < a.Nb) return;                                             // floe_interactions_all.m:249 (i = 1+Nb:N0)
     if (!a.alive_step[i]) return;                                                  // floe_interactions_all.m:280
     double hh = a.h[i], m = a.mass[i]; int alive = a.alive_step[i];
     if (hh > 10) hh = 10; else if (m < 100) { m = 1e3; alive = 0; }                // :36-41
@@ -1619,7 +1620,7 @@ extern "C" int sz_trajectory_step(SzContext* c, const SzTrajectoryParams* p, int
     cudaStream_t st = c->stream; const int n0 = c->n0;
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
     TrajArgs a; memset(&a, 0, sizeof(a));
-    a.n0 = n0; a.nz = c->traj_nz; a.dt = p->dt; a.HFo = p->HFo; a.xo_min = p->xo_min; a.xo_max = p->xo_max; a.yo_min = p->yo_min; a.yo_max = p->yo_max;
+    a.n0 = n0; a.nz = c->traj_nz; a.Nb = c->prm.Nb; a.dt = p->dt; a.HFo = p->HFo; a.xo_min = p->xo_min; a.xo_max = p->xo_max; a.yo_min = p->yo_min; a.yo_max = p->yo_max;
     a.cfx = c->o_fx.p; a.cfy = c->o_fy.p; a.ctq = c->o_tq.p; a.stress_now = c->o_stress.p; a.has_rows = c->has_rows.p; a.alive_step = c->o_alive.p; a.xw = c->o_xi.p; a.yw = c->o_yi.p;
     a.area = c->area.p; a.x = c->x.p; a.y = c->y.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.h = c->h.p; a.alive = c->alive.p;
     a.mass = c->t_mass.p; a.inertia = c->t_inertia.p; a.alpha = c->t_alpha.p; a.dXi_p = c->t_dXi_p.p; a.dYi_p = c->t_dYi_p.p; a.dUi_p = c->t_dUi_p.p; a.dVi_p = c->t_dVi_p.p;
@@ -1677,7 +1678,7 @@ extern "C" int sz_trajectory_ocean_forcing(SzContext* c, const SzTrajectoryParam
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
     CK(cudaMemsetAsync(c->t_forced.p, 0, (size_t)n0, st));
     OceanArgs a; memset(&a, 0, sizeof(a));
-    a.n0 = n0; a.npts = c->npts; a.nx = c->oc_nx; a.ny = c->oc_ny; a.do_int = do_int != 0;
+    a.n0 = n0; a.npts = c->npts; a.nx = c->oc_nx; a.ny = c->oc_ny; a.do_int = do_int != 0; a.Nb = c->prm.Nb;
     a.dt = p->dt; a.HFo = p->HFo; a.xo_min = p->xo_min; a.xo_max = p->xo_max; a.yo_min = p->yo_min; a.yo_max = p->yo_max;
     a.fc = c->oc_fc; a.turn = c->oc_turn; a.rho0 = c->oc_rho0; a.Cd = c->oc_Cd; a.rho_air = c->oc_rho_air; a.Cd_atm = c->oc_Cd_atm;
     a.alive_step = c->o_alive.p; a.xw = c->o_xi.p; a.yw = c->o_yi.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.h = c->h.p;

@@ -1,3 +1,10 @@
+// ------------------------------------------------------------------------------------------------
+// DERIVATIVE WORK NOTICE.  This file is a function-by-function re-implementation, for fixed-capacity GPU data structures,
+// of the Clipper library 6.4.2 -- Copyright Angus Johnson 2010-2017, http://www.angusj.com -- which the reference vendors as
+// private/clipper.cpp / clipper.hpp (an extension of Bala Vatti's clipping algorithm, CACM 35(7), 1992).  Clipper is
+// distributed under the Boost Software License, Version 1.0; that licence and the attribution are reproduced in the
+// NOTICE file at the root of this repository (http://www.boost.org/LICENSE_1_0.txt).
+// ------------------------------------------------------------------------------------------------
 // sz_convex.cuh -- Clipper 6.4.2's scan-beam sweep specialised to ONE call pattern: the intersection
 // (ctIntersection, even-odd) of two STRICTLY CONVEX closed paths without horizontal edges.
 //

@@ -123,6 +123,45 @@ def test_device_trajectory_matches_oracle_over_coupled_steps(n, nz, hfo):
     assert np.abs(st["alpha"]).max() > 0 and np.abs(st["dUi_p"]).max() > 0
 
 
+@pytest.mark.gpu
+def test_device_trajectory_leaves_topography_floes_alone():
+    """Nb > 0 with HFo != 0: the timestepping loop is `parfor i=1+Nb:N0` (floe_interactions_all.m:249-283), so the first Nb
+    floes keep their position, thickness, mass, heading and stress history on the device exactly as uploaded, while the
+    others are integrated; device against the oracle over three coupled steps."""
+    n, nz, hfo, Nb = 1200, 6, 2e-4, 7
+    rng = np.random.default_rng(11)
+    prm, soa = sz.voronoi_field(n, seed=9)
+    prm.dt = 10.0
+    prm.Nb = Nb
+    ref_soa = copy_soa(soa)
+    st = make_state(soa, nz, rng)
+    first = {k: np.array(getattr(soa, k)[:Nb]) for k in ("x", "y", "h", "u", "v", "ksi")}
+    mass0, c0 = st["mass"][:Nb].copy(), soa.vx[:soa.voff[Nb]].copy()
+    L = prm.Lx
+    bounds = (-1.2 * L, 1.2 * L, -1.2 * L, 1.2 * L)
+    with sz.ContactContext(0) as ctx:
+        ctx.upload(prm, soa)
+        ctx.trajectory_init(st["mass"], st["inertia"], nz=nz, **{k: st[k] for k in ("dXi_p", "dYi_p", "FxOA", "FyOA", "torqueOA")})
+        for it in range(3):
+            ctx.step_resident()
+            ns = ctx.trajectory_step(prm.dt, hfo, *bounds)
+            ref = oracle.OracleStep(prm, ref_soa, broad_mode=1)
+            sacked, unsup = oracle.calc_trajectory(ref, ref_soa, st, prm.dt, hfo, bounds, nz, Nb=Nb)
+            assert ns == int(sacked.sum()) and not unsup.any()
+            got = ctx.trajectory_state(nverts=soa.vx.shape[0])
+            for k in ("x", "y", "h", "u", "v", "ksi"):
+                assert np.array_equal(got[k][:Nb], first[k]), (it, k)                # bit for bit what was uploaded
+            assert np.array_equal(got["mass"][:Nb], mass0) and np.array_equal(got["cax"][:c0.shape[0]], c0)
+            assert np.all(got["alpha"][:Nb] == 0) and np.all(got["stress"][:Nb] == 0)
+            tol = 0.0 if it == 0 else 1e-9
+            for k, want in (("x", ref_soa.x), ("y", ref_soa.y), ("u", ref_soa.u), ("v", ref_soa.v), ("ksi", ref_soa.ksi), ("h", ref_soa.h), ("mass", st["mass"]),
+                            ("alpha", st["alpha"]), ("dUi_p", st["dUi_p"]), ("dksi_p", st["dksi_p"]), ("stress", st["stress"])):
+                scale = max(np.abs(want).max(), 1e-300)
+                assert np.abs(got[k] - want).max() / scale <= tol, (it, k)
+            assert np.array_equal(got["alive"], ref_soa.alive)
+    assert np.abs(ref_soa.h[Nb:] - soa.h[Nb:]).max() > 0          # the others were thinned
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # ocean / atmosphere forcing (calc_trajectory.m:94-166) and strain (:224-234)
 def uniform_ocean(L, n=9, U=0.0, V=0.0, Wu=0.0, Wv=0.0, fc=0.0, turn=0.0, **kw):
