@@ -181,6 +181,11 @@ int sz_get_floe_outputs(SzContext* ctx,
                         int32_t* kill, int32_t* transfer);         /* 1-based ids as in :138-145,175-179; 0 = none */
 /* ghost bookkeeping [n - n0]: parent = 1-based index in the extended list, floe_num = FloeNums (negative) */
 int sz_get_ghosts(SzContext* ctx, int32_t* parent, int32_t* floe_num, double* gx, double* gy);
+/* what the reference leaves in the ghost structs Floe(N0+1:N), [n - n0] each, any pointer may be NULL: collision_force and
+ * collision_torque = column sums of the ghost's own rows (floe_interactions_all.m:218-238; before they are folded into the
+ * parent, :242-245) and OverlapArea (:137,198).  The ghosts' interactions are rows row_off[n0..n] of sz_get_rows.  Needed by
+ * a host that runs the reference's ridging / rafting tail, which indexes Floe(partner) with partner > N0 (:312,327,401,416). */
+int sz_get_ghost_outputs(SzContext* ctx, double* fx, double* fy, double* torque, double* overlap_area);
 /* candidate pairs [n_pairs], 1-based (i<j), ascending (i,j) = the order of Floe(i).potentialInteractions;
  * overlap_state: 0, +Inf or -Inf (floe_interactions.m:55-58); status: 0 ok, <0 SzStatus of that pair */
 int sz_get_pairs(SzContext* ctx, int32_t* pi, int32_t* pj, double* overlap_state, int32_t* n_regions, int32_t* status);

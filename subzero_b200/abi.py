@@ -87,6 +87,7 @@ PROTOTYPES = {
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
     "sz_get_floe_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),
+    "sz_get_ghost_outputs": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp]),
     "sz_get_pairs": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_ip, c_ip]),
     "sz_get_rows": (C.c_int, [C.c_void_p, c_lp, c_dp]),
     "sz_trajectory_init": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryInit)]),

@@ -85,6 +85,15 @@ class ContactContext:
         abi.check(abi.lib().sz_get_ghosts(self._h, p(o["parent"], abi.c_ip), p(o["floe_num"], abi.c_ip), p(o["x"], abi.c_dp), p(o["y"], abi.c_dp)))
         return o
 
+    def ghost_outputs(self):
+        """collision_force, collision_torque and OverlapArea the reference leaves in the ghost structs Floe(N0+1:N)
+        (floe_interactions_all.m:218-238,137,198)"""
+        g = self.summary.n - self.summary.n0
+        o = {k: np.empty(g) for k in ("fx", "fy", "torque", "overlap_area")}
+        p = abi._ptr
+        abi.check(abi.lib().sz_get_ghost_outputs(self._h, p(o["fx"], abi.c_dp), p(o["fy"], abi.c_dp), p(o["torque"], abi.c_dp), p(o["overlap_area"], abi.c_dp)))
+        return o
+
     def pairs(self):
         n = self.summary.n_pairs
         o = {"i": np.empty(n, np.int32), "j": np.empty(n, np.int32), "overlap_state": np.empty(n), "n_regions": np.empty(n, np.int32), "status": np.empty(n, np.int32)}
@@ -306,7 +315,8 @@ def floe_interactions_all(Floe, floebound, ocean, winds, c2_boundary, dt, HFo, m
       interactions (K x 7), OverlapArea, collision_force (1x2), collision_torque, Stress-sum input (`StressSum`, 2x2,
       calc_trajectory.m:12-13), alive, Xi, Yi, potentialInteractions (emptied, the reference rmfield-s it at :507);
     and returns (Floe, dissolvedNEW, kill, transfer).  calc_trajectory, ridging/rafting and the kill/fuse tail
-    (:281,288-512) stay with the host model.
+    (:281,288-512) stay with the host model.  With PERIODIC, doInt.flag and RIDGING or RAFTING the returned list also holds
+    the ghost floes Floe(N0+1:N) that tail indexes (N0 = len(kill)); the MATLAB twin is subzero_b200/matlab/floe_interactions_all.m.
     """
     global _default_ctx
     if Modulus is None:
@@ -327,9 +337,11 @@ def floe_interactions_all(Floe, floebound, ocean, winds, c2_boundary, dt, HFo, m
         if _default_ctx is None:
             _default_ctx = ContactContext(0)
         ctx = _default_ctx
+    alive0 = [int(f["alive"]) for f in Floe]
     ctx.step(prm, soa, bnd)
     out = ctx.floe_outputs()
     off, rows = ctx.rows()
+    N0 = len(Floe)
     for i, f in enumerate(Floe):
         if i < Nb:
             continue
@@ -341,4 +353,28 @@ def floe_interactions_all(Floe, floebound, ocean, winds, c2_boundary, dt, HFo, m
         f["alive"] = int(out["alive"][i])
         f["Xi"], f["Yi"] = float(out["xi"][i]), float(out["yi"][i])
         f["potentialInteractions"] = []
+    # ghost structs Floe(N0+1:N) (floe_interactions_all.m:16-66 as data): only the reference's ridging / rafting tail reads
+    # them -- Floe(partner) with partner > N0 (:312,327,401,416) -- so they are materialised only when that tail will run.
+    # A ghost is its parent as it was when the step began, with the shifted centroid (:34,55), and carries what
+    # :76-88,218-238 leave in it.  The caller's tail drops them again (:468, Floe = Floe(1:N0)).
+    flag = doInt.get("flag", False) if isinstance(doInt, dict) else bool(getattr(doInt, "flag", False))
+    if PERIODIC and flag and (RIDGING or RAFTING) and ctx.summary.n > N0:
+        g, go = ctx.ghosts(), ctx.ghost_outputs()
+        ghosts = []
+        for k in range(ctx.summary.n - N0):
+            p = int(g["parent"][k]) - 1
+            if p < N0:
+                d = dict(Floe[p])
+                d["alive"] = alive0[p]
+            else:
+                d = dict(ghosts[p - N0])                 # a y-ghost of an x-ghost (:49-60 runs over the extended list)
+            d["Xi"], d["Yi"] = float(g["x"][k]), float(g["y"][k])
+            d["interactions"] = rows[off[N0 + k]:off[N0 + k + 1]].copy()
+            d["OverlapArea"] = float(go["overlap_area"][k])
+            d["collision_force"] = np.array([go["fx"][k], go["fy"][k]])
+            d["collision_torque"] = float(go["torque"][k])
+            d["StressSum"] = np.zeros((2, 2))
+            d["potentialInteractions"] = []
+            ghosts.append(d)
+        Floe = Floe + ghosts
     return Floe, dissolvedNEW, out["kill"].copy(), out["transfer"].copy()

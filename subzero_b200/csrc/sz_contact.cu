@@ -133,6 +133,7 @@ struct SzContext {
     DBuf<int> tcnt, toff, tlist, rcnt, row_off;
     DBuf<double> rows; i64 n_rows = 0;
     DBuf<double> osum;             // [n*3] own column sums Fx Fy tau
+    DBuf<double> e_ov;             // [n] OverlapArea of every entry (the periodic images included: sz_get_ghost_outputs)
     DBuf<uint8_t> has_rows;
     DBuf<int> kill_i, transfer_i, tmax;
     // per-original outputs
@@ -649,7 +650,7 @@ struct AssembleArgs {
     const int* wnrows; const int* wrow_start; const int* wstatus;
     const int* toff; const int* tlist; const int* row_off; const double* pool;
     const double* boxx; const double* boxy; int boxn;
-    double* rows; double* osum; uint8_t* has_rows; int* kill_i; int* transfer_i;
+    double* rows; double* osum; double* e_ov; uint8_t* has_rows; int* kill_i; int* transfer_i;
     double* o_ov; double* o_stress; double* o_xi; double* o_yi; uint8_t* o_alive;
     Counters* cnt;
 };
@@ -661,7 +662,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
     if (m >= a.n) return;
     const bool owned = a.eowned[m] != 0, orig = a.efn[m] > 0, pairing = a.egid[m] > a.Nb;   // pairing: i >= 1+Nb (:125)
     if (!owned) {
-        a.osum[(size_t)m * 3] = a.osum[(size_t)m * 3 + 1] = a.osum[(size_t)m * 3 + 2] = 0; a.has_rows[m] = 0; a.kill_i[m] = 0; a.transfer_i[m] = 0;
+        a.osum[(size_t)m * 3] = a.osum[(size_t)m * 3 + 1] = a.osum[(size_t)m * 3 + 2] = 0; a.e_ov[m] = 0; a.has_rows[m] = 0; a.kill_i[m] = 0; a.transfer_i[m] = 0;
         if (m < a.nout) { a.o_ov[m] = 0; a.o_xi[m] = a.ex[m]; a.o_yi[m] = a.ey[m]; a.o_alive[m] = a.ealive[m]; double* S = a.o_stress + (size_t)m * 4; S[0] = S[1] = S[2] = S[3] = 0; }
         return;
     }
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
         const double* src = a.pool + (size_t)a.row_start[p] * 5;
         for (int q = 0; q < nr; ++q) { put((double)a.egid[a.pi[p]], -src[q * 5], -src[q * 5 + 1], src[q * 5 + 2], src[q * 5 + 3], src[q * 5 + 4]); ova = ova + src[q * 5 + 4]; ++nfin; }
     }
-    a.osum[(size_t)m * 3] = sfx; a.osum[(size_t)m * 3 + 1] = sfy; a.osum[(size_t)m * 3 + 2] = st;
+    a.osum[(size_t)m * 3] = sfx; a.osum[(size_t)m * 3 + 1] = sfy; a.osum[(size_t)m * 3 + 2] = st; a.e_ov[m] = ova;
     a.has_rows[m] = nr_total > 0;
     a.kill_i[m] = kill; a.transfer_i[m] = transfer;
     if (m < a.nout) {
@@ -837,7 +838,7 @@ extern "C" void sz_destroy(SzContext* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
-                          &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi,
+                          &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->e_ov, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi,
                           &c->oc_Xo, &c->oc_Yo, &c->oc_U, &c->oc_V, &c->oc_Wu, &c->oc_Wv, &c->pt_x, &c->pt_y, &c->t_strain,
                           &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy, &c->cr_ex, &c->cr_ey, &c->eu_lx, &c->eu_ly, &c->eu_in, &c->eu_area, &c->eu_out};
     for (auto* b : db) b->release();
@@ -1318,7 +1319,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     // every row of the pool appears at most twice (its floe's own row and the partner's mirrored row): the row count is
     // bounded without waiting for it; the exact value comes back with the step's last counter read
     const i64 rows_bound = 2 * (i64)c->h_cnt->row_used;
-    CK(c->rows.ensure((size_t)rows_bound * 7 + 7)); CK(c->osum.ensure((size_t)n * 3 + 3)); CK(c->has_rows.ensure(n + 1));
+    CK(c->rows.ensure((size_t)rows_bound * 7 + 7)); CK(c->osum.ensure((size_t)n * 3 + 3)); CK(c->e_ov.ensure(n + 1)); CK(c->has_rows.ensure(n + 1));
     const int nout = ext ? n : n0; c->nout = nout;
     CK(c->kill_i.ensure(n + 1)); CK(c->transfer_i.ensure(n + 1)); CK(c->tmax.ensure(nout + 1));
     CK(c->o_fx.ensure(nout + 1)); CK(c->o_fy.ensure(nout + 1)); CK(c->o_tq.ensure(nout + 1)); CK(c->o_ov.ensure(nout + 1)); CK(c->o_stress.ensure(4 * (size_t)nout + 4));
@@ -1332,7 +1333,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         a.wnrows = c->wnrows.p; a.wrow_start = c->wrow_start.p; a.wstatus = c->wstatus.p;
         a.toff = c->toff.p; a.tlist = c->tlist.p; a.row_off = c->row_off.p; a.pool = c->row_pool.p;
         a.boxx = c->boxx.p; a.boxy = c->boxy.p; a.boxn = c->boxn;
-        a.rows = c->rows.p; a.osum = c->osum.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
+        a.rows = c->rows.p; a.osum = c->osum.p; a.e_ov = c->e_ov.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
         a.o_ov = c->o_ov.p; a.o_stress = c->o_stress.p; a.o_xi = c->o_xi.p; a.o_yi = c->o_yi.p; a.o_alive = c->o_alive.p; a.cnt = c->d_cnt;
         ++g_launches; assemble_kernel<<<nblk(n, 128), 128, 0, st>>>(a);
         if (!ext) {
@@ -1741,6 +1742,26 @@ extern "C" int sz_get_ghosts(SzContext* c, int32_t* parent, int32_t* floe_num, d
     const size_t g = (size_t)(c->n - c->n0); const int n0 = c->n0;
     D2H(parent, c->eparent.p + n0, g * 4); D2H(floe_num, c->efn.p + n0, g * 4); D2H(gx, c->ex.p + n0, g * 8); D2H(gy, c->ey.p + n0, g * 8);
     CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+// what the reference leaves in the ghost structs Floe(N0+1:N) (floe_interactions_all.m:218-238): collision_force and
+// collision_torque = the column sums of the image's own rows (zero when it has none), OverlapArea (:137,198)
+extern "C" int sz_get_ghost_outputs(SzContext* c, double* fx, double* fy, double* torque, double* overlap_area)
+{
+    NEED_STEP("sz_get_ghost_outputs");
+    if (c->ext_mode) { sz_set_error("sz_get_ghost_outputs: not available for a caller-supplied extended list"); return SZ_ERR_STATE; }
+    const size_t g = (size_t)(c->n - c->n0); const int n0 = c->n0;
+    if (g == 0) return SZ_OK;
+    std::vector<double> sums(g * 3); std::vector<uint8_t> has(g);
+    CK(cudaMemcpyAsync(sums.data(), c->osum.p + (size_t)n0 * 3, g * 24, cudaMemcpyDefault, c->stream));
+    CK(cudaMemcpyAsync(has.data(), c->has_rows.p + n0, g, cudaMemcpyDefault, c->stream));
+    D2H(overlap_area, c->e_ov.p + n0, g * 8);
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < g; ++k) {
+        if (fx) fx[k] = has[k] ? sums[k * 3] : 0.0;
+        if (fy) fy[k] = has[k] ? sums[k * 3 + 1] : 0.0;
+        if (torque) torque[k] = has[k] ? sums[k * 3 + 2] : 0.0;
+    }
     return SZ_OK;
 }
 extern "C" int sz_get_pairs(SzContext* c, int32_t* pi, int32_t* pj, double* overlap_state, int32_t* n_regions, int32_t* status)

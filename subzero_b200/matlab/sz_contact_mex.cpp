@@ -11,7 +11,10 @@
 //           concatenated, closed outlines) and voff (length N+1, 0-based offsets)
 //     bnd : struct x y (hole vertices of floebound.poly), box_x box_y (c2_boundary), area h  -- non-periodic runs
 //     out : struct  fx fy torque overlap_area (N x 1), stress (4 x N), xi yi alive kill transfer (N x 1),
-//                   row_off (Next+1 x 1), rows (7 x K, one contact row per column), n_ext, n_pairs, collision_count
+//                   row_off (Next+1 x 1), rows (7 x K, one contact row per column), n_ext, n_pairs, collision_count,
+//                   ghost_parent ghost_x ghost_y ghost_fx ghost_fy ghost_torque ghost_overlap_area (Next-N x 1): the
+//                   periodic images Floe(N+1:Next) of floe_interactions_all.m:16-66 -- parent = 1-based index in the
+//                   extended list, shifted centroid, and what :218-238 leaves in their structs
 //
 // Build (MATLAB):  mex -I../../include sz_contact_mex.cpp -L../_lib -lsubzero_b200
 // The context (device buffers, stream) persists between calls and is released by mexAtExit.
@@ -90,8 +93,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     int rc = sz_contact_step(g_ctx, &P, &F, pB, &S);
     if (rc != SZ_OK) fail(rc);
 
-    const char* names[] = {"fx", "fy", "torque", "overlap_area", "stress", "xi", "yi", "alive", "kill", "transfer", "row_off", "rows", "n_ext", "n_pairs", "collision_count"};
-    mxArray* out = mxCreateStructMatrix(1, 1, 15, names);
+    const char* names[] = {"fx", "fy", "torque", "overlap_area", "stress", "xi", "yi", "alive", "kill", "transfer", "row_off", "rows", "n_ext", "n_pairs", "collision_count",
+                           "ghost_parent", "ghost_x", "ghost_y", "ghost_fx", "ghost_fy", "ghost_torque", "ghost_overlap_area"};
+    mxArray* out = mxCreateStructMatrix(1, 1, 22, names);
     mxArray *fx = mxCreateDoubleMatrix(n, 1, mxREAL), *fy = mxCreateDoubleMatrix(n, 1, mxREAL), *tq = mxCreateDoubleMatrix(n, 1, mxREAL), *ov = mxCreateDoubleMatrix(n, 1, mxREAL);
     mxArray *st = mxCreateDoubleMatrix(4, n, mxREAL), *xi = mxCreateDoubleMatrix(n, 1, mxREAL), *yi = mxCreateDoubleMatrix(n, 1, mxREAL);
     std::vector<uint8_t> al(n); std::vector<int32_t> kill(n), transfer(n);
@@ -105,7 +109,19 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     if (rc != SZ_OK) fail(rc);
     mxArray* ro = mxCreateDoubleMatrix((size_t)S.n + 1, 1, mxREAL);
     for (size_t i = 0; i <= (size_t)S.n; ++i) mxGetPr(ro)[i] = (double)off[i];
-    mxArray* vals[] = {fx, fy, tq, ov, st, xi, yi, ma, mk, mt, ro, rows, mxCreateDoubleScalar(S.n), mxCreateDoubleScalar((double)S.n_pairs), mxCreateDoubleScalar(S.collision_count)};
-    for (int k = 0; k < 15; ++k) mxSetFieldByNumber(out, 0, k, vals[k]);
+    const size_t ng = (size_t)(S.n - S.n0);
+    mxArray *gp = mxCreateDoubleMatrix(ng, 1, mxREAL), *gx = mxCreateDoubleMatrix(ng, 1, mxREAL), *gy = mxCreateDoubleMatrix(ng, 1, mxREAL);
+    mxArray *gfx = mxCreateDoubleMatrix(ng, 1, mxREAL), *gfy = mxCreateDoubleMatrix(ng, 1, mxREAL), *gtq = mxCreateDoubleMatrix(ng, 1, mxREAL), *gov = mxCreateDoubleMatrix(ng, 1, mxREAL);
+    if (ng > 0) {
+        std::vector<int32_t> par(ng), fnum(ng);
+        rc = sz_get_ghosts(g_ctx, par.data(), fnum.data(), mxGetPr(gx), mxGetPr(gy));
+        if (rc != SZ_OK) fail(rc);
+        rc = sz_get_ghost_outputs(g_ctx, mxGetPr(gfx), mxGetPr(gfy), mxGetPr(gtq), mxGetPr(gov));
+        if (rc != SZ_OK) fail(rc);
+        for (size_t i = 0; i < ng; ++i) mxGetPr(gp)[i] = par[i];
+    }
+    mxArray* vals[] = {fx, fy, tq, ov, st, xi, yi, ma, mk, mt, ro, rows, mxCreateDoubleScalar(S.n), mxCreateDoubleScalar((double)S.n_pairs), mxCreateDoubleScalar(S.collision_count),
+                       gp, gx, gy, gfx, gfy, gtq, gov};
+    for (int k = 0; k < 22; ++k) mxSetFieldByNumber(out, 0, k, vals[k]);
     plhs[0] = out;
 }

@@ -1,14 +1,15 @@
-function [Floe, kill, transfer] = sz_contact_step(Floe, floebound, c2_boundary, dt, Nb, COLLISION, PERIODIC, Modulus)
+function [Floe, kill, transfer, ghosts] = sz_contact_step(Floe, floebound, c2_boundary, dt, Nb, COLLISION, PERIODIC, Modulus)
 %SZ_CONTACT_STEP  GPU replacement of floe_interactions_all.m lines 16-277 (ghost floes, potential interactions,
 % floe_interactions over every pair and the walls, mirror, torques, force/torque sums, periodic wrap).
 %
-% Called from inside the reference's floe_interactions_all right after the dead floes have been dropped (:12-14);
-% see INTEGRATION.md for the three-line edit.  On return every floe i > Nb carries the fields the reference writes:
+% Called by this folder's floe_interactions_all.m right after the dead floes have been dropped (:12-14).  On return every
+% floe i > Nb carries the fields the reference writes:
 %   interactions (K x 7: [partner Fx Fy Px Py torque overlap]), OverlapArea, collision_force (1 x 2),
 %   collision_torque, Stress = zeros(2), potentialInteractions = [], alive, Xi, Yi (wrapped),
-% and kill / transfer (1 x N0) are what :138-145,175-179 compute.  calc_trajectory (:281), ridging, rafting and the
-% kill/fuse tail (:288-512) stay the reference's own code.  Ghost floes are not materialised on the MATLAB side:
-% their forces are already folded into their parents (:242-245).
+% and kill / transfer (1 x N0) are what :138-145,175-179 compute.  Ghost floes are not appended to Floe: their forces are
+% already folded into their parents (:242-245).  `ghosts` describes them for a caller that needs the structs (the ridging /
+% rafting tail): parent (1-based index in the extended list), x, y (shifted centroid), interactions (cell of K x 7),
+% overlap_area, fx, fy, torque.
     N0 = numel(Floe);
     prm = struct('Lx', max(c2_boundary(1,:)), 'Ly', max(c2_boundary(2,:)), 'modulus', Modulus, 'dt', dt, ...
                  'Nb', Nb, 'periodic', double(PERIODIC), 'collision', double(COLLISION));
@@ -37,4 +38,12 @@ function [Floe, kill, transfer] = sz_contact_step(Floe, floebound, c2_boundary, 
         Floe(i).Xi = out.xi(i);  Floe(i).Yi = out.yi(i);
     end
     kill = out.kill';  transfer = out.transfer';
+    ng = numel(out.ghost_parent);
+    ghosts = struct('parent', out.ghost_parent, 'x', out.ghost_x, 'y', out.ghost_y, 'fx', out.ghost_fx, 'fy', out.ghost_fy, ...
+                    'torque', out.ghost_torque, 'overlap_area', out.ghost_overlap_area);
+    ghosts.interactions = cell(ng, 1);
+    for k = 1:ng
+        r = out.row_off(N0+k)+1 : out.row_off(N0+k+1);
+        ghosts.interactions{k} = out.rows(:, r)';
+    end
 end

@@ -140,3 +140,53 @@ def test_morton_order_is_a_spatial_renumbering_of_the_same_field():
     assert hop(b) < 0.1 * hop(a)                     # neighbours in number are neighbours in space
     with pytest.raises(ValueError):
         sz.voronoi_field(10, order="hilbert")
+
+
+def test_matlab_drop_in_keeps_the_reference_signature_and_its_pieces_exist():
+    """subzero_b200/matlab/floe_interactions_all.m is the file a maintainer puts ahead of the reference's on the path: same
+    function line as floe_interactions_all.m:1, the pre-step `x` that the kill rule of :282 reads is defined, ghosts are
+    materialised for the ridging / rafting tail, and the tail itself is the generated function (never shipped)."""
+    import re
+    d = os.path.join(ROOT, "subzero_b200", "matlab")
+    src = open(os.path.join(d, "floe_interactions_all.m")).read()
+    norm = lambda s: re.sub(r"\s+", "", s)
+    want = ("function[Floe,dissolvedNEW]=floe_interactions_all(Floe,floebound,ocean,winds,c2_boundary,dt,HFo,min_floe_size,Nx,Ny,Nb,"
+            "dissolvedNEW,doInt,COLLISION,PERIODIC,RIDGING,RAFTING)")
+    assert norm(src.splitlines()[0]) == want
+    ref = "/root/reference/floe_interactions_all.m"
+    if os.path.exists(ref):
+        assert norm(open(ref).readline()) == want
+    body = norm(src)
+    assert "x=cat(1,Floe.Xi);" in body and body.index("x=cat(1,Floe.Xi);") < body.index("sz_contact_step(")          # :282 needs x
+    assert "isnan(x(i))" in body and "calc_trajectory(dt,ocean,winds,Floe(i),HFo,doInt)" in body                     # :281-282
+    assert "sz_floe_interactions_tail(" in body and "Floe=[FloeG];" in body
+    for f in ("sz_contact_step.m", "sz_contact_mex.cpp", "sz_make_tail.m"):
+        assert os.path.exists(os.path.join(d, f)), f
+    assert "ghost_parent" in open(os.path.join(d, "sz_contact_mex.cpp")).read()
+    # nothing of the reference's tail is stored in this repository
+    for f in os.listdir(d):
+        assert "Ridged" not in open(os.path.join(d, f), errors="ignore").read(), f
+
+
+def test_tail_generator_cuts_the_reference_tail(tmp_path):
+    """tools/make_matlab_tail.py (twin of sz_make_tail.m) on the reference as surveyed: the tail is floe_interactions_all.m
+    :288-511, and every variable it reads before writing is an argument of the generated function"""
+    import re
+    import sys
+    ref = "/root/reference/floe_interactions_all.m"
+    if not os.path.exists(ref):
+        pytest.skip("the reference tree is only present in the build container")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_matlab_tail as mt
+    out = mt.make_tail(ref, str(tmp_path / "sz_floe_interactions_tail.m"))
+    text = open(out).read().splitlines()
+    assert text[0].startswith("function [Floe,dissolvedNEW] = sz_floe_interactions_tail(") and text[-1] == "end"
+    first, last, body = mt.cut_tail(open(ref).read())
+    assert (first, last) == (288, 511) and text[2:-1] == body
+    used = set(re.findall(r"[A-Za-z_]\w*", "\n".join(l.split("%")[0] for l in body)))
+    for v in ("Floe", "floebound", "c2_boundary", "c2_boundary_poly", "min_floe_size", "Nx", "Ny", "Nb", "N0", "kill", "transfer", "dissolvedNEW", "doInt",
+              "PERIODIC", "RIDGING", "RAFTING", "id", "id3"):
+        assert v in used and v in mt.ARGS, v
+    # variables of the replaced head that the tail must NOT need
+    for v in ("x", "y", "rmax", "FloeNums", "parent", "N", "Lx", "Ly", "Modulus", "ocean", "winds", "dt", "HFo", "COLLISION"):
+        assert v not in used, v

@@ -278,3 +278,59 @@ def test_full_benchmark_size_1m_floes(ctx):
     rep = oracle.compare_steps(ctx, ref, rtol=RTOL, check_polys=False)
     assert rep["rows_bit_exact"] and rep["fx_bit_exact"] and rep["torque_bit_exact"] and rep["stress_bit_exact"]
 
+
+
+def soa_to_floe_dicts(soa):
+    """the reference's struct array as a list of dicts (the fields the contact loop reads, initialize_floe_values.m:12-52)"""
+    out = []
+    for i in range(soa.n):
+        a, b = int(soa.voff[i]), int(soa.voff[i + 1])
+        out.append({"c_alpha": np.stack([soa.vx[a:b], soa.vy[a:b]]), "Xi": soa.x[i], "Yi": soa.y[i], "rmax": soa.rmax[i], "h": soa.h[i], "area": soa.area[i],
+                    "Ui": soa.u[i], "Vi": soa.v[i], "ksi_ice": soa.ksi[i], "alive": int(soa.alive[i])})
+    return out
+
+
+def test_drop_in_signature_with_ghost_structs(ctx):
+    """floe_interactions_all with the reference's argument list (floe_interactions_all.m:1; the Python twin of
+    subzero_b200/matlab/floe_interactions_all.m) on a periodic field: per-floe fields against the oracle, and -- with RIDGING
+    on -- the ghost structs Floe(N0+1:N) the reference's tail indexes (:312,327,401,416): parents, shifted centroids, their
+    own rows and column sums, and partner numbers > N0 in the originals' interactions resolving to them."""
+    from subzero_b200.contact import floe_interactions_all
+    prm, soa = sz.voronoi_field(900, seed=12)
+    c2 = np.array([[-prm.Lx, -prm.Lx, prm.Lx, prm.Lx, -prm.Lx], [-prm.Ly, prm.Ly, prm.Ly, -prm.Ly, -prm.Ly]])
+    ref = oracle.OracleStep(prm, soa, broad_mode=0)
+    roff, rrow = ref.rows()
+    ro, rg = ref.floe_outputs(), ref.ghosts()
+    N0, N = ref.summary.n0, ref.summary.n
+    assert N > N0
+    for ridging in (False, True):
+        Floe, dis, kill, transfer = floe_interactions_all(soa_to_floe_dicts(soa), None, None, None, c2, prm.dt, 0.0, 0.0, 1, 1, 0, 0.0, {"flag": True},
+                                                          True, True, ridging, False, Modulus=prm.modulus, ctx=ctx)
+        assert len(Floe) == (N if ridging else N0) and len(kill) == N0
+        for i in range(N0):
+            f = Floe[i]
+            assert np.array_equal(f["interactions"], rrow[roff[i]:roff[i + 1]], equal_nan=True)
+            assert f["OverlapArea"] == ro["overlap_area"][i] and f["collision_torque"] == ro["torque"][i]
+            assert f["collision_force"][0] == ro["fx"][i] and f["collision_force"][1] == ro["fy"][i]
+            assert f["Xi"] == ro["xi"][i] and f["Yi"] == ro["yi"][i] and f["potentialInteractions"] == []
+        assert np.array_equal(kill, ro["kill"]) and np.array_equal(transfer, ro["transfer"])
+    seen_ghost_partner = False
+    for k in range(N - N0):
+        g = Floe[N0 + k]
+        p = int(rg["parent"][k]) - 1
+        assert g["Xi"] == rg["x"][k] and g["Yi"] == rg["y"][k]
+        assert g["area"] == Floe[p]["area"] and g["h"] == Floe[p]["h"] and np.array_equal(g["c_alpha"], Floe[p]["c_alpha"])
+        rows = rrow[roff[N0 + k]:roff[N0 + k + 1]]
+        assert np.array_equal(g["interactions"], rows, equal_nan=True)
+        sx = sy = st = 0.0
+        for r in rows:                                  # MATLAB's column sum, top to bottom (:234-235)
+            sx, sy, st = sx + r[1], sy + r[2], st + r[5]
+        assert g["collision_force"][0] == sx and g["collision_force"][1] == sy and g["collision_torque"] == st
+        assert g["OverlapArea"] == pytest.approx(rows[:, 6].sum(), rel=1e-12, abs=0)
+    for i in range(N0):
+        partners = Floe[i]["interactions"][:, 0]
+        for q in partners[np.isfinite(partners)]:
+            if q > N0:
+                seen_ghost_partner = True
+                assert abs(int(rg["floe_num"][int(q) - 1 - N0])) >= 1 and Floe[int(q) - 1]["area"] > 0     # Floe(partner) exists for the tail
+    assert seen_ghost_partner
