@@ -287,6 +287,22 @@ int sz_eulerian_data(SzContext* ctx, int32_t Nx, int32_t Ny, double xmin, double
                      const double* mass, const double* overlap_area, const double* dUi_p, const double* dVi_p, const double* stress, const double* strain,
                      double* out);
 
+/* ---- SURVEY.md 8f row f4, second half: the bounding-radius pair searches of Physical_Processes/weld.m:29-81 and
+ * polygon_operations/FloeSimplify.m:13-31 on the resident floes (positions after sz_trajectory_step when the device
+ * integrates), over a cell grid like the contact step's broad phase.  Predicate of both (weld.m:67, FloeSimplify.m:20):
+ *   alive(j) && d > 1 && d < rmax(i) + rmax(j),   d = sqrt((Xi(i)-Xi(j))^2 + (Yi(i)-Yi(j))^2),   partners ascending j.
+ * mode 0 (weld): the first Nb floes are cut off (:25); the others are binned on an Nx x Ny grid, Binx = fix((Xi-xmin)/
+ *   (xmax-xmin)*Nx+1) and the same in y (:35-36; xmin..ymax = min(x), max(x), min(y), max(y) of the colon vectors of :31-32),
+ *   bin number (Binx-1)*Ny + Biny (:40-48), and a floe only records partners of ITS bin (:56-81).  One query per floe of the
+ *   cut list; bin [n0-Nb] = bin number, 0 = in no bin; partners are 1-based positions in the CUT list Floe(1+Nb:end) (the
+ *   bin-local floeNum of :68 is the rank of that position within the bin).  count / idx unused.
+ * mode 1 (FloeSimplify): `count` query floes idx (1-based positions in the resident list, host or device memory) against the
+ *   whole list (FloeOld of Subzero.m:170-186); partners are 1-based positions in the resident list.  Nb / grid unused; bin = 0.
+ * Results stay on the device until fetched: off [nq + 1] into partner [n_partners]; any pointer may be NULL. */
+int sz_pair_search(SzContext* ctx, int32_t mode, int32_t Nb, int32_t Nx, int32_t Ny, double xmin, double xmax, double ymin, double ymax,
+                   int32_t count, const int32_t* idx, int64_t* n_partners);
+int sz_get_pair_search(SzContext* ctx, int32_t* bin, int64_t* off, int32_t* partner);
+
 /* diagnostic: device time (CUDA events, ms) of the last step by phase:
  * [0] ghost floes (floe_interactions_all.m:16-66)   [1] broad phase (:68-120)
  * [2] narrow phase + force law (:125-174)           [3] mirror/torque/sums (:186-265)   [4] whole step */

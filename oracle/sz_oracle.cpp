@@ -1234,4 +1234,62 @@ int szo_corner_eligibility(const SzFloesSoA* f, const int64_t* row_off, const do
     return (int)pos;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SURVEY.md 8f row f4, second half: the bounding-radius pair searches of weld.m and FloeSimplify.m.
+//
+// szo_weld_search -- Physical_Processes/weld.m:25-81 restated literally.  The first Nb (boundary) floes are cut off (:25), the
+// rest are binned on an Nx x Ny grid (:31-36: Binx = fix((Xi-min(x))/(max(x)-min(x))*Nx+1), the same for y; xmin..ymax are
+// min(x), max(x), min(y), max(y) of the colon vectors of :31-32 as the caller evaluated them), bin `count` = (i-1)*Ny + j holds
+// the floes with Binx == i and Biny == j in their original order (:40-48).  Inside a bin floe i records every floe j of the
+// SAME bin with  alive(j) && d > 1 && d < rmax(i)+rmax(j),  d = sqrt((Xi(i)-Xi(j))^2 + (Yi(i)-Yi(j))^2), ascending j (:66-79).
+// Output, per floe q of the cut list (q = 0 .. n-Nb-1): bin[q] = count (1-based) or 0 when the floe is in no bin;
+// partner[off[q] .. off[q+1]) = partners as 1-BASED positions in the cut list, ascending (their bin-local numbers floeNum are
+// the ranks of those positions within the bin).  Returns the number of partners, or -1 when cap is too small.
+int64_t szo_weld_search(const SzFloesSoA* f, int Nb, int Nx, int Ny, double xmin, double xmax, double ymin, double ymax,
+                        int32_t* bin, int64_t* off, int32_t* partner, int64_t cap)
+{
+    const int n = f->n - Nb;
+    if (n <= 0) { if (off) off[0] = 0; return 0; }
+    std::vector<int> bx(n), by(n);
+    auto fixd = [](double v) { return std::trunc(v); };
+    for (int q = 0; q < n; ++q) {
+        const double X = f->x[Nb + q], Y = f->y[Nb + q];
+        const double a = fixd((X - xmin) / (xmax - xmin) * Nx + 1), b = fixd((Y - ymin) / (ymax - ymin) * Ny + 1);      // :35-36
+        bx[q] = (a >= 1 && a <= Nx) ? (int)a : 0; by[q] = (b >= 1 && b <= Ny) ? (int)b : 0;                                // NaN compares false
+        bin[q] = (bx[q] && by[q]) ? (bx[q] - 1) * Ny + by[q] : 0;                                                          // :40-48
+    }
+    std::vector<std::vector<int>> members((size_t)Nx * Ny + 1);
+    for (int q = 0; q < n; ++q) if (bin[q]) members[bin[q]].push_back(q);
+    int64_t pos = 0; off[0] = 0;
+    for (int q = 0; q < n; ++q) {
+        if (bin[q]) {
+            const double Xi = f->x[Nb + q], Yi = f->y[Nb + q], ri = f->rmax[Nb + q];
+            for (int j : members[bin[q]]) {                                                                                // :66-67, j ascending
+                const double dx = Xi - f->x[Nb + j], dy = Yi - f->y[Nb + j];
+                const double d = std::sqrt(dx * dx + dy * dy);
+                if (f->alive[Nb + j] && d > 1 && d < (ri + f->rmax[Nb + j])) { if (pos >= cap) return -1; partner[pos++] = j + 1; }
+            }
+        }
+        off[q + 1] = pos;
+    }
+    return pos;
+}
+// szo_simplify_search -- polygon_operations/FloeSimplify.m:13-31: the floes Floe0(j) that may overlap the floe about to be
+// simplified:  alive(j) && d > 1 && d < floe.rmax + rmax(j),  ascending j over the whole list.  idx: `count` floe numbers
+// (1-based) whose own record in `f` is the query floe (Subzero.m:176-186 passes Floe(ii) and the list).
+int64_t szo_simplify_search(const SzFloesSoA* f, int count, const int32_t* idx, int64_t* off, int32_t* partner, int64_t cap)
+{
+    int64_t pos = 0; off[0] = 0;
+    for (int q = 0; q < count; ++q) {
+        const int i = idx[q] - 1;
+        for (int j = 0; j < f->n; ++j) {
+            const double dx = f->x[i] - f->x[j], dy = f->y[i] - f->y[j];
+            const double d = std::sqrt(dx * dx + dy * dy);
+            if (f->alive[j] && d > 1 && d < (f->rmax[i] + f->rmax[j])) { if (pos >= cap) return -1; partner[pos++] = j + 1; }
+        }
+        off[q + 1] = pos;
+    }
+    return pos;
+}
+
 }  // extern "C"

@@ -56,6 +56,9 @@ int  szo_calc_eulerian_data(const SzFloesSoA* f, const double* mass, const doubl
 int  szo_corner_eligibility(const SzFloesSoA* f, const int64_t* row_off, const double* rows, int count, const int32_t* idx, int Nb,
                             double Lx, double Ly, const double* boxx, const double* boxy, int nbox,
                             int64_t* da_off, uint8_t* da, int64_t vcap);
+int64_t szo_weld_search(const SzFloesSoA* f, int Nb, int Nx, int Ny, double xmin, double xmax, double ymin, double ymax,
+                        int32_t* bin, int64_t* off, int32_t* partner, int64_t cap);
+int64_t szo_simplify_search(const SzFloesSoA* f, int count, const int32_t* idx, int64_t* off, int32_t* partner, int64_t cap);
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,8 @@ PROTOTYPES = {
     "sz_corner_mask": (C.c_int, [C.c_void_p, C.c_int32, c_ip, C.c_int32, c_lp]),
     "sz_get_corner_mask": (C.c_int, [C.c_void_p, c_lp, c_bp]),
     "sz_eulerian_data": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "sz_pair_search": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, c_ip, c_lp]),
+    "sz_get_pair_search": (C.c_int, [C.c_void_p, c_ip, c_lp, c_ip]),
     "sz_get_trajectory": (C.c_int, [C.c_void_p] + [c_dp] * 6 + [c_bp] + [c_dp] * 10 + [c_ip, c_dp, c_dp]),
     "sz_get_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "sz_get_narrow_class_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

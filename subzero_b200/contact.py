@@ -160,6 +160,27 @@ class ContactContext:
         abi.check(abi.lib().sz_trajectory_step(self._h, C.byref(p), C.byref(ns), C.byref(no)))
         return ns.value
 
+    # ---- weld.m:29-81 / FloeSimplify.m:13-31: the bounding-radius pair searches on the resident floes
+    def weld_search(self, Nb, Nx, Ny, xmin, xmax, ymin, ymax):
+        """returns (bin [n0-Nb], off [n0-Nb+1], partner): bin number (Binx-1)*Ny+Biny of every floe of the cut list
+        Floe(1+Nb:end) (0 = in no bin) and its same-bin partners as 1-based positions in the cut list, ascending"""
+        npn = C.c_int64()
+        abi.check(abi.lib().sz_pair_search(self._h, 0, int(Nb), int(Nx), int(Ny), float(xmin), float(xmax), float(ymin), float(ymax), 0, None, C.byref(npn)))
+        nq = max(0, self._n0 - int(Nb))
+        b, off, pt = np.empty(nq, np.int32), np.empty(nq + 1, np.int64), np.empty(npn.value, np.int32)
+        abi.check(abi.lib().sz_get_pair_search(self._h, abi._ptr(b, abi.c_ip), abi._ptr(off, abi.c_lp), abi._ptr(pt, abi.c_ip)))
+        return b, off, pt
+
+    def simplify_search(self, idx):
+        """idx: floe numbers (1-based) about to be simplified; returns (off [count+1], partner) with partners as 1-based
+        positions in the resident list, ascending"""
+        idx = np.ascontiguousarray(idx, np.int32)
+        npn = C.c_int64()
+        abi.check(abi.lib().sz_pair_search(self._h, 1, 0, 1, 1, 0.0, 1.0, 0.0, 1.0, idx.shape[0], abi._ptr(idx, abi.c_ip), C.byref(npn)))
+        off, pt = np.empty(idx.shape[0] + 1, np.int64), np.empty(npn.value, np.int32)
+        abi.check(abi.lib().sz_get_pair_search(self._h, None, abi._ptr(off, abi.c_lp), abi._ptr(pt, abi.c_ip)))
+        return off, pt
+
     # ---- fracture_floe.m:12-52: deformation of the floes about to be fractured (consumer of the contact rows)
     def fracture_deform(self, idx):
         """idx: floe numbers (1-based) of the last contact step's list; returns dict changed xi yi area vert_off cx cy"""

@@ -153,6 +153,9 @@ struct SzContext {
     int oc_nx = 0, oc_ny = 0, npts = 0; bool have_ocean = false, have_points = false, traj_do_int = false;
     double oc_fc = 0, oc_turn = 0, oc_rho0 = 1027, oc_Cd = 3e-3, oc_rho_air = 1.2, oc_Cd_atm = 1e-3;
     DBuf<int> t_scount, t_flags;
+    // weld / FloeSimplify pair searches
+    DBuf<int> se_bin, se_cnt, se_off, se_q, se_cid, se_ccnt, se_cstart, se_sidx, se_tmp, se_out; DBuf<double> se_sx, se_sy, se_sr;
+    int se_nq = 0, se_np = 0, se_first = 0; bool se_weld = false, have_search = false;
     // clip batch
     int clip_count = 0; i64 clip_paths = 0, clip_verts = 0;
     DBuf<int> c_method, c_status, c_path_start, c_npaths, c_path_vstart, c_path_len, c_listM, c_listL;
@@ -840,13 +843,13 @@ extern "C" void sz_destroy(SzContext* c)
     DBuf<double>* db[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi, &c->vx, &c->vy, &c->bx, &c->by, &c->boxx, &c->boxy, &c->ex, &c->ey,
                           &c->erootx, &c->erooty, &c->s_x, &c->s_y, &c->s_r, &c->povl, &c->wovl, &c->row_pool, &c->rows, &c->osum, &c->e_ov, &c->o_fx, &c->o_fy, &c->o_tq, &c->o_ov, &c->o_stress, &c->o_xi, &c->o_yi,
                           &c->oc_Xo, &c->oc_Yo, &c->oc_U, &c->oc_V, &c->oc_Wu, &c->oc_Wv, &c->pt_x, &c->pt_y, &c->t_strain,
-                          &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy, &c->cr_ex, &c->cr_ey, &c->eu_lx, &c->eu_ly, &c->eu_in, &c->eu_area, &c->eu_out};
+                          &c->fr_xi, &c->fr_yi, &c->fr_area, &c->fr_vx, &c->fr_vy, &c->cr_ex, &c->cr_ey, &c->eu_lx, &c->eu_ly, &c->eu_in, &c->eu_area, &c->eu_out, &c->se_sx, &c->se_sy, &c->se_sr};
     for (auto* b : db) b->release();
     DBuf<int>* ib[] = {&c->egid, &c->voff, &c->esrc, &c->efn, &c->eparent, &c->gx_of, &c->gy_of, &c->flag, &c->pos, &c->scan_tmp, &c->cid, &c->cell_cnt, &c->cell_start, &c->s_idx,
                        &c->pcnt, &c->pair_off, &c->pi, &c->pj, &c->pstatus, &c->pnrows, &c->prow_start, &c->bins, &c->bin_fill, &c->stage, &c->listC, &c->listS, &c->listT, &c->wlistT, &c->env, &c->listM, &c->listL, &c->wstatus, &c->wnrows, &c->wrow_start,
                        &c->wlistM, &c->wlistL, &c->poly_path_start, &c->poly_npaths, &c->path_vstart, &c->path_len, &c->tcnt, &c->toff, &c->tlist, &c->rcnt, &c->row_off,
                        &c->kill_i, &c->transfer_i, &c->tmax, &c->o_kill, &c->o_transfer, &c->c_method, &c->c_status, &c->c_path_start, &c->c_npaths, &c->c_path_vstart,
-                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status, &c->cr_idx, &c->cr_nv, &c->cr_off, &c->cr_esrc, &c->eu_lsrc, &c->eu_icnt, &c->eu_ioff, &c->eu_cell, &c->eu_q, &c->eu_status, &c->eu_iota, &c->eu_sorted, &c->eu_keys, &c->eu_ccnt, &c->eu_coff, &c->eu_listL, &c->ho_st};
+                       &c->c_path_len, &c->c_listM, &c->c_listL, &c->fr_idx, &c->fr_vstart, &c->fr_vcount, &c->fr_status, &c->cr_idx, &c->cr_nv, &c->cr_off, &c->cr_esrc, &c->eu_lsrc, &c->eu_icnt, &c->eu_ioff, &c->eu_cell, &c->eu_q, &c->eu_status, &c->eu_iota, &c->eu_sorted, &c->eu_keys, &c->eu_ccnt, &c->eu_coff, &c->eu_listL, &c->ho_st, &c->se_bin, &c->se_cnt, &c->se_off, &c->se_q, &c->se_cid, &c->se_ccnt, &c->se_cstart, &c->se_sidx, &c->se_tmp, &c->se_out};
     for (auto* b : ib) b->release();
     DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed, &c->cr_da, &c->cr_ealive, &c->eu_tmp};
     for (auto* b : ub) b->release();
@@ -2272,6 +2275,211 @@ extern "C" int sz_get_clip_polys(SzContext* c, int64_t* pair_path_off, int64_t* 
                         c->pvx.p, c->pvy.p, (int)c->summary.n_clip_verts, pair_path_off, path_vert_off, x, y);
 }
 
+// ------------------------------------------------------------------------------------------------ weld / FloeSimplify pair searches
+// SURVEY.md 8f row f4 (second half): the bounding-radius searches of Physical_Processes/weld.m:29-81 and
+// polygon_operations/FloeSimplify.m:13-31 on the resident floes, over the same kind of cell grid as K1.
+//   weld      the floes after the first Nb are binned on an Nx x Ny grid (:31-48); floe i records every floe j OF ITS BIN with
+//             alive(j) && d > 1 && d < rmax(i)+rmax(j), ascending j (:66-79)
+//   simplify  the same predicate for each query floe against the whole list (FloeSimplify.m:20-31)
+struct SearchArgs {
+    int n0, first, weld, nq; const int* qidx; GridDesc g; double rmax_max;
+    const double* x; const double* y; const double* rmax; const uint8_t* alive; const int* bin;
+    const int* cell_start; const int* s_idx; const double* s_x; const double* s_y; const double* s_r;
+    int* cnt; const int* off; int* out;
+};
+// bins of weld.m:35-36,40-48 (0 = in no bin), bounding box and largest rmax of the searched floes
+__global__ void search_prep_kernel(int n0, int first, int weld, int Nx, int Ny, double xmin, double xmax, double ymin, double ymax,
+                                   const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ rmax, int* __restrict__ bin, Counters* c)
+{
+    double xmn = SZ_INF, xmx = -SZ_INF, ymn = SZ_INF, ymx = -SZ_INF, rm = 0;
+    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += gridDim.x * blockDim.x) {
+        const double X = x[i], Y = y[i];
+        if (X == X && Y == Y) { xmn = fmin(xmn, X); xmx = fmax(xmx, X); ymn = fmin(ymn, Y); ymx = fmax(ymx, Y); }
+        const double r = rmax[i]; if (r > rm) rm = r;
+        int b = 0;
+        if (weld) {
+            const double a = trunc((X - xmin) / (xmax - xmin) * Nx + 1), bb = trunc((Y - ymin) / (ymax - ymin) * Ny + 1);     // fix(...)
+            if (a >= 1 && a <= Nx && bb >= 1 && bb <= Ny) b = ((int)a - 1) * Ny + (int)bb;
+        }
+        bin[i] = b;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        xmn = fmin(xmn, __shfl_xor_sync(0xffffffffu, xmn, d)); xmx = fmax(xmx, __shfl_xor_sync(0xffffffffu, xmx, d));
+        ymn = fmin(ymn, __shfl_xor_sync(0xffffffffu, ymn, d)); ymx = fmax(ymx, __shfl_xor_sync(0xffffffffu, ymx, d));
+        rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (xmn <= xmx) { atomicMin(&c->bbox[0], enc_d(xmn)); atomicMax(&c->bbox[1], enc_d(xmx)); atomicMin(&c->bbox[2], enc_d(ymn)); atomicMax(&c->bbox[3], enc_d(ymx)); }
+        atomicMax(&c->rmax_bits, enc_d(rm));
+    }
+}
+__global__ void search_cell_count_kernel(int n0, int first, GridDesc g, const double* __restrict__ x, const double* __restrict__ y, int* __restrict__ cid, int* __restrict__ cell_cnt)
+{
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    const double X = x[i], Y = y[i];
+    int c = -1;
+    if (X == X && Y == Y) { c = cell_coord(Y, g.y0, g.cell, g.ny) * g.nx + cell_coord(X, g.x0, g.cell, g.nx); atomicAdd(&cell_cnt[c], 1); }
+    cid[i] = c;
+}
+__global__ void search_cell_fill_kernel(int n0, int first, const int* __restrict__ cid, const int* __restrict__ cell_start, int* __restrict__ cell_pos,
+                                        const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ rmax,
+                                        int* __restrict__ s_idx, double* __restrict__ s_x, double* __restrict__ s_y, double* __restrict__ s_r)
+{
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    const int c = cid[i];
+    if (c < 0) return;
+    const int t = cell_start[c] + atomicAdd(&cell_pos[c], 1);
+    s_idx[t] = i; s_x[t] = x[i]; s_y[t] = y[i]; s_r[t] = rmax[i];
+}
+// one warp per query floe, like broad_kernel: lanes stride over the cell rows around the floe, ballot + popc compaction
+template <bool FILL>
+__global__ void __launch_bounds__(256) search_kernel(const SearchArgs a)
+{
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= a.nq) return;
+    const int i = a.qidx ? a.qidx[q] : a.first + q;
+    const double xi = a.x[i], yi = a.y[i];
+    const int bi = a.weld ? a.bin[i] : 1;
+    int count = 0;
+    const int off = FILL ? a.off[q] : 0;
+    if (xi == xi && yi == yi && bi != 0) {
+        const double ri = a.rmax[i];
+        const int cxi = cell_coord(xi, a.g.x0, a.g.cell, a.g.nx), cyi = cell_coord(yi, a.g.y0, a.g.cell, a.g.ny);
+        const int R = (int)((ri + a.rmax_max) / a.g.cell) + 1;
+        const int cx0 = cxi - R > 0 ? cxi - R : 0, cx1 = cxi + R < a.g.nx ? cxi + R : a.g.nx - 1;
+        for (int cy = (cyi - R > 0 ? cyi - R : 0); cy <= cyi + R && cy < a.g.ny; ++cy) {
+            const int t0 = a.cell_start[cy * a.g.nx + cx0], t1 = a.cell_start[cy * a.g.nx + cx1 + 1];
+            for (int tb = t0; tb < t1; tb += 32) {
+                const int t = tb + lane;
+                bool ok = false; int j = -1;
+                if (t < t1) {
+                    j = a.s_idx[t];
+                    const double dx = xi - a.s_x[t], dy = yi - a.s_y[t];
+                    const double d = sqrt(dx * dx + dy * dy);
+                    ok = a.alive[j] && d > 1 && d < (ri + a.s_r[t]) && (!a.weld || a.bin[j] == bi);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (FILL && ok) a.out[off + count + __popc(m & ((1u << lane) - 1))] = j;
+                count += __popc(m);
+            }
+        }
+    }
+    if (!FILL && lane == 0) a.cnt[q] = count;
+}
+// ascending order inside every segment (any length): each lane ranks its elements against the whole segment
+__global__ void __launch_bounds__(256) segment_rank_sort_kernel(int nseg, const int* __restrict__ off, const int* __restrict__ in, int* __restrict__ out, int base)
+{
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nseg) return;
+    const int o = off[q], c = off[q + 1] - o;
+    for (int k = lane; k < c; k += 32) {
+        const int v = in[o + k];
+        int rank = 0;
+        for (int m = 0; m < c; ++m) rank += (in[o + m] < v);
+        out[o + rank] = v - base + 1;
+    }
+}
+extern "C" int sz_pair_search(SzContext* c, int32_t mode, int32_t Nb, int32_t Nx, int32_t Ny, double xmin, double xmax, double ymin, double ymax,
+                              int32_t count, const int32_t* idx, int64_t* n_partners)
+{
+    if (!c) { sz_set_error("sz_pair_search: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_input || c->ext_mode) { sz_set_error("sz_pair_search: upload the floes first (single-GPU list)"); return SZ_ERR_STATE; }
+    const bool weld = mode == 0;
+    if (mode != 0 && mode != 1) { sz_set_error("sz_pair_search: mode must be 0 (weld) or 1 (FloeSimplify)"); return SZ_ERR_ARG; }
+    if (weld && (Nb < 0 || Nx < 1 || Ny < 1 || !(xmax > xmin) || !(ymax > ymin))) { sz_set_error("sz_pair_search: bad Nb / grid"); return SZ_ERR_ARG; }
+    if (!weld && (count < 0 || (count > 0 && !idx))) { sz_set_error("sz_pair_search: idx missing"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const int n0 = c->n0;
+    const int first = weld ? std::min(Nb, n0) : 0;
+    const int nq = weld ? n0 - first : count;
+    c->have_search = false; c->se_nq = nq; c->se_np = 0; c->se_weld = weld; c->se_first = first;
+    CK(c->se_bin.ensure(n0 + 1)); CK(c->se_cnt.ensure(nq + 2)); CK(c->se_off.ensure(nq + 2)); CK(c->se_q.ensure(nq + 1));
+    if (!weld && nq > 0) {
+        std::vector<int> q0(nq);
+        cudaPointerAttributes pa; bool host = true;
+        if (cudaPointerGetAttributes(&pa, idx) == cudaSuccess) host = (pa.type == cudaMemoryTypeUnregistered || pa.type == cudaMemoryTypeHost); else cudaGetLastError();
+        std::vector<int> tmp(nq);
+        if (host) memcpy(tmp.data(), idx, (size_t)nq * 4); else CK(cudaMemcpy(tmp.data(), idx, (size_t)nq * 4, cudaMemcpyDefault));
+        for (int k = 0; k < nq; ++k) { if (tmp[k] < 1 || tmp[k] > n0) { sz_set_error("sz_pair_search: floe number %d out of range", tmp[k]); return SZ_ERR_ARG; } q0[k] = tmp[k] - 1; }
+        CK(cudaMemcpyAsync(c->se_q.p, q0.data(), (size_t)nq * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st));
+    }
+    if (n_partners) *n_partners = 0;
+    if (nq == 0 || n0 - first <= 0) { CK(cudaMemsetAsync(c->se_off.p, 0, (size_t)(nq + 1) * 4, st)); CK(cudaStreamSynchronize(st)); c->have_search = true; return SZ_OK; }
+    {
+        Counters init; memset(&init, 0, sizeof(init));
+        init.bbox[0] = enc_d(SZ_INF); init.bbox[1] = enc_d(-SZ_INF); init.bbox[2] = enc_d(SZ_INF); init.bbox[3] = enc_d(-SZ_INF); init.rmax_bits = enc_d(0.0);
+        *c->h_cnt = init;
+        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
+    }
+    const int ns = n0 - first;
+    ++g_launches; search_prep_kernel<<<std::min(nblk(ns, 256), 148 * 8), 256, 0, st>>>(n0, first, weld ? 1 : 0, Nx, Ny, xmin, xmax, ymin, ymax, c->x.p, c->y.p, c->rmax.p, c->se_bin.p, c->d_cnt);
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    GridDesc g; g.x0 = g.y0 = 0; g.cell = 1; g.nx = g.ny = 1;
+    const double rm = dec_d(c->h_cnt->rmax_bits);
+    {
+        const double bx0 = dec_d(c->h_cnt->bbox[0]), bx1 = dec_d(c->h_cnt->bbox[1]), by0 = dec_d(c->h_cnt->bbox[2]), by1 = dec_d(c->h_cnt->bbox[3]);
+        if (bx0 <= bx1 && std::isfinite(bx0) && std::isfinite(bx1) && std::isfinite(by0) && std::isfinite(by1)) {
+            g.x0 = bx0; g.y0 = by0;
+            double cell = 2 * rm; if (!(cell > 0) || !std::isfinite(cell)) cell = 1;
+            const double dens = std::sqrt(4.0 * (bx1 - bx0) * (by1 - by0) / std::max(1, ns));
+            if (dens > 0 && std::isfinite(dens)) cell = std::min(cell, std::max(cell / 8, dens));
+            while ((bx1 - bx0) / cell * ((by1 - by0) / cell) > 1.6e7) cell *= 2;
+            g.cell = cell; g.nx = (int)((bx1 - bx0) / cell) + 1; g.ny = (int)((by1 - by0) / cell) + 1;
+        }
+    }
+    const int ncell = g.nx * g.ny;
+    CK(c->se_cid.ensure(n0 + 1)); CK(c->se_ccnt.ensure(ncell + 2)); CK(c->se_cstart.ensure(ncell + 2));
+    CK(c->se_sidx.ensure(n0 + 1)); CK(c->se_sx.ensure(n0 + 1)); CK(c->se_sy.ensure(n0 + 1)); CK(c->se_sr.ensure(n0 + 1));
+    CK(c->scan_tmp.ensure(scan_tmp_ints(std::max<size_t>((size_t)ncell + 2, (size_t)nq + 2))));
+    CK(cudaMemsetAsync(c->se_ccnt.p, 0, (size_t)(ncell + 1) * 4, st));
+    ++g_launches; search_cell_count_kernel<<<nblk(ns, 256), 256, 0, st>>>(n0, first, g, c->x.p, c->y.p, c->se_cid.p, c->se_ccnt.p);
+    exclusive_scan(c->se_ccnt.p, ncell, c->se_cstart.p, ncell + 1, c->scan_tmp.p, st);
+    CK(cudaMemsetAsync(c->se_ccnt.p, 0, (size_t)(ncell + 1) * 4, st));
+    ++g_launches; search_cell_fill_kernel<<<nblk(ns, 256), 256, 0, st>>>(n0, first, c->se_cid.p, c->se_cstart.p, c->se_ccnt.p, c->x.p, c->y.p, c->rmax.p, c->se_sidx.p, c->se_sx.p, c->se_sy.p, c->se_sr.p);
+    SearchArgs a; memset(&a, 0, sizeof(a));
+    a.n0 = n0; a.first = first; a.weld = weld ? 1 : 0; a.nq = nq; a.qidx = weld ? nullptr : c->se_q.p; a.g = g; a.rmax_max = rm;
+    a.x = c->x.p; a.y = c->y.p; a.rmax = c->rmax.p; a.alive = c->alive.p; a.bin = c->se_bin.p;
+    a.cell_start = c->se_cstart.p; a.s_idx = c->se_sidx.p; a.s_x = c->se_sx.p; a.s_y = c->se_sy.p; a.s_r = c->se_sr.p;
+    a.cnt = c->se_cnt.p; a.off = c->se_off.p;
+    ++g_launches; search_kernel<false><<<nblk(32 * (i64)nq, 256), 256, 0, st>>>(a);
+    exclusive_scan(c->se_cnt.p, nq, c->se_off.p, nq + 1, c->scan_tmp.p, st);
+    CK(cudaMemcpyAsync(D_CNT(n_pairs), c->se_off.p + nq, 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    CKS(read_counters(c));
+    const int np = c->h_cnt->n_pairs;
+    CK(c->se_tmp.ensure(np + 1)); CK(c->se_out.ensure(np + 1));
+    if (np > 0) {
+        a.out = c->se_tmp.p;
+        ++g_launches; search_kernel<true><<<nblk(32 * (i64)nq, 256), 256, 0, st>>>(a);
+        ++g_launches; segment_rank_sort_kernel<<<nblk(32 * (i64)nq, 256), 256, 0, st>>>(nq, c->se_off.p, c->se_tmp.p, c->se_out.p, first);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    c->se_np = np; c->have_search = true;
+    if (n_partners) *n_partners = np;
+    return SZ_OK;
+}
+extern "C" int sz_get_pair_search(SzContext* c, int32_t* bin, int64_t* off, int32_t* partner)
+{
+    if (!c) { sz_set_error("sz_get_pair_search: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_search) { sz_set_error("sz_get_pair_search: no search has been run"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const int nq = c->se_nq;
+    if (bin) { if (c->se_weld) D2H(bin, c->se_bin.p + c->se_first, (size_t)nq * 4); else memset(bin, 0, (size_t)nq * 4); }
+    if (off) {
+        std::vector<int> tmp(nq + 1);
+        CK(cudaMemcpyAsync(tmp.data(), c->se_off.p, (size_t)(nq + 1) * 4, cudaMemcpyDefault, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k <= nq; ++k) off[k] = tmp[k];
+    }
+    D2H(partner, c->se_out.p, (size_t)c->se_np * 4);
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
 // ------------------------------------------------------------------------------------------------ clip batch
 extern "C" int sz_clip_batch(SzContext* c, int32_t count, const int32_t* method, const int64_t* soff, const int64_t* sx, const int64_t* sy,
                              const int64_t* coff, const int64_t* cx, const int64_t* cy, int64_t* n_paths, int64_t* n_verts)

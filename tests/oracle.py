@@ -74,6 +74,10 @@ def lib():
         l.szo_corner_eligibility.restype = C.c_int
         l.szo_corner_eligibility.argtypes = [C.POINTER(abi.SzFloesSoA), abi.c_lp, abi.c_dp, C.c_int, abi.c_ip, C.c_int, C.c_double, C.c_double, abi.c_dp, abi.c_dp, C.c_int,
                                              abi.c_lp, abi.c_bp, C.c_int64]
+        l.szo_weld_search.restype = C.c_int64
+        l.szo_weld_search.argtypes = [C.POINTER(abi.SzFloesSoA), C.c_int, C.c_int, C.c_int] + [C.c_double] * 4 + [abi.c_ip, abi.c_lp, abi.c_ip, C.c_int64]
+        l.szo_simplify_search.restype = C.c_int64
+        l.szo_simplify_search.argtypes = [C.POINTER(abi.SzFloesSoA), C.c_int, abi.c_ip, abi.c_lp, abi.c_ip, C.c_int64]
         _lib = l
     return _lib
 
@@ -277,6 +281,35 @@ def calc_eulerian_data(floes, mass, Nx, Ny, box, periodic, overlap_area=None, dU
                                      *(float(b) for b in box), int(bool(periodic)), p(out, D))
     assert r == 0, r
     return {k: out[i] for i, k in enumerate(EULERIAN_FIELDS)}
+
+
+def weld_search(floes, Nb, Nx, Ny, xmin, xmax, ymin, ymax):
+    """the oracle's literal restatement of weld.m:25-81 (bins + same-bin radius search); returns (bin, off, partner)"""
+    nq = max(0, floes.n - Nb)
+    b, off = np.zeros(nq, np.int32), np.zeros(nq + 1, np.int64)
+    cap = 64 * max(1, nq) + 1024
+    while True:
+        pt = np.zeros(cap, np.int32)
+        view = floes.struct()
+        r = lib().szo_weld_search(C.byref(view), int(Nb), int(Nx), int(Ny), float(xmin), float(xmax), float(ymin), float(ymax),
+                                  abi._ptr(b, abi.c_ip), abi._ptr(off, abi.c_lp), abi._ptr(pt, abi.c_ip), cap)
+        if r >= 0:
+            return b, off, pt[:r]
+        cap *= 4
+
+
+def simplify_search(floes, idx):
+    """the oracle's restatement of FloeSimplify.m:13-31 for the floes idx (1-based); returns (off, partner)"""
+    idx = np.ascontiguousarray(idx, np.int32)
+    off = np.zeros(idx.shape[0] + 1, np.int64)
+    cap = 64 * max(1, idx.shape[0]) + 1024
+    while True:
+        pt = np.zeros(cap, np.int32)
+        view = floes.struct()
+        r = lib().szo_simplify_search(C.byref(view), idx.shape[0], abi._ptr(idx, abi.c_ip), abi._ptr(off, abi.c_lp), abi._ptr(pt, abi.c_ip), cap)
+        if r >= 0:
+            return off, pt[:r]
+        cap *= 4
 
 
 def _rel_err(a, b):
