@@ -106,6 +106,7 @@ typedef struct SzSummary {
     int32_t n_capacity_fail;  /* pairs that exceeded the largest size class */
     float   ms_device;        /* device time of the step (CUDA events), excluding host<->device copies */
     int64_t n_pairs_owned;    /* pairs whose first floe this context owns (== n_pairs unless an extended list was supplied) */
+    int32_t n_kill_events;    /* entries with a kill entry (merges, floe_interactions_all.m:138-145): the cross-rank fix-up of :175-179 only runs when some rank has one */
 } SzSummary;
 
 typedef struct SzContext SzContext;
@@ -145,6 +146,42 @@ int sz_upload_extended(SzContext* ctx, const SzParams* prm, const SzFloesSoA* en
 /* between topology changes only the motion state of the entries changes: refresh it in place ([n] each, NULL = keep) */
 int sz_update_extended_state(SzContext* ctx, const double* x, const double* y, const double* u, const double* v, const double* ksi,
                              const double* root_x, const double* root_y);
+
+/* ---- multi-GPU slabs, device-built list: one process per GPU, each rank OWNS a set of floes -- ascending
+ * global floe numbers `gid` (1-based, the numbering of the single-GPU run; any subset, e.g. a contiguous range after a sort by
+ * slab) -- and keeps their state and the integrator's resident on its GPU.  Every step the rank's part of the global extended
+ * floe list is rebuilt on the device from the CURRENT state, so the step is exact for floes that translate, rotate (c_alpha =
+ * A_rot c0, calc_trajectory.m:221-222), thin (:75-79) and die; nothing is cached between steps.  Per step, all on the context's
+ * stream (sz_set_stream) with no host synchronisation:
+ *   sz_slab_prepare(meta)            image flags of :28-31,49-52 from the current outlines, x-extents, largest rmax -> this rank's
+ *                                    meta record [sz_slab_meta_doubles(cap_img)] in DEVICE memory; the caller all-gathers the records
+ *   sz_slab_pack(all_meta, send)     global list positions of the rank's images (rank among all ranks' images, :33-36,54-57);
+ *                                    every own entry within reach (2 max rmax) of another rank's x-extent is packed for it: state,
+ *                                    FloeNums, root centroid and its CURRENT outline.  send = `world` blocks of
+ *                                    sz_slab_block_doubles(cap_rec, cap_vert) doubles; the caller runs one all-to-all of equal splits
+ *   sz_slab_build(recv, status)      received entries sorted by global position and merged with the own ones into the resident
+ *                                    extended list; status (device, 2 ints, may be NULL) = {capacity overflow, list length}
+ *   sz_step_resident                 pairs with at least one owned floe (straddling pairs are resolved on both sides, which keeps
+ *                                    every floe's rows bit-identical to the single-GPU run and replaces the return of partial forces)
+ *   sz_trajectory_step               integrates the owned floes (sz_trajectory_init after sz_slab_upload)
+ * Capacities: sz_slab_measure / sz_slab_measure_halo (host-synchronous) report the image and halo counts the current state
+ * needs; the caller agrees on cap_img / cap_rec / cap_vert across ranks and calls sz_slab_configure.  A later step that exceeds
+ * them raises the overflow status (and sz_step_resident's results are then invalid): measure, configure, repeat the step.
+ * Walls: pass `bnd` for a non-periodic domain; every rank resolves the wall contacts of the floes it owns.
+ * kill / transfer come back per owned floe BEFORE the serial fix-up of floe_interactions_all.m:175-179, which spans ranks. */
+int64_t sz_slab_meta_doubles(int32_t cap_img);
+int64_t sz_slab_block_doubles(int32_t cap_rec, int32_t cap_vert);
+int sz_slab_upload(SzContext* ctx, const SzParams* prm, const SzFloesSoA* owned, const SzBoundary* bnd, const int32_t* gid, int32_t n_global, int32_t rank, int32_t world);
+int sz_slab_measure(SzContext* ctx, double* local8 /* host: x-images, y-images of originals, y-images of x-images, x-extent of originals [2], of x-images [2], max rmax */);
+int sz_slab_measure_halo(SzContext* ctx, const double* all8 /* host [world*8] */, int64_t* rec_counts /* [world] */, int64_t* vert_counts /* [world] */);
+int sz_slab_configure(SzContext* ctx, int32_t cap_img, int32_t cap_rec, int32_t cap_vert);
+int sz_slab_prepare(SzContext* ctx, double* meta_dev);
+int sz_slab_pack(SzContext* ctx, const double* all_meta_dev, double* send_dev);
+int sz_slab_build(SzContext* ctx, const double* recv_dev, int32_t* status_dev);
+int sz_slab_get_positions(SzContext* ctx, int32_t* opos /* [n_owned] 0-based list positions */, int32_t* n_list);
+int sz_slab_get_list(SzContext* ctx, int32_t* gid, int32_t* floe_num, uint8_t* owned, double* x, double* y);   /* [n_list] each, any may be NULL */
+int sz_slab_get_outputs(SzContext* ctx, double* fx, double* fy, double* torque, double* overlap_area, double* stress, double* xi, double* yi,
+                        uint8_t* alive, int32_t* kill, int32_t* transfer);   /* per owned floe, like sz_get_floe_outputs */
 
 /* Device helpers of the slab step's fast path (subzero_b200/slabs.py): all pointers are DEVICE memory.
  * sz_slab_refresh: for the rank's own entries [originals | x-images | y-images] recompute the image centroids

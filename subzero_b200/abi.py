@@ -64,7 +64,7 @@ class SzSlabRefresh(C.Structure):
 class SzSummary(C.Structure):
     _fields_ = [("n0", C.c_int32), ("n", C.c_int32), ("n_pairs", C.c_int64), ("n_pairs_force", C.c_int64), ("n_rows", C.c_int64),
                 ("n_clip_paths", C.c_int64), ("n_clip_verts", C.c_int64), ("collision_count", C.c_double),
-                ("n_clipper_fail", C.c_int32), ("n_capacity_fail", C.c_int32), ("ms_device", C.c_float), ("n_pairs_owned", C.c_int64)]
+                ("n_clipper_fail", C.c_int32), ("n_capacity_fail", C.c_int32), ("ms_device", C.c_float), ("n_pairs_owned", C.c_int64), ("n_kill_events", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -84,6 +84,18 @@ PROTOTYPES = {
     "sz_update_extended_state": (C.c_int, [C.c_void_p] + [c_dp] * 7),
     "sz_slab_refresh": (C.c_int, [C.c_void_p, C.POINTER(SzSlabRefresh)]),
     "sz_slab_scatter": (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, C.c_int64, c_lp, C.c_int64]),
+    "sz_slab_meta_doubles": (C.c_int64, [C.c_int32]),
+    "sz_slab_block_doubles": (C.c_int64, [C.c_int32, C.c_int32]),
+    "sz_slab_upload": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), c_ip, C.c_int32, C.c_int32, C.c_int32]),
+    "sz_slab_measure": (C.c_int, [C.c_void_p, c_dp]),
+    "sz_slab_measure_halo": (C.c_int, [C.c_void_p, c_dp, c_lp, c_lp]),
+    "sz_slab_configure": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "sz_slab_prepare": (C.c_int, [C.c_void_p, c_dp]),
+    "sz_slab_pack": (C.c_int, [C.c_void_p, c_dp, c_dp]),
+    "sz_slab_build": (C.c_int, [C.c_void_p, c_dp, c_ip]),
+    "sz_slab_get_positions": (C.c_int, [C.c_void_p, c_ip, c_ip]),
+    "sz_slab_get_list": (C.c_int, [C.c_void_p, c_ip, c_ip, c_bp, c_dp, c_dp]),
+    "sz_slab_get_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
     "sz_get_floe_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),

@@ -51,6 +51,8 @@ extern "C" long long sz_launch_count(void) { return g_launches; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     sz_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); return SZ_ERR_CUDA; } } while (0)
 
+#define CKS(call) do { int r_ = (call); if (r_ != SZ_OK) return r_; } while (0)
+
 template <class T>
 struct DBuf {
     T* p = nullptr; size_t cap = 0;
@@ -80,7 +82,7 @@ struct Counters {
     int listC, listS, listT, listM, listL, wlistT, wlistM, wlistL;
     int listC0, listS0;            // list lengths before class C ran (listS grows by the pairs class C declines)
     int total_rows;
-    int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject;
+    int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject, n_kill_events;
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
     u64 rmax_bits;
     u64 n_fin_rows, n_inf_rows;
@@ -116,6 +118,11 @@ struct SzContext {
     int n = 0, n1 = 0;
     DBuf<double> ex, ey, erootx, erooty; DBuf<int> esrc, efn, eparent, gx_of, gy_of, egid; DBuf<uint8_t> ealive, eowned;
     bool ext_mode = false;          // extended list supplied by the caller (multi-GPU slabs), K0 skipped
+    // slab mode (sz_slab_*): the rank's owned floes are the resident originals [0, n0); halo records follow them in the body arrays and the
+    // extended list is rebuilt on the device every step
+    bool slab = false, sl_configured = false, sl_built = false; int sl_rank = 0, sl_world = 1, sl_nglobal = 0, sl_cap_img = 0, sl_cap_rec = 0, sl_cap_vert = 0, sl_nl_cap = 0;
+    struct SlabScratch* sl_scratch = nullptr;
+    DBuf<int> sl_ogid, sl_flag, sl_pos, sl_opos, sl_g, sl_sendcnt, sl_keys, sl_slots, sl_hnv, sl_hvoff; DBuf<uint8_t> sl_cub; DBuf<double> sl_out;
     int nout = 0;                   // entries with per-floe outputs: n0 (single GPU) or n (extended mode)
     DBuf<int> flag, pos, scan_tmp;
     // grid
@@ -730,11 +737,12 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
     a.osum[(size_t)m * 3] = sfx; a.osum[(size_t)m * 3 + 1] = sfy; a.osum[(size_t)m * 3 + 2] = st; a.e_ov[m] = ova;
     a.has_rows[m] = nr_total > 0;
     a.kill_i[m] = kill; a.transfer_i[m] = transfer;
+    if (kill) atomicAdd(&a.cnt->n_kill_events, 1);      // rare (merges)
     if (m < a.nout) {
         a.o_ov[m] = ova; a.o_xi[m] = xw; a.o_yi[m] = yw; a.o_alive[m] = alive_out;
         double* S = a.o_stress + (size_t)m * 4;
         if (pairing && orig && alive_out && nr_total > 0) {
-            const double k = 1 / (2 * a.area[m] * a.h[m]);
+            const double k = 1 / (2 * a.area[a.esrc[m]] * a.h[a.esrc[m]]);
             S[0] = k * (s11 + t11); S[1] = k * (s12 + t12); S[2] = k * (s21 + t21); S[3] = k * (s22 + t22);
         } else { S[0] = S[1] = S[2] = S[3] = 0; }
     }
@@ -859,6 +867,8 @@ extern "C" void sz_destroy(SzContext* c)
     { DBuf<double>* tb[] = {&c->t_mass, &c->t_inertia, &c->t_alpha, &c->t_dXi_p, &c->t_dYi_p, &c->t_dUi_p, &c->t_dVi_p, &c->t_dalpha_p, &c->t_dksi_p, &c->t_FxOA, &c->t_FyOA, &c->t_torqueOA,
                           &c->c0x, &c->c0y, &c->t_stressH, &c->t_stress};
       for (auto* b : tb) b->release(); c->t_scount.release(); c->t_flags.release(); }
+    { DBuf<int>* sb[] = {&c->sl_ogid, &c->sl_flag, &c->sl_pos, &c->sl_opos, &c->sl_g, &c->sl_sendcnt, &c->sl_keys, &c->sl_slots, &c->sl_hnv, &c->sl_hvoff};
+      for (auto* b : sb) b->release(); c->sl_cub.release(); c->sl_out.release(); if (c->sl_scratch) cudaFree(c->sl_scratch); }
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -932,7 +942,7 @@ extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f,
         if (bnd->box_n > 0) { CK(cudaMemcpyAsync(c->boxx.p, bnd->box_x, (size_t)bnd->box_n * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->boxy.p, bnd->box_y, (size_t)bnd->box_n * 8, cudaMemcpyDefault, st)); }
         c->bbody.h = bnd->h; c->bbody.area = bnd->area; c->bbody.Xi = bnd->xi; c->bbody.Yi = bnd->yi; c->bbody.Ui = bnd->u; c->bbody.Vi = bnd->v; c->bbody.ksi = bnd->ksi;
     }
-    c->prm = *prm; c->ext_mode = false; c->have_traj = false;
+    c->prm = *prm; c->ext_mode = false; c->slab = false; c->have_traj = false;
     fill_device_params(prm, (bnd && !prm->periodic) ? bnd : nullptr, c->dprm);
     c->n0 = n; c->nverts = f->nverts;
     CK(cudaStreamSynchronize(st));   // the caller may reuse its buffers
@@ -1047,13 +1057,436 @@ extern "C" int sz_slab_scatter(SzContext* c, const double* own, int64_t n_own, c
     return SZ_OK;      // ordered before the step on the library's stream
 }
 
+// ------------------------------------------------------------------------------------------------ multi-GPU slabs
+// One process per GPU; every rank owns a set of floes (ascending global numbers, the numbering of the single-GPU run) and keeps
+// their state -- and the integrator's -- resident here.  Every step the part of the GLOBAL extended floe list this rank needs is
+// rebuilt on the device from the current state, so the step is exact for a field that translates, rotates, thins and loses
+// floes (calc_trajectory.m:75-79,170-222): there is no plan that could go stale.
+//   sz_slab_prepare   periodic-image flags of the owned floes (floe_interactions_all.m:28-31,49-52) from their CURRENT outlines,
+//                     x-extents, largest rmax -> this rank's meta record (the caller all-gathers the records)
+//   sz_slab_pack      global numbers of the rank's images (their rank among ALL ranks' images, :33-36,54-57), halo selection:
+//                     every own entry within reach (2 max rmax) of another rank's x-extent is packed for that rank -- state,
+//                     FloeNums, root centroid AND its current outline (the caller runs one all-to-all of fixed-size blocks)
+//   sz_slab_build     received entries sorted by global number and merged with the own ones into the resident extended list
+//                     (ascending global position, so `j > i`, partner ids and row order are the single-GPU ones); then
+//                     sz_step_resident resolves every pair with an owned floe, and sz_trajectory_step integrates the owned floes
+// Meta record of a rank, SZ_SLAB_META(cap_img) doubles: [0] x-images [1] y-images of originals [2] y-images of x-images
+// [3,4] x-extent of the originals [5,6] x-extent of the x-images [7] largest rmax, then the global numbers of the originals that
+// have an x-image / a y-image / both (cap_img each, ascending).
+// Block for one peer, SZ_SLAB_BLOCK(cap_rec, cap_vert) doubles: [0] records [1] vertices, cap_rec records of SL_REC doubles
+// (gid FloeNum X Y rootX rootY rmax h area u v ksi alive nverts vstart -), cap_vert (x, y) pairs.
+#define SL_REC 16
+#define SL_META_HDR 8
+struct SlabScratch { u64 ext[4]; u64 rmax_bits; int overflow; int n_list; int pad; };     // a_lo a_hi b_lo b_hi
+__device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; } return lo; }
+__device__ __forceinline__ int lower_bound_i(const int* a, int n, int v) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; } return lo; }
+
+__global__ void slab_flag_kernel(int n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ rmax, const uint8_t* __restrict__ alive,
+                                 const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, double Lx, double Ly, int periodic,
+                                 int* __restrict__ fx, int* __restrict__ fy, int* __restrict__ fxy, SlabScratch* s)
+{
+    double alo = SZ_INF, ahi = -SZ_INF, blo = SZ_INF, bhi = -SZ_INF, rm = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double X = x[i], Y = y[i];
+        int a = 0, b = 0;
+        if (periodic && alive[i]) {
+            double mx = -SZ_INF, my = -SZ_INF;
+            for (int t = voff[i]; t < voff[i + 1]; ++t) { const double ax = fabs(vx[t] + X), ay = fabs(vy[t] + Y); if (ax > mx) mx = ax; if (ay > my) my = ay; }
+            a = mx > Lx; b = my > Ly;            // :31,52 -- an x-image keeps its parent's Yi and outline, so its y flag is the parent's
+        }
+        fx[i] = a; fy[i] = b; fxy[i] = a & b;
+        if (X == X) { alo = fmin(alo, X); ahi = fmax(ahi, X); if (a) { const double Xg = X - 2 * Lx * sgn_d(X); blo = fmin(blo, Xg); bhi = fmax(bhi, Xg); } }
+        rm = fmax(rm, rmax[i]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        alo = fmin(alo, __shfl_xor_sync(0xffffffffu, alo, d)); ahi = fmax(ahi, __shfl_xor_sync(0xffffffffu, ahi, d));
+        blo = fmin(blo, __shfl_xor_sync(0xffffffffu, blo, d)); bhi = fmax(bhi, __shfl_xor_sync(0xffffffffu, bhi, d));
+        rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (alo <= ahi) { atomicMin(&s->ext[0], enc_d(alo)); atomicMax(&s->ext[1], enc_d(ahi)); }
+        if (blo <= bhi) { atomicMin(&s->ext[2], enc_d(blo)); atomicMax(&s->ext[3], enc_d(bhi)); }
+        atomicMax(&s->rmax_bits, enc_d(rm));
+    }
+}
+__global__ void slab_scratch_init_kernel(SlabScratch* s)
+{
+    s->ext[0] = enc_d(SZ_INF); s->ext[1] = enc_d(-SZ_INF); s->ext[2] = enc_d(SZ_INF); s->ext[3] = enc_d(-SZ_INF); s->rmax_bits = enc_d(0.0); s->n_list = 0;
+    // overflow is sticky until the host has seen it (cleared by sz_slab_prepare)
+}
+__global__ void slab_meta_kernel(int n, int cap_img, const int* __restrict__ ogid, const int* __restrict__ fx, const int* __restrict__ fy, const int* __restrict__ fxy,
+                                 const int* __restrict__ px, const int* __restrict__ py, const int* __restrict__ pxy, SlabScratch* s, double* __restrict__ meta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        meta[0] = (double)px[n]; meta[1] = (double)py[n]; meta[2] = (double)pxy[n];
+        meta[3] = dec_d(s->ext[0]); meta[4] = dec_d(s->ext[1]); meta[5] = dec_d(s->ext[2]); meta[6] = dec_d(s->ext[3]); meta[7] = dec_d(s->rmax_bits);
+        if (px[n] > cap_img || py[n] > cap_img) s->overflow = 1;
+    }
+    if (i >= n) return;
+    const double g = (double)ogid[i];
+    if (fx[i] && px[i] < cap_img) meta[SL_META_HDR + px[i]] = g;
+    if (fy[i] && py[i] < cap_img) meta[SL_META_HDR + cap_img + py[i]] = g;
+    if (fxy[i] && pxy[i] < cap_img) meta[SL_META_HDR + 2 * cap_img + pxy[i]] = g;
+}
+struct SlabPackArgs {
+    int n, rank, world, cap_img, cap_rec, cap_vert, n_global, periodic; double Lx, Ly;
+    const double* all_meta; int meta_stride;
+    const int* ogid; const double* x; const double* y; const double* rmax; const double* h; const double* area; const double* u; const double* v; const double* ksi; const uint8_t* alive;
+    const int* voff; const double* vx; const double* vy;
+    const int* fx; const int* fy; const int* fxy; const int* px; const int* py; const int* pxy;
+    int* gx; int* gyo; int* gyx;                 // global positions of the own images (ascending)
+    double* send; long long block; int* send_cnt; SlabScratch* s;
+};
+// rank (0-based) of global number G among ALL ranks' originals of one image class = sum of lower bounds in the ranks' lists
+__device__ __forceinline__ int slab_global_rank(const SlabPackArgs& a, int cls, double G)
+{
+    int r = 0;
+    for (int p = 0; p < a.world; ++p) {
+        const double* m = a.all_meta + (size_t)p * a.meta_stride;
+        int cnt = (int)m[cls]; if (cnt > a.cap_img) cnt = a.cap_img;
+        r += lower_bound_d(m + SL_META_HDR + cls * a.cap_img, cnt, G);
+    }
+    return r;
+}
+__device__ void slab_send(const SlabPackArgs& a, double reach, int i, int gid, int fnum, double X, double Y)
+{
+    for (int p = 0; p < a.world; ++p) {
+        if (p == a.rank) continue;
+        const double* m = a.all_meta + (size_t)p * a.meta_stride;
+        const bool near_a = X >= m[3] - reach && X <= m[4] + reach, near_b = X >= m[5] - reach && X <= m[6] + reach;
+        if (!(near_a || near_b)) continue;
+        const int nv = a.voff[i + 1] - a.voff[i];
+        const int slot = atomicAdd(&a.send_cnt[2 * p], 1), vs = atomicAdd(&a.send_cnt[2 * p + 1], nv);
+        if (slot >= a.cap_rec || vs + nv > a.cap_vert) { a.s->overflow = 1; continue; }
+        double* blk = a.send + (size_t)p * a.block;
+        double* r = blk + 2 + (size_t)slot * SL_REC;
+        r[0] = gid; r[1] = fnum; r[2] = X; r[3] = Y; r[4] = a.x[i]; r[5] = a.y[i]; r[6] = a.rmax[i]; r[7] = a.h[i]; r[8] = a.area[i];
+        r[9] = a.u[i]; r[10] = a.v[i]; r[11] = a.ksi[i]; r[12] = a.alive[i]; r[13] = nv; r[14] = vs; r[15] = 0;
+        double* vdst = blk + 2 + (size_t)a.cap_rec * SL_REC + 2 * (size_t)vs;
+        for (int t = 0; t < nv; ++t) { vdst[2 * t] = a.vx[a.voff[i] + t]; vdst[2 * t + 1] = a.vy[a.voff[i] + t]; }
+    }
+}
+// one thread per owned floe: numbers its images in the global list and packs every entry another rank needs
+__global__ void slab_pack_kernel(const SlabPackArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double rm = 0; int cx_tot = 0, cyo_tot = 0;
+    for (int p = 0; p < a.world; ++p) { const double* m = a.all_meta + (size_t)p * a.meta_stride; rm = fmax(rm, m[7]); cx_tot += (int)m[0]; cyo_tot += (int)m[1]; }
+    const double reach = 2 * rm;
+    const int G = a.ogid[i];
+    const double X = a.x[i], Y = a.y[i];
+    const int n1g = a.n_global + cx_tot, n2g = n1g + cyo_tot;
+    slab_send(a, reach, i, G, G, X, Y);
+    if (!a.periodic) return;
+    double Xg = X, Yg = Y;
+    if (a.fx[i]) {
+        Xg = X - 2 * a.Lx * sgn_d(X);                                               // :34
+        const int g = a.n_global + slab_global_rank(a, 0, (double)G) + 1;
+        if (a.px[i] < a.cap_img) a.gx[a.px[i]] = g;
+        slab_send(a, reach, i, g, -G, Xg, Y);
+    }
+    if (a.fy[i]) {
+        Yg = Y - 2 * a.Ly * sgn_d(Y);                                               // :55
+        const int g = n1g + slab_global_rank(a, 1, (double)G) + 1;
+        if (a.py[i] < a.cap_img) a.gyo[a.py[i]] = g;
+        slab_send(a, reach, i, g, -G, X, Yg);
+    }
+    if (a.fxy[i]) {
+        const int g = n2g + slab_global_rank(a, 2, (double)G) + 1;
+        if (a.pxy[i] < a.cap_img) a.gyx[a.pxy[i]] = g;
+        slab_send(a, reach, i, g, -G, Xg, Yg);
+    }
+}
+__global__ void slab_header_kernel(int world, int cap_rec, int cap_vert, const int* __restrict__ send_cnt, double* send, long long block)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= world) return;
+    const int nr = send_cnt[2 * p], nv = send_cnt[2 * p + 1];
+    send[(size_t)p * block] = (double)(nr < cap_rec ? nr : cap_rec);
+    send[(size_t)p * block + 1] = (double)(nv < cap_vert ? nv : cap_vert);
+}
+// received records: sort key (global position, INT_MAX for unused slots), vertex count per slot
+__global__ void slab_keys_kernel(int world, int rank, int cap_rec, const double* __restrict__ recv, long long block, int* __restrict__ keys, int* __restrict__ slots, int* __restrict__ hnv)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= world * cap_rec) return;
+    const int p = k / cap_rec, s = k - p * cap_rec;
+    const double* blk = recv + (size_t)p * block;
+    int key = 0x7fffffff, nv = 0;
+    if (p != rank && s < (int)blk[0]) { const double* r = blk + 2 + (size_t)s * SL_REC; key = (int)r[0]; nv = (int)r[13]; }
+    keys[k] = key; slots[k] = k; hnv[k] = nv;
+}
+struct SlabBuildArgs {
+    int n, rank, world, cap_img, cap_rec, cap_vert, nl_cap, periodic; double Lx, Ly; long long vown;
+    const double* recv; long long block;
+    const int* keys_sorted; const int* slots_sorted; const int* hvoff;      // hvoff: exclusive scan of the slots' vertex counts
+    const int* ogid; const int* fx; const int* fy; const int* fxy; const int* px; const int* py; const int* pxy; const int* gx; const int* gyo; const int* gyx;
+    double* x; double* y; double* rmax; double* h; double* area; double* u; double* v; double* ksi; uint8_t* alive; int* voff; double* vx; double* vy;     // body records: [owned | halo slots]
+    double* ex; double* ey; double* erootx; double* erooty; int* esrc; int* efn; int* eparent; int* egid; uint8_t* ealive; uint8_t* eowned;
+    int* opos; SlabScratch* s;
+};
+// halo records: body record n + slot, outline copied behind the owned outlines, list entry at (rank among received) + (own entries before)
+__global__ void slab_build_halo_kernel(const SlabBuildArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;          // position among the sorted received keys
+    const int nslots = a.world * a.cap_rec;
+    if (k >= nslots) return;
+    const int slot = a.slots_sorted[k], key = a.keys_sorted[k];
+    const int src = a.n + slot;
+    // every slot gets a (possibly empty) outline range, so that voff stays monotone over [owned | slots]
+    a.voff[src + 1] = (int)a.vown + a.hvoff[slot + 1];
+    if (key == 0x7fffffff) return;
+    const int p = slot / a.cap_rec, s = slot - p * a.cap_rec;
+    const double* blk = a.recv + (size_t)p * a.block;
+    const double* r = blk + 2 + (size_t)s * SL_REC;
+    const int cx = a.px[a.n], cyo = a.py[a.n], cyx = a.pxy[a.n];
+    const int own_before = lower_bound_i(a.ogid, a.n, key) + lower_bound_i(a.gx, cx < a.cap_img ? cx : a.cap_img, key)
+                         + lower_bound_i(a.gyo, cyo < a.cap_img ? cyo : a.cap_img, key) + lower_bound_i(a.gyx, cyx < a.cap_img ? cyx : a.cap_img, key);
+    const int pos = k + own_before;
+    if (pos >= a.nl_cap) { a.s->overflow = 1; return; }
+    a.rmax[src] = r[6]; a.h[src] = r[7]; a.area[src] = r[8]; a.u[src] = r[9]; a.v[src] = r[10]; a.ksi[src] = r[11]; a.alive[src] = (uint8_t)r[12]; a.x[src] = r[4]; a.y[src] = r[5];
+    const int nv = (int)r[13], vs = (int)r[14];
+    const double* vsrc = blk + 2 + (size_t)a.cap_rec * SL_REC + 2 * (size_t)vs;
+    const size_t o = (size_t)a.vown + a.hvoff[slot];
+    for (int t = 0; t < nv; ++t) { a.vx[o + t] = vsrc[2 * t]; a.vy[o + t] = vsrc[2 * t + 1]; }
+    a.ex[pos] = r[2]; a.ey[pos] = r[3]; a.erootx[pos] = r[4]; a.erooty[pos] = r[5]; a.esrc[pos] = src; a.efn[pos] = (int)r[1]; a.eparent[pos] = 0; a.egid[pos] = key;
+    a.ealive[pos] = (uint8_t)r[12]; a.eowned[pos] = 0;
+}
+// owned floes and their images: list position = (own entries before) + (received entries with a smaller global position)
+__global__ void slab_build_own_kernel(const SlabBuildArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nslots = a.world * a.cap_rec;
+    const int cx = a.px[a.n], cyo = a.py[a.n], cyx = a.pxy[a.n];
+    if (i == 0) {
+        int n_recv = lower_bound_i(a.keys_sorted, nslots, 0x7fffffff);
+        a.s->n_list = a.n + cx + cyo + cyx + n_recv;
+        if (a.s->n_list > a.nl_cap) a.s->overflow = 1;
+        a.voff[a.n] = (int)a.vown;      // first halo slot starts behind the owned outlines (== ovoff[n])
+    }
+    if (i >= a.n) return;
+    const int G = a.ogid[i];
+    const double X = a.x[i], Y = a.y[i];
+    auto put = [&](int own_rank, int g, int fnum, double ex, double ey, int parent_pos) {
+        const int pos = own_rank + lower_bound_i(a.keys_sorted, nslots, g);
+        if (pos >= a.nl_cap) { a.s->overflow = 1; return -1; }
+        a.ex[pos] = ex; a.ey[pos] = ey; a.erootx[pos] = X; a.erooty[pos] = Y; a.esrc[pos] = i; a.efn[pos] = fnum; a.eparent[pos] = parent_pos + 1; a.egid[pos] = g;
+        a.ealive[pos] = a.alive[i]; a.eowned[pos] = 1;
+        return pos;
+    };
+    const int p0 = put(i, G, G, X, Y, -1);
+    a.opos[i] = p0;
+    if (!a.periodic) return;
+    double Xg = X, Yg = Y; int pxg = -1;
+    if (a.fx[i] && a.px[i] < a.cap_img) { Xg = X - 2 * a.Lx * sgn_d(X); pxg = put(a.n + a.px[i], a.gx[a.px[i]], -G, Xg, Y, p0); }
+    if (a.fy[i] && a.py[i] < a.cap_img) { Yg = Y - 2 * a.Ly * sgn_d(Y); put(a.n + cx + a.py[i], a.gyo[a.py[i]], -G, X, Yg, p0); }
+    if (a.fxy[i] && a.pxy[i] < a.cap_img) put(a.n + cx + cyo + a.pxy[i], a.gyx[a.pxy[i]], -G, Xg, Yg, pxg);
+}
+// entries behind the list's end are inert: dead, unowned, nowhere
+__global__ void slab_build_tail_kernel(int nl_cap, const SlabScratch* __restrict__ s, double* ex, double* ey, double* erootx, double* erooty, int* esrc, int* efn, int* eparent, int* egid,
+                                       uint8_t* ealive, uint8_t* eowned)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nl_cap || e < s->n_list) return;
+    const double nan = SZ_INF - SZ_INF;
+    ex[e] = nan; ey[e] = nan; erootx[e] = nan; erooty[e] = nan; esrc[e] = 0; efn[e] = 0; eparent[e] = 0; egid[e] = 0x7fffffff; ealive[e] = 0; eowned[e] = 0;
+}
+__global__ void slab_count_halo_kernel(int n, int rank, int world, int periodic, double Lx, double Ly, double reach, const double* __restrict__ ext4,
+                                       const double* __restrict__ x, const double* __restrict__ y, const int* __restrict__ voff,
+                                       const int* __restrict__ fx, const int* __restrict__ fy, const int* __restrict__ fxy, unsigned long long* __restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double X = x[i], Y = y[i];
+    const double Xg = X - 2 * Lx * sgn_d(X);
+    const int nv = voff[i + 1] - voff[i];
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        const double* m = ext4 + 4 * p;
+        const bool near0 = (X >= m[0] - reach && X <= m[1] + reach) || (X >= m[2] - reach && X <= m[3] + reach);
+        const bool near1 = (Xg >= m[0] - reach && Xg <= m[1] + reach) || (Xg >= m[2] - reach && Xg <= m[3] + reach);
+        int k = near0 ? 1 : 0;
+        if (periodic) { if (fx[i] && near1) ++k; if (fy[i] && near0) ++k; if (fxy[i] && near1) ++k; }
+        if (k) { atomicAdd(&cnt[2 * p], (unsigned long long)k); atomicAdd(&cnt[2 * p + 1], (unsigned long long)k * nv); }
+    }
+}
+__global__ void slab_status_kernel(const SlabScratch* __restrict__ s, int* __restrict__ out) { out[0] = s->overflow; out[1] = s->n_list; }
+
+extern "C" int64_t sz_slab_meta_doubles(int32_t cap_img) { return SL_META_HDR + 3 * (int64_t)cap_img; }
+extern "C" int64_t sz_slab_block_doubles(int32_t cap_rec, int32_t cap_vert) { return 2 + (int64_t)cap_rec * SL_REC + 2 * (int64_t)cap_vert; }
+
+extern "C" int sz_slab_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f, const SzBoundary* bnd, const int32_t* gid, int32_t n_global, int32_t rank, int32_t world)
+{
+    if (!c || !prm || !f || (f->n > 0 && !gid) || world < 1 || rank < 0 || rank >= world || n_global < f->n) { sz_set_error("sz_slab_upload: bad argument"); return SZ_ERR_ARG; }
+    int r = sz_upload(c, prm, f, bnd);
+    if (r != SZ_OK) return r;
+    const int n = f->n;
+    CK(c->sl_ogid.ensure(n + 1));
+    if (n > 0) CK(cudaMemcpy(c->sl_ogid.p, gid, (size_t)n * 4, cudaMemcpyDefault));
+    CK(c->sl_flag.ensure(3 * (size_t)(n + 1))); CK(c->sl_pos.ensure(3 * (size_t)(n + 2))); CK(c->sl_opos.ensure(n + 1));
+    CK(c->scan_tmp.ensure(scan_tmp_ints((size_t)n + 2)));
+    if (!c->sl_scratch) CK(cudaMalloc(&c->sl_scratch, sizeof(SlabScratch)));
+    CK(cudaMemset(c->sl_scratch, 0, sizeof(SlabScratch)));
+    c->slab = true; c->ext_mode = true; c->sl_rank = rank; c->sl_world = world; c->sl_nglobal = n_global; c->sl_configured = false; c->sl_built = false;
+    return SZ_OK;
+}
+// flags, scans and extents of the owned floes from their current state (shared by sz_slab_measure and sz_slab_prepare)
+static int slab_flags(SzContext* c)
+{
+    cudaStream_t st = c->stream; const int n = c->n0; const SzParams& P = c->prm;
+    int* fx = c->sl_flag.p; int* fy = fx + (n + 1); int* fxy = fy + (n + 1);
+    int* px = c->sl_pos.p; int* py = px + (n + 2); int* pxy = py + (n + 2);
+    ++g_launches; slab_scratch_init_kernel<<<1, 1, 0, st>>>(c->sl_scratch);
+    if (n > 0) { ++g_launches; slab_flag_kernel<<<std::min(nblk(n, 256), 148 * 16), 256, 0, st>>>(n, c->x.p, c->y.p, c->rmax.p, c->alive.p, c->voff.p, c->vx.p, c->vy.p, P.Lx, P.Ly, P.periodic, fx, fy, fxy, c->sl_scratch); }
+    exclusive_scan(fx, n, px, n + 1, c->scan_tmp.p, st);
+    exclusive_scan(fy, n, py, n + 1, c->scan_tmp.p, st);
+    exclusive_scan(fxy, n, pxy, n + 1, c->scan_tmp.p, st);
+    CK(cudaGetLastError());
+    return SZ_OK;
+}
+// host-synchronous measurements for choosing capacities: local8 = this rank's meta header (counts, extents, largest rmax)
+extern "C" int sz_slab_measure(SzContext* c, double* local8)
+{
+    if (!c || !local8 || !c->slab) { sz_set_error("sz_slab_measure: needs sz_slab_upload"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    CKS(slab_flags(c));
+    const int n = c->n0; cudaStream_t st = c->stream;
+    int cnt[3]; SlabScratch s;
+    int* px = c->sl_pos.p;
+    CK(cudaMemcpyAsync(&cnt[0], px + n, 4, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(&cnt[1], px + (n + 2) + n, 4, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(&cnt[2], px + 2 * (n + 2) + n, 4, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(&s, c->sl_scratch, sizeof(s), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    local8[0] = cnt[0]; local8[1] = cnt[1]; local8[2] = cnt[2];
+    for (int k = 0; k < 4; ++k) local8[3 + k] = dec_d(s.ext[k]);
+    local8[7] = dec_d(s.rmax_bits);
+    return SZ_OK;
+}
+// all8: every rank's header (host, [world*8]); counts of the records and vertices this rank would send to each peer
+extern "C" int sz_slab_measure_halo(SzContext* c, const double* all8, int64_t* rec_counts, int64_t* vert_counts)
+{
+    if (!c || !all8 || !rec_counts || !vert_counts || !c->slab) { sz_set_error("sz_slab_measure_halo: needs sz_slab_upload"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const int n = c->n0, W = c->sl_world; cudaStream_t st = c->stream; const SzParams& P = c->prm;
+    std::vector<double> ext(4 * (size_t)W); double rm = 0;
+    for (int p = 0; p < W; ++p) { for (int k = 0; k < 4; ++k) ext[4 * p + k] = all8[8 * p + 3 + k]; rm = std::max(rm, all8[8 * p + 7]); }
+    double* d_ext = nullptr; unsigned long long* d_cnt = nullptr;
+    CK(cudaMalloc(&d_ext, ext.size() * 8)); CK(cudaMalloc(&d_cnt, 2 * (size_t)W * 8));
+    CK(cudaMemcpyAsync(d_ext, ext.data(), ext.size() * 8, cudaMemcpyDefault, st)); CK(cudaMemsetAsync(d_cnt, 0, 2 * (size_t)W * 8, st));
+    int* fx = c->sl_flag.p; int* fy = fx + (n + 1); int* fxy = fy + (n + 1);
+    if (n > 0) { ++g_launches; slab_count_halo_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->sl_rank, W, P.periodic, P.Lx, P.Ly, 2 * rm, d_ext, c->x.p, c->y.p, c->voff.p, fx, fy, fxy, d_cnt); }
+    std::vector<unsigned long long> h(2 * (size_t)W);
+    CK(cudaMemcpyAsync(h.data(), d_cnt, h.size() * 8, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_ext); cudaFree(d_cnt);
+    for (int p = 0; p < W; ++p) { rec_counts[p] = (int64_t)h[2 * p]; vert_counts[p] = (int64_t)h[2 * p + 1]; }
+    return SZ_OK;
+}
+extern "C" int sz_slab_configure(SzContext* c, int32_t cap_img, int32_t cap_rec, int32_t cap_vert)
+{
+    if (!c || !c->slab || cap_img < 1 || cap_rec < 1 || cap_vert < 1) { sz_set_error("sz_slab_configure: needs sz_slab_upload and positive capacities"); return SZ_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int n = c->n0, W = c->sl_world;
+    const size_t nsrc = (size_t)n + (size_t)W * cap_rec, V = (size_t)c->nverts + (size_t)W * cap_vert;
+    if (nsrc + 4 * (size_t)cap_img > 0x7ffffff0u || V > 0x7ffffff0u) { sz_set_error("sz_slab_configure: capacities overflow 32-bit indices"); return SZ_ERR_ARG; }
+    DBuf<double>* body[] = {&c->x, &c->y, &c->rmax, &c->h, &c->area, &c->u, &c->v, &c->ksi};
+    for (auto* b : body) CK(b->ensure(nsrc + 1, true));
+    CK(c->alive.ensure(nsrc + 1, true)); CK(c->voff.ensure(nsrc + 2, true)); CK(c->vx.ensure(V + 1, true)); CK(c->vy.ensure(V + 1, true));
+    const size_t nl = (size_t)n + 3 * (size_t)cap_img + (size_t)W * cap_rec;
+    CK(c->ex.ensure(nl + 1)); CK(c->ey.ensure(nl + 1)); CK(c->erootx.ensure(nl + 1)); CK(c->erooty.ensure(nl + 1)); CK(c->esrc.ensure(nl + 1)); CK(c->efn.ensure(nl + 1));
+    CK(c->eparent.ensure(nl + 1)); CK(c->egid.ensure(nl + 1)); CK(c->ealive.ensure(nl + 1)); CK(c->eowned.ensure(nl + 1));
+    CK(c->sl_g.ensure(3 * (size_t)cap_img + 3)); CK(c->sl_sendcnt.ensure(2 * (size_t)W + 2));
+    const size_t ns = (size_t)W * cap_rec;
+    CK(c->sl_keys.ensure(2 * ns + 2)); CK(c->sl_slots.ensure(2 * ns + 2)); CK(c->sl_hnv.ensure(ns + 2)); CK(c->sl_hvoff.ensure(ns + 2));
+    CK(c->scan_tmp.ensure(scan_tmp_ints(std::max<size_t>(ns + 2, (size_t)n + 2))));
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->sl_keys.p, c->sl_keys.p + ns, c->sl_slots.p, c->sl_slots.p + ns, (int)ns, 0, 32, c->stream);
+    CK(c->sl_cub.ensure(bytes + 16));
+    c->sl_cap_img = cap_img; c->sl_cap_rec = cap_rec; c->sl_cap_vert = cap_vert; c->sl_nl_cap = (int)nl; c->sl_configured = true; c->sl_built = false;
+    return SZ_OK;
+}
+extern "C" int sz_slab_prepare(SzContext* c, double* meta_dev)
+{
+    if (!c || !meta_dev || !c->slab || !c->sl_configured) { sz_set_error("sz_slab_prepare: needs sz_slab_upload and sz_slab_configure"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const int n = c->n0;
+    c->sl_built = false; c->have_step = false;
+    CK(cudaMemsetAsync(&c->sl_scratch->overflow, 0, 4, st));
+    CKS(slab_flags(c));
+    int* fx = c->sl_flag.p; int* fy = fx + (n + 1); int* fxy = fy + (n + 1);
+    int* px = c->sl_pos.p; int* py = px + (n + 2); int* pxy = py + (n + 2);
+    ++g_launches; slab_meta_kernel<<<std::max(1, nblk(n, 256)), 256, 0, st>>>(n, c->sl_cap_img, c->sl_ogid.p, fx, fy, fxy, px, py, pxy, c->sl_scratch, meta_dev);
+    CK(cudaGetLastError());
+    return SZ_OK;
+}
+extern "C" int sz_slab_pack(SzContext* c, const double* all_meta_dev, double* send_dev)
+{
+    if (!c || !all_meta_dev || !send_dev || !c->slab || !c->sl_configured) { sz_set_error("sz_slab_pack: needs sz_slab_prepare"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const int n = c->n0, W = c->sl_world; const SzParams& P = c->prm;
+    SlabPackArgs a; memset(&a, 0, sizeof(a));
+    a.n = n; a.rank = c->sl_rank; a.world = W; a.cap_img = c->sl_cap_img; a.cap_rec = c->sl_cap_rec; a.cap_vert = c->sl_cap_vert; a.n_global = c->sl_nglobal; a.periodic = P.periodic; a.Lx = P.Lx; a.Ly = P.Ly;
+    a.all_meta = all_meta_dev; a.meta_stride = (int)sz_slab_meta_doubles(c->sl_cap_img);
+    a.ogid = c->sl_ogid.p; a.x = c->x.p; a.y = c->y.p; a.rmax = c->rmax.p; a.h = c->h.p; a.area = c->area.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.alive = c->alive.p;
+    a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
+    a.fx = c->sl_flag.p; a.fy = a.fx + (n + 1); a.fxy = a.fy + (n + 1); a.px = c->sl_pos.p; a.py = a.px + (n + 2); a.pxy = a.py + (n + 2);
+    a.gx = c->sl_g.p; a.gyo = a.gx + (c->sl_cap_img + 1); a.gyx = a.gyo + (c->sl_cap_img + 1);
+    a.send = send_dev; a.block = sz_slab_block_doubles(c->sl_cap_rec, c->sl_cap_vert); a.send_cnt = c->sl_sendcnt.p; a.s = c->sl_scratch;
+    CK(cudaMemsetAsync(c->sl_sendcnt.p, 0, 2 * (size_t)W * 4, st));
+    if (n > 0) { ++g_launches; slab_pack_kernel<<<nblk(n, 128), 128, 0, st>>>(a); }
+    ++g_launches; slab_header_kernel<<<1, std::max(32, W), 0, st>>>(W, c->sl_cap_rec, c->sl_cap_vert, c->sl_sendcnt.p, send_dev, a.block);
+    CK(cudaGetLastError());
+    return SZ_OK;
+}
+extern "C" int sz_slab_build(SzContext* c, const double* recv_dev, int32_t* status_dev)
+{
+    if (!c || !recv_dev || !c->slab || !c->sl_configured) { sz_set_error("sz_slab_build: needs sz_slab_pack"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; const int n = c->n0, W = c->sl_world; const SzParams& P = c->prm;
+    const int ns = W * c->sl_cap_rec;
+    const long long block = sz_slab_block_doubles(c->sl_cap_rec, c->sl_cap_vert);
+    int* keys = c->sl_keys.p; int* keys_s = keys + ns; int* slots = c->sl_slots.p; int* slots_s = slots + ns;
+    ++g_launches; slab_keys_kernel<<<nblk(ns, 256), 256, 0, st>>>(W, c->sl_rank, c->sl_cap_rec, recv_dev, block, keys, slots, c->sl_hnv.p);
+    size_t bytes = c->sl_cub.cap;
+    ++g_launches; CK(cub::DeviceRadixSort::SortPairs(c->sl_cub.p, bytes, keys, keys_s, slots, slots_s, ns, 0, 32, st));
+    exclusive_scan(c->sl_hnv.p, ns, c->sl_hvoff.p, ns + 1, c->scan_tmp.p, st);
+    SlabBuildArgs a; memset(&a, 0, sizeof(a));
+    a.n = n; a.rank = c->sl_rank; a.world = W; a.cap_img = c->sl_cap_img; a.cap_rec = c->sl_cap_rec; a.cap_vert = c->sl_cap_vert; a.nl_cap = c->sl_nl_cap; a.periodic = P.periodic; a.Lx = P.Lx; a.Ly = P.Ly; a.vown = c->nverts;
+    a.recv = recv_dev; a.block = block; a.keys_sorted = keys_s; a.slots_sorted = slots_s; a.hvoff = c->sl_hvoff.p;
+    a.ogid = c->sl_ogid.p; a.fx = c->sl_flag.p; a.fy = a.fx + (n + 1); a.fxy = a.fy + (n + 1); a.px = c->sl_pos.p; a.py = a.px + (n + 2); a.pxy = a.py + (n + 2);
+    a.gx = c->sl_g.p; a.gyo = a.gx + (c->sl_cap_img + 1); a.gyx = a.gyo + (c->sl_cap_img + 1);
+    a.x = c->x.p; a.y = c->y.p; a.rmax = c->rmax.p; a.h = c->h.p; a.area = c->area.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.alive = c->alive.p; a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
+    a.ex = c->ex.p; a.ey = c->ey.p; a.erootx = c->erootx.p; a.erooty = c->erooty.p; a.esrc = c->esrc.p; a.efn = c->efn.p; a.eparent = c->eparent.p; a.egid = c->egid.p; a.ealive = c->ealive.p; a.eowned = c->eowned.p;
+    a.opos = c->sl_opos.p; a.s = c->sl_scratch;
+    ++g_launches; slab_build_own_kernel<<<std::max(1, nblk(n, 128)), 128, 0, st>>>(a);
+    ++g_launches; slab_build_halo_kernel<<<nblk(ns, 128), 128, 0, st>>>(a);
+    ++g_launches; slab_build_tail_kernel<<<nblk(c->sl_nl_cap, 256), 256, 0, st>>>(c->sl_nl_cap, c->sl_scratch, c->ex.p, c->ey.p, c->erootx.p, c->erooty.p, c->esrc.p, c->efn.p, c->eparent.p, c->egid.p, c->ealive.p, c->eowned.p);
+    if (status_dev) { ++g_launches; slab_status_kernel<<<1, 1, 0, st>>>(c->sl_scratch, status_dev); }
+    CK(cudaGetLastError());
+    c->sl_built = true;
+    return SZ_OK;
+}
+// list positions of the owned floes (0-based) in the resident extended list of the last sz_slab_build, and that list's length
+extern "C" int sz_slab_get_positions(SzContext* c, int32_t* opos, int32_t* n_list)
+{
+    if (!c || !c->slab || !c->sl_built) { sz_set_error("sz_slab_get_positions: needs sz_slab_build"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    if (opos && c->n0 > 0) CK(cudaMemcpyAsync(opos, c->sl_opos.p, (size_t)c->n0 * 4, cudaMemcpyDefault, c->stream));
+    SlabScratch s; CK(cudaMemcpyAsync(&s, c->sl_scratch, sizeof(s), cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_list) *n_list = s.n_list;
+    return SZ_OK;
+}
+
 static int read_counters(SzContext* c)
 {
     CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDefault, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SZ_OK;
 }
-#define CKS(call) do { int r_ = (call); if (r_ != SZ_OK) return r_; } while (0)
 #define D_CNT(field) ((int*)((char*)c->d_cnt + offsetof(Counters, field)))
 
 // runs the narrow phase over the pairs (wall = 0) or over floe-vs-wall (wall = 1), escalating S -> M -> L
@@ -1172,8 +1605,10 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     cudaStream_t st = c->stream;
     const SzParams& P = c->prm;
     const int n0 = c->n0, Nb = P.Nb;
-    const bool ext = c->ext_mode;
-    const int ncap = (P.periodic && !ext) ? 4 * n0 : n0;         // every floe has at most an x-, a y- and an xy-ghost
+    const bool ext = c->ext_mode, slab = c->slab;
+    if (slab && !c->sl_built) { sz_set_error("sz_step_resident: slab mode needs sz_slab_build before every step"); return SZ_ERR_STATE; }
+    const int nl0 = slab ? c->sl_nl_cap : n0;                    // length of a caller-supplied / device-built extended list (its tail may be inert)
+    const int ncap = (P.periodic && !ext) ? 4 * n0 : nl0;        // every floe has at most an x-, a y- and an xy-ghost
     c->have_step = false; c->have_rows = false;
     CK(cudaEventRecord(c->ev0, st));
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
@@ -1186,7 +1621,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (n0 > 0 && !ext) { ++g_launches; init_extended_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p, c->gx_of.p, c->gy_of.p); }
     {
         Counters init; memset(&init, 0, sizeof(init));
-        init.n1 = n0; init.n = n0;
+        init.n1 = nl0; init.n = nl0;
         init.bbox[0] = enc_d(SZ_INF); init.bbox[1] = enc_d(-SZ_INF); init.bbox[2] = enc_d(SZ_INF); init.bbox[3] = enc_d(-SZ_INF); init.rmax_bits = enc_d(0.0);
         *c->h_cnt = init;
         CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
@@ -1204,13 +1639,17 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         ++g_launches; ghost_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(n1), n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
                                                                   c->gx_of.p, c->gy_of.p, P.Ly, D_CNT(n));
     }
-    if (ext && n0 > 0) {
-        // the caller supplied the extended list (sz_upload_extended): every entry has its own outline and body record
-        CK(cudaMemcpyAsync(c->ex.p, c->x.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->ey.p, c->y.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(c->ealive.p, c->alive.p, (size_t)n0, cudaMemcpyDeviceToDevice, st));
-        ++g_launches; child_init_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->gx_of.p, c->gy_of.p);
-        ++g_launches; child_mark_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->eparent.p, c->gx_of.p, c->gy_of.p);
-        ++g_launches; child_final_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->gx_of.p, c->gy_of.p);
+    if (ext && nl0 > 0) {
+        // the caller supplied the extended list (sz_upload_extended): every entry has its own outline and body record.
+        // Slab mode (sz_slab_build) wrote the list itself, with esrc pointing into [owned floes | halo records].
+        if (!slab) {
+            CK(cudaMemcpyAsync(c->ex.p, c->x.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->ey.p, c->y.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(c->ealive.p, c->alive.p, (size_t)n0, cudaMemcpyDeviceToDevice, st));
+        }
+        CK(c->gx_of.ensure(nl0 + 1)); CK(c->gy_of.ensure(nl0 + 1));
+        ++g_launches; child_init_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->gx_of.p, c->gy_of.p);
+        ++g_launches; child_mark_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->eparent.p, c->gx_of.p, c->gy_of.p);
+        ++g_launches; child_final_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->gx_of.p, c->gy_of.p);
     } else if (ncap > 0) {
         ++g_launches; finish_extended_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->x.p, c->y.p, c->esrc.p, c->egid.p, c->eowned.p, c->erootx.p, c->erooty.p);
     }
@@ -1364,7 +1803,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     s.n0 = n0; s.n = n; s.n_pairs = np; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows; s.n_pairs_owned = c->h_cnt->n_pairs_owned;
     s.n_clip_paths = P.want_clip_polys ? c->h_cnt->path_used : 0; s.n_clip_verts = P.want_clip_polys ? c->h_cnt->vert_used : 0;
     s.collision_count = (double)c->h_cnt->n_fin_rows / 2 + (double)c->h_cnt->n_inf_rows;   // calc_collisionNum.m:6
-    s.n_clipper_fail = c->h_cnt->n_fail; s.n_capacity_fail = c->h_cnt->n_cap_fail; s.ms_device = ms;
+    s.n_clipper_fail = c->h_cnt->n_fail; s.n_capacity_fail = c->h_cnt->n_cap_fail; s.ms_device = ms; s.n_kill_events = c->h_cnt->n_kill_events;
     c->have_step = true; c->have_rows = true;
     if (out) *out = s;
     if (s.n_capacity_fail > 0) { sz_set_error("%d pair(s) exceed the largest narrow-phase size class (1299 vertices per outline)", s.n_capacity_fail); return SZ_ERR_CAPACITY; }
@@ -1391,6 +1830,7 @@ struct TrajArgs {
     const double* FxOA; const double* FyOA; const double* torqueOA;
     const int* voff; const double* c0x; const double* c0y; double* cax; double* cay;
     double* stress_h; int* scount; int* flags; Counters* cnt;
+    const int* omap;              // slab mode: list position of owned floe i (the contact step's per-entry outputs are indexed by it); NULL: i
     const uint8_t* forced; int do_int; double* strain;     // forcing evaluated this step (h < 0.1 is then fine); doInt.flag: floe.strain (:224-234)
 };
 // calc_trajectory.m for one floe per thread: the branch with doInt.flag = false and the ocean/atmosphere tendencies
@@ -1404,11 +1844,12 @@ __global__ void trajectory_kernel(const TrajArgs a)
     a.flags[i] = 0;
     if (i < a.Nb) return;            // the timestepping loop is `parfor i=1+Nb:N0` (floe_interactions_all.m:249): topography floes are never wrapped, thinned or moved
     // the contact step's per-floe results replace the inputs of the integrator (floe_interactions_all.m:152-155,267-277)
-    uint8_t alive = a.alive_step[i];
-    double X = a.xw[i], Y = a.yw[i];
+    const int m = a.omap ? a.omap[i] : i;
+    uint8_t alive = a.alive_step[m];
+    double X = a.xw[m], Y = a.yw[m];
     a.alive[i] = alive; a.x[i] = X; a.y[i] = Y;
     if (!alive) return;                                                            // :280
-    double ext_fx = a.cfx[i], ext_fy = a.cfy[i], ext_t = a.ctq[i];
+    double ext_fx = a.cfx[m], ext_fy = a.cfy[m], ext_t = a.ctq[m];
     double mass = a.mass[i], inertia = a.inertia[i], h = a.h[i];
     int sc = a.scount[i];
     if (sc > a.nz) sc = 1;                                                        // :15-17
@@ -1428,7 +1869,7 @@ __global__ void trajectory_kernel(const TrajArgs a)
     if (sack) { a.flags[i] = 1; atomicAdd(&a.cnt->n_cap_fail, 1); return; }       // state untouched, like the caller's `kill(i) = i`
     // commit: stress history slot (:18-19), clamps, thinning
     double* slot = a.stress_h + ((size_t)i * a.nz + (sc - 1)) * 4;
-    for (int k = 0; k < 4; ++k) slot[k] = a.has_rows[i] ? a.stress_now[(size_t)i * 4 + k] : 0.0;
+    for (int k = 0; k < 4; ++k) slot[k] = a.has_rows[m] ? a.stress_now[(size_t)m * 4 + k] : 0.0;
     a.scount[i] = sc + 1;
     a.mass[i] = floe_mass; a.inertia[i] = floe_inertia; a.h[i] = h_new; a.alive[i] = alive;
     if (alive != 1) return;                                                       // :118
@@ -1499,6 +1940,7 @@ struct OceanArgs {
     const double* PX; const double* PY; const uint8_t* PA;
     const double* Xo; const double* Yo; const double* U; const double* V; const double* Wu; const double* Wv;
     double* FxOA; double* FyOA; double* torqueOA; uint8_t* forced; int* flags; Counters* cnt;
+    const int* omap;
 };
 // interp2(X, Y, V, xq, yq), 'linear', NaN outside the grid; V column-major (iy + ix*ny) like MATLAB (calc_trajectory.m:135-138)
 __device__ __forceinline__ void interp_cell(const double* __restrict__ X, int nx, double xq, int& ix, double& t)
@@ -1520,12 +1962,13 @@ __global__ void __launch_bounds__(256) ocean_forcing_kernel(const OceanArgs a)
 {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= a.n0 || i < a.Nb) return;                                             // floe_interactions_all.m:249 (i = 1+Nb:N0)
-    if (!a.alive_step[i]) return;                                                  // floe_interactions_all.m:280
-    double hh = a.h[i], m = a.mass[i]; int alive = a.alive_step[i];
+    const int mo = a.omap ? a.omap[i] : i;
+    if (!a.alive_step[mo]) return;                                                 // floe_interactions_all.m:280
+    double hh = a.h[i], m = a.mass[i]; int alive = a.alive_step[mo];
     if (hh > 10) hh = 10; else if (m < 100) { m = 1e3; alive = 0; }                // :36-41
     const double dh = a.HFo * a.dt / hh;
     const double floe_mass = (hh - dh) / hh * m, h_new = hh - dh, floe_area = a.area[i];
-    const double Xi = a.xw[i], Yi = a.yw[i];
+    const double Xi = a.xw[mo], Yi = a.yw[mo];
     if (Xi != Xi) return;                                                          // :89
     if (!(a.do_int || h_new < 0.1)) return;                                        // :94
     double cmaxx = -SZ_INF, cminx = SZ_INF, cmaxy = -SZ_INF, cminy = SZ_INF;
@@ -1593,7 +2036,7 @@ __global__ void stress_mean_kernel(int n0, int nz, const double* __restrict__ st
 extern "C" int sz_trajectory_init(SzContext* c, const SzTrajectoryInit* in)
 {
     if (!c || !in) { sz_set_error("sz_trajectory_init: NULL argument"); return SZ_ERR_ARG; }
-    if (!c->have_input || c->ext_mode) { sz_set_error("sz_trajectory_init: upload the floes first (single-GPU list)"); return SZ_ERR_STATE; }
+    if (!c->have_input || (c->ext_mode && !c->slab)) { sz_set_error("sz_trajectory_init: upload the floes first (single-GPU list or sz_slab_upload)"); return SZ_ERR_STATE; }
     if (in->nz < 1 || !in->mass || !in->inertia) { sz_set_error("sz_trajectory_init: mass, inertia and nz >= 1 are required"); return SZ_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     const size_t n = (size_t)c->n0, nv = (size_t)c->nverts; cudaStream_t st = c->stream;
@@ -1619,7 +2062,7 @@ extern "C" int sz_trajectory_init(SzContext* c, const SzTrajectoryInit* in)
 extern "C" int sz_trajectory_step(SzContext* c, const SzTrajectoryParams* p, int32_t* n_sacked, int32_t* n_needs_ocean)
 {
     if (!c || !p) { sz_set_error("sz_trajectory_step: NULL argument"); return SZ_ERR_ARG; }
-    if (!c->have_traj || !c->have_step || c->ext_mode) { sz_set_error("sz_trajectory_step: needs sz_trajectory_init and a contact step"); return SZ_ERR_STATE; }
+    if (!c->have_traj || !c->have_step || (c->ext_mode && !c->slab)) { sz_set_error("sz_trajectory_step: needs sz_trajectory_init and a contact step"); return SZ_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream; const int n0 = c->n0;
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
@@ -1631,12 +2074,13 @@ extern "C" int sz_trajectory_step(SzContext* c, const SzTrajectoryParams* p, int
     a.dalpha_p = c->t_dalpha_p.p; a.dksi_p = c->t_dksi_p.p; a.FxOA = c->t_FxOA.p; a.FyOA = c->t_FyOA.p; a.torqueOA = c->t_torqueOA.p;
     a.voff = c->voff.p; a.c0x = c->c0x.p; a.c0y = c->c0y.p; a.cax = c->vx.p; a.cay = c->vy.p;
     a.stress_h = c->t_stressH.p; a.scount = c->t_scount.p; a.flags = c->t_flags.p; a.cnt = c->d_cnt;
-    a.forced = c->t_forced.p; a.do_int = c->traj_do_int ? 1 : 0; a.strain = c->t_strain.p;
+    a.forced = c->t_forced.p; a.do_int = c->traj_do_int ? 1 : 0; a.strain = c->t_strain.p; a.omap = c->slab ? c->sl_opos.p : nullptr;
     if (n0 > 0) { ++g_launches; trajectory_kernel<<<nblk(n0, 128), 128, 0, st>>>(a); }
     CK(cudaMemsetAsync(c->t_forced.p, 0, (size_t)n0, st)); c->traj_do_int = false;
     CK(cudaGetLastError());
     CKS(read_counters(c));
     c->have_step = false;            // the contact results belong to the previous positions now
+    if (c->slab) c->sl_built = false; // and so does the extended list
     if (n_sacked) *n_sacked = c->h_cnt->n_cap_fail;
     if (n_needs_ocean) *n_needs_ocean = c->h_cnt->n_fail;
     if (c->h_cnt->n_fail > 0) { sz_set_error("%d floe(s) thinner than 0.1 m need the ocean forcing re-evaluated (calc_trajectory.m:94): not part of this path", c->h_cnt->n_fail); return SZ_ERR_STATE; }
@@ -1663,7 +2107,7 @@ extern "C" int sz_trajectory_set_ocean(SzContext* c, const SzOcean* o)
 extern "C" int sz_trajectory_set_points(SzContext* c, int32_t npts, const double* X, const double* Y, const uint8_t* A)
 {
     if (!c || npts < 1 || !X || !Y || !A) { sz_set_error("sz_trajectory_set_points: NULL argument or npts < 1"); return SZ_ERR_ARG; }
-    if (!c->have_input || c->ext_mode) { sz_set_error("sz_trajectory_set_points: upload the floes first (single-GPU list)"); return SZ_ERR_STATE; }
+    if (!c->have_input || (c->ext_mode && !c->slab)) { sz_set_error("sz_trajectory_set_points: upload the floes first (single-GPU list or sz_slab_upload)"); return SZ_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream; const size_t tot = (size_t)c->n0 * npts;
     CK(c->pt_x.ensure(tot + 1)); CK(c->pt_y.ensure(tot + 1)); CK(c->pt_a.ensure(tot + 1));
@@ -1675,7 +2119,7 @@ extern "C" int sz_trajectory_set_points(SzContext* c, int32_t npts, const double
 extern "C" int sz_trajectory_ocean_forcing(SzContext* c, const SzTrajectoryParams* p, int32_t do_int, int32_t* n_evaluated, int32_t* n_no_points)
 {
     if (!c || !p) { sz_set_error("sz_trajectory_ocean_forcing: NULL argument"); return SZ_ERR_ARG; }
-    if (!c->have_traj || !c->have_step || c->ext_mode) { sz_set_error("sz_trajectory_ocean_forcing: needs sz_trajectory_init and a contact step"); return SZ_ERR_STATE; }
+    if (!c->have_traj || !c->have_step || (c->ext_mode && !c->slab)) { sz_set_error("sz_trajectory_ocean_forcing: needs sz_trajectory_init and a contact step"); return SZ_ERR_STATE; }
     if (!c->have_ocean || !c->have_points) { sz_set_error("sz_trajectory_ocean_forcing: needs sz_trajectory_set_ocean and sz_trajectory_set_points"); return SZ_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream; const int n0 = c->n0;
@@ -1689,7 +2133,7 @@ extern "C" int sz_trajectory_ocean_forcing(SzContext* c, const SzTrajectoryParam
     a.mass = c->t_mass.p; a.area = c->area.p; a.alpha = c->t_alpha.p; a.voff = c->voff.p; a.cax = c->vx.p; a.cay = c->vy.p;
     a.PX = c->pt_x.p; a.PY = c->pt_y.p; a.PA = c->pt_a.p;
     a.Xo = c->oc_Xo.p; a.Yo = c->oc_Yo.p; a.U = c->oc_U.p; a.V = c->oc_V.p; a.Wu = c->oc_Wu.p; a.Wv = c->oc_Wv.p;
-    a.FxOA = c->t_FxOA.p; a.FyOA = c->t_FyOA.p; a.torqueOA = c->t_torqueOA.p; a.forced = c->t_forced.p; a.flags = c->t_flags.p; a.cnt = c->d_cnt;
+    a.FxOA = c->t_FxOA.p; a.FyOA = c->t_FyOA.p; a.torqueOA = c->t_torqueOA.p; a.forced = c->t_forced.p; a.flags = c->t_flags.p; a.cnt = c->d_cnt; a.omap = c->slab ? c->sl_opos.p : nullptr;
     if (n0 > 0) { ++g_launches; ocean_forcing_kernel<<<nblk(32 * (i64)n0, 256), 256, 0, st>>>(a); }
     CK(cudaGetLastError());
     CKS(read_counters(c));
@@ -1736,6 +2180,49 @@ extern "C" int sz_get_floe_outputs(SzContext* c, double* fx, double* fy, double*
     D2H(stress, c->o_stress.p, n * 32); D2H(xi, c->o_xi.p, n * 8); D2H(yi, c->o_yi.p, n * 8); D2H(alive, c->o_alive.p, n);
     D2H(kill, c->o_kill.p, n * 4); D2H(transfer, c->o_transfer.p, n * 4);
     CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+// slab mode: the per-floe outputs of the OWNED floes, in their order (per-entry results gathered through the list positions)
+__global__ void slab_gather_outputs_kernel(int n, const int* __restrict__ opos, const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ tq, const double* __restrict__ ov,
+                                           const double* __restrict__ stress, const double* __restrict__ xi, const double* __restrict__ yi, const uint8_t* __restrict__ alive,
+                                           const int* __restrict__ kill, const int* __restrict__ transfer, double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = opos[i];
+    out[i] = fx[m]; out[(size_t)n + i] = fy[m]; out[2 * (size_t)n + i] = tq[m]; out[3 * (size_t)n + i] = ov[m];
+    for (int k = 0; k < 4; ++k) out[4 * (size_t)n + 4 * (size_t)i + k] = stress[4 * (size_t)m + k];
+    out[8 * (size_t)n + i] = xi[m]; out[9 * (size_t)n + i] = yi[m]; out[10 * (size_t)n + i] = alive[m]; out[11 * (size_t)n + i] = kill[m]; out[12 * (size_t)n + i] = transfer[m];
+}
+// the resident extended list of the last sz_slab_build, [n_list] each (any pointer may be NULL)
+extern "C" int sz_slab_get_list(SzContext* c, int32_t* gid, int32_t* floe_num, uint8_t* owned, double* x, double* y)
+{
+    if (!c || !c->slab || !c->sl_built) { sz_set_error("sz_slab_get_list: needs sz_slab_build"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    SlabScratch s; CK(cudaMemcpyAsync(&s, c->sl_scratch, sizeof(s), cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)std::min(s.n_list, c->sl_nl_cap);
+    D2H(gid, c->egid.p, n * 4); D2H(floe_num, c->efn.p, n * 4); D2H(owned, c->eowned.p, n); D2H(x, c->ex.p, n * 8); D2H(y, c->ey.p, n * 8);
+    CK(cudaStreamSynchronize(c->stream));
+    return SZ_OK;
+}
+extern "C" int sz_slab_get_outputs(SzContext* c, double* fx, double* fy, double* torque, double* overlap_area, double* stress, double* xi, double* yi,
+                                   uint8_t* alive, int32_t* kill, int32_t* transfer)
+{
+    NEED_STEP("sz_slab_get_outputs");
+    if (!c->slab) { sz_set_error("sz_slab_get_outputs: slab mode only"); return SZ_ERR_STATE; }
+    const int n = c->n0; const size_t N = (size_t)n;
+    if (n == 0) return SZ_OK;
+    CK(c->sl_out.ensure(13 * N + 1));
+    ++g_launches; slab_gather_outputs_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->sl_opos.p, c->o_fx.p, c->o_fy.p, c->o_tq.p, c->o_ov.p, c->o_stress.p, c->o_xi.p, c->o_yi.p, c->o_alive.p,
+                                                                                 c->o_kill.p, c->o_transfer.p, c->sl_out.p);
+    CK(cudaGetLastError());
+    const double* o = c->sl_out.p;
+    D2H(fx, o, N * 8); D2H(fy, o + N, N * 8); D2H(torque, o + 2 * N, N * 8); D2H(overlap_area, o + 3 * N, N * 8); D2H(stress, o + 4 * N, N * 32); D2H(xi, o + 8 * N, N * 8); D2H(yi, o + 9 * N, N * 8);
+    std::vector<double> t(3 * N);
+    CK(cudaMemcpyAsync(t.data(), o + 10 * N, 3 * N * 8, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < N; ++i) { if (alive) alive[i] = (uint8_t)t[i]; if (kill) kill[i] = (int32_t)t[N + i]; if (transfer) transfer[i] = (int32_t)t[2 * N + i]; }
     return SZ_OK;
 }
 extern "C" int sz_get_ghosts(SzContext* c, int32_t* parent, int32_t* floe_num, double* gx, double* gy)

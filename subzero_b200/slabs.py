@@ -509,25 +509,201 @@ class SlabStep:
         return out, row_off, rows[off[first]:off[last]]
 
 
-class SlabJob:
-    """bench.py's workload: the synthetic periodic Voronoi field (BASELINE.json configs[4]) on `world` GPUs"""
 
-    def __init__(self, n_floes, seed, rank, world, local_rank, dist, order="site"):
+# ------------------------------------------------------------------------------------------------ device-built slab step
+class DeviceSlab:
+    """One rank's part of a multi-GPU run with the list surgery on the device (sz_slab_* of the C ABI): the rank OWNS the floes
+    `gid` (ascending global floe numbers, 1-based -- the numbering of the single-GPU run; any subset), their state and the
+    integrator's stay resident in the library, and every step the rank's part of the global extended floe list is rebuilt from
+    the CURRENT state -- positions, rotated outlines, thickness, alive flags -- so the step is exact for a moving, rotating,
+    thinning field (calc_trajectory.m:75-79,170-222).  Per step: two library kernels groups around two collectives --
+
+        sz_slab_prepare -> all-gather of the meta records (image counts and numbers, x-extents, largest rmax)
+        sz_slab_pack    -> all-to-all of fixed-size blocks: every own entry (state + CURRENT outline) another rank can reach
+        sz_slab_build   -> received entries merged by global position; sz_step_resident; (sz_trajectory_step)
+
+    -- all on torch's current stream, with no host synchronisation before the step's own final counter read.  Pairs that
+    straddle two slabs are resolved on both sides (bit-identical rows for every floe, no return exchange of partial forces);
+    forces on an owned periodic image are folded into its parent by the owner (floe_interactions_all.m:242-245).  Capacities
+    of the fixed-size blocks are agreed at plan time from measured counts (x 1.5); a step that outgrows them is detected on
+    the device (one all-reduced status word) and repeated after a new plan."""
+
+    def __init__(self, prm, owned, gid, n_global, comm, ctx, bnd=None, slack=1.5):
+        self.prm, self.comm, self.ctx, self.bnd, self.slack = prm, comm, ctx, bnd, slack
+        self.n_global = int(n_global)
+        self.plans = self.steps = 0
+        self.summary = None
+        self.dev = torch.device(comm.device) if comm.device is not None else torch.device("cuda", torch.cuda.current_device())
+        # the library launches on torch's current stream: its kernels and the collectives are ordered by the stream alone
+        ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.upload(owned, gid)
+
+    # ---- state
+    def upload(self, owned, gid, plan=True):
+        self.owned = owned
+        self.gid = np.ascontiguousarray(gid, np.int32)
+        assert self.gid.shape[0] == owned.n and (owned.n < 2 or np.all(np.diff(self.gid) > 0)), "global floe numbers must ascend"
+        fs = owned.struct()
+        bs = self.bnd.struct() if self.bnd is not None else None
+        torch.cuda.current_stream(self.dev).synchronize()
+        abi.check(abi.lib().sz_slab_upload(self.ctx._h, C.byref(self.prm), C.byref(fs), C.byref(bs) if bs is not None else None, abi._ptr(self.gid, abi.c_ip),
+                                           self.n_global, self.comm.rank, self.comm.world))
+        self.ctx._n0 = owned.n
+        if plan:
+            self.plan()
+        else:               # same capacities and buffers as before (a step that outgrows them is detected and re-planned)
+            abi.check(abi.lib().sz_slab_configure(self.ctx._h, self.cap_img, self.cap_rec, self.cap_vert))
+
+    def plan(self, grow=1.0):
+        """measure what the current state needs, agree on the capacities across ranks, allocate the exchange buffers"""
+        lib, W = abi.lib(), self.comm.world
+        local8 = np.zeros(8)
+        abi.check(lib.sz_slab_measure(self.ctx._h, abi._ptr(local8, abi.c_dp)))
+        all8 = self.comm.all_gather(torch.from_numpy(local8).to(self.dev)).cpu().numpy().reshape(W, 8).copy()
+        rec, vert = np.zeros(W, np.int64), np.zeros(W, np.int64)
+        abi.check(lib.sz_slab_measure_halo(self.ctx._h, abi._ptr(all8, abi.c_dp), abi._ptr(rec, abi.c_lp), abi._ptr(vert, abi.c_lp)))
+        need = torch.tensor([float(all8[:, :3].max()), float(rec.max()), float(vert.max())], dtype=F64, device=self.dev)
+        need = self.comm.all_max(need).cpu().numpy()
+        k = self.slack * grow
+        self.cap_img, self.cap_rec, self.cap_vert = (int(k * need[0]) + 64, int(k * need[1]) + 64, int(k * need[2]) + 1024)
+        abi.check(lib.sz_slab_configure(self.ctx._h, self.cap_img, self.cap_rec, self.cap_vert))
+        self.meta_n = int(lib.sz_slab_meta_doubles(self.cap_img))
+        self.block = int(lib.sz_slab_block_doubles(self.cap_rec, self.cap_vert))
+        z = lambda n: torch.zeros(n, dtype=F64, device=self.dev)
+        self.meta, self.all_meta = z(self.meta_n), z(W * self.meta_n)
+        self.send, self.recv = z(W * self.block), z(W * self.block)
+        self.status = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self.halo_measured = (int(rec.sum()), int(vert.sum()))
+        self.plans += 1
+
+    # ---- one step
+    def exchange(self):
+        lib, W, h = abi.lib(), self.comm.world, self.ctx._h
+        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
+        abi.check(lib.sz_slab_prepare(h, P(self.meta, abi.c_dp)))
+        if W == 1:
+            self.all_meta.copy_(self.meta)
+        else:
+            self.all_meta.copy_(self.comm.all_gather(self.meta).reshape(-1))
+        abi.check(lib.sz_slab_pack(h, P(self.all_meta, abi.c_dp), P(self.send, abi.c_dp)))
+        if W > 1:
+            self.recv = self.comm.exchange(self.send.view(W, self.block), [1] * W, [1] * W).reshape(-1)
+            if self.comm.stage:
+                torch.cuda.current_stream(self.dev).synchronize()
+        abi.check(lib.sz_slab_build(h, P(self.recv, abi.c_dp), P(self.status, abi.c_ip)))
+        self.flag = self.comm.all_max(self.status[:1].to(F64)) if W > 1 else self.status[:1]     # capacity overflow on any rank
+
+    def run(self, allow_pair_errors=False):
+        """one contact step on the current state; returns the step's SzSummary (n = the padded list length)"""
+        for attempt in range(4):
+            self.exchange()
+            s = self.ctx.step_resident(allow_pair_errors=allow_pair_errors)
+            if int(self.flag.item()) == 0:
+                self.summary, self.steps = s, self.steps + 1
+                return s
+            self.plan(grow=2.0 ** (attempt + 1))           # the field outgrew the blocks: new capacities, repeat the step
+        raise RuntimeError("slab step: capacities kept overflowing")
+
+    def trajectory_init(self, mass, inertia, nz=1000, **fields):
+        self.ctx.trajectory_init(mass, inertia, nz=nz, **fields)
+
+    def trajectory_step(self, dt, HFo=0.0, *bounds):
+        return self.ctx.trajectory_step(dt, HFo, *bounds)
+
+    # ---- results of the owned floes
+    def outputs(self):
+        n = self.owned.n
+        o = {"fx": np.empty(n), "fy": np.empty(n), "torque": np.empty(n), "overlap_area": np.empty(n), "stress": np.empty((n, 2, 2)), "xi": np.empty(n), "yi": np.empty(n),
+             "alive": np.empty(n, np.uint8), "kill": np.empty(n, np.int32), "transfer": np.empty(n, np.int32)}
+        p = abi._ptr
+        abi.check(abi.lib().sz_slab_get_outputs(self.ctx._h, p(o["fx"], abi.c_dp), p(o["fy"], abi.c_dp), p(o["torque"], abi.c_dp), p(o["overlap_area"], abi.c_dp), p(o["stress"], abi.c_dp),
+                                                p(o["xi"], abi.c_dp), p(o["yi"], abi.c_dp), p(o["alive"], abi.c_bp), p(o["kill"], abi.c_ip), p(o["transfer"], abi.c_ip)))
+        if self.summary is not None and self._any_kill():
+            o["kill"], o["transfer"] = self._fix_kill_transfer(o["kill"], o["transfer"])
+        return o
+
+    def positions(self):
+        pos, nl = np.empty(self.owned.n, np.int32), C.c_int32()
+        abi.check(abi.lib().sz_slab_get_positions(self.ctx._h, abi._ptr(pos, abi.c_ip), C.byref(nl)))
+        return pos, nl.value
+
+    def local_list(self):
+        _, nl = self.positions()
+        o = {"gid": np.empty(nl, np.int32), "floe_num": np.empty(nl, np.int32), "owned": np.empty(nl, np.uint8), "x": np.empty(nl), "y": np.empty(nl)}
+        p = abi._ptr
+        abi.check(abi.lib().sz_slab_get_list(self.ctx._h, p(o["gid"], abi.c_ip), p(o["floe_num"], abi.c_ip), p(o["owned"], abi.c_bp), p(o["x"], abi.c_dp), p(o["y"], abi.c_dp)))
+        return o
+
+    def rows(self):
+        """(row_off [n_owned + 1], rows [K, 7]) of the owned floes in their order; partner ids are global list positions"""
+        pos, _ = self.positions()
+        off, rows = self.ctx.rows()
+        cnt = off[pos + 1] - off[pos]
+        out_off = np.zeros(self.owned.n + 1, np.int64)
+        np.cumsum(cnt, out=out_off[1:])
+        idx = np.repeat(off[pos] - out_off[:-1], cnt) + np.arange(int(out_off[-1]))
+        return out_off, rows[idx]
+
+    def _any_kill(self):
+        t = torch.tensor([float(self.summary.n_kill_events)], dtype=F64, device=self.dev)
+        return float(self.comm.all_max(t)) > 0 if self.comm.world > 1 else self.summary.n_kill_events > 0
+
+    def _fix_kill_transfer(self, kill, transfer):
+        """floe_interactions_all.m:175-179 across ranks (rare: only when some floe merged): for i = 1:length(kill), if kill(i) ~= i
+        && kill(i) > 0, transfer(kill(i)) = i -- serial, so the largest i wins; i runs over the whole extended list (an image's
+        entry counts)."""
+        L = self.local_list()
+        n_list = L["gid"].shape[0]
+        ko, to = np.empty(self.summary.n, np.int32), np.empty(self.summary.n, np.int32)
+        abi.check(abi.lib().sz_get_floe_outputs(self.ctx._h, None, None, None, None, None, None, None, None, abi._ptr(ko, abi.c_ip), abi._ptr(to, abi.c_ip)))
+        ko = ko[:n_list]
+        ev = (L["owned"] != 0) & (ko > 0) & (ko != L["gid"])
+        rec = np.stack([L["gid"][ev], ko[ev]], 1).astype(np.int64) if ev.any() else np.zeros((0, 2), np.int64)
+        cnts = self.comm.all_gather(torch.tensor([rec.shape[0]], dtype=I64, device=self.dev)).cpu().flatten()
+        mx = int(cnts.max())
+        if mx == 0:
+            return kill, transfer
+        pad = torch.zeros((mx, 2), dtype=I64, device=self.dev)
+        pad[:rec.shape[0]] = torch.from_numpy(rec).to(self.dev)
+        allrec = self.comm.all_gather(pad.flatten()).reshape(self.comm.world, mx, 2).cpu().numpy()
+        recs = np.concatenate([allrec[p, :int(cnts[p])] for p in range(self.comm.world)])
+        transfer = transfer.copy()
+        k = np.searchsorted(self.gid, recs[:, 1])
+        ok = (k < self.gid.shape[0]) & (self.gid[np.minimum(k, self.gid.shape[0] - 1)] == recs[:, 1])
+        win = np.zeros(self.gid.shape[0], np.int64)
+        np.maximum.at(win, k[ok], recs[ok, 0])
+        transfer = np.where(win > 0, win.astype(np.int32), transfer)
+        return kill, transfer
+
+
+class SlabJob:
+    """bench.py's workload: the synthetic periodic Voronoi field (BASELINE.json configs[4]) on `world` GPUs.  The floes are
+    numbered slab by slab (a stable sort of the generator's numbering by x-slab; at world 1 the generator's own), rank r owns
+    the r-th slab: floe ownership by centroid."""
+
+    def __init__(self, n_floes, seed, rank, world, local_rank, dist, order="site", number_for_world=None):
         self.rank, self.world, self.dist = rank, world, dist
         self.prm, field = voronoi_field(n_floes, seed=seed, order=order)
         self.ctx = ContactContext(local_rank)
         self.summary = None
+        self.slab = None
+        nw = number_for_world or world
+        if nw > 1:
+            field, starts = sort_by_slab(field, self.prm.Lx, nw)
+        else:
+            starts = np.array([0, field.n], np.int64)
+        self.field, self.starts = field, starts
         if world == 1:
             self.floes = field
+            self.gid = np.arange(1, field.n + 1, dtype=np.int32)
             self.ctx.upload(self.prm, self.floes)
-            self.step = None
         else:
-            field, starts = sort_by_slab(field, self.prm.Lx, world)
-            self.floes = take_range(field, int(starts[rank]), int(starts[rank + 1]))
+            a, b = int(starts[rank]), int(starts[rank + 1])
+            self.floes = take_range(field, a, b)
+            self.gid = np.arange(a + 1, b + 1, dtype=np.int32)
             dev = torch.device("cuda", local_rank)
             self.comm = Comm(dist, rank, world, dev)
-            self.state = SlabState.from_soa(self.floes, int(starts[rank]), n_floes, dev)
-            self.step = SlabStep(self.prm, self.state, self.comm, self.ctx)
+            self.slab = DeviceSlab(self.prm, self.floes, self.gid, field.n, self.comm, self.ctx)
         self._pin()
 
     def _pin(self):
@@ -540,29 +716,32 @@ class SlabJob:
 
     def step_resident(self):
         """one step with this rank's floes resident in HBM; returns (device ms, phase ms)"""
-        if self.step is None:
+        if self.slab is None:
             s = self.ctx.step_resident()
             ms = s.ms_device
         else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            s = self.step.run()
+            s = self.slab.run()
             e1.record()
             e1.synchronize()
-            ms = e0.elapsed_time(e1)          # halo exchange + list surgery + local step, on the device timeline
+            ms = e0.elapsed_time(e1)          # meta all-gather + halo all-to-all + list build + local step, on the device timeline
         self.summary = s
         self.pairs_owned, self.pairs_force_total = int(s.n_pairs_owned), int(s.n_pairs_force)
         ph = self.ctx.phase_ms()
         ph["classes"] = self.ctx.narrow_class_ms()     # per size class: (kernel ms, pairs)
         self.rows_owned = int(s.n_rows)
-        self.ext_entries_owned = int(s.n) if self.step is None else int((self.step.local.owned != 0).sum())
+        if self.slab is None:
+            self.ext_entries_owned = int(s.n)
+        else:
+            self.ext_entries_owned = int(self.slab.status[1].item()) - 0      # list length incl. halo (the halo share is in describe())
         return ms, ph
 
     def e2e_step(self):
         """host buffers in (pinned), per-floe outputs and all contact rows out; returns (h2d, d2h) bytes"""
         f = self.pinned
         h2d = sum(getattr(f, k).nbytes for k in abi.FloesSoA.FIELDS) + f.alive.nbytes + f.voff.nbytes + f.vx.nbytes + f.vy.nbytes
-        if self.step is None:
+        if self.slab is None:
             s = self.ctx.step(self.prm, f)
             n = f.n
             if self._out is None:
@@ -576,16 +755,10 @@ class SlabJob:
             d2h = sum(v.nbytes for v in self._out.values()) + (s.n + 1) * 8 + int(s.n_rows) * 56
         else:
             # this rank's floes travel host -> device, the slab step runs, its floes' results travel back
-            dev = self.state.x.device
-            up = lambda a, dt: torch.from_numpy(a).to(dev, non_blocking=True).to(dt)
-            st = self.state
-            st.x, st.y, st.rmax, st.h, st.area, st.u, st.v, st.ksi = (up(getattr(f, k), F64) for k in abi.FloesSoA.FIELDS)
-            st.alive, st.voff, st.vx, st.vy = up(f.alive, torch.uint8), up(f.voff, I64), up(f.vx, F64), up(f.vy, F64)
-            st.update_outline_extents()
-            s = self.step.run()
-            if self._out is None:
-                self._out = {}
-            out, row_off, rows = self.step.results(pinned=self._out)
+            self.slab.upload(f, self.gid, plan=False)
+            s = self.slab.run()
+            out = self.slab.outputs()
+            row_off, rows = self.slab.rows()
             d2h = sum(v.nbytes for v in out.values()) + row_off.nbytes + rows.nbytes
         self.summary = s
         return h2d, d2h
@@ -593,7 +766,10 @@ class SlabJob:
     def describe(self):
         if self.world == 1:
             return "1 GPU, whole field"
-        return "%d x-slabs, floe ownership by centroid, halo exchange of straddling floes (state + outlines) over NCCL p2p each step" % self.world
+        return ("%d x-slabs, floe ownership by centroid; every step each rank rebuilds its part of the global extended floe list on the device from the current state: "
+                "one all-gather of per-rank meta records (periodic-image counts and numbers, x-extents, largest rmax) and one all-to-all over NCCL of fixed-size blocks "
+                "carrying every entry within reach of another slab -- state, FloeNums, root centroid and its current (rotated) outline; straddling pairs are resolved on "
+                "both sides instead of returning partial forces to the owner (bit-identical rows, no second exchange)") % self.world
 
     def close(self):
         self.ctx.close()

@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(abi.SzParams) == 15 * 8 + 4 * 4
     assert C.sizeof(abi.SzFloesSoA) == 8 + 8 + 12 * 8
     assert C.sizeof(abi.SzBoundary) == 8 + 8 + 8 + 8 + 8 + 8 + 7 * 8
-    assert C.sizeof(abi.SzSummary) == 8 + 5 * 8 + 8 + 4 + 4 + 8 + 8
+    assert C.sizeof(abi.SzSummary) == 8 + 5 * 8 + 8 + 4 + 4 + 8 + 8 + 8          # ... ms_device (+pad), n_pairs_owned, n_kill_events (+pad)
     assert C.sizeof(abi.SzExtendedList) == 6 * 8
 
 
