@@ -141,11 +141,75 @@ def run_reference(args, rank, world):
     sample = "%d-floe periodic Voronoi field (same generator, density and physics as the %d-floe workload), whole contact step, cell-grid broad phase" % (n_sample, args.floes)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+int64",
-            "data": "synthetic", "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes, "sample_floes": n_sample, "floe_order": args.floe_order},
+            "data": "synthetic", "config": {"workload": "configs[4] synthetic packed periodic Voronoi floe field, contact loop only", "floes": args.floes, "sample_floes": n_sample, "floe_order": args.floe_order,
+                                            "same_config": n_sample == args.floes},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": sample + "; oracle = C++ restatement of the MATLAB path calling the reference's unmodified Clipper 6.4.2 (MATLAB itself is not installed)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+
+def verify_against_single_gpu(job, steps, rank, world, local_rank, dist):
+    """Parity of the multi-GPU job inside the bench run: `steps` coupled steps (contact step + integrator with nonzero ksi and
+    thermodynamic thinning, so positions, outlines and thickness change every step) on the slab job, and the same loop on ONE
+    GPU (rank 0, same field, same floe numbering).  Compared bit for bit, per rank's floes: the last step's per-floe outputs and
+    contact rows, and the integrated state (x y u v ksi h alive alpha, rotated outlines).  Returns a dict for the JSON line."""
+    import hashlib
+    import numpy as np
+    import subzero_b200 as sz
+    prm, field, starts = job.prm, job.field, job.starts
+    rho_ice, nz, hfo = 920.0, 1, 1e-4
+    mass = field.area * field.h * rho_ice
+    inertia = mass * field.rmax ** 2 / 4
+
+    def digest(out, row_off, rows, st):
+        h = hashlib.sha256()
+        for k in ("fx", "fy", "torque", "overlap_area", "stress", "xi", "yi", "alive", "kill", "transfer"):
+            h.update(np.ascontiguousarray(out[k]).tobytes())
+        h.update(np.ascontiguousarray(np.diff(row_off)).astype(np.int64).tobytes())
+        h.update(np.ascontiguousarray(rows).tobytes())
+        for k in ("x", "y", "u", "v", "ksi", "h", "alive", "alpha", "cax", "cay"):
+            h.update(np.ascontiguousarray(st[k]).tobytes())
+        return h.hexdigest()
+
+    a, b = int(starts[rank]), int(starts[rank + 1])
+    slab = job.slab
+    slab.trajectory_init(mass[a:b], inertia[a:b], nz=nz, dXi_p=field.u[a:b], dYi_p=field.v[a:b])
+    pairs = 0
+    for _ in range(steps):
+        s = slab.run()
+        pairs = int(s.n_pairs_owned)
+        out, (row_off, rows) = slab.outputs(), slab.rows()
+        slab.trajectory_step(prm.dt, hfo)
+    st = job.ctx.trajectory_state(nverts=job.floes.vx.shape[0])
+    mine = digest(out, row_off, rows, st)
+    alpha_max = float(np.abs(st["alpha"]).max()) if st["alpha"].size else 0.0
+    got = [None] * world
+    dist.all_gather_object(got, (mine, pairs, alpha_max))
+    res = None
+    if rank == 0:
+        with sz.ContactContext(local_rank) as one:
+            one.upload(prm, field)
+            one.trajectory_init(mass, inertia, nz=nz, dXi_p=field.u, dYi_p=field.v)
+            for _ in range(steps):
+                s1 = one.step_resident()
+                o1, (off1, rows1) = one.floe_outputs(), one.rows()
+                one.trajectory_step(prm.dt, hfo)
+            st1 = one.trajectory_state(nverts=field.vx.shape[0])
+        bad = []
+        for r in range(world):
+            ra, rb = int(starts[r]), int(starts[r + 1])
+            va, vb = int(field.voff[ra]), int(field.voff[rb])
+            sl = {k: (st1[k][va:vb] if k in ("cax", "cay") else st1[k][ra:rb]) for k in st1}
+            ref = digest({k: v[ra:rb] for k, v in o1.items()}, off1[ra:rb + 1], rows1[off1[ra]:off1[rb]], sl)
+            if ref != got[r][0]:
+                bad.append(r)
+        res = {"checked": True, "ok": not bad and sum(g[1] for g in got) == int(s1.n_pairs), "steps": steps, "ranks_differing": bad,
+               "max_abs_heading_change_rad": max(g[2] for g in got),
+               "what": "coupled contact + integrator steps (nonzero ksi, HFo %g) at N = %d vs N = 1 on the same field and numbering: sha256 of each rank's per-floe outputs, "
+                       "contact rows (last step) and integrated state incl. rotated outlines" % (hfo, world)}
+    return res
 
 
 def main():
@@ -155,7 +219,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--floes", type=int, default=1000000)
-    ap.add_argument("--cpu-floes", type=int, default=400000)
+    ap.add_argument("--cpu-floes", type=int, default=0, help="floes of the CPU arm's field; 0 (default) = --floes, i.e. the benchmark configuration itself")
+    ap.add_argument("--verify", type=int, default=-1, metavar="STEPS",
+                    help="after the timed region, run STEPS coupled steps (contact step + integrator, nonzero ksi, thinning) and compare every rank's per-floe outputs, contact rows and "
+                         "integrated state with a single-GPU run of the same field bit for bit; prints parity in the line.  Default: 20 at N > 1, off at N = 1")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
@@ -163,6 +230,8 @@ def main():
     ap.add_argument("--floe-order", default="site", choices=["site", "morton"],
                     help="numbering of the synthetic floes: the generator's site order (default, SURVEY.md 8d) or a Z-order curve (experiment; both arms)")
     args = ap.parse_args()
+    if args.cpu_floes <= 0:
+        args.cpu_floes = args.floes
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,6 +310,11 @@ def main():
     e2e_ms = float(te.item())
     e2e_value = total_pairs / (e2e_ms * 1e-3)
 
+    # ---- parity of the multi-GPU path, inside this run
+    parity = None
+    n_verify = args.verify if args.verify >= 0 else (20 if world > 1 else 0)
+    if world > 1 and n_verify > 0:
+        parity = verify_against_single_gpu(job, n_verify, rank, world, local_rank, dist)
     # ---- timesteps/s with the integrator half of the step on the device (contact step + calc_trajectory, N = 1)
     ts_with_ab2 = None
     if world == 1:
@@ -265,13 +339,18 @@ def main():
         narrow_ms_per = narrow_ms / args.steps
         kern_ms_per = kern_ms / args.steps
         achieved = alg_bytes / (kern_ms_per * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, "no ncu capture published (profiles/narrow_traffic.json)"
         tp = os.path.join(ROOT, "profiles", "narrow_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+                from subzero_b200.build import kernel_stamp
+                tj = json.load(open(tp))
+                if tj.get("kernel_stamp") == kernel_stamp():
+                    traffic, traffic_note = tj.get("dram_bytes_per_launch"), "ncu --set full capture of this kernel's sources: " + str(tj.get("source"))
+                else:
+                    traffic_note = "stale: the published capture (%s) was taken from other sources of this kernel" % tj.get("source")
+            except Exception as e:
+                traffic, traffic_note = None, "unreadable: %r" % (e,)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+int64",
                 "data": "synthetic",
@@ -283,8 +362,9 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": launches,
+                "parity": parity if parity is not None else {"checked": False, "why": "N = 1 is the reference of the multi-GPU parity check; its own parity with the oracle is tests/ -m gpu and smoke()"},
                 "roofline": {"bound": "hbm", "kernel": "narrow_convex_kernel<PairS> (class C of the narrow phase: Clipper-exact convex sweep + force law)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms_per, "kernel_pairs_per_launch": kern_pairs,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel_ms": kern_ms_per, "kernel_pairs_per_launch": kern_pairs,
                              "narrow_phase_ms": narrow_ms_per, "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "latency-bound sequential sweep per pair (thread per pair); the HBM roofline is reported as the contract asks, see DESIGN.md 4.2"}}
         if world == 1 and not args.no_cpu:

@@ -127,7 +127,7 @@ int sz_contact_step(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes
 int sz_upload(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes, const SzBoundary* bnd);
 int sz_step_resident(SzContext* ctx, SzSummary* out);
 
-/* ---- multi-GPU slabs: the caller supplies its part of the extended floe list instead of having it built.
+/* ---- caller-supplied extended list (any host that builds its own list; the multi-GPU path below builds it on the device).
  * One record of `floes` per entry (originals and periodic images this rank owns, plus halo entries received from
  * the neighbouring slabs), ascending `gid`; x,y are the image centroids (floe_interactions_all.m:34,55).  Pairs are
  * resolved when either floe is owned; rows, sums and per-floe outputs ([n] in this mode) are produced for owned
@@ -143,9 +143,6 @@ typedef struct SzExtendedList {
     const int32_t* parent;     /* images: 1-based LOCAL index of the parent entry when it is owned here, else 0 */
 } SzExtendedList;
 int sz_upload_extended(SzContext* ctx, const SzParams* prm, const SzFloesSoA* entries, const SzBoundary* bnd, const SzExtendedList* ext);
-/* between topology changes only the motion state of the entries changes: refresh it in place ([n] each, NULL = keep) */
-int sz_update_extended_state(SzContext* ctx, const double* x, const double* y, const double* u, const double* v, const double* ksi,
-                             const double* root_x, const double* root_y);
 
 /* ---- multi-GPU slabs, device-built list: one process per GPU, each rank OWNS a set of floes -- ascending
  * global floe numbers `gid` (1-based, the numbering of the single-GPU run; any subset, e.g. a contiguous range after a sort by
@@ -160,7 +157,7 @@ int sz_update_extended_state(SzContext* ctx, const double* x, const double* y, c
  *                                    FloeNums, root centroid and its CURRENT outline.  send = `world` blocks of
  *                                    sz_slab_block_doubles(cap_rec, cap_vert) doubles; the caller runs one all-to-all of equal splits
  *   sz_slab_build(recv, status)      received entries sorted by global position and merged with the own ones into the resident
- *                                    extended list; status (device, 2 ints, may be NULL) = {capacity overflow, list length}
+ *                                    extended list; status (device, 3 ints, may be NULL) = {capacity overflow, list length, owned floes outside the rank's extent}
  *   sz_step_resident                 pairs with at least one owned floe (straddling pairs are resolved on both sides, which keeps
  *                                    every floe's rows bit-identical to the single-GPU run and replaces the return of partial forces)
  *   sz_trajectory_step               integrates the owned floes (sz_trajectory_init after sz_slab_upload)
@@ -175,6 +172,9 @@ int sz_slab_upload(SzContext* ctx, const SzParams* prm, const SzFloesSoA* owned,
 int sz_slab_measure(SzContext* ctx, double* local8 /* host: x-images, y-images of originals, y-images of x-images, x-extent of originals [2], of x-images [2], max rmax */);
 int sz_slab_measure_halo(SzContext* ctx, const double* all8 /* host [world*8] */, int64_t* rec_counts /* [world] */, int64_t* vert_counts /* [world] */);
 int sz_slab_configure(SzContext* ctx, int32_t cap_img, int32_t cap_rec, int32_t cap_vert);
+/* the x-range [xlo, xhi) this rank's floes are expected to stay in: sz_slab_build's status word [2] counts the live owned floes
+ * whose centroid left it (the caller's cue to move floes between ranks; results never depend on it).  Default: unbounded. */
+int sz_slab_set_extent(SzContext* ctx, double xlo, double xhi);
 int sz_slab_prepare(SzContext* ctx, double* meta_dev);
 int sz_slab_pack(SzContext* ctx, const double* all_meta_dev, double* send_dev);
 int sz_slab_build(SzContext* ctx, const double* recv_dev, int32_t* status_dev);
@@ -182,30 +182,6 @@ int sz_slab_get_positions(SzContext* ctx, int32_t* opos /* [n_owned] 0-based lis
 int sz_slab_get_list(SzContext* ctx, int32_t* gid, int32_t* floe_num, uint8_t* owned, double* x, double* y);   /* [n_list] each, any may be NULL */
 int sz_slab_get_outputs(SzContext* ctx, double* fx, double* fy, double* torque, double* overlap_area, double* stress, double* xi, double* yi,
                         uint8_t* alive, int32_t* kill, int32_t* transfer);   /* per owned floe, like sz_get_floe_outputs */
-
-/* Device helpers of the slab step's fast path (subzero_b200/slabs.py): all pointers are DEVICE memory.
- * sz_slab_refresh: for the rank's own entries [originals | x-images | y-images] recompute the image centroids
- * (floe_interactions_all.m:34,55), write x y u v ksi root_x root_y per entry into own_out, and set *bad_out when the
- * plan is stale (an image flag of :31,52 changed, or a floe moved more than half_skin).  Synchronous.
- * sz_slab_scatter: merge own and received 7-double records into the resident extended list (order[l] indexes
- * [own | recv]); runs on the context's stream ahead of the next sz_step_resident. */
-typedef struct SzSlabRefresh {
-    int32_t n_orig, n_xg, n_yg;
-    const double *x, *y, *u, *v, *ksi;            /* [n_orig] */
-    const uint8_t* alive;                          /* [n_orig] */
-    const double *minvx, *maxvx, *minvy, *maxvy;   /* [n_orig] extents of c_alpha */
-    const int64_t* xg_par;                         /* [n_xg] original each x-image copies */
-    const int64_t* yg_par;                         /* [n_yg] entry of [originals | x-images] each y-image copies */
-    const uint8_t* fx_plan;                        /* [n_orig] */
-    const uint8_t* fy_plan;                        /* [n_orig + n_xg] */
-    const double *x0, *y0;                         /* [n_orig] centroids when the plan was built */
-    double Lx, Ly, half_skin;
-    int32_t periodic;
-    double* own_out;                               /* [(n_orig + n_xg + n_yg) * 7] */
-    int32_t* bad_out;
-} SzSlabRefresh;
-int sz_slab_refresh(SzContext* ctx, const SzSlabRefresh* r);
-int sz_slab_scatter(SzContext* ctx, const double* own, int64_t n_own, const double* recv, int64_t n_recv, const int64_t* order, int64_t n_local);
 
 /* ---- results of the last step (caller-allocated; sizes from SzSummary) ---- */
 /* per floe of the input list, each [n0] unless noted; any pointer may be NULL to skip */
@@ -249,10 +225,14 @@ typedef struct SzTrajectoryInit {
     const double *mass, *inertia, *alpha, *dXi_p, *dYi_p, *dUi_p, *dVi_p, *dalpha_p, *dksi_p, *FxOA, *FyOA, *torqueOA;   /* [n0] */
     const double *c0x, *c0y;                                                                                            /* [nverts] */
     int32_t nz;                  /* depth of the stress history (1000 in the reference, initialize_floe_values.m:24) */
+    const double* stress_h;      /* [n0][nz][4] StressH to resume from (NULL = zeros(2,2,nz)); with stress_count [n0] (NULL = 1) -- a floe that
+                                    moves to another rank (or a restart) carries its history along (sz_get_stress_history) */
+    const int32_t* stress_count;
 } SzTrajectoryInit;
 typedef struct SzTrajectoryParams { double dt, HFo, xo_min, xo_max, yo_min, yo_max; } SzTrajectoryParams;   /* HFo = mean(HFo(:)); ocean grid extent (:116) */
 int sz_trajectory_init(SzContext* ctx, const SzTrajectoryInit* init);
 int sz_trajectory_step(SzContext* ctx, const SzTrajectoryParams* prm, int32_t* n_sacked, int32_t* n_needs_ocean);
+int sz_get_stress_history(SzContext* ctx, double* stress_h /* [n0][nz][4] */, int32_t* stress_count /* [n0] */);
 int sz_get_trajectory(SzContext* ctx, double* x, double* y, double* u, double* v, double* ksi, double* h, uint8_t* alive, double* mass, double* inertia, double* alpha,
                       double* dXi_p, double* dYi_p, double* dUi_p, double* dVi_p, double* dalpha_p, double* dksi_p, double* stress, int32_t* flags, double* cax, double* cay);
 

@@ -43,7 +43,7 @@ class SzExtendedList(C.Structure):
 
 class SzTrajectoryInit(C.Structure):
     NAMES = ("mass", "inertia", "alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p", "FxOA", "FyOA", "torqueOA", "c0x", "c0y")
-    _fields_ = [(n, c_dp) for n in NAMES] + [("nz", C.c_int32)]
+    _fields_ = [(n, c_dp) for n in NAMES] + [("nz", C.c_int32), ("stress_h", c_dp), ("stress_count", c_ip)]
 
 
 class SzTrajectoryParams(C.Structure):
@@ -53,12 +53,6 @@ class SzTrajectoryParams(C.Structure):
 class SzOcean(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("Xo", c_dp), ("Yo", c_dp), ("Uocn", c_dp), ("Vocn", c_dp), ("Uwinds", c_dp), ("Vwinds", c_dp),
                 ("fCoriolis", C.c_double), ("turn_angle", C.c_double), ("rho0", C.c_double), ("Cd", C.c_double), ("rho_air", C.c_double), ("Cd_atm", C.c_double)]
-
-
-class SzSlabRefresh(C.Structure):
-    _fields_ = [("n_orig", C.c_int32), ("n_xg", C.c_int32), ("n_yg", C.c_int32)] + [(n, c_dp) for n in ("x", "y", "u", "v", "ksi")] + [("alive", c_bp)] + [
-        (n, c_dp) for n in ("minvx", "maxvx", "minvy", "maxvy")] + [("xg_par", c_lp), ("yg_par", c_lp), ("fx_plan", c_bp), ("fy_plan", c_bp), ("x0", c_dp), ("y0", c_dp),
-        ("Lx", C.c_double), ("Ly", C.c_double), ("half_skin", C.c_double), ("periodic", C.c_int32), ("own_out", c_dp), ("bad_out", c_ip)]
 
 
 class SzSummary(C.Structure):
@@ -81,9 +75,6 @@ PROTOTYPES = {
     "sz_contact_step": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzSummary)]),
     "sz_upload": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary)]),
     "sz_upload_extended": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), C.POINTER(SzExtendedList)]),
-    "sz_update_extended_state": (C.c_int, [C.c_void_p] + [c_dp] * 7),
-    "sz_slab_refresh": (C.c_int, [C.c_void_p, C.POINTER(SzSlabRefresh)]),
-    "sz_slab_scatter": (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, C.c_int64, c_lp, C.c_int64]),
     "sz_slab_meta_doubles": (C.c_int64, [C.c_int32]),
     "sz_slab_block_doubles": (C.c_int64, [C.c_int32, C.c_int32]),
     "sz_slab_upload": (C.c_int, [C.c_void_p, C.POINTER(SzParams), C.POINTER(SzFloesSoA), C.POINTER(SzBoundary), c_ip, C.c_int32, C.c_int32, C.c_int32]),
@@ -104,6 +95,8 @@ PROTOTYPES = {
     "sz_get_rows": (C.c_int, [C.c_void_p, c_lp, c_dp]),
     "sz_trajectory_init": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryInit)]),
     "sz_trajectory_step": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryParams), c_ip, c_ip]),
+    "sz_get_stress_history": (C.c_int, [C.c_void_p, c_dp, c_ip]),
+    "sz_slab_set_extent": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "sz_trajectory_set_ocean": (C.c_int, [C.c_void_p, C.POINTER(SzOcean)]),
     "sz_trajectory_set_points": (C.c_int, [C.c_void_p, C.c_int32, c_dp, c_dp, c_bp]),
     "sz_trajectory_ocean_forcing": (C.c_int, [C.c_void_p, C.POINTER(SzTrajectoryParams), C.c_int32, c_ip, c_ip]),
@@ -160,8 +153,13 @@ def check(code):
 
 
 def default_params(**kw):
+    """sz_default_params of the C ABI restated on the host (the constants hard-coded in collisions/floe_interactions.m:20-21,37,
+    55-58,79,99,127,141,15,54), so that building a parameter block does not need the CUDA library; tests/test_abi.py holds the
+    two together"""
     p = SzParams()
-    lib().sz_default_params(C.byref(p))
+    p.nu, p.mu, p.merge_frac, p.wall_frac, p.amin_per_vertex = 0.3, 0.2, 0.55, 0.75, 100.0 / 1.75
+    p.vertex_match_tol, p.on_edge_tol, p.dl_min, p.close_gap, p.big_floe_r, p.domain_area_frac = 1.0, 1e-8, 0.1, 1.0, 1e5, 0.95
+    p.dt, p.collision, p.periodic, p.Nb, p.want_clip_polys = 10.0, 1, 0, 0, 0
     for k, v in kw.items():
         setattr(p, k, v)
     return p

@@ -14,12 +14,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("SZ_BUILD_DIR", os.path.join(HERE, "_lib"))       # SZ_BUILD_DIR / SZ_EXTRA_NVCC: experiment builds
 LIB = os.path.join(OUT, "libsubzero_b200.so")
+FIELD_LIB = os.path.join(OUT, "libsz_field.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"] + os.environ.get("SZ_EXTRA_NVCC", "").split()
 CU = ["sz_contact.cu", "sz_narrow_C.cu", "sz_narrow_S.cu", "sz_narrow_T.cu", "sz_narrow_M.cu", "sz_narrow_L.cu"]
 CPP = ["sz_field.cpp"]
 HEADERS = ["sz_clip.cuh", "sz_convex.cuh", "sz_pairforce.cuh", "sz_narrow.cuh", "sz_corners.cuh", "sz_euler.cuh", os.path.join("..", "..", "include", "subzero_b200.h")]
+
+
+def kernel_stamp(files=("sz_narrow_C.cu", "sz_narrow.cuh", "sz_convex.cuh", "sz_pairforce.cuh", "sz_clip.cuh")):
+    """sha256 over the sources of the dominant kernel (class C of the narrow phase).  profiles/narrow_traffic.json records it
+    when the ncu capture is published; bench.py reports `roofline.traffic` only while the stamp still matches, i.e. while the
+    measured DRAM traffic belongs to the kernel that is being timed."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def _newer(src_list, target):
@@ -60,6 +72,10 @@ def build(verbose=False, force=False):
                     print(out)
     if jobs or not os.path.exists(LIB):
         _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lpthread"])
+    # the synthetic-field generator alone (host code, no CUDA): what the CPU reference arm of bench.py loads, so that it never
+    # maps the product library
+    if _newer([os.path.join(CSRC, "sz_field.cpp")] + hdrs, FIELD_LIB):
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread", "-shared", "-DSZ_FIELD_STANDALONE", os.path.join(CSRC, "sz_field.cpp"), "-o", FIELD_LIB])
     return LIB
 
 

@@ -147,12 +147,25 @@ class ContactContext:
         """fields: alpha dXi_p dYi_p dUi_p dVi_p dalpha_p dksi_p FxOA FyOA torqueOA [n0], c0x c0y [nverts]; missing = zeros
         (c0 = the uploaded c_alpha)"""
         init = abi.SzTrajectoryInit()
+        sh, sc = fields.pop("stress_h", None), fields.pop("stress_count", None)
         keep = {"mass": abi.f64(mass), "inertia": abi.f64(inertia)}
         keep.update({k: abi.f64(v) for k, v in fields.items()})
         for k in abi.SzTrajectoryInit.NAMES:
             setattr(init, k, abi._ptr(keep.get(k), abi.c_dp))
         init.nz = int(nz)
+        if sh is not None:
+            keep["stress_h"] = abi.f64(sh)
+            keep["stress_count"] = np.ascontiguousarray(sc, np.int32)
+            init.stress_h, init.stress_count = abi._ptr(keep["stress_h"], abi.c_dp), abi._ptr(keep["stress_count"], abi.c_ip)
+        self._traj_nz = int(nz)
         abi.check(abi.lib().sz_trajectory_init(self._h, C.byref(init)))
+
+    def stress_history(self):
+        """(StressH [n0, nz, 4], StressCount [n0]) of the integrator (calc_trajectory.m:15-19)"""
+        n = self._n0
+        sh, sc = np.empty((n, self._traj_nz, 4)), np.empty(n, np.int32)
+        abi.check(abi.lib().sz_get_stress_history(self._h, abi._ptr(sh, abi.c_dp), abi._ptr(sc, abi.c_ip)))
+        return sh, sc
 
     def trajectory_step(self, dt, HFo=0.0, xo_min=-np.inf, xo_max=np.inf, yo_min=-np.inf, yo_max=np.inf):
         p = abi.SzTrajectoryParams(float(dt), float(HFo), float(xo_min), float(xo_max), float(yo_min), float(yo_max))

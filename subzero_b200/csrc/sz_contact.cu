@@ -121,7 +121,7 @@ struct SzContext {
     // slab mode (sz_slab_*): the rank's owned floes are the resident originals [0, n0); halo records follow them in the body arrays and the
     // extended list is rebuilt on the device every step
     bool slab = false, sl_configured = false, sl_built = false; int sl_rank = 0, sl_world = 1, sl_nglobal = 0, sl_cap_img = 0, sl_cap_rec = 0, sl_cap_vert = 0, sl_nl_cap = 0;
-    struct SlabScratch* sl_scratch = nullptr;
+    struct SlabScratch* sl_scratch = nullptr; double sl_xlo = -SZ_INF, sl_xhi = SZ_INF;
     DBuf<int> sl_ogid, sl_flag, sl_pos, sl_opos, sl_g, sl_sendcnt, sl_keys, sl_slots, sl_hnv, sl_hvoff; DBuf<uint8_t> sl_cub; DBuf<double> sl_out;
     int nout = 0;                   // entries with per-floe outputs: n0 (single GPU) or n (extended mode)
     DBuf<int> flag, pos, scan_tmp;
@@ -971,92 +971,6 @@ extern "C" int sz_upload_extended(SzContext* c, const SzParams* prm, const SzFlo
     return SZ_OK;
 }
 
-extern "C" int sz_update_extended_state(SzContext* c, const double* x, const double* y, const double* u, const double* v, const double* ksi,
-                                        const double* root_x, const double* root_y)
-{
-    if (!c) { sz_set_error("sz_update_extended_state: NULL context"); return SZ_ERR_ARG; }
-    if (!c->have_input || !c->ext_mode) { sz_set_error("sz_update_extended_state: no extended list uploaded"); return SZ_ERR_STATE; }
-    CK(cudaSetDevice(c->device));
-    const size_t b = (size_t)c->n0 * 8; cudaStream_t st = c->stream;
-    if (b) {
-        if (x) CK(cudaMemcpyAsync(c->x.p, x, b, cudaMemcpyDefault, st));
-        if (y) CK(cudaMemcpyAsync(c->y.p, y, b, cudaMemcpyDefault, st));
-        if (u) CK(cudaMemcpyAsync(c->u.p, u, b, cudaMemcpyDefault, st));
-        if (v) CK(cudaMemcpyAsync(c->v.p, v, b, cudaMemcpyDefault, st));
-        if (ksi) CK(cudaMemcpyAsync(c->ksi.p, ksi, b, cudaMemcpyDefault, st));
-        if (root_x) CK(cudaMemcpyAsync(c->erootx.p, root_x, b, cudaMemcpyDefault, st));
-        if (root_y) CK(cudaMemcpyAsync(c->erooty.p, root_y, b, cudaMemcpyDefault, st));
-        CK(cudaStreamSynchronize(st));
-    }
-    return SZ_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ slab refresh
-// One thread per entry of the rank's own part of the extended list [originals | x-images | y-images]: recomputes the
-// image centroids from the current centroids (floe_interactions_all.m:34,55), checks the plan (same floes poke through
-// the periodic boundary, :31,52; no floe moved more than half the halo skin) and writes the 7-double motion record.
-__global__ void slab_refresh_kernel(const SzSlabRefresh r)
-{
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_own = r.n_orig + r.n_xg + r.n_yg;
-    if (e >= n_own) return;
-    int src; double X, Y; bool bad = false;
-    if (e < r.n_orig) {
-        src = e; X = r.x[e]; Y = r.y[e];
-        if (!(fabs(X - r.x0[e]) <= r.half_skin) || !(fabs(Y - r.y0[e]) <= r.half_skin)) bad = true;
-        if (r.periodic) {
-            const bool fx = r.alive[e] && fmax(fabs(r.maxvx[e] + X), fabs(r.minvx[e] + X)) > r.Lx;
-            if (fx != (r.fx_plan[e] != 0)) bad = true;
-        }
-    } else if (e < r.n_orig + r.n_xg) {
-        src = (int)r.xg_par[e - r.n_orig];
-        X = r.x[src] - 2 * r.Lx * sgn_d(r.x[src]); Y = r.y[src];
-    } else {
-        const int q = (int)r.yg_par[e - r.n_orig - r.n_xg];
-        double Yq;
-        if (q < r.n_orig) { src = q; X = r.x[q]; Yq = r.y[q]; }
-        else { src = (int)r.xg_par[q - r.n_orig]; X = r.x[src] - 2 * r.Lx * sgn_d(r.x[src]); Yq = r.y[src]; }
-        Y = Yq - 2 * r.Ly * sgn_d(Yq);
-    }
-    if (r.periodic && e < r.n_orig + r.n_xg) {
-        const bool fy = r.alive[src] && fmax(fabs(r.maxvy[src] + Y), fabs(r.minvy[src] + Y)) > r.Ly;
-        if (fy != (r.fy_plan[e] != 0)) bad = true;
-    }
-    double* o = r.own_out + (size_t)e * 7;
-    o[0] = X; o[1] = Y; o[2] = r.u[src]; o[3] = r.v[src]; o[4] = r.ksi[src]; o[5] = r.x[src]; o[6] = r.y[src];
-    if (bad) atomicExch(r.bad_out, 1);
-}
-__global__ void slab_scatter_kernel(int n_local, const double* __restrict__ own, long long n_own, const double* __restrict__ recv, const long long* __restrict__ order,
-                                    double* x, double* y, double* u, double* v, double* ksi, double* rx, double* ry)
-{
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_local) return;
-    const long long k = order[l];
-    const double* row = k < n_own ? own + k * 7 : recv + (k - n_own) * 7;
-    x[l] = row[0]; y[l] = row[1]; u[l] = row[2]; v[l] = row[3]; ksi[l] = row[4]; rx[l] = row[5]; ry[l] = row[6];
-}
-extern "C" int sz_slab_refresh(SzContext* c, const SzSlabRefresh* r)
-{
-    if (!c || !r || !r->own_out || !r->bad_out) { sz_set_error("sz_slab_refresh: NULL argument"); return SZ_ERR_ARG; }
-    CK(cudaSetDevice(c->device));
-    const int n_own = r->n_orig + r->n_xg + r->n_yg;
-    CK(cudaMemsetAsync(r->bad_out, 0, 4, c->stream));
-    if (n_own > 0) { ++g_launches; slab_refresh_kernel<<<nblk(n_own, 256), 256, 0, c->stream>>>(*r); }
-    CK(cudaGetLastError());
-    if (c->stream == c->own_stream) CK(cudaStreamSynchronize(c->stream));      // a caller-provided stream orders the consumers itself
-    return SZ_OK;
-}
-extern "C" int sz_slab_scatter(SzContext* c, const double* own, int64_t n_own, const double* recv, int64_t n_recv, const int64_t* order, int64_t n_local)
-{
-    if (!c || (n_local > 0 && !order)) { sz_set_error("sz_slab_scatter: NULL argument"); return SZ_ERR_ARG; }
-    if (!c->have_input || !c->ext_mode || n_local != c->n0 || n_own + n_recv != n_local) { sz_set_error("sz_slab_scatter: the resident extended list has a different size"); return SZ_ERR_STATE; }
-    CK(cudaSetDevice(c->device));
-    if (n_local > 0) { ++g_launches; slab_scatter_kernel<<<nblk(n_local, 256), 256, 0, c->stream>>>((int)n_local, own, n_own, recv, (const long long*)order,
-                                                                                                      c->x.p, c->y.p, c->u.p, c->v.p, c->ksi.p, c->erootx.p, c->erooty.p); }
-    CK(cudaGetLastError());
-    return SZ_OK;      // ordered before the step on the library's stream
-}
-
 // ------------------------------------------------------------------------------------------------ multi-GPU slabs
 // One process per GPU; every rank owns a set of floes (ascending global numbers, the numbering of the single-GPU run) and keeps
 // their state -- and the integrator's -- resident here.  Every step the part of the GLOBAL extended floe list this rank needs is
@@ -1077,14 +991,15 @@ extern "C" int sz_slab_scatter(SzContext* c, const double* own, int64_t n_own, c
 // (gid FloeNum X Y rootX rootY rmax h area u v ksi alive nverts vstart -), cap_vert (x, y) pairs.
 #define SL_REC 16
 #define SL_META_HDR 8
-struct SlabScratch { u64 ext[4]; u64 rmax_bits; int overflow; int n_list; int pad; };     // a_lo a_hi b_lo b_hi
+struct SlabScratch { u64 ext[4]; u64 rmax_bits; int overflow; int n_list; int n_outside; int pad; };     // a_lo a_hi b_lo b_hi
 __device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; } return lo; }
 __device__ __forceinline__ int lower_bound_i(const int* a, int n, int v) { int lo = 0, hi = n; while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; } return lo; }
 
 __global__ void slab_flag_kernel(int n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ rmax, const uint8_t* __restrict__ alive,
                                  const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, double Lx, double Ly, int periodic,
-                                 int* __restrict__ fx, int* __restrict__ fy, int* __restrict__ fxy, SlabScratch* s)
+                                 int* __restrict__ fx, int* __restrict__ fy, int* __restrict__ fxy, SlabScratch* s, double xlo, double xhi)
 {
+    int outside = 0;
     double alo = SZ_INF, ahi = -SZ_INF, blo = SZ_INF, bhi = -SZ_INF, rm = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double X = x[i], Y = y[i];
@@ -1095,16 +1010,17 @@ __global__ void slab_flag_kernel(int n, const double* __restrict__ x, const doub
             a = mx > Lx; b = my > Ly;            // :31,52 -- an x-image keeps its parent's Yi and outline, so its y flag is the parent's
         }
         fx[i] = a; fy[i] = b; fxy[i] = a & b;
-        if (X == X) { alo = fmin(alo, X); ahi = fmax(ahi, X); if (a) { const double Xg = X - 2 * Lx * sgn_d(X); blo = fmin(blo, Xg); bhi = fmax(bhi, Xg); } }
+        if (X == X) { outside += (alive[i] && (X < xlo || X >= xhi)); alo = fmin(alo, X); ahi = fmax(ahi, X); if (a) { const double Xg = X - 2 * Lx * sgn_d(X); blo = fmin(blo, Xg); bhi = fmax(bhi, Xg); } }
         rm = fmax(rm, rmax[i]);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         alo = fmin(alo, __shfl_xor_sync(0xffffffffu, alo, d)); ahi = fmax(ahi, __shfl_xor_sync(0xffffffffu, ahi, d));
         blo = fmin(blo, __shfl_xor_sync(0xffffffffu, blo, d)); bhi = fmax(bhi, __shfl_xor_sync(0xffffffffu, bhi, d));
-        rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, d));
+        rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, d)); outside += __shfl_xor_sync(0xffffffffu, outside, d);
     }
     if ((threadIdx.x & 31) == 0) {
+        if (outside) atomicAdd(&s->n_outside, outside);
         if (alo <= ahi) { atomicMin(&s->ext[0], enc_d(alo)); atomicMax(&s->ext[1], enc_d(ahi)); }
         if (blo <= bhi) { atomicMin(&s->ext[2], enc_d(blo)); atomicMax(&s->ext[3], enc_d(bhi)); }
         atomicMax(&s->rmax_bits, enc_d(rm));
@@ -1112,7 +1028,7 @@ __global__ void slab_flag_kernel(int n, const double* __restrict__ x, const doub
 }
 __global__ void slab_scratch_init_kernel(SlabScratch* s)
 {
-    s->ext[0] = enc_d(SZ_INF); s->ext[1] = enc_d(-SZ_INF); s->ext[2] = enc_d(SZ_INF); s->ext[3] = enc_d(-SZ_INF); s->rmax_bits = enc_d(0.0); s->n_list = 0;
+    s->ext[0] = enc_d(SZ_INF); s->ext[1] = enc_d(-SZ_INF); s->ext[2] = enc_d(SZ_INF); s->ext[3] = enc_d(-SZ_INF); s->rmax_bits = enc_d(0.0); s->n_list = 0; s->n_outside = 0;
     // overflow is sticky until the host has seen it (cleared by sz_slab_prepare)
 }
 __global__ void slab_meta_kernel(int n, int cap_img, const int* __restrict__ ogid, const int* __restrict__ fx, const int* __restrict__ fy, const int* __restrict__ fxy,
@@ -1313,7 +1229,7 @@ __global__ void slab_count_halo_kernel(int n, int rank, int world, int periodic,
         if (k) { atomicAdd(&cnt[2 * p], (unsigned long long)k); atomicAdd(&cnt[2 * p + 1], (unsigned long long)k * nv); }
     }
 }
-__global__ void slab_status_kernel(const SlabScratch* __restrict__ s, int* __restrict__ out) { out[0] = s->overflow; out[1] = s->n_list; }
+__global__ void slab_status_kernel(const SlabScratch* __restrict__ s, int* __restrict__ out) { out[0] = s->overflow; out[1] = s->n_list; out[2] = s->n_outside; }
 
 extern "C" int64_t sz_slab_meta_doubles(int32_t cap_img) { return SL_META_HDR + 3 * (int64_t)cap_img; }
 extern "C" int64_t sz_slab_block_doubles(int32_t cap_rec, int32_t cap_vert) { return 2 + (int64_t)cap_rec * SL_REC + 2 * (int64_t)cap_vert; }
@@ -1330,7 +1246,7 @@ extern "C" int sz_slab_upload(SzContext* c, const SzParams* prm, const SzFloesSo
     CK(c->scan_tmp.ensure(scan_tmp_ints((size_t)n + 2)));
     if (!c->sl_scratch) CK(cudaMalloc(&c->sl_scratch, sizeof(SlabScratch)));
     CK(cudaMemset(c->sl_scratch, 0, sizeof(SlabScratch)));
-    c->slab = true; c->ext_mode = true; c->sl_rank = rank; c->sl_world = world; c->sl_nglobal = n_global; c->sl_configured = false; c->sl_built = false;
+    c->slab = true; c->ext_mode = true; c->sl_xlo = -SZ_INF; c->sl_xhi = SZ_INF; c->sl_rank = rank; c->sl_world = world; c->sl_nglobal = n_global; c->sl_configured = false; c->sl_built = false;
     return SZ_OK;
 }
 // flags, scans and extents of the owned floes from their current state (shared by sz_slab_measure and sz_slab_prepare)
@@ -1340,7 +1256,7 @@ static int slab_flags(SzContext* c)
     int* fx = c->sl_flag.p; int* fy = fx + (n + 1); int* fxy = fy + (n + 1);
     int* px = c->sl_pos.p; int* py = px + (n + 2); int* pxy = py + (n + 2);
     ++g_launches; slab_scratch_init_kernel<<<1, 1, 0, st>>>(c->sl_scratch);
-    if (n > 0) { ++g_launches; slab_flag_kernel<<<std::min(nblk(n, 256), 148 * 16), 256, 0, st>>>(n, c->x.p, c->y.p, c->rmax.p, c->alive.p, c->voff.p, c->vx.p, c->vy.p, P.Lx, P.Ly, P.periodic, fx, fy, fxy, c->sl_scratch); }
+    if (n > 0) { ++g_launches; slab_flag_kernel<<<std::min(nblk(n, 256), 148 * 16), 256, 0, st>>>(n, c->x.p, c->y.p, c->rmax.p, c->alive.p, c->voff.p, c->vx.p, c->vy.p, P.Lx, P.Ly, P.periodic, fx, fy, fxy, c->sl_scratch, c->sl_xlo, c->sl_xhi); }
     exclusive_scan(fx, n, px, n + 1, c->scan_tmp.p, st);
     exclusive_scan(fy, n, py, n + 1, c->scan_tmp.p, st);
     exclusive_scan(fxy, n, pxy, n + 1, c->scan_tmp.p, st);
@@ -1406,6 +1322,12 @@ extern "C" int sz_slab_configure(SzContext* c, int32_t cap_img, int32_t cap_rec,
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->sl_keys.p, c->sl_keys.p + ns, c->sl_slots.p, c->sl_slots.p + ns, (int)ns, 0, 32, c->stream);
     CK(c->sl_cub.ensure(bytes + 16));
     c->sl_cap_img = cap_img; c->sl_cap_rec = cap_rec; c->sl_cap_vert = cap_vert; c->sl_nl_cap = (int)nl; c->sl_configured = true; c->sl_built = false;
+    return SZ_OK;
+}
+extern "C" int sz_slab_set_extent(SzContext* c, double xlo, double xhi)
+{
+    if (!c || !c->slab) { sz_set_error("sz_slab_set_extent: needs sz_slab_upload"); return SZ_ERR_STATE; }
+    c->sl_xlo = xlo; c->sl_xhi = xhi;
     return SZ_OK;
 }
 extern "C" int sz_slab_prepare(SzContext* c, double* meta_dev)
@@ -2050,8 +1972,10 @@ extern "C" int sz_trajectory_init(SzContext* c, const SzTrajectoryInit* in)
     // c0 = the unrotated outline (initialize_floe_values.m:18); default: the current c_alpha, i.e. alpha_i = 0
     CK(cudaMemcpyAsync(c->c0x.p, in->c0x ? in->c0x : c->vx.p, nv * 8, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(c->c0y.p, in->c0y ? in->c0y : c->vy.p, nv * 8, cudaMemcpyDefault, st));
     CK(c->t_stressH.ensure(n * (size_t)in->nz * 4 + 4)); CK(c->t_stress.ensure(n * 4 + 4)); CK(c->t_scount.ensure(n + 1)); CK(c->t_flags.ensure(n + 1));
-    CK(cudaMemsetAsync(c->t_stressH.p, 0, n * (size_t)in->nz * 32, st));            // StressH = zeros(2,2,1000), StressCount = 1 (:24-25)
-    { std::vector<int> ones(n, 1); CK(cudaMemcpyAsync(c->t_scount.p, ones.data(), n * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st)); }
+    if (in->stress_h) CK(cudaMemcpyAsync(c->t_stressH.p, in->stress_h, n * (size_t)in->nz * 32, cudaMemcpyDefault, st));
+    else CK(cudaMemsetAsync(c->t_stressH.p, 0, n * (size_t)in->nz * 32, st));       // StressH = zeros(2,2,1000), StressCount = 1 (:24-25)
+    if (in->stress_count) { CK(cudaMemcpyAsync(c->t_scount.p, in->stress_count, n * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st)); }
+    else { std::vector<int> ones(n, 1); CK(cudaMemcpyAsync(c->t_scount.p, ones.data(), n * 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st)); }
     CK(cudaMemsetAsync(c->t_flags.p, 0, n * 4, st));
     CK(c->t_strain.ensure(n * 4 + 4)); CK(c->t_forced.ensure(n + 1));
     CK(cudaMemsetAsync(c->t_strain.p, 0, n * 32, st)); CK(cudaMemsetAsync(c->t_forced.p, 0, n, st));      // floe.strain starts at zero
@@ -2084,6 +2008,16 @@ extern "C" int sz_trajectory_step(SzContext* c, const SzTrajectoryParams* p, int
     if (n_sacked) *n_sacked = c->h_cnt->n_cap_fail;
     if (n_needs_ocean) *n_needs_ocean = c->h_cnt->n_fail;
     if (c->h_cnt->n_fail > 0) { sz_set_error("%d floe(s) thinner than 0.1 m need the ocean forcing re-evaluated (calc_trajectory.m:94): not part of this path", c->h_cnt->n_fail); return SZ_ERR_STATE; }
+    return SZ_OK;
+}
+extern "C" int sz_get_stress_history(SzContext* c, double* stress_h, int32_t* stress_count)
+{
+    if (!c) { sz_set_error("sz_get_stress_history: NULL context"); return SZ_ERR_ARG; }
+    if (!c->have_traj) { sz_set_error("sz_get_stress_history: no integrator state"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n0;
+    D2H(stress_h, c->t_stressH.p, n * (size_t)c->traj_nz * 32); D2H(stress_count, c->t_scount.p, n * 4);
+    CK(cudaStreamSynchronize(c->stream));
     return SZ_OK;
 }
 extern "C" int sz_trajectory_set_ocean(SzContext* c, const SzOcean* o)

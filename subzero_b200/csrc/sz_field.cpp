@@ -16,7 +16,14 @@
 #include <algorithm>
 #include <string>
 
-void sz_set_error(const char* fmt, ...);   // sz_abi (sz_kernels.cu)
+#ifdef SZ_FIELD_STANDALONE
+// libsz_field.so: the generator without the CUDA library around it (bench.py's CPU arm); errors go to stderr
+#include <cstdio>
+#include <cstdarg>
+void sz_set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); }
+#else
+void sz_set_error(const char* fmt, ...);   // sz_contact.cu
+#endif
 
 struct SzField {
     std::vector<double> x, y, rmax, h, area, u, v, ksi, vx, vy;

@@ -4,7 +4,27 @@ import ctypes as C
 
 import numpy as np
 
+import os
+
 from . import abi
+
+_flib = None
+
+
+def _field_lib():
+    """the generator's own small host library (libsz_field.so, built next to the product library): the CPU reference arm uses
+    the same synthetic field without mapping the CUDA library"""
+    global _flib
+    if _flib is None:
+        path = os.path.join(os.path.dirname(abi.LIB_PATH), "libsz_field.so")
+        if not os.path.exists(path):
+            raise RuntimeError("subzero_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+        l = C.CDLL(path)
+        for name in ("sz_field_voronoi", "sz_field_view", "sz_field_free"):
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = abi.PROTOTYPES[name]
+        _flib = l
+    return _flib
 
 
 def morton_order(x, y, Lx, Ly):
@@ -27,16 +47,17 @@ def voronoi_field(n_floes, seed=0, mean_area=4e6, inflate=0.02, dt=10.0, order="
     experiment on how much a spatial numbering is worth to the gather-bound kernels; same floes, different input order)."""
     prm = abi.default_params()
     h = C.c_void_p()
-    abi.check(abi.lib().sz_field_voronoi(C.byref(h), int(n_floes), int(seed), float(mean_area), float(inflate), C.byref(prm)))
+    flib = _field_lib()
+    abi.check(flib.sz_field_voronoi(C.byref(h), int(n_floes), int(seed), float(mean_area), float(inflate), C.byref(prm)))
     try:
         v = abi.SzFloesSoA()
-        abi.check(abi.lib().sz_field_view(h, C.byref(v)))
+        abi.check(flib.sz_field_view(h, C.byref(v)))
         n, nv = v.n, v.nverts
         cp = lambda p, m, dt_: np.ctypeslib.as_array(p, shape=(m,)).astype(dt_, copy=True) if m else np.zeros(0, dt_)
         soa = abi.FloesSoA(*(cp(getattr(v, k), n, np.float64) for k in abi.FloesSoA.FIELDS),
                            cp(v.alive, n, np.uint8), cp(v.voff, n + 1, np.int32), cp(v.vx, nv, np.float64), cp(v.vy, nv, np.float64))
     finally:
-        abi.lib().sz_field_free(h)
+        flib.sz_field_free(h)
     prm.periodic, prm.collision, prm.dt, prm.Nb = 1, 1, float(dt), 0
     if order == "morton":
         soa = soa.take(morton_order(soa.x, soa.y, prm.Lx, prm.Ly))

@@ -1,23 +1,26 @@
-"""Work partition of one contact step over the GPUs of one box: spatial slabs with a halo exchange.
+"""Work partition of the contact step over the GPUs of one box: spatial slabs with a halo exchange.
 
-One process per GPU.  The domain [-Lx, Lx) is cut into `world` equal-width slabs along x; a floe belongs to
-the slab that holds its centroid (floes are numbered slab by slab, so every rank owns a contiguous range of
-global floe ids).  Every step each rank
+One process per GPU.  The domain [-Lx, Lx) is cut into `world` slabs along x (equal widths, or the quantiles of the centroids
+for a field of non-uniform density); a floe is owned by the rank whose slab held its centroid when the field was (re)partitioned
+-- the floes are numbered slab by slab, so a rank usually owns a contiguous range of the global floe numbers, but the device
+path works for any ascending subset (after `DeviceSlab.repartition` moved floes between ranks, numbers stay what they were).
 
-  1. builds the periodic images of ITS floes (floe_interactions_all.m:16-66) and numbers them in the global
-     extended list with one tiny all-gather of counts -- the global list [originals | x-ghosts | y-ghosts] is the
-     reference's, so every `j > i` comparison, partner id and row order is the single-GPU one;
-  2. sends to every other rank the entries (state + outline) that lie within reach (2 max(rmax)) of the x-extent
-     of that rank's entries: the halo exchange, variable-size peer-to-peer messages over NCCL (NVLink);
-  3. resolves, on its own GPU, every pair with at least one owned floe through the extended-list entry point of
-     the C ABI (sz_upload_extended) -- pairs straddling two slabs are evaluated on both sides (about
-     2 * reach / slab_width of all pairs), which keeps each floe's rows bit-identical to the single-GPU
-     result and removes the return exchange of partial forces: the forces on an owned periodic image are
-     folded into its parent by the owner (:242-245), exactly as on one GPU;
-  4. applies the serial kill/transfer fix-up of :175-179 across ranks (all-gather of the rare merge events).
+The product path is `DeviceSlab`: the list surgery runs in the library's kernels (sz_slab_prepare / _pack / _build) every step,
+from the current state, around two collectives (an all-gather of small per-rank meta records and an all-to-all of fixed-size
+blocks with the halo entries and their current outlines), all on one CUDA stream.
 
-All list surgery is torch tensor code, so the same functions run on CPU tensors under gloo (tests) and on CUDA
-tensors under NCCL.  There is no data-path collective besides the halo exchange and two small all-gathers.
+`build_local_list` / `fix_kill_transfer` are the same list logic written with torch tensor operations: the reference
+implementation that runs under gloo on CPU tensors (tests/test_slabs_cpu.py: against the oracle's global extended list and
+candidate pairs) and that the GPU worker compares the device-built list with (tests/slab_worker.py).
+
+What every rank's list holds, and why results are the single-GPU ones:
+  1. the periodic images of ITS floes (floe_interactions_all.m:16-66), numbered in the GLOBAL extended list [originals |
+     x-ghosts | y-ghosts] -- so every `j > i` comparison, partner id and row order is the single-GPU one;
+  2. every entry of another rank that lies within reach (2 max(rmax)) of this rank's x-extent: the halo;
+  3. every pair with at least one owned floe is resolved locally -- pairs straddling two slabs on both sides (about
+     2 * reach / slab_width of all pairs), which keeps each floe's rows bit-identical to the single-GPU result and replaces the
+     return exchange of partial forces; the forces on an owned periodic image are folded into its parent by the owner (:242-245);
+  4. the serial kill/transfer fix-up of :175-179 runs across ranks on the (rare) merge events.
 """
 import ctypes as C
 from dataclasses import dataclass
@@ -189,7 +192,7 @@ class LocalList:
     n_ext_global: int
     halo_sent: int
     halo_bytes: int
-    plan: dict = None        # what refresh_local_state needs to move only the motion state on later steps
+    plan: dict = None        # bookkeeping of the build (image parents, halo selection), kept for inspection
 
 
 def _sgn(t):
@@ -197,8 +200,10 @@ def _sgn(t):
 
 
 def build_local_list(st, Lx, Ly, periodic, reach, comm, skin=0.0):
-    """Steps 1 and 2 of the module docstring.  `reach` = 2 * max(rmax) over all ranks; `skin` widens the halo so that the
-    list stays valid while no floe has moved more than skin / 2 (refresh_local_state)."""
+    """The rank's part of the global extended floe list in torch (CPU or CUDA tensors): the REFERENCE IMPLEMENTATION of what
+    the library's sz_slab_prepare / sz_slab_pack / sz_slab_build kernels do on the device.  It runs under gloo on CPU tensors
+    (tests/test_slabs_cpu.py holds it to the oracle's global list and candidate pairs) and the GPU worker compares the
+    device-built list with it entry by entry.  `reach` = 2 * max(rmax) over all ranks; `skin` optionally widens the halo."""
     reach = reach + skin
     dev = st.x.device
     n = st.n
@@ -307,40 +312,6 @@ def build_local_list(st, Lx, Ly, periodic, reach, comm, skin=0.0):
                   order=order, n_own=n_own, x0=st.x.clone(), y0=st.y.clone(), skin=skin))
 
 
-def refresh_local_state(st, Lx, Ly, periodic, plan, comm):
-    """Later steps of an unchanged topology: only the motion state (centroids, velocities) moves.  Recomputes the image
-    centroids of the planned images, checks that the plan still holds -- same floes poke through the periodic boundary
-    (the image set is exact every step) and no floe has moved more than skin / 2 (the planned halo still covers every
-    candidate pair) -- and exchanges 7 doubles per halo entry.  Returns (valid, state [7, n_local]) with rows
-    x y u v ksi root_x root_y in local (ascending gid) order; valid is agreed by all ranks."""
-    dev = st.x.device
-    n = st.n
-    bad = torch.zeros((), dtype=F64, device=dev)
-    if periodic:
-        minvx, maxvx, minvy, maxvy = st.ext
-        alive = st.alive != 0
-        fx = alive & (torch.maximum((maxvx + st.x).abs(), (minvx + st.x).abs()) > Lx)
-        xg_par = plan["xg_par"]
-        xg_x, xg_y = st.x[xg_par] - 2 * Lx * _sgn(st.x[xg_par]), st.y[xg_par]
-        src_all = plan["src_all"]
-        x_all, y_all = torch.cat([st.x, xg_x]), torch.cat([st.y, xg_y])
-        fy = alive[src_all] & (torch.maximum((maxvy[src_all] + y_all).abs(), (minvy[src_all] + y_all).abs()) > Ly)
-        yg_par = plan["yg_par"]
-        yg_x, yg_y = x_all[yg_par], y_all[yg_par] - 2 * Ly * _sgn(y_all[yg_par])
-        bad = bad + (fx != plan["fx"]).any().to(F64) + (fy != plan["fy"]).any().to(F64)
-        ox, oy = torch.cat([x_all, yg_x]), torch.cat([y_all, yg_y])
-    else:
-        ox, oy = st.x, st.y
-    moved = torch.maximum((st.x - plan["x0"]).abs().max(), (st.y - plan["y0"]).abs().max()) if n else bad
-    bad = bad + (~(moved <= 0.5 * plan["skin"])).to(F64)          # NaN counts as moved
-    src = plan["src"]
-    own = torch.stack([ox, oy, st.u[src], st.v[src], st.ksi[src], st.x[src], st.y[src]], 1)       # [n_own, 7]
-    if float(comm.all_max(bad.reshape(1))) != 0.0:
-        return False, None
-    recv = comm.exchange(own[plan["sidx"]], plan["send_counts"], plan["recv_counts"])
-    return True, torch.cat([own, recv])[plan["order"]].t().contiguous()
-
-
 def fix_kill_transfer(gid, floe_num, owned, kill_i, transfer_i, id0, n_own, comm):
     """floe_interactions_all.m:175-179 across ranks:  for i = 1:length(kill): if kill(i) ~= i && kill(i) > 0,
     transfer(kill(i)) = i  (serial, so the largest i wins).  Inputs are per local entry; returns (kill, transfer)
@@ -365,149 +336,6 @@ def fix_kill_transfer(gid, floe_num, owned, kill_i, transfer_i, id0, n_own, comm
         win = torch.zeros(n_own, dtype=I64, device=dev).scatter_reduce(0, tgt[ok], recs[ok, 0], "amax", include_self=True)
         transfer = torch.where(win > 0, win.to(transfer.dtype), transfer)
     return kill, transfer
-
-
-# ------------------------------------------------------------------------------------------------ the job
-class SlabStep:
-    """one rank's contact step over its slab: halo exchange + local GPU step + extraction of its floes' results"""
-
-    def __init__(self, prm, st, comm, ctx, skin=None):
-        self.prm, self.st, self.comm, self.ctx = prm, st, comm, ctx
-        self.plans = self.fast_steps = 0
-        rm = st.rmax.max() if st.n else torch.zeros((), dtype=F64, device=st.x.device)
-        self.reach = 2.0 * float(comm.all_gather(rm.reshape(1).to(F64)).max())
-        self.skin = 0.05 * self.reach if skin is None else float(skin)      # halo skin: the plan survives moves < skin / 2
-        self.local = None
-        self._first = None
-        self.summary = None
-        self._shared_stream = False
-        if st.x.is_cuda and comm.dist is not None and not comm.stage:
-            # NCCL's exchange is ordered on torch's current stream: let the library launch there too, so that refresh ->
-            # exchange -> scatter -> step need no host synchronisation between them
-            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-            self._shared_stream = True
-
-    def _refresh_on_device(self):
-        """refresh_local_state with the list surgery done by the library's slab kernels (CUDA tensors).  Returns the
-        device flag "the plan is stale on some rank" (already all-reduced); the caller reads it after the step, which it
-        repeats with a new plan in that rare case, instead of stalling the pipeline before the exchange."""
-        st, prm, plan, comm = self.st, self.prm, self.local.plan, self.comm
-        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ) if t is not None and t.numel() else None
-        dev = st.x.device
-        if "own_buf" not in plan:
-            u8 = lambda t: t.to(torch.uint8).contiguous() if t is not None else None
-            plan.update(own_buf=torch.empty((plan["n_own"], 7), dtype=F64, device=dev), bad_buf=torch.zeros(1, dtype=torch.int32, device=dev),
-                        fx8=u8(plan["fx"]), fy8=u8(plan["fy"]), xg_c=plan["xg_par"].contiguous(), yg_c=plan["yg_par"].contiguous(), order_c=plan["order"].contiguous())
-        srcs = (st.x, st.y, st.u, st.v, st.ksi, st.ext[0], st.ext[1], st.ext[2], st.ext[3], plan["x0"], plan["y0"], st.alive)
-        key = tuple(t.data_ptr() for t in srcs) + tuple(t.is_contiguous() for t in srcs)
-        if plan.get("_refresh_key") != key or not all(key[len(srcs):]):
-            # the descriptor only holds pointers: it is rebuilt when a state tensor was replaced (not when it was updated in place)
-            r = abi.SzSlabRefresh()
-            r.n_orig, r.n_xg, r.n_yg = st.n, int(plan["xg_c"].shape[0]), int(plan["yg_c"].shape[0])
-            keep = []
-            for nm, t in zip(("x", "y", "u", "v", "ksi", "minvx", "maxvx", "minvy", "maxvy", "x0", "y0"), srcs[:11]):
-                t = t.contiguous(); keep.append(t)
-                setattr(r, nm, P(t, abi.c_dp))
-            r.alive = P(st.alive, abi.c_bp)
-            r.xg_par, r.yg_par = P(plan["xg_c"], abi.c_lp), P(plan["yg_c"], abi.c_lp)
-            r.fx_plan, r.fy_plan = P(plan["fx8"], abi.c_bp), P(plan["fy8"], abi.c_bp)
-            r.Lx, r.Ly, r.half_skin, r.periodic = prm.Lx, prm.Ly, 0.5 * plan["skin"], int(bool(prm.periodic))
-            r.own_out, r.bad_out = P(plan["own_buf"], abi.c_dp), P(plan["bad_buf"], abi.c_ip)
-            plan["_refresh_desc"], plan["_refresh_keep"], plan["_refresh_key"] = r, keep, key
-        r = plan["_refresh_desc"]
-        if not self._shared_stream:
-            torch.cuda.current_stream().synchronize()
-        abi.check(abi.lib().sz_slab_refresh(self.ctx._h, C.byref(r)))
-        bad = comm.all_max(plan["bad_buf"])           # one small all-reduce, left on the stream
-        send = plan["own_buf"][plan["sidx"]]
-        recv = comm.exchange(send, plan["send_counts"], plan["recv_counts"])
-        if not self._shared_stream:
-            torch.cuda.current_stream().synchronize()
-        n_own, n_recv = plan["n_own"], int(recv.shape[0])
-        abi.check(abi.lib().sz_slab_scatter(self.ctx._h, P(plan["own_buf"], abi.c_dp), n_own, P(recv, abi.c_dp), n_recv, P(plan["order_c"], abi.c_lp), n_own + n_recv))
-        plan["_keep"] = (recv, send)          # the exchange and the scatter kernel read them asynchronously
-        return bad
-
-    def invalidate(self):
-        """call when floes were created, destroyed or reshaped (the outlines and the alive flags are part of the plan)"""
-        self.local = None
-
-    def run(self):
-        """one contact step.  The first call (and every call after the plan went stale) builds the local list and
-        uploads it; the others move only the motion state: 7 doubles per entry, one small all-gather, one exchange."""
-        st, prm = self.st, self.prm
-        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
-        if self.local is not None and self.skin > 0:
-            if st.x.is_cuda:
-                bad = self._refresh_on_device()         # two library kernels + one gather around the exchange
-                summary = self.ctx.step_resident()
-                if int(bad) == 0:                       # read after the step (its counter read-backs synchronised already)
-                    self.fast_steps += 1
-                    self.summary = summary
-                    return summary
-                ok = False                              # some rank's plan went stale: this step is repeated with a new plan
-            else:
-                ok, dyn = refresh_local_state(st, prm.Lx, prm.Ly, bool(prm.periodic), self.local.plan, self.comm)
-                if ok:
-                    abi.check(abi.lib().sz_update_extended_state(self.ctx._h, *(P(dyn[k], abi.c_dp) for k in range(7))))
-            if ok:
-                self.fast_steps += 1
-                self.summary = self.ctx.step_resident()
-                return self.summary
-        L = build_local_list(st, prm.Lx, prm.Ly, bool(prm.periodic), self.reach, self.comm, self.skin)
-        self.local = L
-        self._first = None
-        self.plans += 1
-        n = L.gid.shape[0]
-        i32 = lambda t: t.to(torch.int32).contiguous()
-        keep = [L.x.contiguous(), L.y.contiguous()] + [L.body[:, k].contiguous() for k in range(6)] + [L.alive.contiguous(), i32(L.voff), L.vx.contiguous(), L.vy.contiguous(),
-                i32(L.gid + 1), i32(L.floe_num), L.root_x.contiguous(), L.root_y.contiguous(), L.owned.contiguous(), i32(L.parent)]
-        x, y, rmax, h, area, u, v, ksi, alive, voff, vx, vy, gid1, fnum, rx, ry, owned, parent = keep
-        fs = abi.SzFloesSoA()
-        fs.n, fs.nverts = n, vx.shape[0]
-        for nm, t in (("x", x), ("y", y), ("rmax", rmax), ("h", h), ("area", area), ("u", u), ("v", v), ("ksi", ksi), ("vx", vx), ("vy", vy)):
-            setattr(fs, nm, P(t, abi.c_dp))
-        fs.alive, fs.voff = P(alive, abi.c_bp), P(voff, abi.c_ip)
-        ext = abi.SzExtendedList(P(gid1, abi.c_ip), P(fnum, abi.c_ip), P(rx, abi.c_dp), P(ry, abi.c_dp), P(owned, abi.c_bp), P(parent, abi.c_ip))
-        if x.is_cuda:
-            torch.cuda.current_stream().synchronize()        # the library copies from these tensors on its own stream
-        abi.check(abi.lib().sz_upload_extended(self.ctx._h, C.byref(prm), C.byref(fs), None, C.byref(ext)))
-        self.ctx._n0 = n
-        self.summary = self.ctx.step_resident()
-        return self.summary
-
-    def results(self, pinned=None):
-        """per-floe outputs and contact rows of this rank's original floes, in global id order (they are one contiguous
-        run of the local list: lower ranks' originals sort before it, higher ranks' and every image after it).
-        `pinned`: optional dict that caches page-locked receive buffers between calls."""
-        L, ctx = self.local, self.ctx
-        n_loc, n_rows = int(L.gid.shape[0]), int(self.summary.n_rows)
-        if pinned is not None:
-            if pinned.get("n") != n_loc:
-                z = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-                pinned.update(n=n_loc, out={"fx": z(n_loc, F64), "fy": z(n_loc, F64), "torque": z(n_loc, F64), "overlap_area": z(n_loc, F64), "stress": z((n_loc, 2, 2), F64),
-                                            "xi": z(n_loc, F64), "yi": z(n_loc, F64), "alive": z(n_loc, torch.uint8), "kill": z(n_loc, torch.int32), "transfer": z(n_loc, torch.int32)},
-                              off=z(n_loc + 1, I64), rows=None)
-            if pinned["rows"] is None or pinned["rows"].shape[0] < n_rows:
-                pinned["rows"] = torch.empty((int(n_rows * 1.1) + 16, 7), dtype=F64).pin_memory().numpy()
-            o = ctx.floe_outputs(into=pinned["out"])
-            off, rows = pinned["off"], pinned["rows"]
-            abi.check(abi.lib().sz_get_rows(ctx._h, abi._ptr(off, abi.c_lp), abi._ptr(rows, abi.c_dp)))
-        else:
-            o = ctx.floe_outputs()
-            off, rows = ctx.rows()
-        if self._first is None:
-            self._first = int(torch.searchsorted(L.gid, self.st.id0))
-        first = self._first
-        last = first + self.st.n
-        out = {k: v[first:last] for k, v in o.items()}
-        dev = L.gid.device
-        kill, transfer = fix_kill_transfer(L.gid, L.floe_num, L.owned, torch.from_numpy(o["kill"]).to(dev).to(I64), torch.from_numpy(o["transfer"]).to(dev).to(I64),
-                                           self.st.id0, self.st.n, self.comm)
-        out["kill"], out["transfer"] = kill.cpu().numpy().astype(np.int32), transfer.cpu().numpy().astype(np.int32)
-        row_off = off[first:last + 1] - off[first]
-        return out, row_off, rows[off[first]:off[last]]
-
 
 
 # ------------------------------------------------------------------------------------------------ device-built slab step
@@ -572,7 +400,7 @@ class DeviceSlab:
         z = lambda n: torch.zeros(n, dtype=F64, device=self.dev)
         self.meta, self.all_meta = z(self.meta_n), z(W * self.meta_n)
         self.send, self.recv = z(W * self.block), z(W * self.block)
-        self.status = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros(3, dtype=torch.int32, device=self.dev)
         self.halo_measured = (int(rec.sum()), int(vert.sum()))
         self.plans += 1
 
@@ -591,21 +419,78 @@ class DeviceSlab:
             if self.comm.stage:
                 torch.cuda.current_stream(self.dev).synchronize()
         abi.check(lib.sz_slab_build(h, P(self.recv, abi.c_dp), P(self.status, abi.c_ip)))
-        self.flag = self.comm.all_max(self.status[:1].to(F64)) if W > 1 else self.status[:1]     # capacity overflow on any rank
+        # agreed by all ranks: [capacity overflow on some rank, owned floes that left their rank's extent]
+        self.flag = self.comm.all_max(self.status[[0, 2]].to(F64)) if W > 1 else self.status[[0, 2]].to(F64)
 
     def run(self, allow_pair_errors=False):
         """one contact step on the current state; returns the step's SzSummary (n = the padded list length)"""
         for attempt in range(4):
             self.exchange()
             s = self.ctx.step_resident(allow_pair_errors=allow_pair_errors)
-            if int(self.flag.item()) == 0:
-                self.summary, self.steps = s, self.steps + 1
+            flag = self.flag.cpu()
+            if int(flag[0]) == 0:
+                self.summary, self.steps, self.n_outside = s, self.steps + 1, int(flag[1])
                 return s
             self.plan(grow=2.0 ** (attempt + 1))           # the field outgrew the blocks: new capacities, repeat the step
         raise RuntimeError("slab step: capacities kept overflowing")
 
     def trajectory_init(self, mass, inertia, nz=1000, **fields):
         self.ctx.trajectory_init(mass, inertia, nz=nz, **fields)
+        self._nz = int(nz)
+        self._c0 = (np.array(fields["c0x"], np.float64), np.array(fields["c0y"], np.float64)) if "c0x" in fields else (self.owned.vx.copy(), self.owned.vy.copy())
+
+    def set_extent(self, xlo, xhi, tol=0.0):
+        """the x-range this rank's floes belong to (its slab, widened by `tol`): after a step `n_outside` says how many live
+        owned floes have left it on some rank -- the cue for repartition()"""
+        self.extent, self.extent_tol = (float(xlo), float(xhi)), float(tol)
+        abi.check(abi.lib().sz_slab_set_extent(self.ctx._h, float(xlo) - tol, float(xhi) + tol))
+
+    def repartition(self, edges):
+        """Floe migration between slabs: every floe goes to the rank whose slab [edges[r-1], edges[r]) holds its CURRENT centroid
+        (interior edges [world - 1] as from slab_edges()); floes keep their global numbers, so results stay those of the
+        single-GPU run.  A moving floe takes everything along: state, rotated outline and c0, the integrator's previous-step
+        values and forcing, its stress history.  Host-mediated (rare: a floe has to cross a slab first); needs
+        trajectory_init.  Returns the number of floes this rank gave away."""
+        comm, W, r = self.comm, self.comm.world, self.comm.rank
+        n, nv = self.owned.n, self.owned.vx.shape[0]
+        st = self.ctx.trajectory_state(nverts=nv)
+        fo = self.ctx.trajectory_forcing()
+        sh, sc = self.ctx.stress_history()
+        dest = slab_of(st["x"], self.prm.Lx, W, edges)
+        dest = np.where(np.isnan(st["x"]), r, dest)
+        voff = self.owned.voff.astype(np.int64)
+        per_floe = {k: st[k] for k in ("x", "y", "u", "v", "ksi", "h", "alive", "mass", "inertia", "alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p")}
+        per_floe.update(rmax=self.owned.rmax, area=self.owned.area, FxOA=fo["FxOA"], FyOA=fo["FyOA"], torqueOA=fo["torqueOA"], gid=self.gid, stress_count=sc, nv=np.diff(voff))
+        per_floe["stress_h"] = sh.reshape(n, -1)
+
+        def take(idx):
+            d = {k: np.ascontiguousarray(v[idx]) for k, v in per_floe.items()}
+            vi = np.repeat(voff[idx] - np.concatenate([[0], np.cumsum(per_floe["nv"][idx])[:-1]]), per_floe["nv"][idx]) + np.arange(int(per_floe["nv"][idx].sum())) if len(idx) else np.zeros(0, np.int64)
+            d.update(cax=st["cax"][vi], cay=st["cay"][vi], c0x=self._c0[0][vi], c0y=self._c0[1][vi])
+            return d
+        out = {p: take(np.nonzero(dest == p)[0]) for p in range(W) if p != r and (dest == p).any()}
+        gathered = [None] * W
+        if W > 1:
+            comm.dist.all_gather_object(gathered, out)
+        parts = [take(np.nonzero(dest == r)[0])] + [g[r] for p, g in enumerate(gathered) if p != r and g and r in g]
+        cat = lambda k: np.concatenate([p_[k] for p_ in parts])
+        order = np.argsort(cat("gid"), kind="stable")
+        nvs = cat("nv")
+        starts = np.concatenate([[0], np.cumsum(nvs)[:-1]]).astype(np.int64)
+        vi = np.repeat(starts[order] - np.concatenate([[0], np.cumsum(nvs[order])[:-1]]), nvs[order]) + np.arange(int(nvs.sum())) if len(order) else np.zeros(0, np.int64)
+        g = lambda k: cat(k)[order]
+        new_voff = np.concatenate([[0], np.cumsum(nvs[order])]).astype(np.int32)
+        owned = abi.FloesSoA(g("x"), g("y"), g("rmax"), g("h"), g("area"), g("u"), g("v"), g("ksi"), g("alive").astype(np.uint8), new_voff, cat("cax")[vi], cat("cay")[vi])
+        gave = int((dest != r).sum())
+        self.upload(owned, g("gid").astype(np.int32), plan=True)
+        nz = self._nz
+        self.trajectory_init(g("mass"), g("inertia"), nz=nz, c0x=cat("c0x")[vi], c0y=cat("c0y")[vi], stress_h=g("stress_h").reshape(owned.n, nz, 4), stress_count=g("stress_count"),
+                             **{k: g(k) for k in ("alpha", "dXi_p", "dYi_p", "dUi_p", "dVi_p", "dalpha_p", "dksi_p", "FxOA", "FyOA", "torqueOA")})
+        lo = -np.inf if r == 0 else float(edges[r - 1])
+        hi = np.inf if r == W - 1 else float(edges[r])
+        if hasattr(self, "extent_tol"):
+            self.set_extent(lo, hi, self.extent_tol)
+        return gave
 
     def trajectory_step(self, dt, HFo=0.0, *bounds):
         return self.ctx.trajectory_step(dt, HFo, *bounds)

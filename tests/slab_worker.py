@@ -42,6 +42,7 @@ def main():
             prm.periodic = 0
             c2, fb = scenarios.domain(prm.Lx, prm.Ly)
             bnd = sz.Boundary(fb["c"][0], fb["c"][1], c2[0], c2[1], fb["area"], fb["h"])
+    migrate = kind == "migrate"
     fast = kind != "real"
     if fast:
         field.u[:] *= 100.0      # tens of metres per step: floes cross the periodic boundary and the slab edges within the run
@@ -69,17 +70,63 @@ def main():
         one.trajectory_init(mass, inertia, nz=nz, dXi_p=field.u, dYi_p=field.v, torqueOA=torque_oa)
     ok = True
     moved = 0.0
+    n_migrated = [0]
     for it in range(steps):
         s = slab.run(allow_pair_errors=True)
+        if it == 0:
+            # the list the kernels built against the torch reference implementation of the same logic (subzero_b200.slabs.build_local_list)
+            st = slabs.SlabState.from_soa(mine, a, field.n, dev)
+            reach = 2.0 * float(comm.all_gather(st.rmax.max().reshape(1)).max())
+            Lt = slabs.build_local_list(st, prm.Lx, prm.Ly, bool(prm.periodic), reach, comm)
+            Ld = slab.local_list()
+            same = (np.array_equal(Ld["gid"], Lt.gid.cpu().numpy() + 1) and np.array_equal(Ld["floe_num"], Lt.floe_num.cpu().numpy()) and np.array_equal(Ld["owned"], Lt.owned.cpu().numpy())
+                    and np.array_equal(Ld["x"], Lt.x.cpu().numpy(), equal_nan=True) and np.array_equal(Ld["y"], Lt.y.cpu().numpy(), equal_nan=True))
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(same))
+            if not all(flags):
+                ok = False
+                if rank == 0:
+                    print("MISMATCH device-built list vs torch reference list", flags)
         out = slab.outputs()
         row_off, rows = slab.rows()
         n_sacked = slab.trajectory_step(prm.dt, hfo, *bounds)
         state = ctx.trajectory_state(nverts=mine.vx.shape[0])
         stats = np.array([s.n_pairs_owned, s.n_pairs_force, s.collision_count, s.n_pairs, n_sacked, slab.plans], dtype=np.float64)
         gathered = [None] * world
-        dist.gather_object({"out": out, "row_off": row_off, "rows": rows, "stats": stats, "state": state}, gathered if rank == 0 else None, dst=0)
+        dist.gather_object({"out": out, "row_off": row_off, "rows": rows, "stats": stats, "state": state, "gid": slab.gid.copy(), "nv": np.diff(slab.owned.voff)},
+                           gathered if rank == 0 else None, dst=0)
+        if migrate and it in (1, 3):
+            # floe migration: ownership follows the current centroids; the floes keep their numbers, so the comparison below
+            # sorts every rank's results back into global order
+            gave = slab.repartition(slabs.slab_edges(field.x, prm.Lx, world))
+            tot_gave = [None] * world
+            dist.all_gather_object(tot_gave, gave)
+            if rank == 0:
+                print("MIGRATED", it, tot_gave, flush=True)
+                n_migrated[0] += sum(tot_gave)
         if rank == 0:
             good = True
+            # global order of the gathered floes (ranks own arbitrary ascending subsets after a migration)
+            all_gid = np.concatenate([g["gid"] for g in gathered])
+            order = np.argsort(all_gid, kind="stable")
+            assert np.array_equal(all_gid[order], np.arange(1, field.n + 1))
+
+            def ragged(vals, counts):
+                starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+                co = counts[order]
+                idx = np.repeat(starts[order] - np.concatenate([[0], np.cumsum(co)[:-1]]), co) + np.arange(int(co.sum()))
+                return vals[idx]
+            for g in gathered:
+                g["rowcnt"] = np.diff(g["row_off"])
+            per = lambda key, sub: np.concatenate([g[sub][key] for g in gathered])[order]
+            cat_rows = ragged(np.concatenate([g["rows"] for g in gathered]), np.concatenate([g["rowcnt"] for g in gathered]))
+            cat_cnt = np.concatenate([g["rowcnt"] for g in gathered])[order]
+            nvs = np.concatenate([g["nv"] for g in gathered])
+            for g in gathered:
+                g["out"] = dict(g["out"])
+            gathered = [{"out": {k: per(k, "out") for k in gathered[0]["out"]}, "rows": cat_rows, "row_off": np.concatenate([[0], np.cumsum(cat_cnt)]),
+                         "state": {k: (ragged(np.concatenate([g["state"][k] for g in gathered]), nvs) if k in ("cax", "cay") else per(k, "state")) for k in gathered[0]["state"]},
+                         "stats": np.sum([g["stats"] for g in gathered], 0)}]
             s1 = one.step_resident(allow_pair_errors=True)
             o1 = one.floe_outputs()
             off1, rows1 = one.rows()
@@ -112,8 +159,11 @@ def main():
             print("STEP %d %s pairs=%d rows=%d duplicated_pairs=%.3f ghosts=%d kills=%d plans=%d" % (it, "OK" if good else "FAIL", s1.n_pairs, off1[field.n], tot[3] / max(1, s1.n_pairs) - 1,
                                                                                              s1.n - s1.n0, int((o1["kill"] > 0).sum()), int(tot[5])), flush=True)
     if rank == 0:
-        print("RESULT %s world=%d backend=%s floes=%d steps=%d max_alpha=%.3e kill_events=%d" % ("OK" if ok and moved > 0 else "FAIL", world, backend, field.n, steps, moved,
-                                                                                           int((o1["kill"] > 0).sum())), flush=True)
+        if migrate and n_migrated[0] == 0:
+            ok = False
+            print("no floe migrated: the test did not exercise repartition()")
+        print("RESULT %s world=%d backend=%s floes=%d steps=%d max_alpha=%.3e kill_events=%d migrated=%d" % ("OK" if ok and moved > 0 else "FAIL", world, backend, field.n, steps, moved,
+                                                                                                        int((o1["kill"] > 0).sum()), n_migrated[0]), flush=True)
         one.close()
     ctx.close()
     dist.barrier()

@@ -45,6 +45,22 @@ def test_default_params_are_the_reference_constants():
     # floe_interactions.m:20-21 nu, mu; :55-58 0.55; :37 0.75; :79 100/1.75; :99 1; :127 1e-8; :141 0.1; :15 1e5; :54 0.95
     assert (p.nu, p.mu, p.merge_frac, p.wall_frac, p.amin_per_vertex) == (0.3, 0.2, 0.55, 0.75, 100 / 1.75)
     assert (p.vertex_match_tol, p.on_edge_tol, p.dl_min, p.close_gap, p.big_floe_r, p.domain_area_frac) == (1, 1e-8, 0.1, 1, 1e5, 0.95)
+    q = abi.SzParams()
+    abi.lib().sz_default_params(C.byref(q))                      # the host restatement and the library agree field by field
+    assert bytes(p) == bytes(q)
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """bench.py --impl reference: the synthetic field comes from libsz_field.so and the parameter block from the host, so the CPU
+    arm never loads libsubzero_b200.so"""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import subzero_b200 as sz, oracle\n"
+            "prm, f = sz.voronoi_field(300, seed=1)\n"
+            "r = oracle.OracleStep(prm, f, nthreads=2, broad_mode=1)\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "print('PAIRS', r.summary.n_pairs, 'PRODUCT' if 'libsubzero_b200.so' in maps else 'CLEAN', 'FIELD' if 'libsz_field.so' in maps else 'NOFIELD')\n") % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "CLEAN FIELD" in r.stdout and "PAIRS" in r.stdout, r.stdout + r.stderr
 
 
 def test_bad_arguments_are_rejected_without_a_device():

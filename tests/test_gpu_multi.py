@@ -67,6 +67,13 @@ def test_three_slabs_voronoi_coupled():
     print(run(3, 6000, 2, "voronoi"))
 
 
+def test_three_slabs_with_floe_migration():
+    """DeviceSlab.repartition(): floes that crossed a slab edge move to the new owner with their whole state (rotated outline,
+    integrator history, stress history) and keep their global numbers; the coupled loop stays bit-identical to one GPU"""
+    out = run(3, 9000, 7, "migrate", steps=6)
+    assert "migrated=0" not in out
+
+
 def test_two_slabs_walls_coupled():
     """non-periodic domain: wall contacts and floes leaving the domain, resolved by the owner of each floe"""
     print(run(2, 8000, 5, "walls"))

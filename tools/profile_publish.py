@@ -27,6 +27,8 @@ g = lambda n: (float(V[Hh.index(n)].replace(',', '')), U[Hh.index(n)])
 mul = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'Tbyte': 1e12}
 rd, ru = g('dram__bytes_read.sum'); wr, wu = g('dram__bytes_write.sum'); t, tu = g('gpu__time_duration.sum')
 tms = t if tu == 'ms' else t / 1e3 if tu == 'us' else t * 1e3 if tu == 's' else t / 1e6
-d = {"kernel": "narrow_convex_kernel<PairS>", "workload": "bench.py default (1M floes, 1 GPU)", "dram_bytes_per_launch": rd * mul[ru] + wr * mul[wu], "dram_read": rd * mul[ru],
+sys.path.insert(0, R)
+from subzero_b200.build import kernel_stamp
+d = {"kernel": "narrow_convex_kernel<PairS>", "kernel_stamp": kernel_stamp(), "workload": "bench.py default (1M floes, 1 GPU)", "dram_bytes_per_launch": rd * mul[ru] + wr * mul[wu], "dram_read": rd * mul[ru],
      "dram_write": wr * mul[wu], "gpu_time_ms_under_ncu": tms, "dram_gb_per_s": (rd * mul[ru] + wr * mul[wu]) / tms / 1e6, "source": "profiles/%s_narrow_C_1M.txt (ncu --set full, one launch)" % tag}
 json.dump(d, open(os.path.join(R, 'profiles', 'narrow_traffic.json'), 'w'), indent=1); print(json.dumps(d))
