@@ -90,7 +90,7 @@ def main():
         out = slab.outputs()
         row_off, rows = slab.rows()
         n_sacked = slab.trajectory_step(prm.dt, hfo, *bounds)
-        state = ctx.trajectory_state(nverts=mine.vx.shape[0])
+        state = ctx.trajectory_state(nverts=slab.owned.vx.shape[0])
         stats = np.array([s.n_pairs_owned, s.n_pairs_force, s.collision_count, s.n_pairs, n_sacked, slab.plans], dtype=np.float64)
         gathered = [None] * world
         dist.gather_object({"out": out, "row_off": row_off, "rows": rows, "stats": stats, "state": state, "gid": slab.gid.copy(), "nv": np.diff(slab.owned.voff)},
