@@ -157,7 +157,7 @@ int sz_upload_extended(SzContext* ctx, const SzParams* prm, const SzFloesSoA* en
  *                                    FloeNums, root centroid and its CURRENT outline.  send = `world` blocks of
  *                                    sz_slab_block_doubles(cap_rec, cap_vert) doubles; the caller runs one all-to-all of equal splits
  *   sz_slab_build(recv, status)      received entries sorted by global position and merged with the own ones into the resident
- *                                    extended list; status (device, 3 ints, may be NULL) = {capacity overflow, list length, owned floes outside the rank's extent}
+ *                                    extended list; status (device, 4 ints, may be NULL) = {capacity overflow, owned floes outside the rank's extent, list length, 0}
  *   sz_step_resident                 pairs with at least one owned floe (straddling pairs are resolved on both sides, which keeps
  *                                    every floe's rows bit-identical to the single-GPU run and replaces the return of partial forces)
  *   sz_trajectory_step               integrates the owned floes (sz_trajectory_init after sz_slab_upload)
@@ -172,7 +172,7 @@ int sz_slab_upload(SzContext* ctx, const SzParams* prm, const SzFloesSoA* owned,
 int sz_slab_measure(SzContext* ctx, double* local8 /* host: x-images, y-images of originals, y-images of x-images, x-extent of originals [2], of x-images [2], max rmax */);
 int sz_slab_measure_halo(SzContext* ctx, const double* all8 /* host [world*8] */, int64_t* rec_counts /* [world] */, int64_t* vert_counts /* [world] */);
 int sz_slab_configure(SzContext* ctx, int32_t cap_img, int32_t cap_rec, int32_t cap_vert);
-/* the x-range [xlo, xhi) this rank's floes are expected to stay in: sz_slab_build's status word [2] counts the live owned floes
+/* the x-range [xlo, xhi) this rank's floes are expected to stay in: sz_slab_build's status word [1] counts the live owned floes
  * whose centroid left it (the caller's cue to move floes between ranks; results never depend on it).  Default: unbounded. */
 int sz_slab_set_extent(SzContext* ctx, double xlo, double xhi);
 int sz_slab_prepare(SzContext* ctx, double* meta_dev);
@@ -345,8 +345,16 @@ int sz_set_stream(SzContext* ctx, void* cuda_stream);
  *                  Results are bit-identical either way (tests/test_zzzz_experiments.py).
  *   "euler_cell_warp"  1 (default): sz_eulerian_data adds a cell's items up with a warp per cell (32 items' terms at a time,
  *                  added in list order); 0: one thread per cell.  Same order of additions, same results.
+ *   "speculate"     1 (default): a step takes its list length, cell grid, pair and row capacities from the step before (with
+ *                  slack), every kernel reads the true counts from device memory and the host reads the counters once, at the
+ *                  end of the step; a step that outgrew a capacity, or needs a larger narrow-phase size class, is flagged on
+ *                  the device and repeated with measured sizes.  0: measure every size as it is needed (four counter reads).
+ *                  Results are identical either way (tests/test_gpu_parity.py).
  * Returns SZ_ERR_ARG for an unknown name. */
 int sz_set_option(SzContext* ctx, const char* name, int32_t value);
+/* counters of the context: "speculated_steps" (steps that ran on carried-over sizes), "repeated_steps" (steps that had to be
+ * repeated because a carried-over size was too small) */
+int sz_get_stat(SzContext* ctx, const char* name, int64_t* value);
 
 /* ---- stand-alone polygon clip with the gateway's semantics (private/mexclipper.cpp:204-305):
  * `count` independent (subject, clip) pairs, one closed path each, int64 coordinates, even-odd fill,

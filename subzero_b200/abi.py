@@ -112,6 +112,7 @@ PROTOTYPES = {
     "sz_get_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "sz_get_narrow_class_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "sz_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "sz_get_stat": (C.c_int, [C.c_void_p, C.c_char_p, c_lp]),
     "sz_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sz_get_clip_polys": (C.c_int, [C.c_void_p, c_lp, c_lp, c_lp, c_lp]),
     "sz_clip_batch": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp, c_lp]),

@@ -129,6 +129,11 @@ class ContactContext:
             h = int(cuda_stream) or 1                 # cudaStreamLegacy
         abi.check(abi.lib().sz_set_stream(self._h, C.c_void_p(h)))
 
+    def stat(self, name):
+        v = C.c_int64()
+        abi.check(abi.lib().sz_get_stat(self._h, name.encode(), C.byref(v)))
+        return v.value
+
     def set_option(self, name, value):
         abi.check(abi.lib().sz_set_option(self._h, name.encode(), int(value)))
 

@@ -83,6 +83,7 @@ struct Counters {
     int listC0, listS0;            // list lengths before class C ran (listS grows by the pairs class C declines)
     int total_rows;
     int n_pairs_force, n_fail, n_cap_fail, n_pairs_owned, n_bbox_reject, n_kill_events;
+    int overflow;                  // a speculated capacity (list, pairs, rows) was too small: the step is repeated with measured sizes
     u64 bbox[4];                   // order-preserving encodings of min x, max x, min y, max y
     u64 rmax_bits;
     u64 n_fin_rows, n_inf_rows;
@@ -102,6 +103,9 @@ struct SzContext {
     cudaEvent_t evk[10] = {};                  // start/stop of the narrow-phase launch of each size class (C, S, T, M, L)
     bool evk_used[5] = {false, false, false, false, false}; int class_pairs[5] = {0, 0, 0, 0, 0};
     int opt_convex_fast = 1;
+    int opt_speculate = 1;           // sizes of the step (list, grid, pairs, rows) carried over from the previous step: one counter read per step instead of four
+    bool plan_valid = false; int plan_n0 = -1, plan_nl0 = -1, plan_ncap = 0, plan_npcap = 0; long long plan_rowscap = 0; struct GridDescHost { double x0, y0, cell; int nx, ny; } plan_g = {0, 0, 1, 1, 1};
+    int n_fast_steps = 0, n_slow_steps = 0;
     int opt_convex_split = 0;        // experiment: class C as two kernels (sweep, then force law)
     int opt_euler_cell_warp = 1;     // calc_eulerian_data: a warp per cell (0: one thread per cell)
     Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
@@ -125,6 +129,7 @@ struct SzContext {
     DBuf<int> sl_ogid, sl_flag, sl_pos, sl_opos, sl_g, sl_sendcnt, sl_keys, sl_slots, sl_hnv, sl_hvoff; DBuf<uint8_t> sl_cub; DBuf<double> sl_out;
     int nout = 0;                   // entries with per-floe outputs: n0 (single GPU) or n (extended mode)
     DBuf<int> flag, pos, scan_tmp;
+    DBuf<u64> scan_state; u64 scan_ticket_base = 0; unsigned scan_epoch = 0;      // single-pass scan: [0] ticket counter, [1..] tile status words
     // grid
     DBuf<int> cid, cell_cnt, cell_start, s_idx; DBuf<double> s_x, s_y, s_r;
     // pairs
@@ -170,15 +175,25 @@ struct SzContext {
 };
 
 // ------------------------------------------------------------------------------------------------ scan
-// Exclusive prefix sum of int32: out[k] = sum in[0..k), k in [0, n_out).  Reads of in[k] for k >= n_in
-// yield 0, so calling with n_out = n_in + 1 leaves the grand total in out[n_in].
+// Exclusive prefix sum of int32: out[k] = sum in[0..k), k in [0, n_out).  Reads of in[k] for k >= n_in yield 0, so calling with
+// n_out = n_in + 1 leaves the grand total in out[n_in].
+// ONE launch (the step runs about ten scans over lists of 1e5..1e6 entries, where three launches each were a visible part
+// of the step's fixed cost): single-pass scan with decoupled look-back.  Tiles take their number from a ticket counter, so a
+// tile only ever waits for tiles that are already running; a tile publishes its aggregate, looks back over its predecessors'
+// words until it meets an inclusive prefix, and publishes its own.  A status word carries the launch's epoch, so the array
+// needs no reset between launches: [epoch 24 | flag 2 (1 aggregate, 2 inclusive prefix) | pad 6 | value 32].
 #define SCAN_TPB 256
 #define SCAN_ITEMS 8
 #define SCAN_TILE (SCAN_TPB * SCAN_ITEMS)
-__global__ void __launch_bounds__(SCAN_TPB) scan_tile_kernel(const int* __restrict__ in, int n_in, int* __restrict__ out, int n_out, int* __restrict__ tile_sums)
+__global__ void __launch_bounds__(SCAN_TPB) scan_lookback_kernel(const int* __restrict__ in, int n_in, int* __restrict__ out, int n_out,
+                                                                 volatile u64* status, u64* ticket, u64 ticket_base, unsigned epoch)
 {
     __shared__ int warp_sums[SCAN_TPB / 32];
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    __shared__ int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)(atomicAdd(ticket, 1ULL) - ticket_base);
+    __syncthreads();
+    const int tile = s_tile;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS]; int s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) { int idx = base + k; v[k] = (idx < n_in) ? in[idx] : 0; s += v[k]; }
@@ -195,27 +210,45 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_tile_kernel(const int* __restri
         if (lane < SCAN_TPB / 32) warp_sums[lane] = ws;   // inclusive
     }
     __syncthreads();
-    int run = incl - s + (wid > 0 ? warp_sums[wid - 1] : 0);
+    if (threadIdx.x == 0) {
+        const int agg = warp_sums[SCAN_TPB / 32 - 1];
+        const u64 tag = (u64)epoch << 40;
+        int excl = 0;
+        if (tile == 0) status[0] = tag | (2ULL << 38) | (unsigned)agg;
+        else {
+            status[tile] = tag | (1ULL << 38) | (unsigned)agg;
+            for (int p = tile - 1; ; --p) {
+                u64 w;
+                do { w = status[p]; } while ((w >> 40) != epoch || ((w >> 38) & 3ULL) == 0);
+                excl += (int)(unsigned)(w & 0xffffffffULL);
+                if (((w >> 38) & 3ULL) == 2) break;
+            }
+            status[tile] = tag | (2ULL << 38) | (unsigned)(excl + agg);
+        }
+        s_prefix = excl;
+    }
+    __syncthreads();
+    int run = s_prefix + incl - s + (wid > 0 ? warp_sums[wid - 1] : 0);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) { int idx = base + k; if (idx < n_out) out[idx] = run; run += v[k]; }
-    if (threadIdx.x == SCAN_TPB - 1 && tile_sums) tile_sums[blockIdx.x] = run;
 }
-__global__ void scan_add_kernel(int* __restrict__ out, int n_out, const int* __restrict__ tile_off)
+static int exclusive_scan(SzContext* c, const int* in, int n_in, int* out, int n_out)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n_out) out[idx] += tile_off[idx / SCAN_TILE];
-}
-// tmp must hold >= n_out/SCAN_TILE + n_out/SCAN_TILE^2 + 8 ints
-static void exclusive_scan(const int* in, int n_in, int* out, int n_out, int* tmp, cudaStream_t st)
-{
+    if (n_out <= 0) return SZ_OK;
     const int tiles = (n_out + SCAN_TILE - 1) / SCAN_TILE;
-    if (tiles <= 1) { ++g_launches; scan_tile_kernel<<<1, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, nullptr); return; }
-    int* sums = tmp; int* sums_scanned = tmp + tiles + 1;
-    ++g_launches; scan_tile_kernel<<<tiles, SCAN_TPB, 0, st>>>(in, n_in, out, n_out, sums);
-    exclusive_scan(sums, tiles, sums_scanned, tiles, sums_scanned + tiles + 1, st);
-    ++g_launches; scan_add_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(out, n_out, sums_scanned);
+    if ((size_t)tiles + 2 > c->scan_state.cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(c->scan_state.ensure((size_t)tiles + 2));
+        CK(cudaMemset(c->scan_state.p, 0, c->scan_state.cap * 8));
+        c->scan_ticket_base = 0; c->scan_epoch = 0;
+    }
+    if (++c->scan_epoch >= (1u << 24)) { CK(cudaMemsetAsync(c->scan_state.p + 1, 0, (c->scan_state.cap - 1) * 8, c->stream)); c->scan_epoch = 1; }
+    ++g_launches;
+    scan_lookback_kernel<<<tiles, SCAN_TPB, 0, c->stream>>>(in, n_in, out, n_out, c->scan_state.p + 1, c->scan_state.p, c->scan_ticket_base, c->scan_epoch);
+    c->scan_ticket_base += (u64)tiles;
+    return SZ_OK;
 }
-static size_t scan_tmp_ints(size_t n) { size_t t = 0; while (n > SCAN_TILE) { n = (n + SCAN_TILE - 1) / SCAN_TILE; t += 2 * n + 4; } return t + 16; }
+static size_t scan_tmp_ints(size_t n) { (void)n; return 16; }      // (the single-pass scan keeps its state in the context)
 
 // ------------------------------------------------------------------------------------------------ K0 ghosts
 __device__ __forceinline__ double sgn_d(double v) { return (double)((v > 0) - (v < 0)); }
@@ -340,7 +373,8 @@ __global__ void cell_fill_kernel(int n, const int* __restrict__ cid, const int* 
 }
 
 struct BroadArgs {
-    int n, n0, Nb, collision; GridDesc g; double minL2, rmax_max;
+    int n, n0, Nb, collision; GridDesc g; double minL2; const u64* rmax_bits;     // largest rmax of the list, as bbox_kernel left it on the device
+    int np_cap; int* overflow;
     const double* ex; const double* ey; const int* esrc; const int* efn; const uint8_t* ealive; const double* rmax;
     const int* egid; const uint8_t* eowned; const double* erootx; const double* erooty;
     const int* cell_start; const int* s_idx; const double* s_x; const double* s_y; const double* s_r;
@@ -378,6 +412,7 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
     const bool own_i = b.eowned[i] != 0;
     int count = 0;
     const int off = FILL ? b.pair_off[i] : 0;
+    if (FILL && b.pair_off[i + 1] > b.np_cap) { if (lane == 0) *b.overflow = 1; return; }     // more pairs than the speculated capacity: flagged, the step is repeated
     bool staged = false;
     if (FILL && b.stage) {
         count = b.pair_off[i + 1] - off;
@@ -389,7 +424,7 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
         const double ri = b.rmax[b.esrc[i]];
         const int cxi = cell_coord(xi, b.g.x0, b.g.cell, b.g.nx), cyi = cell_coord(yi, b.g.y0, b.g.cell, b.g.ny);
         // a partner has |dx|, |dy| < ri + rmax_j <= ri + max(rmax): that many cells each way (floor differences <= ceil)
-        const int R = (int)((ri + b.rmax_max) / b.g.cell) + 1;
+        const int R = (int)((ri + dec_d(*b.rmax_bits)) / b.g.cell) + 1;
         const int cx0 = cxi - R > 0 ? cxi - R : 0, cx1 = cxi + R < b.g.nx ? cxi + R : b.g.nx - 1;
         for (int cy = (cyi - R > 0 ? cyi - R : 0); cy <= cyi + R && cy < b.g.ny; ++cy) {
             const int t0 = b.cell_start[cy * b.g.nx + cx0], t1 = b.cell_start[cy * b.g.nx + cx1 + 1];
@@ -495,7 +530,7 @@ __device__ bool sat_separated(const double* __restrict__ vx, const double* __res
 // strictly disjoint has an empty Clipper intersection (and cannot fail), so floe_interactions returns zero force and
 // overlap 0 (:43-51,71-74): it is answered here.  Every other pair is bucketed by n1 + n2 so that the pairs a CTA
 // sweeps together have the same number of scanbeams.
-__global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
+__global__ void pair_classify_kernel(int pass, int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
                                      const uint8_t* __restrict__ evalid, const int* __restrict__ env, const uint8_t* __restrict__ eno, const int* __restrict__ esrc,
                                      const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
@@ -507,6 +542,7 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
     for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) sh[t] = 0;
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int np = c->overflow ? 0 : (*np_dev < np_cap ? *np_dev : np_cap);     // a flagged step is going to be repeated: its pair list may be incomplete
     int key = -1, slot = 0; bool cvx = false;
     if (p < np && pass == 1) {
         key = pkey[p];
@@ -565,8 +601,9 @@ __global__ void pair_classify_kernel(int pass, int np, const int* __restrict__ p
 // Exclusive offsets of the buckets in launch order: longest outlines first (the CTAs with the longest sweeps start
 // first, which shortens the tail of the launch).  One thread per (n1, n2) combination; its rank in the order
 // "n1 + n2 descending, n1 descending" is closed-form, a 256-wide shared-memory scan does the rest.
-__global__ void __launch_bounds__(SZ_BIN_N * SZ_BIN_N) bins_scan_kernel(Counters* c, int np, int* __restrict__ bins, int* __restrict__ bin_fill)
+__global__ void __launch_bounds__(SZ_BIN_N * SZ_BIN_N) bins_scan_kernel(Counters* c, int np_cap, int* __restrict__ bins, int* __restrict__ bin_fill)
 {
+    const int np = c->n_pairs < np_cap ? c->n_pairs : np_cap;
     bins += blockIdx.x * SZ_NBINS; bin_fill += blockIdx.x * SZ_NBINS;      // block 0: class C buckets, block 1: class S buckets
     const int B = SZ_BIN_N, t = threadIdx.x, ni = t / B, nj = t % B, sum = ni + nj;
     __shared__ int tot[SZ_BIN_N * SZ_BIN_N], scan[SZ_BIN_N * SZ_BIN_N];
@@ -588,14 +625,16 @@ __global__ void __launch_bounds__(SZ_BIN_N * SZ_BIN_N) bins_scan_kernel(Counters
 }
 
 // ------------------------------------------------------------------------------------------------ K4 assembly
-__global__ void tcount_kernel(int np, const int* __restrict__ pj, const int* __restrict__ nrows, int* __restrict__ tcnt)
+__global__ void tcount_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pj, const int* __restrict__ nrows, int* __restrict__ tcnt)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int np = *np_dev < np_cap ? *np_dev : np_cap;
     if (p < np && nrows[p] > 0) atomicAdd(&tcnt[pj[p]], 1);
 }
-__global__ void tfill_kernel(int np, const int* __restrict__ pj, const int* __restrict__ nrows, const int* __restrict__ toff, int* __restrict__ tpos, int* __restrict__ tlist)
+__global__ void tfill_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pj, const int* __restrict__ nrows, const int* __restrict__ toff, int* __restrict__ tpos, int* __restrict__ tlist)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int np = *np_dev < np_cap ? *np_dev : np_cap;
     if (p < np && nrows[p] > 0) { const int j = pj[p]; tlist[toff[j] + atomicAdd(&tpos[j], 1)] = p; }
 }
 // rows of floe m = own pairs + wall + mirrored (floe_interactions_all.m:136,167,196)
@@ -660,7 +699,7 @@ struct AssembleArgs {
     const int* wnrows; const int* wrow_start; const int* wstatus;
     const int* toff; const int* tlist; const int* row_off; const double* pool;
     const double* boxx; const double* boxy; int boxn;
-    double* rows; double* osum; double* e_ov; uint8_t* has_rows; int* kill_i; int* transfer_i;
+    double* rows; long long rows_cap; double* osum; double* e_ov; uint8_t* has_rows; int* kill_i; int* transfer_i;
     double* o_ov; double* o_stress; double* o_xi; double* o_yi; uint8_t* o_alive;
     Counters* cnt;
 };
@@ -670,6 +709,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= a.n) return;
+    if (a.cnt->overflow) return;                                              // an earlier phase outgrew its capacity: the step is repeated
+    if (a.row_off[m + 1] > a.rows_cap) { a.cnt->overflow = 1; return; }      // more rows than the speculated capacity: flagged, the step is repeated
     const bool owned = a.eowned[m] != 0, orig = a.efn[m] > 0, pairing = a.egid[m] > a.Nb;   // pairing: i >= 1+Nb (:125)
     if (!owned) {
         a.osum[(size_t)m * 3] = a.osum[(size_t)m * 3 + 1] = a.osum[(size_t)m * 3 + 2] = 0; a.e_ov[m] = 0; a.has_rows[m] = 0; a.kill_i[m] = 0; a.transfer_i[m] = 0;
@@ -759,13 +800,15 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
     }
 }
 // ghost sums folded into their parents in creation order (:242-245), then the floe's own column sums (:262-263)
-__global__ void fold_kernel(int nout, int Nb, const int* __restrict__ egid, const int* __restrict__ gx_of, const int* __restrict__ gy_of, const double* __restrict__ osum,
+__global__ void fold_kernel(int nout, int n, int Nb, const int* __restrict__ egid, const int* __restrict__ gx_of, const int* __restrict__ gy_of, const double* __restrict__ osum,
                             const uint8_t* __restrict__ has_rows, double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ tq)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nout) return;
     double f0 = 0, f1 = 0, t = 0;
-    const int gx = gx_of[m], gy = gy_of[m];
+    int gx = gx_of[m], gy = gy_of[m];
+    if (gx >= n) gx = -1;            // an image beyond the (speculated) list length: the step is flagged and repeated
+    if (gy >= n) gy = -1;
     if (gx >= 0) { f0 = f0 + (has_rows[gx] ? osum[(size_t)gx * 3] : 0.0); f1 = f1 + (has_rows[gx] ? osum[(size_t)gx * 3 + 1] : 0.0); t = t + (has_rows[gx] ? osum[(size_t)gx * 3 + 2] : 0.0); }
     if (gy >= 0) { f0 = f0 + (has_rows[gy] ? osum[(size_t)gy * 3] : 0.0); f1 = f1 + (has_rows[gy] ? osum[(size_t)gy * 3 + 1] : 0.0); t = t + (has_rows[gy] ? osum[(size_t)gy * 3 + 2] : 0.0); }
     if (egid[m] > Nb && has_rows[m]) { f0 = osum[(size_t)m * 3] + f0; f1 = osum[(size_t)m * 3 + 1] + f1; t = osum[(size_t)m * 3 + 2] + t; }
@@ -785,10 +828,11 @@ __global__ void kill_final_kernel(int n0, const int* __restrict__ kill_i, const 
     if (i >= n0) return;
     kill[i] = kill_i[i]; transfer[i] = tmax[i] ? tmax[i] : transfer_i[i];
 }
-__global__ void pair_stats_kernel(int np, const int* __restrict__ status, const int* __restrict__ nrows, const int* __restrict__ pi, const uint8_t* __restrict__ eowned,
+__global__ void pair_stats_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ status, const int* __restrict__ nrows, const int* __restrict__ pi, const uint8_t* __restrict__ eowned,
                                   int count_force, Counters* c)
 {
     int f = 0, e = 0, k = 0, u = 0;
+    const int np = c->overflow ? 0 : ((np_dev && *np_dev < np_cap) ? *np_dev : np_cap);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
         if (!eowned[pi ? pi[p] : p]) continue;
         const int s = status[p];
@@ -863,6 +907,7 @@ extern "C" void sz_destroy(SzContext* c)
     for (auto* b : ub) b->release();
     DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy, &c->ho_x, &c->ho_y};
     for (auto* b : lb) b->release();
+    c->scan_state.release();
     c->pkey.release();
     { DBuf<double>* tb[] = {&c->t_mass, &c->t_inertia, &c->t_alpha, &c->t_dXi_p, &c->t_dYi_p, &c->t_dUi_p, &c->t_dVi_p, &c->t_dalpha_p, &c->t_dksi_p, &c->t_FxOA, &c->t_FyOA, &c->t_torqueOA,
                           &c->c0x, &c->c0y, &c->t_stressH, &c->t_stress};
@@ -943,6 +988,7 @@ extern "C" int sz_upload(SzContext* c, const SzParams* prm, const SzFloesSoA* f,
         c->bbody.h = bnd->h; c->bbody.area = bnd->area; c->bbody.Xi = bnd->xi; c->bbody.Yi = bnd->yi; c->bbody.Ui = bnd->u; c->bbody.Vi = bnd->v; c->bbody.ksi = bnd->ksi;
     }
     c->prm = *prm; c->ext_mode = false; c->slab = false; c->have_traj = false;
+    if (c->plan_n0 != f->n) c->plan_valid = false;
     fill_device_params(prm, (bnd && !prm->periodic) ? bnd : nullptr, c->dprm);
     c->n0 = n; c->nverts = f->nverts;
     CK(cudaStreamSynchronize(st));   // the caller may reuse its buffers
@@ -1142,7 +1188,7 @@ struct SlabBuildArgs {
     const int* ogid; const int* fx; const int* fy; const int* fxy; const int* px; const int* py; const int* pxy; const int* gx; const int* gyo; const int* gyx;
     double* x; double* y; double* rmax; double* h; double* area; double* u; double* v; double* ksi; uint8_t* alive; int* voff; double* vx; double* vy;     // body records: [owned | halo slots]
     double* ex; double* ey; double* erootx; double* erooty; int* esrc; int* efn; int* eparent; int* egid; uint8_t* ealive; uint8_t* eowned;
-    int* opos; SlabScratch* s;
+    int* opos; int* child0; int* child1; SlabScratch* s;      // child0/1: the (at most two) images of an entry, in creation order (:242-245)
 };
 // halo records: body record n + slot, outline copied behind the owned outlines, list entry at (rank among received) + (own entries before)
 __global__ void slab_build_halo_kernel(const SlabBuildArgs a)
@@ -1169,7 +1215,7 @@ __global__ void slab_build_halo_kernel(const SlabBuildArgs a)
     const size_t o = (size_t)a.vown + a.hvoff[slot];
     for (int t = 0; t < nv; ++t) { a.vx[o + t] = vsrc[2 * t]; a.vy[o + t] = vsrc[2 * t + 1]; }
     a.ex[pos] = r[2]; a.ey[pos] = r[3]; a.erootx[pos] = r[4]; a.erooty[pos] = r[5]; a.esrc[pos] = src; a.efn[pos] = (int)r[1]; a.eparent[pos] = 0; a.egid[pos] = key;
-    a.ealive[pos] = (uint8_t)r[12]; a.eowned[pos] = 0;
+    a.ealive[pos] = (uint8_t)r[12]; a.eowned[pos] = 0; a.child0[pos] = -1; a.child1[pos] = -1;
 }
 // owned floes and their images: list position = (own entries before) + (received entries with a smaller global position)
 __global__ void slab_build_own_kernel(const SlabBuildArgs a)
@@ -1190,23 +1236,28 @@ __global__ void slab_build_own_kernel(const SlabBuildArgs a)
         const int pos = own_rank + lower_bound_i(a.keys_sorted, nslots, g);
         if (pos >= a.nl_cap) { a.s->overflow = 1; return -1; }
         a.ex[pos] = ex; a.ey[pos] = ey; a.erootx[pos] = X; a.erooty[pos] = Y; a.esrc[pos] = i; a.efn[pos] = fnum; a.eparent[pos] = parent_pos + 1; a.egid[pos] = g;
-        a.ealive[pos] = a.alive[i]; a.eowned[pos] = 1;
+        a.ealive[pos] = a.alive[i]; a.eowned[pos] = 1; a.child0[pos] = -1; a.child1[pos] = -1;
         return pos;
     };
     const int p0 = put(i, G, G, X, Y, -1);
     a.opos[i] = p0;
     if (!a.periodic) return;
     double Xg = X, Yg = Y; int pxg = -1;
+    int pyg = -1, pxyg = -1;
     if (a.fx[i] && a.px[i] < a.cap_img) { Xg = X - 2 * a.Lx * sgn_d(X); pxg = put(a.n + a.px[i], a.gx[a.px[i]], -G, Xg, Y, p0); }
-    if (a.fy[i] && a.py[i] < a.cap_img) { Yg = Y - 2 * a.Ly * sgn_d(Y); put(a.n + cx + a.py[i], a.gyo[a.py[i]], -G, X, Yg, p0); }
-    if (a.fxy[i] && a.pxy[i] < a.cap_img) put(a.n + cx + cyo + a.pxy[i], a.gyx[a.pxy[i]], -G, Xg, Yg, pxg);
+    if (a.fy[i] && a.py[i] < a.cap_img) { Yg = Y - 2 * a.Ly * sgn_d(Y); pyg = put(a.n + cx + a.py[i], a.gyo[a.py[i]], -G, X, Yg, p0); }
+    if (a.fxy[i] && a.pxy[i] < a.cap_img) pxyg = put(a.n + cx + cyo + a.pxy[i], a.gyx[a.pxy[i]], -G, Xg, Yg, pxg);
+    // images of an entry in creation order: the floe's x-image, then its y-image; an x-image's only image is the xy one
+    if (p0 >= 0) { a.child0[p0] = pxg >= 0 ? pxg : pyg; a.child1[p0] = pxg >= 0 ? pyg : -1; }
+    if (pxg >= 0) a.child0[pxg] = pxyg;
 }
 // entries behind the list's end are inert: dead, unowned, nowhere
-__global__ void slab_build_tail_kernel(int nl_cap, const SlabScratch* __restrict__ s, double* ex, double* ey, double* erootx, double* erooty, int* esrc, int* efn, int* eparent, int* egid,
-                                       uint8_t* ealive, uint8_t* eowned)
+__global__ void slab_build_tail_kernel(int nl_cap, const int* __restrict__ n_dev, double* ex, double* ey, double* erootx, double* erooty, int* esrc, int* efn, int* eparent, int* egid,
+                                       uint8_t* ealive, uint8_t* eowned, int* child0, int* child1)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nl_cap || e < s->n_list) return;
+    if (e >= nl_cap || e < *n_dev) return;
+    if (child0) { child0[e] = -1; child1[e] = -1; }
     const double nan = SZ_INF - SZ_INF;
     ex[e] = nan; ey[e] = nan; erootx[e] = nan; erooty[e] = nan; esrc[e] = 0; efn[e] = 0; eparent[e] = 0; egid[e] = 0x7fffffff; ealive[e] = 0; eowned[e] = 0;
 }
@@ -1229,7 +1280,7 @@ __global__ void slab_count_halo_kernel(int n, int rank, int world, int periodic,
         if (k) { atomicAdd(&cnt[2 * p], (unsigned long long)k); atomicAdd(&cnt[2 * p + 1], (unsigned long long)k * nv); }
     }
 }
-__global__ void slab_status_kernel(const SlabScratch* __restrict__ s, int* __restrict__ out) { out[0] = s->overflow; out[1] = s->n_list; out[2] = s->n_outside; }
+__global__ void slab_status_kernel(const SlabScratch* __restrict__ s, int* __restrict__ out) { out[0] = s->overflow; out[1] = s->n_outside; out[2] = s->n_list; out[3] = 0; }
 
 extern "C" int64_t sz_slab_meta_doubles(int32_t cap_img) { return SL_META_HDR + 3 * (int64_t)cap_img; }
 extern "C" int64_t sz_slab_block_doubles(int32_t cap_rec, int32_t cap_vert) { return 2 + (int64_t)cap_rec * SL_REC + 2 * (int64_t)cap_vert; }
@@ -1257,9 +1308,9 @@ static int slab_flags(SzContext* c)
     int* px = c->sl_pos.p; int* py = px + (n + 2); int* pxy = py + (n + 2);
     ++g_launches; slab_scratch_init_kernel<<<1, 1, 0, st>>>(c->sl_scratch);
     if (n > 0) { ++g_launches; slab_flag_kernel<<<std::min(nblk(n, 256), 148 * 16), 256, 0, st>>>(n, c->x.p, c->y.p, c->rmax.p, c->alive.p, c->voff.p, c->vx.p, c->vy.p, P.Lx, P.Ly, P.periodic, fx, fy, fxy, c->sl_scratch, c->sl_xlo, c->sl_xhi); }
-    exclusive_scan(fx, n, px, n + 1, c->scan_tmp.p, st);
-    exclusive_scan(fy, n, py, n + 1, c->scan_tmp.p, st);
-    exclusive_scan(fxy, n, pxy, n + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, fx, n, px, n + 1));
+    CKS(exclusive_scan(c, fy, n, py, n + 1));
+    CKS(exclusive_scan(c, fxy, n, pxy, n + 1));
     CK(cudaGetLastError());
     return SZ_OK;
 }
@@ -1313,7 +1364,7 @@ extern "C" int sz_slab_configure(SzContext* c, int32_t cap_img, int32_t cap_rec,
     CK(c->alive.ensure(nsrc + 1, true)); CK(c->voff.ensure(nsrc + 2, true)); CK(c->vx.ensure(V + 1, true)); CK(c->vy.ensure(V + 1, true));
     const size_t nl = (size_t)n + 3 * (size_t)cap_img + (size_t)W * cap_rec;
     CK(c->ex.ensure(nl + 1)); CK(c->ey.ensure(nl + 1)); CK(c->erootx.ensure(nl + 1)); CK(c->erooty.ensure(nl + 1)); CK(c->esrc.ensure(nl + 1)); CK(c->efn.ensure(nl + 1));
-    CK(c->eparent.ensure(nl + 1)); CK(c->egid.ensure(nl + 1)); CK(c->ealive.ensure(nl + 1)); CK(c->eowned.ensure(nl + 1));
+    CK(c->eparent.ensure(nl + 1)); CK(c->egid.ensure(nl + 1)); CK(c->ealive.ensure(nl + 1)); CK(c->eowned.ensure(nl + 1)); CK(c->gx_of.ensure(nl + 1)); CK(c->gy_of.ensure(nl + 1));
     CK(c->sl_g.ensure(3 * (size_t)cap_img + 3)); CK(c->sl_sendcnt.ensure(2 * (size_t)W + 2));
     const size_t ns = (size_t)W * cap_rec;
     CK(c->sl_keys.ensure(2 * ns + 2)); CK(c->sl_slots.ensure(2 * ns + 2)); CK(c->sl_hnv.ensure(ns + 2)); CK(c->sl_hvoff.ensure(ns + 2));
@@ -1374,7 +1425,7 @@ extern "C" int sz_slab_build(SzContext* c, const double* recv_dev, int32_t* stat
     ++g_launches; slab_keys_kernel<<<nblk(ns, 256), 256, 0, st>>>(W, c->sl_rank, c->sl_cap_rec, recv_dev, block, keys, slots, c->sl_hnv.p);
     size_t bytes = c->sl_cub.cap;
     ++g_launches; CK(cub::DeviceRadixSort::SortPairs(c->sl_cub.p, bytes, keys, keys_s, slots, slots_s, ns, 0, 32, st));
-    exclusive_scan(c->sl_hnv.p, ns, c->sl_hvoff.p, ns + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->sl_hnv.p, ns, c->sl_hvoff.p, ns + 1));
     SlabBuildArgs a; memset(&a, 0, sizeof(a));
     a.n = n; a.rank = c->sl_rank; a.world = W; a.cap_img = c->sl_cap_img; a.cap_rec = c->sl_cap_rec; a.cap_vert = c->sl_cap_vert; a.nl_cap = c->sl_nl_cap; a.periodic = P.periodic; a.Lx = P.Lx; a.Ly = P.Ly; a.vown = c->nverts;
     a.recv = recv_dev; a.block = block; a.keys_sorted = keys_s; a.slots_sorted = slots_s; a.hvoff = c->sl_hvoff.p;
@@ -1382,10 +1433,10 @@ extern "C" int sz_slab_build(SzContext* c, const double* recv_dev, int32_t* stat
     a.gx = c->sl_g.p; a.gyo = a.gx + (c->sl_cap_img + 1); a.gyx = a.gyo + (c->sl_cap_img + 1);
     a.x = c->x.p; a.y = c->y.p; a.rmax = c->rmax.p; a.h = c->h.p; a.area = c->area.p; a.u = c->u.p; a.v = c->v.p; a.ksi = c->ksi.p; a.alive = c->alive.p; a.voff = c->voff.p; a.vx = c->vx.p; a.vy = c->vy.p;
     a.ex = c->ex.p; a.ey = c->ey.p; a.erootx = c->erootx.p; a.erooty = c->erooty.p; a.esrc = c->esrc.p; a.efn = c->efn.p; a.eparent = c->eparent.p; a.egid = c->egid.p; a.ealive = c->ealive.p; a.eowned = c->eowned.p;
-    a.opos = c->sl_opos.p; a.s = c->sl_scratch;
+    a.opos = c->sl_opos.p; a.child0 = c->gx_of.p; a.child1 = c->gy_of.p; a.s = c->sl_scratch;
     ++g_launches; slab_build_own_kernel<<<std::max(1, nblk(n, 128)), 128, 0, st>>>(a);
     ++g_launches; slab_build_halo_kernel<<<nblk(ns, 128), 128, 0, st>>>(a);
-    ++g_launches; slab_build_tail_kernel<<<nblk(c->sl_nl_cap, 256), 256, 0, st>>>(c->sl_nl_cap, c->sl_scratch, c->ex.p, c->ey.p, c->erootx.p, c->erooty.p, c->esrc.p, c->efn.p, c->eparent.p, c->egid.p, c->ealive.p, c->eowned.p);
+    ++g_launches; slab_build_tail_kernel<<<nblk(c->sl_nl_cap, 256), 256, 0, st>>>(c->sl_nl_cap, &c->sl_scratch->n_list, c->ex.p, c->ey.p, c->erootx.p, c->erooty.p, c->esrc.p, c->efn.p, c->eparent.p, c->egid.p, c->ealive.p, c->eowned.p, c->gx_of.p, c->gy_of.p);
     if (status_dev) { ++g_launches; slab_status_kernel<<<1, 1, 0, st>>>(c->sl_scratch, status_dev); }
     CK(cudaGetLastError());
     c->sl_built = true;
@@ -1412,7 +1463,7 @@ static int read_counters(SzContext* c)
 #define D_CNT(field) ((int*)((char*)c->d_cnt + offsetof(Counters, field)))
 
 // runs the narrow phase over the pairs (wall = 0) or over floe-vs-wall (wall = 1), escalating S -> M -> L
-static int run_narrow(SzContext* c, int wall, int n_work)
+static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
 {
     cudaStream_t st = c->stream;
     NarrowArgs a; memset(&a, 0, sizeof(a));
@@ -1439,10 +1490,10 @@ static int run_narrow(SzContext* c, int wall, int n_work)
         static const int key_mode = getenv("SZ_CVX_KEY") ? atoi(getenv("SZ_CVX_KEY")) : 1;   // 0: direction sectors for class C too (experiments)
         CK(c->bins.ensure(2 * SZ_NBINS)); CK(c->bin_fill.ensure(2 * SZ_NBINS));
         CK(cudaMemsetAsync(c->bins.p, 0, 2 * SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, 2 * SZ_NBINS * sizeof(int), st));
-        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
+        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
                                                             c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt, key_mode);
         bins_scan_kernel<<<2, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
-        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
+        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
                                                             c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt, key_mode);
         g_launches += 3;
         // class C: strictly convex pairs through the four-edge sweep; what it declines is appended to class S's list.
@@ -1469,6 +1520,9 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     if (!wall) { CK(cudaEventRecord(c->evk[3], st)); c->evk_used[1] = true; }
     a.list = nullptr; a.list_count = nullptr;
     CK(cudaGetLastError());
+    // speculative step: the lists of the larger size classes were empty last step; whether they still are is checked with the
+    // step's single counter read at the end (a non-empty list repeats the step on the synchronous path)
+    if (fast) return SZ_OK;
     CKS(read_counters(c));
     if (!wall) { c->class_pairs[0] = c->h_cnt->listC0; c->class_pairs[1] = c->h_cnt->listS; }
     const int nT = wall ? c->h_cnt->wlistT : c->h_cnt->listT;
@@ -1519,6 +1573,27 @@ static int run_narrow(SzContext* c, int wall, int n_work)
     return SZ_OK;
 }
 
+// the cell grid of the broad phase from the list's bounding box and largest rmax: about four floes per cell, never more than 8
+// cells per reach (2 max(rmax)); every floe widens its own search by its radius, and any grid is CORRECT for any list (entries
+// outside the box are clamped into the border cells, which only moves them towards their partners), so a step may use the grid
+// of the step before
+static GridDesc make_grid(const Counters* h, int n)
+{
+    GridDesc g; g.x0 = g.y0 = 0; g.cell = 1; g.nx = g.ny = 1;
+    const double rm = dec_d(h->rmax_bits);
+    const double xmn = dec_d(h->bbox[0]), xmx = dec_d(h->bbox[1]), ymn = dec_d(h->bbox[2]), ymx = dec_d(h->bbox[3]);
+    if (xmn <= xmx && std::isfinite(xmn) && std::isfinite(xmx) && std::isfinite(ymn) && std::isfinite(ymx)) {
+        g.x0 = xmn; g.y0 = ymn;
+        double cell = 2 * rm; if (!(cell > 0) || !std::isfinite(cell)) cell = 1;
+        const double dens = std::sqrt(4.0 * (xmx - xmn) * (ymx - ymn) / std::max(1, n));
+        if (dens > 0 && std::isfinite(dens)) cell = std::min(cell, std::max(cell / 8, dens));
+        while ((xmx - xmn) / cell * ((ymx - ymn) / cell) > 1.6e7) cell *= 2;      // keep the grid below ~16M cells
+        g.cell = cell;
+        g.nx = (int)((xmx - xmn) / cell) + 1; g.ny = (int)((ymx - ymn) / cell) + 1;
+    }
+    return g;
+}
+
 extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
 {
     if (!c) { sz_set_error("sz_step_resident: NULL context"); return SZ_ERR_ARG; }
@@ -1552,12 +1627,12 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         CK(c->scan_tmp.ensure(scan_tmp_ints(2 * (size_t)n0 + 2)));
         // x pass over the originals
         ++g_launches; ghost_flag_kernel<<<nblk(n0, 128), 128, 0, st>>>(0, n0, nullptr, c->ex.p, c->esrc.p, c->ealive.p, c->voff.p, c->vx.p, P.Lx, c->flag.p);
-        exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+        CKS(exclusive_scan(c, c->flag.p, n0, c->pos.p, n0 + 1));
         ++g_launches; ghost_emit_kernel<<<nblk(n0, 256), 256, 0, st>>>(0, n0, nullptr, n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
                                                          c->gx_of.p, c->gy_of.p, P.Lx, D_CNT(n1));
         // y pass over originals + x-ghosts (their number is only known on the device: bound 2*n0)
         ++g_launches; ghost_flag_kernel<<<nblk(2 * (i64)n0, 128), 128, 0, st>>>(1, 2 * n0, D_CNT(n1), c->ey.p, c->esrc.p, c->ealive.p, c->voff.p, c->vy.p, P.Ly, c->flag.p);
-        exclusive_scan(c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1, c->scan_tmp.p, st);
+        CKS(exclusive_scan(c, c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1));
         ++g_launches; ghost_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(n1), n0, c->flag.p, c->pos.p, c->ex.p, c->ey.p, c->esrc.p, c->efn.p, c->eparent.p, c->ealive.p,
                                                                   c->gx_of.p, c->gy_of.p, P.Ly, D_CNT(n));
     }
@@ -1568,36 +1643,36 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
             CK(cudaMemcpyAsync(c->ex.p, c->x.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->ey.p, c->y.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(c->ealive.p, c->alive.p, (size_t)n0, cudaMemcpyDeviceToDevice, st));
         }
-        CK(c->gx_of.ensure(nl0 + 1)); CK(c->gy_of.ensure(nl0 + 1));
-        ++g_launches; child_init_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->gx_of.p, c->gy_of.p);
-        ++g_launches; child_mark_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->eparent.p, c->gx_of.p, c->gy_of.p);
-        ++g_launches; child_final_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->gx_of.p, c->gy_of.p);
+        if (!slab) {      // (sz_slab_build wrote the images of every entry itself)
+            CK(c->gx_of.ensure(nl0 + 1)); CK(c->gy_of.ensure(nl0 + 1));
+            ++g_launches; child_init_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->gx_of.p, c->gy_of.p);
+            ++g_launches; child_mark_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->eparent.p, c->gx_of.p, c->gy_of.p);
+            ++g_launches; child_final_kernel<<<nblk(nl0, 256), 256, 0, st>>>(nl0, c->gx_of.p, c->gy_of.p);
+        }
     } else if (ncap > 0) {
         ++g_launches; finish_extended_kernel<<<nblk(ncap, 256), 256, 0, st>>>(ncap, D_CNT(n), c->x.p, c->y.p, c->esrc.p, c->egid.p, c->eowned.p, c->erootx.p, c->erooty.p);
     }
     if (ncap > 0) { ++g_launches; bbox_kernel<<<std::min(nblk(ncap, 256), 148 * 8), 256, 0, st>>>(ncap, D_CNT(n), c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->d_cnt); }
     CK(cudaGetLastError());
-    CKS(read_counters(c));
-    const int n = c->h_cnt->n; c->n = n; c->n1 = c->h_cnt->n1;
+    // Speculative step: list length, grid, pair and row capacities come from the previous step (with slack), every kernel
+    // takes the true counts from device memory, and the host reads the counters ONCE, at the end; a step whose counts
+    // outgrew a capacity (or that needs a larger size class) raises a flag there and is repeated on the synchronous path.
+    const bool fast = c->opt_speculate && c->plan_valid && c->plan_n0 == n0 && c->plan_nl0 == nl0 && !P.want_clip_polys && c->plan_ncap <= ncap;
+    int n;
+    if (fast) {
+        n = slab ? nl0 : c->plan_ncap;
+        if (!ext && n > 0) { ++g_launches; slab_build_tail_kernel<<<nblk(n, 256), 256, 0, st>>>(n, D_CNT(n), c->ex.p, c->ey.p, c->erootx.p, c->erooty.p, c->esrc.p, c->efn.p, c->eparent.p, c->egid.p, c->ealive.p, c->eowned.p, nullptr, nullptr); }
+    } else {
+        CKS(read_counters(c));
+        n = c->h_cnt->n; c->n1 = c->h_cnt->n1;
+    }
+    c->n = n;
 
     CK(cudaEventRecord(c->evp[0], st));
     // ---- K1: cell grid + candidate pairs
-    GridDesc g; g.x0 = g.y0 = 0; g.cell = 1; g.nx = g.ny = 1;
-    {
-        const double rm = dec_d(c->h_cnt->rmax_bits);
-        const double xmn = dec_d(c->h_cnt->bbox[0]), xmx = dec_d(c->h_cnt->bbox[1]), ymn = dec_d(c->h_cnt->bbox[2]), ymx = dec_d(c->h_cnt->bbox[3]);
-        if (xmn <= xmx && std::isfinite(xmn) && std::isfinite(xmx) && std::isfinite(ymn) && std::isfinite(ymx)) {
-            g.x0 = xmn; g.y0 = ymn;
-            // about four floes per cell, but never more than 8 cells per reach (2 max(rmax)); the search widens per floe
-            double cell = 2 * rm; if (!(cell > 0) || !std::isfinite(cell)) cell = 1;
-            const double dens = std::sqrt(4.0 * (xmx - xmn) * (ymx - ymn) / std::max(1, n));
-            if (dens > 0 && std::isfinite(dens)) cell = std::min(cell, std::max(cell / 8, dens));
-            // keep the grid below ~16M cells
-            while ((xmx - xmn) / cell * ((ymx - ymn) / cell) > 1.6e7) cell *= 2;
-            g.cell = cell;
-            g.nx = (int)((xmx - xmn) / cell) + 1; g.ny = (int)((ymx - ymn) / cell) + 1;
-        }
-    }
+    GridDesc g;
+    if (fast) { g.x0 = c->plan_g.x0; g.y0 = c->plan_g.y0; g.cell = c->plan_g.cell; g.nx = c->plan_g.nx; g.ny = c->plan_g.ny; }
+    else g = make_grid(c->h_cnt, n);
     const int ncell = g.nx * g.ny;
     CK(c->cid.ensure(n + 1)); CK(c->cell_cnt.ensure(ncell + 2)); CK(c->cell_start.ensure(ncell + 2));
     CK(c->s_idx.ensure(n + 1)); CK(c->s_x.ensure(n + 1)); CK(c->s_y.ensure(n + 1)); CK(c->s_r.ensure(n + 1));
@@ -1608,10 +1683,10 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     BroadArgs b; memset(&b, 0, sizeof(b));
     if (n > 0) {
         ++g_launches; cell_count_kernel<<<nblk(n, 256), 256, 0, st>>>(n, g, c->ex.p, c->ey.p, c->ealive.p, c->cid.p, c->cell_cnt.p);
-        exclusive_scan(c->cell_cnt.p, ncell, c->cell_start.p, ncell + 1, c->scan_tmp.p, st);
+        CKS(exclusive_scan(c, c->cell_cnt.p, ncell, c->cell_start.p, ncell + 1));
         CK(cudaMemsetAsync(c->cell_cnt.p, 0, (size_t)(ncell + 1) * 4, st));
         ++g_launches; cell_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->cid.p, c->cell_start.p, c->cell_cnt.p, c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->s_idx.p, c->s_x.p, c->s_y.p, c->s_r.p);
-        b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly); b.rmax_max = dec_d(c->h_cnt->rmax_bits);
+        b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly); b.rmax_bits = (const u64*)((const char*)c->d_cnt + offsetof(Counters, rmax_bits)); b.overflow = D_CNT(overflow);
         b.ex = c->ex.p; b.ey = c->ey.p; b.esrc = c->esrc.p; b.efn = c->efn.p; b.ealive = c->ealive.p; b.rmax = c->rmax.p;
         b.egid = c->egid.p; b.eowned = c->eowned.p; b.erootx = c->erootx.p; b.erooty = c->erooty.p;
         b.cell_start = c->cell_start.p; b.s_idx = c->s_idx.p; b.s_x = c->s_x.p; b.s_y = c->s_y.p; b.s_r = c->s_r.p;
@@ -1620,15 +1695,17 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         if (stage_cap > 0) { CK(c->stage.ensure((size_t)n * stage_cap + 1)); b.stage = c->stage.p; b.stage_cap = stage_cap > 32 ? 32 : stage_cap; }
         { ++g_launches; broad_kernel<false><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
     }
-    exclusive_scan(c->pcnt.p, n, c->pair_off.p, n + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->pcnt.p, n, c->pair_off.p, n + 1));
     CK(cudaMemcpyAsync(D_CNT(n_pairs), c->pair_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
     // per-entry preparation of the narrow phase (bounding boxes, convexity): independent of the pair list, so it is queued
     // before the host waits for the pair count
     CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1));
     if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p); }
     CK(cudaGetLastError());
-    CKS(read_counters(c));
-    const int np = c->h_cnt->n_pairs; c->n_pairs = np;
+    int np;
+    if (fast) np = c->plan_npcap;
+    else { CKS(read_counters(c)); np = c->h_cnt->n_pairs; }
+    c->n_pairs = np; b.np_cap = np;
     CK(c->pi.ensure(np + 1)); CK(c->pj.ensure(np + 1)); CK(c->pstatus.ensure(np + 1)); CK(c->pnrows.ensure(np + 1)); CK(c->prow_start.ensure(np + 1)); CK(c->povl.ensure(np + 1));
     CK(c->listT.ensure(np + 1)); CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
@@ -1644,19 +1721,22 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         CK(c->path_vstart.ensure((size_t)np + 256)); CK(c->path_len.ensure(c->path_vstart.cap)); CK(c->pvx.ensure(8 * (size_t)np + 1024)); CK(c->pvy.ensure(c->pvx.cap));
     }
     for (int attempt = 0; attempt < 3; ++attempt) {
-        Counters z = *c->h_cnt;
-        z.row_used = z.path_used = z.vert_used = z.n_bbox_reject = z.listC = z.listS = z.listC0 = z.listS0 = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
-
-        *c->h_cnt = z;
-        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
+        if (!fast) {
+            // (the host copy of the counters is current here: the pair count was just read)
+            Counters z = *c->h_cnt;
+            z.row_used = z.path_used = z.vert_used = z.n_bbox_reject = z.listC = z.listS = z.listC0 = z.listS0 = z.listT = z.listM = z.listL = z.wlistT = z.wlistM = z.wlistL = 0;
+            *c->h_cnt = z;
+            CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
+        }
         CK(cudaMemsetAsync(c->pstatus.p, 0, (size_t)(np + 1) * 4, st)); CK(cudaMemsetAsync(c->pnrows.p, 0, (size_t)(np + 1) * 4, st));
         for (int k = 0; k < 5; ++k) { c->evk_used[k] = false; c->class_pairs[k] = 0; }
-        if (np > 0) CKS(run_narrow(c, 0, np));
+        if (np > 0) CKS(run_narrow(c, 0, np, fast));
         if (wall) {
             // floes below Nb take no part in the wall call (:125 loops i = 1+Nb:N)
             CK(cudaMemsetAsync(c->wstatus.p, 0, (size_t)(n + 1) * 4, st)); CK(cudaMemsetAsync(c->wnrows.p, 0, (size_t)(n + 1) * 4, st));
-            if (n > 0) CKS(run_narrow(c, 1, n));
+            if (n > 0) CKS(run_narrow(c, 1, n, fast));
         }
+        if (fast) break;          // capacities are checked with the counters at the end of the step
         // run_narrow ends with a counter read-back and nothing was launched since: the host copy is current
         bool again = false;
         if ((size_t)c->h_cnt->row_used * 5 > c->row_pool.cap) { CK(c->row_pool.ensure((size_t)c->h_cnt->row_used * 5 + 1024)); again = true; }
@@ -1672,17 +1752,17 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     // ---- K4: mirror, rows, sums
     CK(c->tcnt.ensure(n + 2)); CK(c->toff.ensure(n + 2)); CK(c->tlist.ensure(np + 1)); CK(c->rcnt.ensure(n + 2)); CK(c->row_off.ensure(n + 2));
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
-    if (np > 0) { ++g_launches; tcount_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->tcnt.p); }
-    exclusive_scan(c->tcnt.p, n, c->toff.p, n + 1, c->scan_tmp.p, st);
+    if (np > 0) { ++g_launches; tcount_kernel<<<nblk(np, 256), 256, 0, st>>>(np, D_CNT(n_pairs), c->pj.p, c->pnrows.p, c->tcnt.p); }
+    CKS(exclusive_scan(c, c->tcnt.p, n, c->toff.p, n + 1));
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
-    if (np > 0) { ++g_launches; tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p); }
+    if (np > 0) { ++g_launches; tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, D_CNT(n_pairs), c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p); }
     if (n > 0) { ++g_launches; rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->eowned.p, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p); }
-    exclusive_scan(c->rcnt.p, n, c->row_off.p, n + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->rcnt.p, n, c->row_off.p, n + 1));
     CK(cudaMemcpyAsync(D_CNT(total_rows), c->row_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
     // every row of the pool appears at most twice (its floe's own row and the partner's mirrored row): the row count is
     // bounded without waiting for it; the exact value comes back with the step's last counter read
-    const i64 rows_bound = 2 * (i64)c->h_cnt->row_used;
+    const i64 rows_bound = fast ? (i64)c->plan_rowscap : 2 * (i64)c->h_cnt->row_used;
     CK(c->rows.ensure((size_t)rows_bound * 7 + 7)); CK(c->osum.ensure((size_t)n * 3 + 3)); CK(c->e_ov.ensure(n + 1)); CK(c->has_rows.ensure(n + 1));
     const int nout = ext ? n : n0; c->nout = nout;
     CK(c->kill_i.ensure(n + 1)); CK(c->transfer_i.ensure(n + 1)); CK(c->tmax.ensure(nout + 1));
@@ -1697,7 +1777,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         a.wnrows = c->wnrows.p; a.wrow_start = c->wrow_start.p; a.wstatus = c->wstatus.p;
         a.toff = c->toff.p; a.tlist = c->tlist.p; a.row_off = c->row_off.p; a.pool = c->row_pool.p;
         a.boxx = c->boxx.p; a.boxy = c->boxy.p; a.boxn = c->boxn;
-        a.rows = c->rows.p; a.osum = c->osum.p; a.e_ov = c->e_ov.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
+        a.rows = c->rows.p; a.rows_cap = rows_bound; a.osum = c->osum.p; a.e_ov = c->e_ov.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
         a.o_ov = c->o_ov.p; a.o_stress = c->o_stress.p; a.o_xi = c->o_xi.p; a.o_yi = c->o_yi.p; a.o_alive = c->o_alive.p; a.cnt = c->d_cnt;
         ++g_launches; assemble_kernel<<<nblk(n, 128), 128, 0, st>>>(a);
         if (!ext) {
@@ -1708,9 +1788,9 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
             // extended mode: raw per-entry kill/transfer (global ids); the cross-rank fix-up of :175-179 is the caller's
             CK(cudaMemcpyAsync(c->o_kill.p, c->kill_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->o_transfer.p, c->transfer_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st));
         }
-        if (nout > 0) { ++g_launches; fold_kernel<<<nblk(nout, 256), 256, 0, st>>>(nout, Nb, c->egid.p, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p); }
-        if (np > 0) { ++g_launches; pair_stats_kernel<<<std::min(nblk(np, 256), 148 * 8), 256, 0, st>>>(np, c->pstatus.p, c->pnrows.p, c->pi.p, c->eowned.p, 1, c->d_cnt); }
-        if (wall) { ++g_launches; pair_stats_kernel<<<std::min(nblk(n, 256), 148 * 8), 256, 0, st>>>(n, c->wstatus.p, c->wnrows.p, nullptr, c->eowned.p, 0, c->d_cnt); }
+        if (nout > 0) { ++g_launches; fold_kernel<<<nblk(nout, 256), 256, 0, st>>>(nout, n, Nb, c->egid.p, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p); }
+        if (np > 0) { ++g_launches; pair_stats_kernel<<<std::min(nblk(np, 256), 148 * 8), 256, 0, st>>>(np, D_CNT(n_pairs), c->pstatus.p, c->pnrows.p, c->pi.p, c->eowned.p, 1, c->d_cnt); }
+        if (wall) { ++g_launches; pair_stats_kernel<<<std::min(nblk(n, 256), 148 * 8), 256, 0, st>>>(n, nullptr, c->wstatus.p, c->wnrows.p, nullptr, c->eowned.p, 0, c->d_cnt); }
     }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
@@ -1719,10 +1799,32 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     CK(cudaEventElapsedTime(&c->phase_ms[0], c->ev0, c->evp[0])); CK(cudaEventElapsedTime(&c->phase_ms[1], c->evp[0], c->evp[1]));
     CK(cudaEventElapsedTime(&c->phase_ms[2], c->evp[1], c->evp[2])); CK(cudaEventElapsedTime(&c->phase_ms[3], c->evp[2], c->ev1)); c->phase_ms[4] = ms;
 
+    {
+        const Counters& H = *c->h_cnt;
+        const bool big_lists = H.listT || H.listM || H.listL || H.wlistT || H.wlistM || H.wlistL;
+        if (fast) {
+            const bool bad = H.overflow || H.n > n || H.n_pairs > np || (size_t)H.row_used * 5 > c->row_pool.cap || (i64)H.total_rows > rows_bound || big_lists;
+            if (bad) { c->plan_valid = false; ++c->n_slow_steps; return sz_step_resident(c, out); }      // nothing was consumed: the same step again, with measured sizes
+            ++c->n_fast_steps;
+            c->class_pairs[0] = H.listC0; c->class_pairs[1] = H.listS;
+            if (!slab) c->n = H.n;
+            c->n1 = H.n1; c->n_pairs = H.n_pairs;
+        }
+        // what the next step may assume
+        const int n_act = slab ? nl0 : H.n;
+        c->plan_n0 = n0; c->plan_nl0 = nl0;
+        c->plan_ncap = slab ? nl0 : std::min(ncap, n_act + std::max(4096, n_act / 32));
+        const GridDesc pg = make_grid(c->h_cnt, std::max(1, slab ? H.n : n_act));
+        c->plan_g.x0 = pg.x0; c->plan_g.y0 = pg.y0; c->plan_g.cell = pg.cell; c->plan_g.nx = pg.nx; c->plan_g.ny = pg.ny;
+        c->plan_npcap = H.n_pairs + H.n_pairs / 16 + 8192;
+        c->plan_rowscap = (i64)H.total_rows + H.total_rows / 8 + 8192;
+        c->plan_valid = !big_lists && H.n_fail == 0 && H.n_cap_fail == 0;
+    }
+    const int n_list = c->n, np_act = c->n_pairs;
     const i64 nrows = c->h_cnt->total_rows; c->n_rows = nrows;
     if (nrows > rows_bound) { sz_set_error("sz_step_resident: %lld contact rows exceed the bound %lld", (long long)nrows, (long long)rows_bound); return SZ_ERR_CAPACITY; }
     SzSummary& s = c->summary; memset(&s, 0, sizeof(s));
-    s.n0 = n0; s.n = n; s.n_pairs = np; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows; s.n_pairs_owned = c->h_cnt->n_pairs_owned;
+    s.n0 = n0; s.n = n_list; s.n_pairs = np_act; s.n_pairs_force = c->h_cnt->n_pairs_force; s.n_rows = nrows; s.n_pairs_owned = c->h_cnt->n_pairs_owned;
     s.n_clip_paths = P.want_clip_polys ? c->h_cnt->path_used : 0; s.n_clip_verts = P.want_clip_polys ? c->h_cnt->vert_used : 0;
     s.collision_count = (double)c->h_cnt->n_fin_rows / 2 + (double)c->h_cnt->n_inf_rows;   // calc_collisionNum.m:6
     s.n_clipper_fail = c->h_cnt->n_fail; s.n_capacity_fail = c->h_cnt->n_cap_fail; s.ms_device = ms; s.n_kill_events = c->h_cnt->n_kill_events;
@@ -2247,8 +2349,17 @@ extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
     if (!c || !name) { sz_set_error("sz_set_option: NULL argument"); return SZ_ERR_ARG; }
     if (strcmp(name, "convex_fast") == 0) { c->opt_convex_fast = value != 0; return SZ_OK; }
     if (strcmp(name, "convex_split") == 0) { c->opt_convex_split = value != 0; return SZ_OK; }
+    if (strcmp(name, "speculate") == 0) { c->opt_speculate = value != 0; c->plan_valid = false; return SZ_OK; }
     if (strcmp(name, "euler_cell_warp") == 0) { c->opt_euler_cell_warp = value != 0; return SZ_OK; }
     sz_set_error("sz_set_option: unknown option '%s'", name);
+    return SZ_ERR_ARG;
+}
+extern "C" int sz_get_stat(SzContext* c, const char* name, int64_t* value)
+{
+    if (!c || !name || !value) { sz_set_error("sz_get_stat: NULL argument"); return SZ_ERR_ARG; }
+    if (strcmp(name, "speculated_steps") == 0) { *value = c->n_fast_steps; return SZ_OK; }
+    if (strcmp(name, "repeated_steps") == 0) { *value = c->n_slow_steps; return SZ_OK; }
+    sz_set_error("sz_get_stat: unknown statistic '%s'", name);
     return SZ_ERR_ARG;
 }
 // ------------------------------------------------------------------------------------------------ fracture deformation
@@ -2389,10 +2500,10 @@ extern "C" int sz_corner_mask(SzContext* c, int32_t count, const int32_t* floe_i
     const double Lx = c->prm.Lx, Ly = c->prm.Ly;
     ++g_launches; corner_ext_init_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->x.p, c->y.p, c->alive.p, c->cr_ex.p, c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p);
     ++g_launches; ghost_flag_kernel<<<nblk(n0, 128), 128, 0, st>>>(0, n0, nullptr, c->cr_ex.p, c->cr_esrc.p, c->cr_ealive.p, c->voff.p, c->vx.p, Lx, c->flag.p);
-    exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->flag.p, n0, c->pos.p, n0 + 1));
     ++g_launches; corner_ext_emit_kernel<<<nblk(n0, 256), 256, 0, st>>>(0, n0, nullptr, c->flag.p, c->pos.p, c->cr_ex.p, c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p, Lx, D_CNT(cr_n1));
     ++g_launches; ghost_flag_kernel<<<nblk(2 * (i64)n0, 128), 128, 0, st>>>(1, 2 * n0, D_CNT(cr_n1), c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p, c->voff.p, c->vy.p, Ly, c->flag.p);
-    exclusive_scan(c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->flag.p, 2 * n0, c->pos.p, 2 * n0 + 1));
     ++g_launches; corner_ext_emit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(1, 2 * n0, D_CNT(cr_n1), c->flag.p, c->pos.p, c->cr_ex.p, c->cr_ey.p, c->cr_esrc.p, c->cr_ealive.p, Ly, D_CNT(cr_n));
     // ---- one slot of da per polyshape vertex of every selected floe
     szcorn::CornerArgs a; memset(&a, 0, sizeof(a));
@@ -2403,7 +2514,7 @@ extern "C" int sz_corner_mask(SzContext* c, int32_t count, const int32_t* floe_i
     a.boxx = c->boxx.p; a.boxy = c->boxy.p; a.nbox = c->have_bnd ? c->boxn : 0;
     CK(c->cr_nv.ensure(count + 1)); CK(c->cr_off.ensure(count + 2));
     ++g_launches; corner_count_kernel<<<nblk(count, 256), 256, 0, st>>>(a, c->cr_nv.p);
-    exclusive_scan(c->cr_nv.p, count, c->cr_off.p, count + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->cr_nv.p, count, c->cr_off.p, count + 1));
     CK(cudaGetLastError());
     int total = 0;
     CK(cudaMemcpyAsync(&total, c->cr_off.p + count, 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st));
@@ -2592,11 +2703,11 @@ extern "C" int sz_eulerian_data(SzContext* c, int32_t Nx, int32_t Ny, double xmi
     CK(c->flag.ensure(2 * (size_t)n0 + 2)); CK(c->pos.ensure(2 * (size_t)n0 + 2)); CK(c->scan_tmp.ensure(scan_tmp_ints(std::max<size_t>(lcap + 2, (size_t)cells + 2))));
     CK(cudaMemsetAsync(D_CNT(eu_n1), 0, 7 * sizeof(int), st));             // eu_n1 .. eu_cap
     ++g_launches; euler_alive_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->alive.p, c->flag.p);
-    exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->flag.p, n0, c->pos.p, n0 + 1));
     ++g_launches; euler_list_init_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, c->flag.p, c->pos.p, c->x.p, c->y.p, c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, D_CNT(eu_n1));
     if (periodic) {
         ++g_launches; euler_xflag_kernel<<<nblk(n0, 128), 128, 0, st>>>(n0, D_CNT(eu_n1), c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, c->voff.p, c->vx.p, c->vy.p, xmax, ymax, c->flag.p, D_CNT(eu_yflag));
-        exclusive_scan(c->flag.p, n0, c->pos.p, n0 + 1, c->scan_tmp.p, st);
+        CKS(exclusive_scan(c, c->flag.p, n0, c->pos.p, n0 + 1));
         ++g_launches; euler_xemit_kernel<<<nblk(n0, 256), 256, 0, st>>>(n0, D_CNT(eu_n1), c->flag.p, c->pos.p, c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, xmax, D_CNT(eu_n2));
         ++g_launches; euler_yemit_kernel<<<nblk(2 * (i64)n0, 256), 256, 0, st>>>(2 * n0, D_CNT(eu_n2), D_CNT(eu_yflag), c->eu_lsrc.p, c->eu_lx.p, c->eu_ly.p, ymax, D_CNT(eu_n));
     } else {
@@ -2616,7 +2727,7 @@ extern "C" int sz_eulerian_data(SzContext* c, int32_t Nx, int32_t Ny, double xmi
     CK(c->eu_icnt.ensure((size_t)n_list + 2)); CK(c->eu_ioff.ensure((size_t)n_list + 2));
     CK(c->eu_ccnt.ensure((size_t)cells + 2)); CK(c->eu_coff.ensure((size_t)cells + 2));
     ++g_launches; euler_item_count_kernel<<<nblk(n_list, 128), 128, 0, st>>>(a, c->eu_icnt.p);
-    exclusive_scan(c->eu_icnt.p, n_list, c->eu_ioff.p, n_list + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->eu_icnt.p, n_list, c->eu_ioff.p, n_list + 1));
     CK(cudaGetLastError());
     int n_items = 0;
     CK(cudaMemcpyAsync(&n_items, c->eu_ioff.p + n_list, 4, cudaMemcpyDefault, st)); CK(cudaStreamSynchronize(st));
@@ -2647,7 +2758,7 @@ extern "C" int sz_eulerian_data(SzContext* c, int32_t Nx, int32_t Ny, double xmi
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->eu_cell.p, c->eu_keys.p, c->eu_iota.p, c->eu_sorted.p, n_items, 0, end_bit, st));
     CK(c->eu_tmp.ensure(tmp_bytes + 16));
     ++g_launches; CK(cub::DeviceRadixSort::SortPairs(c->eu_tmp.p, tmp_bytes, c->eu_cell.p, c->eu_keys.p, c->eu_iota.p, c->eu_sorted.p, n_items, 0, end_bit, st));
-    exclusive_scan(c->eu_ccnt.p, cells, c->eu_coff.p, cells + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->eu_ccnt.p, cells, c->eu_coff.p, cells + 1));
     a.sorted = c->eu_sorted.p; a.cell_off = c->eu_coff.p;
     CK(cudaGetLastError());
     CKS(read_counters(c));
@@ -2858,7 +2969,7 @@ extern "C" int sz_pair_search(SzContext* c, int32_t mode, int32_t Nb, int32_t Nx
     CK(c->scan_tmp.ensure(scan_tmp_ints(std::max<size_t>((size_t)ncell + 2, (size_t)nq + 2))));
     CK(cudaMemsetAsync(c->se_ccnt.p, 0, (size_t)(ncell + 1) * 4, st));
     ++g_launches; search_cell_count_kernel<<<nblk(ns, 256), 256, 0, st>>>(n0, first, g, c->x.p, c->y.p, c->se_cid.p, c->se_ccnt.p);
-    exclusive_scan(c->se_ccnt.p, ncell, c->se_cstart.p, ncell + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->se_ccnt.p, ncell, c->se_cstart.p, ncell + 1));
     CK(cudaMemsetAsync(c->se_ccnt.p, 0, (size_t)(ncell + 1) * 4, st));
     ++g_launches; search_cell_fill_kernel<<<nblk(ns, 256), 256, 0, st>>>(n0, first, c->se_cid.p, c->se_cstart.p, c->se_ccnt.p, c->x.p, c->y.p, c->rmax.p, c->se_sidx.p, c->se_sx.p, c->se_sy.p, c->se_sr.p);
     SearchArgs a; memset(&a, 0, sizeof(a));
@@ -2867,7 +2978,7 @@ extern "C" int sz_pair_search(SzContext* c, int32_t mode, int32_t Nb, int32_t Nx
     a.cell_start = c->se_cstart.p; a.s_idx = c->se_sidx.p; a.s_x = c->se_sx.p; a.s_y = c->se_sy.p; a.s_r = c->se_sr.p;
     a.cnt = c->se_cnt.p; a.off = c->se_off.p;
     ++g_launches; search_kernel<false><<<nblk(32 * (i64)nq, 256), 256, 0, st>>>(a);
-    exclusive_scan(c->se_cnt.p, nq, c->se_off.p, nq + 1, c->scan_tmp.p, st);
+    CKS(exclusive_scan(c, c->se_cnt.p, nq, c->se_off.p, nq + 1));
     CK(cudaMemcpyAsync(D_CNT(n_pairs), c->se_off.p + nq, 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
     CKS(read_counters(c));

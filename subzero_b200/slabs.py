@@ -107,6 +107,36 @@ class Comm:
         self.dist.all_reduce(src, op=self.dist.ReduceOp.MAX)
         return src.to(t.device)
 
+    # ---- the three collectives of the device-built slab step, in place on preallocated tensors (one NCCL call each; under
+    # gloo with CUDA tensors they are staged through the host, which is what the two-ranks-on-one-GPU tests use)
+    def all_gather_into(self, out, t):
+        """out [world * k] <- every rank's t [k]"""
+        if self.world == 1:
+            out.copy_(t)
+        elif self.stage:
+            out.copy_(self.all_gather(t).reshape(-1))
+        else:
+            self.dist.all_gather_into_tensor(out, t)
+
+    def all_to_all_into(self, out, t):
+        """equal splits: block p of t goes to rank p, block p of out comes from rank p"""
+        if self.world == 1:
+            return
+        if self.stage or self.dist.get_backend() == "gloo":
+            k = t.numel() // self.world
+            out.copy_(self.exchange(t.view(self.world, k), [1] * self.world, [1] * self.world).reshape(-1))
+        else:
+            self.dist.all_to_all_single(out, t)
+
+    def all_max_(self, t):
+        """elementwise maximum over the ranks, in place"""
+        if self.world == 1:
+            return
+        if self.stage:
+            t.copy_(self.all_max(t))
+        else:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+
     def exchange(self, send, send_counts, recv_counts):
         """variable all-to-all of rows: send [sum(send_counts), k] grouped by destination -> [sum(recv_counts), k]"""
         k = send.shape[1:]
@@ -400,27 +430,23 @@ class DeviceSlab:
         z = lambda n: torch.zeros(n, dtype=F64, device=self.dev)
         self.meta, self.all_meta = z(self.meta_n), z(W * self.meta_n)
         self.send, self.recv = z(W * self.block), z(W * self.block)
-        self.status = torch.zeros(3, dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros(4, dtype=torch.int32, device=self.dev)      # [overflow, outside | list length, -]: the first two are all-reduced
+        self.flag = self.status[:2]
+        P = lambda x, typ: C.cast(C.c_void_p(x.data_ptr()), typ)
+        self._p_meta, self._p_all_meta, self._p_send, self._p_recv, self._p_status = (P(self.meta, abi.c_dp), P(self.all_meta, abi.c_dp), P(self.send, abi.c_dp),
+                                                                                      P(self.recv, abi.c_dp), P(self.status, abi.c_ip))
         self.halo_measured = (int(rec.sum()), int(vert.sum()))
         self.plans += 1
 
     # ---- one step
     def exchange(self):
-        lib, W, h = abi.lib(), self.comm.world, self.ctx._h
-        P = lambda t, typ: C.cast(C.c_void_p(t.data_ptr()), typ)
-        abi.check(lib.sz_slab_prepare(h, P(self.meta, abi.c_dp)))
-        if W == 1:
-            self.all_meta.copy_(self.meta)
-        else:
-            self.all_meta.copy_(self.comm.all_gather(self.meta).reshape(-1))
-        abi.check(lib.sz_slab_pack(h, P(self.all_meta, abi.c_dp), P(self.send, abi.c_dp)))
-        if W > 1:
-            self.recv = self.comm.exchange(self.send.view(W, self.block), [1] * W, [1] * W).reshape(-1)
-            if self.comm.stage:
-                torch.cuda.current_stream(self.dev).synchronize()
-        abi.check(lib.sz_slab_build(h, P(self.recv, abi.c_dp), P(self.status, abi.c_ip)))
-        # agreed by all ranks: [capacity overflow on some rank, owned floes that left their rank's extent]
-        self.flag = self.comm.all_max(self.status[[0, 2]].to(F64)) if W > 1 else self.status[[0, 2]].to(F64)
+        lib, h, comm = abi.lib(), self.ctx._h, self.comm
+        abi.check(lib.sz_slab_prepare(h, self._p_meta))
+        comm.all_gather_into(self.all_meta, self.meta)
+        abi.check(lib.sz_slab_pack(h, self._p_all_meta, self._p_send))
+        comm.all_to_all_into(self.recv, self.send)
+        abi.check(lib.sz_slab_build(h, self._p_recv, self._p_status))
+        comm.all_max_(self.flag)       # agreed by all ranks: [capacity overflow on some rank, owned floes that left their rank's extent]
 
     def run(self, allow_pair_errors=False):
         """one contact step on the current state; returns the step's SzSummary (n = the padded list length)"""
@@ -619,7 +645,7 @@ class SlabJob:
         if self.slab is None:
             self.ext_entries_owned = int(s.n)
         else:
-            self.ext_entries_owned = int(self.slab.status[1].item()) - 0      # list length incl. halo (the halo share is in describe())
+            self.ext_entries_owned = int(self.slab.status[2].item())      # list length incl. halo (the halo share is in describe())
         return ms, ph
 
     def e2e_step(self):

@@ -334,3 +334,46 @@ def test_drop_in_signature_with_ghost_structs(ctx):
                 seen_ghost_partner = True
                 assert abs(int(rg["floe_num"][int(q) - 1 - N0])) >= 1 and Floe[int(q) - 1]["area"] > 0     # Floe(partner) exists for the tail
     assert seen_ghost_partner
+
+
+def test_speculated_sizes_give_the_same_step_and_recover_from_overflow():
+    """option "speculate": steps that take list length, grid, pair and row capacities from the step before must reproduce the
+    fully measured step bit for bit; a step whose field outgrew the carried-over capacities (same floe count, far more pairs
+    and rows) is flagged on the device and repeated; floes that drift (integrator) keep the speculation valid."""
+    def run(spec, fields, traj):
+        outs = []
+        c = sz.ContactContext(0)
+        try:
+            c.set_option("speculate", spec)
+            for prm, soa in fields:
+                c.upload(prm, soa)
+                if traj:
+                    mass = soa.area * soa.h * 920.0
+                    c.trajectory_init(mass, mass * soa.rmax ** 2 / 4, nz=2, dXi_p=soa.u, dYi_p=soa.v)
+                for it in range(4):
+                    s = c.step_resident(allow_pair_errors=True)
+                    off, rows = c.rows()
+                    outs.append((s.n, s.n_pairs, s.n_rows, s.collision_count, c.floe_outputs(), off, rows, c.pairs(), c.ghosts()))
+                    if traj:
+                        c.trajectory_step(prm.dt, 1e-4)
+            return outs, c.stat("speculated_steps"), c.stat("repeated_steps")
+        finally:
+            c.close()
+    prm_a, a = sz.voronoi_field(9000, seed=31, inflate=0.01)
+    prm_b, b = sz.voronoi_field(9000, seed=32, inflate=0.2)          # same floe count: the plan survives the upload ...
+    b.rmax[:] *= 2.0                                                 # ... but the candidate pairs quadruple (and rows grow with the deeper overlaps)
+    for traj in (False, True):
+        if traj:
+            a.u[:] *= 80; a.v[:] *= 80; b.u[:] *= 80; b.v[:] *= 80
+        want, f0, r0 = run(0, [(prm_a, a), (prm_b, b)], traj)
+        got, f1, r1 = run(1, [(prm_a, a), (prm_b, b)], traj)
+        assert f0 == 0 and r0 == 0 and f1 >= 5 and r1 >= 1, (f0, r0, f1, r1)
+        for k, (w, g) in enumerate(zip(want, got)):
+            assert w[:4] == g[:4], (traj, k, w[:4], g[:4])
+            for key in w[4]:
+                assert np.array_equal(w[4][key], g[4][key], equal_nan=True), (traj, k, key)
+            assert np.array_equal(w[5], g[5]) and np.array_equal(w[6], g[6], equal_nan=True), (traj, k)
+            for key in w[7]:
+                assert np.array_equal(w[7][key], g[7][key], equal_nan=True), (traj, k, key)
+            for key in w[8]:
+                assert np.array_equal(w[8][key], g[8][key], equal_nan=True), (traj, k, key)
