@@ -277,6 +277,7 @@ def main():
         narrow_ms += ph["narrow"]
         kern_ms += ph["classes"]["C"][0]          # the dominant kernel: class C of the narrow phase (CUDA events on the library's stream)
         kern_pairs = ph["classes"]["C"][1]
+    phase_last = {k: v for k, v in ph.items() if k != "classes"}
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     launches = abi.lib().sz_launch_count() - launches1
@@ -358,7 +359,8 @@ def main():
                            "floes_incl_ghosts": total_ext, "pairs_per_step": total_pairs, "pairs_with_force": total_force,
                            "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "timesteps_per_s_with_trajectory_update": ts_with_ab2, "parallelism": job.describe(),
                            "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed, "floe_order": args.floe_order, "options": args.opt,
-                           "wall_ms_per_step": wall_ms / args.steps},
+                           "wall_ms_per_step": wall_ms / args.steps, "phase_ms_rank0": phase_last,
+                           "slab_stage_ms_rank0": (job.slab.stage_ms() if job.slab is not None else None)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": launches,

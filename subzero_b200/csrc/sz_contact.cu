@@ -500,96 +500,127 @@ __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const doub
     eno[e] = cvx ? (uint8_t)no : 0;
     erot[e] = cvx ? (uint8_t)szpf::ring_bottom_vertex(Get{vx, vy, X, Y, o}, no) : 0;     // start of the sweep input (PairHints)
 }
-// Separating-axis test for two strictly convex outlines: true when an edge line of one outline has every vertex of
-// the other at least 1 mm (4e6 Clipper units) on its outer side.  Then the outlines are disjoint with a margin a
+// Separating-axis test for two strictly convex outlines (sat_side_group below): true when an edge line of one outline has every
+// vertex of the other at least 1 mm (4e6 Clipper units) on its outer side.  Then the outlines are disjoint with a margin a
 // million times Clipper's rounding, the intersection is empty and the sweep cannot fail: zero force, overlap 0.
-__device__ bool sat_separated(const double* __restrict__ vx, const double* __restrict__ vy, int o1, int n1, double X1, double Y1,
-                              int o2, int n2, double X2, double Y2)
+// Work list of the narrow phase.  classify: a pair whose outlines both survive AddPath and whose integer bounding boxes are
+// strictly disjoint -- or, for two strictly convex outlines, that an edge line of one separates with 1 mm to spare -- has an
+// empty Clipper intersection (and cannot fail), so floe_interactions returns zero force and overlap 0 (:43-51,71-74): it is
+// answered here.  Every other pair gets a bucket key (n1, n2, class C: vertices inside the shared Y range = scanbeams of the
+// convex sweep; class S: direction sector of the partner) so that the pairs a CTA sweeps together have similar event orders.
+// The separating-axis test used to be a doubly nested loop over (edge of one outline) x (vertex of the other) with an early exit:
+// 7.5 of 32 lanes active, 29 % of the FP64 pipe, 16 % of the whole step.  An edge line can only have EVERY vertex of the other
+// outline beyond it if that outline's centroid (inside its convex hull) is beyond it too, so the vertex loop now runs only for
+// the one to three edges that pass this one-product test: the same decisions for a quarter of the arithmetic.
+// CLS_G lanes per pair (compile-time; 1 = a thread per pair): with CLS_G > 1 the lanes of a group take the edges in turn and
+// vote -- measured slower at 8 (2.84 vs 1.81 ms at 1M floes: the per-pair gathers of boxes, flags and offsets are repeated by
+// every lane of the group and dominate).
+#ifndef CLS_G
+#define CLS_G 1
+#endif
+__device__ __forceinline__ bool sat_side_group(const double* __restrict__ vx, const double* __restrict__ vy, int oa, int na, double XA, double YA,
+                                               int ob, int nb, double XB, double YB, int gl)
 {
-    for (int side = 0; side < 2; ++side) {
-        const int oa = side ? o2 : o1, na = side ? n2 : n1, ob = side ? o1 : o2, nb = side ? n1 : n2;
-        const double XA = side ? X2 : X1, YA = side ? Y2 : Y1, XB = side ? X1 : X2, YB = side ? Y1 : Y2;
-        // orientation of A from its first turn (strictly convex: every turn has this sign)
-        const double t = ((vx[oa + 1] - vx[oa]) * (vy[oa + 2] - vy[oa + 1]) - (vy[oa + 1] - vy[oa]) * (vx[oa + 2] - vx[oa + 1]));
-        const double sg = t > 0 ? 1.0 : -1.0;       // inner side of an edge is where sg * cross > 0
-        for (int e = 0; e < na; ++e) {
-            const int e1 = (e + 1 == na) ? 0 : e + 1;
-            const double ax = vx[oa + e] + XA, ay = vy[oa + e] + YA, dx = (vx[oa + e1] + XA) - ax, dy = (vy[oa + e1] + YA) - ay;
-            const double lim = -1e-3 * sqrt(dx * dx + dy * dy);
-            bool all_out = true;
-            for (int q = 0; q < nb && all_out; ++q) {
-                const double cr = sg * (dx * ((vy[ob + q] + YB) - ay) - dy * ((vx[ob + q] + XB) - ax));
-                all_out = cr < lim;
-            }
-            if (all_out) return true;
+    // (XB, YB) is the other outline's centroid: c_alpha is the outline about the centroid (initialize_floe_values.m:17)
+    // orientation of A from its first turn (strictly convex: every turn has this sign)
+    const double t = ((vx[oa + 1] - vx[oa]) * (vy[oa + 2] - vy[oa + 1]) - (vy[oa + 1] - vy[oa]) * (vx[oa + 2] - vx[oa + 1]));
+    const double sg = t > 0 ? 1.0 : -1.0;       // inner side of an edge is where sg * cross > 0
+    // a point inside B's convex hull: the mean of its vertices (the field's Xi, Yi need not be trusted for this)
+    double cbx = 0, cby = 0;
+    for (int q = 0; q < nb; ++q) { cbx += vx[ob + q]; cby += vy[ob + q]; }
+    cbx = cbx / nb + XB; cby = cby / nb + YB;
+    bool found = false;
+    for (int e = gl; e < na; e += CLS_G) {
+        const int e1 = (e + 1 == na) ? 0 : e + 1;
+        const double ax = vx[oa + e] + XA, ay = vy[oa + e] + YA, dx = (vx[oa + e1] + XA) - ax, dy = (vy[oa + e1] + YA) - ay;
+        const double lim = -1e-3 * sqrt(dx * dx + dy * dy);
+        // necessary condition: a point of B's convex hull -- the mean of its vertices -- is beyond the line by the same margin
+        if (!(sg * (dx * (cby - ay) - dy * (cbx - ax)) < lim)) continue;
+        bool all_out = true;
+        for (int q = 0; q < nb && all_out; ++q) {
+            const double cr = sg * (dx * ((vy[ob + q] + YB) - ay) - dy * ((vx[ob + q] + XB) - ax));
+            all_out = cr < lim;
         }
+        found = found || all_out;
     }
-    return false;
+    return found;
 }
-// Pass 0 counts, pass 1 scatters.  A pair whose outlines both survive AddPath and whose integer bounding boxes are
-// strictly disjoint has an empty Clipper intersection (and cannot fail), so floe_interactions returns zero force and
-// overlap 0 (:43-51,71-74): it is answered here.  Every other pair is bucketed by n1 + n2 so that the pairs a CTA
-// sweeps together have the same number of scanbeams.
-__global__ void pair_classify_kernel(int pass, int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
+__global__ void __launch_bounds__(256) pair_classify_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
                                      const uint8_t* __restrict__ evalid, const int* __restrict__ env, const uint8_t* __restrict__ eno, const int* __restrict__ esrc,
                                      const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
-                                     int* __restrict__ listC, int* __restrict__ listS, const double* __restrict__ ex, const double* __restrict__ ey,
-                                     int* __restrict__ bins, int* __restrict__ bin_fill, short* __restrict__ pkey, Counters* c, int cvx_key_mode)
+                                     const double* __restrict__ ex, const double* __restrict__ ey, int* __restrict__ bins, short* __restrict__ pkey, Counters* c, int cvx_key_mode)
 {
     // per bucket: pairs of strictly convex outlines (class C) in the high half-word, the others (class S) in the low one
     __shared__ int sh[SZ_NBINS];
     for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) sh[t] = 0;
     __syncthreads();
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int np = c->overflow ? 0 : (*np_dev < np_cap ? *np_dev : np_cap);     // a flagged step is going to be repeated: its pair list may be incomplete
-    int key = -1, slot = 0; bool cvx = false;
-    if (p < np && pass == 1) {
-        key = pkey[p];
-        if (key >= 0) { cvx = (key & SZ_NBINS) != 0; key &= SZ_NBINS - 1; const int old = atomicAdd(&sh[key], cvx ? 65536 : 1); slot = cvx ? (old >> 16) : (old & 0xffff); }
-    }
-    if (p < np && pass == 0) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) / CLS_G, gl = threadIdx.x & (CLS_G - 1);
+    const unsigned gmask = ((1u << CLS_G) - 1u) << ((threadIdx.x & 31) & ~(CLS_G - 1));
+    if (p < np) {                                   // group-uniform
         const int i = pi[p], j = pj[p];
         const i64* a = ebb + (size_t)i * 4; const i64* b = ebb + (size_t)j * 4;
         bool disjoint = evalid[i] && evalid[j] && (a[1] < b[0] || b[1] < a[0] || a[3] < b[2] || b[3] < a[2]);
-        cvx = eno[i] >= 3 && eno[j] >= 3;                    // both strictly convex (eno is 0 otherwise)
-        if (!disjoint && cvx)
-            disjoint = sat_separated(vx, vy, voff[esrc[i]], eno[i], ex[i], ey[i], voff[esrc[j]], eno[j], ex[j], ey[j]);
-        if (disjoint) {
-            status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0;
-        } else {
-            const int ni = env[i] < SZ_BIN_N ? env[i] : SZ_BIN_N - 1, nj = env[j] < SZ_BIN_N ? env[j] : SZ_BIN_N - 1;
-            // pairs of one bucket have the same vertex counts and the partner in the same octant: similar event orders
-            const double dx = ex[j] - ex[i], dy = ey[j] - ey[i];
-            const double adx = fabs(dx), ady = fabs(dy), mn = adx < ady ? adx : ady, mx = adx < ady ? ady : adx;
-            int oct = (dx > 0) | ((dy > 0) << 1) | ((adx > ady) << 2) | ((mn > 0.41421356237309503 * mx) << 3);
-            if (cvx && cvx_key_mode == 1) {
-                // class C sweeps one scanbeam per CTA-synchronous iteration, and only over the Y range the two outlines
-                // share: bucket by the number of vertices in that range (= iterations) instead of the direction
-                const double lo = (double)(a[2] > b[2] ? a[2] : b[2]), hi = (double)(a[3] < b[3] ? a[3] : b[3]);
-                int cnt = 0;
-                const int oi = voff[esrc[i]], oj = voff[esrc[j]];
-                for (int t = 0; t < eno[i]; ++t) { const double y = (vy[oi + t] + ey[i]) * SZ_SCALE; cnt += (y >= lo && y <= hi); }
-                for (int t = 0; t < eno[j]; ++t) { const double y = (vy[oj + t] + ey[j]) * SZ_SCALE; cnt += (y >= lo && y <= hi); }
-                oct = cnt < SZ_NSECT ? cnt : SZ_NSECT - 1;
-            }
-            key = (ni * SZ_BIN_N + nj) * SZ_NSECT + oct;
-            atomicAdd(&sh[key], cvx ? 65536 : 1);
+        const int ni = eno[i], nj = eno[j];
+        const bool cvx = ni >= 3 && nj >= 3;                    // both strictly convex (eno is 0 otherwise)
+        const int oi = voff[esrc[i]], oj = voff[esrc[j]];
+        const double Xi = ex[i], Yi = ey[i], Xj = ex[j], Yj = ey[j];
+        if (!disjoint && cvx) {
+            bool f = sat_side_group(vx, vy, oi, ni, Xi, Yi, oj, nj, Xj, Yj, gl);
+            f = f || sat_side_group(vx, vy, oj, nj, Xj, Yj, oi, ni, Xi, Yi, gl);
+            disjoint = __any_sync(gmask, f);
         }
-        pkey[p] = (short)(key < 0 ? key : (key | (cvx ? SZ_NBINS : 0)));
+        int cnt = 0;
+        if (!disjoint && cvx && cvx_key_mode == 1) {
+            // class C sweeps one scanbeam per CTA-synchronous iteration, and only over the Y range the two outlines share:
+            // bucket by the number of vertices in that range (= iterations) instead of the direction
+            const double lo = (double)(a[2] > b[2] ? a[2] : b[2]), hi = (double)(a[3] < b[3] ? a[3] : b[3]);
+            for (int t = gl; t < ni; t += CLS_G) { const double y = (vy[oi + t] + Yi) * SZ_SCALE; cnt += (y >= lo && y <= hi); }
+            for (int t = gl; t < nj; t += CLS_G) { const double y = (vy[oj + t] + Yj) * SZ_SCALE; cnt += (y >= lo && y <= hi); }
+            cnt = __reduce_add_sync(gmask, cnt);
+        }
+        if (gl == 0) {
+            int key = -1;
+            if (disjoint) {
+                status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0;
+            } else {
+                const int bi = env[i] < SZ_BIN_N ? env[i] : SZ_BIN_N - 1, bj = env[j] < SZ_BIN_N ? env[j] : SZ_BIN_N - 1;
+                // pairs of one bucket have the same vertex counts and the partner in the same octant: similar event orders
+                const double dx = Xj - Xi, dy = Yj - Yi;
+                const double adx = fabs(dx), ady = fabs(dy), mn = adx < ady ? adx : ady, mx = adx < ady ? ady : adx;
+                int oct = (dx > 0) | ((dy > 0) << 1) | ((adx > ady) << 2) | ((mn > 0.41421356237309503 * mx) << 3);
+                if (cvx && cvx_key_mode == 1) oct = cnt < SZ_NSECT ? cnt : SZ_NSECT - 1;
+                key = (bi * SZ_BIN_N + bj) * SZ_NSECT + oct;
+                atomicAdd(&sh[key], cvx ? 65536 : 1);
+            }
+            pkey[p] = (short)(key < 0 ? key : (key | (cvx ? SZ_NBINS : 0)));
+        }
     }
     __syncthreads();
-    if (pass == 0) {
-        for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) {
-            const int v = sh[t];
-            if (v >> 16) atomicAdd(&bins[t], v >> 16);
-            if (v & 0xffff) atomicAdd(&bins[SZ_NBINS + t], v & 0xffff);
-        }
-        return;
+    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) {
+        const int v = sh[t];
+        if (v >> 16) atomicAdd(&bins[t], v >> 16);
+        if (v & 0xffff) atomicAdd(&bins[SZ_NBINS + t], v & 0xffff);
     }
-    // pass 1: bins[] holds exclusive offsets (class C buckets, then class S buckets); reserve this CTA's share of every
-    // bucket, then place -- class C first, then class S through the same shared array
+}
+// scatter: bins[] holds exclusive offsets (class C buckets, then class S buckets); every CTA reserves its share of every bucket,
+// then places its pairs -- class C first, then class S through the same shared array
+__global__ void __launch_bounds__(256) pair_scatter_kernel(int np_cap, const int* __restrict__ np_dev, const short* __restrict__ pkey, const int* __restrict__ bins, int* __restrict__ bin_fill,
+                                                           int* __restrict__ listC, int* __restrict__ listS, const Counters* __restrict__ c)
+{
+    __shared__ int sh[SZ_NBINS];
     __shared__ int base[SZ_NBINS];
+    for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    const int np = c->overflow ? 0 : (*np_dev < np_cap ? *np_dev : np_cap);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int key = -1, slot = 0; bool cvx = false;
+    if (p < np) {
+        key = pkey[p];
+        if (key >= 0) { cvx = (key & SZ_NBINS) != 0; key &= SZ_NBINS - 1; const int old = atomicAdd(&sh[key], cvx ? 65536 : 1); slot = cvx ? (old >> 16) : (old & 0xffff); }
+    }
+    __syncthreads();
     for (int t = threadIdx.x; t < SZ_NBINS; t += blockDim.x) base[t] = (sh[t] >> 16) ? atomicAdd(&bin_fill[t], sh[t] >> 16) : 0;
     __syncthreads();
     if (key >= 0 && cvx) listC[bins[key] + base[key] + slot] = p;
@@ -1490,11 +1521,10 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         static const int key_mode = getenv("SZ_CVX_KEY") ? atoi(getenv("SZ_CVX_KEY")) : 1;   // 0: direction sectors for class C too (experiments)
         CK(c->bins.ensure(2 * SZ_NBINS)); CK(c->bin_fill.ensure(2 * SZ_NBINS));
         CK(cudaMemsetAsync(c->bins.p, 0, 2 * SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, 2 * SZ_NBINS * sizeof(int), st));
-        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(0, n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt, key_mode);
+        pair_classify_kernel<<<nblk((i64)n_work * CLS_G, 256), 256, 0, st>>>(n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->ex.p, c->ey.p, c->bins.p, c->pkey.p, c->d_cnt, key_mode);
         bins_scan_kernel<<<2, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
-        pair_classify_kernel<<<nblk(n_work, 256), 256, 0, st>>>(1, n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->listC.p, c->listS.p, c->ex.p, c->ey.p, c->bins.p, c->bin_fill.p, c->pkey.p, c->d_cnt, key_mode);
+        pair_scatter_kernel<<<nblk(n_work, 256), 256, 0, st>>>(n_work, D_CNT(n_pairs), c->pkey.p, c->bins.p, c->bin_fill.p, c->listC.p, c->listS.p, c->d_cnt);
         g_launches += 3;
         // class C: strictly convex pairs through the four-edge sweep; what it declines is appended to class S's list.
         // Both launches are sized for all pairs (the list lengths are only known on the device; surplus CTAs exit at once).

@@ -391,6 +391,8 @@ class DeviceSlab:
         self.n_global = int(n_global)
         self.plans = self.steps = 0
         self.summary = None
+        import os
+        self.timing = {"ms": [0.0] * 7, "n": 0} if os.environ.get("SZ_SLAB_TIMING") else None
         self.dev = torch.device(comm.device) if comm.device is not None else torch.device("cuda", torch.cuda.current_device())
         # the library launches on torch's current stream: its kernels and the collectives are ordered by the stream alone
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -441,18 +443,46 @@ class DeviceSlab:
     # ---- one step
     def exchange(self):
         lib, h, comm = abi.lib(), self.ctx._h, self.comm
+        ev = self._stage_events() if self.timing is not None else None
         abi.check(lib.sz_slab_prepare(h, self._p_meta))
+        if ev: ev[1].record()
         comm.all_gather_into(self.all_meta, self.meta)
+        if ev: ev[2].record()
         abi.check(lib.sz_slab_pack(h, self._p_all_meta, self._p_send))
+        if ev: ev[3].record()
         comm.all_to_all_into(self.recv, self.send)
+        if ev: ev[4].record()
         abi.check(lib.sz_slab_build(h, self._p_recv, self._p_status))
+        if ev: ev[5].record()
         comm.all_max_(self.flag)       # agreed by all ranks: [capacity overflow on some rank, owned floes that left their rank's extent]
+        if ev: ev[6].record()
+
+    STAGES = ("prepare", "all_gather", "pack", "all_to_all", "build", "all_reduce", "contact_step")
+
+    def _stage_events(self):
+        """SZ_SLAB_TIMING=1: CUDA events between the stages of a step (diagnostic; read back by stage_ms())"""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+        ev[0].record()
+        self._ev = ev
+        return ev
+
+    def stage_ms(self):
+        """mean device ms per stage over the steps timed so far (SZ_SLAB_TIMING=1), or None"""
+        if not self.timing or not self.timing["n"]:
+            return None
+        return {k: self.timing["ms"][i] / self.timing["n"] for i, k in enumerate(self.STAGES)}
 
     def run(self, allow_pair_errors=False):
         """one contact step on the current state; returns the step's SzSummary (n = the padded list length)"""
         for attempt in range(4):
             self.exchange()
             s = self.ctx.step_resident(allow_pair_errors=allow_pair_errors)
+            if self.timing is not None:
+                self._ev[7].record()
+                self._ev[7].synchronize()
+                for i in range(7):
+                    self.timing["ms"][i] += self._ev[i].elapsed_time(self._ev[i + 1])
+                self.timing["n"] += 1
             flag = self.flag.cpu()
             if int(flag[0]) == 0:
                 self.summary, self.steps, self.n_outside = s, self.steps + 1, int(flag[1])
