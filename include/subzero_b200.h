@@ -179,6 +179,9 @@ int sz_slab_prepare(SzContext* ctx, double* meta_dev);
 int sz_slab_pack(SzContext* ctx, const double* all_meta_dev, double* send_dev);
 int sz_slab_build(SzContext* ctx, const double* recv_dev, int32_t* status_dev);
 int sz_slab_get_positions(SzContext* ctx, int32_t* opos /* [n_owned] 0-based list positions */, int32_t* n_list);
+/* Floe(i).interactions of the owned floes in their order (gathered on the device): row_off [n_owned + 1], rows [n_rows * 7] with room
+ * for rows_cap rows; call with rows = NULL to learn n_rows first.  Partner ids are global list positions. */
+int sz_slab_get_rows(SzContext* ctx, int64_t* row_off, double* rows, int64_t rows_cap, int64_t* n_rows);
 int sz_slab_get_list(SzContext* ctx, int32_t* gid, int32_t* floe_num, uint8_t* owned, double* x, double* y);   /* [n_list] each, any may be NULL */
 int sz_slab_get_outputs(SzContext* ctx, double* fx, double* fy, double* torque, double* overlap_area, double* stress, double* xi, double* yi,
                         uint8_t* alive, int32_t* kill, int32_t* transfer);   /* per owned floe, like sz_get_floe_outputs */

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "sz_slab_pack": (C.c_int, [C.c_void_p, c_dp, c_dp]),
     "sz_slab_build": (C.c_int, [C.c_void_p, c_dp, c_ip]),
     "sz_slab_get_positions": (C.c_int, [C.c_void_p, c_ip, c_ip]),
+    "sz_slab_get_rows": (C.c_int, [C.c_void_p, c_lp, c_dp, C.c_int64, c_lp]),
     "sz_slab_get_list": (C.c_int, [C.c_void_p, c_ip, c_ip, c_bp, c_dp, c_dp]),
     "sz_slab_get_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),

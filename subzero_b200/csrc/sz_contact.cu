@@ -63,6 +63,8 @@ struct DBuf {
         T* q = nullptr;
         cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
         if (e != cudaSuccess) return e;
+        static const bool poison = getenv("SZ_DEBUG_POISON") != nullptr;      // debugging aid: fresh buffers start as 0xFF.. instead of whatever was there
+        if (poison) cudaMemset(q, 0x7F, ncap * sizeof(T));
         if (keep && p && cap) cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
         if (p) cudaFree(p);
         p = q; cap = ncap;
@@ -126,7 +128,7 @@ struct SzContext {
     // extended list is rebuilt on the device every step
     bool slab = false, sl_configured = false, sl_built = false; int sl_rank = 0, sl_world = 1, sl_nglobal = 0, sl_cap_img = 0, sl_cap_rec = 0, sl_cap_vert = 0, sl_nl_cap = 0;
     struct SlabScratch* sl_scratch = nullptr; double sl_xlo = -SZ_INF, sl_xhi = SZ_INF;
-    DBuf<int> sl_ogid, sl_flag, sl_pos, sl_opos, sl_g, sl_sendcnt, sl_keys, sl_slots, sl_hnv, sl_hvoff; DBuf<uint8_t> sl_cub; DBuf<double> sl_out;
+    DBuf<int> sl_ogid, sl_flag, sl_pos, sl_opos, sl_g, sl_sendcnt, sl_keys, sl_slots, sl_hnv, sl_hvoff; DBuf<uint8_t> sl_cub; DBuf<double> sl_out, sl_rows; DBuf<int> sl_rcnt, sl_roff;
     int nout = 0;                   // entries with per-floe outputs: n0 (single GPU) or n (extended mode)
     DBuf<int> flag, pos, scan_tmp;
     DBuf<u64> scan_state; u64 scan_ticket_base = 0; unsigned scan_epoch = 0;      // single-pass scan: [0] ticket counter, [1..] tile status words
@@ -135,7 +137,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> stage, listC, listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
+    DBuf<int> stage, listC, listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb, erec /* EntryRec [n], 8 words each */; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -435,7 +437,12 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
                     j = b.s_idx[t];
                     if (j > i && (own_i || b.eowned[j])) {     // a pair is resolved where either floe is owned
                         const double dx = xi - b.s_x[t], dy = yi - b.s_y[t], rs = ri + b.s_r[t];
-                        if (sqrt(dx * dx + dy * dy) < rs) {
+                        // sqrt((xi-xj)^2+(yi-yj)^2) < rmax_i+rmax_j (:103).  The square root is only taken when the squares are
+                        // within 1e-12 of each other: further apart, the correctly rounded root cannot land on the other side
+                        // of rs (its relative distance from rs is > 4e-13, four thousand ulps)
+                        const double d2 = dx * dx + dy * dy, r2 = rs * rs;
+                        const bool near = d2 < r2 * (1 - 1e-12) ? true : (d2 > r2 * (1 + 1e-12) ? false : sqrt(d2) < rs);
+                        if (near) {
                             ok = true;
                             if (b.efn[j] < 0 && ghost_is_member(b, i, j) && !(2 * rs > b.minL2)) ok = false;
                         }
@@ -466,11 +473,14 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
 }
 
 // ------------------------------------------------------------------------------------------------ narrow-phase work list
+// Everything the pair classifier needs about one entry of the extended list in ONE 64-byte record (two sectors): the classifier
+// is a gather over randomly numbered partners, and it used to touch eight separate arrays per entry.
+struct __align__(16) EntryRec { i64 bb[4]; double x, y; int vo; short nv; unsigned char no, valid; int pad; };
 // Per entry of the extended list: the bounding box of its outline in Clipper's coordinates (polyclip.m:66) and
 // whether the outline survives Clipper's AddPath (>= 3 vertices, not all collinear: clipper.cpp:1058,1119-1123).
 __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const double* __restrict__ ey, const int* __restrict__ esrc, const int* __restrict__ voff,
                                 const double* __restrict__ vx, const double* __restrict__ vy, i64* __restrict__ ebb, uint8_t* __restrict__ evalid, int* __restrict__ env,
-                                uint8_t* __restrict__ econvex, uint8_t* __restrict__ erot, uint8_t* __restrict__ eno)
+                                uint8_t* __restrict__ econvex, uint8_t* __restrict__ erot, uint8_t* __restrict__ eno, EntryRec* __restrict__ erec)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -499,6 +509,9 @@ __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const doub
     econvex[e] = cvx;
     eno[e] = cvx ? (uint8_t)no : 0;
     erot[e] = cvx ? (uint8_t)szpf::ring_bottom_vertex(Get{vx, vy, X, Y, o}, no) : 0;     // start of the sweep input (PairHints)
+    EntryRec r; r.bb[0] = xmn; r.bb[1] = xmx; r.bb[2] = ymn; r.bb[3] = ymx; r.x = X; r.y = Y; r.vo = o; r.nv = (short)(nv < 32767 ? nv : 32767); r.no = cvx ? (unsigned char)no : 0;
+    r.valid = valid ? 1 : 0; r.pad = 0;
+    erec[e] = r;
 }
 // Separating-axis test for two strictly convex outlines (sat_side_group below): true when an edge line of one outline has every
 // vertex of the other at least 1 mm (4e6 Clipper units) on its outer side.  Then the outlines are disjoint with a margin a
@@ -545,11 +558,10 @@ __device__ __forceinline__ bool sat_side_group(const double* __restrict__ vx, co
     }
     return found;
 }
-__global__ void __launch_bounds__(256) pair_classify_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const i64* __restrict__ ebb,
-                                     const uint8_t* __restrict__ evalid, const int* __restrict__ env, const uint8_t* __restrict__ eno, const int* __restrict__ esrc,
-                                     const int* __restrict__ voff, const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
+__global__ void __launch_bounds__(256) pair_classify_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const EntryRec* __restrict__ erec,
+                                     const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
-                                     const double* __restrict__ ex, const double* __restrict__ ey, int* __restrict__ bins, short* __restrict__ pkey, Counters* c, int cvx_key_mode)
+                                     int* __restrict__ bins, short* __restrict__ pkey, Counters* c, int cvx_key_mode)
 {
     // per bucket: pairs of strictly convex outlines (class C) in the high half-word, the others (class S) in the low one
     __shared__ int sh[SZ_NBINS];
@@ -560,12 +572,13 @@ __global__ void __launch_bounds__(256) pair_classify_kernel(int np_cap, const in
     const unsigned gmask = ((1u << CLS_G) - 1u) << ((threadIdx.x & 31) & ~(CLS_G - 1));
     if (p < np) {                                   // group-uniform
         const int i = pi[p], j = pj[p];
-        const i64* a = ebb + (size_t)i * 4; const i64* b = ebb + (size_t)j * 4;
-        bool disjoint = evalid[i] && evalid[j] && (a[1] < b[0] || b[1] < a[0] || a[3] < b[2] || b[3] < a[2]);
-        const int ni = eno[i], nj = eno[j];
-        const bool cvx = ni >= 3 && nj >= 3;                    // both strictly convex (eno is 0 otherwise)
-        const int oi = voff[esrc[i]], oj = voff[esrc[j]];
-        const double Xi = ex[i], Yi = ey[i], Xj = ex[j], Yj = ey[j];
+        const EntryRec ri = erec[i], rj = erec[j];
+        const i64* a = ri.bb; const i64* b = rj.bb;
+        bool disjoint = ri.valid && rj.valid && (a[1] < b[0] || b[1] < a[0] || a[3] < b[2] || b[3] < a[2]);
+        const int ni = ri.no, nj = rj.no;
+        const bool cvx = ni >= 3 && nj >= 3;                    // both strictly convex (no is 0 otherwise)
+        const int oi = ri.vo, oj = rj.vo;
+        const double Xi = ri.x, Yi = ri.y, Xj = rj.x, Yj = rj.y;
         if (!disjoint && cvx) {
             bool f = sat_side_group(vx, vy, oi, ni, Xi, Yi, oj, nj, Xj, Yj, gl);
             f = f || sat_side_group(vx, vy, oj, nj, Xj, Yj, oi, ni, Xi, Yi, gl);
@@ -585,7 +598,7 @@ __global__ void __launch_bounds__(256) pair_classify_kernel(int np_cap, const in
             if (disjoint) {
                 status[p] = 0; nrows[p] = 0; ovl[p] = 0; if (want_polys) poly_npaths[p] = 0;
             } else {
-                const int bi = env[i] < SZ_BIN_N ? env[i] : SZ_BIN_N - 1, bj = env[j] < SZ_BIN_N ? env[j] : SZ_BIN_N - 1;
+                const int bi = ri.nv < SZ_BIN_N ? ri.nv : SZ_BIN_N - 1, bj = rj.nv < SZ_BIN_N ? rj.nv : SZ_BIN_N - 1;
                 // pairs of one bucket have the same vertex counts and the partner in the same octant: similar event orders
                 const double dx = Xj - Xi, dy = Yj - Yi;
                 const double adx = fabs(dx), ady = fabs(dy), mn = adx < ady ? adx : ady, mx = adx < ady ? ady : adx;
@@ -740,8 +753,9 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= a.n) return;
-    if (a.cnt->overflow) return;                                              // an earlier phase outgrew its capacity: the step is repeated
-    if (a.row_off[m + 1] > a.rows_cap) { a.cnt->overflow = 1; return; }      // more rows than the speculated capacity: flagged, the step is repeated
+    // an earlier phase outgrew its (speculated) capacity, or there are more rows than the speculated row capacity: the step is
+    // flagged and will be repeated; nothing may be read through its incomplete lists, and the kill fix-up must find no event
+    if (a.cnt->overflow || a.row_off[m + 1] > a.rows_cap) { a.cnt->overflow = 1; a.kill_i[m] = 0; a.transfer_i[m] = 0; a.has_rows[m] = 0; return; }
     const bool owned = a.eowned[m] != 0, orig = a.efn[m] > 0, pairing = a.egid[m] > a.Nb;   // pairing: i >= 1+Nb (:125)
     if (!owned) {
         a.osum[(size_t)m * 3] = a.osum[(size_t)m * 3 + 1] = a.osum[(size_t)m * 3 + 2] = 0; a.e_ov[m] = 0; a.has_rows[m] = 0; a.kill_i[m] = 0; a.transfer_i[m] = 0;
@@ -936,7 +950,7 @@ extern "C" void sz_destroy(SzContext* c)
     for (auto* b : ib) b->release();
     DBuf<uint8_t>* ub[] = {&c->evalid, &c->econvex, &c->erot, &c->eno, &c->eowned, &c->alive, &c->ealive, &c->has_rows, &c->o_alive, &c->scratchM, &c->scratchL, &c->pt_a, &c->t_forced, &c->fr_changed, &c->cr_da, &c->cr_ealive, &c->eu_tmp};
     for (auto* b : ub) b->release();
-    DBuf<i64>* lb[] = {&c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy, &c->ho_x, &c->ho_y};
+    DBuf<i64>* lb[] = {&c->erec, &c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy, &c->ho_x, &c->ho_y};
     for (auto* b : lb) b->release();
     c->scan_state.release();
     c->pkey.release();
@@ -944,7 +958,7 @@ extern "C" void sz_destroy(SzContext* c)
                           &c->c0x, &c->c0y, &c->t_stressH, &c->t_stress};
       for (auto* b : tb) b->release(); c->t_scount.release(); c->t_flags.release(); }
     { DBuf<int>* sb[] = {&c->sl_ogid, &c->sl_flag, &c->sl_pos, &c->sl_opos, &c->sl_g, &c->sl_sendcnt, &c->sl_keys, &c->sl_slots, &c->sl_hnv, &c->sl_hvoff};
-      for (auto* b : sb) b->release(); c->sl_cub.release(); c->sl_out.release(); if (c->sl_scratch) cudaFree(c->sl_scratch); }
+      for (auto* b : sb) b->release(); c->sl_cub.release(); c->sl_out.release(); c->sl_rows.release(); c->sl_rcnt.release(); c->sl_roff.release(); if (c->sl_scratch) cudaFree(c->sl_scratch); }
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1485,6 +1499,16 @@ extern "C" int sz_slab_get_positions(SzContext* c, int32_t* opos, int32_t* n_lis
     return SZ_OK;
 }
 
+// debugging aid (SZ_DEBUG_SYNC=1): synchronise at the phase boundaries of the step and name the phase a CUDA error belongs to
+static int dbg_sync(SzContext* c, const char* what)
+{
+    static const bool on = getenv("SZ_DEBUG_SYNC") != nullptr;
+    if (!on) return SZ_OK;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { sz_set_error("CUDA error %s after phase '%s'", cudaGetErrorString(e), what); fprintf(stderr, "[sz] CUDA error %s after phase '%s'\n", cudaGetErrorString(e), what); return SZ_ERR_CUDA; }
+    return SZ_OK;
+}
 static int read_counters(SzContext* c)
 {
     CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDefault, c->stream));
@@ -1521,11 +1545,12 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         static const int key_mode = getenv("SZ_CVX_KEY") ? atoi(getenv("SZ_CVX_KEY")) : 1;   // 0: direction sectors for class C too (experiments)
         CK(c->bins.ensure(2 * SZ_NBINS)); CK(c->bin_fill.ensure(2 * SZ_NBINS));
         CK(cudaMemsetAsync(c->bins.p, 0, 2 * SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, 2 * SZ_NBINS * sizeof(int), st));
-        pair_classify_kernel<<<nblk((i64)n_work * CLS_G, 256), 256, 0, st>>>(n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, c->ebb.p, c->evalid.p, c->env.p, c->eno.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->ex.p, c->ey.p, c->bins.p, c->pkey.p, c->d_cnt, key_mode);
+        pair_classify_kernel<<<nblk((i64)n_work * CLS_G, 256), 256, 0, st>>>(n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, (const EntryRec*)c->erec.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->bins.p, c->pkey.p, c->d_cnt, key_mode);
         bins_scan_kernel<<<2, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
         pair_scatter_kernel<<<nblk(n_work, 256), 256, 0, st>>>(n_work, D_CNT(n_pairs), c->pkey.p, c->bins.p, c->bin_fill.p, c->listC.p, c->listS.p, c->d_cnt);
         g_launches += 3;
+        CKS(dbg_sync(c, "pair classify + scatter"));
         // class C: strictly convex pairs through the four-edge sweep; what it declines is appended to class S's list.
         // Both launches are sized for all pairs (the list lengths are only known on the device; surplus CTAs exit at once).
         static const bool env_no_fast = getenv("SZ_NO_CONVEX_FAST") != nullptr;      // experiment switch: everything through class S
@@ -1698,6 +1723,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     }
     c->n = n;
 
+    CKS(dbg_sync(c, fast ? "K0 (speculated)" : "K0"));
     CK(cudaEventRecord(c->evp[0], st));
     // ---- K1: cell grid + candidate pairs
     GridDesc g;
@@ -1725,12 +1751,13 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         if (stage_cap > 0) { CK(c->stage.ensure((size_t)n * stage_cap + 1)); b.stage = c->stage.p; b.stage_cap = stage_cap > 32 ? 32 : stage_cap; }
         { ++g_launches; broad_kernel<false><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
     }
+    CKS(dbg_sync(c, "cell grid + broad count"));
     CKS(exclusive_scan(c, c->pcnt.p, n, c->pair_off.p, n + 1));
     CK(cudaMemcpyAsync(D_CNT(n_pairs), c->pair_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
     // per-entry preparation of the narrow phase (bounding boxes, convexity): independent of the pair list, so it is queued
     // before the host waits for the pair count
-    CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1));
-    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p); }
+    CK(c->erec.ensure(8 * (size_t)n + 8)); CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1));
+    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p, (EntryRec*)c->erec.p); }
     CK(cudaGetLastError());
     int np;
     if (fast) np = c->plan_npcap;
@@ -1740,6 +1767,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     CK(c->listT.ensure(np + 1)); CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
+    CKS(dbg_sync(c, "ext_prep + broad fill"));
     CK(cudaEventRecord(c->evp[1], st));
     CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
@@ -1778,6 +1806,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         if (attempt == 2) { sz_set_error("sz_step_resident: result pools kept overflowing"); return SZ_ERR_CAPACITY; }
     }
 
+    CKS(dbg_sync(c, "narrow phase"));
     CK(cudaEventRecord(c->evp[2], st));
     // ---- K4: mirror, rows, sums
     CK(c->tcnt.ensure(n + 2)); CK(c->toff.ensure(n + 2)); CK(c->tlist.ensure(np + 1)); CK(c->rcnt.ensure(n + 2)); CK(c->row_off.ensure(n + 2));
@@ -1788,6 +1817,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { ++g_launches; tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, D_CNT(n_pairs), c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p); }
     if (n > 0) { ++g_launches; rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->eowned.p, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p); }
     CKS(exclusive_scan(c, c->rcnt.p, n, c->row_off.p, n + 1));
+    CKS(dbg_sync(c, "tcount/tfill/rowcount"));
     CK(cudaMemcpyAsync(D_CNT(total_rows), c->row_off.p + n, 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
     // every row of the pool appears at most twice (its floe's own row and the partner's mirrored row): the row count is
@@ -1810,6 +1840,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         a.rows = c->rows.p; a.rows_cap = rows_bound; a.osum = c->osum.p; a.e_ov = c->e_ov.p; a.has_rows = c->has_rows.p; a.kill_i = c->kill_i.p; a.transfer_i = c->transfer_i.p;
         a.o_ov = c->o_ov.p; a.o_stress = c->o_stress.p; a.o_xi = c->o_xi.p; a.o_yi = c->o_yi.p; a.o_alive = c->o_alive.p; a.cnt = c->d_cnt;
         ++g_launches; assemble_kernel<<<nblk(n, 128), 128, 0, st>>>(a);
+        CKS(dbg_sync(c, "assemble_kernel"));
         if (!ext) {
             CK(cudaMemsetAsync(c->tmax.p, 0, (size_t)(nout + 1) * 4, st));
             ++g_launches; kill_mark_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->kill_i.p, c->tmax.p);
@@ -1818,10 +1849,13 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
             // extended mode: raw per-entry kill/transfer (global ids); the cross-rank fix-up of :175-179 is the caller's
             CK(cudaMemcpyAsync(c->o_kill.p, c->kill_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(c->o_transfer.p, c->transfer_i.p, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st));
         }
+        CKS(dbg_sync(c, "kill fix-up"));
         if (nout > 0) { ++g_launches; fold_kernel<<<nblk(nout, 256), 256, 0, st>>>(nout, n, Nb, c->egid.p, c->gx_of.p, c->gy_of.p, c->osum.p, c->has_rows.p, c->o_fx.p, c->o_fy.p, c->o_tq.p); }
+        CKS(dbg_sync(c, "fold"));
         if (np > 0) { ++g_launches; pair_stats_kernel<<<std::min(nblk(np, 256), 148 * 8), 256, 0, st>>>(np, D_CNT(n_pairs), c->pstatus.p, c->pnrows.p, c->pi.p, c->eowned.p, 1, c->d_cnt); }
         if (wall) { ++g_launches; pair_stats_kernel<<<std::min(nblk(n, 256), 148 * 8), 256, 0, st>>>(n, nullptr, c->wstatus.p, c->wnrows.p, nullptr, c->eowned.p, 0, c->d_cnt); }
     }
+    CKS(dbg_sync(c, "assembly"));
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
     CKS(read_counters(c));
@@ -2289,6 +2323,48 @@ extern "C" int sz_slab_get_outputs(SzContext* c, double* fx, double* fy, double*
     CK(cudaMemcpyAsync(t.data(), o + 10 * N, 3 * N * 8, cudaMemcpyDefault, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < N; ++i) { if (alive) alive[i] = (uint8_t)t[i]; if (kill) kill[i] = (int32_t)t[N + i]; if (transfer) transfer[i] = (int32_t)t[2 * N + i]; }
+    return SZ_OK;
+}
+// slab mode: Floe(i).interactions of the OWNED floes, in their order, gathered on the device through the list positions
+__global__ void slab_rowcount_kernel(int n, const int* __restrict__ opos, const int* __restrict__ row_off, int* __restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int m = opos[i]; cnt[i] = row_off[m + 1] - row_off[m]; }
+}
+__global__ void __launch_bounds__(256) slab_rowcopy_kernel(int n, const int* __restrict__ opos, const int* __restrict__ row_off, const int* __restrict__ out_off,
+                                                           const double* __restrict__ rows, double* __restrict__ out)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int m = opos[i];
+    const size_t src = (size_t)row_off[m] * 7, dst = (size_t)out_off[i] * 7;
+    const int cnt = (row_off[m + 1] - row_off[m]) * 7;
+    for (int t = lane; t < cnt; t += 32) out[dst + t] = rows[src + t];
+}
+extern "C" int sz_slab_get_rows(SzContext* c, int64_t* row_off, double* rows, int64_t rows_cap, int64_t* n_rows)
+{
+    NEED_STEP("sz_slab_get_rows");
+    if (!c->slab) { sz_set_error("sz_slab_get_rows: slab mode only"); return SZ_ERR_STATE; }
+    const int n = c->n0; cudaStream_t st = c->stream;
+    if (n_rows) *n_rows = 0;
+    if (n == 0) { if (row_off) row_off[0] = 0; return SZ_OK; }
+    CK(c->sl_rcnt.ensure(n + 2)); CK(c->sl_roff.ensure(n + 2));
+    ++g_launches; slab_rowcount_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->sl_opos.p, c->row_off.p, c->sl_rcnt.p);
+    CKS(exclusive_scan(c, c->sl_rcnt.p, n, c->sl_roff.p, n + 1));
+    std::vector<int> off(n + 1);
+    CK(cudaMemcpyAsync(off.data(), c->sl_roff.p, (size_t)(n + 1) * 4, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    const i64 total = off[n];
+    if (n_rows) *n_rows = total;
+    if (row_off) for (int k = 0; k <= n; ++k) row_off[k] = off[k];
+    if (rows && total > 0) {
+        if (total > rows_cap) { sz_set_error("sz_slab_get_rows: %lld rows, room for %lld", (long long)total, (long long)rows_cap); return SZ_ERR_CAPACITY; }
+        CK(c->sl_rows.ensure((size_t)total * 7 + 7));
+        ++g_launches; slab_rowcopy_kernel<<<nblk(32 * (i64)n, 256), 256, 0, st>>>(n, c->sl_opos.p, c->row_off.p, c->sl_roff.p, c->rows.p, c->sl_rows.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(rows, c->sl_rows.p, (size_t)total * 56, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return SZ_OK;
 }
 extern "C" int sz_get_ghosts(SzContext* c, int32_t* parent, int32_t* floe_num, double* gx, double* gy)
