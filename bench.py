@@ -212,6 +212,87 @@ def verify_against_single_gpu(job, steps, rank, world, local_rank, dist):
     return res
 
 
+
+def run_real_shapes(args):
+    """Second workload (--workload real_shapes / real_shapes_raw), one GPU: the reference's own floe outlines
+    (test/test_conservation/FloeShapes.mat, 7..591 vertices, concave; decoded into tests/golden by tools/make_golden_floeshapes.py)
+    tiled into a periodic field -- `real_shapes`: thinned to <= 30 vertices, what FloeSimplify leaves in a production run
+    (Subzero.m:169-217; narrow-phase class T); `real_shapes_raw`: as they are (classes M and L).  Same JSON contract."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenarios
+    import subzero_b200 as sz
+    from subzero_b200 import abi
+    raw = args.workload == "real_shapes_raw"
+    n_side = args.tiles
+    prm, Floe = scenarios.real_shape_field(n_side, seed=args.seed, max_vertices=None if raw else 30)
+    soa = sz.floes_to_soa(Floe)
+    ctx = sz.ContactContext(0)
+    ctx.upload(prm, soa)
+    for _ in range(max(3, args.warmup)):
+        ctx.step_resident(allow_pair_errors=True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = abi.lib().sz_launch_count()
+    ms, cls_ms, cls_pairs = 0.0, {}, {}
+    for _ in range(args.steps):
+        s = ctx.step_resident(allow_pair_errors=True)
+        ms += s.ms_device
+        for k, (t, p) in ctx.narrow_class_ms().items():
+            cls_ms[k] = cls_ms.get(k, 0.0) + t
+            cls_pairs[k] = p
+    torch.cuda.synchronize()
+    launches = abi.lib().sz_launch_count() - l0
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    pinned = abi.FloesSoA(*(pin(getattr(soa, k)) for k in abi.FloesSoA.FIELDS), pin(soa.alive), pin(soa.voff), pin(soa.vx), pin(soa.vy))
+    h2d = sum(getattr(pinned, k).nbytes for k in abi.FloesSoA.FIELDS) + pinned.alive.nbytes + pinned.voff.nbytes + pinned.vx.nbytes + pinned.vy.nbytes
+    e2e_t, d2h = 0.0, 0
+    for it in range(4):
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        ctx.step(prm, pinned, allow_pair_errors=True)
+        o = ctx.floe_outputs()
+        off, rows = ctx.rows()
+        dt = time.perf_counter() - w0
+        if it:
+            e2e_t += dt
+        d2h = sum(v.nbytes for v in o.values()) + off.nbytes + rows.nbytes
+    e2e_ms = 1e3 * e2e_t / 3
+    top = max(cls_ms, key=lambda k: cls_ms[k])
+    peak, peak_src = load_peaks()
+    nv_mean = soa.vx.shape[0] / max(1, soa.n)
+    alg = cls_pairs[top] * (2 * nv_mean * 16 + 2 * 72 + 8) + s.n_rows * 56 * (cls_pairs[top] / max(1, s.n_pairs))
+    kms = cls_ms[top] / args.steps
+    line = {"metric": METRIC, "value": s.n_pairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
+            "config": {"workload": "%s: %d x %d tiles of the reference's FloeShapes.mat outlines%s, periodic, contact loop only" % (args.workload, n_side, n_side, "" if raw else " thinned to <= 30 vertices"),
+                       "floes": soa.n, "floes_incl_ghosts": int(s.n), "pairs_per_step": int(s.n_pairs), "pairs_with_force": int(s.n_pairs_force), "rows_per_step": int(s.n_rows),
+                       "vertices_per_outline_mean": nv_mean, "class_pairs": cls_pairs, "class_ms": {k: v / args.steps for k, v in cls_ms.items()},
+                       "l2": "the same field every step; the per-pair arenas (class T: 35 KB of local memory per thread, M/L: HBM scratch) exceed L2", "seed": args.seed},
+            "clocks": clocks, "e2e": {"value": s.n_pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": 3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "narrow phase class %s (general Clipper-exact sweep + force law, thread per pair)" % top, "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kms, "kernel_pairs_per_launch": cls_pairs[top],
+                         "note": "latency-bound sequential sweep per pair; no ncu capture for this workload"}}
+    if not args.no_cpu:
+        import oracle
+        threads = max(1, oracle.lib().szo_hardware_threads())
+        p, dt = 0, 0.0
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = oracle.OracleStep(prm, soa, nthreads=threads, broad_mode=1)
+            dt += time.perf_counter() - t0
+            p += r.summary.n_pairs
+        line["cpu_baseline"] = {"value": p / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "the same field, 2 whole contact steps (%.1f s on %d threads); oracle = C++ restatement of the MATLAB path calling the reference's unmodified Clipper 6.4.2" % (dt, threads)}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -224,6 +305,9 @@ def main():
                     help="after the timed region, run STEPS coupled steps (contact step + integrator, nonzero ksi, thinning) and compare every rank's per-floe outputs, contact rows and "
                          "integrated state with a single-GPU run of the same field bit for bit; prints parity in the line.  Default: 20 at N > 1, off at N = 1")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--workload", default="voronoi", choices=["voronoi", "real_shapes", "real_shapes_raw"],
+                    help="voronoi (default): BASELINE.json configs[4], the headline; real_shapes / real_shapes_raw: the reference's own concave floe outlines tiled (one GPU)")
+    ap.add_argument("--tiles", type=int, default=120, help="real_shapes: tiles per side (120 -> 14,400 floes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="run-time switch of the library (sz_set_option), e.g. convex_split=1; experiments only, recorded in config")
@@ -237,6 +321,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "voronoi":
+        if rank == 0:
+            run_real_shapes(args)
         return
 
     import numpy as np

@@ -437,12 +437,7 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
                     j = b.s_idx[t];
                     if (j > i && (own_i || b.eowned[j])) {     // a pair is resolved where either floe is owned
                         const double dx = xi - b.s_x[t], dy = yi - b.s_y[t], rs = ri + b.s_r[t];
-                        // sqrt((xi-xj)^2+(yi-yj)^2) < rmax_i+rmax_j (:103).  The square root is only taken when the squares are
-                        // within 1e-12 of each other: further apart, the correctly rounded root cannot land on the other side
-                        // of rs (its relative distance from rs is > 4e-13, four thousand ulps)
-                        const double d2 = dx * dx + dy * dy, r2 = rs * rs;
-                        const bool near = d2 < r2 * (1 - 1e-12) ? true : (d2 > r2 * (1 + 1e-12) ? false : sqrt(d2) < rs);
-                        if (near) {
+                        if (sqrt(dx * dx + dy * dy) < rs) {
                             ok = true;
                             if (b.efn[j] < 0 && ghost_is_member(b, i, j) && !(2 * rs > b.minL2)) ok = false;
                         }

@@ -9,6 +9,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# Fresh device buffers of the library start as 0x7F.. instead of whatever the allocator hands out (read once, at the first
+# allocation): a kernel that reads something it never wrote fails the same way on every box, not only behind an unlucky test
+os.environ.setdefault("SZ_DEBUG_POISON", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
