@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--workload", default="voronoi", choices=["voronoi", "real_shapes", "real_shapes_raw"],
                     help="voronoi (default): BASELINE.json configs[4], the headline; real_shapes / real_shapes_raw: the reference's own concave floe outlines tiled (one GPU)")
-    ap.add_argument("--tiles", type=int, default=120, help="real_shapes: tiles per side (120 -> 14,400 floes)")
+    ap.add_argument("--tiles", type=int, default=240, help="real_shapes: tiles per side (240 -> 57,600 floes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="run-time switch of the library (sz_set_option), e.g. convex_split=1; experiments only, recorded in config")

@@ -1606,7 +1606,7 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class M: %d pairs on %d threads, %.2f ms\n", nM, threads, dms); }
         int nL = wall ? c->h_cnt->wlistL : c->h_cnt->listL;
         if (nL > 0) {
-            static const int l_tpsm = getenv("SZ_L_TPSM") ? atoi(getenv("SZ_L_TPSM")) : 32;    // class L (1.1 MB each)
+            static const int l_tpsm = getenv("SZ_L_TPSM") ? atoi(getenv("SZ_L_TPSM")) : 128;   // class L (1.1 MB of HBM scratch each: 21 GB at most; more threads in flight, fewer rounds)
             const int threadsL = std::min((nL + 63) / 64 * 64, 148 * l_tpsm);
             CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
             a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;

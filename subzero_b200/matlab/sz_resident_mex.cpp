@@ -298,5 +298,37 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         plhs[0] = out;
         return;
     }
+    if (cmd == "weld_search" || cmd == "simplify_search") {
+        // the bounding-radius pair searches of weld.m:29-81 / FloeSimplify.m:13-31 on the resident floes (sz_pair_search):
+        //   w = sz_resident_mex('weld_search', struct('Nb',Nb,'Nx',Nx,'Ny',Ny,'xmin',min(x),'xmax',max(x),'ymin',min(y),'ymax',max(y)))
+        //       w.bin (bin number of every floe of Floe(1+Nb:end), 0 = none), w.off, w.partner (1-based positions in that cut list)
+        //   s = sz_resident_mex('simplify_search', idx)        s.off, s.partner (1-based positions in the resident list)
+        const bool weld = cmd == "weld_search";
+        if (nrhs < 2) mexErrMsgIdAndTxt("subzero_b200:arg", "usage: sz_resident_mex('weld_search', g) / sz_resident_mex('simplify_search', idx)");
+        int64_t np = 0; size_t nq = 0;
+        if (weld) {
+            const int Nb = (int)scalar_field(prhs[1], "Nb", 0, false), Nx = (int)scalar_field(prhs[1], "Nx", 0, true), Ny = (int)scalar_field(prhs[1], "Ny", 0, true);
+            check(sz_pair_search(g_ctx, 0, Nb, Nx, Ny, scalar_field(prhs[1], "xmin", 0, true), scalar_field(prhs[1], "xmax", 0, true), scalar_field(prhs[1], "ymin", 0, true),
+                                 scalar_field(prhs[1], "ymax", 0, true), 0, nullptr, &np));
+            nq = g_n > (size_t)Nb ? g_n - (size_t)Nb : 0;
+        } else {
+            nq = mxGetNumberOfElements(prhs[1]);
+            const double* id = need_array(prhs[1], nq, "idx");
+            std::vector<int32_t> idx(nq);
+            for (size_t k = 0; k < nq; ++k) idx[k] = (int32_t)id[k];
+            check(sz_pair_search(g_ctx, 1, 0, 1, 1, 0, 1, 0, 1, (int32_t)nq, idx.data(), &np));
+        }
+        std::vector<int32_t> bin(nq + 1), partner((size_t)np + 1); std::vector<int64_t> off(nq + 1);
+        check(sz_get_pair_search(g_ctx, bin.data(), off.data(), partner.data()));
+        const char* names[] = {"bin", "off", "partner"};
+        mxArray* out = mxCreateStructMatrix(1, 1, 3, names);
+        mxArray *vb = vec(nq), *vo = vec(nq + 1), *vp = vec((size_t)np);
+        for (size_t k = 0; k < nq; ++k) mxGetPr(vb)[k] = bin[k];
+        for (size_t k = 0; k <= nq; ++k) mxGetPr(vo)[k] = (double)off[k];
+        for (size_t k = 0; k < (size_t)np; ++k) mxGetPr(vp)[k] = partner[k];
+        mxSetFieldByNumber(out, 0, 0, vb); mxSetFieldByNumber(out, 0, 1, vo); mxSetFieldByNumber(out, 0, 2, vp);
+        plhs[0] = out;
+        return;
+    }
     mexErrMsgIdAndTxt("subzero_b200:arg", "unknown command '%s'", cmdbuf);
 }
