@@ -373,7 +373,13 @@ def main():
     pairs_local = job.pairs_owned
     t = torch.tensor([dev_ms, wall_ms, narrow_ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([pairs_local, job.rows_owned, launches, job.pairs_force_total, job.ext_entries_owned], dtype=torch.float64, device="cuda")
+    per_rank = None
     if dist is not None:
+        # every rank's own numbers (the step time is the slowest rank's): device ms per step, contact step alone, narrow phase, owned pairs
+        mine = torch.tensor([dev_ms / args.steps, ph["total"], ph["narrow"], float(pairs_local)], dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 4) for v in r.tolist()] for r in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms, narrow_ms = [float(v) for v in t.tolist()]
@@ -447,7 +453,7 @@ def main():
                            "floes_incl_ghosts": total_ext, "pairs_per_step": total_pairs, "pairs_with_force": total_force,
                            "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "timesteps_per_s_with_trajectory_update": ts_with_ab2, "parallelism": job.describe(),
                            "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed, "floe_order": args.floe_order, "options": args.opt,
-                           "wall_ms_per_step": wall_ms / args.steps, "phase_ms_rank0": phase_last,
+                           "wall_ms_per_step": wall_ms / args.steps, "phase_ms_rank0": phase_last, "per_rank_ms_step_contact_narrow_pairs": per_rank,
                            "slab_stage_ms_rank0": (job.slab.stage_ms() if job.slab is not None else None)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},

@@ -20,9 +20,10 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 open(os.path.join(R, 'profiles', '%s_launches_1M_summary.txt' % tag), 'w').write('\n'.join(out) + '\n')
 import shutil; shutil.copy(launch_csv, os.path.join(R, 'profiles', '%s_launches_1M.csv' % tag))
 print('\n'.join(out[:8]))
-subprocess.run([sys.executable, os.path.join(R, 'tools', 'ncu_summary.py'), rep, '40'], stdout=open(os.path.join(R, 'profiles', '%s_narrow_C_1M.txt' % tag), 'w'))
+subprocess.run([sys.executable, os.path.join(R, 'tools', 'ncu_summary.py'), rep, '40'], stdout=open(os.path.join(R, 'profiles', '%s_top_kernels_1M.txt' % tag), 'w'))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-r = list(csv.reader(io.StringIO(raw))); Hh, U, V = r[0], r[1], r[2]
+r = list(csv.reader(io.StringIO(raw))); Hh, U = r[0], r[1]
+V = next((row for row in r[2:] if "narrow_convex_kernel" in row[Hh.index("Kernel Name")]), r[2])      # the class C launch of a multi-kernel capture
 g = lambda n: (float(V[Hh.index(n)].replace(',', '')), U[Hh.index(n)])
 mul = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'Tbyte': 1e12}
 rd, ru = g('dram__bytes_read.sum'); wr, wu = g('dram__bytes_write.sum'); t, tu = g('gpu__time_duration.sum')
@@ -30,5 +31,5 @@ tms = t if tu == 'ms' else t / 1e3 if tu == 'us' else t * 1e3 if tu == 's' else 
 sys.path.insert(0, R)
 from subzero_b200.build import kernel_stamp
 d = {"kernel": "narrow_convex_kernel<PairS>", "kernel_stamp": kernel_stamp(), "workload": "bench.py default (1M floes, 1 GPU)", "dram_bytes_per_launch": rd * mul[ru] + wr * mul[wu], "dram_read": rd * mul[ru],
-     "dram_write": wr * mul[wu], "gpu_time_ms_under_ncu": tms, "dram_gb_per_s": (rd * mul[ru] + wr * mul[wu]) / tms / 1e6, "source": "profiles/%s_narrow_C_1M.txt (ncu --set full, one launch)" % tag}
+     "dram_write": wr * mul[wu], "gpu_time_ms_under_ncu": tms, "dram_gb_per_s": (rd * mul[ru] + wr * mul[wu]) / tms / 1e6, "source": "profiles/%s_top_kernels_1M.txt (ncu --set full, one launch per kernel)" % tag}
 json.dump(d, open(os.path.join(R, 'profiles', 'narrow_traffic.json'), 'w'), indent=1); print(json.dumps(d))
