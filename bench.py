@@ -309,6 +309,7 @@ def main():
                     help="voronoi (default): BASELINE.json configs[4], the headline; real_shapes / real_shapes_raw: the reference's own concave floe outlines tiled (one GPU)")
     ap.add_argument("--tiles", type=int, default=240, help="real_shapes: tiles per side (240 -> 57,600 floes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch every kernel and collective of a step from the host instead of replaying the step's CUDA graph")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="run-time switch of the library (sz_set_option), e.g. convex_split=1; experiments only, recorded in config")
     ap.add_argument("--floe-order", default="site", choices=["site", "morton"],
@@ -338,7 +339,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from subzero_b200 import slabs
-    job = slabs.SlabJob(args.floes, args.seed, rank, world, local_rank, dist, order=args.floe_order)
+    job = slabs.SlabJob(args.floes, args.seed, rank, world, local_rank, dist, order=args.floe_order, graph=not args.no_graph)
     for o in args.opt:
         name, _, val = o.partition("=")
         job.ctx.set_option(name.strip(), int(val or 1))
@@ -454,7 +455,8 @@ def main():
                            "rows_per_step": total_rows, "timesteps_per_s": 1e3 / ms_per_step, "timesteps_per_s_with_trajectory_update": ts_with_ab2, "parallelism": job.describe(),
                            "l2": "inputs larger than L2 (state + vertex pool + pair buffers >> 126 MB at 1M floes); no flush", "seed": args.seed, "floe_order": args.floe_order, "options": args.opt,
                            "wall_ms_per_step": wall_ms / args.steps, "phase_ms_rank0": phase_last, "per_rank_ms_step_contact_narrow_pairs": per_rank,
-                           "slab_stage_ms_rank0": (job.slab.stage_ms() if job.slab is not None else None)},
+                           "slab_stage_ms_rank0": (job.slab.stage_ms() if job.slab is not None else None),
+                           "cuda_graph": (None if job.slab is None else {"enabled": job.slab.want_graph, "replays": job.slab.graph_replays, "launches_per_replay": job.slab.graph_launches})},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": launches,

@@ -126,6 +126,16 @@ int sz_contact_step(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes
 /* ---- split form for device-resident state: upload once, step many times ---- */
 int sz_upload(SzContext* ctx, const SzParams* prm, const SzFloesSoA* floes, const SzBoundary* bnd);
 int sz_step_resident(SzContext* ctx, SzSummary* out);
+/* The same step in two halves, for callers that keep the host out of the loop (a CUDA graph of the whole step, NCCL calls
+ * included; software pipelining): sz_step_enqueue launches the step on carried-over sizes (option "speculate"; fails with
+ * SZ_ERR_STATE until one sz_step_resident has run) and queues the copy of the counters, without any host synchronisation;
+ * sz_step_finish waits for the stream, validates the step and fills the summary.  It returns 1 (not an error) when a carried-over
+ * size was too small: nothing was consumed, run sz_step_resident on the unchanged state.  With option "graph_safe" set, nothing
+ * the enqueue half launches depends on host state of the call (no event timing, scans reset their own state), so the launches
+ * can be captured once and replayed.  sz_add_launches credits replayed launches to sz_launch_count. */
+int sz_step_enqueue(SzContext* ctx);
+int sz_step_finish(SzContext* ctx, SzSummary* out);
+void sz_add_launches(long long n);
 
 /* ---- caller-supplied extended list (any host that builds its own list; the multi-GPU path below builds it on the device).
  * One record of `floes` per entry (originals and periodic images this rank owns, plus halo entries received from
@@ -353,6 +363,7 @@ int sz_set_stream(SzContext* ctx, void* cuda_stream);
  *                  end of the step; a step that outgrew a capacity, or needs a larger narrow-phase size class, is flagged on
  *                  the device and repeated with measured sizes.  0: measure every size as it is needed (four counter reads).
  *                  Results are identical either way (tests/test_gpu_parity.py).
+ *   "graph_safe"    0 (default); 1: see sz_step_enqueue.
  * Returns SZ_ERR_ARG for an unknown name. */
 int sz_set_option(SzContext* ctx, const char* name, int32_t value);
 /* counters of the context: "speculated_steps" (steps that ran on carried-over sizes), "repeated_steps" (steps that had to be

@@ -89,6 +89,9 @@ PROTOTYPES = {
     "sz_slab_get_list": (C.c_int, [C.c_void_p, c_ip, c_ip, c_bp, c_dp, c_dp]),
     "sz_slab_get_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_step_resident": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
+    "sz_step_enqueue": (C.c_int, [C.c_void_p]),
+    "sz_step_finish": (C.c_int, [C.c_void_p, C.POINTER(SzSummary)]),
+    "sz_add_launches": (None, [C.c_longlong]),
     "sz_get_floe_outputs": (C.c_int, [C.c_void_p] + [c_dp] * 7 + [c_bp, c_ip, c_ip]),
     "sz_get_ghosts": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp, c_dp]),
     "sz_get_ghost_outputs": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp]),

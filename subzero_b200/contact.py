@@ -66,6 +66,18 @@ class ContactContext:
         code = abi.lib().sz_step_resident(self._h, C.byref(s))
         return self._finish(code, s, allow_pair_errors)
 
+    def step_enqueue(self):
+        """launch the step without waiting for it (sizes carried over from the step before); step_finish() completes it"""
+        abi.check(abi.lib().sz_step_enqueue(self._h))
+
+    def step_finish(self, allow_pair_errors=False):
+        """returns the summary, or None when the enqueued step has to be repeated with step_resident()"""
+        s = SzSummary()
+        code = abi.lib().sz_step_finish(self._h, C.byref(s))
+        if code == 1:
+            return None
+        return self._finish(code, s, allow_pair_errors)
+
     # ---- results
     def floe_outputs(self, into=None):
         n = self._n0

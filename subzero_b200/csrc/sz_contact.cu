@@ -105,6 +105,8 @@ struct SzContext {
     cudaEvent_t evk[10] = {};                  // start/stop of the narrow-phase launch of each size class (C, S, T, M, L)
     bool evk_used[5] = {false, false, false, false, false}; int class_pairs[5] = {0, 0, 0, 0, 0};
     int opt_convex_fast = 1;
+    int opt_graph_safe = 0;          // the step may be captured into a CUDA graph: no host-carried scan state, no event timing in sz_step_enqueue
+    struct { bool active = false; int n = 0, np = 0; long long rows_bound = 0; } pend; bool enq_mode = false;      // a step enqueued by sz_step_enqueue and not finished yet
     int opt_speculate = 1;           // sizes of the step (list, grid, pairs, rows) carried over from the previous step: one counter read per step instead of four
     bool plan_valid = false; int plan_n0 = -1, plan_nl0 = -1, plan_ncap = 0, plan_npcap = 0; long long plan_rowscap = 0; struct GridDescHost { double x0, y0, cell; int nx, ny; } plan_g = {0, 0, 1, 1, 1};
     int n_fast_steps = 0, n_slow_steps = 0;
@@ -244,7 +246,17 @@ static int exclusive_scan(SzContext* c, const int* in, int n_in, int* out, int n
         CK(cudaMemset(c->scan_state.p, 0, c->scan_state.cap * 8));
         c->scan_ticket_base = 0; c->scan_epoch = 0;
     }
-    if (++c->scan_epoch >= (1u << 24)) { CK(cudaMemsetAsync(c->scan_state.p + 1, 0, (c->scan_state.cap - 1) * 8, c->stream)); c->scan_epoch = 1; }
+    if (c->opt_graph_safe) {
+        // a launch that may be replayed from a CUDA graph cannot carry the host's ticket base and epoch: it resets the ticket
+        // and the status words it is going to use instead (one small memset node)
+        CK(cudaMemsetAsync(c->scan_state.p, 0, ((size_t)tiles + 1) * 8, c->stream));
+        ++g_launches;
+        scan_lookback_kernel<<<tiles, SCAN_TPB, 0, c->stream>>>(in, n_in, out, n_out, c->scan_state.p + 1, c->scan_state.p, 0ULL, 0xFFFFFFu);
+        c->scan_ticket_base = 0; c->scan_epoch = 0;      // (the next ordinary launch starts from a clean array: epoch 0xFFFFFF words are stale for it)
+        CK(cudaMemsetAsync(c->scan_state.p, 0, 8, c->stream));      // (the ticket)
+        return SZ_OK;
+    }
+    if (++c->scan_epoch >= (1u << 24) - 1) { CK(cudaMemsetAsync(c->scan_state.p + 1, 0, (c->scan_state.cap - 1) * 8, c->stream)); c->scan_epoch = 1; }
     ++g_launches;
     scan_lookback_kernel<<<tiles, SCAN_TPB, 0, c->stream>>>(in, n_in, out, n_out, c->scan_state.p + 1, c->scan_state.p, c->scan_ticket_base, c->scan_epoch);
     c->scan_ticket_base += (u64)tiles;
@@ -1552,7 +1564,7 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         const bool no_fast = env_no_fast || !c->opt_convex_fast;
         a.list = c->listC.p; a.list_count = D_CNT(listC); a.next_list = c->listS.p; a.next_count = D_CNT(listS);
         CK(cudaMemcpyAsync(D_CNT(listC0), D_CNT(listC), 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(D_CNT(listS0), D_CNT(listS), 4, cudaMemcpyDeviceToDevice, st));
-        CK(cudaEventRecord(c->evk[0], st));
+        if (!c->enq_mode) CK(cudaEventRecord(c->evk[0], st));
         static const bool env_split = getenv("SZ_CONVEX_SPLIT") != nullptr;
         if (!no_fast && (c->opt_convex_split || env_split)) {
             enum { HO_CAP = 16 };                       // a larger intersection polygon sends the pair to class S
@@ -1562,12 +1574,12 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         } else
         if (!no_fast) { ++g_launches; sz_launch_narrow_C(&a, st); CK(cudaGetLastError()); }
         else { a.list = c->listC.p; a.next_list = lstT; a.next_count = cntT; ++g_launches; sz_launch_narrow_S(&a, st); CK(cudaGetLastError()); }
-        CK(cudaEventRecord(c->evk[1], st)); c->evk_used[0] = true;
+        if (!c->enq_mode) CK(cudaEventRecord(c->evk[1], st)); c->evk_used[0] = !c->enq_mode;
         a.list = c->listS.p; a.list_count = D_CNT(listS); a.next_list = lstT; a.next_count = cntT;
     }
-    if (!wall) CK(cudaEventRecord(c->evk[2], st));
+    if (!wall) if (!c->enq_mode) CK(cudaEventRecord(c->evk[2], st));
     ++g_launches; sz_launch_narrow_S(&a, st);
-    if (!wall) { CK(cudaEventRecord(c->evk[3], st)); c->evk_used[1] = true; }
+    if (!wall) { if (!c->enq_mode) CK(cudaEventRecord(c->evk[3], st)); c->evk_used[1] = !c->enq_mode; }
     a.list = nullptr; a.list_count = nullptr;
     CK(cudaGetLastError());
     // speculative step: the lists of the larger size classes were empty last step; whether they still are is checked with the
@@ -1579,9 +1591,9 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
     if (nT > 0) {
         // class T: pairs that did not fit class S, arena still in local memory
         a.list = lstT; a.list_count = cntT; a.n_work = nT; a.next_list = lstM; a.next_count = cntM;
-        if (!wall) { CK(cudaEventRecord(c->evk[4], st)); c->class_pairs[2] = nT; }
+        if (!wall) { if (!c->enq_mode) CK(cudaEventRecord(c->evk[4], st)); c->class_pairs[2] = nT; }
         ++g_launches; sz_launch_narrow_T(&a, st);
-        if (!wall) { CK(cudaEventRecord(c->evk[5], st)); c->evk_used[2] = true; }
+        if (!wall) { if (!c->enq_mode) CK(cudaEventRecord(c->evk[5], st)); c->evk_used[2] = !c->enq_mode; }
         a.list = nullptr; a.list_count = nullptr;
         CK(cudaGetLastError());
         CKS(read_counters(c));
@@ -1597,10 +1609,10 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
         a.list = lstM; a.list_count = cntM; a.next_list = lstL; a.next_count = cntL; a.scratch = c->scratchM.p; a.n_threads = threads;
         if (dbg) cudaEventRecord(d0, st);
-        if (!wall) { CK(cudaEventRecord(c->evk[6], st)); c->class_pairs[3] = nM; }
+        if (!wall) { if (!c->enq_mode) CK(cudaEventRecord(c->evk[6], st)); c->class_pairs[3] = nM; }
         ++g_launches; sz_launch_narrow_M(&a, st);
         CK(cudaGetLastError());
-        if (!wall) { CK(cudaEventRecord(c->evk[7], st)); c->evk_used[3] = true; }
+        if (!wall) { if (!c->enq_mode) CK(cudaEventRecord(c->evk[7], st)); c->evk_used[3] = !c->enq_mode; }
         if (dbg) cudaEventRecord(d1, st);
         CKS(read_counters(c));
         if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class M: %d pairs on %d threads, %.2f ms\n", nM, threads, dms); }
@@ -1611,10 +1623,10 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
             CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
             a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
             if (dbg) cudaEventRecord(d0, st);
-            if (!wall) { CK(cudaEventRecord(c->evk[8], st)); c->class_pairs[4] = nL; }
+            if (!wall) { if (!c->enq_mode) CK(cudaEventRecord(c->evk[8], st)); c->class_pairs[4] = nL; }
             ++g_launches; sz_launch_narrow_L(&a, st);
             CK(cudaGetLastError());
-            if (!wall) { CK(cudaEventRecord(c->evk[9], st)); c->evk_used[4] = true; }
+            if (!wall) { if (!c->enq_mode) CK(cudaEventRecord(c->evk[9], st)); c->evk_used[4] = !c->enq_mode; }
             if (dbg) cudaEventRecord(d1, st);
             CKS(read_counters(c));
             if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class L: %d pairs on %d threads, %.2f ms\n", nL, threadsL, dms); }
@@ -1644,11 +1656,16 @@ static GridDesc make_grid(const Counters* h, int n)
     return g;
 }
 
-extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
+static int step_finish(SzContext* c, SzSummary* out, int n, int np, i64 rows_bound, bool fast, bool enqueued, float ms);
+// mode 0: the whole step; mode 1: enqueue only (speculated sizes required), the counters travel to the host asynchronously
+// and sz_step_finish completes the step
+static int step_impl(SzContext* c, SzSummary* out, int mode)
 {
     if (!c) { sz_set_error("sz_step_resident: NULL context"); return SZ_ERR_ARG; }
     if (!c->have_input) { sz_set_error("sz_step_resident: no floes uploaded"); return SZ_ERR_STATE; }
     CK(cudaSetDevice(c->device));
+    const bool enq = mode == 1;
+    c->pend.active = false; c->enq_mode = enq;
     cudaStream_t st = c->stream;
     const SzParams& P = c->prm;
     const int n0 = c->n0, Nb = P.Nb;
@@ -1657,7 +1674,9 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     const int nl0 = slab ? c->sl_nl_cap : n0;                    // length of a caller-supplied / device-built extended list (its tail may be inert)
     const int ncap = (P.periodic && !ext) ? 4 * n0 : nl0;        // every floe has at most an x-, a y- and an xy-ghost
     c->have_step = false; c->have_rows = false;
-    CK(cudaEventRecord(c->ev0, st));
+    const bool fast = c->opt_speculate && c->plan_valid && c->plan_n0 == n0 && c->plan_nl0 == nl0 && !P.want_clip_polys && c->plan_ncap <= ncap;
+    if (enq && !fast) { sz_set_error("sz_step_enqueue: no sizes to carry over yet (run sz_step_resident first; not with want_clip_polys)"); return SZ_ERR_STATE; }
+    if (!enq) CK(cudaEventRecord(c->ev0, st));
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
 
     // ---- K0: extended list
@@ -1707,7 +1726,6 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     // Speculative step: list length, grid, pair and row capacities come from the previous step (with slack), every kernel
     // takes the true counts from device memory, and the host reads the counters ONCE, at the end; a step whose counts
     // outgrew a capacity (or that needs a larger size class) raises a flag there and is repeated on the synchronous path.
-    const bool fast = c->opt_speculate && c->plan_valid && c->plan_n0 == n0 && c->plan_nl0 == nl0 && !P.want_clip_polys && c->plan_ncap <= ncap;
     int n;
     if (fast) {
         n = slab ? nl0 : c->plan_ncap;
@@ -1719,7 +1737,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     c->n = n;
 
     CKS(dbg_sync(c, fast ? "K0 (speculated)" : "K0"));
-    CK(cudaEventRecord(c->evp[0], st));
+    if (!enq) CK(cudaEventRecord(c->evp[0], st));
     // ---- K1: cell grid + candidate pairs
     GridDesc g;
     if (fast) { g.x0 = c->plan_g.x0; g.y0 = c->plan_g.y0; g.cell = c->plan_g.cell; g.nx = c->plan_g.nx; g.ny = c->plan_g.ny; }
@@ -1763,7 +1781,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CKS(dbg_sync(c, "ext_prep + broad fill"));
-    CK(cudaEventRecord(c->evp[1], st));
+    if (!enq) CK(cudaEventRecord(c->evp[1], st));
     CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
@@ -1802,7 +1820,7 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     }
 
     CKS(dbg_sync(c, "narrow phase"));
-    CK(cudaEventRecord(c->evp[2], st));
+    if (!enq) CK(cudaEventRecord(c->evp[2], st));
     // ---- K4: mirror, rows, sums
     CK(c->tcnt.ensure(n + 2)); CK(c->toff.ensure(n + 2)); CK(c->tlist.ensure(np + 1)); CK(c->rcnt.ensure(n + 2)); CK(c->row_off.ensure(n + 2));
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
@@ -1851,19 +1869,33 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
         if (wall) { ++g_launches; pair_stats_kernel<<<std::min(nblk(n, 256), 148 * 8), 256, 0, st>>>(n, nullptr, c->wstatus.p, c->wnrows.p, nullptr, c->eowned.p, 0, c->d_cnt); }
     }
     CKS(dbg_sync(c, "assembly"));
-    CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
+    if (enq) {
+        CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDefault, st));
+        c->pend.active = true; c->pend.n = n; c->pend.np = np; c->pend.rows_bound = rows_bound;
+        return SZ_OK;
+    }
+    CK(cudaEventRecord(c->ev1, st));
     CKS(read_counters(c));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     CK(cudaEventElapsedTime(&c->phase_ms[0], c->ev0, c->evp[0])); CK(cudaEventElapsedTime(&c->phase_ms[1], c->evp[0], c->evp[1]));
     CK(cudaEventElapsedTime(&c->phase_ms[2], c->evp[1], c->evp[2])); CK(cudaEventElapsedTime(&c->phase_ms[3], c->evp[2], c->ev1)); c->phase_ms[4] = ms;
-
+    return step_finish(c, out, n, np, rows_bound, fast, false, ms);
+}
+// the host half of a step: the counters are in h_cnt; validates a speculated step, records what the next one may assume, fills the summary.
+// Returns 1 when an ENQUEUED step has to be repeated (the caller runs sz_step_resident on the unchanged state).
+static int step_finish(SzContext* c, SzSummary* out, int n, int np, i64 rows_bound, bool fast, bool enqueued, float ms)
+{
+    const SzParams& P = c->prm;
+    const int n0 = c->n0; const bool ext = c->ext_mode, slab = c->slab;
+    const int nl0 = slab ? c->sl_nl_cap : n0;
+    const int ncap = (P.periodic && !ext) ? 4 * n0 : nl0;
     {
         const Counters& H = *c->h_cnt;
         const bool big_lists = H.listT || H.listM || H.listL || H.wlistT || H.wlistM || H.wlistL;
         if (fast) {
             const bool bad = H.overflow || H.n > n || H.n_pairs > np || (size_t)H.row_used * 5 > c->row_pool.cap || (i64)H.total_rows > rows_bound || big_lists;
-            if (bad) { c->plan_valid = false; ++c->n_slow_steps; return sz_step_resident(c, out); }      // nothing was consumed: the same step again, with measured sizes
+            if (bad) { c->plan_valid = false; ++c->n_slow_steps; if (enqueued) return 1; return step_impl(c, out, 0); }      // nothing was consumed: the same step again, with measured sizes
             ++c->n_fast_steps;
             c->class_pairs[0] = H.listC0; c->class_pairs[1] = H.listS;
             if (!slab) c->n = H.n;
@@ -1894,6 +1926,20 @@ extern "C" int sz_step_resident(SzContext* c, SzSummary* out)
     return SZ_OK;
 }
 
+extern "C" int sz_step_resident(SzContext* c, SzSummary* out) { return step_impl(c, out, 0); }
+extern "C" int sz_step_enqueue(SzContext* c) { return step_impl(c, nullptr, 1); }
+extern "C" int sz_step_finish(SzContext* c, SzSummary* out)
+{
+    if (!c) { sz_set_error("sz_step_finish: NULL context"); return SZ_ERR_ARG; }
+    // (the enqueued launches may have been captured into a CUDA graph and replayed: the sizes they carry stay valid until an
+    // ordinary step or an upload replaces them)
+    if (!c->pend.active) { sz_set_error("sz_step_finish: no enqueued step"); return SZ_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 5; ++k) c->phase_ms[k] = 0;
+    return step_finish(c, out, c->pend.n, c->pend.np, c->pend.rows_bound, true, true, 0.0f);
+}
+extern "C" void sz_add_launches(long long n) { g_launches += n; }
 extern "C" int sz_contact_step(SzContext* c, const SzParams* prm, const SzFloesSoA* f, const SzBoundary* bnd, SzSummary* out)
 {
     int r = sz_upload(c, prm, f, bnd);
@@ -2450,6 +2496,7 @@ extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
     if (!c || !name) { sz_set_error("sz_set_option: NULL argument"); return SZ_ERR_ARG; }
     if (strcmp(name, "convex_fast") == 0) { c->opt_convex_fast = value != 0; return SZ_OK; }
     if (strcmp(name, "convex_split") == 0) { c->opt_convex_split = value != 0; return SZ_OK; }
+    if (strcmp(name, "graph_safe") == 0) { c->opt_graph_safe = value != 0; return SZ_OK; }
     if (strcmp(name, "speculate") == 0) { c->opt_speculate = value != 0; c->plan_valid = false; return SZ_OK; }
     if (strcmp(name, "euler_cell_warp") == 0) { c->opt_euler_cell_warp = value != 0; return SZ_OK; }
     sz_set_error("sz_set_option: unknown option '%s'", name);

@@ -394,8 +394,11 @@ class DeviceSlab:
         import os
         self.timing = {"ms": [0.0] * 7, "n": 0} if os.environ.get("SZ_SLAB_TIMING") else None
         self.dev = torch.device(comm.device) if comm.device is not None else torch.device("cuda", torch.cuda.current_device())
-        # the library launches on torch's current stream: its kernels and the collectives are ordered by the stream alone
-        ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        # One stream for everything of a step: the library launches there and torch's collectives are issued there, so kernels
+        # and collectives are ordered by the stream alone.  Under gloo (host-staged tests) it is torch's current stream.
+        self.stream = torch.cuda.Stream(self.dev) if (comm.world > 1 and not comm.stage) else torch.cuda.current_stream(self.dev)
+        ctx.set_stream(self.stream.cuda_stream)
+        self.graph, self.want_graph, self.graph_launches, self.graph_replays = None, False, 0, 0
         self.upload(owned, gid)
 
     # ---- state
@@ -405,7 +408,8 @@ class DeviceSlab:
         assert self.gid.shape[0] == owned.n and (owned.n < 2 or np.all(np.diff(self.gid) > 0)), "global floe numbers must ascend"
         fs = owned.struct()
         bs = self.bnd.struct() if self.bnd is not None else None
-        torch.cuda.current_stream(self.dev).synchronize()
+        self.graph = None
+        self.stream.synchronize()
         abi.check(abi.lib().sz_slab_upload(self.ctx._h, C.byref(self.prm), C.byref(fs), C.byref(bs) if bs is not None else None, abi._ptr(self.gid, abi.c_ip),
                                            self.n_global, self.comm.rank, self.comm.world))
         self.ctx._n0 = owned.n
@@ -417,6 +421,7 @@ class DeviceSlab:
     def plan(self, grow=1.0):
         """measure what the current state needs, agree on the capacities across ranks, allocate the exchange buffers"""
         lib, W = abi.lib(), self.comm.world
+        self.graph = None
         local8 = np.zeros(8)
         abi.check(lib.sz_slab_measure(self.ctx._h, abi._ptr(local8, abi.c_dp)))
         all8 = self.comm.all_gather(torch.from_numpy(local8).to(self.dev)).cpu().numpy().reshape(W, 8).copy()
@@ -438,6 +443,7 @@ class DeviceSlab:
         self._p_meta, self._p_all_meta, self._p_send, self._p_recv, self._p_status = (P(self.meta, abi.c_dp), P(self.all_meta, abi.c_dp), P(self.send, abi.c_dp),
                                                                                       P(self.recv, abi.c_dp), P(self.status, abi.c_ip))
         self.halo_measured = (int(rec.sum()), int(vert.sum()))
+        torch.cuda.synchronize(self.dev)          # the buffers were made on torch's current stream, the step uses self.stream
         self.plans += 1
 
     # ---- one step
@@ -472,24 +478,62 @@ class DeviceSlab:
             return None
         return {k: self.timing["ms"][i] / self.timing["n"] for i, k in enumerate(self.STAGES)}
 
+    def enable_graph(self, on=True):
+        """Capture a whole step -- the library's kernels AND the NCCL collectives between them -- into one CUDA graph and replay
+        it every step: one launch from the host instead of ~60, so the GPU is never waiting for the host to enqueue the next
+        kernel or collective (at 8 GPUs / 125k floes per rank that wait was a quarter of the step).  Needs NCCL (not the
+        host-staged gloo path).  Everything the graph bakes in is a capacity, never a count: list, pair and row capacities,
+        the cell grid, the exchange blocks; counts are read from device memory.  A step that outgrows a capacity is detected
+        as usual, repeated on the ordinary path, and the graph is captured again with the new sizes."""
+        self.want_graph = bool(on) and self.comm.world > 1 and not self.comm.stage
+        if not self.want_graph:
+            self.graph = None
+        self.ctx.set_option("graph_safe", 1 if self.want_graph else 0)
+
+    def _capture(self):
+        lib, h = abi.lib(), self.ctx._h
+        g = torch.cuda.CUDAGraph()
+        l0 = lib.sz_launch_count()
+        with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+            self.exchange()
+            abi.check(lib.sz_step_enqueue(h))
+        self.graph_launches = int(lib.sz_launch_count() - l0)
+        self.graph = g
+
     def run(self, allow_pair_errors=False):
         """one contact step on the current state; returns the step's SzSummary (n = the padded list length)"""
-        for attempt in range(4):
-            self.exchange()
-            s = self.ctx.step_resident(allow_pair_errors=allow_pair_errors)
-            if self.timing is not None:
-                self._ev[7].record()
-                self._ev[7].synchronize()
-                self.timing["seen"] = self.timing.get("seen", 0) + 1
-                if self.timing["seen"] > 3:         # the first steps carry NCCL's connection set-up and the planning step
-                    for i in range(7):
-                        self.timing["ms"][i] += self._ev[i].elapsed_time(self._ev[i + 1])
-                    self.timing["n"] += 1
-            flag = self.flag.cpu()
-            if int(flag[0]) == 0:
-                self.summary, self.steps, self.n_outside = s, self.steps + 1, int(flag[1])
-                return s
-            self.plan(grow=2.0 ** (attempt + 1))           # the field outgrew the blocks: new capacities, repeat the step
+        with torch.cuda.stream(self.stream):
+            if self.want_graph and self.graph is None and self.steps >= 2:
+                try:
+                    self._capture()       # (the sizes of the step before are carried over: capture from the third step on)
+                except abi.SzError:
+                    self.graph = None     # no sizes to carry over yet (a re-plan changed the list capacity): ordinary step first
+            if self.graph is not None:
+                self.graph.replay()
+                self.graph_replays += 1
+                abi.lib().sz_add_launches(self.graph_launches)
+                s = self.ctx.step_finish(allow_pair_errors=allow_pair_errors)
+                flag = self.flag.cpu()
+                if s is not None and int(flag[0]) == 0:
+                    self.summary, self.steps, self.n_outside = s, self.steps + 1, int(flag[1])
+                    return s
+                self.graph = None         # a capacity was outgrown: the ordinary path below repeats the step and re-plans
+            for attempt in range(4):
+                self.exchange()
+                s = self.ctx.step_resident(allow_pair_errors=allow_pair_errors)
+                if self.timing is not None:
+                    self._ev[7].record()
+                    self._ev[7].synchronize()
+                    self.timing["seen"] = self.timing.get("seen", 0) + 1
+                    if self.timing["seen"] > 3:         # the first steps carry NCCL's connection set-up and the planning step
+                        for i in range(7):
+                            self.timing["ms"][i] += self._ev[i].elapsed_time(self._ev[i + 1])
+                        self.timing["n"] += 1
+                flag = self.flag.cpu()
+                if int(flag[0]) == 0:
+                    self.summary, self.steps, self.n_outside = s, self.steps + 1, int(flag[1])
+                    return s
+                self.plan(grow=2.0 ** (attempt + 1))           # the field outgrew the blocks: new capacities, repeat the step
         raise RuntimeError("slab step: capacities kept overflowing")
 
     def trajectory_init(self, mass, inertia, nz=1000, **fields):
@@ -632,7 +676,7 @@ class SlabJob:
     numbered slab by slab (a stable sort of the generator's numbering by x-slab; at world 1 the generator's own), rank r owns
     the r-th slab: floe ownership by centroid."""
 
-    def __init__(self, n_floes, seed, rank, world, local_rank, dist, order="site", number_for_world=None):
+    def __init__(self, n_floes, seed, rank, world, local_rank, dist, order="site", number_for_world=None, graph=True):
         self.rank, self.world, self.dist = rank, world, dist
         self.prm, field = voronoi_field(n_floes, seed=seed, order=order)
         self.ctx = ContactContext(local_rank)
@@ -655,6 +699,7 @@ class SlabJob:
             dev = torch.device("cuda", local_rank)
             self.comm = Comm(dist, rank, world, dev)
             self.slab = DeviceSlab(self.prm, self.floes, self.gid, field.n, self.comm, self.ctx)
+            self.slab.enable_graph(graph)
         self._pin()
 
     def _pin(self):
@@ -672,9 +717,9 @@ class SlabJob:
             ms = s.ms_device
         else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0.record(self.slab.stream)
             s = self.slab.run()
-            e1.record()
+            e1.record(self.slab.stream)
             e1.synchronize()
             ms = e0.elapsed_time(e1)          # meta all-gather + halo all-to-all + list build + local step, on the device timeline
         self.summary = s

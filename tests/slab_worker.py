@@ -43,6 +43,7 @@ def main():
             c2, fb = scenarios.domain(prm.Lx, prm.Ly)
             bnd = sz.Boundary(fb["c"][0], fb["c"][1], c2[0], c2[1], fb["area"], fb["h"])
     migrate = kind == "migrate"
+    use_graph = kind == "graph"           # the whole step replayed from one CUDA graph (NCCL only)
     fast = kind != "real"
     if fast:
         field.u[:] *= 100.0      # tens of metres per step: floes cross the periodic boundary and the slab edges within the run
@@ -55,6 +56,8 @@ def main():
     comm = slabs.Comm(dist, rank, world, dev)
     ctx = sz.ContactContext(local)
     slab = slabs.DeviceSlab(prm, mine, gid, field.n, comm, ctx, bnd=bnd)
+    if use_graph:
+        slab.enable_graph(True)
     nz, hfo = 3, 2e-4
     L = prm.Lx
     bounds = (-1.5 * L, 1.5 * L, -1.5 * L, 1.5 * L)
@@ -162,8 +165,11 @@ def main():
         if migrate and n_migrated[0] == 0:
             ok = False
             print("no floe migrated: the test did not exercise repartition()")
-        print("RESULT %s world=%d backend=%s floes=%d steps=%d max_alpha=%.3e kill_events=%d migrated=%d" % ("OK" if ok and moved > 0 else "FAIL", world, backend, field.n, steps, moved,
-                                                                                                        int((o1["kill"] > 0).sum()), n_migrated[0]), flush=True)
+        if use_graph and slab.graph_replays == 0:
+            ok = False
+            print("the CUDA graph was never replayed")
+        print("RESULT %s world=%d backend=%s floes=%d steps=%d max_alpha=%.3e kill_events=%d migrated=%d graph_replays=%d" % (
+            "OK" if ok and moved > 0 else "FAIL", world, backend, field.n, steps, moved, int((o1["kill"] > 0).sum()), n_migrated[0], slab.graph_replays), flush=True)
         one.close()
     ctx.close()
     dist.barrier()

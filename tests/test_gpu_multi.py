@@ -92,3 +92,11 @@ def test_four_slabs_nccl():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs for the NCCL path")
 def test_two_slabs_nccl():
     print(run(2, 30000, 6, "voronoi"))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs for the NCCL path")
+def test_two_slabs_nccl_cuda_graph():
+    """the whole step -- library kernels and NCCL collectives -- captured once and replayed: same bits as one GPU, every step of
+    a coupled loop (the graph reads counts from device memory, so moving floes do not invalidate it)"""
+    out = run(2, 30000, 8, "graph", steps=8)
+    assert "graph_replays=0" not in out
