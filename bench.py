@@ -352,8 +352,11 @@ def main():
 
     # ---- device-resident throughput
     launches0 = abi.lib().sz_launch_count()
+    warm_kern_ms, warm_narrow_ms, warm_pairs = 0.0, 0.0, 0
     for _ in range(max(3, args.warmup)):
-        job.step_resident()
+        _, wph = job.step_resident()
+        if wph["classes"]["C"][0] > 0:            # (steps replayed from a CUDA graph carry no per-kernel events: N > 1 reports the class C launch of a warm-up step)
+            warm_kern_ms, warm_narrow_ms, warm_pairs = wph["classes"]["C"][0], wph["narrow"], wph["classes"]["C"][1]
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -434,6 +437,8 @@ def main():
         alg_bytes = algorithmic_bytes(floes, job.summary) * (kern_pairs / max(1, job.summary.n_pairs))
         narrow_ms_per = narrow_ms / args.steps
         kern_ms_per = kern_ms / args.steps
+        if kern_ms_per <= 0:
+            kern_ms_per, narrow_ms_per, kern_pairs = warm_kern_ms, warm_narrow_ms, warm_pairs
         achieved = alg_bytes / (kern_ms_per * 1e-3) / 1e9
         traffic, traffic_note = None, "no ncu capture published (profiles/narrow_traffic.json)"
         tp = os.path.join(ROOT, "profiles", "narrow_traffic.json")
@@ -480,7 +485,10 @@ def main():
     job.close()
     if dist is not None:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)      # (no destroy_process_group: tearing NCCL down after CUDA-graph capture of its collectives has hung on this stack; the line is printed, every rank is past the barrier)
 
 
 if __name__ == "__main__":

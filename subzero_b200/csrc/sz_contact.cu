@@ -112,7 +112,7 @@ struct SzContext {
     int n_fast_steps = 0, n_slow_steps = 0;
     int opt_convex_split = 0;        // experiment: class C as two kernels (sweep, then force law)
     int opt_euler_cell_warp = 1;     // calc_eulerian_data: a warp per cell (0: one thread per cell)
-    Counters* d_cnt = nullptr; Counters* h_cnt = nullptr;
+    Counters* d_cnt = nullptr; Counters* h_cnt = nullptr; Counters* h_init = nullptr;      // h_init: the step's initial counters (pinned; never the target of a read-back, so a replayed copy node finds them unchanged)
     // inputs
     bool have_input = false, have_step = false;
     bool have_rows = false;                 // the contact rows of the last step are still on the device (also after the integrator moved the floes)
@@ -933,7 +933,7 @@ extern "C" int sz_create(SzContext** out, int device)
     for (auto& e : c->evp) CK(cudaEventCreate(&e));
     for (auto& e : c->evk) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&c->d_cnt, sizeof(Counters)));
-    CK(cudaMallocHost(&c->h_cnt, sizeof(Counters)));
+    CK(cudaMallocHost(&c->h_cnt, sizeof(Counters))); CK(cudaMallocHost(&c->h_init, sizeof(Counters)));
     memset(&c->summary, 0, sizeof(c->summary));
     *out = c;
     return SZ_OK;
@@ -968,6 +968,7 @@ extern "C" void sz_destroy(SzContext* c)
       for (auto* b : sb) b->release(); c->sl_cub.release(); c->sl_out.release(); c->sl_rows.release(); c->sl_rcnt.release(); c->sl_roff.release(); if (c->sl_scratch) cudaFree(c->sl_scratch); }
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    if (c->h_init) cudaFreeHost(c->h_init);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto& e : c->evp) if (e) cudaEventDestroy(e);
@@ -1689,8 +1690,8 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
         Counters init; memset(&init, 0, sizeof(init));
         init.n1 = nl0; init.n = nl0;
         init.bbox[0] = enc_d(SZ_INF); init.bbox[1] = enc_d(-SZ_INF); init.bbox[2] = enc_d(SZ_INF); init.bbox[3] = enc_d(-SZ_INF); init.rmax_bits = enc_d(0.0);
-        *c->h_cnt = init;
-        CK(cudaMemcpyAsync(c->d_cnt, c->h_cnt, sizeof(Counters), cudaMemcpyDefault, st));
+        *c->h_cnt = init; *c->h_init = init;
+        CK(cudaMemcpyAsync(c->d_cnt, c->h_init, sizeof(Counters), cudaMemcpyDefault, st));
     }
     if (P.periodic && n0 > 0 && !ext) {
         CK(c->scan_tmp.ensure(scan_tmp_ints(2 * (size_t)n0 + 2)));
@@ -1937,6 +1938,7 @@ extern "C" int sz_step_finish(SzContext* c, SzSummary* out)
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 5; ++k) c->phase_ms[k] = 0;
+    if (c->slab) c->sl_built = true;          // the step that just ran (launched or replayed) followed a list build on the same stream
     return step_finish(c, out, c->pend.n, c->pend.np, c->pend.rows_bound, true, true, 0.0f);
 }
 extern "C" void sz_add_launches(long long n) { g_launches += n; }

@@ -774,4 +774,7 @@ class SlabJob:
                 "both sides instead of returning partial forces to the owner (bit-identical rows, no second exchange)") % self.world
 
     def close(self):
+        if self.slab is not None:
+            self.slab.graph = None            # a captured graph holds NCCL kernels: release it before the process group goes away
+            torch.cuda.synchronize()
         self.ctx.close()

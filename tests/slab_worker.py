@@ -171,8 +171,14 @@ def main():
         print("RESULT %s world=%d backend=%s floes=%d steps=%d max_alpha=%.3e kill_events=%d migrated=%d graph_replays=%d" % (
             "OK" if ok and moved > 0 else "FAIL", world, backend, field.n, steps, moved, int((o1["kill"] > 0).sum()), n_migrated[0], slab.graph_replays), flush=True)
         one.close()
+    slab.graph = None                 # a captured graph holds NCCL kernels: let it go before the process group
+    torch.cuda.synchronize()
     ctx.close()
     dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if use_graph:
+        os._exit(0 if ok else 1)      # tearing NCCL down after its collectives were captured into a CUDA graph has hung on this stack
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
