@@ -22,6 +22,7 @@
 #include "sz_corners.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdarg>
@@ -471,6 +472,22 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
         for (int m = 0; m < count; ++m) rank += (__shfl_sync(0xffffffffu, v, m) < v);
         __syncwarp();
         if (lane < count) { b.pj[off + rank] = v; b.pi[off + lane] = i; }
+    } else if (count <= 256) {
+        // up to eight partners per lane: every lane ranks its own against the whole segment, then all write in place
+        int v[8], r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = lane + 32 * q;
+            v[q] = k < count ? b.pj[off + k] : 0x7fffffff; r[q] = 0;
+        }
+        for (int m = 0; m < count; ++m) {
+            const int w = b.pj[off + m];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] += (w < v[q]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (lane + 32 * q < count) { b.pj[off + r[q]] = v[q]; b.pi[off + lane + 32 * q] = i; }
     } else {
         if (lane == 0) {
             for (int a = 1; a < count; ++a) { int v = b.pj[off + a], k = a - 1; while (k >= 0 && b.pj[off + k] > v) { b.pj[off + k + 1] = b.pj[off + k]; --k; } b.pj[off + k + 1] = v; }
@@ -1677,6 +1694,8 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
     c->have_step = false; c->have_rows = false;
     const bool fast = c->opt_speculate && c->plan_valid && c->plan_n0 == n0 && c->plan_nl0 == nl0 && !P.want_clip_polys && c->plan_ncap <= ncap;
     if (enq && !fast) { sz_set_error("sz_step_enqueue: no sizes to carry over yet (run sz_step_resident first; not with want_clip_polys)"); return SZ_ERR_STATE; }
+    // NVTX ranges name the phases on a timeline (Nsight Systems; free when no tool is attached)
+    struct Nvtx { Nvtx(const char* n) { nvtxRangePushA(n); } ~Nvtx() { nvtxRangePop(); } void next(const char* n) { nvtxRangePop(); nvtxRangePushA(n); } } nvtx("sz K0 extended list");
     if (!enq) CK(cudaEventRecord(c->ev0, st));
     CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), st));
 
@@ -1739,6 +1758,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
 
     CKS(dbg_sync(c, fast ? "K0 (speculated)" : "K0"));
     if (!enq) CK(cudaEventRecord(c->evp[0], st));
+    nvtx.next("sz K1 broad phase");
     // ---- K1: cell grid + candidate pairs
     GridDesc g;
     if (fast) { g.x0 = c->plan_g.x0; g.y0 = c->plan_g.y0; g.cell = c->plan_g.cell; g.nx = c->plan_g.nx; g.ny = c->plan_g.ny; }
@@ -1783,6 +1803,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
 
     CKS(dbg_sync(c, "ext_prep + broad fill"));
     if (!enq) CK(cudaEventRecord(c->evp[1], st));
+    nvtx.next("sz K2+K3 narrow phase and force law");
     CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
@@ -1822,6 +1843,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
 
     CKS(dbg_sync(c, "narrow phase"));
     if (!enq) CK(cudaEventRecord(c->evp[2], st));
+    nvtx.next("sz K4 mirror, rows, sums");
     // ---- K4: mirror, rows, sums
     CK(c->tcnt.ensure(n + 2)); CK(c->toff.ensure(n + 2)); CK(c->tlist.ensure(np + 1)); CK(c->rcnt.ensure(n + 2)); CK(c->row_off.ensure(n + 2));
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));

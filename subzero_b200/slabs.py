@@ -408,7 +408,8 @@ class DeviceSlab:
         assert self.gid.shape[0] == owned.n and (owned.n < 2 or np.all(np.diff(self.gid) > 0)), "global floe numbers must ascend"
         fs = owned.struct()
         bs = self.bnd.struct() if self.bnd is not None else None
-        self.graph = None
+        if plan:
+            self.graph = None        # (plan=False: same floes, same capacities, same buffers -- only their contents change, a captured step stays valid)
         self.stream.synchronize()
         abi.check(abi.lib().sz_slab_upload(self.ctx._h, C.byref(self.prm), C.byref(fs), C.byref(bs) if bs is not None else None, abi._ptr(self.gid, abi.c_ip),
                                            self.n_global, self.comm.rank, self.comm.world))

@@ -377,3 +377,18 @@ def test_speculated_sizes_give_the_same_step_and_recover_from_overflow():
                 assert np.array_equal(w[7][key], g[7][key], equal_nan=True), (traj, k, key)
             for key in w[8]:
                 assert np.array_equal(w[8][key], g[8][key], equal_nan=True), (traj, k, key)
+
+
+def test_floes_with_many_candidate_partners(ctx):
+    """a few floes whose bounding radius is many times their neighbours' (rmax is an input: initialize_floe_values.m:21) collect
+    40..300 candidate partners each: the in-warp ranked sort of 33..256 partners and the serial one beyond, against the oracle's
+    ascending lists (floe_interactions_all.m:100-116)"""
+    prm, soa = sz.voronoi_field(6000, seed=17)
+    soa.rmax[100] *= 4.0
+    soa.rmax[2500] *= 7.0
+    soa.rmax[10] *= 20.0
+    rep, ref = run_both(ctx, prm, soa, broad_mode=1)
+    p = ref.pairs()
+    per_i = np.bincount(p["i"], minlength=6001)
+    assert 32 < per_i[101] <= 256 or 32 < per_i[2501] <= 256          # the ranked path ...
+    assert per_i.max() > 256                                          # ... and the serial one both ran
