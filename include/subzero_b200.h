@@ -62,6 +62,11 @@ typedef struct SzParams {
     int32_t periodic;         /* PERIODIC  */
     int32_t collision;        /* COLLISION */
     int32_t want_clip_polys;  /* 1: keep clip #1's int64 polygons per pair for bit-exact parity checks */
+    int32_t pair_with_boundary_floes;   /* 0 (default) = the reference: the first Nb (topography) floes are never anybody's partner, because
+                                 * the search only looks at j > i >= Nb+1 (floe_interactions_all.m:76,102-103).  1 = opt-in, NOT
+                                 * reference behaviour: a floe i > Nb also records the topography floes j <= Nb within reach (ascending, ahead of
+                                 * its other partners); the force acts on i only (no mirrored row: :196 needs partner > i), such a pair never
+                                 * raises kill / transfer, and it takes no part in the ghost de-dup of :93-99,113. */
 } SzParams;
 
 /* The hot-path fields of the reference's Floe struct array (Initialize_Model/initialize_floe_values.m:12-52),

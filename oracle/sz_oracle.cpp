@@ -496,17 +496,18 @@ void floe_interactions_all(const SzParams& P, const SzFloesSoA& in, const SzBoun
         std::vector<int> mems;                                                        // :93-99
         if (FloeNums[i] < 0) {
             int num = std::abs(FloeNums[i]);
-            for (auto& pi : F[num - 1].potentialInteractions) mems.push_back((int)pi.floeNum);
+            for (auto& pi : F[num - 1].potentialInteractions) if (pi.floeNum > Nb) mems.push_back((int)pi.floeNum);      // (opt-in topography partners take no part in the de-dup)
         }
         if (!(alive[i] && !std::isnan(x[i]) && P.collision)) continue;               // :101
         std::vector<int> cand;
-        if (broad_mode == 0) { for (int j = i + 1; j < N; ++j) cand.push_back(j); }
+        const bool opt_in = P.pair_with_boundary_floes != 0;      // NOT the reference: topography floes j <= Nb as partners of i > Nb
+        if (broad_mode == 0) { if (opt_in) for (int j = 0; j < Nb && j < i; ++j) cand.push_back(j); for (int j = i + 1; j < N; ++j) cand.push_back(j); }
         else if (!std::isnan(y[i])) {
             int cxi = (int)((x[i] - gx0) / cell), cyi = (int)((y[i] - gy0) / cell);
             for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
                 int cx = cxi + dx, cy = cyi + dy; if (cx < 0 || cy < 0 || cx >= gnx || cy >= gny) continue;
                 int c = cy * gnx + cx;
-                for (int t = cell_start[c]; t < cell_start[c + 1]; ++t) if (cell_items[t] > i) cand.push_back(cell_items[t]);
+                for (int t = cell_start[c]; t < cell_start[c + 1]; ++t) if (cell_items[t] > i || (opt_in && cell_items[t] < Nb)) cand.push_back(cell_items[t]);
             }
             std::sort(cand.begin(), cand.end());
         }
@@ -520,7 +521,7 @@ void floe_interactions_all(const SzParams& P, const SzFloesSoA& in, const SzBoun
             for (size_t v = 0; v < F[j].c_alpha.x.size(); ++v) { p.c.x.push_back(F[j].c_alpha.x[v] + x[j]); p.c.y.push_back(F[j].c_alpha.y[v] + y[j]); }
             p.Ui = F[j].Ui; p.Vi = F[j].Vi; p.h = F[j].h; p.area = F[j].area; p.Xi = x[j]; p.Yi = y[j]; p.ksi = F[j].ksi;
             fi.potentialInteractions.push_back(p);
-            mems.push_back(FloeNums[j]);                                              // :113 (signed)
+            if (j >= Nb) mems.push_back(FloeNums[j]);                                 // :113 (signed)
         }
     }
 
@@ -563,7 +564,7 @@ void floe_interactions_all(const SzParams& P, const SzFloesSoA& in, const SzBoun
                     }
                     fi.OverlapArea = so + fi.OverlapArea;
                     pd.n_regions = (int)fo.force.size(); npf++;
-                } else if (fo.overlap_is_scalar && std::isinf(fo.overlap[0]) && i + 1 > Nb) {   // :138-145
+                } else if (fo.overlap_is_scalar && std::isinf(fo.overlap[0]) && i + 1 > Nb && pk.floeNum > Nb) {   // :138-145 (an opt-in topography partner raises no kill / transfer)
                     if (i + 1 <= N0 && fo.overlap[0] > 0) { kill_i[i] = i + 1; transfer_i[i] = (int)pk.floeNum; }
                     else if (pk.floeNum <= N0) kill_i[i] = (int)pk.floeNum;
                 }

@@ -24,7 +24,7 @@ class SzParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "Lx", "Ly", "modulus", "dt", "nu", "mu", "merge_frac", "wall_frac", "amin_per_vertex", "vertex_match_tol",
         "on_edge_tol", "dl_min", "close_gap", "big_floe_r", "domain_area_frac")] + [
-        (n, C.c_int32) for n in ("Nb", "periodic", "collision", "want_clip_polys")]
+        (n, C.c_int32) for n in ("Nb", "periodic", "collision", "want_clip_polys", "pair_with_boundary_floes")]
 
 
 class SzFloesSoA(C.Structure):
@@ -164,7 +164,7 @@ def default_params(**kw):
     p = SzParams()
     p.nu, p.mu, p.merge_frac, p.wall_frac, p.amin_per_vertex = 0.3, 0.2, 0.55, 0.75, 100.0 / 1.75
     p.vertex_match_tol, p.on_edge_tol, p.dl_min, p.close_gap, p.big_floe_r, p.domain_area_frac = 1.0, 1e-8, 0.1, 1.0, 1e5, 0.95
-    p.dt, p.collision, p.periodic, p.Nb, p.want_clip_polys = 10.0, 1, 0, 0, 0
+    p.dt, p.collision, p.periodic, p.Nb, p.want_clip_polys, p.pair_with_boundary_floes = 10.0, 1, 0, 0, 0, 0
     for k, v in kw.items():
         setattr(p, k, v)
     return p

@@ -389,7 +389,7 @@ __global__ void cell_fill_kernel(int n, const int* __restrict__ cid, const int* 
 
 struct BroadArgs {
     int n, n0, Nb, collision; GridDesc g; double minL2; const u64* rmax_bits;     // largest rmax of the list, as bbox_kernel left it on the device
-    int np_cap; int* overflow;
+    int np_cap; int* overflow; int pair_boundary;      // pair_boundary: SzParams.pair_with_boundary_floes
     const double* ex; const double* ey; const int* esrc; const int* efn; const uint8_t* ealive; const double* rmax;
     const int* egid; const uint8_t* eowned; const double* erootx; const double* erooty;
     const int* cell_start; const int* s_idx; const double* s_x; const double* s_y; const double* s_r;
@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
                 bool ok = false; int j = -1;
                 if (t < t1) {
                     j = b.s_idx[t];
-                    if (j > i && (own_i || b.eowned[j])) {     // a pair is resolved where either floe is owned
+                    // j > i (:103); opt-in: also the topography floes j <= Nb below it (never i themselves: `active` needs egid > Nb)
+                    if ((j > i || (b.pair_boundary && b.egid[j] <= b.Nb)) && (own_i || b.eowned[j])) {     // a pair is resolved where either floe is owned
                         const double dx = xi - b.s_x[t], dy = yi - b.s_y[t], rs = ri + b.s_r[t];
                         if (sqrt(dx * dx + dy * dy) < rs) {
                             ok = true;
@@ -693,17 +694,17 @@ __global__ void __launch_bounds__(SZ_BIN_N * SZ_BIN_N) bins_scan_kernel(Counters
 }
 
 // ------------------------------------------------------------------------------------------------ K4 assembly
-__global__ void tcount_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pj, const int* __restrict__ nrows, int* __restrict__ tcnt)
+__global__ void tcount_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const int* __restrict__ nrows, int* __restrict__ tcnt)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int np = *np_dev < np_cap ? *np_dev : np_cap;
-    if (p < np && nrows[p] > 0) atomicAdd(&tcnt[pj[p]], 1);
+    if (p < np && nrows[p] > 0 && pj[p] > pi[p]) atomicAdd(&tcnt[pj[p]], 1);      // mirrored only to a partner behind i (:196)
 }
-__global__ void tfill_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pj, const int* __restrict__ nrows, const int* __restrict__ toff, int* __restrict__ tpos, int* __restrict__ tlist)
+__global__ void tfill_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const int* __restrict__ nrows, const int* __restrict__ toff, int* __restrict__ tpos, int* __restrict__ tlist)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int np = *np_dev < np_cap ? *np_dev : np_cap;
-    if (p < np && nrows[p] > 0) { const int j = pj[p]; tlist[toff[j] + atomicAdd(&tpos[j], 1)] = p; }
+    if (p < np && nrows[p] > 0 && pj[p] > pi[p]) { const int j = pj[p]; tlist[toff[j] + atomicAdd(&tpos[j], 1)] = p; }
 }
 // rows of floe m = own pairs + wall + mirrored (floe_interactions_all.m:136,167,196)
 __global__ void rowcount_kernel(int n, const uint8_t* __restrict__ eowned, const int* __restrict__ pair_off, const int* __restrict__ nrows, const int* __restrict__ wnrows,
@@ -815,7 +816,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleArgs a)
             ova = so + ova;
         } else if (a.pstatus[p] == 0) {
             const double ov = a.ovl[p];
-            if ((ov == SZ_INF || ov == -SZ_INF) && pairing) {          // :138-145
+            if ((ov == SZ_INF || ov == -SZ_INF) && pairing && a.egid[a.pj[p]] > a.Nb) {          // :138-145 (an opt-in topography partner raises no kill / transfer)
                 if (orig && ov > 0) { kill = a.egid[m]; transfer = a.egid[a.pj[p]]; }
                 else if (a.efn[a.pj[p]] > 0) kill = a.egid[a.pj[p]];
             }
@@ -929,7 +930,7 @@ extern "C" void sz_default_params(SzParams* p)
     memset(p, 0, sizeof(*p));
     p->nu = 0.3; p->mu = 0.2; p->merge_frac = 0.55; p->wall_frac = 0.75; p->amin_per_vertex = 100.0 / 1.75;
     p->vertex_match_tol = 1; p->on_edge_tol = 1e-8; p->dl_min = 0.1; p->close_gap = 1; p->big_floe_r = 1e5; p->domain_area_frac = 0.95;
-    p->dt = 10; p->collision = 1; p->periodic = 0; p->Nb = 0; p->want_clip_polys = 0;
+    p->dt = 10; p->collision = 1; p->periodic = 0; p->Nb = 0; p->want_clip_polys = 0; p->pair_with_boundary_floes = 0;
 }
 
 extern "C" int sz_create(SzContext** out, int device)
@@ -1776,7 +1777,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
         CKS(exclusive_scan(c, c->cell_cnt.p, ncell, c->cell_start.p, ncell + 1));
         CK(cudaMemsetAsync(c->cell_cnt.p, 0, (size_t)(ncell + 1) * 4, st));
         ++g_launches; cell_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, c->cid.p, c->cell_start.p, c->cell_cnt.p, c->ex.p, c->ey.p, c->esrc.p, c->rmax.p, c->s_idx.p, c->s_x.p, c->s_y.p, c->s_r.p);
-        b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly); b.rmax_bits = (const u64*)((const char*)c->d_cnt + offsetof(Counters, rmax_bits)); b.overflow = D_CNT(overflow);
+        b.n = n; b.n0 = n0; b.Nb = Nb; b.collision = P.collision; b.g = g; b.minL2 = std::min(2 * P.Lx, 2 * P.Ly); b.rmax_bits = (const u64*)((const char*)c->d_cnt + offsetof(Counters, rmax_bits)); b.overflow = D_CNT(overflow); b.pair_boundary = P.pair_with_boundary_floes;
         b.ex = c->ex.p; b.ey = c->ey.p; b.esrc = c->esrc.p; b.efn = c->efn.p; b.ealive = c->ealive.p; b.rmax = c->rmax.p;
         b.egid = c->egid.p; b.eowned = c->eowned.p; b.erootx = c->erootx.p; b.erooty = c->erooty.p;
         b.cell_start = c->cell_start.p; b.s_idx = c->s_idx.p; b.s_x = c->s_x.p; b.s_y = c->s_y.p; b.s_r = c->s_r.p;
@@ -1847,10 +1848,10 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
     // ---- K4: mirror, rows, sums
     CK(c->tcnt.ensure(n + 2)); CK(c->toff.ensure(n + 2)); CK(c->tlist.ensure(np + 1)); CK(c->rcnt.ensure(n + 2)); CK(c->row_off.ensure(n + 2));
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
-    if (np > 0) { ++g_launches; tcount_kernel<<<nblk(np, 256), 256, 0, st>>>(np, D_CNT(n_pairs), c->pj.p, c->pnrows.p, c->tcnt.p); }
+    if (np > 0) { ++g_launches; tcount_kernel<<<nblk(np, 256), 256, 0, st>>>(np, D_CNT(n_pairs), c->pi.p, c->pj.p, c->pnrows.p, c->tcnt.p); }
     CKS(exclusive_scan(c, c->tcnt.p, n, c->toff.p, n + 1));
     CK(cudaMemsetAsync(c->tcnt.p, 0, (size_t)(n + 1) * 4, st));
-    if (np > 0) { ++g_launches; tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, D_CNT(n_pairs), c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p); }
+    if (np > 0) { ++g_launches; tfill_kernel<<<nblk(np, 256), 256, 0, st>>>(np, D_CNT(n_pairs), c->pi.p, c->pj.p, c->pnrows.p, c->toff.p, c->tcnt.p, c->tlist.p); }
     if (n > 0) { ++g_launches; rowcount_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->eowned.p, c->pair_off.p, c->pnrows.p, wall ? c->wnrows.p : nullptr, c->toff.p, c->tlist.p, c->rcnt.p); }
     CKS(exclusive_scan(c, c->rcnt.p, n, c->row_off.p, n + 1));
     CKS(dbg_sync(c, "tcount/tfill/rowcount"));

@@ -91,6 +91,7 @@ static void cmd_upload(int nrhs, const mxArray* prhs[])
     P.Lx = scalar_field(p, "Lx", 0, true); P.Ly = scalar_field(p, "Ly", 0, true);
     P.modulus = scalar_field(p, "modulus", 0, true); P.dt = scalar_field(p, "dt", 0, true);
     P.Nb = (int32_t)scalar_field(p, "Nb", 0, false);
+    P.pair_with_boundary_floes = scalar_field(p, "pair_with_boundary_floes", 0, false) != 0;      // opt-in, not reference behaviour
     P.periodic = scalar_field(p, "periodic", 0, true) != 0; P.collision = scalar_field(p, "collision", 1, false) != 0;
     P.nu = scalar_field(p, "nu", P.nu, false); P.mu = scalar_field(p, "mu", P.mu, false);
     const mxArray* s = prhs[2];

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     """sizes implied by the header's field lists (8-byte alignment)"""
-    assert C.sizeof(abi.SzParams) == 15 * 8 + 4 * 4
+    assert C.sizeof(abi.SzParams) == 15 * 8 + 6 * 4          # five int32 fields + padding
     assert C.sizeof(abi.SzFloesSoA) == 8 + 8 + 12 * 8
     assert C.sizeof(abi.SzBoundary) == 8 + 8 + 8 + 8 + 8 + 8 + 7 * 8
     assert C.sizeof(abi.SzSummary) == 8 + 5 * 8 + 8 + 4 + 4 + 8 + 8 + 8          # ... ms_device (+pad), n_pairs_owned, n_kill_events (+pad)

@@ -108,6 +108,19 @@ def test_boundary_floes_nb(ctx):
     assert ref.pairs()["i"].min() > 40
 
 
+def test_boundary_floes_opt_in_pairing(ctx):
+    """SzParams.pair_with_boundary_floes (opt-in, not the reference): floes i > Nb also record the topography
+    floes below them, ahead of their other partners; no mirrored rows, no kill / transfer from such pairs"""
+    prm, soa = sz.voronoi_field(1500, seed=6)
+    prm.Nb = 40
+    prm.pair_with_boundary_floes = 1
+    rep, ref = run_both(ctx, prm, soa, broad_mode=1)
+    p = ref.pairs()
+    assert (p["j"] <= 40).sum() > 50 and p["i"].min() > 40
+    off, rows = ref.rows()
+    assert off[40] == 0                                         # the topography floes carry no rows
+
+
 def test_small_periodic_domain_big_floes(ctx):
     """2(rmax_i+rmax_j) > min(2Lx,2Ly): the ghost de-dup exemption of floe_interactions_all.m:103"""
     prm, soa = sz.voronoi_field(12, seed=8)

@@ -8,6 +8,7 @@ import pytest
 import oracle
 import scenarios
 from subzero_b200 import abi
+import subzero_b200 as sz
 
 S = 2.0 ** 32
 P = abi._ptr
@@ -219,3 +220,37 @@ def test_contact_thresholds_hand_derived():
         off, rows = st.rows()
         return off, rows, st.pairs(), st.floe_outputs()
     run_threshold_checks(step)
+
+
+def test_topography_floes_pair_only_when_opted_in():
+    """as written, floes 1..Nb can never be anybody's partner (floe_interactions_all.m:76,102-103: i >= Nb+1 and
+    j > i) -- the reference behaviour and the default.  SzParams.pair_with_boundary_floes = 1 (opt-in, NOT the reference) lets
+    a floe i > Nb record the topography floes below it; the force acts on i only.  Worked by hand: floe 1 (topography, Nb = 1)
+    = [0,1000]^2, floe 2 = [900,1900] x [0,1000] overlapping it in a 100 m strip, floe 3 far away.  Default: no pairs at all
+    between 1 and 2.  Opted in: pair (2,1); floe 2 gets one row [1 Fx 0 950 500 . 1e5] with Fx > 0 (pushed away from floe 1,
+    the same magnitude floe 1 would get from the mirrored pair (1,2) if it were an ordinary floe); floe 1 gets nothing."""
+    import scenarios
+    sq = lambda x0: np.array([[x0, 0.0], [x0, 1000.0], [x0 + 1000.0, 1000.0], [x0 + 1000.0, 0.0]])
+    Floe = [scenarios.floe_from_polygon(sq(0.0)), scenarios.floe_from_polygon(sq(900.0)), scenarios.floe_from_polygon(sq(5000.0))]
+    soa = sz.floes_to_soa(Floe)
+    prm = sz.default_params()
+    prm.Lx = prm.Ly = 1e4
+    prm.modulus, prm.dt, prm.periodic, prm.collision, prm.Nb = 9e7, 10.0, 1, 1, 1
+    ref = oracle.OracleStep(prm, soa, broad_mode=0)
+    assert ref.summary.n_pairs == 0 and ref.summary.n_rows == 0                       # the reference: topography never pairs
+    prm.pair_with_boundary_floes = 1
+    for mode in (0, 1):
+        ref = oracle.OracleStep(prm, soa, broad_mode=mode)
+        p = ref.pairs()
+        assert p["i"].tolist() == [2] and p["j"].tolist() == [1]
+        off, rows = ref.rows()
+        assert (off[1] - off[0], off[2] - off[1], off[3] - off[2]) == (0, 1, 0)       # only floe 2 carries a row
+        r = rows[0]
+        assert r[0] == 1 and r[1] > 0 and r[2] == 0 and r[3] == pytest.approx(950.0) and r[4] == pytest.approx(500.0) and r[6] == pytest.approx(1e5)
+        o = ref.floe_outputs()
+        assert o["fx"][0] == 0 and o["fx"][1] == r[1] and o["overlap_area"][0] == 0 and o["overlap_area"][1] == pytest.approx(1e5)
+    # the same contact between two ordinary floes: pair (1,2), floe 1 carries the row, floe 2 the mirrored one of equal magnitude
+    prm.Nb, prm.pair_with_boundary_floes = 0, 0
+    ref0 = oracle.OracleStep(prm, soa, broad_mode=0)
+    off0, rows0 = ref0.rows()
+    assert rows0[off0[1]][0] == 1 and rows0[off0[1]][1] == pytest.approx(r[1], rel=1e-12)
