@@ -1765,6 +1765,11 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
     if (fast) { g.x0 = c->plan_g.x0; g.y0 = c->plan_g.y0; g.cell = c->plan_g.cell; g.nx = c->plan_g.nx; g.ny = c->plan_g.ny; }
     else g = make_grid(c->h_cnt, n);
     const int ncell = g.nx * g.ny;
+    if (g.nx < 1 || g.ny < 1 || (double)g.nx * (double)g.ny > 3.2e7) {
+        sz_set_error("sz_step_resident: bad cell grid %d x %d (cell %g, origin %g %g; %s path; bbox %g..%g x %g..%g, rmax %g, n %d)", g.nx, g.ny, g.cell, g.x0, g.y0, fast ? "speculated" : "measured",
+                     dec_d(c->h_cnt->bbox[0]), dec_d(c->h_cnt->bbox[1]), dec_d(c->h_cnt->bbox[2]), dec_d(c->h_cnt->bbox[3]), dec_d(c->h_cnt->rmax_bits), n);
+        return SZ_ERR_STATE;
+    }
     CK(c->cid.ensure(n + 1)); CK(c->cell_cnt.ensure(ncell + 2)); CK(c->cell_start.ensure(ncell + 2));
     CK(c->s_idx.ensure(n + 1)); CK(c->s_x.ensure(n + 1)); CK(c->s_y.ensure(n + 1)); CK(c->s_r.ensure(n + 1));
     CK(c->pcnt.ensure(n + 2)); CK(c->pair_off.ensure(n + 2));
