@@ -416,7 +416,7 @@ __device__ __forceinline__ bool ghost_is_member(const BroadArgs& b, int i, int j
 // one warp per floe i: lanes stride over the three cell rows (each row's three cells are contiguous in
 // the bucketed arrays), ballot + popc compacts accepted partners, then an in-warp rank sort restores
 // ascending j (the order of Floe(i).potentialInteractions)
-template <bool FILL>
+template <bool FILL, bool PB>      // PB: the opt-in pairing with topography floes (a separate instantiation keeps the default's registers: 40, not 54)
 __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) broad_kernel(const BroadArgs b)
                 if (t < t1) {
                     j = b.s_idx[t];
                     // j > i (:103); opt-in: also the topography floes j <= Nb below it (never i themselves: `active` needs egid > Nb)
-                    if ((j > i || (b.pair_boundary && b.egid[j] <= b.Nb)) && (own_i || b.eowned[j])) {     // a pair is resolved where either floe is owned
+                    if ((j > i || (PB && b.egid[j] <= b.Nb)) && (own_i || b.eowned[j])) {     // a pair is resolved where either floe is owned
                         const double dx = xi - b.s_x[t], dy = yi - b.s_y[t], rs = ri + b.s_r[t];
                         if (sqrt(dx * dx + dy * dy) < rs) {
                             ok = true;
@@ -1789,7 +1789,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
         b.pcnt = c->pcnt.p; b.pair_off = c->pair_off.p;
         static const int stage_cap = getenv("SZ_BROAD_STAGE") ? atoi(getenv("SZ_BROAD_STAGE")) : 16;     // 0: the fill pass searches again
         if (stage_cap > 0) { CK(c->stage.ensure((size_t)n * stage_cap + 1)); b.stage = c->stage.p; b.stage_cap = stage_cap > 32 ? 32 : stage_cap; }
-        { ++g_launches; broad_kernel<false><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
+        { ++g_launches; if (b.pair_boundary) broad_kernel<false, true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); else broad_kernel<false, false><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
     }
     CKS(dbg_sync(c, "cell grid + broad count"));
     CKS(exclusive_scan(c, c->pcnt.p, n, c->pair_off.p, n + 1));
@@ -1805,7 +1805,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
     c->n_pairs = np; b.np_cap = np;
     CK(c->pi.ensure(np + 1)); CK(c->pj.ensure(np + 1)); CK(c->pstatus.ensure(np + 1)); CK(c->pnrows.ensure(np + 1)); CK(c->prow_start.ensure(np + 1)); CK(c->povl.ensure(np + 1));
     CK(c->listT.ensure(np + 1)); CK(c->listM.ensure(np + 1)); CK(c->listL.ensure(np + 1));
-    if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; broad_kernel<true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
+    if (np > 0) { b.pi = c->pi.p; b.pj = c->pj.p; ++g_launches; if (b.pair_boundary) broad_kernel<true, true><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); else broad_kernel<true, false><<<nblk(32 * (i64)n, 256), 256, 0, st>>>(b); }
 
     CKS(dbg_sync(c, "ext_prep + broad fill"));
     if (!enq) CK(cudaEventRecord(c->evp[1], st));
