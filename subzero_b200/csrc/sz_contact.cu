@@ -65,7 +65,9 @@ struct DBuf {
         cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
         if (e != cudaSuccess) return e;
         static const bool poison = getenv("SZ_DEBUG_POISON") != nullptr;      // debugging aid: fresh buffers start as 0xFF.. instead of whatever was there
-        if (poison) cudaMemset(q, 0x7F, ncap * sizeof(T));
+        // (the memset runs on the NULL stream, which the contexts' non-blocking streams do not wait for: without the synchronisation it
+        // can land AFTER the first real writes to the new buffer -- it did, and looked like a flaky physics bug for an hour)
+        if (poison) { cudaMemset(q, 0x7F, ncap * sizeof(T)); cudaDeviceSynchronize(); }
         if (keep && p && cap) cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
         if (p) cudaFree(p);
         p = q; cap = ncap;
@@ -946,6 +948,7 @@ extern "C" int sz_create(SzContext** out, int device)
     CK(cudaSetDevice(device));
     SzContext* c = new SzContext;
     c->device = device;
+    if (getenv("SZ_NO_SPECULATE")) c->opt_speculate = 0;      // debugging aid: measure every size as it is needed
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)); c->stream = c->own_stream;
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     for (auto& e : c->evp) CK(cudaEventCreate(&e));
