@@ -104,8 +104,7 @@ struct ConvexSweep {
     // the two open rings in Clipper coordinates (SweepMem), vertex 0 = bottom vertex (largest Y, then smallest X); [0] subject, [1] clip
     int n[2];
     typedef const SweepMem& M;
-    SZ_HD static i64 vxat(M m, int p, int i) { return m.vxs[p * NV + i]; }
-    SZ_HD static i64 vyat(M m, int p, int i) { return m.vys[p * NV + i]; }
+    SZ_HD static P64 vat(const SweepMem& m, int p, int i) { P64 q; q.x = m.vxs[p * NV + i]; q.y = m.vys[p * NV + i]; return q; }
     int sw;                                   // slot q holds ring q ^ sw
     // current edge of every bound (clipper.cpp:66-84 TEdge, reduced like szclip::Edge)
     SZ_EDGE_FIELD(i64, botx, 0); SZ_EDGE_FIELD(i64, boty, 1); SZ_EDGE_FIELD(i64, topx, 2); SZ_EDGE_FIELD(i64, topy, 3); SZ_EDGE_FIELD(i64, curx, 4);
@@ -122,7 +121,20 @@ struct ConvexSweep {
     SZ_HD void set_bail(int r) { if (!bail) { bail = true; why = r; } }
 
     SZ_HD int ord_at(int k) const { return (int)((ordp >> (4 * k)) & 15u); }
-    SZ_HD int pos_of(int e) const { for (int k = 0; k < na; ++k) if (ord_at(k) == e) return k; return -1; }
+    // position of edge e in the AEL, -1 when absent: nibble k of ordp equals e exactly when nibble k of x is zero, and
+    // (x - 0x1111) & ~x & 0x8888 marks zero nibbles (its lowest mark is always a true one; an id occurs once among the first na)
+    SZ_HD int pos_of(int e) const
+    {
+        const unsigned x = (ordp ^ ((unsigned)e * 0x1111u)) & 0xffffu;
+        const unsigned z = (x - 0x1111u) & ~x & 0x8888u;
+        if (z == 0) return -1;
+#if defined(__CUDA_ARCH__)
+        const int k = (__ffs((int)z) - 1) >> 2;
+#else
+        const int k = __builtin_ctz(z) >> 2;
+#endif
+        return k < na ? k : -1;
+    }
     SZ_HD int pael(int e) const { const int k = pos_of(e); return k > 0 ? ord_at(k - 1) : NILE; }
     SZ_HD int nael(int e) const { const int k = pos_of(e); return (k >= 0 && k + 1 < na) ? ord_at(k + 1) : NILE; }
     SZ_HD bool bit(unsigned m, int e) const { return ((m >> e) & 1u) != 0; }
@@ -140,12 +152,13 @@ struct ConvexSweep {
     {
         const int p = (e >> 1) ^ sw, nn = n[p], st = bit(f_back, e) ? -1 : 1;
         int to = from + st; if (to >= nn) to -= nn; else if (to < 0) to += nn;
-        const i64 bx = vxat(m, p, from), by = vyat(m, p, from), tx = vxat(m, p, to), ty = vyat(m, p, to);
+        const P64 pb = vat(m, p, from), pt = vat(m, p, to);
+        const i64 bx = pb.x, by = pb.y, tx = pt.x, ty = pt.y;
         wr4(botx, e, bx); wr4(boty, e, by); wr4(topx, e, tx); wr4(topy, e, ty); wr4(vi, e, to); wr4(curx, e, bx);
         if (ty >= by) { set_bail(1); return; }                           // horizontal (or not a bound of a convex path)
         wr4(dx, e, fp::div(fp::cvt(tx - bx), fp::cvt(ty - by)));
         int nx = to + st; if (nx >= nn) nx -= nn; else if (nx < 0) nx += nn;
-        const i64 ny = vyat(m, p, nx);
+        const i64 ny = vat(m, p, nx).y;
         if (ny == ty) { set_bail(2); return; }                           // horizontal edge at the top of this one
         if (ny > ty) f_last |= 1u << e; else f_last &= ~(1u << e);
     }
@@ -391,7 +404,7 @@ struct ConvexSweep {
         for (int id = 0; id < 4; ++id) { botx[id] = boty[id] = topx[id] = topy[id] = curx[id] = 0; dx[id] = 0; vi[id] = 0; }
         if (n[0] < 3 || n[1] < 3 || n[0] > NV || n[1] > NV) { set_bail(17); return false; }
         // Reset :1247-1276: minima sorted by Y descending (std::sort of two elements is stable: the subject on a tie)
-        sw = (vyat(m, 1, 0) > vyat(m, 0, 0)) ? 1 : 0;
+        sw = (vat(m, 1, 0).y > vat(m, 0, 0).y) ? 1 : 0;
         SZ_UNROLL4
         for (int q = 0; q < 2; ++q) {
             // the two bounds of the path's single local minimum (AddPath :1172-1219): e = forward edge, e.prev = backward
@@ -450,9 +463,31 @@ struct ConvexSweep {
         // BuildIntersectList :2863-2868: Curr.X of every active edge at the top of the scanbeam
         SZ_UNROLL4
         for (int id = 0; id < 4; ++id) curx[id] = bit(act, id) ? top_x(id, top_y) : 0;
-        bool inv = false;
-        for (int k = 0; k + 1 < na; ++k) inv = inv || (rd4(curx, ord_at(k)) > rd4(curx, ord_at(k + 1)));
-        if (inv) {
+        // Curr.X in AEL order; positions behind the list compare as "in order"
+        const i64 big = 0x7fffffffffffffffLL;
+        const i64 c0 = na > 0 ? rd4(curx, ord_at(0)) : big, c1 = na > 1 ? rd4(curx, ord_at(1)) : big, c2 = na > 2 ? rd4(curx, ord_at(2)) : big, c3 = na > 3 ? rd4(curx, ord_at(3)) : big;
+        const bool i01 = c0 > c1, i12 = c1 > c2, i23 = c2 > c3;
+        const bool inv = i01 || i12 || i23;
+        // The usual scanbeam with an intersection has exactly ONE: two neighbours change places and fit between their outer
+        // neighbours afterwards.  BuildIntersectList's bubble sort (:2871-2900) then swaps that one pair in its first pass and
+        // nothing in its second, the list has one node, FixupIntersectionOrder (:2934) is not entered: the node is processed here
+        // directly, without the 12-comparison order matrix and the sort (they were 9 % of class C's instructions at 5 of 32 lanes).
+        bool simple = false; int ks = 0;
+#if !defined(SZ_CVX_NO_SIMPLE_IL)
+        if (((int)i01 + (int)i12 + (int)i23) == 1) {
+            ks = i01 ? 0 : (i12 ? 1 : 2);
+            const i64 lft = i01 ? -big - 1 : (i12 ? c0 : c1), a = i01 ? c0 : (i12 ? c1 : c2), b = i01 ? c1 : (i12 ? c2 : c3), rgt = i01 ? c2 : (i12 ? c3 : big);
+            simple = lft <= b && a <= rgt;
+        }
+#endif
+        if (simple) {
+            const int e = ord_at(ks), en = ord_at(ks + 1);
+            P64 pt = intersect_point(e, en);
+            if (pt.y < top_y) { pt.x = top_x(e, top_y); pt.y = top_y; }
+            intersect_edges(m, e, en, pt);                       // ProcessIntersectList :2906-2918
+            ordp = swap_nibbles(ordp, ks, ks + 1);
+            if (bail) return false;
+        } else if (inv) {
             unsigned gt = 0;
             SZ_UNROLL4
             for (int a = 0; a < 4; ++a) {

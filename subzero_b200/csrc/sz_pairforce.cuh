@@ -287,9 +287,35 @@ SZ_HD int ring_bottom_vertex(const Getter& get, int n)
 
 // FP64 Sutherland-Hodgman clip of the convex polygon S by the convex polygon K (open rings).  Used ONLY to decide
 // the sign test of floe_interactions.m:151-165 when the decision has a wide margin (see convex_sign_test); never to
-// produce a polygon that is output.  Returns the vertex count in (ox, oy), or -1 when a buffer would overflow.
+// produce a polygon that is output.  Returns the vertex count with (*rx, *ry) pointing at the result (one of the two
+// buffers the caller passed), or -1 when a buffer would overflow.
+//
+// One pass per edge line of K.  A line cuts a convex ring in at most two places, so for rings of up to 32 vertices the
+// pass first takes the side of every vertex into a bit mask (a uniform loop: the lanes of a warp clip different pairs),
+// and then: all inside -> the ring is left where it is (most edges of K do not reach the overlap strip at all);
+// all outside -> empty; one inside run -> [entry point, the run, exit point] goes to the other buffer, the two
+// intersection points computed by all lanes at once instead of wherever each lane's loop happens to meet them (the
+// one-lane-at-a-time divisions were 4 % of class C's instructions).  Anything else (a ring that rounding left
+// non-convex, more than 32 vertices) takes the vertex-by-vertex loop.  The ring may come out rotated against that loop's;
+// its area is compared with a margin six orders of magnitude above the rounding either way.
+SZ_HD int sz_popc32(unsigned v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+SZ_HD int sz_ctz32(unsigned v)     // v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
 SZ_HD int sh_clip_convex(const double* sx, const double* sy, int ns, double shx, double shy, const double* kx, const double* ky, int nk,
-                         double* ax, double* ay, double* bx, double* by, int cap)
+                         double* ax, double* ay, double* bx, double* by, int cap, const double** rx, const double** ry)
 {
     if (ns > cap) return -1;
     for (int i = 0; i < ns; ++i) { ax[i] = sx[i] + shx; ay[i] = sy[i] + shy; }
@@ -300,31 +326,65 @@ SZ_HD int sh_clip_convex(const double* sx, const double* sy, int ns, double shx,
     for (int e = 0; e < nk && n > 0; ++e) {
         const int e1 = (e + 1 == nk) ? 0 : e + 1;
         const double px = kx[e], py = ky[e], dx = kx[e1] - px, dy = ky[e1] - py;
+#if !defined(SZ_SH_PLAIN)
+        if (n <= 32) {
+            unsigned in = 0;
+            for (int i = 0; i < n; ++i) { if (sK * (dx * (ay[i] - py) - dy * (ax[i] - px)) >= 0) in |= 1u << i; }
+            const unsigned full = (n == 32) ? 0xffffffffu : ((1u << n) - 1u);
+            if (in == full) continue;
+            if (in == 0) { n = 0; break; }
+            const unsigned prev = ((in << 1) | (in >> (n - 1))) & full;      // bit i: the side of vertex i - 1
+            const unsigned tr = in ^ prev;
+            if (sz_popc32(tr) == 2) {
+                const int s = sz_ctz32(tr & in), t = sz_ctz32(tr & ~in);     // first vertex of the inside run, first vertex behind it
+                int run = t - s; if (run < 0) run += n;
+                if (run + 2 > cap) return -1;
+                {
+                    const int q = (s == 0) ? n - 1 : s - 1;
+                    const double qx = ax[q], qy = ay[q], rx_ = ax[s], ry_ = ay[s];
+                    const double dq = sK * (dx * (qy - py) - dy * (qx - px)), dr = sK * (dx * (ry_ - py) - dy * (rx_ - px));
+                    const double u = dq / (dq - dr);
+                    bx[0] = qx + u * (rx_ - qx); by[0] = qy + u * (ry_ - qy);
+                }
+                for (int k = 0, i = s; k < run; ++k) { bx[1 + k] = ax[i]; by[1 + k] = ay[i]; if (++i == n) i = 0; }
+                {
+                    const int q = (t == 0) ? n - 1 : t - 1;
+                    const double qx = ax[q], qy = ay[q], rx_ = ax[t], ry_ = ay[t];
+                    const double dq = sK * (dx * (qy - py) - dy * (qx - px)), dr = sK * (dx * (ry_ - py) - dy * (rx_ - px));
+                    const double u = dq / (dq - dr);
+                    bx[run + 1] = qx + u * (rx_ - qx); by[run + 1] = qy + u * (ry_ - qy);
+                }
+                double* t1 = ax; ax = bx; bx = t1; t1 = ay; ay = by; by = t1;
+                n = run + 2;
+                continue;
+            }
+        }
+#endif
         int m = 0;
         double qx = ax[n - 1], qy = ay[n - 1];
         double dq = sK * (dx * (qy - py) - dy * (qx - px));
         for (int i = 0; i < n; ++i) {
-            const double rx = ax[i], ry = ay[i];
-            const double dr = sK * (dx * (ry - py) - dy * (rx - px));
+            const double rx_ = ax[i], ry_ = ay[i];
+            const double dr = sK * (dx * (ry_ - py) - dy * (rx_ - px));
             if ((dq >= 0) != (dr >= 0)) {
                 if (m >= cap) return -1;
-                const double t = dq / (dq - dr);
-                bx[m] = qx + t * (rx - qx); by[m] = qy + t * (ry - qy); ++m;
+                const double u = dq / (dq - dr);
+                bx[m] = qx + u * (rx_ - qx); by[m] = qy + u * (ry_ - qy); ++m;
             }
-            if (dr >= 0) { if (m >= cap) return -1; bx[m] = rx; by[m] = ry; ++m; }
-            qx = rx; qy = ry; dq = dr;
+            if (dr >= 0) { if (m >= cap) return -1; bx[m] = rx_; by[m] = ry_; ++m; }
+            qx = rx_; qy = ry_; dq = dr;
         }
         double* t1 = ax; ax = bx; bx = t1; t1 = ay; ay = by; by = t1;
         n = m;
     }
-    // the result sits in (ax, ay) after the swaps: copy to the caller's first buffer if needed is left to the caller
-    return (nk & 1) ? -2 - n : n;      // odd number of swaps: result is in the (bx, by) the caller passed
+    *rx = ax; *ry = ay;
+    return n;
 }
 
 // Decides the sign test of floe_interactions.m:151-165 for a convex pair without clips #2/#3 when it can be decided
 // with margin.  The reference re-clips floe 1 nudged by force_dir (1 m) and flips force_dir once for every new
 // region that meets region k and is larger than it (:158-163).  For convex outlines the new intersection is one convex
-// region Q; this computes Q in FP64 (error ~1e-9 m per vertex, like Clipper's own 2^-32 m grid) and answers
+// region Q; this computes its area in FP64 (error ~1e-8 m^2) and answers
 //   -1  no flip:  area(Q) < Ak - tol  (no region of the new clip can exceed Ak, whatever its exact shape)
 //   +1  flip:     area(Q) > Ak + tol, and one disc of radius >= 1 mm lies inside both Q and region k
 //    0  undecided -> the caller runs the reference's clips.
@@ -336,14 +396,13 @@ SZ_HD int convex_sign_test(W& w, double fdx, double fdy, const i64* RX, const i6
     int n1 = w.n1, n2 = w.n2;
     while (n1 > 1 && w.c1x[n1 - 1] == w.c1x[0] && w.c1y[n1 - 1] == w.c1y[0]) --n1;
     while (n2 > 1 && w.c2x[n2 - 1] == w.c2x[0] && w.c2y[n2 - 1] == w.c2y[0]) --n2;
+    const double tol = 1e-6 * Ak + 1.0;
     const int cap = C::RV / 2;
     double* ax = reinterpret_cast<double*>(w.rbx); double* ay = ax + cap;
     double* bx = reinterpret_cast<double*>(w.rby); double* by = bx + cap;
-    int n = sh_clip_convex(w.c1x, w.c1y, n1, fdx, fdy, w.c2x, w.c2y, n2, ax, ay, bx, by, cap);
-    if (n == -1) return 0;
     const double* qx = ax; const double* qy = ay;
-    if (n <= -2) { n = -2 - n; qx = bx; qy = by; }
-    const double tol = 1e-6 * Ak + 1.0;
+    const int n = sh_clip_convex(w.c1x, w.c1y, n1, fdx, fdy, w.c2x, w.c2y, n2, ax, ay, bx, by, cap, &qx, &qy);
+    if (n < 0) return 0;
     if (n < 3) return (0.0 < Ak - tol) ? -1 : 0;
     double a2 = 0;
     for (int i = 0; i < n; ++i) { const int j = (i + 1 == n) ? 0 : i + 1; a2 += (qx[i] - qx[0]) * (qy[j] - qy[0]) - (qx[j] - qx[0]) * (qy[i] - qy[0]); }
@@ -362,9 +421,100 @@ SZ_HD int convex_sign_test(W& w, double fdx, double fdy, const i64* RX, const i6
     return 1;
 }
 
+// unique(...,'rows') of InterX.m:77 on the collected points: insertion sort by (x, then y), duplicates dropped
+template <class W>
+SZ_HD void interx_sort_unique(W& w, int np)
+{
+    for (int i = 1; i < np; ++i) {
+        double vx = w.px[i], vy = w.py[i]; int k = i - 1;
+        while (k >= 0 && (w.px[k] > vx || (w.px[k] == vx && w.py[k] > vy))) { w.px[k + 1] = w.px[k]; w.py[k + 1] = w.py[k]; --k; }
+        w.px[k + 1] = vx; w.py[k + 1] = vy;
+    }
+    int m = 0;
+    for (int i = 0; i < np; ++i) if (m == 0 || !(w.px[i] == w.px[m - 1] && w.py[i] == w.py[m - 1])) { w.px[m] = w.px[i]; w.py[m] = w.py[i]; ++m; }
+    w.np = m;
+}
+
+// InterX.m:54-77 for outlines of at most 32 segments each (classes C and S), arranged so that the lanes of a warp -- which
+// resolve different pairs -- stay together.  The reference evaluates, for every (segment i of curve 1, segment j of curve 2),
+//   test a  (a0 - S1)(a1 - S1) <= 0   the ends of segment j lie on different sides of the line of segment i,
+//   test b  (b0 - S2)(b1 - S2) <= 0   the same the other way round,
+// and computes a point where both hold and the segments are not parallel.  Written as one doubly nested loop with early
+// `continue`s (interx_general below) the few lanes that pass test a run test b, and the one or two that pass both run the two
+// divisions, while the rest of the warp waits: 2.1 of 32 lanes in the profile of class C.  Here the two tests are two uniform
+// passes -- test a into one bit mask per segment of curve 1, then test b, recording the (j, i) that pass both in the
+// reference's order (j outer, i inner) -- and the points are computed in a third loop in which almost every lane has the
+// same two hits.  Every expression is the reference's own (a1 of segment j is a0 of segment j + 1: the same operands, the
+// same rounding), so the points are bit-identical.
+#ifndef SZ_INTERX_HITS
+#define SZ_INTERX_HITS 12
+#endif
+template <class C, class W>
+SZ_HD bool interx_general(W& w);
+template <class C, class W>
+SZ_HD bool interx_masked(W& w)
+{
+    const int n1 = w.n1 - 1, n2 = w.n2 - 1;
+    if (n1 > 32 || n2 > 32 || n1 > C::NV || n2 > C::NV) return interx_general<C>(w);
+    // scratch in the clip #2 region buffers, idle between clip #1 and the sign test -- and in their MIDDLE, where the convex
+    // sweep's output deque has just been (class C's time follows the distinct local-memory lines a thread touches)
+    static_assert(C::RV >= 40 && (C::RV / 2 - 4) * sizeof(i64) + 32 * sizeof(int) <= C::RV * sizeof(i64), "rbx holds the masks");
+    static_assert((C::RV / 2 - 4) * sizeof(i64) + SZ_INTERX_HITS * sizeof(int) <= C::RV * sizeof(i64), "rby holds the hit list");
+    unsigned* passA = reinterpret_cast<unsigned*>(w.rbx + (C::RV / 2 - 4));
+    for (int i = 0; i < n1; ++i) {
+        const double x1a = w.c1x[i], y1a = w.c1y[i], x1b = w.c1x[i + 1], y1b = w.c1y[i + 1];
+        const double dx1 = x1b - x1a, dy1 = y1b - y1a;
+        const double S1 = dx1 * y1a - dy1 * x1a;
+        double prev = (dx1 * w.c2y[0] - dy1 * w.c2x[0]) - S1;
+        unsigned m = 0;
+        for (int j = 0; j < n2; ++j) {
+            const double nxt = (dx1 * w.c2y[j + 1] - dy1 * w.c2x[j + 1]) - S1;
+            if ((prev * nxt) <= 0) m |= 1u << j;
+            prev = nxt;
+        }
+        passA[i] = m;
+    }
+    int* hits = reinterpret_cast<int*>(w.rby + (C::RV / 2 - 4)); int nh = 0;
+    for (int j = 0; j < n2; ++j) {
+        const double x2a = w.c2x[j], y2a = w.c2y[j], x2b = w.c2x[j + 1], y2b = w.c2y[j + 1];
+        const double dx2 = x2b - x2a, dy2 = y2b - y2a;
+        const double S2 = dx2 * y2a - dy2 * x2a;
+        double prev = (w.c1y[0] * dx2 - w.c1x[0] * dy2) - S2;
+        for (int i = 0; i < n1; ++i) {
+            const double nxt = (w.c1y[i + 1] * dx2 - w.c1x[i + 1] * dy2) - S2;
+            if (((prev * nxt) <= 0) && ((passA[i] >> j) & 1u)) { if (nh < SZ_INTERX_HITS) hits[nh] = (j << 8) | i; ++nh; }
+            prev = nxt;
+        }
+    }
+    if (nh > SZ_INTERX_HITS) return interx_general<C>(w);       // many touching segments: the plain loop handles any number
+    int np = 0;
+    for (int t = 0; t < nh; ++t) {
+        const int j = hits[t] >> 8, i = hits[t] & 255;
+        const double x1a = w.c1x[i], y1a = w.c1y[i], x2a = w.c2x[j], y2a = w.c2y[j];
+        const double dx1 = w.c1x[i + 1] - x1a, dy1 = w.c1y[i + 1] - y1a, dx2 = w.c2x[j + 1] - x2a, dy2 = w.c2y[j + 1] - y2a;
+        const double S1 = dx1 * y1a - dy1 * x1a, S2 = dx2 * y2a - dy2 * x2a;
+        const double L = dy2 * dx1 - dy1 * dx2;
+        if (L == 0) continue;
+        if (np >= C::NP) return false;
+        w.px[np] = (dx2 * S1 - dx1 * S2) / L;
+        w.py[np] = (dy2 * S1 - dy1 * S2) / L;
+        ++np;
+    }
+    interx_sort_unique(w, np);
+    return true;
+}
+
 // InterX.m:54-77 (two-curve form).  Points are collected, sorted (x, then y) and de-duplicated.
 template <class C, class W>
 SZ_HD bool interx(W& w)
+{
+#if !defined(SZ_INTERX_PLAIN)
+    if constexpr (C::NV <= 33) return interx_masked<C>(w);
+#endif
+    return interx_general<C>(w);
+}
+template <class C, class W>
+SZ_HD bool interx_general(W& w)
 {
     const int n1 = w.n1 - 1, n2 = w.n2 - 1;
     int np = 0;
@@ -388,15 +538,7 @@ SZ_HD bool interx(W& w)
             ++np;
         }
     }
-    // unique(...,'rows')
-    for (int i = 1; i < np; ++i) {
-        double vx = w.px[i], vy = w.py[i]; int k = i - 1;
-        while (k >= 0 && (w.px[k] > vx || (w.px[k] == vx && w.py[k] > vy))) { w.px[k + 1] = w.px[k]; w.py[k + 1] = w.py[k]; --k; }
-        w.px[k + 1] = vx; w.py[k + 1] = vy;
-    }
-    int m = 0;
-    for (int i = 0; i < np; ++i) if (m == 0 || !(w.px[i] == w.px[m - 1] && w.py[i] == w.py[m - 1])) { w.px[m] = w.px[i]; w.py[m] = w.py[i]; ++m; }
-    w.np = m;
+    interx_sort_unique(w, np);
     return true;
 }
 
@@ -472,6 +614,134 @@ template <class W>
 SZ_HD double abs_poly_dist(const W& w, double xq, double yq) { return abs_poly_dist_xy(w.c1x, w.c1y, w.n1, xq, yq); }
 template <class W>
 SZ_HD bool outline_ok_for_poly_dist(const W& w) { return outline_ok_for_poly_dist_xy(w.c1x, w.c1y, w.n1); }
+
+// ------------------------------------------------------------------------------------------------
+// The general contact-direction branch (floe_interactions.m:117-137) done by the 32 lanes of a warp for ONE of them.
+// The branch is rare (0.7 % of the overlap regions of the packed Voronoi field: InterX found a number of points other than two
+// near the region's vertices) and long: for every edge of the region one inpolygon() of a probe point against the region
+// and one p_poly_dist() of the edge's midpoint against floe 1's outline -- about 6,000 instructions that a single lane used
+// to run while the other 31, and with the CTA-wide votes of class C the other 15 warps, waited: leaving the branch out
+// (a timing experiment with wrong results) made class C 0.6 ms = 8 % faster.  Here lane src's region and outline are dealt
+// out over the lanes (vertex l to lane l), every lane evaluates its own edge of the region for inpolygon and its own vertex
+// and segment of the outline for p_poly_dist, and the lanes combine: the winding sum is a sum of small integers (exact in
+// any order), the two minima of p_poly_dist are "first index of the smallest value", which a (value, index) reduction
+// reproduces.  Every term is the expression the one-lane code evaluates (in_region, abs_poly_dist_xy above), so the
+// result is bit-identical; a NaN anywhere makes the function return false and the lane runs the one-lane code.
+// Needs nr <= 32 region vertices and n1 <= 32 outline points (the caller checks), all 32 lanes converged.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void warp_argmin_first(double& v, int& i)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, d); const int oi = __shfl_xor_sync(0xffffffffu, i, d);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+__device__ __forceinline__ bool coop_general_direction(int src, int lane, const i64* RX, const i64* RY, int nr_, const double* c1x, const double* c1y, int n1_,
+                                                       double force_factor_, double on_edge_tol, double& ofx, double& ofy, double& odl)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int NR = __shfl_sync(FULL, nr_, src), N1 = __shfl_sync(FULL, n1_, src);
+    const double ff = __shfl_sync(FULL, force_factor_, src);
+    // deal out: lane l keeps region vertex l (metres, as the one-lane code converts it at every use) and outline point l
+    double rx = 0, ry = 0, ox = 0, oy = 0;
+    const int nmax = NR > N1 ? NR : N1;
+    for (int j = 0; j < nmax; ++j) {
+        double a = 0, b = 0, c = 0, d = 0;
+        if (lane == src) {
+            if (j < NR) { a = (double)RX[j] / SZ_SCALE; b = (double)RY[j] / SZ_SCALE; }
+            if (j < N1) { c = c1x[j]; d = c1y[j]; }
+        }
+        a = __shfl_sync(FULL, a, src); b = __shfl_sync(FULL, b, src); c = __shfl_sync(FULL, c, src); d = __shfl_sync(FULL, d, src);
+        if (lane == j) { rx = a; ry = b; ox = c; oy = d; }
+    }
+    // neighbours: next region vertex (closed ring), next outline point
+    const int ln = (lane + 1 >= NR) ? 0 : lane + 1;
+    const double rxn = __shfl_sync(FULL, rx, ln), ryn = __shfl_sync(FULL, ry, ln);
+    const int lo = (lane + 1 > 31) ? 31 : lane + 1;
+    const double oxn = __shfl_sync(FULL, ox, lo), oyn = __shfl_sync(FULL, oy, lo);
+    // bounding box of the region (inpolygon's quick reject)
+    double xmin = lane < NR ? rx : SZ_INF, xmax = lane < NR ? rx : -SZ_INF, ymin = lane < NR ? ry : SZ_INF, ymax = lane < NR ? ry : -SZ_INF;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(FULL, xmin, d)); xmax = fmax(xmax, __shfl_xor_sync(FULL, xmax, d));
+        ymin = fmin(ymin, __shfl_xor_sync(FULL, ymin, d)); ymax = fmax(ymax, __shfl_xor_sync(FULL, ymax, d));
+    }
+    // this lane's segment of the outline in p_poly_dist's rotated frame (does not depend on the query point)
+    const int ns = N1 - 1;
+    double vds = 0, ct = 0, st = 0, p1rx = 0, p1ry = 0;
+    if (lane < ns) {
+        const double dvx = oxn - ox, dvy = oyn - oy;
+        vds = hypot(dvx, dvy);
+        ct = dvx / vds; st = dvy / vds;
+        p1rx = ct * ox + st * oy;
+        p1ry = -st * ox + ct * oy;
+    }
+    bool bad = false;
+    double sx = 0, sy = 0, sb = 0; int non = 0;
+    for (int e = 0; e < NR; ++e) {
+        const int e1 = (e + 1 == NR) ? 0 : e + 1;
+        const double xa = __shfl_sync(FULL, rx, e), ya = __shfl_sync(FULL, ry, e), xb = __shfl_sync(FULL, rx, e1), yb = __shfl_sync(FULL, ry, e1);
+        const double xgh = xb - xa, ygh = yb - ya, xm = (xb + xa) / 2, ym = (yb + ya) / 2;
+        const double b = sqrt(xgh * xgh + ygh * ygh);
+        double nx = -ygh / b, ny = xgh / b;
+        const double xt = xm + nx / 100, yt = ym + ny / 100;
+        // inpolygon(xt, yt, region): lane m evaluates edge m -> m + 1
+        bool inside = false;
+        if (xt >= xmin && xt <= xmax && yt >= ymin && yt <= ymax) {
+            int dqi = 0; bool on = false;
+            if (lane < NR) {
+                const double vx0 = rx - xt, vy0 = ry - yt, vx1 = rxn - xt, vy1 = ryn - yt;
+                const bool px0 = vx0 > 0, py0 = vy0 > 0, px1 = vx1 > 0, py1 = vy1 > 0;
+                const double q0 = (double)((!px0 && py0) + 2 * (!px0 && !py0) + 3 * (px0 && !py0));
+                const double q1 = (double)((!px1 && py1) + 2 * (!px1 && !py1) + 3 * (px1 && !py1));
+                const double avx = fabs(0.5 * (rx + rxn)), avy = fabs(0.5 * (ry + ryn));
+                double sf = avx > avy ? avx : avy; const double pr = avx * avy; if (pr > sf) sf = pr;
+                const double seps = sf * SZ_EPS * 3;
+                const double cross = vx0 * vy1 - vx1 * vy0;
+                double sgn = (double)((cross > 0) - (cross < 0));
+                if (fabs(cross) < seps) sgn = 0;
+                const double dot = vx0 * vx1 + vy0 * vy1;
+                double dq = q1 - q0;
+                if (fabs(dq) == 3) dq = -dq / 3; else if (fabs(dq) == 2) dq = 2 * sgn;
+                dqi = (int)dq;                                  // -2 .. 2
+                on = (sgn == 0 && dot <= 0);
+                if (!(cross == cross) || !(dot == dot)) bad = true;
+            }
+            const int sum = __reduce_add_sync(FULL, dqi);
+            inside = (sum != 0) || __any_sync(FULL, on);
+        }
+        if (!inside) { nx = -nx; ny = -ny; }
+        // |p_poly_dist(xm, ym, outline)|: lane k evaluates vertex k and segment k -> k + 1
+        double dv = SZ_INF; int iv = 0x7fffffff;
+        if (lane < N1) {
+            const double a = fabs(hypot(ox - xm, oy - ym));
+            if (a < SZ_INF) { dv = a; iv = lane; }
+            if (!(a == a)) bad = true;
+        }
+        warp_argmin_first(dv, iv);
+        if (iv == 0x7fffffff) iv = 0;
+        double dc = SZ_INF; int ic = 0x7fffffff; bool have = false;
+        if (lane < ns) {
+            const double r = (xm * ct + ym * st) - p1rx;
+            const double cr = (xm * (-st) + ym * ct) - p1ry;
+            if (r > 0 && r < vds) { have = true; dc = fabs(cr); ic = lane; if (!(cr == cr)) bad = true; }
+        }
+        have = __any_sync(FULL, have);
+        warp_argmin_first(dc, ic);
+        const bool is_vertex = !have || ((ic != iv) && (dc - dv) > 0);
+        const double dist = is_vertex ? dv : dc;
+        if (dist < on_edge_tol) { sx += (-ff * b) * nx; sy += (-ff * b) * ny; sb += b; ++non; }
+    }
+    if (__any_sync(FULL, bad)) return false;
+    ofx = 0; ofy = 0; odl = 0;
+    if (non < NR && non > 0) {
+        const double nrm = sqrt(sx * sx + sy * sy);
+        ofx = sx / nrm; ofy = sy / nrm; odl = sb / (double)non;
+    }
+    return true;
+}
+#endif
 
 // normal + tangential force of one overlap region (floe_interactions.m:167-187): r = Fx Fy Px Py overlap
 SZ_HD void force_row(const Body& f1, const Body& f2, const Params& P, double G, double mu, double force_factor,
@@ -555,17 +825,15 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
         SZ_LANE_SYNC();
     }
     if constexpr (FAST && MODE != 2) {
+        bool run = false;
+        const bool go = valid && convex_pair && !boundary && hints.no1 >= 3 && hints.no2 >= 3;
+        ClipInput subj, clip;
+        subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = hints.no1; subj.ring = 0; subj.rot = hints.rot1;
+        clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = hints.no2; clip.ring = 0; clip.rot = hints.rot2;
         static_assert(C::NP >= 2 * C::NV, "the InterX buffers must hold both int64 outlines");
         szcvx::ConvexSweep<C::NV> cs;
         const szcvx::SweepMem mem{w.svx, w.svy, w.rbx, w.rby, C::RV};       // outlines in the InterX buffers, deque in the clip #2 buffers
-        bool run = false;
-        const bool go = valid && convex_pair && !boundary && hints.no1 >= 3 && hints.no2 >= 3;
-        if (go) {
-            ClipInput subj, clip;
-            subj.x = w.c1x; subj.y = w.c1y; subj.dx = 0; subj.dy = 0; subj.ix = subj.iy = 0; subj.n = hints.no1; subj.ring = 0; subj.rot = hints.rot1;
-            clip.x = w.c2x; clip.y = w.c2y; clip.dx = 0; clip.dy = 0; clip.ix = clip.iy = 0; clip.n = hints.no2; clip.ring = 0; clip.rot = hints.rot2;
-            cs.load_ring(mem, 0, subj, subj.n); cs.load_ring(mem, 1, clip, clip.n);
-        }
+        if (go) { cs.load_ring(mem, 0, subj, subj.n); cs.load_ring(mem, 1, clip, clip.n); }
         SZ_LANE_SYNC();
         if (go) run = cs.begin(mem);
 #ifndef SZ_C_STEPS_PER_SYNC
@@ -761,6 +1029,25 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
             }
         }
         SZ_LANE_SYNC();
+        // the general branch (:117-137) of the lanes that need it, one lane at a time with the whole warp working on it
+        bool coop_done = false; double cfx = 0, cfy = 0, cdl = 0;
+#if defined(__CUDA_ARCH__) && defined(SZ_COOP_GENERAL)
+        {
+            bool ask = next_region && Ak != 0 && m != 2 && m != 0 && nr <= 32 && w.n1 <= 32;
+            if (ask) {
+                if (!outline_checked) { outline_ok = outline_ok_for_poly_dist(w); outline_checked = true; }
+                ask = outline_ok;
+            }
+            unsigned req = __ballot_sync(0xffffffffu, ask);
+            const int lane = threadIdx.x & 31;
+            while (req) {
+                const int src = __ffs((int)req) - 1; req &= req - 1;
+                double gx = 0, gy = 0, gl = 0;
+                const bool good = coop_general_direction(src, lane, RX, RY, nr, w.c1x, w.c1y, w.n1, force_factor, P.on_edge_tol, gx, gy, gl);
+                if (lane == src && good) { coop_done = true; cfx = gx; cfy = gy; cdl = gl; }
+            }
+        }
+#endif
         if (next_region) {
             fdx = 0; fdy = 0; dl = 0; pcx = cx; pcy = cy;
             if (Ak == 0) { pcx = 0; pcy = 0; }                                        // :103-106
@@ -768,7 +1055,8 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
                 double xgh = p1x - p0x, ygh = p1y - p0y;
                 double b = sqrt(xgh * xgh + ygh * ygh);
                 fdx = -ygh / b; fdy = xgh / b; dl = b;
-            } else if (m != 0) {
+            } else if (m != 0 && coop_done) { fdx = cfx; fdy = cfy; dl = cdl; }
+            else if (m != 0) {
                 // general branch (:117-137), streamed edge by edge
                 if (!outline_checked) { outline_ok = outline_ok_for_poly_dist(w); outline_checked = true; }
                 if (!outline_ok) { res.status = PS_BAD_POLY; phase = PH_DONE; next_region = false; }

@@ -10,5 +10,5 @@ for n in sizes:
     for it in range(3):
         t = time.time(); s = ctx.step_resident(); w = time.time() - t
         print(n, it, 'pairs', s.n_pairs, 'force', s.n_pairs_force, 'rows', s.n_rows, 'ms', round(s.ms_device, 3), 'wall_ms', round(w * 1e3, 3),
-              'pairs/s %.3e' % (s.n_pairs / s.ms_device * 1e3), {k: round(v, 3) for k, v in ctx.phase_ms().items()}, flush=True)
+              'pairs/s %.3e' % (s.n_pairs / s.ms_device * 1e3), {k: round(v, 3) for k, v in ctx.phase_ms().items()}, 'classC', round(ctx.narrow_class_ms()['C'][0], 3), flush=True)
     ctx.close()
