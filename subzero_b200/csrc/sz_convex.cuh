@@ -544,19 +544,28 @@ struct ConvexSweep {
         if (n_or == 0) return CV_OK;
         const int cnt = hi - lo + 1;
         // ring in Next order from Pts: r(t) = d[lo + t].  Area :406-416
+        // (both loops carry the previous vertices over in registers: one load of each deque entry per loop)
         double ar = 0;
-        for (int t = 0; t < cnt; ++t) {
-            const int c = lo + t, pv = (t == 0) ? hi : c - 1;
-            ar = fp::add(ar, fp::mul(fp::cvt(m.dqx[pv] + m.dqx[c]), fp::cvt(m.dqy[pv] - m.dqy[c])));
+        {
+            P64 pv; pv.x = m.dqx[hi]; pv.y = m.dqy[hi];
+            for (int t = 0; t < cnt; ++t) {
+                P64 c; c.x = m.dqx[lo + t]; c.y = m.dqy[lo + t];
+                ar = fp::add(ar, fp::mul(fp::cvt(pv.x + c.x), fp::cvt(pv.y - c.y)));
+                pv = c;
+            }
         }
         ar = fp::mul(ar, 0.5);
         const bool rev = !(ar > 0);        // :1594-1600: not a hole, so reversed unless the area is positive
         // FixupOutPolygon :3143-3181 would remove duplicate / collinear points: outside the model
         if (cnt < 3) { why = 14; return CV_BAIL; }
-        for (int t = 0; t < cnt; ++t) {
-            const int c = lo + t, pv = (t == 0) ? hi : c - 1, nx = (t == cnt - 1) ? lo : c + 1;
-            P64 A, B, C; A.x = m.dqx[pv]; A.y = m.dqy[pv]; B.x = m.dqx[c]; B.y = m.dqy[c]; C.x = m.dqx[nx]; C.y = m.dqy[nx];
-            if (B == C || B == A || szclip::slopes_eq3(A, B, C)) { why = 15; return CV_BAIL; }
+        {
+            P64 A, B; A.x = m.dqx[hi]; A.y = m.dqy[hi]; B.x = m.dqx[lo]; B.y = m.dqy[lo];
+            for (int t = 0; t < cnt; ++t) {
+                const int nx = (t == cnt - 1) ? lo : lo + t + 1;
+                P64 C; C.x = m.dqx[nx]; C.y = m.dqy[nx];
+                if (B == C || B == A || szclip::slopes_eq3(A, B, C)) { why = 15; return CV_BAIL; }
+                A = B; B = C;
+            }
         }
         if (cnt > ocap) { why = 16; return CV_BAIL; }
         // BuildResult :3199-3217: start at Pts->Prev, walk Prev

@@ -1031,7 +1031,7 @@ SZ_HD void pair_force_impl(W& w, const Body& f1, const Body& f2, bool boundary, 
         SZ_LANE_SYNC();
         // the general branch (:117-137) of the lanes that need it, one lane at a time with the whole warp working on it
         bool coop_done = false; double cfx = 0, cfy = 0, cdl = 0;
-#if defined(__CUDA_ARCH__) && defined(SZ_COOP_GENERAL)
+#if defined(__CUDA_ARCH__) && !defined(SZ_NO_COOP_GENERAL)
         {
             bool ask = next_region && Ak != 0 && m != 2 && m != 0 && nr <= 32 && w.n1 <= 32;
             if (ask) {
