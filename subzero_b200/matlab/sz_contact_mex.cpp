@@ -52,10 +52,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
 {
     if (nrhs < 2 || nrhs > 3) mexErrMsgIdAndTxt("subzero_b200:arg", "usage: out = sz_contact_mex(prm, soa [, bnd])");
     if (nlhs > 1) mexErrMsgIdAndTxt("subzero_b200:arg", "one output");
-    if (!g_ctx) {
-        if (sz_create(&g_ctx, 0) != SZ_OK) fail(SZ_ERR_CUDA);
-        mexAtExit(release_ctx);
-    }
+    // every argument is checked before the device is touched (mexclipper.cpp:22-41 checks before it converts)
     SzParams P; sz_default_params(&P);
     const mxArray* p = prhs[0];
     P.Lx = scalar_field(p, "Lx", 0, true); P.Ly = scalar_field(p, "Ly", 0, true);
@@ -88,7 +85,14 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
         B.n = (int32_t)mxGetNumberOfElements(need_field(b, "x", 3)); B.x = mxGetPr(need_field(b, "x", 3)); B.y = mxGetPr(need_field(b, "y", (size_t)B.n));
         B.box_n = (int32_t)mxGetNumberOfElements(need_field(b, "box_x", 3)); B.box_x = mxGetPr(need_field(b, "box_x", 3)); B.box_y = mxGetPr(need_field(b, "box_y", (size_t)B.box_n));
         B.area = scalar_field(b, "area", 0, true); B.h = scalar_field(b, "h", 0, false);
+        // floebound's own kinematics (floe_interactions.m:109-110 reads floe2.Ui / Vi / ksi_ice / Xi / Yi of the boundary too); zero when absent
+        B.xi = scalar_field(b, "xi", 0, false); B.yi = scalar_field(b, "yi", 0, false);
+        B.u = scalar_field(b, "u", 0, false); B.v = scalar_field(b, "v", 0, false); B.ksi = scalar_field(b, "ksi", 0, false);
         pB = &B;
+    }
+    if (!g_ctx) {
+        if (sz_create(&g_ctx, 0) != SZ_OK) fail(SZ_ERR_CUDA);
+        mexAtExit(release_ctx);
     }
     SzSummary S;
     int rc = sz_contact_step(g_ctx, &P, &F, pB, &S);

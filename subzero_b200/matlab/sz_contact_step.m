@@ -23,7 +23,8 @@ function [Floe, kill, transfer, ghosts] = sz_contact_step(Floe, floebound, c2_bo
     else
         hv = holes(floebound.poly).Vertices;                 % floe_interactions.m:31
         bnd = struct('x', hv(:,1), 'y', hv(:,2), 'box_x', c2_boundary(1,:)', 'box_y', c2_boundary(2,:)', ...
-                     'area', floebound.area, 'h', floebound.h);
+                     'area', floebound.area, 'h', floebound.h, 'xi', floebound.Xi, 'yi', floebound.Yi, ...
+                     'u', floebound.Ui, 'v', floebound.Vi, 'ksi', floebound.ksi_ice);   % floe_interactions.m:171 reads them (zeros in Subzero.m)
         out = sz_contact_mex(prm, soa, bnd);
     end
     for i = 1+Nb:N0

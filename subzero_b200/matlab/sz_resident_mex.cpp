@@ -115,6 +115,8 @@ static void cmd_upload(int nrhs, const mxArray* prhs[])
         B.n = (int32_t)mxGetNumberOfElements(need_field(b, "x", 3)); B.x = mxGetPr(need_field(b, "x", 3)); B.y = mxGetPr(need_field(b, "y", (size_t)B.n));
         B.box_n = (int32_t)mxGetNumberOfElements(need_field(b, "box_x", 3)); B.box_x = mxGetPr(need_field(b, "box_x", 3)); B.box_y = mxGetPr(need_field(b, "box_y", (size_t)B.box_n));
         B.area = scalar_field(b, "area", 0, true); B.h = scalar_field(b, "h", 0, false);
+        B.xi = scalar_field(b, "xi", 0, false); B.yi = scalar_field(b, "yi", 0, false);
+        B.u = scalar_field(b, "u", 0, false); B.v = scalar_field(b, "v", 0, false); B.ksi = scalar_field(b, "ksi", 0, false);
         pB = &B;
     }
     check(sz_upload(g_ctx, &P, &F, pB));

@@ -26,7 +26,8 @@ function [Floe, kill, transfer, info] = sz_resident_timestep(Floe, floebound, oc
             sz_resident_mex('upload', prm, soa);
         else
             hv = holes(floebound.poly).Vertices;                 % floe_interactions.m:31
-            bnd = struct('x', hv(:,1), 'y', hv(:,2), 'box_x', c2_boundary(1,:)', 'box_y', c2_boundary(2,:)', 'area', floebound.area, 'h', floebound.h);
+            bnd = struct('x', hv(:,1), 'y', hv(:,2), 'box_x', c2_boundary(1,:)', 'box_y', c2_boundary(2,:)', 'area', floebound.area, 'h', floebound.h, ...
+                         'xi', floebound.Xi, 'yi', floebound.Yi, 'u', floebound.Ui, 'v', floebound.Vi, 'ksi', floebound.ksi_ice);
             sz_resident_mex('upload', prm, soa, bnd);
         end
         z = @(name) cat(1, Floe.(name));

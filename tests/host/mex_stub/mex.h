@@ -1,5 +1,5 @@
-/* Minimal declarations of the MATLAB mex API, ONLY so that the gateway source can be syntax-checked in a container
- * without MATLAB (tests/test_abi.py).  Not a MATLAB header and never shipped. */
+/* Minimal declarations of the MATLAB mex API, so that the gateway sources can be compiled in a container
+ * without MATLAB: syntax check in tests/test_abi.py, and the builds of tests/host/Makefile that run against mex_mock/.  Not a MATLAB header and never shipped. */
 #pragma once
 #include <stddef.h>
 typedef struct mxArray_tag mxArray;
@@ -12,4 +12,6 @@ double* mxGetPr(const mxArray*); double mxGetScalar(const mxArray*);
 mxArray* mxCreateDoubleMatrix(size_t, size_t, mxComplexity); mxArray* mxCreateDoubleScalar(double);
 mxArray* mxCreateStructMatrix(size_t, size_t, int, const char**); void mxSetFieldByNumber(mxArray*, size_t, int, mxArray*);
 void mexErrMsgIdAndTxt(const char*, const char*, ...); int mexAtExit(void (*)(void));
+/* like MATLAB's mex.h: the entry point has C linkage */
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]);
 }
