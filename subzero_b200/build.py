@@ -20,7 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"] + os.environ.get("SZ_EXTRA_NVCC", "").split()
 CU = ["sz_contact.cu", "sz_narrow_C.cu", "sz_narrow_S.cu", "sz_narrow_T.cu", "sz_narrow_M.cu", "sz_narrow_L.cu"]
 CPP = ["sz_field.cpp"]
-HEADERS = ["sz_clip.cuh", "sz_convex.cuh", "sz_pairforce.cuh", "sz_narrow.cuh", "sz_corners.cuh", "sz_euler.cuh", os.path.join("..", "..", "include", "subzero_b200.h")]
+HEADERS = ["sz_clip.cuh", "sz_convex.cuh", "sz_pairforce.cuh", "sz_narrow.cuh", "sz_corners.cuh", "sz_euler.cuh", "sz_apart.cuh", os.path.join("..", "..", "include", "subzero_b200.h")]
 
 
 def kernel_stamp(files=("sz_narrow_C.cu", "sz_narrow.cuh", "sz_convex.cuh", "sz_pairforce.cuh", "sz_clip.cuh")):

@@ -20,6 +20,7 @@
 #include "../../include/subzero_b200.h"
 #include "sz_narrow.cuh"
 #include "sz_corners.cuh"
+#include "sz_apart.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
@@ -97,6 +98,7 @@ struct Counters {
     int fr_vert_used, fr_changed;  // fracture deformation: vertices of the new outlines, floes changed
     int cr_n1, cr_n;               // corners.m's own periodic list: sizes after the x pass / after the y pass
     int eu_n1, eu_n2, eu_n, eu_yflag, eu_listL, eu_fail, eu_cap;   // calc_eulerian_data: list sizes (alive, + x images, + y images), the stale-polygon flag, class L items, failures
+    int any_concave;               // some AddPath-valid outline is not strictly convex (ext_prep_kernel): the classifier's edge-by-edge rule has work
 };
 
 struct SzContext {
@@ -114,6 +116,7 @@ struct SzContext {
     bool plan_valid = false; int plan_n0 = -1, plan_nl0 = -1, plan_ncap = 0, plan_npcap = 0; long long plan_rowscap = 0; struct GridDescHost { double x0, y0, cell; int nx, ny; } plan_g = {0, 0, 1, 1, 1};
     int n_fast_steps = 0, n_slow_steps = 0;
     int opt_convex_split = 0;        // experiment: class C as two kernels (sweep, then force law)
+    int opt_apart = 1;               // classifier: outlines of any shape certified apart edge by edge (sz_apart.cuh); 0 = bounding boxes only, as before
     int opt_euler_cell_warp = 1;     // calc_eulerian_data: a warp per cell (0: one thread per cell)
     Counters* d_cnt = nullptr; Counters* h_cnt = nullptr; Counters* h_init = nullptr;      // h_init: the step's initial counters (pinned; never the target of a read-back, so a replayed copy node finds them unchanged)
     // inputs
@@ -142,7 +145,7 @@ struct SzContext {
     // pairs
     int n_pairs = 0;
     DBuf<int> pcnt, pair_off, pi, pj, pstatus, pnrows, prow_start; DBuf<double> povl;
-    DBuf<int> stage, listC, listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb, erec /* EntryRec [n], 8 words each */; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno;
+    DBuf<int> stage, listC, listS, listT, wlistT, listM, listL, env, bins, bin_fill; /* bins: class-S work list buckets */ DBuf<i64> ebb, erec /* EntryRec [n], 8 words each */; DBuf<short> pkey; DBuf<uint8_t> evalid, econvex, erot, eno, papart /* per pair: certified apart */;
     DBuf<int> wstatus, wnrows, wrow_start, wlistM, wlistL; DBuf<double> wovl;
     DBuf<double> row_pool;
     DBuf<int> poly_path_start, poly_npaths, path_vstart, path_len; DBuf<i64> pvx, pvy;
@@ -520,7 +523,7 @@ struct __align__(16) EntryRec { i64 bb[4]; double x, y; int vo; short nv; unsign
 // whether the outline survives Clipper's AddPath (>= 3 vertices, not all collinear: clipper.cpp:1058,1119-1123).
 __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const double* __restrict__ ey, const int* __restrict__ esrc, const int* __restrict__ voff,
                                 const double* __restrict__ vx, const double* __restrict__ vy, i64* __restrict__ ebb, uint8_t* __restrict__ evalid, int* __restrict__ env,
-                                uint8_t* __restrict__ econvex, uint8_t* __restrict__ erot, uint8_t* __restrict__ eno, EntryRec* __restrict__ erec)
+                                uint8_t* __restrict__ econvex, uint8_t* __restrict__ erot, uint8_t* __restrict__ eno, EntryRec* __restrict__ erec, Counters* __restrict__ cnt)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -547,6 +550,7 @@ __global__ void ext_prep_kernel(int n, const double* __restrict__ ex, const doub
     while (no > 1 && vx[o + no - 1] == vx[o] && vy[o + no - 1] == vy[o]) --no;
     const bool cvx = valid && no <= 255 && szpf::ring_is_strictly_convex(Get{vx, vy, X, Y, o}, no);
     econvex[e] = cvx;
+    if (valid && !cvx) cnt->any_concave = 1;        // (every writer stores the same value)
     eno[e] = cvx ? (uint8_t)no : 0;
     erot[e] = cvx ? (uint8_t)szpf::ring_bottom_vertex(Get{vx, vy, X, Y, o}, no) : 0;     // start of the sweep input (PairHints)
     EntryRec r; r.bb[0] = xmn; r.bb[1] = xmx; r.bb[2] = ymn; r.bb[3] = ymx; r.x = X; r.y = Y; r.vo = o; r.nv = (short)(nv < 32767 ? nv : 32767); r.no = cvx ? (unsigned char)no : 0;
@@ -598,10 +602,32 @@ __device__ __forceinline__ bool sat_side_group(const double* __restrict__ vx, co
     }
     return found;
 }
+// Pre-pass of the classifier for fields with concave outlines (skipped at once on a field of strictly convex floes): a pair of
+// AddPath-valid outlines that are not both strictly convex, with overlapping boxes, is certified apart edge by edge
+// (sz_apart.cuh) -- the sweep would return nothing and the pair take the zero-force branch (floe_interactions.m:43-44,71-74).
+// 40 % of the candidate pairs of a field of the reference's own floe shapes.  A kernel of its own: inlined into the classifier it
+// raised that kernel from 73 to 122 registers for the convex field, which never uses it.
+__global__ void __launch_bounds__(128) pair_apart_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const EntryRec* __restrict__ erec,
+                                                         const double* __restrict__ vx, const double* __restrict__ vy, uint8_t* __restrict__ apart, const Counters* __restrict__ c)
+{
+    if (!c->any_concave || c->overflow) return;                 // a convex field leaves after one load per thread (fixed, small grid)
+    const int np = *np_dev < np_cap ? *np_dev : np_cap;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+    const EntryRec ri = erec[pi[p]], rj = erec[pj[p]];
+    bool ap = false;
+    const bool cvx = ri.no >= 3 && rj.no >= 3;                  // both strictly convex: the separating-axis rule of the classifier is complete for them
+    if (ri.valid && rj.valid && !cvx && ri.nv < 32767 && rj.nv < 32767 && !(ri.bb[1] < rj.bb[0] || rj.bb[1] < ri.bb[0] || ri.bb[3] < rj.bb[2] || rj.bb[3] < ri.bb[2])) {
+        const double s = 1.0 / SZ_SCALE;                        // the int64 boxes of ext_prep_kernel in metres (only a filter)
+        ap = szapart::rings_apart(vx + ri.vo, vy + ri.vo, ri.nv, ri.x, ri.y, (double)ri.bb[0] * s, (double)ri.bb[1] * s, (double)ri.bb[2] * s, (double)ri.bb[3] * s,
+                                  vx + rj.vo, vy + rj.vo, rj.nv, rj.x, rj.y, (double)rj.bb[0] * s, (double)rj.bb[1] * s, (double)rj.bb[2] * s, (double)rj.bb[3] * s);
+    }
+    apart[p] = ap;
+    }
+}
 __global__ void __launch_bounds__(256) pair_classify_kernel(int np_cap, const int* __restrict__ np_dev, const int* __restrict__ pi, const int* __restrict__ pj, const EntryRec* __restrict__ erec,
                                      const double* __restrict__ vx, const double* __restrict__ vy, int want_polys,
                                      int* __restrict__ status, int* __restrict__ nrows, double* __restrict__ ovl, int* __restrict__ poly_npaths,
-                                     int* __restrict__ bins, short* __restrict__ pkey, Counters* c, int cvx_key_mode)
+                                     int* __restrict__ bins, short* __restrict__ pkey, Counters* c, int cvx_key_mode, const uint8_t* __restrict__ apart)
 {
     // per bucket: pairs of strictly convex outlines (class C) in the high half-word, the others (class S) in the low one
     __shared__ int sh[SZ_NBINS];
@@ -624,6 +650,7 @@ __global__ void __launch_bounds__(256) pair_classify_kernel(int np_cap, const in
             f = f || sat_side_group(vx, vy, oj, nj, Xj, Yj, oi, ni, Xi, Yi, gl);
             disjoint = __any_sync(gmask, f);
         }
+        if (!disjoint && !cvx && apart != nullptr && c->any_concave) disjoint = apart[p] != 0;      // pair_apart_kernel's certificate
         int cnt = 0;
         if (!disjoint && cvx && cvx_key_mode == 1) {
             // class C sweeps one scanbeam per CTA-synchronous iteration, and only over the Y range the two outlines share:
@@ -994,7 +1021,7 @@ extern "C" void sz_destroy(SzContext* c)
     DBuf<i64>* lb[] = {&c->erec, &c->ebb, &c->pvx, &c->pvy, &c->c_soff, &c->c_coff, &c->c_sx, &c->c_sy, &c->c_cx, &c->c_cy, &c->c_pvx, &c->c_pvy, &c->ho_x, &c->ho_y};
     for (auto* b : lb) b->release();
     c->scan_state.release();
-    c->pkey.release();
+    c->pkey.release(); c->papart.release();
     { DBuf<double>* tb[] = {&c->t_mass, &c->t_inertia, &c->t_alpha, &c->t_dXi_p, &c->t_dYi_p, &c->t_dUi_p, &c->t_dVi_p, &c->t_dalpha_p, &c->t_dksi_p, &c->t_FxOA, &c->t_FyOA, &c->t_torqueOA,
                           &c->c0x, &c->c0y, &c->t_stressH, &c->t_stress};
       for (auto* b : tb) b->release(); c->t_scount.release(); c->t_flags.release(); }
@@ -1587,8 +1614,9 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         static const int key_mode = getenv("SZ_CVX_KEY") ? atoi(getenv("SZ_CVX_KEY")) : 1;   // 0: direction sectors for class C too (experiments)
         CK(c->bins.ensure(2 * SZ_NBINS)); CK(c->bin_fill.ensure(2 * SZ_NBINS));
         CK(cudaMemsetAsync(c->bins.p, 0, 2 * SZ_NBINS * sizeof(int), st)); CK(cudaMemsetAsync(c->bin_fill.p, 0, 2 * SZ_NBINS * sizeof(int), st));
+        if (c->opt_apart) { ++g_launches; pair_apart_kernel<<<std::min(nblk(n_work, 128), 148 * 16), 128, 0, st>>>(n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, (const EntryRec*)c->erec.p, c->vx.p, c->vy.p, c->papart.p, c->d_cnt); }
         pair_classify_kernel<<<nblk((i64)n_work * CLS_G, 256), 256, 0, st>>>(n_work, D_CNT(n_pairs), c->pi.p, c->pj.p, (const EntryRec*)c->erec.p, c->vx.p, c->vy.p, c->prm.want_clip_polys,
-                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->bins.p, c->pkey.p, c->d_cnt, key_mode);
+                                                            c->pstatus.p, c->pnrows.p, c->povl.p, c->poly_npaths.p, c->bins.p, c->pkey.p, c->d_cnt, key_mode, c->opt_apart ? c->papart.p : nullptr);
         bins_scan_kernel<<<2, SZ_BIN_N * SZ_BIN_N, 0, st>>>(c->d_cnt, n_work, c->bins.p, c->bin_fill.p);
         pair_scatter_kernel<<<nblk(n_work, 256), 256, 0, st>>>(n_work, D_CNT(n_pairs), c->pkey.p, c->bins.p, c->bin_fill.p, c->listC.p, c->listS.p, c->d_cnt);
         g_launches += 3;
@@ -1639,7 +1667,7 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
     int nM = wall ? c->h_cnt->wlistM : c->h_cnt->listM;
     if (dbg) fprintf(stderr, "[sz] class S -> T %d, T -> M %d\n", nT, nM);
     if (nM > 0) {
-        static const int m_tpsm = getenv("SZ_M_TPSM") ? atoi(getenv("SZ_M_TPSM")) : 512;   // persistent threads per SM of class M (160 KB of HBM scratch each)
+        static const int m_tpsm = getenv("SZ_M_TPSM") ? atoi(getenv("SZ_M_TPSM")) : 768;   // persistent threads per SM of class M (160 KB of HBM scratch each: 18 GB at most)
         const int threads = std::min((nM + 63) / 64 * 64, 148 * m_tpsm);
         CK(c->scratchM.ensure((size_t)threads * sz_workspace_bytes_M()));
         a.list = lstM; a.list_count = cntM; a.next_list = lstL; a.next_count = cntL; a.scratch = c->scratchM.p; a.n_threads = threads;
@@ -1653,7 +1681,8 @@ static int run_narrow(SzContext* c, int wall, int n_work, bool fast)
         if (dbg) { cudaEventElapsedTime(&dms, d0, d1); fprintf(stderr, "[sz] class M: %d pairs on %d threads, %.2f ms\n", nM, threads, dms); }
         int nL = wall ? c->h_cnt->wlistL : c->h_cnt->listL;
         if (nL > 0) {
-            static const int l_tpsm = getenv("SZ_L_TPSM") ? atoi(getenv("SZ_L_TPSM")) : 128;   // class L (1.1 MB of HBM scratch each: 21 GB at most; more threads in flight, fewer rounds)
+            static const int l_tpsm = getenv("SZ_L_TPSM") ? atoi(getenv("SZ_L_TPSM")) : 160;   // class L (1.1 MB of HBM scratch each: 26 GB at most; a thread sweeps one pair in ~0.3 s, so the launch lasts as many rounds as
+                                                                                                 // pairs / threads: 512 + 128 -> 768 + 160 took the 57,600-floe raw field from 745 to 605 ms per step, profiles/r02i_lm_threads.txt)
             const int threadsL = std::min((nL + 63) / 64 * 64, 148 * l_tpsm);
             CK(c->scratchL.ensure((size_t)threadsL * sz_workspace_bytes_L()));
             a.list = lstL; a.list_count = cntL; a.next_list = nullptr; a.next_count = nullptr; a.scratch = c->scratchL.p; a.n_threads = threadsL;
@@ -1816,7 +1845,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
     // per-entry preparation of the narrow phase (bounding boxes, convexity): independent of the pair list, so it is queued
     // before the host waits for the pair count
     CK(c->erec.ensure(8 * (size_t)n + 8)); CK(c->ebb.ensure(4 * (size_t)n + 4)); CK(c->evalid.ensure(n + 1)); CK(c->econvex.ensure(n + 1)); CK(c->erot.ensure(n + 1)); CK(c->eno.ensure(n + 1)); CK(c->env.ensure(n + 1));
-    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p, (EntryRec*)c->erec.p); }
+    if (n > 0) { ++g_launches; ext_prep_kernel<<<nblk(n, 128), 128, 0, st>>>(n, c->ex.p, c->ey.p, c->esrc.p, c->voff.p, c->vx.p, c->vy.p, c->ebb.p, c->evalid.p, c->env.p, c->econvex.p, c->erot.p, c->eno.p, (EntryRec*)c->erec.p, c->d_cnt); }
     CK(cudaGetLastError());
     int np;
     if (fast) np = c->plan_npcap;
@@ -1829,7 +1858,7 @@ static int step_impl(SzContext* c, SzSummary* out, int mode)
     CKS(dbg_sync(c, "ext_prep + broad fill"));
     if (!enq) CK(cudaEventRecord(c->evp[1], st));
     nvtx.next("sz K2+K3 narrow phase and force law");
-    CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1));
+    CK(c->listC.ensure(np + 1)); CK(c->listS.ensure(np + 1)); CK(c->pkey.ensure(np + 1)); CK(c->papart.ensure(np + 1));
     // ---- K2 + K3: narrow phase (pool capacities are guesses; exact needs come back in the counters)
     const bool wall = c->have_bnd && !P.periodic;
     if (wall) { CK(c->wstatus.ensure(n + 1)); CK(c->wnrows.ensure(n + 1)); CK(c->wrow_start.ensure(n + 1)); CK(c->wovl.ensure(n + 1)); CK(c->wlistT.ensure(n + 1)); CK(c->wlistM.ensure(n + 1)); CK(c->wlistL.ensure(n + 1)); }
@@ -2545,6 +2574,7 @@ extern "C" int sz_set_option(SzContext* c, const char* name, int32_t value)
     if (!c || !name) { sz_set_error("sz_set_option: NULL argument"); return SZ_ERR_ARG; }
     if (strcmp(name, "convex_fast") == 0) { c->opt_convex_fast = value != 0; return SZ_OK; }
     if (strcmp(name, "convex_split") == 0) { c->opt_convex_split = value != 0; return SZ_OK; }
+    if (strcmp(name, "apart") == 0) { c->opt_apart = value != 0; return SZ_OK; }
     if (strcmp(name, "graph_safe") == 0) { c->opt_graph_safe = value != 0; return SZ_OK; }
     if (strcmp(name, "speculate") == 0) { c->opt_speculate = value != 0; c->plan_valid = false; return SZ_OK; }
     if (strcmp(name, "euler_cell_warp") == 0) { c->opt_euler_cell_warp = value != 0; return SZ_OK; }
@@ -2556,6 +2586,7 @@ extern "C" int sz_get_stat(SzContext* c, const char* name, int64_t* value)
     if (!c || !name || !value) { sz_set_error("sz_get_stat: NULL argument"); return SZ_ERR_ARG; }
     if (strcmp(name, "speculated_steps") == 0) { *value = c->n_fast_steps; return SZ_OK; }
     if (strcmp(name, "repeated_steps") == 0) { *value = c->n_slow_steps; return SZ_OK; }
+    if (strcmp(name, "classifier_answered") == 0) { *value = c->h_cnt ? c->h_cnt->n_bbox_reject : 0; return SZ_OK; }     // pairs of the last step that needed no sweep (boxes, separating axis, edge-by-edge certificate)
     sz_set_error("sz_get_stat: unknown statistic '%s'", name);
     return SZ_ERR_ARG;
 }

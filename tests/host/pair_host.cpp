@@ -197,3 +197,15 @@ extern "C" int szport_calc_eulerian_data(const SzFloesSoA* f, const double* mass
     for (size_t c = 0; c < cells; ++c) szeul::cell_reduce(a, (int)c);
     return 0;
 }
+
+// the classifier's certificate for outlines of any shape (sz_apart.cuh); bounding boxes computed here like ext_prep_kernel's
+#include "../../subzero_b200/csrc/sz_apart.cuh"
+extern "C" int szport_rings_apart(const double* ax, const double* ay, int na, double AX, double AY, const double* bx, const double* by, int nb, double BX, double BY)
+{
+    auto box = [](const double* x, const double* y, int n, double X, double Y, double* o) {
+        o[0] = o[2] = 1e300; o[1] = o[3] = -1e300;
+        for (int i = 0; i < n; ++i) { const double u = x[i] + X, v = y[i] + Y; o[0] = u < o[0] ? u : o[0]; o[1] = u > o[1] ? u : o[1]; o[2] = v < o[2] ? v : o[2]; o[3] = v > o[3] ? v : o[3]; }
+    };
+    double A[4], B[4]; box(ax, ay, na, AX, AY, A); box(bx, by, nb, BX, BY, B);
+    return szapart::rings_apart(ax, ay, na, AX, AY, A[0], A[1], A[2], A[3], bx, by, nb, BX, BY, B[0], B[1], B[2], B[3]) ? 1 : 0;
+}

@@ -141,6 +141,34 @@ def test_non_periodic_with_walls(ctx):
     assert ref.floe_outputs()["alive"].sum() < soa.n
 
 
+@pytest.mark.parametrize("max_vertices", [None, 30])
+def test_apart_certificate_saves_sweeps_and_changes_no_output(ctx, max_vertices):
+    """the classifier's edge-by-edge certificate for concave outlines (sz_apart.cuh, option "apart"): with it the step equals the
+    oracle like any other, and equals the step without it bit for bit -- pair states, Clipper polygons, rows, per-floe outputs --
+    while a good part of the candidate pairs is answered without a sweep"""
+    prm, Floe = scenarios.real_shape_field(10, seed=6, max_vertices=max_vertices)
+    soa = sz.floes_to_soa(Floe)
+    prm.want_clip_polys = 1
+    res = {}
+    for on in (0, 1):
+        ctx.set_option("apart", on)
+        s = ctx.step(prm, soa, allow_pair_errors=True)
+        off, rows = ctx.rows()
+        res[on] = (ctx.floe_outputs(), off.copy(), rows.copy(), ctx.pairs(), ctx.clip_polys(), ctx.stat("classifier_answered"), s.n_pairs)
+    o0, off0, rows0, p0, c0, a0, np0 = res[0]
+    o1, off1, rows1, p1, c1, a1, np1 = res[1]
+    assert np0 == np1 and a1 >= a0 + 0.2 * np1, (a0, a1, np1)           # the certificate answers a fifth of all pairs at least
+    assert np.array_equal(off0, off1) and np.array_equal(rows0, rows1)
+    for k in o0:
+        assert np.array_equal(o0[k], o1[k], equal_nan=True), k
+    for k in p0:
+        assert np.array_equal(p0[k], p1[k], equal_nan=True), k
+    for a, b in zip(c0, c1):
+        assert np.array_equal(a, b)
+    rep, ref = run_both(ctx, prm, soa)                                   # option on (the default): against the oracle
+    assert rep["pairs"] == np1
+
+
 def test_real_concave_shapes_periodic(ctx):
     """tiled FloeShapes.mat polygons (7..591 vertices): size classes M and L, multi-region contacts, merges"""
     prm, Floe = scenarios.real_shape_field(12, seed=1)
