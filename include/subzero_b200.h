@@ -369,10 +369,17 @@ int sz_set_stream(SzContext* ctx, void* cuda_stream);
  *                  the device and repeated with measured sizes.  0: measure every size as it is needed (four counter reads).
  *                  Results are identical either way (tests/test_gpu_parity.py).
  *   "graph_safe"    0 (default); 1: see sz_step_enqueue.
+ *   "apart"         1 (default): before the narrow phase, a pair of outlines of any shape (concave, any length) whose edges are
+ *                  all more than 1 mm apart and neither of which holds the other's first vertex is answered without a sweep --
+ *                  the reference's clip would return nothing and the pair take the zero-force branch
+ *                  (collisions/floe_interactions.m:43-44,71-74); csrc/sz_apart.cuh.  0: only bounding boxes (and the
+ *                  separating-axis rule for convex pairs) answer pairs.  Results are bit-identical either way
+ *                  (tests/test_gpu_parity.py, tests/test_apart.py).
  * Returns SZ_ERR_ARG for an unknown name. */
 int sz_set_option(SzContext* ctx, const char* name, int32_t value);
 /* counters of the context: "speculated_steps" (steps that ran on carried-over sizes), "repeated_steps" (steps that had to be
- * repeated because a carried-over size was too small) */
+ * repeated because a carried-over size was too small), "classifier_answered" (candidate pairs of the last step that needed no
+ * sweep: disjoint boxes, a separating axis, or the "apart" certificate) */
 int sz_get_stat(SzContext* ctx, const char* name, int64_t* value);
 
 /* ---- stand-alone polygon clip with the gateway's semantics (private/mexclipper.cpp:204-305):
